@@ -1,0 +1,258 @@
+/* rau.h -- C ABI of librau.so: the B200 (sm_100a) implementation of the RAU_VQA
+ * recurrent-answering-unit training/inference hot path.
+ *
+ * This header is the whole boundary.  It is plain C (no C++ types, no callbacks, no torch
+ * types) so that the same text can be handed to LuaJIT `ffi.cdef` (the reference's host
+ * language, see lua/ and INTEGRATION.md) and to Python cffi (tests/, bench.py).
+ *
+ * Reference interfaces replaced (paths relative to the reference repo root):
+ *   F:  experiments/Ours_Full/LstmAttCtrlGradNoiseDontSelect.lua
+ *   A:  model/ATTLSTM.lua        D:  model/DeepLSTM.lua
+ *   OU: utils/optim_updates.lua  MU: utils/model_utils.lua
+ *
+ * Conventions
+ *   - every tensor is a caller-owned DEVICE pointer, float32, row-major, batch-first,
+ *     contiguous unless a leading dimension `ld*` is given; the library never frees or
+ *     retains caller pointers past the call (nn.Module clones re-point storages, F:322-347);
+ *   - token ids / labels are 1-based and delivered as float, like the reference (F:454-455);
+ *   - all calls enqueue on the ctx stream and return immediately; scalars are written to
+ *     device memory and are valid after rau_sync();
+ *   - return 0 on success, a negative rau_status otherwise; text via rau_last_error();
+ *   - there is NO CPU fallback: host pointers or a non-sm_100 device are errors.
+ */
+#ifndef RAU_H
+#define RAU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rau_ctx rau_ctx;
+
+typedef enum {
+  RAU_OK = 0,
+  RAU_EINVAL = -1,   /* bad shape / null / misaligned / host pointer */
+  RAU_ECUDA = -2,    /* CUDA runtime or driver error */
+  RAU_ENCCL = -3,    /* NCCL error or libnccl not loadable */
+  RAU_EARCH = -4,    /* device is not sm_100 (B200) */
+  RAU_ENOMEM = -5,
+  RAU_ESTATE = -6    /* call sequence error (e.g. bwd without fwd) */
+} rau_status;
+
+/* gate chunk order of the 4H pre-activation vector */
+typedef enum {
+  RAU_GATES_IFOG = 0,  /* model/DeepLSTM.lua:47-54  [in|forget|out|transform] */
+  RAU_GATES_IGFO = 1   /* model/ATTLSTM.lua:12-19   [in|transform|forget|out] */
+} rau_gate_order;
+
+/* arithmetic mode of the dense contractions (pointwise math, cell state, softmax, losses and all
+ * weight-gradient accumulators are float32 in every mode) */
+typedef enum {
+  RAU_PREC_F32 = 0,     /* fp32 operands, CUDA-core FMA: the exact mode */
+  RAU_PREC_BF16 = 1,    /* bf16 operands, tcgen05 MMA, fp32 accumulate in TMEM: the fast mode */
+  RAU_PREC_BF16X3 = 2   /* bf16 hi/lo split operands (3 MMA passes), ~fp32 accuracy on tcgen05 */
+} rau_precision;
+
+typedef enum {
+  RAU_OPT_SGD = 0,      /* OU:7-9   */
+  RAU_OPT_SGDM = 1,     /* OU:11-19 */
+  RAU_OPT_SGDMOM = 2,   /* OU:21-31 */
+  RAU_OPT_ADAGRAD = 3,  /* OU:33-43 */
+  RAU_OPT_RMSPROP = 4,  /* OU:46-57 */
+  RAU_OPT_ADAM = 5      /* OU:59-87 */
+} rau_optim;
+
+/* The constants the experiment scripts hard-code (F:202-229) plus run-time sizes. */
+typedef struct {
+  int V;        /* vocab_size                 F:204 */
+  int embed;    /* embed_dim = 200            F:202 */
+  int Hq;       /* rnn_size = 512             F:208 */
+  int nlayer;   /* nrnn_layer = 2             F:209 (only 2 is supported by the fused encoder) */
+  int C;        /* cnnout_dim 512 / 2048      F:216, RN:217 */
+  int S;        /* cnnout_w*cnnout_h = 196    F:219 */
+  int M;        /* multfeat_dim = 512         F:220 */
+  int A;        /* attfeat_dim = 256          F:221 */
+  int H;        /* att_rnn_size = 512         F:225 */
+  int N;        /* netout_dim = answer_size   F:222 */
+  int nHop;     /* -nhop                      F:53  */
+  int T;        /* seq_len (<= 26)            LD:1418 */
+  float p_embed, p_rnn, p_q, p_x, p_m;   /* dropout rates F:205, F:210, F:233, F:239, F:277 */
+} rau_config;
+
+/* ------------------------------------------------------------------ context ------------- */
+int rau_version(void);
+const char* rau_last_error(void);                      /* thread-local message of the last failure */
+int rau_ctx_create(rau_ctx** out, int device, void* cuda_stream /* cudaStream_t or NULL */);
+int rau_ctx_destroy(rau_ctx* ctx);
+int rau_set_stream(rau_ctx* ctx, void* cuda_stream);
+int rau_set_seed(rau_ctx* ctx, uint64_t seed);         /* Philox key for dropout masks and gradient noise */
+int rau_set_precision(rau_ctx* ctx, int precision);    /* rau_precision */
+int rau_get_precision(rau_ctx* ctx);
+int rau_sync(rau_ctx* ctx);
+/* number of kernels this library launched on ctx since creation (bench.py's gpu_launches) */
+int64_t rau_launch_count(rau_ctx* ctx);
+
+/* flat parameter layout (our own; nngraph's order is not recoverable):
+ *   group 0 "embed": E[V,embed]
+ *   group 1 "rnn"  : per layer L: Wi[4Hq,in] bi[4Hq] Wh[4Hq,Hq] bh[4Hq]
+ *   group 2 "mult" : Wq bq Wh bh Wi bi Wqa bqa Wa ba ws bs Wm bm Wp bp Wx bx Whh bhh Wo bo Ws bso wd bd */
+int64_t rau_group_size(const rau_config* cfg, int group);
+/* offset (in floats) of a named tensor inside its group, -1 if unknown; e.g. ("mult","Wi") */
+int64_t rau_param_offset(const rau_config* cfg, int group, const char* name);
+
+/* ------------------------------------------------------------------ a1/a2: LSTM cell ----- */
+/* One LSTM layer step: G = x Wi^T + bi + h_prev Wh^T + bh; gates per `gate_order`;
+ * c = f*c_prev + i*g; h = o*tanh(c).  Replaces the nngraph built by lstm() A:4-28 and by the
+ * loop body D:33-65.  ld* are row pitches in floats (DeepLSTM keeps c/h as Narrow views of a
+ * [B, 2*Hq*nlayer] state, D:23-24).  `saved` receives 5*B*H floats (i,f,o,g,tanh(c)). */
+typedef struct {
+  int B, in_size, H, gate_order;
+  int ldx, ldc_prev, ldh_prev, ldc, ldh;
+} rau_lstm_desc;
+size_t rau_lstm_saved_bytes(const rau_lstm_desc* d);
+int rau_lstm_cell_fwd(rau_ctx* ctx, const rau_lstm_desc* d,
+                      const float* x, const float* c_prev, const float* h_prev,
+                      const float* Wi, const float* bi, const float* Wh, const float* bh,
+                      float* c, float* h, float* saved);
+/* updateGradInput + accGradParameters(scale) in one call.  dc/dh are the gradOutput pair (either may
+ * be NULL = zeros); dh_extra (NULL or contiguous [B,H]) is added to dh: in a stack, next_h feeds both the
+ * module output and the layer above (D:39, A:52).  dx/dc_prev/dh_prev are the gradInput triple
+ * (overwritten); gW* accumulate (+= scale * ...), any of them may be NULL to skip. */
+int rau_lstm_cell_bwd(rau_ctx* ctx, const rau_lstm_desc* d,
+                      const float* x, const float* c_prev, const float* h_prev,
+                      const float* Wi, const float* Wh, const float* saved,
+                      const float* dc, const float* dh, int lddc, int lddh, const float* dh_extra,
+                      float* dx, float* dc_prev, float* dh_prev, int lddx, int lddc_prev, int lddh_prev,
+                      float* gWi, float* gbi, float* gWh, float* gbh, float scale);
+
+/* ------------------------------------------------------------------ a3: word embedding --- */
+/* tanh(dropout(E[x])) for n = rows ids (F:203-206). mask: optional 0/1 keep bytes [n,embed]
+ * (parity tests); NULL + train!=0 draws Philox masks with `stream_id`; train==0 is evaluate(). */
+int rau_embed_fwd(rau_ctx* ctx, const rau_config* cfg, int n, const float* ids, const float* E,
+                  int train, const uint8_t* mask, uint64_t stream_id, float* out);
+int rau_embed_bwd(rau_ctx* ctx, const rau_config* cfg, int n, const float* ids, const float* out,
+                  int train, const uint8_t* mask, uint64_t stream_id, const float* dout, float* gE);
+
+/* nn.Dropout (v2) on n floats: y = x * keep / (1-p) in training, y = x in evaluate() (A:52, D:39, F:205).
+ * The backward pass of Dropout is the same call on the gradient with the same mask / stream_id. */
+int rau_dropout(rau_ctx* ctx, int64_t n, const float* x, float p, int train, const uint8_t* mask,
+                uint64_t stream_id, float* y);
+
+/* ------------------------------------------------------------------ fused step ----------- */
+/* Optional explicit dropout masks (0/1 keep bytes) for parity runs; any NULL member = Philox. */
+typedef struct {
+  const uint8_t* embed;   /* [T,B,embed] */
+  const uint8_t* rnn;     /* [T,B,Hq]    (input of encoder layer 2, D:39) */
+  const uint8_t* q;       /* [nHop,B,Q]  Q = 2*Hq*nlayer */
+  const uint8_t* x;       /* [nHop,B,C,S] */
+  const uint8_t* m;       /* [nHop,B,M]  */
+} rau_masks;
+
+typedef struct {
+  int B;                    /* local batch */
+  int B_global;             /* loss/gradient normaliser (= B on one GPU; world*B under data parallel) */
+  const float* feats;       /* [B,C,14,14]   F:451-453 */
+  const float* tokens;      /* [T,B] 1-based, pad = 1 */
+  const float* lengths;     /* [B]   question lengths */
+  int max_len;              /* host-known x_len:max() (F:460); 0 = run all T steps (same result) */
+  const float* labels;      /* [B]   1-based answers */
+} rau_batch;
+
+typedef struct {
+  float* loss;          /* [nHop+2]  tab_loss (F:535, F:548, F:557); local-batch sums / B_global */
+  float* loss_do_pred;  /* [nHop]    tab_loss_do_pred (F:572) */
+  float* answers;       /* [nHop+2,B] argmax per hop, uni, select (1-based), may be NULL */
+  float* scores;        /* [nHop,B,N] may be NULL */
+  float* attprob;       /* [nHop,B,S] may be NULL */
+  float* do_pred;       /* [nHop,B]   may be NULL */
+  float* norms;         /* [3] pre-clip L2 norms of embed/rnn/mult grads (F:627-648), may be NULL */
+} rau_step_out;
+
+/* feval forward+backward (F:445-615): zeroes the three flat grads, runs the encoder unroll, the nHop
+ * answering units, the joint loss and BPTT.  hop_mask[h] (HOST array of nHop floats 0/1, may be NULL =
+ * all 1) is tab_multhop_compute_loss (F:587-589).  Gradients are left in grads[3] BEFORE noise/clip so that a
+ * data-parallel caller can all-reduce them. */
+int rau_feval(rau_ctx* ctx, const rau_config* cfg, const rau_batch* batch,
+              float* const params[3], float* const grads[3],
+              const float* hop_mask, const rau_masks* masks, int64_t step_t, const rau_step_out* out);
+
+/* gradient noise + per-group clip (F:617-648): g += N(0, sqrt(eta/((step_t+1)*gamma))) (noise_override
+ * [3] optional explicit noise tensors; eta<=0 disables), then g *= clip/||g|| when ||g|| > clip.
+ * norms (device [3]) may be NULL. */
+int rau_noise_clip(rau_ctx* ctx, const rau_config* cfg, float* const grads[3], int64_t step_t,
+                   float eta, float gamma, float clip, const float* const noise_override[3], float* norms);
+
+/* utils/optim_updates.lua on one flat vector, in place.  state0/state1 are caller-owned device
+ * vectors of n floats (adam: m,v; rmsprop/adagrad/sgdmom: m; sgdm: v); t is the 1-based step count
+ * AFTER increment (adam bias correction, OU:80-83).  h0..h2: sgd -; sgdm alpha; sgdmom alpha;
+ * adagrad eps; rmsprop alpha,eps; adam beta1,beta2,eps. */
+int rau_optim_step(rau_ctx* ctx, int optim, int64_t n, float* x, const float* dx, float lr,
+                   float h0, float h1, float h2, float* state0, float* state1, int64_t t);
+
+/* One whole training iteration = rau_feval -> [all-reduce when a communicator is attached] ->
+ * rau_noise_clip -> rau_optim_step x3 (F:786-791).  opt_state[g][0..1] as in rau_optim_step. */
+typedef struct {
+  int optim;                 /* rau_optim */
+  float lr[3];               /* learningrate, learningrate, multlearningrate (F:788-790) */
+  float h0, h1, h2;          /* optimizer hyper-parameters (see rau_optim_step) */
+  float eta, gamma, clip;    /* F:54-55, F:49 */
+  const float* const* noise_override; /* NULL or [3] */
+} rau_train_hparams;
+int rau_train_step(rau_ctx* ctx, const rau_config* cfg, const rau_batch* batch,
+                   float* const params[3], float* const grads[3], float* const opt_state[3][2],
+                   const float* hop_mask, const rau_masks* masks, int64_t step_t,
+                   const rau_train_hparams* hp, const rau_step_out* out);
+
+/* predict_result (F:652-724): evaluate()-mode forward; pred[nHop+2,B,N] and att[nHop+2,B,S]
+ * (hops, uni = mean over hops, select = first hop with do_pred>0.5, forced at the last hop). */
+int rau_predict(rau_ctx* ctx, const rau_config* cfg, const rau_batch* batch,
+                float* const params[3], float* pred, float* att);
+
+/* ------------------------------------------------------------------ module-level hop ----- */
+/* protos.multimodal forward (F:292-307) for one hop: {q,X,c,h} -> {score,do_pred,p,c',h'}.
+ * `saved` is a caller-owned buffer of rau_hop_saved_bytes() (each Lua clone owns its own). */
+size_t rau_hop_saved_bytes(const rau_config* cfg, int B);
+int rau_hop_fwd(rau_ctx* ctx, const rau_config* cfg, int B, const float* mult_params,
+                const float* q, const float* X, const float* c, const float* h,
+                int train, const uint8_t* mask_q, const uint8_t* mask_x, const uint8_t* mask_m,
+                uint64_t stream_id,
+                float* score, float* do_pred, float* p, float* c_out, float* h_out, void* saved);
+/* multimodals[h]:backward (F:590-593): gradOutput {dscore, ddo_pred, dp, dc', dh'} (any NULL = 0),
+ * gradInput {dq, dX (NULL to skip: the caller discards it, F:598), dc, dh}; mult grads accumulate. */
+int rau_hop_bwd(rau_ctx* ctx, const rau_config* cfg, int B, const float* mult_params, float* mult_grads,
+                const float* q, const float* X, const float* c, const float* h, int train, const void* saved,
+                const float* dscore, const float* ddo_pred, const float* dp, const float* dc_out, const float* dh_out,
+                float* dq, float* dX, float* dc, float* dh);
+
+/* ------------------------------------------------------------------ multi-GPU - */
+/* One process per GPU.  rank 0 calls rau_comm_unique_id, ships the 128 bytes to the other ranks,
+ * every rank calls rau_comm_init.  rau_allreduce_grads sums the three flat grads across ranks. */
+int rau_comm_unique_id(uint8_t id_out[128]);
+int rau_comm_init(rau_ctx* ctx, const uint8_t id[128], int rank, int world);
+int rau_comm_destroy(rau_ctx* ctx);
+int rau_allreduce_grads(rau_ctx* ctx, float* const grads[3], const int64_t sizes[3]);
+int rau_allreduce(rau_ctx* ctx, float* buf, int64_t n);
+
+/* ------------------------------------------------------------------ building blocks ------ */
+/* Exposed for unit parity tests and the kernel sweep in bench.py. */
+/* C[M,N] (+)= A[M,K] B[N,K]^T on the ctx precision mode's engine; ta/tb: 0 = operand stored
+ * [rows,K] (K-major), 1 = stored [K,rows].  accumulate != 0 adds into C. */
+int rau_gemm(rau_ctx* ctx, int M, int N, int K, const float* A, int lda, int ta,
+             const float* B, int ldb, int tb, float* C, int ldc, int accumulate);
+/* softmax cross-entropy of score[B,N] against 1-based labels: loss_sum += scale*sum_b nll_b,
+ * dscore = scale*(softmax - onehot), answers = argmax (1-based, ties -> lowest index). */
+int rau_softmax_ce(rau_ctx* ctx, int B, int N, const float* score, const float* labels, float scale,
+                   float* loss_sum, float* dscore, float* answers);
+/* kernel-only timing hook used by bench.py for the roofline line: runs the attention-hop projection
+ * kernel (I = tanh(Wi drop(X) + bi)) `iters` times on the ctx stream between two events and returns the
+ * average milliseconds per launch. */
+int rau_time_iembed(rau_ctx* ctx, const rau_config* cfg, int B, const float* mult_params,
+                    const float* X, int iters, float* ms_per_launch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAU_H */

@@ -1,0 +1,395 @@
+// k_pointwise.cu -- HBM-bound elementwise / gather / reduction kernels of the RAU path.  Each replaces a
+// chain of tiny cunn kernels of the reference: Dropout+Tanh+LookupTable, the ~12 pointwise
+// nodes of an LSTM cell, Narrow/CAddTable glue, and the per-row host copy loops of F:472-478 / F:604-610.
+#include "rau_kernels.cuh"
+
+namespace {
+constexpr int TPB = 256;
+inline int grid_for(int64_t n, int per_thread = 1) {
+  int64_t b = (n + (int64_t)TPB * per_thread - 1) / ((int64_t)TPB * per_thread);
+  if (b < 1) b = 1;
+  if (b > 148 * 32) b = 148 * 32;
+  return (int)b;
+}
+
+// ---------------------------------------------------------------- masks
+__global__ void mask_gen_kernel(uint32_t* __restrict__ bits, int64_t nwords, int64_t n, uint32_t thresh,
+                                int keep_all, uint2 key, uint32_t stream_lo, uint32_t stream_hi) {
+  for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < nwords; w += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t word = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {  // 8 Philox calls x 4 lanes = 32 keep bits
+      uint4 r = philox4x32(make_uint4((uint32_t)(w * 8 + q), (uint32_t)((w * 8 + q) >> 32), stream_lo, stream_hi), key);
+      word |= (uint32_t)(r.x < thresh) << (q * 4 + 0);
+      word |= (uint32_t)(r.y < thresh) << (q * 4 + 1);
+      word |= (uint32_t)(r.z < thresh) << (q * 4 + 2);
+      word |= (uint32_t)(r.w < thresh) << (q * 4 + 3);
+    }
+    if (keep_all) word = 0xffffffffu;
+    bits[w] = word;
+  }
+}
+
+__global__ void mask_pack_kernel(uint32_t* __restrict__ bits, const uint8_t* __restrict__ bytes, int64_t nwords, int64_t n) {
+  for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < nwords; w += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t word = 0;
+    for (int k = 0; k < 32; ++k) {
+      int64_t i = w * 32 + k;
+      if (i < n && bytes[i]) word |= 1u << k;
+    }
+    bits[w] = word;
+  }
+}
+
+// ---------------------------------------------------------------- embedding
+__global__ void embed_fwd_kernel(const float* __restrict__ ids, int n, int D, int V, const float* __restrict__ E,
+                                 const uint32_t* __restrict__ bits, float scale, float* __restrict__ out_f,
+                                 bf16* __restrict__ out_b, int ldb) {
+  const int64_t total = (int64_t)n * D;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / D), d = (int)(i % D);
+    int id = (int)ids[r] - 1;
+    id = min(max(id, 0), V - 1);
+    const float v = tanhf(E[(int64_t)id * D + d] * keep_scale(bits, i, scale));
+    if (out_f) out_f[i] = v;
+    if (out_b) out_b[(int64_t)r * ldb + d] = __float2bfloat16(v);
+  }
+}
+
+__global__ void embed_bwd_kernel(const float* __restrict__ ids, int n, int D, int V, const float* __restrict__ out,
+                                 const uint32_t* __restrict__ bits, float scale, const float* __restrict__ dout, int lddout,
+                                 float* __restrict__ gE) {
+  const int64_t total = (int64_t)n * D;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / D), d = (int)(i % D);
+    int id = (int)ids[r] - 1;
+    id = min(max(id, 0), V - 1);
+    const float e = out[i];
+    const float g = dout[(int64_t)r * lddout + d] * (1.0f - e * e) * keep_scale(bits, i, scale);
+    if (g != 0.0f) atomicAdd(&gE[(int64_t)id * D + d], g);
+  }
+}
+
+// ---------------------------------------------------------------- LSTM pointwise
+// chunk index of gates (i,f,o,g) inside the 4H pre-activation vector
+__device__ __forceinline__ void gate_chunks(int order, int& ci, int& cf, int& co, int& cg) {
+  if (order == RAU_GATES_IFOG) { ci = 0; cf = 1; co = 2; cg = 3; }
+  else { ci = 0; cg = 1; cf = 2; co = 3; }
+}
+
+__global__ void lstm_fwd_kernel(int B, int H, int order, const float* __restrict__ G, int ldg,
+                                const float* __restrict__ c_prev, int ldcp, float* __restrict__ c, int ldc,
+                                float* __restrict__ h, int ldh, bf16* __restrict__ h_b, int ldhb, float* __restrict__ saved) {
+  int ci, cf, co, cg;
+  gate_chunks(order, ci, cf, co, cg);
+  const int64_t total = (int64_t)B * H, plane = total;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / H), j = (int)(idx % H);
+    const float* g = G + (int64_t)b * ldg;
+    const float i_ = sigmoidf_(g[ci * H + j]);
+    const float f_ = sigmoidf_(g[cf * H + j]);
+    const float o_ = sigmoidf_(g[co * H + j]);
+    const float g_ = tanhf(g[cg * H + j]);
+    const float cp = c_prev ? c_prev[(int64_t)b * ldcp + j] : 0.0f;
+    const float cn = f_ * cp + i_ * g_;
+    const float tc = tanhf(cn);
+    const float hn = o_ * tc;
+    c[(int64_t)b * ldc + j] = cn;
+    h[(int64_t)b * ldh + j] = hn;
+    if (h_b) h_b[(int64_t)b * ldhb + j] = __float2bfloat16(hn);
+    if (saved) {
+      saved[idx] = i_; saved[plane + idx] = f_; saved[2 * plane + idx] = o_;
+      saved[3 * plane + idx] = g_; saved[4 * plane + idx] = tc;
+    }
+  }
+}
+
+__global__ void lstm_bwd_kernel(int B, int H, int order, const float* __restrict__ dc_out, int lddc,
+                                const float* __restrict__ dh_out, int lddh, const float* __restrict__ dh_extra, int ldhe,
+                                const float* __restrict__ lengths, int t, const float* __restrict__ dq_c,
+                                const float* __restrict__ dq_h, int lddq,
+                                const float* __restrict__ c_prev, int ldcp, const float* __restrict__ saved,
+                                float* __restrict__ dG, bf16* __restrict__ dG_b, float* __restrict__ dc_prev, int lddcp) {
+  int ci, cf, co, cg;
+  gate_chunks(order, ci, cf, co, cg);
+  const int64_t total = (int64_t)B * H, plane = total;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / H), j = (int)(idx % H);
+    float dc_o = dc_out ? dc_out[(int64_t)b * lddc + j] : 0.0f;
+    float dh_o = dh_out ? dh_out[(int64_t)b * lddh + j] : 0.0f;
+    if (lengths != nullptr && (int)lengths[b] == t) {   // drnn_out[k] = d_feats[1][k]  (F:604-610)
+      dc_o = dq_c[(int64_t)b * lddq + j];
+      dh_o = dq_h[(int64_t)b * lddq + j];
+    }
+    if (dh_extra) dh_o += dh_extra[(int64_t)b * ldhe + j];
+    const float i_ = saved[idx], f_ = saved[plane + idx], o_ = saved[2 * plane + idx];
+    const float g_ = saved[3 * plane + idx], tc = saved[4 * plane + idx];
+    const float cp = c_prev ? c_prev[(int64_t)b * ldcp + j] : 0.0f;
+    const float d_o = dh_o * tc;
+    const float dc = dc_o + dh_o * o_ * (1.0f - tc * tc);
+    const float d_f = dc * cp, d_i = dc * g_, d_g = dc * i_;
+    if (dc_prev) dc_prev[(int64_t)b * lddcp + j] = dc * f_;
+    const float gi = d_i * i_ * (1.0f - i_), gf = d_f * f_ * (1.0f - f_);
+    const float go = d_o * o_ * (1.0f - o_), gg = d_g * (1.0f - g_ * g_);
+    const int64_t row = (int64_t)b * 4 * H;
+    if (dG) {
+      dG[row + ci * H + j] = gi; dG[row + cf * H + j] = gf; dG[row + co * H + j] = go; dG[row + cg * H + j] = gg;
+    }
+    if (dG_b) {
+      dG_b[row + ci * H + j] = __float2bfloat16(gi); dG_b[row + cf * H + j] = __float2bfloat16(gf);
+      dG_b[row + co * H + j] = __float2bfloat16(go); dG_b[row + cg * H + j] = __float2bfloat16(gg);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- elementwise
+__global__ void dropout_kernel(const float* __restrict__ x, int64_t rows, int cols, int ldx,
+                               const uint32_t* __restrict__ bits, float scale,
+                               float* __restrict__ y_f, int ldyf, bf16* __restrict__ y_b, int ldyb, int cols_pad) {
+  const int64_t total = rows * cols_pad;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols_pad;
+    const int c = (int)(i % cols_pad);
+    float v = 0.0f;
+    if (c < cols) v = x[r * ldx + c] * keep_scale(bits, r * cols + c, scale);
+    if (y_f) y_f[r * ldyf + c] = v;
+    if (y_b) y_b[r * ldyb + c] = __float2bfloat16(v);
+  }
+}
+
+__global__ void dropout_bwd_acc_kernel(const float* __restrict__ dx, int64_t n, const uint32_t* __restrict__ bits,
+                                       float scale, float* __restrict__ y, int accumulate) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = dx[i] * keep_scale(bits, i, scale);
+    y[i] = accumulate ? y[i] + v : v;
+  }
+}
+
+__global__ void tanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int64_t n,
+                                float* __restrict__ dx_f, bf16* __restrict__ dx_b) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = dy[i] * (1.0f - y[i] * y[i]);
+    if (dx_f) dx_f[i] = v;
+    if (dx_b) dx_b[i] = __float2bfloat16(v);
+  }
+}
+
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, float* __restrict__ y) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = a[i] + b[i];
+}
+__global__ void axpy_kernel(float alpha, const float* __restrict__ x, int64_t n, float* __restrict__ y) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] += alpha * x[i];
+}
+__global__ void fill_kernel(float* __restrict__ x, int64_t n, float v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] = v;
+}
+__global__ void to_bf16_kernel(const float* __restrict__ x, int64_t rows, int cols, int ldx, bf16* __restrict__ y, int ldy, int cols_pad) {
+  const int64_t total = rows * cols_pad;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols_pad;
+    const int c = (int)(i % cols_pad);
+    y[r * ldy + c] = __float2bfloat16(c < cols ? x[r * ldx + c] : 0.0f);
+  }
+}
+
+// y[b] = sigmoid(x[b,:] . w + bias)   -- the do_pred head, F:281 (Linear(M,1) -> Sigmoid -> Sum(2))
+__global__ void rowdot_sigmoid_kernel(const float* __restrict__ x, int B, int K, const float* __restrict__ w,
+                                      const float* __restrict__ bias, float* __restrict__ y) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  float s = 0.0f;
+  for (int k = lane; k < K; k += 32) s += x[(int64_t)warp * K + k] * w[k];
+  s = warp_sum(s);
+  if (lane == 0) y[warp] = 1.0f / (1.0f + expf(-(s + bias[0])));
+}
+
+__global__ void dopred_bwd_kernel(const float* __restrict__ ddo, const float* __restrict__ dop, const float* __restrict__ m,
+                                  const float* __restrict__ wd, int B, int K, float* __restrict__ dm_acc,
+                                  float* __restrict__ gwd, float* __restrict__ gbd) {
+  // one block per feature chunk; loops over the batch (tiny: only used when a caller passes a do_pred gradient)
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  float gw = 0.0f, gb = 0.0f;
+  for (int b = 0; b < B; ++b) {
+    const float dl = ddo[b] * dop[b] * (1.0f - dop[b]);
+    if (k < K) {
+      dm_acc[(int64_t)b * K + k] += dl * wd[k];
+      gw += dl * m[(int64_t)b * K + k];
+    }
+    gb += dl;
+  }
+  if (k < K) gwd[k] += gw;
+  if (k == 0) gbd[0] += gb;
+}
+
+// ---------------------------------------------------------------- reductions
+// out[c] (+)= sum_r x[r, c]; block = 32 columns x 8 row-lanes
+__global__ void colsum_kernel(const float* __restrict__ x, int64_t rows, int cols, int ld, float* __restrict__ out, int accumulate) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.0f;
+  if (c < cols)
+    for (int64_t r = threadIdx.y; r < rows; r += 8) s += x[r * ld + c];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    out[c] = accumulate ? out[c] + t : t;
+  }
+}
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ldf<bf16>(const bf16* p) { return __bfloat162float(*p); }
+
+template <typename T>
+__global__ void rowsum_bms_kernel(const T* __restrict__ x, int B, int M, int S, int Sp, float* __restrict__ out) {
+  __shared__ float red[32];
+  const int m = blockIdx.x;
+  float s = 0.0f;
+  for (int b = 0; b < B; ++b) {
+    const T* row = x + ((int64_t)b * M + m) * Sp;
+    for (int k = threadIdx.x; k < S; k += blockDim.x) s += ldf<T>(row + k);
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[m] += s;
+}
+
+__global__ void sum_all_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out, int accumulate) {
+  __shared__ float red[32];
+  float s = 0.0f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[0] = accumulate ? out[0] + s : s;
+}
+
+// rnn_out[b] = state_{t = len_b}[b]   (F:472-478 host loop, fused)
+__global__ void select_state_kernel(const float* __restrict__ S_all, int T, int B, int Q,
+                                    const float* __restrict__ lengths, float* __restrict__ out) {
+  const int64_t total = (int64_t)B * Q;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / Q);
+    int t = (int)lengths[b];
+    float v = 0.0f;                       // rnn_out:zero() when no step matches (F:464)
+    if (t >= 1 && t <= T) v = S_all[((int64_t)t * B + b) * Q + (i % Q)];
+    out[i] = v;
+  }
+}
+}  // namespace
+
+// ================================================================== host wrappers
+int k_mask_gen(rau_ctx* ctx, uint32_t* bits, int64_t n, float p, uint64_t seed, uint64_t stream_id) {
+  const int64_t nw = (n + 31) / 32;
+  double keep = 1.0 - (double)p;
+  uint32_t thresh = keep >= 1.0 ? 0xffffffffu : (uint32_t)(keep * 4294967296.0);
+  mask_gen_kernel<<<grid_for(nw), TPB, 0, ctx->stream>>>(bits, nw, n, thresh, p <= 0.0f ? 1 : 0,
+      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), (uint32_t)stream_id, (uint32_t)(stream_id >> 32));
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+int k_mask_pack(rau_ctx* ctx, uint32_t* bits, const uint8_t* bytes, int64_t n) {
+  const int64_t nw = (n + 31) / 32;
+  mask_pack_kernel<<<grid_for(nw), TPB, 0, ctx->stream>>>(bits, bytes, nw, n);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+int k_embed_fwd(rau_ctx* ctx, const float* ids, int n, int D, int V, const float* E, const uint32_t* bits, float scale,
+                float* out_f, bf16* out_b, int ldb) {
+  embed_fwd_kernel<<<grid_for((int64_t)n * D), TPB, 0, ctx->stream>>>(ids, n, D, V, E, bits, scale, out_f, out_b, ldb);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+int k_embed_bwd(rau_ctx* ctx, const float* ids, int n, int D, int V, const float* out, const uint32_t* bits, float scale,
+                const float* dout, int lddout, float* gE) {
+  embed_bwd_kernel<<<grid_for((int64_t)n * D), TPB, 0, ctx->stream>>>(ids, n, D, V, out, bits, scale, dout, lddout, gE);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+int k_lstm_fwd(rau_ctx* ctx, int B, int H, int order, const float* G, int ldg, const float* c_prev, int ldcp,
+               float* c, int ldc, float* h, int ldh, bf16* h_b, int ldhb, float* saved) {
+  lstm_fwd_kernel<<<grid_for((int64_t)B * H), TPB, 0, ctx->stream>>>(B, H, order, G, ldg, c_prev, ldcp, c, ldc, h, ldh, h_b, ldhb, saved);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+int k_lstm_bwd(rau_ctx* ctx, int B, int H, int order, const float* dc_out, int lddc, const float* dh_out, int lddh,
+               const float* dh_extra, int ldhe, const float* lengths, int t, const float* dq_c, const float* dq_h, int lddq,
+               const float* c_prev, int ldcp, const float* saved, float* dG, bf16* dG_b, float* dc_prev, int lddcp) {
+  lstm_bwd_kernel<<<grid_for((int64_t)B * H), TPB, 0, ctx->stream>>>(B, H, order, dc_out, lddc, dh_out, lddh, dh_extra, ldhe,
+      lengths, t, dq_c, dq_h, lddq, c_prev, ldcp, saved, dG, dG_b, dc_prev, lddcp);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+int k_dropout(rau_ctx* ctx, const float* x, int64_t rows, int cols, int ldx, const uint32_t* bits, float scale,
+              float* y_f, int ldyf, bf16* y_b, int ldyb, int cols_pad) {
+  dropout_kernel<<<grid_for(rows * cols_pad, 4), TPB, 0, ctx->stream>>>(x, rows, cols, ldx, bits, scale, y_f, ldyf, y_b, ldyb, cols_pad);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+int k_dropout_bwd_acc(rau_ctx* ctx, const float* dx, int64_t n, const uint32_t* bits, float scale, float* y, int accumulate) {
+  dropout_bwd_acc_kernel<<<grid_for(n, 4), TPB, 0, ctx->stream>>>(dx, n, bits, scale, y, accumulate);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+int k_tanh_bwd(rau_ctx* ctx, const float* dy, const float* y, int64_t n, float* dx_f, bf16* dx_b) {
+  tanh_bwd_kernel<<<grid_for(n, 4), TPB, 0, ctx->stream>>>(dy, y, n, dx_f, dx_b);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+int k_add(rau_ctx* ctx, const float* a, const float* b, int64_t n, float* y) {
+  add_kernel<<<grid_for(n, 4), TPB, 0, ctx->stream>>>(a, b, n, y);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+int k_axpy(rau_ctx* ctx, float alpha, const float* x, int64_t n, float* y) {
+  axpy_kernel<<<grid_for(n, 4), TPB, 0, ctx->stream>>>(alpha, x, n, y);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+int k_fill(rau_ctx* ctx, float* x, int64_t n, float v) {
+  if (n <= 0) return RAU_OK;
+  fill_kernel<<<grid_for(n, 4), TPB, 0, ctx->stream>>>(x, n, v);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+int k_to_bf16(rau_ctx* ctx, const float* x, int64_t rows, int cols, int ldx, bf16* y, int ldy, int cols_pad) {
+  to_bf16_kernel<<<grid_for(rows * cols_pad, 4), TPB, 0, ctx->stream>>>(x, rows, cols, ldx, y, ldy, cols_pad);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+int k_rowdot_sigmoid(rau_ctx* ctx, const float* x, int B, int K, const float* w, const float* b, float* y) {
+  rowdot_sigmoid_kernel<<<cdiv((int64_t)B * 32, TPB), TPB, 0, ctx->stream>>>(x, B, K, w, b, y);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+int k_dopred_bwd(rau_ctx* ctx, const float* ddo, const float* dop, const float* m, const float* wd, int B, int K,
+                 float* dm_acc, float* gwd, float* gbd) {
+  dopred_bwd_kernel<<<cdiv(K, TPB), TPB, 0, ctx->stream>>>(ddo, dop, m, wd, B, K, dm_acc, gwd, gbd);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+int k_colsum(rau_ctx* ctx, const float* x, int64_t rows, int cols, int ld, float* out, int accumulate) {
+  colsum_kernel<<<cdiv(cols, 32), dim3(32, 8), 0, ctx->stream>>>(x, rows, cols, ld, out, accumulate);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+template <typename T>
+int k_rowsum_bms(rau_ctx* ctx, const T* x, int B, int M, int S, int Sp, float* out) {
+  rowsum_bms_kernel<T><<<M, TPB, 0, ctx->stream>>>(x, B, M, S, Sp, out);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+template int k_rowsum_bms<float>(rau_ctx*, const float*, int, int, int, int, float*);
+template int k_rowsum_bms<bf16>(rau_ctx*, const bf16*, int, int, int, int, float*);
+int k_sum_all(rau_ctx* ctx, const float* x, int64_t n, float* out, int accumulate) {
+  sum_all_kernel<<<1, 1024, 0, ctx->stream>>>(x, n, out, accumulate);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+int k_select_state(rau_ctx* ctx, const float* S_all, int T, int B, int Q, const float* lengths, float* out) {
+  select_state_kernel<<<grid_for((int64_t)B * Q), TPB, 0, ctx->stream>>>(S_all, T, B, Q, lengths, out);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}

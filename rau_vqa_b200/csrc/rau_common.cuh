@@ -1,0 +1,158 @@
+// rau_common.cuh -- context, error plumbing and small device helpers shared by every kernel file.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include <map>
+#include <string>
+#include "../../include/rau.h"
+
+typedef __nv_bfloat16 bf16;
+
+void rau_set_error(const char* fmt, ...);
+
+#define RAU_CHECK_CUDA(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      rau_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return RAU_ECUDA;                                                                   \
+    }                                                                                     \
+  } while (0)
+
+#define RAU_REQUIRE(cond, ...)                                                            \
+  do {                                                                                    \
+    if (!(cond)) {                                                                        \
+      rau_set_error(__VA_ARGS__);                                                         \
+      return RAU_EINVAL;                                                                  \
+    }                                                                                     \
+  } while (0)
+
+#define RAU_TRY(expr)                                                                     \
+  do {                                                                                    \
+    int _s = (expr);                                                                      \
+    if (_s != RAU_OK) return _s;                                                          \
+  } while (0)
+
+// A growable device arena: buffers are keyed by name, re-used across calls, grown on demand.
+struct RauArena {
+  struct Buf { void* p = nullptr; size_t bytes = 0; };
+  std::map<std::string, Buf> bufs;
+  int get(const char* name, size_t bytes, void** out);
+  void release();
+};
+
+struct RauComm;  // rau_comm.cu
+
+struct rau_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  uint64_t seed = 0x5eed5eedULL;
+  int precision = RAU_PREC_BF16;
+  int sm_count = 148;
+  int64_t launches = 0;
+  RauArena arena;
+  RauComm* comm = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+#define RAU_LAUNCH_CHECK(ctx)                                                             \
+  do {                                                                                    \
+    (ctx)->launches++;                                                                    \
+    cudaError_t _e = cudaGetLastError();                                                  \
+    if (_e != cudaSuccess) {                                                              \
+      rau_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return RAU_ECUDA;                                                                   \
+    }                                                                                     \
+  } while (0)
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------ device helpers
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide sum for blockDim.x <= 1024 (multiple of 32); `red` is >= 32 floats of shared memory.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0f;
+  if (w == 0) r = warp_sum(r);
+  if (threadIdx.x == 0) red[0] = r;
+  __syncthreads();
+  r = red[0];
+  return r;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = (threadIdx.x < nw) ? red[threadIdx.x] : -INFINITY;
+  if (w == 0) r = warp_max(r);
+  if (threadIdx.x == 0) red[0] = r;
+  __syncthreads();
+  r = red[0];
+  return r;
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter-based: no state to carry between forward and backward.
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0; key.y += W1;
+  }
+  return ctr;
+}
+
+// keep-bit lookup in a packed mask (bit i of word i>>5); nullptr = keep everything (evaluate()).
+__device__ __forceinline__ float keep_scale(const uint32_t* __restrict__ bits, int64_t i, float scale) {
+  if (bits == nullptr) return 1.0f;
+  return ((bits[i >> 5] >> (i & 31)) & 1u) ? scale : 0.0f;
+}
+
+// ------------------------------------------------------------------ internal entry points
+// k_gemm_simt.cu
+struct SimtGemm {
+  int M = 0, N = 0, K = 0;
+  const float* A = nullptr; int64_t sam = 0, sak = 0;   // A(m,k) = A[m*sam + k*sak]
+  const float* B = nullptr; int64_t sbk = 0, sbn = 0;   // B(k,n) = B[k*sbk + n*sbn]
+  float* C = nullptr; int64_t scm = 0, scn = 1;
+  int batch = 1; int64_t bA = 0, bB = 0, bC = 0;        // independent problems (blockIdx.z)
+  int kbatch = 1; int64_t kA = 0, kB = 0;               // batches reduced into one C
+  int ksplit = 1;                                       // >1: grid.z slices of the reduction, atomicAdd into C
+  const float* A2 = nullptr; int64_t sam2 = 0, sak2 = 0; // optional second K segment (same M,N)
+  const float* B2 = nullptr; int64_t sbk2 = 0, sbn2 = 0; int K2 = 0;
+  const float* bias_m = nullptr;   // [M]
+  const float* bias_n = nullptr;   // [N]
+  const float* bias_n2 = nullptr;  // [N] second bias (i2h + h2h)
+  const float* bias_bm = nullptr;  // [batch, M]
+  const float* addend = nullptr; int64_t sdm = 0, sdn = 1, bD = 0;  // same indexing as C
+  const float* addend2 = nullptr;  // same strides as addend
+  int accumulate = 0;
+  float alpha = 1.0f;
+  int act = 0;                     // 0 none, 1 tanh, 2 sigmoid
+  int n_valid = -1;                // columns >= n_valid are written as 0 (spatial pad)
+};
+int simt_gemm(rau_ctx* ctx, const SimtGemm& g);

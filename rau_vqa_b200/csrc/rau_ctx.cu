@@ -1,0 +1,184 @@
+// rau_ctx.cu -- context lifetime, error text, device arena and the flat parameter layout of include/rau.h.
+#include "rau_layout.cuh"
+#include <stdarg.h>
+#include <stdlib.h>
+
+static thread_local char g_err[512] = "";
+
+void rau_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int RauArena::get(const char* name, size_t bytes, void** out) {
+  Buf& b = bufs[name];
+  if (b.bytes < bytes) {
+    if (b.p) {
+      // the stream may still be using the old block: drain before freeing
+      cudaDeviceSynchronize();
+      cudaFree(b.p);
+      b.p = nullptr;
+      b.bytes = 0;
+    }
+    size_t want = (bytes + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+      rau_set_error("cudaMalloc(%zu) for '%s' failed: %s", want, name, cudaGetErrorString(e));
+      return RAU_ENOMEM;
+    }
+    b.bytes = want;
+  }
+  *out = b.p;
+  return RAU_OK;
+}
+
+void RauArena::release() {
+  for (auto& kv : bufs)
+    if (kv.second.p) cudaFree(kv.second.p);
+  bufs.clear();
+}
+
+int rau_comm_destroy_internal(rau_ctx* ctx);  // rau_comm.cu
+
+extern "C" {
+
+int rau_version(void) { return 100; }
+
+const char* rau_last_error(void) { return g_err; }
+
+int rau_ctx_create(rau_ctx** out, int device, void* cuda_stream) {
+  if (out == nullptr) { rau_set_error("rau_ctx_create: out == NULL"); return RAU_EINVAL; }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    rau_set_error("no CUDA device (%s); librau has no CPU fallback", cudaGetErrorString(e));
+    return RAU_ECUDA;
+  }
+  RAU_REQUIRE(device >= 0 && device < ndev, "device %d out of range (%d devices)", device, ndev);
+  cudaDeviceProp prop;
+  RAU_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    rau_set_error("device %d is sm_%d%d; librau is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    return RAU_EARCH;
+  }
+  RAU_CHECK_CUDA(cudaSetDevice(device));
+  rau_ctx* ctx = new rau_ctx();
+  ctx->device = device;
+  ctx->stream = (cudaStream_t)cuda_stream;
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+    rau_set_error("cudaEventCreate failed");
+    delete ctx;
+    return RAU_ECUDA;
+  }
+  *out = ctx;
+  return RAU_OK;
+}
+
+int rau_ctx_destroy(rau_ctx* ctx) {
+  if (ctx == nullptr) return RAU_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  rau_comm_destroy_internal(ctx);
+  ctx->arena.release();
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  delete ctx;
+  return RAU_OK;
+}
+
+int rau_set_stream(rau_ctx* ctx, void* cuda_stream) {
+  RAU_REQUIRE(ctx, "ctx == NULL");
+  ctx->stream = (cudaStream_t)cuda_stream;
+  return RAU_OK;
+}
+
+int rau_set_seed(rau_ctx* ctx, uint64_t seed) {
+  RAU_REQUIRE(ctx, "ctx == NULL");
+  ctx->seed = seed;
+  return RAU_OK;
+}
+
+int rau_set_precision(rau_ctx* ctx, int precision) {
+  RAU_REQUIRE(ctx, "ctx == NULL");
+  RAU_REQUIRE(precision >= RAU_PREC_F32 && precision <= RAU_PREC_BF16X3, "unknown precision %d", precision);
+  ctx->precision = precision;
+  return RAU_OK;
+}
+
+int rau_get_precision(rau_ctx* ctx) { return ctx ? ctx->precision : RAU_EINVAL; }
+
+int rau_sync(rau_ctx* ctx) {
+  RAU_REQUIRE(ctx, "ctx == NULL");
+  RAU_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RAU_OK;
+}
+
+int64_t rau_launch_count(rau_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int64_t rau_group_size(const rau_config* cfg, int group) {
+  if (cfg == nullptr) return -1;
+  return rau_layout(cfg, group, nullptr);
+}
+
+int64_t rau_param_offset(const rau_config* cfg, int group, const char* name) {
+  if (cfg == nullptr || name == nullptr) return -1;
+  std::vector<ParamEntry> e;
+  if (rau_layout(cfg, group, &e) < 0) return -1;
+  for (const auto& p : e)
+    if (strcmp(p.name, name) == 0) return p.off;
+  return -1;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ layout
+static const char* kRnnNames[4][4] = {{"l1.Wi", "l1.bi", "l1.Wh", "l1.bh"},
+                                      {"l2.Wi", "l2.bi", "l2.Wh", "l2.bh"},
+                                      {"l3.Wi", "l3.bi", "l3.Wh", "l3.bh"},
+                                      {"l4.Wi", "l4.bi", "l4.Wh", "l4.bh"}};
+
+int64_t rau_layout(const rau_config* cfg, int group, std::vector<ParamEntry>* out) {
+  int64_t off = 0;
+  auto add = [&](const char* name, int64_t rows, int64_t cols) {
+    if (out) out->push_back(ParamEntry{name, off, rows, cols});
+    off += rows * cols;
+  };
+  const int Q = 2 * cfg->Hq * cfg->nlayer;
+  switch (group) {
+    case 0:
+      add("E", cfg->V, cfg->embed);
+      break;
+    case 1:
+      if (cfg->nlayer < 1 || cfg->nlayer > 4) return -1;
+      for (int L = 0; L < cfg->nlayer; ++L) {
+        const int in = L == 0 ? cfg->embed : cfg->Hq;
+        add(kRnnNames[L][0], 4 * cfg->Hq, in);
+        add(kRnnNames[L][1], 4 * cfg->Hq, 1);
+        add(kRnnNames[L][2], 4 * cfg->Hq, cfg->Hq);
+        add(kRnnNames[L][3], 4 * cfg->Hq, 1);
+      }
+      break;
+    case 2:
+      add("Wq", cfg->M, Q);            add("bq", cfg->M, 1);
+      add("Wh", cfg->M, cfg->H);       add("bh", cfg->M, 1);
+      add("Wi", cfg->M, cfg->C);       add("bi", cfg->M, 1);
+      add("Wqa", cfg->A, cfg->M);      add("bqa", cfg->A, 1);
+      add("Wa", cfg->A, cfg->M);       add("ba", cfg->A, 1);
+      add("ws", 1, cfg->A);            add("bs", 1, 1);
+      add("Wm", cfg->S, cfg->H);       add("bm", cfg->S, 1);
+      add("Wp", cfg->M, cfg->S);       add("bp", cfg->M, 1);
+      add("Wx", 4 * cfg->H, cfg->M);   add("bx", 4 * cfg->H, 1);
+      add("Whh", 4 * cfg->H, cfg->H);  add("bhh", 4 * cfg->H, 1);
+      add("Wo", cfg->M, cfg->H);       add("bo", cfg->M, 1);
+      add("Ws", cfg->N, cfg->M);       add("bso", cfg->N, 1);
+      add("wd", 1, cfg->M);            add("bd", 1, 1);
+      break;
+    default:
+      return -1;
+  }
+  return off;
+}

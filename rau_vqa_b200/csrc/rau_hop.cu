@@ -1,0 +1,479 @@
+// rau_hop.cu -- one recurrent answering unit: protos.multimodal forward (F:292-307) and its backward
+// (what multimodals[h]:backward computes, F:590-593), plus the module-level C ABI around them and around the
+// LSTM cells of model/ATTLSTM.lua and model/DeepLSTM.lua.  The math is SURVEY.md Appendix A; every
+// contraction goes through rau_contract() so that the precision mode picks the engine.
+#include "rau_model.cuh"
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+size_t hop_saved_layout(const rau_config* cfg, int B, void* base, HopSaved* sv) {
+  const int Q = 2 * cfg->Hq * cfg->nlayer, Sp = rau_sp(cfg->S);
+  size_t off = 0;
+  char* b = (char*)base;
+  auto take = [&](size_t bytes) {
+    void* p = b ? (void*)(b + off) : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  HopSaved s;
+  s.qbits = (uint32_t*)take(mask_words((int64_t)B * Q) * 4);
+  s.xbits = (uint32_t*)take(mask_words((int64_t)B * cfg->C * cfg->S) * 4);
+  s.mbits = (uint32_t*)take(mask_words((int64_t)B * cfg->M) * 4);
+  s.qd = (float*)take(sizeof(float) * B * Q);
+  s.qf = (float*)take(sizeof(float) * B * cfg->M);
+  s.I = (float*)take(sizeof(float) * (size_t)B * cfg->M * Sp);
+  s.E = (float*)take(sizeof(float) * (size_t)B * cfg->A * Sp);
+  s.p = (float*)take(sizeof(float) * B * cfg->S);
+  s.j = (float*)take(sizeof(float) * B * cfg->M);
+  s.lsav = (float*)take(sizeof(float) * 5 * B * cfg->H);
+  s.hout = (float*)take(sizeof(float) * B * cfg->H);
+  s.m = (float*)take(sizeof(float) * B * cfg->M);
+  s.dop = (float*)take(sizeof(float) * B);
+  if (sv) *sv = s;
+  return off;
+}
+
+static inline float drop_scale(float p) { return p > 0.0f ? 1.0f / (1.0f - p) : 1.0f; }
+
+#define ARENA(ptr, type, name, count) \
+  type* ptr = nullptr;                \
+  RAU_TRY(ctx->arena.get(name, sizeof(type) * (size_t)(count), (void**)&ptr))
+
+int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const float*>& P,
+                const float* q, const float* X, const float* c, const float* h, int train, const HopSaved& sv,
+                float* score, float* do_pred, float* p_out, float* c_out, float* h_out) {
+  const int Q = 2 * cfg->Hq * cfg->nlayer, M = cfg->M, A = cfg->A, H = cfg->H, S = cfg->S, C = cfg->C, N = cfg->N;
+  const int Sp = rau_sp(S);
+  const uint32_t* qb = (train && cfg->p_q > 0) ? sv.qbits : nullptr;
+  const uint32_t* xb = (train && cfg->p_x > 0) ? sv.xbits : nullptr;
+  const uint32_t* mb = (train && cfg->p_m > 0) ? sv.mbits : nullptr;
+  ARENA(Xd, float, "hop.Xd", (size_t)B * C * Sp);
+  ARENA(qatt, float, "hop.qatt", B * A);
+  ARENA(mem, float, "hop.mem", B * S);
+  ARENA(a, float, "hop.a", B * M);
+  ARENA(Gt, float, "hop.G", B * 4 * H);
+  ARENA(prem, float, "hop.prem", B * M);
+
+  // q_embed (F:231-236): qf = tanh(Wq drop(q) + bq + Wh h + bh)
+  RAU_TRY(k_dropout(ctx, q, B, Q, Q, qb, drop_scale(cfg->p_q), sv.qd, Q, nullptr, 0, Q));
+  {
+    SimtGemm g = lin_fwd(B, M, Q, sv.qd, Q, P.Wq, sv.qf, M);
+    lin_seg2(g, H, h, H, P.Wh);
+    g.bias_n = P.bq; g.bias_n2 = P.bh; g.act = 1;
+    RAU_TRY(rau_contract(ctx, g));
+  }
+  // i_embed (F:238-242): I[b] = tanh(Wi drop(X[b]) + bi), 1x1 convolution = per-image [M,C]x[C,S] product
+  RAU_TRY(k_dropout(ctx, X, (int64_t)B * C, S, S, xb, drop_scale(cfg->p_x), Xd, Sp, nullptr, 0, Sp));
+  {
+    SimtGemm g;
+    g.M = M; g.N = Sp; g.K = C;
+    g.A = P.Wi; g.sam = C; g.sak = 1;
+    g.B = Xd; g.sbk = Sp; g.sbn = 1; g.bB = (int64_t)C * Sp;
+    g.C = sv.I; g.scm = Sp; g.scn = 1; g.bC = (int64_t)M * Sp;
+    g.batch = B; g.bias_m = P.bi; g.act = 1; g.n_valid = S;
+    RAU_TRY(rau_contract(ctx, g));
+  }
+  // attbycontent (F:244-252): E[b] = tanh(Wa I[b] + ba + (Wqa qf + bqa) 1^T); the 256->1 conv is fused below
+  {
+    SimtGemm g = lin_fwd(B, A, M, sv.qf, M, P.Wqa, qatt, A);
+    g.bias_n = P.bqa;
+    RAU_TRY(rau_contract(ctx, g));
+  }
+  {
+    SimtGemm g;
+    g.M = A; g.N = Sp; g.K = M;
+    g.A = P.Wa; g.sam = M; g.sak = 1;
+    g.B = sv.I; g.sbk = Sp; g.sbn = 1; g.bB = (int64_t)M * Sp;
+    g.C = sv.E; g.scm = Sp; g.scn = 1; g.bC = (int64_t)A * Sp;
+    g.batch = B; g.bias_m = P.ba; g.bias_bm = qatt; g.act = 1; g.n_valid = S;
+    RAU_TRY(rau_contract(ctx, g));
+  }
+  // attbymemory (F:285-290) + attselect (F:254-263): p = softmax(ws.E + bs + Wm h + bm) ; a = I p
+  // (the scalar conv bias bs shifts every logit alike, so the softmax does not see it)
+  {
+    SimtGemm g = lin_fwd(B, S, H, h, H, P.Wm, mem, S);
+    g.bias_n = P.bm;
+    RAU_TRY(rau_contract(ctx, g));
+  }
+  RAU_TRY(k_attn_fwd<float>(ctx, B, M, A, S, Sp, sv.E, sv.I, P.ws, mem, sv.p, nullptr, 0, a, nullptr));
+  if (p_out && p_out != sv.p)
+    RAU_CHECK_CUDA(cudaMemcpyAsync(p_out, sv.p, sizeof(float) * B * S, cudaMemcpyDeviceToDevice, ctx->stream));
+  // classifier (F:265-283): j = qf + a + Wp p + bp
+  {
+    SimtGemm g = lin_fwd(B, M, S, sv.p, S, P.Wp, sv.j, M);
+    g.bias_n = P.bp; g.addend = sv.qf; g.sdm = M; g.sdn = 1; g.addend2 = a;
+    RAU_TRY(rau_contract(ctx, g));
+  }
+  // attlstm (A:4-28): gates (i,g,f,o)
+  {
+    SimtGemm g = lin_fwd(B, 4 * H, M, sv.j, M, P.Wx, Gt, 4 * H);
+    lin_seg2(g, H, h, H, P.Whh);
+    g.bias_n = P.bx; g.bias_n2 = P.bhh;
+    RAU_TRY(rau_contract(ctx, g));
+  }
+  RAU_TRY(k_lstm_fwd(ctx, B, H, RAU_GATES_IGFO, Gt, 4 * H, c, H, c_out, H, sv.hout, H, nullptr, 0, sv.lsav));
+  if (h_out)
+    RAU_CHECK_CUDA(cudaMemcpyAsync(h_out, sv.hout, sizeof(float) * B * H, cudaMemcpyDeviceToDevice, ctx->stream));
+  // m = drop(j + Wo h' + bo) ; score = Ws m + bs ; do_pred = sigmoid(wd.m + bd)   (F:276-281)
+  {
+    SimtGemm g = lin_fwd(B, M, H, sv.hout, H, P.Wo, prem, M);
+    g.bias_n = P.bo; g.addend = sv.j; g.sdm = M; g.sdn = 1;
+    RAU_TRY(rau_contract(ctx, g));
+  }
+  RAU_TRY(k_dropout(ctx, prem, B, M, M, mb, drop_scale(cfg->p_m), sv.m, M, nullptr, 0, M));
+  {
+    SimtGemm g = lin_fwd(B, N, M, sv.m, M, P.Ws, score, N);
+    g.bias_n = P.bso;
+    RAU_TRY(rau_contract(ctx, g));
+  }
+  RAU_TRY(k_rowdot_sigmoid(ctx, sv.m, B, M, P.wd, P.bd, sv.dop));
+  if (do_pred)
+    RAU_CHECK_CUDA(cudaMemcpyAsync(do_pred, sv.dop, sizeof(float) * B, cudaMemcpyDeviceToDevice, ctx->stream));
+  return RAU_OK;
+}
+
+int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const float*>& P, const MultT<float*>& G,
+                 const float* X, const float* c, const float* h, int train, const HopSaved& sv,
+                 const float* dscore, const float* ddo_pred, const float* dp_att, const float* dc_out, const float* dh_out,
+                 float* dq, int dq_accumulate, float* dX, float* dc, float* dh) {
+  const int Q = 2 * cfg->Hq * cfg->nlayer, M = cfg->M, A = cfg->A, H = cfg->H, S = cfg->S, C = cfg->C, N = cfg->N;
+  const int Sp = rau_sp(S);
+  const uint32_t* qb = (train && cfg->p_q > 0) ? sv.qbits : nullptr;
+  const uint32_t* xb = (train && cfg->p_x > 0) ? sv.xbits : nullptr;
+  const uint32_t* mb = (train && cfg->p_m > 0) ? sv.mbits : nullptr;
+  ARENA(Xd, float, "hop.Xd", (size_t)B * C * Sp);
+  ARENA(du, float, "hopb.du", B * M);
+  ARENA(dh2, float, "hopb.dh2", B * H);
+  ARENA(dG, float, "hopb.dG", B * 4 * H);
+  ARENA(dj, float, "hopb.dj", B * M);
+  ARENA(dp, float, "hopb.dp", B * S);
+  ARENA(ds, float, "hopb.ds", B * S);
+  ARENA(dZ, float, "hopb.dZ", (size_t)B * A * Sp);
+  ARENA(dqa, float, "hopb.dqa", B * A);
+  ARENA(gwsp, float, "hopb.gwsp", B * A);
+  ARENA(dI, float, "hopb.dI", (size_t)B * M * Sp);
+  ARENA(dqf, float, "hopb.dqf", B * M);
+  ARENA(dpre, float, "hopb.dpre", B * M);
+  ARENA(dqt, float, "hopb.dqt", B * Q);
+  const int ks_img = B >= 64 ? 32 : (B >= 8 ? 8 : 1);   // split of the per-image reductions
+
+  // heads: dm = Ws^T dscore (+ do_pred head) ; gWs += dscore (x) m
+  if (dscore) {
+    RAU_TRY(rau_contract(ctx, lin_dgrad(B, N, M, dscore, N, P.Ws, du, M)));
+    RAU_TRY(rau_contract(ctx, lin_wgrad(B, N, M, dscore, N, sv.m, M, G.Ws, 1.0f)));
+    RAU_TRY(k_colsum(ctx, dscore, B, N, N, G.bso, 1));
+  } else {
+    RAU_TRY(k_fill(ctx, du, (int64_t)B * M, 0.0f));
+  }
+  if (ddo_pred) RAU_TRY(k_dopred_bwd(ctx, ddo_pred, sv.dop, sv.m, P.wd, B, M, du, G.wd, G.bd));
+  RAU_TRY(k_dropout_bwd_acc(ctx, du, (int64_t)B * M, mb, drop_scale(cfg->p_m), du, 0));
+  // dh' = dh_next + Wo^T du ; gWo += du (x) h'
+  {
+    SimtGemm g = lin_dgrad(B, M, H, du, M, P.Wo, dh2, H);
+    if (dh_out) { g.addend = dh_out; g.sdm = H; g.sdn = 1; }
+    RAU_TRY(rau_contract(ctx, g));
+  }
+  RAU_TRY(rau_contract(ctx, lin_wgrad(B, M, H, du, M, sv.hout, H, G.Wo, 1.0f)));
+  RAU_TRY(k_colsum(ctx, du, B, M, M, G.bo, 1));
+  // attlstm backward
+  RAU_TRY(k_lstm_bwd(ctx, B, H, RAU_GATES_IGFO, dc_out, H, dh2, H, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, c, H,
+                     sv.lsav, dG, nullptr, dc, H));
+  {
+    SimtGemm g = lin_dgrad(B, 4 * H, M, dG, 4 * H, P.Wx, dj, M);
+    g.addend = du; g.sdm = M; g.sdn = 1;
+    RAU_TRY(rau_contract(ctx, g));
+  }
+  RAU_TRY(rau_contract(ctx, lin_dgrad(B, 4 * H, H, dG, 4 * H, P.Whh, dh, H)));
+  RAU_TRY(rau_contract(ctx, lin_wgrad(B, 4 * H, M, dG, 4 * H, sv.j, M, G.Wx, 1.0f)));
+  RAU_TRY(rau_contract(ctx, lin_wgrad(B, 4 * H, H, dG, 4 * H, h, H, G.Whh, 1.0f)));
+  RAU_TRY(k_colsum(ctx, dG, B, 4 * H, 4 * H, G.bx, 1));
+  RAU_TRY(k_colsum(ctx, dG, B, 4 * H, 4 * H, G.bhh, 1));
+  // join: dqf = da = dj ; dp = dp_att + Wp^T dj ; gWp += dj (x) p
+  {
+    SimtGemm g = lin_dgrad(B, M, S, dj, M, P.Wp, dp, S);
+    if (dp_att) { g.addend = dp_att; g.sdm = S; g.sdn = 1; }
+    RAU_TRY(rau_contract(ctx, g));
+  }
+  RAU_TRY(rau_contract(ctx, lin_wgrad(B, M, S, dj, M, sv.p, S, G.Wp, 1.0f)));
+  RAU_TRY(k_colsum(ctx, dj, B, M, M, G.bp, 1));
+  // attselect + softmax + score conv + tanh of attbycontent, one CTA per image
+  RAU_TRY(k_attn_bwd<float>(ctx, B, M, A, S, Sp, sv.E, sv.I, P.ws, sv.p, dp, dj, ds, nullptr, 0, dZ, dqa, nullptr, gwsp));
+  {
+    SimtGemm g = lin_dgrad(B, S, H, ds, S, P.Wm, dh, H);
+    g.accumulate = 1;
+    RAU_TRY(rau_contract(ctx, g));
+  }
+  RAU_TRY(rau_contract(ctx, lin_wgrad(B, S, H, ds, S, h, H, G.Wm, 1.0f)));
+  RAU_TRY(k_colsum(ctx, ds, B, S, S, G.bm, 1));
+  RAU_TRY(k_colsum(ctx, gwsp, B, A, A, G.ws, 1));
+  RAU_TRY(k_sum_all(ctx, ds, (int64_t)B * S, G.bs, 1));
+  // dI = Wa^T dZ (+ da p^T inside the pointwise) ; dY = dI (1 - I^2)
+  {
+    SimtGemm g;
+    g.M = M; g.N = Sp; g.K = A;
+    g.A = P.Wa; g.sam = 1; g.sak = M;
+    g.B = dZ; g.sbk = Sp; g.sbn = 1; g.bB = (int64_t)A * Sp;
+    g.C = dI; g.scm = Sp; g.scn = 1; g.bC = (int64_t)M * Sp;
+    g.batch = B;
+    RAU_TRY(rau_contract(ctx, g));
+  }
+  RAU_TRY(k_iembed_bwd_pw<float>(ctx, B, M, S, Sp, dI, sv.I, dj, sv.p, dI));
+  // gWa += sum_b dZ[b] I[b]^T ; gba += sum dZ
+  {
+    SimtGemm g;
+    g.M = A; g.N = M; g.K = Sp;
+    g.A = dZ; g.sam = Sp; g.sak = 1; g.kA = (int64_t)A * Sp;
+    g.B = sv.I; g.sbk = 1; g.sbn = Sp; g.kB = (int64_t)M * Sp;
+    g.C = G.Wa; g.scm = M; g.scn = 1;
+    g.kbatch = B; g.accumulate = 1; g.ksplit = ks_img;
+    RAU_TRY(rau_contract(ctx, g));
+  }
+  RAU_TRY(k_rowsum_bms<float>(ctx, dZ, B, A, S, Sp, G.ba));
+  // dqf = dj + Wqa^T dqa ; gWqa += dqa (x) qf
+  {
+    SimtGemm g = lin_dgrad(B, A, M, dqa, A, P.Wqa, dqf, M);
+    g.addend = dj; g.sdm = M; g.sdn = 1;
+    RAU_TRY(rau_contract(ctx, g));
+  }
+  RAU_TRY(rau_contract(ctx, lin_wgrad(B, A, M, dqa, A, sv.qf, M, G.Wqa, 1.0f)));
+  RAU_TRY(k_colsum(ctx, dqa, B, A, A, G.bqa, 1));
+  // i_embed: gWi += sum_b dY[b] drop(X[b])^T ; gbi += sum dY ; dX only on request (the caller discards it, F:598)
+  RAU_TRY(k_dropout(ctx, X, (int64_t)B * C, S, S, xb, drop_scale(cfg->p_x), Xd, Sp, nullptr, 0, Sp));
+  {
+    SimtGemm g;
+    g.M = M; g.N = C; g.K = Sp;
+    g.A = dI; g.sam = Sp; g.sak = 1; g.kA = (int64_t)M * Sp;
+    g.B = Xd; g.sbk = 1; g.sbn = Sp; g.kB = (int64_t)C * Sp;
+    g.C = G.Wi; g.scm = C; g.scn = 1;
+    g.kbatch = B; g.accumulate = 1; g.ksplit = ks_img;
+    RAU_TRY(rau_contract(ctx, g));
+  }
+  RAU_TRY(k_rowsum_bms<float>(ctx, dI, B, M, S, Sp, G.bi));
+  if (dX) {
+    SimtGemm g;
+    g.M = C; g.N = Sp; g.K = M;
+    g.A = P.Wi; g.sam = 1; g.sak = C;
+    g.B = dI; g.sbk = Sp; g.sbn = 1; g.bB = (int64_t)M * Sp;
+    g.C = Xd; g.scm = Sp; g.scn = 1; g.bC = (int64_t)C * Sp;
+    g.batch = B;
+    RAU_TRY(rau_contract(ctx, g));
+    RAU_TRY(k_dropout(ctx, Xd, (int64_t)B * C, S, Sp, xb, drop_scale(cfg->p_x), dX, S, nullptr, 0, S));
+  }
+  // q_embed backward
+  RAU_TRY(k_tanh_bwd(ctx, dqf, sv.qf, (int64_t)B * M, dpre, nullptr));
+  RAU_TRY(rau_contract(ctx, lin_dgrad(B, M, Q, dpre, M, P.Wq, dqt, Q)));
+  RAU_TRY(k_dropout_bwd_acc(ctx, dqt, (int64_t)B * Q, qb, drop_scale(cfg->p_q), dq, dq_accumulate));
+  {
+    SimtGemm g = lin_dgrad(B, M, H, dpre, M, P.Wh, dh, H);
+    g.accumulate = 1;
+    RAU_TRY(rau_contract(ctx, g));
+  }
+  RAU_TRY(rau_contract(ctx, lin_wgrad(B, M, Q, dpre, M, sv.qd, Q, G.Wq, 1.0f)));
+  RAU_TRY(rau_contract(ctx, lin_wgrad(B, M, H, dpre, M, h, H, G.Wh, 1.0f)));
+  RAU_TRY(k_colsum(ctx, dpre, B, M, M, G.bq, 1));
+  RAU_TRY(k_colsum(ctx, dpre, B, M, M, G.bh, 1));
+  return RAU_OK;
+}
+
+// ================================================================== module-level C ABI
+static int check_cfg(const rau_config* cfg) {
+  RAU_REQUIRE(cfg != nullptr, "cfg == NULL");
+  RAU_REQUIRE(cfg->V > 0 && cfg->embed > 0 && cfg->Hq > 0 && cfg->C > 0 && cfg->S > 0 && cfg->M > 0 && cfg->A > 0 &&
+                  cfg->H > 0 && cfg->N > 0 && cfg->nHop > 0 && cfg->T > 0,
+              "rau_config has a non-positive size");
+  RAU_REQUIRE(cfg->S <= 256, "S = %d > 256 grid cells is not supported by the attention kernel", cfg->S);
+  RAU_REQUIRE(cfg->nHop <= 64, "nHop = %d > 64", cfg->nHop);
+  return RAU_OK;
+}
+int rau_check_cfg(const rau_config* cfg) { return check_cfg(cfg); }
+
+int rau_check_dev(const void* p, const char* what) {
+  if (p == nullptr) { rau_set_error("%s is NULL", what); return RAU_EINVAL; }
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)) {
+    cudaGetLastError();
+    rau_set_error("%s is not a device pointer (librau has no CPU path)", what);
+    return RAU_EINVAL;
+  }
+  return RAU_OK;
+}
+
+int rau_prepare_mask(rau_ctx* ctx, uint32_t* bits, int64_t n, float p, int train, const uint8_t* bytes, uint64_t stream_id) {
+  if (!train || p <= 0.0f) return RAU_OK;
+  if (bytes) return k_mask_pack(ctx, bits, bytes, n);
+  return k_mask_gen(ctx, bits, n, p, ctx->seed, stream_id);
+}
+
+extern "C" {
+
+size_t rau_hop_saved_bytes(const rau_config* cfg, int B) {
+  if (cfg == nullptr || B <= 0) return 0;
+  return hop_saved_layout(cfg, B, nullptr, nullptr);
+}
+
+int rau_hop_fwd(rau_ctx* ctx, const rau_config* cfg, int B, const float* mult_params, const float* q, const float* X,
+                const float* c, const float* h, int train, const uint8_t* mask_q, const uint8_t* mask_x,
+                const uint8_t* mask_m, uint64_t stream_id, float* score, float* do_pred, float* p, float* c_out,
+                float* h_out, void* saved) {
+  RAU_REQUIRE(ctx, "ctx == NULL");
+  RAU_TRY(check_cfg(cfg));
+  RAU_REQUIRE(B > 0, "B = %d", B);
+  RAU_TRY(rau_check_dev(mult_params, "mult_params"));
+  RAU_TRY(rau_check_dev(q, "q")); RAU_TRY(rau_check_dev(X, "X"));
+  RAU_TRY(rau_check_dev(c, "c")); RAU_TRY(rau_check_dev(h, "h"));
+  RAU_TRY(rau_check_dev(score, "score")); RAU_TRY(rau_check_dev(c_out, "c_out"));
+  RAU_TRY(rau_check_dev(saved, "saved"));
+  RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  HopSaved sv;
+  hop_saved_layout(cfg, B, saved, &sv);
+  const int Q = 2 * cfg->Hq * cfg->nlayer;
+  RAU_TRY(rau_prepare_mask(ctx, sv.qbits, (int64_t)B * Q, cfg->p_q, train, mask_q, stream_id * 4 + 0));
+  RAU_TRY(rau_prepare_mask(ctx, sv.xbits, (int64_t)B * cfg->C * cfg->S, cfg->p_x, train, mask_x, stream_id * 4 + 1));
+  RAU_TRY(rau_prepare_mask(ctx, sv.mbits, (int64_t)B * cfg->M, cfg->p_m, train, mask_m, stream_id * 4 + 2));
+  MultT<const float*> P = mult_views<const float*, const float>(cfg, mult_params);
+  return hop_forward(ctx, cfg, B, P, q, X, c, h, train, sv, score, do_pred, p, c_out, h_out);
+}
+
+int rau_hop_bwd(rau_ctx* ctx, const rau_config* cfg, int B, const float* mult_params, float* mult_grads, const float* q,
+                const float* X, const float* c, const float* h, int train, const void* saved, const float* dscore,
+                const float* ddo_pred, const float* dp, const float* dc_out, const float* dh_out, float* dq, float* dX,
+                float* dc, float* dh) {
+  (void)q;
+  RAU_REQUIRE(ctx, "ctx == NULL");
+  RAU_TRY(check_cfg(cfg));
+  RAU_REQUIRE(B > 0, "B = %d", B);
+  RAU_TRY(rau_check_dev(mult_params, "mult_params")); RAU_TRY(rau_check_dev(mult_grads, "mult_grads"));
+  RAU_TRY(rau_check_dev(X, "X")); RAU_TRY(rau_check_dev(c, "c")); RAU_TRY(rau_check_dev(h, "h"));
+  RAU_TRY(rau_check_dev(saved, "saved")); RAU_TRY(rau_check_dev(dq, "dq"));
+  RAU_TRY(rau_check_dev(dc, "dc")); RAU_TRY(rau_check_dev(dh, "dh"));
+  RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  HopSaved sv;
+  hop_saved_layout(cfg, B, (void*)saved, &sv);
+  MultT<const float*> P = mult_views<const float*, const float>(cfg, mult_params);
+  MultT<float*> G = mult_views<float*, float>(cfg, mult_grads);
+  return hop_backward(ctx, cfg, B, P, G, X, c, h, train, sv, dscore, ddo_pred, dp, dc_out, dh_out, dq, 0, dX, dc, dh);
+}
+
+// ---------------------------------------------------------------- a1/a2: one LSTM layer step
+size_t rau_lstm_saved_bytes(const rau_lstm_desc* d) {
+  if (d == nullptr || d->B <= 0 || d->H <= 0) return 0;
+  return sizeof(float) * 5 * (size_t)d->B * d->H;
+}
+
+int rau_lstm_cell_fwd(rau_ctx* ctx, const rau_lstm_desc* d, const float* x, const float* c_prev, const float* h_prev,
+                      const float* Wi, const float* bi, const float* Wh, const float* bh, float* c, float* h,
+                      float* saved) {
+  RAU_REQUIRE(ctx && d, "ctx/desc == NULL");
+  RAU_REQUIRE(d->B > 0 && d->in_size > 0 && d->H > 0, "bad lstm desc B=%d in=%d H=%d", d->B, d->in_size, d->H);
+  RAU_REQUIRE(d->gate_order == RAU_GATES_IFOG || d->gate_order == RAU_GATES_IGFO, "bad gate order %d", d->gate_order);
+  RAU_REQUIRE(d->ldx >= d->in_size && d->ldc_prev >= d->H && d->ldh_prev >= d->H && d->ldc >= d->H && d->ldh >= d->H,
+              "lstm desc: a row pitch is smaller than its row");
+  RAU_TRY(rau_check_dev(x, "x")); RAU_TRY(rau_check_dev(c_prev, "c_prev")); RAU_TRY(rau_check_dev(h_prev, "h_prev"));
+  RAU_TRY(rau_check_dev(Wi, "Wi")); RAU_TRY(rau_check_dev(Wh, "Wh")); RAU_TRY(rau_check_dev(bi, "bi"));
+  RAU_TRY(rau_check_dev(bh, "bh")); RAU_TRY(rau_check_dev(c, "c")); RAU_TRY(rau_check_dev(h, "h"));
+  RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  ARENA(Gt, float, "lstm.G", (size_t)d->B * 4 * d->H);
+  SimtGemm g = lin_fwd(d->B, 4 * d->H, d->in_size, x, d->ldx, Wi, Gt, 4 * d->H);
+  lin_seg2(g, d->H, h_prev, d->ldh_prev, Wh);
+  g.bias_n = bi; g.bias_n2 = bh;
+  RAU_TRY(rau_contract(ctx, g));
+  return k_lstm_fwd(ctx, d->B, d->H, d->gate_order, Gt, 4 * d->H, c_prev, d->ldc_prev, c, d->ldc, h, d->ldh, nullptr, 0, saved);
+}
+
+int rau_lstm_cell_bwd(rau_ctx* ctx, const rau_lstm_desc* d, const float* x, const float* c_prev, const float* h_prev,
+                      const float* Wi, const float* Wh, const float* saved, const float* dc, const float* dh, int lddc,
+                      int lddh, const float* dh_extra, float* dx, float* dc_prev, float* dh_prev, int lddx, int lddc_prev, int lddh_prev,
+                      float* gWi, float* gbi, float* gWh, float* gbh, float scale) {
+  RAU_REQUIRE(ctx && d, "ctx/desc == NULL");
+  RAU_REQUIRE(d->B > 0 && d->in_size > 0 && d->H > 0, "bad lstm desc");
+  RAU_TRY(rau_check_dev(x, "x")); RAU_TRY(rau_check_dev(c_prev, "c_prev")); RAU_TRY(rau_check_dev(h_prev, "h_prev"));
+  RAU_TRY(rau_check_dev(Wi, "Wi")); RAU_TRY(rau_check_dev(Wh, "Wh")); RAU_TRY(rau_check_dev(saved, "saved"));
+  RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  const int B = d->B, H = d->H, in = d->in_size;
+  ARENA(dG, float, "lstm.dG", (size_t)B * 4 * H);
+  ARENA(dcp, float, "lstm.dcp", (size_t)B * H);
+  RAU_TRY(k_lstm_bwd(ctx, B, H, d->gate_order, dc, lddc, dh, lddh, dh_extra, H, nullptr, 0, nullptr, nullptr, 0, c_prev,
+                     d->ldc_prev, saved, dG, nullptr, dc_prev ? dc_prev : dcp, dc_prev ? lddc_prev : H));
+  if (dx) RAU_TRY(rau_contract(ctx, lin_dgrad(B, 4 * H, in, dG, 4 * H, Wi, dx, lddx)));
+  if (dh_prev) RAU_TRY(rau_contract(ctx, lin_dgrad(B, 4 * H, H, dG, 4 * H, Wh, dh_prev, lddh_prev)));
+  if (gWi) RAU_TRY(rau_contract(ctx, lin_wgrad(B, 4 * H, in, dG, 4 * H, x, d->ldx, gWi, scale)));
+  if (gWh) RAU_TRY(rau_contract(ctx, lin_wgrad(B, 4 * H, H, dG, 4 * H, h_prev, d->ldh_prev, gWh, scale)));
+  if (gbi || gbh) {
+    ARENA(cs, float, "lstm.cs", 4 * H);
+    RAU_TRY(k_colsum(ctx, dG, B, 4 * H, 4 * H, cs, 0));
+    if (gbi) RAU_TRY(k_axpy(ctx, scale, cs, 4 * H, gbi));
+    if (gbh) RAU_TRY(k_axpy(ctx, scale, cs, 4 * H, gbh));
+  }
+  return RAU_OK;
+}
+
+// ---------------------------------------------------------------- a3: word embedding
+int rau_embed_fwd(rau_ctx* ctx, const rau_config* cfg, int n, const float* ids, const float* E, int train,
+                  const uint8_t* mask, uint64_t stream_id, float* out) {
+  RAU_REQUIRE(ctx, "ctx == NULL");
+  RAU_TRY(check_cfg(cfg));
+  RAU_REQUIRE(n > 0, "n = %d", n);
+  RAU_TRY(rau_check_dev(ids, "ids")); RAU_TRY(rau_check_dev(E, "E")); RAU_TRY(rau_check_dev(out, "out"));
+  RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  const int64_t cnt = (int64_t)n * cfg->embed;
+  ARENA(bits, uint32_t, "embed.bits", mask_words(cnt));
+  const bool drop = train && cfg->p_embed > 0;
+  RAU_TRY(rau_prepare_mask(ctx, bits, cnt, cfg->p_embed, train, mask, stream_id));
+  return k_embed_fwd(ctx, ids, n, cfg->embed, cfg->V, E, drop ? bits : nullptr, drop_scale(cfg->p_embed), out, nullptr, 0);
+}
+
+int rau_embed_bwd(rau_ctx* ctx, const rau_config* cfg, int n, const float* ids, const float* out, int train,
+                  const uint8_t* mask, uint64_t stream_id, const float* dout, float* gE) {
+  RAU_REQUIRE(ctx, "ctx == NULL");
+  RAU_TRY(check_cfg(cfg));
+  RAU_REQUIRE(n > 0, "n = %d", n);
+  RAU_TRY(rau_check_dev(ids, "ids")); RAU_TRY(rau_check_dev(out, "out"));
+  RAU_TRY(rau_check_dev(dout, "dout")); RAU_TRY(rau_check_dev(gE, "gE"));
+  RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  const int64_t cnt = (int64_t)n * cfg->embed;
+  ARENA(bits, uint32_t, "embed.bits", mask_words(cnt));
+  const bool drop = train && cfg->p_embed > 0;
+  RAU_TRY(rau_prepare_mask(ctx, bits, cnt, cfg->p_embed, train, mask, stream_id));   // Philox: same stream => same mask
+  return k_embed_bwd(ctx, ids, n, cfg->embed, cfg->V, out, drop ? bits : nullptr, drop_scale(cfg->p_embed), dout,
+                     cfg->embed, gE);
+}
+
+int rau_dropout(rau_ctx* ctx, int64_t n, const float* x, float p, int train, const uint8_t* mask, uint64_t stream_id,
+                float* y) {
+  RAU_REQUIRE(ctx, "ctx == NULL");
+  RAU_REQUIRE(n > 0 && p >= 0.0f && p < 1.0f, "bad dropout arguments n=%lld p=%f", (long long)n, p);
+  RAU_TRY(rau_check_dev(x, "x")); RAU_TRY(rau_check_dev(y, "y"));
+  RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  ARENA(bits, uint32_t, "dropout.bits", mask_words(n));
+  const bool drop = train && p > 0;
+  RAU_TRY(rau_prepare_mask(ctx, bits, n, p, train, mask, stream_id));
+  return k_dropout_bwd_acc(ctx, x, n, drop ? bits : nullptr, drop_scale(p), y, 0);
+}
+
+// ---------------------------------------------------------------- building blocks
+int rau_gemm(rau_ctx* ctx, int M, int N, int K, const float* A, int lda, int ta, const float* B, int ldb, int tb,
+             float* C, int ldc, int accumulate) {
+  RAU_REQUIRE(ctx, "ctx == NULL");
+  RAU_REQUIRE(M > 0 && N > 0 && K > 0, "bad gemm shape %dx%dx%d", M, N, K);
+  RAU_TRY(rau_check_dev(A, "A")); RAU_TRY(rau_check_dev(B, "B")); RAU_TRY(rau_check_dev(C, "C"));
+  RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  SimtGemm g;
+  g.M = M; g.N = N; g.K = K;
+  g.A = A; g.sam = ta ? 1 : lda; g.sak = ta ? lda : 1;
+  g.B = B; g.sbn = tb ? 1 : ldb; g.sbk = tb ? ldb : 1;
+  g.C = C; g.scm = ldc; g.scn = 1;
+  g.accumulate = accumulate;
+  return rau_contract(ctx, g);
+}
+
+int rau_softmax_ce(rau_ctx* ctx, int B, int N, const float* score, const float* labels, float scale, float* loss_sum,
+                   float* dscore, float* answers) {
+  RAU_REQUIRE(ctx, "ctx == NULL");
+  RAU_REQUIRE(B > 0 && N > 0, "bad shape");
+  RAU_TRY(rau_check_dev(score, "score")); RAU_TRY(rau_check_dev(labels, "labels"));
+  RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  return k_softmax_ce(ctx, B, N, score, labels, scale, scale, loss_sum, dscore, nullptr, 0, answers);
+}
+
+}  // extern "C"

@@ -1,0 +1,59 @@
+// rau_model.cuh -- internal interfaces between the orchestration files.
+#pragma once
+#include "rau_kernels.cuh"
+#include "rau_layout.cuh"
+
+// contraction front-end: routes a SimtGemm description to the tcgen05 engine (k_gemm_tc.cu) when the
+// ctx precision mode and the operand shapes allow it, else to the fp32 CUDA-core engine (k_gemm_simt.cu).
+int rau_contract(rau_ctx* ctx, const SimtGemm& g);
+// k_gemm_tc.cu: returns 1 when it ran the product on tcgen05, 0 when the shape is not eligible, <0 on error
+int tc_gemm_try(rau_ctx* ctx, const SimtGemm& g);
+
+// nn.Linear helpers over row-major activations [rows, *] and weights [N, K]
+static inline SimtGemm lin_fwd(int rows, int N, int K, const float* X, int ldx, const float* W, float* Y, int ldy) {
+  SimtGemm g;
+  g.M = rows; g.N = N; g.K = K;
+  g.A = X; g.sam = ldx; g.sak = 1;
+  g.B = W; g.sbk = 1; g.sbn = K;
+  g.C = Y; g.scm = ldy; g.scn = 1;
+  return g;
+}
+static inline void lin_seg2(SimtGemm& g, int K2, const float* X2, int ldx2, const float* W2) {
+  g.A2 = X2; g.sam2 = ldx2; g.sak2 = 1;
+  g.B2 = W2; g.sbk2 = 1; g.sbn2 = K2; g.K2 = K2;
+}
+// dX[rows,K] = dY[rows,N] W[N,K]
+static inline SimtGemm lin_dgrad(int rows, int N, int K, const float* dY, int lddy, const float* W, float* dX, int lddx) {
+  SimtGemm g;
+  g.M = rows; g.N = K; g.K = N;
+  g.A = dY; g.sam = lddy; g.sak = 1;
+  g.B = W; g.sbk = K; g.sbn = 1;
+  g.C = dX; g.scm = lddx; g.scn = 1;
+  return g;
+}
+// gW[N,K] += scale * dY[rows,N]^T X[rows,K]
+static inline SimtGemm lin_wgrad(int rows, int N, int K, const float* dY, int lddy, const float* X, int ldx, float* gW, float scale) {
+  SimtGemm g;
+  g.M = N; g.N = K; g.K = rows;
+  g.A = dY; g.sam = 1; g.sak = lddy;
+  g.B = X; g.sbk = ldx; g.sbn = 1;
+  g.C = gW; g.scm = K; g.scn = 1;
+  g.accumulate = 1;
+  g.alpha = scale;
+  return g;
+}
+
+// activations one answering unit keeps for its backward pass (carved out of one caller- or arena-owned block)
+struct HopSaved {
+  uint32_t *qbits, *xbits, *mbits;   // packed keep bits of the three dropouts (F:233, F:239, F:277)
+  float *qd, *qf, *I, *E, *p, *j, *lsav, *hout, *m, *dop;
+};
+size_t hop_saved_layout(const rau_config* cfg, int B, void* base, HopSaved* sv);
+
+int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const float*>& P,
+                const float* q, const float* X, const float* c, const float* h, int train, const HopSaved& sv,
+                float* score, float* do_pred, float* p_out, float* c_out, float* h_out);
+int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const float*>& P, const MultT<float*>& G,
+                 const float* X, const float* c, const float* h, int train, const HopSaved& sv,
+                 const float* dscore, const float* ddo_pred, const float* dp_att, const float* dc_out, const float* dh_out,
+                 float* dq, int dq_accumulate, float* dX, float* dc, float* dh);

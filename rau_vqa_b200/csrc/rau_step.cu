@@ -1,0 +1,399 @@
+// rau_step.cu -- the training step of the experiment scripts as device work enqueued on one stream:
+//   rau_feval      = feval (F:445-615): encoder unroll, nHop answering units, joint loss, BPTT
+//   rau_noise_clip = gradient noise + per-group clip (F:617-648)
+//   rau_optim_step = utils/optim_updates.lua (OU:7-87)
+//   rau_train_step = feval -> [all-reduce] -> noise/clip -> optimizer x3 (F:786-791)
+//   rau_predict    = predict_result (F:652-724)
+// Differences from the reference's schedule that do not change results: the layer-1 and layer-2 input
+// projections of the encoder are hoisted out of the time loop (one [T*B,in]x[in,4H] product each), the
+// per-row "select the state at t == len" host loops (F:472-478, F:604-610) are device kernels, the encoder's
+// weight gradients are single contractions over all T*B rows, and dX of the image features is never formed.
+#include "rau_model.cuh"
+
+int rau_check_cfg(const rau_config* cfg);
+int rau_check_dev(const void* p, const char* what);
+int rau_prepare_mask(rau_ctx* ctx, uint32_t* bits, int64_t n, float p, int train, const uint8_t* bytes, uint64_t stream_id);
+int rau_allreduce_internal(rau_ctx* ctx, float* buf, int64_t n);   // rau_comm.cu
+bool rau_comm_attached(rau_ctx* ctx);
+int rau_comm_rank(rau_ctx* ctx);
+
+#define ARENA(ptr, type, name, count) \
+  type* ptr = nullptr;                \
+  RAU_TRY(ctx->arena.get(name, sizeof(type) * (size_t)(count), (void**)&ptr))
+
+static inline float drop_scale(float p) { return p > 0.0f ? 1.0f / (1.0f - p) : 1.0f; }
+
+// Philox stream ids: [step:40][kind:8][index:16]; dropout streams are offset per rank, noise streams are not
+static inline uint64_t stream_of(int64_t step, int kind, int idx, int rank) {
+  return ((uint64_t)step << 24) ^ ((uint64_t)kind << 16) ^ (uint64_t)idx ^ ((uint64_t)rank << 56);
+}
+enum { SK_EMBED = 1, SK_RNN = 2, SK_Q = 3, SK_X = 4, SK_M = 5, SK_NOISE = 9 };
+
+struct Encoder {
+  int B, Tm;          // batch, number of unrolled steps
+  uint32_t *ebits, *rbits;
+  float *e_all, *G1x, *G2x, *u2, *S_all, *sav1, *sav2, *Gt, *rnn_out;
+};
+
+static int encoder_alloc(rau_ctx* ctx, const rau_config* cfg, int B, Encoder* en) {
+  const int T = cfg->T, Hq = cfg->Hq, E = cfg->embed, Q = 4 * Hq;
+  ARENA(ebits, uint32_t, "enc.ebits", mask_words((int64_t)T * B * E));
+  ARENA(rbits, uint32_t, "enc.rbits", mask_words((int64_t)T * B * Hq));
+  ARENA(e_all, float, "enc.e", (size_t)T * B * E);
+  ARENA(G1x, float, "enc.G1x", (size_t)T * B * 4 * Hq);
+  ARENA(G2x, float, "enc.G2x", (size_t)T * B * 4 * Hq);
+  ARENA(u2, float, "enc.u2", (size_t)T * B * Hq);
+  ARENA(S_all, float, "enc.S", (size_t)(T + 1) * B * Q);
+  ARENA(sav1, float, "enc.sav1", (size_t)T * 5 * B * Hq);
+  ARENA(sav2, float, "enc.sav2", (size_t)T * 5 * B * Hq);
+  ARENA(Gt, float, "enc.G", (size_t)B * 4 * Hq);
+  ARENA(rnn_out, float, "enc.out", (size_t)B * Q);
+  en->B = B; en->ebits = ebits; en->rbits = rbits; en->e_all = e_all; en->G1x = G1x; en->G2x = G2x; en->u2 = u2;
+  en->S_all = S_all; en->sav1 = sav1; en->sav2 = sav2; en->Gt = Gt; en->rnn_out = rnn_out;
+  return RAU_OK;
+}
+
+// F:460-479.  State rows are [c1|h1|c2|h2] (D:23-24, D:68); S_all[t] is the state after step t, S_all[0] = 0.
+static int encoder_forward(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, const float* Pe, const float* Pr,
+                           int train, const rau_masks* masks, int64_t step_t, Encoder* en) {
+  const int B = bt->B, Hq = cfg->Hq, E = cfg->embed, Q = 4 * Hq, G4 = 4 * Hq;
+  const int Tm = (bt->max_len > 0 && bt->max_len <= cfg->T) ? bt->max_len : cfg->T;
+  en->Tm = Tm;
+  RnnLayerOff L[4];
+  rnn_offsets(cfg, L);
+  const int rank = rau_comm_rank(ctx);
+  const bool de = train && cfg->p_embed > 0, dr = train && cfg->p_rnn > 0;
+  RAU_TRY(rau_prepare_mask(ctx, en->ebits, (int64_t)Tm * B * E, cfg->p_embed, train, masks ? masks->embed : nullptr,
+                           stream_of(step_t, SK_EMBED, 0, rank)));
+  RAU_TRY(rau_prepare_mask(ctx, en->rbits, (int64_t)Tm * B * Hq, cfg->p_rnn, train, masks ? masks->rnn : nullptr,
+                           stream_of(step_t, SK_RNN, 0, rank)));
+  // word_embed for every step at once (F:203-206, F:468)
+  RAU_TRY(k_embed_fwd(ctx, bt->tokens, Tm * B, E, cfg->V, Pe, de ? en->ebits : nullptr, drop_scale(cfg->p_embed),
+                      en->e_all, nullptr, 0));
+  // layer 1 input projection hoisted over time: G1x = e Wi1^T + bi1 + bh1
+  {
+    SimtGemm g = lin_fwd(Tm * B, G4, E, en->e_all, E, Pr + L[0].Wi, en->G1x, G4);
+    g.bias_n = Pr + L[0].bi; g.bias_n2 = Pr + L[0].bh;
+    RAU_TRY(rau_contract(ctx, g));
+  }
+  RAU_TRY(k_fill(ctx, en->S_all, (int64_t)B * Q, 0.0f));
+  for (int t = 1; t <= Tm; ++t) {   // layer 1 recurrence
+    float* Sp_ = en->S_all + (size_t)(t - 1) * B * Q;
+    float* Sn = en->S_all + (size_t)t * B * Q;
+    SimtGemm g = lin_fwd(B, G4, Hq, Sp_ + Hq, Q, Pr + L[0].Wh, en->Gt, G4);
+    g.addend = en->G1x + (size_t)(t - 1) * B * G4; g.sdm = G4; g.sdn = 1;
+    RAU_TRY(rau_contract(ctx, g));
+    RAU_TRY(k_lstm_fwd(ctx, B, Hq, RAU_GATES_IFOG, en->Gt, G4, Sp_, Q, Sn, Q, Sn + Hq, Q, nullptr, 0,
+                       en->sav1 + (size_t)(t - 1) * 5 * B * Hq));
+  }
+  // u2 = drop(h1) for every step (D:38-39), then the layer-2 input projection hoisted over time
+  RAU_TRY(k_dropout(ctx, en->S_all + (size_t)B * Q + Hq, (int64_t)Tm * B, Hq, Q, dr ? en->rbits : nullptr,
+                    drop_scale(cfg->p_rnn), en->u2, Hq, nullptr, 0, Hq));
+  {
+    SimtGemm g = lin_fwd(Tm * B, G4, Hq, en->u2, Hq, Pr + L[1].Wi, en->G2x, G4);
+    g.bias_n = Pr + L[1].bi; g.bias_n2 = Pr + L[1].bh;
+    RAU_TRY(rau_contract(ctx, g));
+  }
+  for (int t = 1; t <= Tm; ++t) {   // layer 2 recurrence
+    float* Sp_ = en->S_all + (size_t)(t - 1) * B * Q;
+    float* Sn = en->S_all + (size_t)t * B * Q;
+    SimtGemm g = lin_fwd(B, G4, Hq, Sp_ + 3 * Hq, Q, Pr + L[1].Wh, en->Gt, G4);
+    g.addend = en->G2x + (size_t)(t - 1) * B * G4; g.sdm = G4; g.sdn = 1;
+    RAU_TRY(rau_contract(ctx, g));
+    RAU_TRY(k_lstm_fwd(ctx, B, Hq, RAU_GATES_IFOG, en->Gt, G4, Sp_ + 2 * Hq, Q, Sn + 2 * Hq, Q, Sn + 3 * Hq, Q, nullptr, 0,
+                       en->sav2 + (size_t)(t - 1) * 5 * B * Hq));
+  }
+  // rnn_out[k] = state at t == x_len[k] (F:472-478)
+  RAU_TRY(k_select_state(ctx, en->S_all, Tm, B, Q, bt->lengths, en->rnn_out));
+  return RAU_OK;
+}
+
+// F:600-615 with dq = sum over hops of the answering units' gradient w.r.t. rnn_out (branch:backward, F:598)
+static int encoder_backward(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, const float* Pr, float* gE,
+                            float* gR, int train, const Encoder* en, const float* dq) {
+  const int B = bt->B, Hq = cfg->Hq, E = cfg->embed, Q = 4 * Hq, G4 = 4 * Hq, Tm = en->Tm;
+  RnnLayerOff L[4];
+  rnn_offsets(cfg, L);
+  const bool de = train && cfg->p_embed > 0, dr = train && cfg->p_rnn > 0;
+  ARENA(dG1, float, "encb.dG1", (size_t)cfg->T * B * G4);
+  ARENA(dG2, float, "encb.dG2", (size_t)cfg->T * B * G4);
+  ARENA(dC, float, "encb.dC", (size_t)B * Hq);
+  ARENA(dH, float, "encb.dH", (size_t)B * Hq);
+  ARENA(du2, float, "encb.du2", (size_t)cfg->T * B * Hq);
+  ARENA(de_all, float, "encb.de", (size_t)cfg->T * B * E);
+  // layer 2, t = Tm..1
+  for (int t = Tm; t >= 1; --t) {
+    const bool last = t == Tm;
+    const float* Sp_ = en->S_all + (size_t)(t - 1) * B * Q;
+    float* dGt = dG2 + (size_t)(t - 1) * B * G4;
+    RAU_TRY(k_lstm_bwd(ctx, B, Hq, RAU_GATES_IFOG, last ? nullptr : dC, Hq, last ? nullptr : dH, Hq, nullptr, 0,
+                       bt->lengths, t, dq + 2 * Hq, dq + 3 * Hq, Q, Sp_ + 2 * Hq, Q,
+                       en->sav2 + (size_t)(t - 1) * 5 * B * Hq, dGt, nullptr, dC, Hq));
+    if (t > 1) RAU_TRY(rau_contract(ctx, lin_dgrad(B, G4, Hq, dGt, G4, Pr + L[1].Wh, dH, Hq)));
+  }
+  // gradient into h1 through layer 2's input, all steps at once: du2 = (dG2 Wi2) * mask
+  RAU_TRY(rau_contract(ctx, lin_dgrad(Tm * B, G4, Hq, dG2, G4, Pr + L[1].Wi, du2, Hq)));
+  RAU_TRY(k_dropout_bwd_acc(ctx, du2, (int64_t)Tm * B * Hq, dr ? en->rbits : nullptr, drop_scale(cfg->p_rnn), du2, 0));
+  // layer 1, t = Tm..1
+  for (int t = Tm; t >= 1; --t) {
+    const bool last = t == Tm;
+    const float* Sp_ = en->S_all + (size_t)(t - 1) * B * Q;
+    float* dGt = dG1 + (size_t)(t - 1) * B * G4;
+    RAU_TRY(k_lstm_bwd(ctx, B, Hq, RAU_GATES_IFOG, last ? nullptr : dC, Hq, last ? nullptr : dH, Hq,
+                       du2 + (size_t)(t - 1) * B * Hq, Hq, bt->lengths, t, dq, dq + Hq, Q, Sp_, Q,
+                       en->sav1 + (size_t)(t - 1) * 5 * B * Hq, dGt, nullptr, dC, Hq));
+    if (t > 1) RAU_TRY(rau_contract(ctx, lin_dgrad(B, G4, Hq, dGt, G4, Pr + L[0].Wh, dH, Hq)));
+  }
+  // word embedding: de = dG1 Wi1 for all steps, scatter-add into gE (LookupTable accGradParameters)
+  RAU_TRY(rau_contract(ctx, lin_dgrad(Tm * B, G4, E, dG1, G4, Pr + L[0].Wi, de_all, E)));
+  RAU_TRY(k_embed_bwd(ctx, bt->tokens, Tm * B, E, cfg->V, en->e_all, de ? en->ebits : nullptr, drop_scale(cfg->p_embed),
+                      de_all, E, gE));
+  // weight gradients as single contractions over all Tm*B rows
+  const int R = Tm * B;
+  const int ks = R >= 2048 ? 8 : (R >= 512 ? 4 : 1);
+  auto wg = [&](const float* dG, const float* Xin, int ldx, int K, float* gW) {
+    SimtGemm g = lin_wgrad(R, G4, K, dG, G4, Xin, ldx, gW, 1.0f);
+    g.ksplit = ks;
+    return rau_contract(ctx, g);
+  };
+  RAU_TRY(wg(dG1, en->e_all, E, E, gR + L[0].Wi));
+  RAU_TRY(wg(dG1, en->S_all + Hq, Q, Hq, gR + L[0].Wh));          // h1 of the previous step
+  RAU_TRY(wg(dG2, en->u2, Hq, Hq, gR + L[1].Wi));
+  RAU_TRY(wg(dG2, en->S_all + 3 * Hq, Q, Hq, gR + L[1].Wh));      // h2 of the previous step
+  RAU_TRY(k_colsum(ctx, dG1, R, G4, G4, gR + L[0].bi, 1));
+  RAU_TRY(k_colsum(ctx, dG1, R, G4, G4, gR + L[0].bh, 1));
+  RAU_TRY(k_colsum(ctx, dG2, R, G4, G4, gR + L[1].bi, 1));
+  RAU_TRY(k_colsum(ctx, dG2, R, G4, G4, gR + L[1].bh, 1));
+  return RAU_OK;
+}
+
+static int check_batch(const rau_config* cfg, const rau_batch* bt) {
+  RAU_REQUIRE(bt != nullptr, "batch == NULL");
+  RAU_REQUIRE(bt->B > 0, "batch size %d", bt->B);
+  RAU_REQUIRE(bt->max_len >= 0 && bt->max_len <= cfg->T, "max_len %d outside [0, T=%d]", bt->max_len, cfg->T);
+  RAU_TRY(rau_check_dev(bt->feats, "batch.feats"));
+  RAU_TRY(rau_check_dev(bt->tokens, "batch.tokens"));
+  RAU_TRY(rau_check_dev(bt->lengths, "batch.lengths"));
+  return RAU_OK;
+}
+
+extern "C" {
+
+int rau_feval(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float* const params[3], float* const grads[3],
+              const float* hop_mask, const rau_masks* masks, int64_t step_t, const rau_step_out* out) {
+  RAU_REQUIRE(ctx, "ctx == NULL");
+  RAU_TRY(rau_check_cfg(cfg));
+  RAU_REQUIRE(cfg->nlayer == 2, "the fused encoder supports nlayer == 2 (F:209), got %d", cfg->nlayer);
+  RAU_TRY(check_batch(cfg, bt));
+  RAU_TRY(rau_check_dev(bt->labels, "batch.labels"));
+  RAU_REQUIRE(params && grads, "params/grads == NULL");
+  for (int g = 0; g < 3; ++g) {
+    RAU_TRY(rau_check_dev(params[g], "params[g]"));
+    RAU_TRY(rau_check_dev(grads[g], "grads[g]"));
+  }
+  RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  const int B = bt->B, nHop = cfg->nHop, N = cfg->N, S = cfg->S, H = cfg->H, Q = 4 * cfg->Hq;
+  const int Bg = bt->B_global > 0 ? bt->B_global : B;
+  const int rank = rau_comm_rank(ctx);
+  const int train = 1;
+
+  for (int g = 0; g < 3; ++g)   // F:446-448
+    RAU_TRY(k_fill(ctx, grads[g], rau_group_size(cfg, g), 0.0f));
+
+  Encoder en;
+  RAU_TRY(encoder_alloc(ctx, cfg, B, &en));
+  RAU_TRY(encoder_forward(ctx, cfg, bt, params[0], params[1], train, masks, step_t, &en));
+
+  // answering units (F:495-537)
+  const size_t sv_bytes = hop_saved_layout(cfg, B, nullptr, nullptr);
+  ARENA(sv_base, char, "step.saved", sv_bytes * nHop);
+  ARENA(c_all, float, "step.c", (size_t)(nHop + 1) * B * H);
+  ARENA(h_all, float, "step.h", (size_t)(nHop + 1) * B * H);
+  ARENA(scores_own, float, "step.scores", (size_t)nHop * B * N);
+  ARENA(dscore, float, "step.dscore", (size_t)nHop * B * N);
+  ARENA(dop_own, float, "step.dop", (size_t)nHop * B);
+  ARENA(att_own, float, "step.att", (size_t)nHop * B * S);
+  ARENA(ans_own, float, "step.ans", (size_t)(nHop + 2) * B);
+  ARENA(loss_own, float, "step.loss", 2 * nHop + 2);
+  float* scores = (out && out->scores) ? out->scores : scores_own;
+  float* dop = (out && out->do_pred) ? out->do_pred : dop_own;
+  float* att = (out && out->attprob) ? out->attprob : att_own;
+  float* ans = (out && out->answers) ? out->answers : ans_own;
+  float* loss = (out && out->loss) ? out->loss : loss_own;
+  float* loss_dp = (out && out->loss_do_pred) ? out->loss_do_pred : loss_own + nHop + 2;
+  RAU_TRY(k_fill(ctx, c_all, (int64_t)B * H, 0.0f));   // F:362-364
+  RAU_TRY(k_fill(ctx, h_all, (int64_t)B * H, 0.0f));
+  RAU_TRY(k_fill(ctx, loss, nHop + 2, 0.0f));
+  RAU_TRY(k_fill(ctx, loss_dp, nHop, 0.0f));
+  MultT<const float*> P = mult_views<const float*, const float>(cfg, params[2]);
+  MultT<float*> G = mult_views<float*, float>(cfg, grads[2]);
+  std::vector<HopSaved> sv(nHop);
+  for (int hp = 0; hp < nHop; ++hp) {
+    hop_saved_layout(cfg, B, sv_base + sv_bytes * hp, &sv[hp]);
+    RAU_TRY(rau_prepare_mask(ctx, sv[hp].qbits, (int64_t)B * Q, cfg->p_q, train,
+                             masks && masks->q ? masks->q + (size_t)hp * B * Q : nullptr, stream_of(step_t, SK_Q, hp, rank)));
+    RAU_TRY(rau_prepare_mask(ctx, sv[hp].xbits, (int64_t)B * cfg->C * S, cfg->p_x, train,
+                             masks && masks->x ? masks->x + (size_t)hp * B * cfg->C * S : nullptr,
+                             stream_of(step_t, SK_X, hp, rank)));
+    RAU_TRY(rau_prepare_mask(ctx, sv[hp].mbits, (int64_t)B * cfg->M, cfg->p_m, train,
+                             masks && masks->m ? masks->m + (size_t)hp * B * cfg->M : nullptr,
+                             stream_of(step_t, SK_M, hp, rank)));
+    RAU_TRY(hop_forward(ctx, cfg, B, P, en.rnn_out, bt->feats, c_all + (size_t)hp * B * H, h_all + (size_t)hp * B * H, train,
+                        sv[hp], scores + (size_t)hp * B * N, dop + (size_t)hp * B, att + (size_t)hp * B * S,
+                        c_all + (size_t)(hp + 1) * B * H, h_all + (size_t)(hp + 1) * B * H));
+    // criterion forward + backward + argmax in one pass (F:505, F:535, F:585-589)
+    const float hm = hop_mask ? hop_mask[hp] : 1.0f;
+    RAU_TRY(k_softmax_ce(ctx, B, N, scores + (size_t)hp * B * N, bt->labels, 1.0f / Bg, hm / Bg, loss + hp,
+                         dscore + (size_t)hp * B * N, nullptr, 0, ans + (size_t)hp * B));
+  }
+  // logging-only losses on the averaged / selected predictions and the do_pred BCE (F:539-574)
+  RAU_TRY(k_merge_preds(ctx, nHop, B, N, S, scores, dop, nullptr, bt->labels, ans, 0, 1.0f / Bg, loss + nHop, loss_dp,
+                        ans + (size_t)nHop * B, nullptr, nullptr, nullptr, nullptr));
+
+  // BPTT through the hops (F:578-597); do_pred and attprob receive zero gradient (F:582-583, F:592)
+  ARENA(dcs, float, "step.dc", (size_t)2 * B * H);
+  ARENA(dhs, float, "step.dh", (size_t)2 * B * H);
+  ARENA(dq, float, "step.dq", (size_t)B * Q);
+  for (int hp = nHop - 1; hp >= 0; --hp) {
+    const bool last = hp == nHop - 1;
+    const float* dc_in = last ? nullptr : dcs + (size_t)((hp + 1) & 1) * B * H;
+    const float* dh_in = last ? nullptr : dhs + (size_t)((hp + 1) & 1) * B * H;
+    RAU_TRY(hop_backward(ctx, cfg, B, P, G, bt->feats, c_all + (size_t)hp * B * H, h_all + (size_t)hp * B * H, train, sv[hp],
+                         dscore + (size_t)hp * B * N, nullptr, nullptr, dc_in, dh_in, dq, last ? 0 : 1, nullptr,
+                         dcs + (size_t)(hp & 1) * B * H, dhs + (size_t)(hp & 1) * B * H));
+  }
+  RAU_TRY(encoder_backward(ctx, cfg, bt, params[1], grads[0], grads[1], train, &en, dq));
+  (void)out;
+  return RAU_OK;
+}
+
+int rau_noise_clip(rau_ctx* ctx, const rau_config* cfg, float* const grads[3], int64_t step_t, float eta, float gamma,
+                   float clip, const float* const noise_override[3], float* norms) {
+  RAU_REQUIRE(ctx, "ctx == NULL");
+  RAU_TRY(rau_check_cfg(cfg));
+  RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  ARENA(norm2, double, "opt.norm2", 4);
+  RAU_CHECK_CUDA(cudaMemsetAsync(norm2, 0, sizeof(double) * 4, ctx->stream));
+  const float std_ = (eta > 0.0f && gamma > 0.0f) ? sqrtf(eta / ((float)(step_t + 1) * gamma)) : 0.0f;   // F:617-618
+  for (int g = 0; g < 3; ++g) {
+    RAU_TRY(rau_check_dev(grads[g], "grads[g]"));
+    const int64_t n = rau_group_size(cfg, g);
+    RAU_TRY(k_noise_norm(ctx, grads[g], n, std_, noise_override ? noise_override[g] : nullptr, ctx->seed,
+                         stream_of(step_t, SK_NOISE, g, 0), norm2 + g));
+  }
+  for (int g = 0; g < 3; ++g)
+    RAU_TRY(k_clip_optim(ctx, -1, rau_group_size(cfg, g), nullptr, grads[g], norm2 + g, clip, 0, 0, 0, 0, nullptr, nullptr, 0,
+                         norms ? norms + g : nullptr));
+  return RAU_OK;
+}
+
+int rau_optim_step(rau_ctx* ctx, int optim, int64_t n, float* x, const float* dx, float lr, float h0, float h1, float h2,
+                   float* state0, float* state1, int64_t t) {
+  RAU_REQUIRE(ctx, "ctx == NULL");
+  RAU_REQUIRE(optim >= RAU_OPT_SGD && optim <= RAU_OPT_ADAM, "unknown optimizer %d", optim);
+  RAU_REQUIRE(n > 0, "n = %lld", (long long)n);
+  RAU_TRY(rau_check_dev(x, "x")); RAU_TRY(rau_check_dev(dx, "dx"));
+  if (optim != RAU_OPT_SGD) RAU_TRY(rau_check_dev(state0, "state0"));
+  if (optim == RAU_OPT_ADAM) RAU_TRY(rau_check_dev(state1, "state1"));
+  RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  return k_clip_optim(ctx, optim, n, x, (float*)dx, nullptr, 0.0f, lr, h0, h1, h2, state0, state1, t, nullptr);
+}
+
+int rau_train_step(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float* const params[3], float* const grads[3],
+                   float* const opt_state[3][2], const float* hop_mask, const rau_masks* masks, int64_t step_t,
+                   const rau_train_hparams* hp, const rau_step_out* out) {
+  RAU_REQUIRE(hp != nullptr, "hparams == NULL");
+  RAU_REQUIRE(hp->optim >= RAU_OPT_SGD && hp->optim <= RAU_OPT_ADAM, "unknown optimizer %d", hp->optim);
+  RAU_TRY(rau_feval(ctx, cfg, bt, params, grads, hop_mask, masks, step_t, out));
+  if (rau_comm_attached(ctx)) {   // data parallel: one sum over ranks of each flat gradient
+    for (int g = 0; g < 3; ++g) RAU_TRY(rau_allreduce_internal(ctx, grads[g], rau_group_size(cfg, g)));
+    if (out && out->loss) RAU_TRY(rau_allreduce_internal(ctx, out->loss, cfg->nHop + 2));
+    if (out && out->loss_do_pred) RAU_TRY(rau_allreduce_internal(ctx, out->loss_do_pred, cfg->nHop));
+  }
+  ARENA(norm2, double, "opt.norm2", 4);
+  RAU_CHECK_CUDA(cudaMemsetAsync(norm2, 0, sizeof(double) * 4, ctx->stream));
+  const float std_ = (hp->eta > 0.0f && hp->gamma > 0.0f) ? sqrtf(hp->eta / ((float)(step_t + 1) * hp->gamma)) : 0.0f;
+  for (int g = 0; g < 3; ++g)
+    RAU_TRY(k_noise_norm(ctx, grads[g], rau_group_size(cfg, g), std_, hp->noise_override ? hp->noise_override[g] : nullptr,
+                         ctx->seed, stream_of(step_t, SK_NOISE, g, 0), norm2 + g));
+  for (int g = 0; g < 3; ++g)   // F:788-790: adam(embed, lr) adam(rnn, lr) adam(mult, multlr); t counts from 1
+    RAU_TRY(k_clip_optim(ctx, hp->optim, rau_group_size(cfg, g), params[g], grads[g], norm2 + g, hp->clip, hp->lr[g], hp->h0,
+                         hp->h1, hp->h2, opt_state ? opt_state[g][0] : nullptr, opt_state ? opt_state[g][1] : nullptr,
+                         step_t + 1, (out && out->norms) ? out->norms + g : nullptr));
+  return RAU_OK;
+}
+
+int rau_predict(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float* const params[3], float* pred, float* att) {
+  RAU_REQUIRE(ctx, "ctx == NULL");
+  RAU_TRY(rau_check_cfg(cfg));
+  RAU_REQUIRE(cfg->nlayer == 2, "the fused encoder supports nlayer == 2 (F:209), got %d", cfg->nlayer);
+  RAU_TRY(check_batch(cfg, bt));
+  RAU_TRY(rau_check_dev(pred, "pred"));
+  for (int g = 0; g < 3; ++g) RAU_TRY(rau_check_dev(params[g], "params[g]"));
+  RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  const int B = bt->B, nHop = cfg->nHop, N = cfg->N, S = cfg->S, H = cfg->H;
+  Encoder en;
+  RAU_TRY(encoder_alloc(ctx, cfg, B, &en));
+  RAU_TRY(encoder_forward(ctx, cfg, bt, params[0], params[1], 0, nullptr, 0, &en));
+  const size_t sv_bytes = hop_saved_layout(cfg, B, nullptr, nullptr);
+  ARENA(sv_base, char, "step.saved", sv_bytes);
+  ARENA(c_all, float, "step.c", (size_t)2 * B * H);
+  ARENA(h_all, float, "step.h", (size_t)2 * B * H);
+  ARENA(dop, float, "step.dop", (size_t)nHop * B);
+  ARENA(att_own, float, "step.att", (size_t)(nHop + 2) * B * S);
+  float* attp = att ? att : att_own;
+  RAU_TRY(k_fill(ctx, c_all, (int64_t)B * H, 0.0f));
+  RAU_TRY(k_fill(ctx, h_all, (int64_t)B * H, 0.0f));
+  MultT<const float*> P = mult_views<const float*, const float>(cfg, params[2]);
+  HopSaved sv;
+  hop_saved_layout(cfg, B, sv_base, &sv);
+  for (int hp = 0; hp < nHop; ++hp)
+    RAU_TRY(hop_forward(ctx, cfg, B, P, en.rnn_out, bt->feats, c_all + (size_t)(hp & 1) * B * H, h_all + (size_t)(hp & 1) * B * H,
+                        0, sv, pred + (size_t)hp * B * N, dop + (size_t)hp * B, attp + (size_t)hp * B * S,
+                        c_all + (size_t)((hp + 1) & 1) * B * H, h_all + (size_t)((hp + 1) & 1) * B * H));
+  // uni = mean over hops, select = first hop with do_pred > 0.5, forced at the last hop (F:699-721)
+  RAU_TRY(k_merge_preds(ctx, nHop, B, N, S, pred, dop, attp, nullptr, nullptr, 1, 0.0f, nullptr, nullptr, nullptr,
+                        pred + (size_t)nHop * B * N, pred + (size_t)(nHop + 1) * B * N, attp + (size_t)nHop * B * S,
+                        attp + (size_t)(nHop + 1) * B * S));
+  return RAU_OK;
+}
+
+int rau_time_iembed(rau_ctx* ctx, const rau_config* cfg, int B, const float* mult_params, const float* X, int iters,
+                    float* ms_per_launch) {
+  RAU_REQUIRE(ctx && ms_per_launch, "ctx/ms == NULL");
+  RAU_TRY(rau_check_cfg(cfg));
+  RAU_REQUIRE(B > 0 && iters > 0, "B=%d iters=%d", B, iters);
+  RAU_TRY(rau_check_dev(mult_params, "mult_params")); RAU_TRY(rau_check_dev(X, "X"));
+  RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  const int Sp = rau_sp(cfg->S), M = cfg->M, C = cfg->C, S = cfg->S;
+  ARENA(Xd, float, "hop.Xd", (size_t)B * C * Sp);
+  ARENA(I, float, "time.I", (size_t)B * M * Sp);
+  MultT<const float*> P = mult_views<const float*, const float>(cfg, mult_params);
+  RAU_TRY(k_dropout(ctx, X, (int64_t)B * C, S, S, nullptr, 1.0f, Xd, Sp, nullptr, 0, Sp));
+  SimtGemm g;
+  g.M = M; g.N = Sp; g.K = C;
+  g.A = P.Wi; g.sam = C; g.sak = 1;
+  g.B = Xd; g.sbk = Sp; g.sbn = 1; g.bB = (int64_t)C * Sp;
+  g.C = I; g.scm = Sp; g.scn = 1; g.bC = (int64_t)M * Sp;
+  g.batch = B; g.bias_m = P.bi; g.act = 1; g.n_valid = S;
+  RAU_TRY(rau_contract(ctx, g));   // warm-up
+  RAU_CHECK_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  for (int i = 0; i < iters; ++i) RAU_TRY(rau_contract(ctx, g));
+  RAU_CHECK_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  RAU_CHECK_CUDA(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.0f;
+  RAU_CHECK_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *ms_per_launch = ms / iters;
+  return RAU_OK;
+}
+
+}  // extern "C"
+
+int rau_contract(rau_ctx* ctx, const SimtGemm& g) {
+  if (ctx->precision != RAU_PREC_F32) {
+    const int r = tc_gemm_try(ctx, g);
+    if (r < 0) return r;
+    if (r == 1) return RAU_OK;
+  }
+  return simt_gemm(ctx, g);
+}
