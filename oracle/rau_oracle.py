@@ -286,14 +286,14 @@ def hop_fwd(P, cfg, q, X, c, h, masks):
     qd = dropout_fwd(q, mq, cfg.p_q)                                   # F:233
     qf = np.tanh(qd @ P["Wq"].T + P["bq"] + h @ P["Wh"].T + P["bh"])   # F:233-235
     Xd = dropout_fwd(X.reshape(B, cfg.C, cfg.S), mX, cfg.p_x)          # F:239
-    I = np.tanh(np.einsum("mc,bcs->bms", P["Wi"], Xd) + P["bi"][None, :, None])   # F:240-242
+    I = np.tanh(np.matmul(P["Wi"], Xd) + P["bi"][None, :, None])   # F:240-242
     qatt = qf @ P["Wqa"].T + P["bqa"]                                  # F:246
-    Z = np.einsum("am,bms->bas", P["Wa"], I) + P["ba"][None, :, None]  # F:247-249
+    Z = np.matmul(P["Wa"], I) + P["ba"][None, :, None]  # F:247-249
     E = np.tanh(Z + qatt[:, :, None])                                  # F:250
-    s = np.einsum("a,bas->bs", P["ws"][0], E) + P["bs"][0]             # F:251
+    s = np.matmul(P["ws"][0], E) + P["bs"][0]             # F:251
     mem = h @ P["Wm"].T + P["bm"]                                      # F:287
     p = softmax_rows(s + mem)                                          # F:288-289
-    a = np.einsum("bms,bs->bm", I, p)                                  # F:254-263
+    a = np.matmul(I, p[:, :, None])[:, :, 0]                                  # F:254-263
     fp = p @ P["Wp"].T + P["bp"]                                       # F:271
     j = qf + a + fp                                                    # F:270,272
     c2, h2, lcache = attlstm_fwd(P["Wx"], P["bx"], P["Whh"], P["bhh"], j, c, h)   # F:273
@@ -336,7 +336,7 @@ def hop_bwd(P, gP, cfg, cache, dscore, ddo_pred, dp_att, dc_next, dh_next, want_
     gP["bp"] += dj.sum(0)
     # attselect: a = I p
     dI = da[:, :, None] * p[:, None, :]
-    dp = dp + np.einsum("bm,bms->bs", da, I)
+    dp = dp + np.matmul(da[:, None, :], I)[:, 0, :]
     # softmax
     ds = p * (dp - (p * dp).sum(axis=1, keepdims=True))
     dh_prev = dh_prev + ds @ P["Wm"]
@@ -344,11 +344,11 @@ def hop_bwd(P, gP, cfg, cache, dscore, ddo_pred, dp_att, dc_next, dh_next, want_
     gP["bm"] += ds.sum(0)
     # score conv: s = ws.E + bs
     dE = P["ws"][0][None, :, None] * ds[:, None, :]
-    gP["ws"] += np.einsum("bs,bas->a", ds, E)[None, :]
+    gP["ws"] += np.matmul(E, ds[:, :, None])[:, :, 0].sum(0)[None, :]
     gP["bs"] += ds.sum()
     dZ = dE * (1.0 - E * E)
-    dI = dI + np.einsum("am,bas->bms", P["Wa"], dZ)
-    gP["Wa"] += np.einsum("bas,bms->am", dZ, I)
+    dI = dI + np.matmul(P["Wa"].T, dZ)
+    gP["Wa"] += np.tensordot(dZ, I, axes=([0, 2], [0, 2]))
     gP["ba"] += dZ.sum(axis=(0, 2))
     dqa = dZ.sum(axis=2)
     dqf = dqf + dqa @ P["Wqa"]
@@ -356,11 +356,11 @@ def hop_bwd(P, gP, cfg, cache, dscore, ddo_pred, dp_att, dc_next, dh_next, want_
     gP["bqa"] += dqa.sum(0)
     # i_embed
     dY = dI * (1.0 - I * I)
-    gP["Wi"] += np.einsum("bms,bcs->mc", dY, Xd)
+    gP["Wi"] += np.tensordot(dY, Xd, axes=([0, 2], [0, 2]))
     gP["bi"] += dY.sum(axis=(0, 2))
     dX = None
     if want_dX:   # computed by the reference then discarded (F:598)
-        dX = dropout_bwd(np.einsum("mc,bms->bcs", P["Wi"], dY), mX, cfg.p_x)
+        dX = dropout_bwd(np.matmul(P["Wi"].T, dY), mX, cfg.p_x)
     # q_embed
     dpre = dqf * (1.0 - qf * qf)
     dq = dropout_bwd(dpre @ P["Wq"], mq, cfg.p_q)

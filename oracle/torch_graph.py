@@ -81,8 +81,9 @@ class TorchRAU:
         if masks is not None:
             mq, mX, mm = masks.get("q"), masks.get("X"), masks.get("m")
         B = q.shape[0]
+        gw, gh = (14, 14) if cfg.S == 196 else (cfg.S, 1)     # cnnout_w x cnnout_h (F:217-219); toy grids are S x 1
         qf = torch.tanh(Fn.linear(self._drop(q, mq, cfg.p_q), P["Wq"], P["bq"]) + Fn.linear(h, P["Wh"], P["bh"]))  # F:233-235
-        Xd = self._drop(X.view(B, cfg.C, 14, 14), None if mX is None else np.asarray(mX).reshape(B, cfg.C, 14, 14), cfg.p_x)
+        Xd = self._drop(X.reshape(B, cfg.C, gw, gh), None if mX is None else np.asarray(mX).reshape(B, cfg.C, gw, gh), cfg.p_x)
         I = torch.tanh(Fn.conv2d(Xd, P["Wi"].view(cfg.M, cfg.C, 1, 1), P["bi"])).reshape(B, cfg.M, cfg.S)  # F:239-242
         qatt = Fn.linear(qf, P["Wqa"], P["bqa"]).unsqueeze(2).expand(B, cfg.A, cfg.S)      # F:246 Replicate
         proj = Fn.conv2d(I.reshape(B, cfg.M, cfg.S, 1), P["Wa"].view(cfg.A, cfg.M, 1, 1), P["ba"]).reshape(B, cfg.A, cfg.S)  # F:247-249

@@ -1,0 +1,233 @@
+"""Parity of the CUDA path (through the C ABI) against the float64 oracle on identical inputs, weights, dropout
+masks and noise.  Tolerance: north_star's 1e-3 relative (tensor-level, max|a-b|/max|b|) for logits and
+gradients; argmax answers bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import small_cfg
+from helpers import dev, lib_cfg, lib_masks, load_golden, oracle_masks_from_golden, rel_err, run_lib_feval
+from oracle import rau_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3          # north_star tolerance
+TOL_F32 = 2e-5      # what the exact (fp32 CUDA-core) mode actually achieves
+
+
+@pytest.fixture(scope="module")
+def R():
+    import torch
+    assert torch.cuda.is_available(), "the gpu tests need a B200"
+    import rau_vqa_b200 as R
+    return R
+
+
+@pytest.fixture(scope="module", params=["f32", "default"])
+def ctx(R, request):
+    from rau_vqa_b200 import core
+    c = R.Context(0)
+    if request.param == "f32":
+        c.set_precision(core.PREC_F32)
+    c.mode = request.param
+    yield c
+    c.close()
+
+
+def tol_for(ctx):
+    return TOL_F32 if ctx.mode == "f32" else TOL
+
+
+def _check_step(ctx, cfg, params, X, x, x_len, y, masks, hop_mask=None):
+    res = O.feval(cfg, {g: params[g].astype(np.float32).astype(np.float64) for g in O.GROUPS},
+                  X.astype(np.float32).astype(np.float64), x, x_len, y, masks=masks, hop_mask=hop_mask, clip=False)
+    grads, out = run_lib_feval(ctx, cfg, params, X, x, x_len, y, masks=masks, hop_mask=hop_mask)
+    tol = tol_for(ctx)
+    sc = out.scores.cpu().numpy()
+    for h in range(cfg.nHop):
+        assert rel_err(sc[h], res.scores[h]) <= tol, ("score", h)
+        assert rel_err(out.attprob[h].cpu().numpy(), res.attprob[h]) <= tol
+        assert rel_err(out.do_pred[h].cpu().numpy(), res.do_pred[h]) <= tol
+    np.testing.assert_allclose(out.loss.cpu().numpy(), res.loss, rtol=tol)
+    np.testing.assert_allclose(out.loss_do_pred.cpu().numpy(), res.loss_do_pred, rtol=10 * tol, atol=1e-6)
+    # argmax bit-exact wherever the oracle's top-1/top-2 margin is above the tolerance
+    ans = out.answers.cpu().numpy().astype(np.int64)
+    for h in range(cfg.nHop):
+        top2 = np.sort(res.scores[h], axis=1)[:, -2:]
+        safe = (top2[:, 1] - top2[:, 0]) > 4 * tol * np.abs(res.scores[h]).max()
+        assert safe.sum() >= 1
+        np.testing.assert_array_equal(ans[h][safe], res.answers[h][safe])
+    for g in O.GROUPS:
+        assert rel_err(grads[g], res.grads[g]) <= tol, g
+    return res, grads, out
+
+
+def test_toy_step_matches_oracle(ctx):
+    cfg = small_cfg()
+    params = O.init_params(cfg, seed=3)
+    X, x, x_len, y = O.synth_batch(cfg, 5, seed=4, min_len=1)
+    masks = O.synth_masks(cfg, 5, seed=5)
+    _check_step(ctx, cfg, params, X, x, x_len, y, masks)
+
+
+def test_toy_step_hop_mask_and_ragged_lengths(ctx):
+    cfg = small_cfg(nHop=3, T=7)
+    params = O.init_params(cfg, seed=13)
+    X, x, x_len, y = O.synth_batch(cfg, 6, seed=14, min_len=1)
+    x_len[:] = [1, 7, 3, 7, 2, 5]
+    for b in range(6):
+        x[x_len[b]:, b] = 1
+    masks = O.synth_masks(cfg, 6, seed=15)
+    _check_step(ctx, cfg, params, X, x, x_len, y, masks, hop_mask=[1, 0, 1])
+
+
+def test_batch_of_one(ctx):
+    cfg = small_cfg(nHop=1)
+    params = O.init_params(cfg, seed=23)
+    X, x, x_len, y = O.synth_batch(cfg, 1, seed=24, min_len=2)
+    _check_step(ctx, cfg, params, X, x, x_len, y, O.synth_masks(cfg, 1, seed=25))
+
+
+@pytest.mark.parametrize("C,nHop,N", [(512, 2, 2000), (2048, 1, 1000)])
+def test_reference_dims_step_matches_oracle(ctx, C, nHop, N):
+    """Ours_SS / Ours_ResNet shapes (14x14xC features, 2000- or 1000-way head), small batch so the oracle takes seconds."""
+    cfg = O.RauConfig(V=2000, C=C, nHop=nHop, N=N)
+    B = 4
+    params = O.init_params(cfg, seed=123)
+    X, x, x_len, y = O.synth_batch(cfg, B, seed=124)
+    masks = O.synth_masks(cfg, B, seed=125)
+    _check_step(ctx, cfg, params, X, x, x_len, y, masks)
+
+
+@pytest.mark.parametrize("name", ["step_toy_adam.npz", "step_toy_rmsprop.npz"])
+def test_train_step_matches_golden_fixture(R, ctx, name):
+    """feval -> explicit noise -> per-group clip -> adam / rmsprop against the committed fixture."""
+    from rau_vqa_b200 import core
+    z, cfg = load_golden(name)
+    lc = lib_cfg(cfg)
+    masks = oracle_masks_from_golden(z, cfg)
+    P = [dev(z[f"p0_{g}"]) for g in O.GROUPS]
+    G = [t.clone().zero_() for t in P]
+    noise = [dev(z[f"noise_{g}"]) for g in O.GROUPS]
+    adam = str(z["optim"]) == "adam"
+    st = [[t.clone().zero_(), t.clone().zero_() if adam else None] for t in P]
+    out = R.StepBuffers(lc, int(z["B"]), P[0].device)
+    R.train_step(ctx, lc, P, G, st, dev(z["X"]), dev(z["x"]), dev(z["x_len"]), dev(z["y"]), out,
+                 optim=core.OPT_ADAM if adam else core.OPT_RMSPROP, lrs=(cfg.lr, cfg.lr, cfg.mult_lr),
+                 hyper=(0.9, 0.999, 1e-8) if adam else (0.99, 1e-8, 0.0), eta=cfg.noisy_eta, gamma=cfg.noisy_gamma,
+                 clip=cfg.grad_clip, masks=lib_masks(masks), noise=noise, step_t=0, max_len=int(z["x_len"].max()))
+    ctx.sync()
+    tol = tol_for(ctx)
+    np.testing.assert_allclose(out.loss.cpu().numpy(), z["loss"], rtol=tol)
+    np.testing.assert_allclose(out.norms.cpu().numpy(), z["norms"], rtol=tol)
+    for i, g in enumerate(O.GROUPS):
+        assert rel_err(G[i].cpu().numpy(), z[f"g_{g}"]) <= tol, g
+        # the update is lr-sized: compare the parameter DELTA, not the parameters
+        d_lib = P[i].cpu().numpy().astype(np.float64) - z[f"p0_{g}"].astype(np.float32).astype(np.float64)
+        d_ref = z[f"p1_{g}"] - z[f"p0_{g}"]
+        assert rel_err(d_lib, d_ref) <= max(tol, 2e-3), g     # fp32 parameter storage rounds the delta itself
+
+
+def test_noise_clip_and_every_optimizer(R, ctx):
+    from rau_vqa_b200 import core
+    cfg = small_cfg()
+    lc = lib_cfg(cfg)
+    rng = np.random.default_rng(0)
+    grads = {g: rng.standard_normal(O.group_size(cfg, g)) * s for g, s in zip(O.GROUPS, (1e-3, 1.0, 1e-5))}
+    noise = {g: rng.standard_normal(O.group_size(cfg, g)) * 1e-4 for g in O.GROUPS}
+    G = [dev(grads[g]) for g in O.GROUPS]
+    norms = dev(np.zeros(3))
+    R.noise_clip(ctx, lc, G, 4, 0.01, 0.55, 0.1, noise=[dev(noise[g]) for g in O.GROUPS], norms=norms)
+    ctx.sync()
+    for i, g in enumerate(O.GROUPS):
+        ref = grads[g].astype(np.float32).astype(np.float64) + noise[g].astype(np.float32).astype(np.float64)
+        n = O.noise_and_clip(cfg, ref, None)
+        assert norms[i].item() == pytest.approx(n, rel=1e-5)
+        assert rel_err(G[i].cpu().numpy(), ref) <= 1e-5
+    # Philox noise: right standard deviation, same draw on a second context with the same seed (replicas stay identical)
+    big = [dev(np.zeros(O.group_size(cfg, g))) for g in O.GROUPS]
+    R.noise_clip(ctx, lc, big, 9, 0.01, 0.55, 0.0)
+    ctx.sync()
+    std = np.sqrt(0.01 / (10 * 0.55))
+    assert big[1].std().item() == pytest.approx(std, rel=0.03)
+    assert abs(big[1].mean().item()) < 4 * std / np.sqrt(big[1].numel())
+    # the six update rules of utils/optim_updates.lua, two steps each
+    from rau_vqa_b200.utils import optim_updates as OU
+    n = 1000
+    x0, g1, g2 = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(n)
+    cases = [("sgd", lambda x, g, s: O.sgd(x, g, 0.1), lambda x, g, s: OU.sgd(x, g, 0.1)),
+             ("sgdm", lambda x, g, s: O.sgdm(x, g, 0.1, 0.9, s), lambda x, g, s: OU.sgdm(x, g, 0.1, 0.9, s)),
+             ("sgdmom", lambda x, g, s: O.sgdmom(x, g, 0.1, 0.9, s), lambda x, g, s: OU.sgdmom(x, g, 0.1, 0.9, s)),
+             ("adagrad", lambda x, g, s: O.adagrad(x, g, 0.1, 1e-8, s), lambda x, g, s: OU.adagrad(x, g, 0.1, 1e-8, s)),
+             ("rmsprop", lambda x, g, s: O.rmsprop(x, g, 0.1, 0.99, 1e-8, s), lambda x, g, s: OU.rmsprop(x, g, 0.1, 0.99, 1e-8, s)),
+             ("adam", lambda x, g, s: O.adam(x, g, 0.1, s), lambda x, g, s: OU.adam(x, g, 0.1, None, None, None, s))]
+    for name, ref_fn, lib_fn in cases:
+        xr, sr = x0.astype(np.float32).astype(np.float64), {}
+        xl, sl = dev(x0), {}
+        for g in (g1, g2):
+            ref_fn(xr, g.astype(np.float32).astype(np.float64), sr)
+            lib_fn(xl, dev(g), sl)
+        ctx.sync()
+        import torch
+        torch.cuda.synchronize()
+        assert rel_err(xl.cpu().numpy(), xr) <= 1e-5, name
+
+
+def test_predict_matches_oracle_and_argmax_is_exact(R, ctx):
+    cfg = small_cfg(nHop=3)
+    lc = lib_cfg(cfg)
+    params = O.init_params(cfg, seed=33)
+    X, x, x_len, y = O.synth_batch(cfg, 6, seed=34, min_len=1)
+    p32 = {g: params[g].astype(np.float32).astype(np.float64) for g in O.GROUPS}
+    preds, atts = O.predict(cfg, p32, X.astype(np.float32).astype(np.float64), x, x_len)
+    pred, att = R.predict(ctx, lc, [dev(params[g]) for g in O.GROUPS], dev(X), dev(x), dev(x_len), max_len=int(x_len.max()))
+    ctx.sync()
+    tol = tol_for(ctx)
+    for k in range(cfg.nHop + 2):
+        assert rel_err(pred[k].cpu().numpy(), preds[k]) <= tol, k
+        assert rel_err(att[k].cpu().numpy(), atts[k]) <= tol, k
+        top2 = np.sort(preds[k], axis=1)[:, -2:]
+        safe = (top2[:, 1] - top2[:, 0]) > 4 * tol * np.abs(preds[k]).max()
+        np.testing.assert_array_equal(pred[k].cpu().numpy().argmax(1)[safe], preds[k].argmax(1)[safe])
+
+
+def test_data_parallel_shards_sum_to_the_big_batch(R, ctx):
+    """SURVEY.md 8e on one GPU: two 'virtual ranks' each run half the batch with B_global = B; the sum of their
+    gradients equals the single-GPU big-batch gradient."""
+    cfg = small_cfg(nHop=2)
+    B = 6
+    params = O.init_params(cfg, seed=43)
+    X, x, x_len, y = O.synth_batch(cfg, B, seed=44, min_len=1)
+    masks = O.synth_masks(cfg, B, seed=45)
+    full, out_full = run_lib_feval(ctx, cfg, params, X, x, x_len, y, masks=masks)
+    tot = {g: 0 for g in O.GROUPS}
+    loss = 0
+    for r in range(2):
+        sl = slice(r * 3, r * 3 + 3)
+        mk = dict(embed=masks["embed"][:, sl], rnn=masks["rnn"][:, sl],
+                  hops=[{k: v[sl] for k, v in hm.items()} for hm in masks["hops"]])
+        # every shard unrolls to the GLOBAL max length so that the mask tensors line up
+        g, o = run_lib_feval(ctx, cfg, params, X[sl], x[:, sl], x_len[sl], y[sl], masks=mk, B_global=B)
+        for k in O.GROUPS:
+            tot[k] = tot[k] + g[k]
+        loss = loss + o.loss.cpu().numpy()
+    for k in O.GROUPS:
+        assert rel_err(tot[k], full[k]) <= 1e-4, k
+    np.testing.assert_allclose(loss[:cfg.nHop], out_full.loss.cpu().numpy()[:cfg.nHop], rtol=1e-4)
+
+
+def test_errors_are_reported_not_thrown(R, ctx):
+    import torch
+    from rau_vqa_b200 import core
+    cfg = lib_cfg(small_cfg())
+    host = torch.zeros(10)
+    with pytest.raises(TypeError):
+        core.optim_step(ctx, core.OPT_SGD, host.double(), host, 0.1)
+    with pytest.raises(R.RauError) as e:   # host pointer: no CPU path
+        core.optim_step(ctx, core.OPT_SGD, host, host, 0.1)
+    assert "not a device pointer" in str(e.value)
+    bad = lib_cfg(small_cfg(nlayer=3))
+    P = [dev(np.zeros(bad.group_size(g))) for g in range(3)]
+    out = R.StepBuffers(bad, 2, P[0].device)
+    with pytest.raises(R.RauError):
+        R.feval(ctx, bad, P, [p.clone() for p in P], dev(np.zeros((2, bad.C, bad.S))), dev(np.ones((bad.T, 2))),
+                dev(np.ones(2)), dev(np.ones(2)), out)
