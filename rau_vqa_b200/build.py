@@ -60,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-lcudart", "-lcuda", "-ldl"]
+    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -1,3 +1,454 @@
-// k_gemm_tc.cu -- tcgen05 engine (placeholder until the TMA/TMEM kernel lands): reports "not eligible".
+// k_gemm_tc.cu -- the tcgen05 contraction engine (sm_100a): bf16 operands staged by TMA into 128B-swizzled shared
+// memory, tcgen05.mma (cta_group::1, M=128) accumulating fp32 in TMEM, tcgen05.ld epilogue with the fused
+// bias / broadcast-add / tanh / spatial-pad logic of the reference's Linear / SpatialConvolution+Tanh nodes.
+//
+//   C'[i,j] = sum_seg sum_kb sum_k P_seg[kb][i,k] * Q_seg[kb][j,k]      i -> TMEM lane, j -> TMEM column
+//
+// * either operand may be K-major (k contiguous) or MN-major (i / j contiguous) -- the UMMA instruction descriptor
+//   carries the major-ness, so nn.Linear forward (both K-major), its dgrad (W read MN-major), its wgrad (both
+//   MN-major) and the per-image 1x1 convolutions (features read MN-major, [C,196] as stored) need no transposes;
+// * up to 6 K-segments accumulate into one tile: (x,W_i2h)+(h,W_h2h) of an LSTM layer, or the bf16x3 split
+//   (hi*hi + hi*lo + lo*hi) that recovers ~fp32 accuracy on the bf16 tensor pipe (RAU_PREC_BF16X3);
+// * a third tensor coordinate selects the image (independent batch, blockIdx.z) or walks a reduced batch (kb).
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane), warps 2..9 = epilogue.
 #include "rau_model.cuh"
-int tc_gemm_try(rau_ctx* ctx, const SimtGemm& g) { (void)ctx; (void)g; return 0; }
+#include <cuda.h>
+#include <stdlib.h>
+
+namespace {
+
+constexpr int TC_BM = 128;        // TMEM lanes per tile (UMMA M)
+constexpr int TC_BK = 64;         // k elements per pipeline stage = one 128-byte swizzle row of bf16
+constexpr int TC_THREADS = 320;   // 10 warps
+constexpr int TC_MAXSEG = 6;
+constexpr int TC_SMEM_BUDGET = 100 * 1024;   // two CTAs per SM
+
+struct TcParams {
+  CUtensorMap mapP[TC_MAXSEG], mapQ[TC_MAXSEG];
+  int nseg, kblocks[TC_MAXSEG];
+  int p_mn, q_mn;                 // 1 = MN-major operand
+  int p_zmode, q_zmode;           // 0 = shared (z = 0), 1 = independent batch (z = bz), 2 = reduced batch (z = kb)
+  int kbatch, ksplit;
+  int BN, stages, tmem_cols;
+  int extI, extJ, i_valid, j_valid;
+  float* C; long long sci, scj, bC;
+  float alpha;
+  const float *bias_i, *bias_i2, *bias_j, *bias_j2, *bias_bi, *bias_bj;
+  const float *addend, *addend2; long long sdi, sdj, bD;
+  int act, accumulate, atomic;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[k]);
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
+// version=1 [46,48) | layout SWIZZLE_128B=2 [61,64).  8 rows x 128 bytes form one 1024-byte swizzle atom.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[8], empty_bar[8], acc_bar;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int BN = p.BN;
+  const int BNbox = (BN + 63) / 64 * 64;                 // smem footprint of a Q tile (MN-major chunks are 64 wide)
+  const uint32_t p_bytes = TC_BM * TC_BK * 2, q_bytes = (uint32_t)BNbox * TC_BK * 2;
+  const uint32_t stage_bytes = p_bytes + q_bytes;
+  const uint32_t tx_bytes = p_bytes + (p.q_mn ? q_bytes : (uint32_t)BN * TC_BK * 2);   // bytes the TMA boxes deliver
+  const int i0 = blockIdx.y * TC_BM, j0 = blockIdx.x * BN;
+  const int bz = blockIdx.z / p.ksplit, ks = blockIdx.z % p.ksplit;
+  int kb_lo = 0, kb_hi = p.kbatch;
+  if (p.ksplit > 1) {
+    const int per = (p.kbatch + p.ksplit - 1) / p.ksplit;
+    kb_lo = ks * per;
+    kb_hi = min(p.kbatch, kb_lo + per);
+  }
+  int kper = 0;
+  for (int s = 0; s < p.nseg; ++s) kper += p.kblocks[s];
+  const int total = max(kb_hi - kb_lo, 0) * kper;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int kb = kb_lo; kb < kb_hi; ++kb) {
+        const int zp = p.p_zmode == 1 ? bz : (p.p_zmode == 2 ? kb : 0);
+        const int zq = p.q_zmode == 1 ? bz : (p.q_zmode == 2 ? kb : 0);
+        for (int s = 0; s < p.nseg; ++s) {
+          for (int kk = 0; kk < p.kblocks[s]; ++kk, ++it) {
+            const int st = it % p.stages;
+            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+            mbar_wait(&empty_bar[st], ph ^ 1u);
+            uint8_t* sp = smem + (size_t)st * stage_bytes;
+            uint8_t* sq = sp + p_bytes;
+            mbar_expect_tx(&full_bar[st], tx_bytes);
+            if (p.p_mn) {   // [k rows][64 i] boxes, one per 64-wide chunk of i
+              tma_load_3d(sp, &p.mapP[s], &full_bar[st], i0, kk * TC_BK, zp);
+              tma_load_3d(sp + 8192, &p.mapP[s], &full_bar[st], i0 + 64, kk * TC_BK, zp);
+            } else {        // [128 i rows][64 k]
+              tma_load_3d(sp, &p.mapP[s], &full_bar[st], kk * TC_BK, i0, zp);
+            }
+            if (p.q_mn) {
+              for (int c = 0; c < BNbox / 64; ++c)
+                tma_load_3d(sq + c * 8192, &p.mapQ[s], &full_bar[st], j0 + c * 64, kk * TC_BK, zq);
+            } else {
+              tma_load_3d(sq, &p.mapQ[s], &full_bar[st], kk * TC_BK, j0, zq);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6) | A=bf16 [7,10) | B=bf16 [10,13) |
+      // a_major [15] | b_major [16] | N>>3 [17,23) | M>>4 [24,29)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.p_mn << 15) | ((uint32_t)p.q_mn << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int it = 0; it < total; ++it) {
+        const int st = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        mbar_wait(&full_bar[st], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sp = smem_u32(smem + (size_t)st * stage_bytes);
+        const uint32_t sq = sp + p_bytes;
+        // K-major: rows of 128 B, 8-row atoms 1024 B apart (SBO); a 16-element k step is +32 B inside the swizzle row.
+        // MN-major: 64-wide chunks of i/j 8192 B apart (LBO), 8-k-row atoms 1024 B apart (SBO); a k step is 16 rows = 2048 B.
+        const uint64_t da = p.p_mn ? make_desc(sp, 8192, 1024) : make_desc(sp, 16, 1024);
+        const uint64_t db = p.q_mn ? make_desc(sq, 8192, 1024) : make_desc(sq, 16, 1024);
+        const uint32_t ka = p.p_mn ? (2048u >> 4) : (32u >> 4), kq = p.q_mn ? (2048u >> 4) : (32u >> 4);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k)
+          umma_bf16(tmem_base, da + (uint64_t)(k * ka), db + (uint64_t)(k * kq), idesc, (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&empty_bar[st]);   // frees the stage when these MMAs have read it
+      }
+      umma_commit(&acc_bar);           // accumulator complete
+    }
+  } else {
+    // ===================== epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).., two warps share a lane quarter
+    const int q4 = warp & 3, half = (warp - 2) >> 2;
+    mbar_wait(&acc_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int i = i0 + q4 * 32 + lane;
+    const int nchunk = (BN + 15) / 16;
+    const int c_lo = half == 0 ? 0 : (nchunk + 1) / 2, c_hi = half == 0 ? (nchunk + 1) / 2 : nchunk;
+    const bool i_ok = i < p.extI;
+    float bi = 0.0f;
+    if (i_ok) {
+      if (p.bias_i) bi += p.bias_i[i];
+      if (p.bias_i2) bi += p.bias_i2[i];
+      if (p.bias_bi) bi += p.bias_bi[(long long)bz * p.extI + i];
+    }
+    float* Crow = p.C + (long long)bz * p.bC + (long long)i * p.sci;
+    const float* Drow = p.addend ? p.addend + (long long)bz * p.bD + (long long)i * p.sdi : nullptr;
+    const float* D2row = p.addend2 ? p.addend2 + (long long)bz * p.bD + (long long)i * p.sdi : nullptr;
+    for (int c = c_lo; c < c_hi; ++c) {
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(c * 16), v);
+      if (total == 0) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = 0.0f;
+      }
+      if (!i_ok) continue;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int j = j0 + c * 16 + k;
+        if (j >= p.extJ || c * 16 + k >= BN) continue;
+        float x = v[k] * p.alpha + bi;
+        if (p.bias_j) x += p.bias_j[j];
+        if (p.bias_j2) x += p.bias_j2[j];
+        if (p.bias_bj) x += p.bias_bj[(long long)bz * p.extJ + j];
+        if (Drow) {
+          x += Drow[(long long)j * p.sdj];
+          if (D2row) x += D2row[(long long)j * p.sdj];
+        }
+        if (p.act == 1) x = tanhf(x);
+        else if (p.act == 2) x = 1.0f / (1.0f + expf(-x));
+        if (i >= p.i_valid || j >= p.j_valid) x = 0.0f;
+        float* dst = Crow + (long long)j * p.scj;
+        if (p.atomic) atomicAdd(dst, x);
+        else if (p.accumulate) *dst += x;
+        else *dst = x;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- fp32 -> bf16 (hi, lo) operand packing
+// out[b][r][c] = bf16(in[b*sb + r*ld + c]); lo = bf16(x - float(hi)).  Rows are padded to ldo (multiple of 8).
+__global__ void pack_bf16_kernel(const float* __restrict__ in, long long sb, long long ld, int nb, int R, int Cc, int ldo,
+                                 bf16* __restrict__ hi, bf16* __restrict__ lo) {
+  const long long total = (long long)nb * R * ldo;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % ldo);
+    const long long br = idx / ldo;
+    const int r = (int)(br % R);
+    const long long b = br / R;
+    float x = 0.0f;
+    if (c < Cc) x = in[b * sb + (long long)r * ld + c];
+    const bf16 h = __float2bfloat16(x);
+    hi[idx] = h;
+    if (lo) lo[idx] = __float2bfloat16(x - __bfloat162float(h));
+  }
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn g_encode = nullptr;
+
+int get_encode() {
+  if (g_encode) return RAU_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr);
+  if (e != cudaSuccess || fn == nullptr) {
+    rau_set_error("cuTensorMapEncodeTiled is not available: %s", cudaGetErrorString(e));
+    return RAU_ECUDA;
+  }
+  g_encode = (EncodeFn)fn;
+  return RAU_OK;
+}
+
+// one operand of the contraction as the SimtGemm strides describe it
+struct Operand {
+  const float* ptr; int ext, K; long long s_ext, s_k;   // element (e, k) at ptr[e*s_ext + k*s_k]
+  int zmode; int nz; long long s_z;                      // third coordinate
+  bool is_const;
+};
+
+struct Packed { bf16 *hi = nullptr, *lo = nullptr; int mn = 0, R = 0, Cc = 0, ldo = 0, nz = 1; };
+
+int pack_operand(rau_ctx* ctx, const Operand& o, bool want_lo, const char* slot, Packed* out) {
+  Packed pk;
+  pk.mn = (o.s_k != 1 && o.s_ext == 1) ? 1 : 0;
+  if (o.s_k != 1 && o.s_ext != 1) return 1;   // neither dimension contiguous: not eligible
+  pk.R = pk.mn ? o.K : o.ext;
+  pk.Cc = pk.mn ? o.ext : o.K;
+  pk.ldo = (pk.Cc + 7) / 8 * 8;
+  pk.nz = o.nz;
+  const long long ld = pk.mn ? o.s_k : o.s_ext;
+  const size_t elems = (size_t)pk.nz * pk.R * pk.ldo;
+  char name[160];
+  bool cached = false;
+  if (o.is_const) {
+    snprintf(name, sizeof(name), "tcw.%p.%d.%d.%lld.%d.%d", (const void*)o.ptr, pk.R, pk.Cc, ld, pk.nz, want_lo ? 1 : 0);
+    auto it = ctx->tc_epoch.find(name);
+    cached = it != ctx->tc_epoch.end() && it->second == ctx->epoch;
+  } else {
+    snprintf(name, sizeof(name), "tc.%s", slot);
+  }
+  void* buf = nullptr;
+  RAU_TRY(ctx->arena.get(name, elems * sizeof(bf16) * (want_lo ? 2 : 1) + 256, &buf));
+  pk.hi = (bf16*)buf;
+  pk.lo = want_lo ? pk.hi + ((elems + 127) / 128 * 128) : nullptr;
+  if (!cached) {
+    long long blocks = ((long long)elems + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    pack_bf16_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(o.ptr, o.s_z, ld, pk.nz, pk.R, pk.Cc, pk.ldo, pk.hi, pk.lo);
+    RAU_LAUNCH_CHECK(ctx);
+    if (o.is_const) ctx->tc_epoch[name] = ctx->epoch;
+  }
+  *out = pk;
+  return RAU_OK;
+}
+
+int encode_map(CUtensorMap* m, const bf16* base, const Packed& pk, int box_rows) {
+  cuuint64_t dims[3] = {(cuuint64_t)pk.Cc, (cuuint64_t)pk.R, (cuuint64_t)pk.nz};
+  cuuint64_t strides[2] = {(cuuint64_t)pk.ldo * 2, (cuuint64_t)pk.ldo * 2 * (cuuint64_t)pk.R};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    rau_set_error("cuTensorMapEncodeTiled failed (%d) dims=%llu,%llu,%llu ld=%d box_rows=%d", (int)r,
+                  (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], pk.ldo, box_rows);
+    return RAU_ECUDA;
+  }
+  return RAU_OK;
+}
+
+bool g_attr_set = false;
+
+// products below this many multiply-adds stay on the CUDA cores (RAU_TC_MIN_WORK overrides; tests set it to 0 so
+// that toy shapes exercise every TMA / descriptor edge case)
+long long tc_min_work() {
+  static long long v = -1;
+  if (v < 0) {
+    const char* e = getenv("RAU_TC_MIN_WORK");
+    v = e ? atoll(e) : (1ll << 18);
+  }
+  return v;
+}
+}  // namespace
+
+int tc_gemm_try(rau_ctx* ctx, const SimtGemm& g) {
+  if (ctx->precision == RAU_PREC_F32) return 0;
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
+  // tiny or vector-like products stay on the CUDA cores
+  if ((long long)g.M * g.N * (long long)(g.K + g.K2) * g.kbatch < tc_min_work()) return 0;
+  if (g.batch > 1 && g.kbatch > 1) return 0;
+  if (g.ksplit > 1 && g.kbatch <= 1) return 0;   // split over K itself is not wired into this engine
+  RAU_TRY(get_encode());
+  const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+
+  // roles: TMEM lanes (i) take 128 rows per tile, TMEM columns (j) up to 256; pick the cheaper padding
+  auto cost = [](int I, int J) { return (long long)((I + 127) / 128 * 128) * ((J + 15) / 16 * 16); };
+  const bool swap = cost(g.N, g.M) < cost(g.M, g.N);
+  const int zmodeA = g.batch > 1 ? (g.bA ? 1 : 0) : (g.kbatch > 1 ? (g.kA ? 2 : 0) : 0);
+  const int zmodeB = g.batch > 1 ? (g.bB ? 1 : 0) : (g.kbatch > 1 ? (g.kB ? 2 : 0) : 0);
+  const int nzv = g.batch > 1 ? g.batch : g.kbatch;
+  Operand opA[2], opB[2];
+  int nseg_in = 1;
+  opA[0] = Operand{g.A, g.M, g.K, g.sam, g.sak, zmodeA, zmodeA ? nzv : 1, g.batch > 1 ? g.bA : g.kA, g.a_const != 0};
+  opB[0] = Operand{g.B, g.N, g.K, g.sbn, g.sbk, zmodeB, zmodeB ? nzv : 1, g.batch > 1 ? g.bB : g.kB, g.b_const != 0};
+  if (g.A2) {
+    if (g.batch > 1 || g.kbatch > 1) return 0;
+    opA[1] = Operand{g.A2, g.M, g.K2, g.sam2, g.sak2, 0, 1, 0, g.a_const != 0};
+    opB[1] = Operand{g.B2, g.N, g.K2, g.sbn2, g.sbk2, 0, 1, 0, g.b_const != 0};
+    nseg_in = 2;
+  }
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  Packed pkP[2], pkQ[2];
+  if (nseg_in * (x3 ? 3 : 1) > TC_MAXSEG) return 0;
+  for (int s = 0; s < nseg_in; ++s) {
+    const Operand& oP = swap ? opB[s] : opA[s];
+    const Operand& oQ = swap ? opA[s] : opB[s];
+    char slotP[16], slotQ[16];
+    snprintf(slotP, sizeof(slotP), "P%d", s);
+    snprintf(slotQ, sizeof(slotQ), "Q%d", s);
+    int r = pack_operand(ctx, oP, x3, slotP, &pkP[s]);
+    if (r == 1) return 0;
+    if (r != RAU_OK) return r;
+    r = pack_operand(ctx, oQ, x3, slotQ, &pkQ[s]);
+    if (r == 1) return 0;
+    if (r != RAU_OK) return r;
+    if (s > 0 && (pkP[s].mn != pkP[0].mn || pkQ[s].mn != pkQ[0].mn)) return 0;
+  }
+  const int extI = swap ? g.N : g.M, extJ = swap ? g.M : g.N;
+  // tile width: keep whole rows of j in one tile when they fit, shrink to spread small problems over the SMs
+  int BN = extJ <= 256 ? (extJ + 15) / 16 * 16 : 256;
+  const long long itiles = (extI + TC_BM - 1) / TC_BM;
+  const long long zcount = (long long)g.batch * g.ksplit;
+  while (BN > 64 && itiles * ((extJ + BN - 1) / BN) * zcount < 148 && (BN / 2) % 16 == 0) BN /= 2;
+  const int BNbox = (BN + 63) / 64 * 64;
+  p.BN = BN;
+  p.p_mn = pkP[0].mn; p.q_mn = pkQ[0].mn;
+  const Operand& oP0 = swap ? opB[0] : opA[0];
+  const Operand& oQ0 = swap ? opA[0] : opB[0];
+  p.p_zmode = oP0.zmode; p.q_zmode = oQ0.zmode;
+  p.kbatch = g.kbatch; p.ksplit = g.ksplit;
+  int ns = 0;
+  for (int s = 0; s < nseg_in; ++s) {
+    const int kblocks = ((swap ? opB[s].K : opA[s].K) + TC_BK - 1) / TC_BK;
+    const int combos = x3 ? 3 : 1;
+    for (int c = 0; c < combos; ++c, ++ns) {
+      const bf16* bp = (c == 2) ? pkP[s].lo : pkP[s].hi;     // hi*hi, hi*lo, lo*hi
+      const bf16* bq = (c == 1) ? pkQ[s].lo : pkQ[s].hi;
+      RAU_TRY(encode_map(&p.mapP[ns], bp, pkP[s], pkP[s].mn ? TC_BK : TC_BM));
+      RAU_TRY(encode_map(&p.mapQ[ns], bq, pkQ[s], pkQ[s].mn ? TC_BK : BN));
+      p.kblocks[ns] = kblocks;
+    }
+  }
+  p.nseg = ns;
+  const int stage_bytes = TC_BM * TC_BK * 2 + BNbox * TC_BK * 2;
+  p.stages = TC_SMEM_BUDGET / stage_bytes;
+  if (p.stages > 8) p.stages = 8;
+  if (p.stages < 2) p.stages = 2;
+  p.tmem_cols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  p.extI = extI; p.extJ = extJ;
+  p.i_valid = extI; p.j_valid = extJ;
+  if (g.n_valid >= 0) { if (swap) p.i_valid = g.n_valid; else p.j_valid = g.n_valid; }
+  p.C = g.C; p.sci = swap ? g.scn : g.scm; p.scj = swap ? g.scm : g.scn; p.bC = g.bC;
+  p.alpha = g.alpha;
+  if (swap) { p.bias_j = g.bias_m; p.bias_i = g.bias_n; p.bias_i2 = g.bias_n2; p.bias_bj = g.bias_bm; }
+  else { p.bias_i = g.bias_m; p.bias_j = g.bias_n; p.bias_j2 = g.bias_n2; p.bias_bi = g.bias_bm; }
+  p.addend = g.addend; p.addend2 = g.addend2; p.bD = g.bD;
+  p.sdi = swap ? g.sdn : g.sdm; p.sdj = swap ? g.sdm : g.sdn;
+  p.act = g.act; p.accumulate = g.accumulate; p.atomic = g.ksplit > 1 ? 1 : 0;
+
+  const int smem_bytes = p.stages * stage_bytes + 1024;
+  if (!g_attr_set) {
+    RAU_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    g_attr_set = true;
+  }
+  dim3 grid((extJ + BN - 1) / BN, (unsigned)itiles, (unsigned)zcount);
+  tc_gemm_kernel<<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p);
+  RAU_LAUNCH_CHECK(ctx);
+  return 1;
+}

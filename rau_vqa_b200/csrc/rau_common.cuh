@@ -51,10 +51,12 @@ struct rau_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   uint64_t seed = 0x5eed5eedULL;
-  int precision = RAU_PREC_BF16;
+  int precision = RAU_PREC_BF16X3;
   int sm_count = 148;
   int64_t launches = 0;
   RauArena arena;
+  uint64_t epoch = 1;                              // bumped at every public entry: bf16 weight shadows are per epoch
+  std::map<std::string, uint64_t> tc_epoch;        // shadow name -> epoch it was packed in
   RauComm* comm = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -150,6 +152,7 @@ struct SimtGemm {
   const float* bias_bm = nullptr;  // [batch, M]
   const float* addend = nullptr; int64_t sdm = 0, sdn = 1, bD = 0;  // same indexing as C
   const float* addend2 = nullptr;  // same strides as addend
+  int a_const = 0, b_const = 0;    // operand is a parameter tensor (constant within one public call)
   int accumulate = 0;
   float alpha = 1.0f;
   int act = 0;                     // 0 none, 1 tanh, 2 sigmoid

@@ -67,7 +67,7 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
   {
     SimtGemm g;
     g.M = M; g.N = Sp; g.K = C;
-    g.A = P.Wi; g.sam = C; g.sak = 1;
+    g.A = P.Wi; g.sam = C; g.sak = 1; g.a_const = 1;
     g.B = Xd; g.sbk = Sp; g.sbn = 1; g.bB = (int64_t)C * Sp;
     g.C = sv.I; g.scm = Sp; g.scn = 1; g.bC = (int64_t)M * Sp;
     g.batch = B; g.bias_m = P.bi; g.act = 1; g.n_valid = S;
@@ -82,7 +82,7 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
   {
     SimtGemm g;
     g.M = A; g.N = Sp; g.K = M;
-    g.A = P.Wa; g.sam = M; g.sak = 1;
+    g.A = P.Wa; g.sam = M; g.sak = 1; g.a_const = 1;
     g.B = sv.I; g.sbk = Sp; g.sbn = 1; g.bB = (int64_t)M * Sp;
     g.C = sv.E; g.scm = Sp; g.scn = 1; g.bC = (int64_t)A * Sp;
     g.batch = B; g.bias_m = P.ba; g.bias_bm = qatt; g.act = 1; g.n_valid = S;
@@ -211,7 +211,7 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   {
     SimtGemm g;
     g.M = M; g.N = Sp; g.K = A;
-    g.A = P.Wa; g.sam = 1; g.sak = M;
+    g.A = P.Wa; g.sam = 1; g.sak = M; g.a_const = 1;
     g.B = dZ; g.sbk = Sp; g.sbn = 1; g.bB = (int64_t)A * Sp;
     g.C = dI; g.scm = Sp; g.scn = 1; g.bC = (int64_t)M * Sp;
     g.batch = B;
@@ -252,7 +252,7 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   if (dX) {
     SimtGemm g;
     g.M = C; g.N = Sp; g.K = M;
-    g.A = P.Wi; g.sam = 1; g.sak = C;
+    g.A = P.Wi; g.sam = 1; g.sak = C; g.a_const = 1;
     g.B = dI; g.sbk = Sp; g.sbn = 1; g.bB = (int64_t)M * Sp;
     g.C = Xd; g.scm = Sp; g.scn = 1; g.bC = (int64_t)C * Sp;
     g.batch = B;
@@ -325,6 +325,7 @@ int rau_hop_fwd(rau_ctx* ctx, const rau_config* cfg, int B, const float* mult_pa
   RAU_TRY(rau_check_dev(score, "score")); RAU_TRY(rau_check_dev(c_out, "c_out"));
   RAU_TRY(rau_check_dev(saved, "saved"));
   RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  ctx->epoch++;
   HopSaved sv;
   hop_saved_layout(cfg, B, saved, &sv);
   const int Q = 2 * cfg->Hq * cfg->nlayer;
@@ -348,6 +349,7 @@ int rau_hop_bwd(rau_ctx* ctx, const rau_config* cfg, int B, const float* mult_pa
   RAU_TRY(rau_check_dev(saved, "saved")); RAU_TRY(rau_check_dev(dq, "dq"));
   RAU_TRY(rau_check_dev(dc, "dc")); RAU_TRY(rau_check_dev(dh, "dh"));
   RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  ctx->epoch++;
   HopSaved sv;
   hop_saved_layout(cfg, B, (void*)saved, &sv);
   MultT<const float*> P = mult_views<const float*, const float>(cfg, mult_params);
@@ -373,6 +375,7 @@ int rau_lstm_cell_fwd(rau_ctx* ctx, const rau_lstm_desc* d, const float* x, cons
   RAU_TRY(rau_check_dev(Wi, "Wi")); RAU_TRY(rau_check_dev(Wh, "Wh")); RAU_TRY(rau_check_dev(bi, "bi"));
   RAU_TRY(rau_check_dev(bh, "bh")); RAU_TRY(rau_check_dev(c, "c")); RAU_TRY(rau_check_dev(h, "h"));
   RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  ctx->epoch++;
   ARENA(Gt, float, "lstm.G", (size_t)d->B * 4 * d->H);
   SimtGemm g = lin_fwd(d->B, 4 * d->H, d->in_size, x, d->ldx, Wi, Gt, 4 * d->H);
   lin_seg2(g, d->H, h_prev, d->ldh_prev, Wh);
@@ -390,6 +393,7 @@ int rau_lstm_cell_bwd(rau_ctx* ctx, const rau_lstm_desc* d, const float* x, cons
   RAU_TRY(rau_check_dev(x, "x")); RAU_TRY(rau_check_dev(c_prev, "c_prev")); RAU_TRY(rau_check_dev(h_prev, "h_prev"));
   RAU_TRY(rau_check_dev(Wi, "Wi")); RAU_TRY(rau_check_dev(Wh, "Wh")); RAU_TRY(rau_check_dev(saved, "saved"));
   RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  ctx->epoch++;
   const int B = d->B, H = d->H, in = d->in_size;
   ARENA(dG, float, "lstm.dG", (size_t)B * 4 * H);
   ARENA(dcp, float, "lstm.dcp", (size_t)B * H);
@@ -416,6 +420,7 @@ int rau_embed_fwd(rau_ctx* ctx, const rau_config* cfg, int n, const float* ids, 
   RAU_REQUIRE(n > 0, "n = %d", n);
   RAU_TRY(rau_check_dev(ids, "ids")); RAU_TRY(rau_check_dev(E, "E")); RAU_TRY(rau_check_dev(out, "out"));
   RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  ctx->epoch++;
   const int64_t cnt = (int64_t)n * cfg->embed;
   ARENA(bits, uint32_t, "embed.bits", mask_words(cnt));
   const bool drop = train && cfg->p_embed > 0;
@@ -431,6 +436,7 @@ int rau_embed_bwd(rau_ctx* ctx, const rau_config* cfg, int n, const float* ids, 
   RAU_TRY(rau_check_dev(ids, "ids")); RAU_TRY(rau_check_dev(out, "out"));
   RAU_TRY(rau_check_dev(dout, "dout")); RAU_TRY(rau_check_dev(gE, "gE"));
   RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  ctx->epoch++;
   const int64_t cnt = (int64_t)n * cfg->embed;
   ARENA(bits, uint32_t, "embed.bits", mask_words(cnt));
   const bool drop = train && cfg->p_embed > 0;
@@ -445,6 +451,7 @@ int rau_dropout(rau_ctx* ctx, int64_t n, const float* x, float p, int train, con
   RAU_REQUIRE(n > 0 && p >= 0.0f && p < 1.0f, "bad dropout arguments n=%lld p=%f", (long long)n, p);
   RAU_TRY(rau_check_dev(x, "x")); RAU_TRY(rau_check_dev(y, "y"));
   RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  ctx->epoch++;
   ARENA(bits, uint32_t, "dropout.bits", mask_words(n));
   const bool drop = train && p > 0;
   RAU_TRY(rau_prepare_mask(ctx, bits, n, p, train, mask, stream_id));
@@ -458,6 +465,7 @@ int rau_gemm(rau_ctx* ctx, int M, int N, int K, const float* A, int lda, int ta,
   RAU_REQUIRE(M > 0 && N > 0 && K > 0, "bad gemm shape %dx%dx%d", M, N, K);
   RAU_TRY(rau_check_dev(A, "A")); RAU_TRY(rau_check_dev(B, "B")); RAU_TRY(rau_check_dev(C, "C"));
   RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  ctx->epoch++;
   SimtGemm g;
   g.M = M; g.N = N; g.K = K;
   g.A = A; g.sam = ta ? 1 : lda; g.sak = ta ? lda : 1;
@@ -473,6 +481,7 @@ int rau_softmax_ce(rau_ctx* ctx, int B, int N, const float* score, const float* 
   RAU_REQUIRE(B > 0 && N > 0, "bad shape");
   RAU_TRY(rau_check_dev(score, "score")); RAU_TRY(rau_check_dev(labels, "labels"));
   RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  ctx->epoch++;
   return k_softmax_ce(ctx, B, N, score, labels, scale, scale, loss_sum, dscore, nullptr, 0, answers);
 }
 

@@ -16,6 +16,7 @@ static inline SimtGemm lin_fwd(int rows, int N, int K, const float* X, int ldx, 
   g.A = X; g.sam = ldx; g.sak = 1;
   g.B = W; g.sbk = 1; g.sbn = K;
   g.C = Y; g.scm = ldy; g.scn = 1;
+  g.b_const = 1;
   return g;
 }
 static inline void lin_seg2(SimtGemm& g, int K2, const float* X2, int ldx2, const float* W2) {
@@ -29,6 +30,7 @@ static inline SimtGemm lin_dgrad(int rows, int N, int K, const float* dY, int ld
   g.A = dY; g.sam = lddy; g.sak = 1;
   g.B = W; g.sbk = K; g.sbn = 1;
   g.C = dX; g.scm = lddx; g.scn = 1;
+  g.b_const = 1;
   return g;
 }
 // gW[N,K] += scale * dY[rows,N]^T X[rows,K]

@@ -192,6 +192,7 @@ int rau_feval(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float* c
     RAU_TRY(rau_check_dev(grads[g], "grads[g]"));
   }
   RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  ctx->epoch++;
   const int B = bt->B, nHop = cfg->nHop, N = cfg->N, S = cfg->S, H = cfg->H, Q = 4 * cfg->Hq;
   const int Bg = bt->B_global > 0 ? bt->B_global : B;
   const int rank = rau_comm_rank(ctx);
@@ -272,6 +273,7 @@ int rau_noise_clip(rau_ctx* ctx, const rau_config* cfg, float* const grads[3], i
   RAU_REQUIRE(ctx, "ctx == NULL");
   RAU_TRY(rau_check_cfg(cfg));
   RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  ctx->epoch++;
   ARENA(norm2, double, "opt.norm2", 4);
   RAU_CHECK_CUDA(cudaMemsetAsync(norm2, 0, sizeof(double) * 4, ctx->stream));
   const float std_ = (eta > 0.0f && gamma > 0.0f) ? sqrtf(eta / ((float)(step_t + 1) * gamma)) : 0.0f;   // F:617-618
@@ -296,6 +298,7 @@ int rau_optim_step(rau_ctx* ctx, int optim, int64_t n, float* x, const float* dx
   if (optim != RAU_OPT_SGD) RAU_TRY(rau_check_dev(state0, "state0"));
   if (optim == RAU_OPT_ADAM) RAU_TRY(rau_check_dev(state1, "state1"));
   RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  ctx->epoch++;
   return k_clip_optim(ctx, optim, n, x, (float*)dx, nullptr, 0.0f, lr, h0, h1, h2, state0, state1, t, nullptr);
 }
 
@@ -331,6 +334,7 @@ int rau_predict(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float*
   RAU_TRY(rau_check_dev(pred, "pred"));
   for (int g = 0; g < 3; ++g) RAU_TRY(rau_check_dev(params[g], "params[g]"));
   RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  ctx->epoch++;
   const int B = bt->B, nHop = cfg->nHop, N = cfg->N, S = cfg->S, H = cfg->H;
   Encoder en;
   RAU_TRY(encoder_alloc(ctx, cfg, B, &en));
@@ -365,6 +369,7 @@ int rau_time_iembed(rau_ctx* ctx, const rau_config* cfg, int B, const float* mul
   RAU_REQUIRE(B > 0 && iters > 0, "B=%d iters=%d", B, iters);
   RAU_TRY(rau_check_dev(mult_params, "mult_params")); RAU_TRY(rau_check_dev(X, "X"));
   RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  ctx->epoch++;
   const int Sp = rau_sp(cfg->S), M = cfg->M, C = cfg->C, S = cfg->S;
   ARENA(Xd, float, "hop.Xd", (size_t)B * C * Sp);
   ARENA(I, float, "time.I", (size_t)B * M * Sp);
@@ -372,7 +377,7 @@ int rau_time_iembed(rau_ctx* ctx, const rau_config* cfg, int B, const float* mul
   RAU_TRY(k_dropout(ctx, X, (int64_t)B * C, S, S, nullptr, 1.0f, Xd, Sp, nullptr, 0, Sp));
   SimtGemm g;
   g.M = M; g.N = Sp; g.K = C;
-  g.A = P.Wi; g.sam = C; g.sak = 1;
+  g.A = P.Wi; g.sam = C; g.sak = 1; g.a_const = 1;
   g.B = Xd; g.sbk = Sp; g.sbn = 1; g.bB = (int64_t)C * Sp;
   g.C = I; g.scm = Sp; g.scn = 1; g.bC = (int64_t)M * Sp;
   g.batch = B; g.bias_m = P.bi; g.act = 1; g.n_valid = S;

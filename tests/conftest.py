@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# route even toy-sized products through the tcgen05 engine so that the parity tests cover its edge cases
+os.environ.setdefault("RAU_TC_MIN_WORK", "0")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
