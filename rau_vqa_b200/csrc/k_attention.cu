@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(ATT_T) attn_bwd_kernel(int M, int A, int S, in
                                                          const float* __restrict__ da, float* __restrict__ ds_out,
                                                          bf16* __restrict__ ds_b, int lddsb, T* __restrict__ dZ,
                                                          float* __restrict__ dqa, bf16* __restrict__ dqa_b,
-                                                         float* __restrict__ gws_part) {
+                                                         float* __restrict__ gws_part, bf16* __restrict__ dZ_hi,
+                                                         bf16* __restrict__ dZ_lo) {
   extern __shared__ float sm[];
   float* ds = sm;          // [Sp]
   float* das = sm + Sp;    // [M]
@@ -77,7 +78,9 @@ __global__ void __launch_bounds__(ATT_T) attn_bwd_kernel(int M, int A, int S, in
   const int b = blockIdx.x, tid = threadIdx.x;
   const T* Eb = E + (int64_t)b * A * Sp;
   const T* Ib = I + (int64_t)b * M * Sp;
-  T* dZb = dZ + (int64_t)b * A * Sp;
+  T* dZb = dZ ? dZ + (int64_t)b * A * Sp : nullptr;
+  bf16* hib = dZ_hi ? dZ_hi + (int64_t)b * A * Sp : nullptr;
+  bf16* lob = dZ_lo ? dZ_lo + (int64_t)b * A * Sp : nullptr;
   for (int m = tid; m < M; m += ATT_T) das[m] = da[(int64_t)b * M + m];
   __syncthreads();
   float pv = 0.0f, dpv = 0.0f;
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(ATT_T) attn_bwd_kernel(int M, int A, int S, in
   const int warp = tid >> 5, lane = tid & 31, nw = ATT_T / 32;
   for (int a = warp; a < A; a += nw) {
     const T* row = Eb + (int64_t)a * Sp;
-    T* drow = dZb + (int64_t)a * Sp;
+    T* drow = dZb ? dZb + (int64_t)a * Sp : nullptr;
     const float w = ws[a];
     float sz = 0.0f, sg = 0.0f;
     for (int s = lane; s < Sp; s += 32) {
@@ -108,7 +111,12 @@ __global__ void __launch_bounds__(ATT_T) attn_bwd_kernel(int M, int A, int S, in
         sg = fmaf(ds[s], e, sg);
         sz += dz;
       }
-      stf<T>(drow + s, dz);
+      if (drow) stf<T>(drow + s, dz);
+      if (hib) {
+        const bf16 h = __float2bfloat16(dz);
+        hib[(int64_t)a * Sp + s] = h;
+        if (lob) lob[(int64_t)a * Sp + s] = __float2bfloat16(dz - __bfloat162float(h));
+      }
     }
     sz = warp_sum(sz);
     sg = warp_sum(sg);
@@ -134,6 +142,39 @@ __global__ void iembed_bwd_pw_kernel(int64_t total, int M, int S, int Sp, const 
       v = (dI[i] + da[bm] * p[(int64_t)b * S + s]) * (1.0f - y * y);
     }
     stf<T>(dY + i, v);
+  }
+}
+
+// one warp per (image, channel) row of 196 cells: dY = (dI + da p) (1 - I^2)
+__global__ void __launch_bounds__(256) iembed_bwd_rows_kernel(int64_t rows, int M, int S, int Sp, const float* __restrict__ dI,
+                                                              const float* __restrict__ I, const float* __restrict__ da,
+                                                              const float* __restrict__ p, float* __restrict__ dY,
+                                                              bf16* __restrict__ hi, bf16* __restrict__ lo,
+                                                              float* __restrict__ gbi) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = w0; row < rows; row += nw) {
+    const int64_t b = row / M;
+    const int m = (int)(row % M);
+    const float d = da[row];
+    const float* pr = p + b * S;
+    float sum = 0.0f;
+    for (int s = lane; s < Sp; s += 32) {
+      float v = 0.0f;
+      if (s < S) {
+        const float y = I[row * Sp + s];
+        v = (dI[row * Sp + s] + d * pr[s]) * (1.0f - y * y);
+        sum += v;
+      }
+      if (dY) dY[row * Sp + s] = v;
+      if (hi) {
+        const bf16 h = __float2bfloat16(v);
+        hi[row * Sp + s] = h;
+        if (lo) lo[row * Sp + s] = __float2bfloat16(v - __bfloat162float(h));
+      }
+    }
+    sum = warp_sum(sum);
+    if (lane == 0 && gbi) atomicAdd(&gbi[m], sum);
   }
 }
 
@@ -309,15 +350,15 @@ template int k_attn_fwd<bf16>(rau_ctx*, int, int, int, int, int, const bf16*, co
 template <typename T>
 int k_attn_bwd(rau_ctx* ctx, int B, int M, int A, int S, int Sp, const T* E, const T* I, const float* ws, const float* p,
                const float* dp_in, const float* da, float* ds, bf16* ds_b, int lddsb, T* dZ, float* dqa, bf16* dqa_b,
-               float* gws_part) {
+               float* gws_part, bf16* dZ_hi, bf16* dZ_lo) {
   if (S > ATT_T || Sp > ATT_T || lddsb > ATT_T) { rau_set_error("attention grid S=%d too large", S); return RAU_EINVAL; }
   attn_bwd_kernel<T><<<B, ATT_T, (Sp + M) * sizeof(float), ctx->stream>>>(M, A, S, Sp, E, I, ws, p, dp_in, da, ds, ds_b, lddsb,
-                                                                          dZ, dqa, dqa_b, gws_part);
+                                                                          dZ, dqa, dqa_b, gws_part, dZ_hi, dZ_lo);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
-template int k_attn_bwd<float>(rau_ctx*, int, int, int, int, int, const float*, const float*, const float*, const float*, const float*, const float*, float*, bf16*, int, float*, float*, bf16*, float*);
-template int k_attn_bwd<bf16>(rau_ctx*, int, int, int, int, int, const bf16*, const bf16*, const float*, const float*, const float*, const float*, float*, bf16*, int, bf16*, float*, bf16*, float*);
+template int k_attn_bwd<float>(rau_ctx*, int, int, int, int, int, const float*, const float*, const float*, const float*, const float*, const float*, float*, bf16*, int, float*, float*, bf16*, float*, bf16*, bf16*);
+template int k_attn_bwd<bf16>(rau_ctx*, int, int, int, int, int, const bf16*, const bf16*, const float*, const float*, const float*, const float*, float*, bf16*, int, bf16*, float*, bf16*, float*, bf16*, bf16*);
 
 template <typename T>
 int k_iembed_bwd_pw(rau_ctx* ctx, int B, int M, int S, int Sp, const float* dI, const T* I, const float* da, const float* p, T* dY) {
@@ -330,6 +371,16 @@ int k_iembed_bwd_pw(rau_ctx* ctx, int B, int M, int S, int Sp, const float* dI, 
 }
 template int k_iembed_bwd_pw<float>(rau_ctx*, int, int, int, int, const float*, const float*, const float*, const float*, float*);
 template int k_iembed_bwd_pw<bf16>(rau_ctx*, int, int, int, int, const float*, const bf16*, const float*, const float*, bf16*);
+
+int k_iembed_bwd_rows(rau_ctx* ctx, int B, int M, int S, int Sp, const float* dI, const float* I, const float* da,
+                      const float* p, float* dY, bf16* dY_hi, bf16* dY_lo, float* gbi) {
+  const int64_t rows = (int64_t)B * M;
+  int64_t blocks = (rows + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  iembed_bwd_rows_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(rows, M, S, Sp, dI, I, da, p, dY, dY_hi, dY_lo, gbi);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
 
 int k_softmax_ce(rau_ctx* ctx, int B, int N, const float* score, const float* labels, float loss_scale, float grad_scale,
                  float* loss_sum, float* dscore_f, bf16* dscore_b, int lddb, float* answers) {

@@ -20,18 +20,21 @@ namespace {
 constexpr int TC_BM = 128;        // TMEM lanes per tile (UMMA M)
 constexpr int TC_BK = 64;         // k elements per pipeline stage = one 128-byte swizzle row of bf16
 constexpr int TC_THREADS = 320;   // 10 warps
-constexpr int TC_MAXSEG = 6;
-constexpr int TC_SMEM_BUDGET = 100 * 1024;   // two CTAs per SM
+constexpr int TC_MAXSEG = 2;
+constexpr int TC_SMEM_2CTA = 100 * 1024;    // two CTAs per SM when the grid is large
+constexpr int TC_SMEM_1CTA = 200 * 1024;    // deeper pipeline when there is at most one CTA per SM anyway
 
 struct TcParams {
-  CUtensorMap mapP[TC_MAXSEG], mapQ[TC_MAXSEG];
+  CUtensorMap mapP[TC_MAXSEG][2], mapQ[TC_MAXSEG][2];   // [segment][hi, lo]
   int nseg, kblocks[TC_MAXSEG];
+  int split;                      // 1: one product per k-block; 2: bf16x3 (hi*hi + hi*lo + lo*hi on tiles loaded once)
   int p_mn, q_mn;                 // 1 = MN-major operand
   int p_zmode, q_zmode;           // 0 = shared (z = 0), 1 = independent batch (z = bz), 2 = reduced batch (z = kb)
   int kbatch, ksplit;
   int BN, stages, tmem_cols;
   int extI, extJ, i_valid, j_valid;
   float* C; long long sci, scj, bC;
+  bf16 *C_hi, *C_lo;              // optional bf16 (hi, lo) copies of the result, indexed like C
   float alpha;
   const float *bias_i, *bias_i2, *bias_j, *bias_j2, *bias_bi, *bias_bj;
   const float *addend, *addend2; long long sdi, sdj, bD;
@@ -103,20 +106,23 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int BN = p.BN;
   const int BNbox = (BN + 63) / 64 * 64;                 // smem footprint of a Q tile (MN-major chunks are 64 wide)
+  const int nt = p.split;                                // tiles per operand per stage (hi [, lo])
   const uint32_t p_bytes = TC_BM * TC_BK * 2, q_bytes = (uint32_t)BNbox * TC_BK * 2;
-  const uint32_t stage_bytes = p_bytes + q_bytes;
-  const uint32_t tx_bytes = p_bytes + (p.q_mn ? q_bytes : (uint32_t)BN * TC_BK * 2);   // bytes the TMA boxes deliver
+  const uint32_t stage_bytes = nt * (p_bytes + q_bytes);
+  const uint32_t tx_bytes = nt * (p_bytes + (p.q_mn ? q_bytes : (uint32_t)BN * TC_BK * 2));   // bytes the TMA boxes deliver
   const int i0 = blockIdx.y * TC_BM, j0 = blockIdx.x * BN;
   const int bz = blockIdx.z / p.ksplit, ks = blockIdx.z % p.ksplit;
-  int kb_lo = 0, kb_hi = p.kbatch;
-  if (p.ksplit > 1) {
-    const int per = (p.kbatch + p.ksplit - 1) / p.ksplit;
-    kb_lo = ks * per;
-    kb_hi = min(p.kbatch, kb_lo + per);
-  }
   int kper = 0;
   for (int s = 0; s < p.nseg; ++s) kper += p.kblocks[s];
-  const int total = max(kb_hi - kb_lo, 0) * kper;
+  // the reduction space is (reduced batch kb) x (segment) x (k-block), flattened; split-K slices partition it evenly
+  const int space = p.kbatch * kper;
+  int it_lo = 0, it_hi = space;
+  if (p.ksplit > 1) {
+    const int per = (space + p.ksplit - 1) / p.ksplit;
+    it_lo = min(space, ks * per);
+    it_hi = min(space, it_lo + per);
+  }
+  const int total = it_hi - it_lo;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -137,30 +143,33 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const __grid_con
   if (warp == 0) {
     // ===================== TMA producer
     if (lane == 0) {
-      int it = 0;
-      for (int kb = kb_lo; kb < kb_hi; ++kb) {
+      for (int n = 0; n < total; ++n) {
+        const int it = it_lo + n;
+        const int kb = it / kper;
+        int kk = it - kb * kper, s = 0;
+        while (kk >= p.kblocks[s]) { kk -= p.kblocks[s]; ++s; }
         const int zp = p.p_zmode == 1 ? bz : (p.p_zmode == 2 ? kb : 0);
         const int zq = p.q_zmode == 1 ? bz : (p.q_zmode == 2 ? kb : 0);
-        for (int s = 0; s < p.nseg; ++s) {
-          for (int kk = 0; kk < p.kblocks[s]; ++kk, ++it) {
-            const int st = it % p.stages;
-            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-            mbar_wait(&empty_bar[st], ph ^ 1u);
-            uint8_t* sp = smem + (size_t)st * stage_bytes;
-            uint8_t* sq = sp + p_bytes;
-            mbar_expect_tx(&full_bar[st], tx_bytes);
-            if (p.p_mn) {   // [k rows][64 i] boxes, one per 64-wide chunk of i
-              tma_load_3d(sp, &p.mapP[s], &full_bar[st], i0, kk * TC_BK, zp);
-              tma_load_3d(sp + 8192, &p.mapP[s], &full_bar[st], i0 + 64, kk * TC_BK, zp);
-            } else {        // [128 i rows][64 k]
-              tma_load_3d(sp, &p.mapP[s], &full_bar[st], kk * TC_BK, i0, zp);
-            }
-            if (p.q_mn) {
-              for (int c = 0; c < BNbox / 64; ++c)
-                tma_load_3d(sq + c * 8192, &p.mapQ[s], &full_bar[st], j0 + c * 64, kk * TC_BK, zq);
-            } else {
-              tma_load_3d(sq, &p.mapQ[s], &full_bar[st], kk * TC_BK, j0, zq);
-            }
+        const int st = n % p.stages;
+        const uint32_t ph = (uint32_t)(n / p.stages) & 1u;
+        mbar_wait(&empty_bar[st], ph ^ 1u);
+        uint8_t* sp = smem + (size_t)st * stage_bytes;
+        uint8_t* sq = sp + nt * p_bytes;
+        mbar_expect_tx(&full_bar[st], tx_bytes);
+        for (int h = 0; h < nt; ++h) {
+          uint8_t* dp = sp + h * p_bytes;
+          if (p.p_mn) {   // [k rows][64 i] boxes, one per 64-wide chunk of i
+            tma_load_3d(dp, &p.mapP[s][h], &full_bar[st], i0, kk * TC_BK, zp);
+            tma_load_3d(dp + 8192, &p.mapP[s][h], &full_bar[st], i0 + 64, kk * TC_BK, zp);
+          } else {        // [128 i rows][64 k]
+            tma_load_3d(dp, &p.mapP[s][h], &full_bar[st], kk * TC_BK, i0, zp);
+          }
+          uint8_t* dq = sq + h * q_bytes;
+          if (p.q_mn) {
+            for (int c = 0; c < BNbox / 64; ++c)
+              tma_load_3d(dq + c * 8192, &p.mapQ[s][h], &full_bar[st], j0 + c * 64, kk * TC_BK, zq);
+          } else {
+            tma_load_3d(dq, &p.mapQ[s][h], &full_bar[st], kk * TC_BK, j0, zq);
           }
         }
       }
@@ -172,21 +181,25 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const __grid_con
       // a_major [15] | b_major [16] | N>>3 [17,23) | M>>4 [24,29)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.p_mn << 15) | ((uint32_t)p.q_mn << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      for (int it = 0; it < total; ++it) {
-        const int st = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+      // K-major: rows of 128 B, 8-row atoms 1024 B apart (SBO); a 16-element k step is +32 B inside the swizzle row.
+      // MN-major: 64-wide chunks of i/j 8192 B apart (LBO), 8-k-row atoms 1024 B apart (SBO); a k step is 16 rows = 2048 B.
+      const uint32_t ka = p.p_mn ? (2048u >> 4) : (32u >> 4), kq = p.q_mn ? (2048u >> 4) : (32u >> 4);
+      const int ncombo = nt == 2 ? 3 : 1;
+      for (int n = 0; n < total; ++n) {
+        const int st = n % p.stages;
+        const uint32_t ph = (uint32_t)(n / p.stages) & 1u;
         mbar_wait(&full_bar[st], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sp = smem_u32(smem + (size_t)st * stage_bytes);
-        const uint32_t sq = sp + p_bytes;
-        // K-major: rows of 128 B, 8-row atoms 1024 B apart (SBO); a 16-element k step is +32 B inside the swizzle row.
-        // MN-major: 64-wide chunks of i/j 8192 B apart (LBO), 8-k-row atoms 1024 B apart (SBO); a k step is 16 rows = 2048 B.
-        const uint64_t da = p.p_mn ? make_desc(sp, 8192, 1024) : make_desc(sp, 16, 1024);
-        const uint64_t db = p.q_mn ? make_desc(sq, 8192, 1024) : make_desc(sq, 16, 1024);
-        const uint32_t ka = p.p_mn ? (2048u >> 4) : (32u >> 4), kq = p.q_mn ? (2048u >> 4) : (32u >> 4);
+        const uint32_t sq = sp + nt * p_bytes;
+        for (int c = 0; c < ncombo; ++c) {   // hi*hi, hi*lo, lo*hi
+          const uint32_t pa = sp + (c == 2 ? p_bytes : 0), qa = sq + (c == 1 ? q_bytes : 0);
+          const uint64_t da = p.p_mn ? make_desc(pa, 8192, 1024) : make_desc(pa, 16, 1024);
+          const uint64_t db = p.q_mn ? make_desc(qa, 8192, 1024) : make_desc(qa, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k)
-          umma_bf16(tmem_base, da + (uint64_t)(k * ka), db + (uint64_t)(k * kq), idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_bf16(tmem_base, da + (uint64_t)(k * ka), db + (uint64_t)(k * kq), idesc, (n > 0 || c > 0 || k > 0) ? 1u : 0u);
+        }
         umma_commit(&empty_bar[st]);   // frees the stage when these MMAs have read it
       }
       umma_commit(&acc_bar);           // accumulator complete
@@ -200,8 +213,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const __grid_con
     const int nchunk = (BN + 15) / 16;
     const int c_lo = half == 0 ? 0 : (nchunk + 1) / 2, c_hi = half == 0 ? (nchunk + 1) / 2 : nchunk;
     const bool i_ok = i < p.extI;
+    const bool lead = ks == 0;                     // under split-K only slice 0 applies biases / addends
     float bi = 0.0f;
-    if (i_ok) {
+    if (i_ok && lead) {
       if (p.bias_i) bi += p.bias_i[i];
       if (p.bias_i2) bi += p.bias_i2[i];
       if (p.bias_bi) bi += p.bias_bi[(long long)bz * p.extI + i];
@@ -222,10 +236,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const __grid_con
         const int j = j0 + c * 16 + k;
         if (j >= p.extJ || c * 16 + k >= BN) continue;
         float x = v[k] * p.alpha + bi;
-        if (p.bias_j) x += p.bias_j[j];
-        if (p.bias_j2) x += p.bias_j2[j];
-        if (p.bias_bj) x += p.bias_bj[(long long)bz * p.extJ + j];
-        if (Drow) {
+        if (lead) {
+          if (p.bias_j) x += p.bias_j[j];
+          if (p.bias_j2) x += p.bias_j2[j];
+          if (p.bias_bj) x += p.bias_bj[(long long)bz * p.extJ + j];
+        }
+        if (Drow && lead) {
           x += Drow[(long long)j * p.sdj];
           if (D2row) x += D2row[(long long)j * p.sdj];
         }
@@ -236,6 +252,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const __grid_con
         if (p.atomic) atomicAdd(dst, x);
         else if (p.accumulate) *dst += x;
         else *dst = x;
+        if (p.C_hi) {
+          const long long o = (long long)bz * p.bC + (long long)i * p.sci + (long long)j * p.scj;
+          const bf16 h = __float2bfloat16(x);
+          p.C_hi[o] = h;
+          if (p.C_lo) p.C_lo[o] = __float2bfloat16(x - __bfloat162float(h));
+        }
       }
     }
   }
@@ -264,6 +286,30 @@ __global__ void pack_bf16_kernel(const float* __restrict__ in, long long sb, lon
   }
 }
 
+// same, four columns per thread (Cc, ld, sb multiples of 4; 16-byte aligned input): 128-bit loads, 64-bit stores
+__global__ void pack_bf16_vec4_kernel(const float* __restrict__ in, long long sb, long long ld, int nb, int R, int Cc, int ldo,
+                                      bf16* __restrict__ hi, bf16* __restrict__ lo) {
+  const int q = ldo >> 2;
+  const long long total = (long long)nb * R * q;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % q) * 4;
+    const long long br = idx / q;
+    const int r = (int)(br % R);
+    const long long b = br / R;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < Cc) x = *reinterpret_cast<const float4*>(in + b * sb + (long long)r * ld + c);
+    const float xs[4] = {x.x, x.y, x.z, x.w};
+    __align__(8) bf16 h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      h[k] = __float2bfloat16(xs[k]);
+      l[k] = __float2bfloat16(xs[k] - __bfloat162float(h[k]));
+    }
+    *reinterpret_cast<uint2*>(hi + idx * 4) = *reinterpret_cast<const uint2*>(h);
+    if (lo) *reinterpret_cast<uint2*>(lo + idx * 4) = *reinterpret_cast<const uint2*>(l);
+  }
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -287,9 +333,10 @@ struct Operand {
   const float* ptr; int ext, K; long long s_ext, s_k;   // element (e, k) at ptr[e*s_ext + k*s_k]
   int zmode; int nz; long long s_z;                      // third coordinate
   bool is_const;
+  const bf16 *pre_hi, *pre_lo;                           // producer already wrote the packed (hi, lo) form
 };
 
-struct Packed { bf16 *hi = nullptr, *lo = nullptr; int mn = 0, R = 0, Cc = 0, ldo = 0, nz = 1; };
+struct Packed { const bf16 *hi = nullptr, *lo = nullptr; int mn = 0, R = 0, Cc = 0, ldo = 0, nz = 1; };
 
 int pack_operand(rau_ctx* ctx, const Operand& o, bool want_lo, const char* slot, Packed* out) {
   Packed pk;
@@ -300,6 +347,15 @@ int pack_operand(rau_ctx* ctx, const Operand& o, bool want_lo, const char* slot,
   pk.ldo = (pk.Cc + 7) / 8 * 8;
   pk.nz = o.nz;
   const long long ld = pk.mn ? o.s_k : o.s_ext;
+  if (o.pre_hi && (!want_lo || o.pre_lo)) {
+    // producers write rows of pitch ld (a multiple of 8) and batches of pitch s_z, zero padded
+    if (ld % 8 != 0 || (o.nz > 1 && o.s_z != (long long)pk.R * ld)) return 1;
+    pk.ldo = (int)ld;
+    pk.hi = o.pre_hi;
+    pk.lo = o.pre_lo;
+    *out = pk;
+    return RAU_OK;
+  }
   const size_t elems = (size_t)pk.nz * pk.R * pk.ldo;
   char name[160];
   bool cached = false;
@@ -311,14 +367,19 @@ int pack_operand(rau_ctx* ctx, const Operand& o, bool want_lo, const char* slot,
     snprintf(name, sizeof(name), "tc.%s", slot);
   }
   void* buf = nullptr;
-  RAU_TRY(ctx->arena.get(name, elems * sizeof(bf16) * (want_lo ? 2 : 1) + 256, &buf));
-  pk.hi = (bf16*)buf;
-  pk.lo = want_lo ? pk.hi + ((elems + 127) / 128 * 128) : nullptr;
+  RAU_TRY(ctx->arena.get(name, elems * sizeof(bf16) * (want_lo ? 2 : 1) + 512, &buf));
+  bf16* hi = (bf16*)buf;
+  bf16* lo = want_lo ? hi + ((elems + 127) / 128 * 128) : nullptr;
+  pk.hi = hi;
+  pk.lo = lo;
   if (!cached) {
-    long long blocks = ((long long)elems + 255) / 256;
+    const bool vec = (pk.Cc % 4 == 0) && (ld % 4 == 0) && (o.s_z % 4 == 0) && (((uintptr_t)o.ptr & 15) == 0);
+    long long work = vec ? (long long)elems / 4 : (long long)elems;
+    long long blocks = (work + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    pack_bf16_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(o.ptr, o.s_z, ld, pk.nz, pk.R, pk.Cc, pk.ldo, pk.hi, pk.lo);
+    if (vec) pack_bf16_vec4_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(o.ptr, o.s_z, ld, pk.nz, pk.R, pk.Cc, pk.ldo, hi, lo);
+    else pack_bf16_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(o.ptr, o.s_z, ld, pk.nz, pk.R, pk.Cc, pk.ldo, hi, lo);
     RAU_LAUNCH_CHECK(ctx);
     if (o.is_const) ctx->tc_epoch[name] = ctx->epoch;
   }
@@ -359,10 +420,9 @@ long long tc_min_work() {
 int tc_gemm_try(rau_ctx* ctx, const SimtGemm& g) {
   if (ctx->precision == RAU_PREC_F32) return 0;
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
-  // tiny or vector-like products stay on the CUDA cores
-  if ((long long)g.M * g.N * (long long)(g.K + g.K2) * g.kbatch < tc_min_work()) return 0;
+  const bool prepacked = g.A_hi || g.B_hi;     // producers skipped the fp32 form: this engine must take the product
+  if (!prepacked && (long long)g.M * g.N * (long long)(g.K + g.K2) * g.kbatch < tc_min_work()) return 0;
   if (g.batch > 1 && g.kbatch > 1) return 0;
-  if (g.ksplit > 1 && g.kbatch <= 1) return 0;   // split over K itself is not wired into this engine
   RAU_TRY(get_encode());
   const bool x3 = ctx->precision == RAU_PREC_BF16X3;
 
@@ -373,20 +433,20 @@ int tc_gemm_try(rau_ctx* ctx, const SimtGemm& g) {
   const int zmodeB = g.batch > 1 ? (g.bB ? 1 : 0) : (g.kbatch > 1 ? (g.kB ? 2 : 0) : 0);
   const int nzv = g.batch > 1 ? g.batch : g.kbatch;
   Operand opA[2], opB[2];
-  int nseg_in = 1;
-  opA[0] = Operand{g.A, g.M, g.K, g.sam, g.sak, zmodeA, zmodeA ? nzv : 1, g.batch > 1 ? g.bA : g.kA, g.a_const != 0};
-  opB[0] = Operand{g.B, g.N, g.K, g.sbn, g.sbk, zmodeB, zmodeB ? nzv : 1, g.batch > 1 ? g.bB : g.kB, g.b_const != 0};
+  int nseg = 1;
+  opA[0] = Operand{g.A, g.M, g.K, g.sam, g.sak, zmodeA, zmodeA ? nzv : 1, g.batch > 1 ? g.bA : g.kA, g.a_const != 0, g.A_hi, g.A_lo};
+  opB[0] = Operand{g.B, g.N, g.K, g.sbn, g.sbk, zmodeB, zmodeB ? nzv : 1, g.batch > 1 ? g.bB : g.kB, g.b_const != 0, g.B_hi, g.B_lo};
   if (g.A2) {
     if (g.batch > 1 || g.kbatch > 1) return 0;
-    opA[1] = Operand{g.A2, g.M, g.K2, g.sam2, g.sak2, 0, 1, 0, g.a_const != 0};
-    opB[1] = Operand{g.B2, g.N, g.K2, g.sbn2, g.sbk2, 0, 1, 0, g.b_const != 0};
-    nseg_in = 2;
+    opA[1] = Operand{g.A2, g.M, g.K2, g.sam2, g.sak2, 0, 1, 0, g.a_const != 0, nullptr, nullptr};
+    opB[1] = Operand{g.B2, g.N, g.K2, g.sbn2, g.sbk2, 0, 1, 0, g.b_const != 0, nullptr, nullptr};
+    nseg = 2;
   }
+
   TcParams p;
   memset(&p, 0, sizeof(p));
   Packed pkP[2], pkQ[2];
-  if (nseg_in * (x3 ? 3 : 1) > TC_MAXSEG) return 0;
-  for (int s = 0; s < nseg_in; ++s) {
+  for (int s = 0; s < nseg; ++s) {
     const Operand& oP = swap ? opB[s] : opA[s];
     const Operand& oQ = swap ? opA[s] : opB[s];
     char slotP[16], slotQ[16];
@@ -401,53 +461,80 @@ int tc_gemm_try(rau_ctx* ctx, const SimtGemm& g) {
     if (s > 0 && (pkP[s].mn != pkP[0].mn || pkQ[s].mn != pkQ[0].mn)) return 0;
   }
   const int extI = swap ? g.N : g.M, extJ = swap ? g.M : g.N;
+  const int nt = x3 ? 2 : 1;
+  int kper = 0;
+  for (int s = 0; s < nseg; ++s) {
+    p.kblocks[s] = ((swap ? opB[s].K : opA[s].K) + TC_BK - 1) / TC_BK;
+    kper += p.kblocks[s];
+  }
+  const int space = kper * g.kbatch;
   // tile width: keep whole rows of j in one tile when they fit, shrink to spread small problems over the SMs
   int BN = extJ <= 256 ? (extJ + 15) / 16 * 16 : 256;
   const long long itiles = (extI + TC_BM - 1) / TC_BM;
-  const long long zcount = (long long)g.batch * g.ksplit;
-  while (BN > 64 && itiles * ((extJ + BN - 1) / BN) * zcount < 148 && (BN / 2) % 16 == 0) BN /= 2;
+  while (BN > 64 && itiles * ((extJ + BN - 1) / BN) * g.batch * g.ksplit < 148 && (BN / 2) % 16 == 0) BN /= 2;
   const int BNbox = (BN + 63) / 64 * 64;
+  const long long tiles = itiles * ((extJ + BN - 1) / BN) * g.batch;
+  // split-K: requested by the caller (accumulating products), or chosen here for latency-bound products that would
+  // leave most SMs idle: slices add into C with atomics, slice 0 carries biases/addends, C is cleared first
+  int ksplit = g.ksplit;
+  bool clear_c = false;
+  if (ksplit == 1 && g.act == 0 && g.n_valid < 0 && g.batch == 1 && tiles * 2 <= 148 && space >= 8 && g.C_hi == nullptr &&
+      g.addend != g.C && g.addend2 != g.C) {
+    int want = (int)(148 / tiles);
+    if (want > space / 4) want = space / 4;
+    if (want > 16) want = 16;
+    if (want >= 2) {
+      ksplit = want;
+      clear_c = !g.accumulate;
+    }
+  }
+  if (clear_c && !(g.scn == 1 || g.scm == 1)) { ksplit = 1; clear_c = false; }
   p.BN = BN;
+  p.split = nt;
+  p.nseg = nseg;
   p.p_mn = pkP[0].mn; p.q_mn = pkQ[0].mn;
   const Operand& oP0 = swap ? opB[0] : opA[0];
   const Operand& oQ0 = swap ? opA[0] : opB[0];
   p.p_zmode = oP0.zmode; p.q_zmode = oQ0.zmode;
-  p.kbatch = g.kbatch; p.ksplit = g.ksplit;
-  int ns = 0;
-  for (int s = 0; s < nseg_in; ++s) {
-    const int kblocks = ((swap ? opB[s].K : opA[s].K) + TC_BK - 1) / TC_BK;
-    const int combos = x3 ? 3 : 1;
-    for (int c = 0; c < combos; ++c, ++ns) {
-      const bf16* bp = (c == 2) ? pkP[s].lo : pkP[s].hi;     // hi*hi, hi*lo, lo*hi
-      const bf16* bq = (c == 1) ? pkQ[s].lo : pkQ[s].hi;
-      RAU_TRY(encode_map(&p.mapP[ns], bp, pkP[s], pkP[s].mn ? TC_BK : TC_BM));
-      RAU_TRY(encode_map(&p.mapQ[ns], bq, pkQ[s], pkQ[s].mn ? TC_BK : BN));
-      p.kblocks[ns] = kblocks;
+  p.kbatch = g.kbatch; p.ksplit = ksplit;
+  for (int s = 0; s < nseg; ++s) {
+    for (int h = 0; h < nt; ++h) {
+      RAU_TRY(encode_map(&p.mapP[s][h], h ? pkP[s].lo : pkP[s].hi, pkP[s], pkP[s].mn ? TC_BK : TC_BM));
+      RAU_TRY(encode_map(&p.mapQ[s][h], h ? pkQ[s].lo : pkQ[s].hi, pkQ[s], pkQ[s].mn ? TC_BK : BN));
     }
   }
-  p.nseg = ns;
-  const int stage_bytes = TC_BM * TC_BK * 2 + BNbox * TC_BK * 2;
-  p.stages = TC_SMEM_BUDGET / stage_bytes;
+  const int stage_bytes = nt * (TC_BM * TC_BK * 2 + BNbox * TC_BK * 2);
+  const long long ctas = tiles * ksplit;
+  const int budget = ctas <= 148 ? TC_SMEM_1CTA : TC_SMEM_2CTA;
+  p.stages = budget / stage_bytes;
   if (p.stages > 8) p.stages = 8;
   if (p.stages < 2) p.stages = 2;
+  if (p.stages > space) p.stages = space < 2 ? 2 : space;
   p.tmem_cols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   p.extI = extI; p.extJ = extJ;
   p.i_valid = extI; p.j_valid = extJ;
   if (g.n_valid >= 0) { if (swap) p.i_valid = g.n_valid; else p.j_valid = g.n_valid; }
   p.C = g.C; p.sci = swap ? g.scn : g.scm; p.scj = swap ? g.scm : g.scn; p.bC = g.bC;
+  p.C_hi = g.C_hi; p.C_lo = x3 ? g.C_lo : nullptr;
   p.alpha = g.alpha;
   if (swap) { p.bias_j = g.bias_m; p.bias_i = g.bias_n; p.bias_i2 = g.bias_n2; p.bias_bj = g.bias_bm; }
   else { p.bias_i = g.bias_m; p.bias_j = g.bias_n; p.bias_j2 = g.bias_n2; p.bias_bi = g.bias_bm; }
   p.addend = g.addend; p.addend2 = g.addend2; p.bD = g.bD;
   p.sdi = swap ? g.sdn : g.sdm; p.sdj = swap ? g.sdm : g.sdn;
-  p.act = g.act; p.accumulate = g.accumulate; p.atomic = g.ksplit > 1 ? 1 : 0;
+  p.act = g.act; p.accumulate = g.accumulate; p.atomic = ksplit > 1 ? 1 : 0;
+  if (clear_c) {
+    if (g.scn == 1)
+      RAU_CHECK_CUDA(cudaMemset2DAsync(g.C, (size_t)g.scm * 4, 0, (size_t)g.N * 4, (size_t)g.M, ctx->stream));
+    else
+      RAU_CHECK_CUDA(cudaMemset2DAsync(g.C, (size_t)g.scn * 4, 0, (size_t)g.M * 4, (size_t)g.N, ctx->stream));
+  }
 
   const int smem_bytes = p.stages * stage_bytes + 1024;
   if (!g_attr_set) {
-    RAU_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    RAU_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     g_attr_set = true;
   }
-  dim3 grid((extJ + BN - 1) / BN, (unsigned)itiles, (unsigned)zcount);
+  dim3 grid((extJ + BN - 1) / BN, (unsigned)itiles, (unsigned)(g.batch * ksplit));
   tc_gemm_kernel<<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p);
   RAU_LAUNCH_CHECK(ctx);
   return 1;

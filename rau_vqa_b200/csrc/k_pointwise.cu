@@ -157,6 +157,36 @@ __global__ void dropout_kernel(const float* __restrict__ x, int64_t rows, int co
   }
 }
 
+// nn.Dropout fused with the tcgen05 operand packing: y = x * keep * scale written only as bf16 (hi, lo) rows of
+// pitch cols_pad (zero padded).  Four columns per thread: 128-bit loads, 64-bit stores.
+__global__ void dropout_pack_kernel(const float* __restrict__ x, int64_t rows, int cols, const uint32_t* __restrict__ bits,
+                                    float scale, bf16* __restrict__ hi, bf16* __restrict__ lo, int cols_pad) {
+  const int q = cols_pad >> 2;
+  const int64_t total = rows * q;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / q;
+    const int c = (int)(i % q) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c + 3 < cols) {
+      const float4 t = *reinterpret_cast<const float4*>(x + r * cols + c);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (c + k < cols) v[k] = x[r * cols + c + k];
+    }
+    __align__(8) bf16 h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float y = (c + k < cols) ? v[k] * keep_scale(bits, r * cols + c + k, scale) : 0.0f;
+      h[k] = __float2bfloat16(y);
+      l[k] = __float2bfloat16(y - __bfloat162float(h[k]));
+    }
+    *reinterpret_cast<uint2*>(hi + i * 4) = *reinterpret_cast<const uint2*>(h);
+    if (lo) *reinterpret_cast<uint2*>(lo + i * 4) = *reinterpret_cast<const uint2*>(l);
+  }
+}
+
 __global__ void dropout_bwd_acc_kernel(const float* __restrict__ dx, int64_t n, const uint32_t* __restrict__ bits,
                                        float scale, float* __restrict__ y, int accumulate) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -250,12 +280,12 @@ __global__ void rowsum_bms_kernel(const T* __restrict__ x, int B, int M, int S, 
   __shared__ float red[32];
   const int m = blockIdx.x;
   float s = 0.0f;
-  for (int b = 0; b < B; ++b) {
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
     const T* row = x + ((int64_t)b * M + m) * Sp;
     for (int k = threadIdx.x; k < S; k += blockDim.x) s += ldf<T>(row + k);
   }
   s = block_sum(s, red);
-  if (threadIdx.x == 0) out[m] += s;
+  if (threadIdx.x == 0) atomicAdd(&out[m], s);
 }
 
 __global__ void sum_all_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out, int accumulate) {
@@ -328,6 +358,16 @@ int k_dropout(rau_ctx* ctx, const float* x, int64_t rows, int cols, int ldx, con
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
+int k_dropout_pack(rau_ctx* ctx, const float* x, int64_t rows, int cols, const uint32_t* bits, float scale, bf16* hi, bf16* lo,
+                   int cols_pad) {
+  if (cols % 4 != 0 || cols_pad % 4 != 0 || ((uintptr_t)x & 15) != 0) {
+    rau_set_error("k_dropout_pack: cols=%d cols_pad=%d must be multiples of 4 and x 16-byte aligned", cols, cols_pad);
+    return RAU_EINVAL;
+  }
+  dropout_pack_kernel<<<grid_for(rows * (cols_pad / 4), 2), TPB, 0, ctx->stream>>>(x, rows, cols, bits, scale, hi, lo, cols_pad);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
 int k_dropout_bwd_acc(rau_ctx* ctx, const float* dx, int64_t n, const uint32_t* bits, float scale, float* y, int accumulate) {
   dropout_bwd_acc_kernel<<<grid_for(n, 4), TPB, 0, ctx->stream>>>(dx, n, bits, scale, y, accumulate);
   RAU_LAUNCH_CHECK(ctx);
@@ -377,7 +417,7 @@ int k_colsum(rau_ctx* ctx, const float* x, int64_t rows, int cols, int ld, float
 }
 template <typename T>
 int k_rowsum_bms(rau_ctx* ctx, const T* x, int B, int M, int S, int Sp, float* out) {
-  rowsum_bms_kernel<T><<<M, TPB, 0, ctx->stream>>>(x, B, M, S, Sp, out);
+  rowsum_bms_kernel<T><<<dim3(M, B >= 16 ? 16 : 1), 64, 0, ctx->stream>>>(x, B, M, S, Sp, out);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }

@@ -153,6 +153,10 @@ struct SimtGemm {
   const float* addend = nullptr; int64_t sdm = 0, sdn = 1, bD = 0;  // same indexing as C
   const float* addend2 = nullptr;  // same strides as addend
   int a_const = 0, b_const = 0;    // operand is a parameter tensor (constant within one public call)
+  // tcgen05 engine only: operands a producer already wrote as packed bf16 (hi, lo) with the fp32 operand's own
+  // indexing, and optional bf16 (hi, lo) copies of the result indexed like C
+  const bf16 *A_hi = nullptr, *A_lo = nullptr, *B_hi = nullptr, *B_lo = nullptr;
+  bf16 *C_hi = nullptr, *C_lo = nullptr;
   int accumulate = 0;
   float alpha = 1.0f;
   int act = 0;                     // 0 none, 1 tanh, 2 sigmoid

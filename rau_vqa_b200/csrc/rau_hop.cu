@@ -29,6 +29,10 @@ size_t hop_saved_layout(const rau_config* cfg, int B, void* base, HopSaved* sv) 
   s.hout = (float*)take(sizeof(float) * B * cfg->H);
   s.m = (float*)take(sizeof(float) * B * cfg->M);
   s.dop = (float*)take(sizeof(float) * B);
+  s.Xd_hi = (bf16*)take(sizeof(bf16) * (size_t)B * cfg->C * Sp);
+  s.Xd_lo = (bf16*)take(sizeof(bf16) * (size_t)B * cfg->C * Sp);
+  s.I_hi = (bf16*)take(sizeof(bf16) * (size_t)B * cfg->M * Sp);
+  s.I_lo = (bf16*)take(sizeof(bf16) * (size_t)B * cfg->M * Sp);
   if (sv) *sv = s;
   return off;
 }
@@ -47,7 +51,10 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
   const uint32_t* qb = (train && cfg->p_q > 0) ? sv.qbits : nullptr;
   const uint32_t* xb = (train && cfg->p_x > 0) ? sv.xbits : nullptr;
   const uint32_t* mb = (train && cfg->p_m > 0) ? sv.mbits : nullptr;
-  ARENA(Xd, float, "hop.Xd", (size_t)B * C * Sp);
+  const bool tc = ctx->precision != RAU_PREC_F32 && S % 4 == 0;   // tcgen05 modes: operands are produced packed
+  const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+  float* Xd = nullptr;
+  if (!tc) RAU_TRY(ctx->arena.get("hop.Xd", sizeof(float) * (size_t)B * C * Sp, (void**)&Xd));
   ARENA(qatt, float, "hop.qatt", B * A);
   ARENA(mem, float, "hop.mem", B * S);
   ARENA(a, float, "hop.a", B * M);
@@ -63,7 +70,8 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
     RAU_TRY(rau_contract(ctx, g));
   }
   // i_embed (F:238-242): I[b] = tanh(Wi drop(X[b]) + bi), 1x1 convolution = per-image [M,C]x[C,S] product
-  RAU_TRY(k_dropout(ctx, X, (int64_t)B * C, S, S, xb, drop_scale(cfg->p_x), Xd, Sp, nullptr, 0, Sp));
+  if (tc) RAU_TRY(k_dropout_pack(ctx, X, (int64_t)B * C, S, xb, drop_scale(cfg->p_x), sv.Xd_hi, x3 ? sv.Xd_lo : nullptr, Sp));
+  else RAU_TRY(k_dropout(ctx, X, (int64_t)B * C, S, S, xb, drop_scale(cfg->p_x), Xd, Sp, nullptr, 0, Sp));
   {
     SimtGemm g;
     g.M = M; g.N = Sp; g.K = C;
@@ -71,6 +79,7 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
     g.B = Xd; g.sbk = Sp; g.sbn = 1; g.bB = (int64_t)C * Sp;
     g.C = sv.I; g.scm = Sp; g.scn = 1; g.bC = (int64_t)M * Sp;
     g.batch = B; g.bias_m = P.bi; g.act = 1; g.n_valid = S;
+    if (tc) { g.B_hi = sv.Xd_hi; g.B_lo = sv.Xd_lo; g.C_hi = sv.I_hi; g.C_lo = sv.I_lo; }
     RAU_TRY(rau_contract(ctx, g));
   }
   // attbycontent (F:244-252): E[b] = tanh(Wa I[b] + ba + (Wqa qf + bqa) 1^T); the 256->1 conv is fused below
@@ -86,6 +95,7 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
     g.B = sv.I; g.sbk = Sp; g.sbn = 1; g.bB = (int64_t)M * Sp;
     g.C = sv.E; g.scm = Sp; g.scn = 1; g.bC = (int64_t)A * Sp;
     g.batch = B; g.bias_m = P.ba; g.bias_bm = qatt; g.act = 1; g.n_valid = S;
+    if (tc) { g.B_hi = sv.I_hi; g.B_lo = sv.I_lo; }
     RAU_TRY(rau_contract(ctx, g));
   }
   // attbymemory (F:285-290) + attselect (F:254-263): p = softmax(ws.E + bs + Wm h + bm) ; a = I p
@@ -141,14 +151,28 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   const uint32_t* qb = (train && cfg->p_q > 0) ? sv.qbits : nullptr;
   const uint32_t* xb = (train && cfg->p_x > 0) ? sv.xbits : nullptr;
   const uint32_t* mb = (train && cfg->p_m > 0) ? sv.mbits : nullptr;
-  ARENA(Xd, float, "hop.Xd", (size_t)B * C * Sp);
+  const bool tc = ctx->precision != RAU_PREC_F32 && S % 4 == 0;
+  const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+  float* Xd = nullptr;
+  if (!tc || dX) RAU_TRY(ctx->arena.get("hop.Xd", sizeof(float) * (size_t)B * C * Sp, (void**)&Xd));
   ARENA(du, float, "hopb.du", B * M);
   ARENA(dh2, float, "hopb.dh2", B * H);
   ARENA(dG, float, "hopb.dG", B * 4 * H);
   ARENA(dj, float, "hopb.dj", B * M);
   ARENA(dp, float, "hopb.dp", B * S);
   ARENA(ds, float, "hopb.ds", B * S);
-  ARENA(dZ, float, "hopb.dZ", (size_t)B * A * Sp);
+  float* dZ = nullptr;
+  bf16 *dZ_hi = nullptr, *dZ_lo = nullptr, *dY_hi = nullptr, *dY_lo = nullptr;
+  if (tc) {
+    RAU_TRY(ctx->arena.get("hopb.dZh", sizeof(bf16) * (size_t)B * A * Sp, (void**)&dZ_hi));
+    RAU_TRY(ctx->arena.get("hopb.dYh", sizeof(bf16) * (size_t)B * M * Sp, (void**)&dY_hi));
+    if (x3) {
+      RAU_TRY(ctx->arena.get("hopb.dZl", sizeof(bf16) * (size_t)B * A * Sp, (void**)&dZ_lo));
+      RAU_TRY(ctx->arena.get("hopb.dYl", sizeof(bf16) * (size_t)B * M * Sp, (void**)&dY_lo));
+    }
+  } else {
+    RAU_TRY(ctx->arena.get("hopb.dZ", sizeof(float) * (size_t)B * A * Sp, (void**)&dZ));
+  }
   ARENA(dqa, float, "hopb.dqa", B * A);
   ARENA(gwsp, float, "hopb.gwsp", B * A);
   ARENA(dI, float, "hopb.dI", (size_t)B * M * Sp);
@@ -197,7 +221,8 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   RAU_TRY(rau_contract(ctx, lin_wgrad(B, M, S, dj, M, sv.p, S, G.Wp, 1.0f)));
   RAU_TRY(k_colsum(ctx, dj, B, M, M, G.bp, 1));
   // attselect + softmax + score conv + tanh of attbycontent, one CTA per image
-  RAU_TRY(k_attn_bwd<float>(ctx, B, M, A, S, Sp, sv.E, sv.I, P.ws, sv.p, dp, dj, ds, nullptr, 0, dZ, dqa, nullptr, gwsp));
+  RAU_TRY(k_attn_bwd<float>(ctx, B, M, A, S, Sp, sv.E, sv.I, P.ws, sv.p, dp, dj, ds, nullptr, 0, dZ, dqa, nullptr, gwsp,
+                            dZ_hi, dZ_lo));
   {
     SimtGemm g = lin_dgrad(B, S, H, ds, S, P.Wm, dh, H);
     g.accumulate = 1;
@@ -215,9 +240,11 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
     g.B = dZ; g.sbk = Sp; g.sbn = 1; g.bB = (int64_t)A * Sp;
     g.C = dI; g.scm = Sp; g.scn = 1; g.bC = (int64_t)M * Sp;
     g.batch = B;
+    if (tc) { g.B_hi = dZ_hi; g.B_lo = dZ_lo; }
     RAU_TRY(rau_contract(ctx, g));
   }
-  RAU_TRY(k_iembed_bwd_pw<float>(ctx, B, M, S, Sp, dI, sv.I, dj, sv.p, dI));
+  if (tc) RAU_TRY(k_iembed_bwd_rows(ctx, B, M, S, Sp, dI, sv.I, dj, sv.p, dX ? dI : nullptr, dY_hi, dY_lo, G.bi));
+  else RAU_TRY(k_iembed_bwd_pw<float>(ctx, B, M, S, Sp, dI, sv.I, dj, sv.p, dI));
   // gWa += sum_b dZ[b] I[b]^T ; gba += sum dZ
   {
     SimtGemm g;
@@ -226,9 +253,10 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
     g.B = sv.I; g.sbk = 1; g.sbn = Sp; g.kB = (int64_t)M * Sp;
     g.C = G.Wa; g.scm = M; g.scn = 1;
     g.kbatch = B; g.accumulate = 1; g.ksplit = ks_img;
+    if (tc) { g.A_hi = dZ_hi; g.A_lo = dZ_lo; g.B_hi = sv.I_hi; g.B_lo = sv.I_lo; }
     RAU_TRY(rau_contract(ctx, g));
   }
-  RAU_TRY(k_rowsum_bms<float>(ctx, dZ, B, A, S, Sp, G.ba));
+  RAU_TRY(k_colsum(ctx, dqa, B, A, A, G.ba, 1));   // gba = sum_b sum_s dZ = sum_b dqa
   // dqf = dj + Wqa^T dqa ; gWqa += dqa (x) qf
   {
     SimtGemm g = lin_dgrad(B, A, M, dqa, A, P.Wqa, dqf, M);
@@ -238,7 +266,7 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   RAU_TRY(rau_contract(ctx, lin_wgrad(B, A, M, dqa, A, sv.qf, M, G.Wqa, 1.0f)));
   RAU_TRY(k_colsum(ctx, dqa, B, A, A, G.bqa, 1));
   // i_embed: gWi += sum_b dY[b] drop(X[b])^T ; gbi += sum dY ; dX only on request (the caller discards it, F:598)
-  RAU_TRY(k_dropout(ctx, X, (int64_t)B * C, S, S, xb, drop_scale(cfg->p_x), Xd, Sp, nullptr, 0, Sp));
+  if (!tc) RAU_TRY(k_dropout(ctx, X, (int64_t)B * C, S, S, xb, drop_scale(cfg->p_x), Xd, Sp, nullptr, 0, Sp));
   {
     SimtGemm g;
     g.M = M; g.N = C; g.K = Sp;
@@ -246,9 +274,10 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
     g.B = Xd; g.sbk = 1; g.sbn = Sp; g.kB = (int64_t)C * Sp;
     g.C = G.Wi; g.scm = C; g.scn = 1;
     g.kbatch = B; g.accumulate = 1; g.ksplit = ks_img;
+    if (tc) { g.A_hi = dY_hi; g.A_lo = dY_lo; g.B_hi = sv.Xd_hi; g.B_lo = sv.Xd_lo; }
     RAU_TRY(rau_contract(ctx, g));
   }
-  RAU_TRY(k_rowsum_bms<float>(ctx, dI, B, M, S, Sp, G.bi));
+  if (!tc) RAU_TRY(k_rowsum_bms<float>(ctx, dI, B, M, S, Sp, G.bi));   // (the packed path reduced gbi with dY)
   if (dX) {
     SimtGemm g;
     g.M = C; g.N = Sp; g.K = M;
@@ -256,6 +285,7 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
     g.B = dI; g.sbk = Sp; g.sbn = 1; g.bB = (int64_t)M * Sp;
     g.C = Xd; g.scm = Sp; g.scn = 1; g.bC = (int64_t)C * Sp;
     g.batch = B;
+    if (tc) { g.B_hi = dY_hi; g.B_lo = dY_lo; }
     RAU_TRY(rau_contract(ctx, g));
     RAU_TRY(k_dropout(ctx, Xd, (int64_t)B * C, S, Sp, xb, drop_scale(cfg->p_x), dX, S, nullptr, 0, S));
   }

@@ -32,6 +32,9 @@ int k_lstm_bwd(rau_ctx* ctx, int B, int H, int order,
 // y = x * keep(bits) * scale over a [rows, cols] matrix (mask indexed by row*cols+col); padded output pitch
 int k_dropout(rau_ctx* ctx, const float* x, int64_t rows, int cols, int ldx, const uint32_t* bits, float scale,
               float* y_f, int ldyf, bf16* y_b, int ldyb, int cols_pad);
+// y = x*keep*scale written only as packed bf16 (hi, lo) rows of pitch cols_pad: a tcgen05 operand (cols % 4 == 0)
+int k_dropout_pack(rau_ctx* ctx, const float* x, int64_t rows, int cols, const uint32_t* bits, float scale, bf16* hi, bf16* lo,
+                   int cols_pad);
 // y (+)= x*keep*scale  (used for dq accumulation over hops and dX)
 int k_dropout_bwd_acc(rau_ctx* ctx, const float* dx, int64_t n, const uint32_t* bits, float scale, float* y, int accumulate);
 int k_tanh_bwd(rau_ctx* ctx, const float* dy, const float* y, int64_t n, float* dx_f, bf16* dx_b);
@@ -62,11 +65,16 @@ int k_attn_fwd(rau_ctx* ctx, int B, int M, int A, int S, int Sp, const T* E, con
 template <typename T>
 int k_attn_bwd(rau_ctx* ctx, int B, int M, int A, int S, int Sp, const T* E, const T* I,
                const float* ws, const float* p, const float* dp_in, const float* da,
-               float* ds, bf16* ds_b, int lddsb, T* dZ, float* dqa, bf16* dqa_b, float* gws_part);
+               float* ds, bf16* ds_b, int lddsb, T* dZ, float* dqa, bf16* dqa_b, float* gws_part,
+               bf16* dZ_hi = nullptr, bf16* dZ_lo = nullptr);   // dZ may be NULL when only the packed form is wanted
 // dY = (dI + da[b,m] p[b,s]) * (1 - I^2), pad columns zeroed; dI may alias dY when T == float
 template <typename T>
 int k_iembed_bwd_pw(rau_ctx* ctx, int B, int M, int S, int Sp, const float* dI, const T* I,
                     const float* da, const float* p, T* dY);
+// same, one warp per (image, channel) row: writes dY as fp32 (dY may be NULL) and/or packed bf16 (hi, lo) and adds
+// the row sums into gbi[m] (the bias gradient of the 1x1 convolution)
+int k_iembed_bwd_rows(rau_ctx* ctx, int B, int M, int S, int Sp, const float* dI, const float* I, const float* da,
+                      const float* p, float* dY, bf16* dY_hi, bf16* dY_lo, float* gbi);
 
 // ---- criteria (a12)
 int k_softmax_ce(rau_ctx* ctx, int B, int N, const float* score, const float* labels, float loss_scale, float grad_scale,

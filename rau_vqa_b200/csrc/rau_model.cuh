@@ -49,6 +49,7 @@ static inline SimtGemm lin_wgrad(int rows, int N, int K, const float* dY, int ld
 struct HopSaved {
   uint32_t *qbits, *xbits, *mbits;   // packed keep bits of the three dropouts (F:233, F:239, F:277)
   float *qd, *qf, *I, *E, *p, *j, *lsav, *hout, *m, *dop;
+  bf16 *Xd_hi, *Xd_lo, *I_hi, *I_lo;   // tcgen05 modes: packed operands kept for the backward pass
 };
 size_t hop_saved_layout(const rau_config* cfg, int B, void* base, HopSaved* sv);
 

@@ -399,6 +399,10 @@ int rau_contract(rau_ctx* ctx, const SimtGemm& g) {
     const int r = tc_gemm_try(ctx, g);
     if (r < 0) return r;
     if (r == 1) return RAU_OK;
+    if (g.A_hi || g.B_hi) {
+      rau_set_error("internal: a packed-operand product was refused by the tcgen05 engine");
+      return RAU_EINVAL;
+    }
   }
   return simt_gemm(ctx, g);
 }
