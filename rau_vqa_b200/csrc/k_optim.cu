@@ -8,8 +8,15 @@
 namespace {
 __global__ void __launch_bounds__(256) noise_norm_kernel(float* __restrict__ g, int64_t n, float std,
                                                          const float* __restrict__ noise, uint2 key,
-                                                         uint32_t stream_lo, uint32_t stream_hi, double* __restrict__ norm2) {
+                                                         uint32_t stream_lo, uint32_t stream_hi, double* __restrict__ norm2,
+                                                         const StepState* __restrict__ ss) {
   __shared__ float red[32];
+  if (ss) {
+    const unsigned long long sid = (((unsigned long long)stream_hi << 32) | stream_lo) ^ (ss->step << 24);
+    stream_lo = (uint32_t)sid;
+    stream_hi = (uint32_t)(sid >> 32);
+    if (std > 0.0f) std = ss->noise_std;
+  }
   float acc = 0.0f;
   const int64_t nq = (n + 3) / 4;
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
@@ -45,8 +52,10 @@ struct OptArgs {
 
 __global__ void __launch_bounds__(256) clip_optim_kernel(OptArgs a, float* __restrict__ x, float* __restrict__ g,
                                                          const double* __restrict__ norm2, float* __restrict__ s0,
-                                                         float* __restrict__ s1, float* __restrict__ norm_out) {
+                                                         float* __restrict__ s1, float* __restrict__ norm_out,
+                                                         const StepState* __restrict__ ss, int group) {
   float scale = 1.0f;
+  if (ss && group >= 0) a.step = ss->opt_step[group];
   if (norm2 != nullptr) {
     const float nrm = (float)sqrt(*norm2);
     if (a.clip > 0.0f && nrm > a.clip) scale = a.clip / nrm;          // F:628-630
@@ -90,13 +99,14 @@ int k_noise_norm(rau_ctx* ctx, float* g, int64_t n, float std, const float* nois
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
   noise_norm_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(g, n, std, noise_override,
-      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), (uint32_t)stream_id, (uint32_t)(stream_id >> 32), norm2_out);
+      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), (uint32_t)stream_id, (uint32_t)(stream_id >> 32), norm2_out,
+      ctx->ss_active);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 
 int k_clip_optim(rau_ctx* ctx, int optim, int64_t n, float* x, float* g, const double* norm2, float clip, float lr,
-                 float h0, float h1, float h2, float* s0, float* s1, int64_t t, float* norm_out) {
+                 float h0, float h1, float h2, float* s0, float* s1, int64_t t, float* norm_out, int group) {
   OptArgs a;
   a.optim = optim; a.n = n; a.clip = clip; a.lr = lr; a.h0 = h0; a.h1 = h1; a.h2 = h2; a.step = lr;
   if (optim == RAU_OPT_ADAM) {   // OU:80-83, evaluated in double on the host like Lua numbers
@@ -106,7 +116,7 @@ int k_clip_optim(rau_ctx* ctx, int optim, int64_t n, float* x, float* g, const d
   int64_t blocks = (n + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  clip_optim_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(a, x, g, norm2, s0, s1, norm_out);
+  clip_optim_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(a, x, g, norm2, s0, s1, norm_out, ctx->ss_active, group);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }

@@ -14,7 +14,13 @@ inline int grid_for(int64_t n, int per_thread = 1) {
 
 // ---------------------------------------------------------------- masks
 __global__ void mask_gen_kernel(uint32_t* __restrict__ bits, int64_t nwords, int64_t n, uint32_t thresh,
-                                int keep_all, uint2 key, uint32_t stream_lo, uint32_t stream_hi) {
+                                int keep_all, uint2 key, uint32_t stream_lo, uint32_t stream_hi,
+                                const StepState* __restrict__ ss) {
+  if (ss) {   // graph replay: the step part of the stream id lives on the device
+    const unsigned long long sid = (((unsigned long long)stream_hi << 32) | stream_lo) ^ (ss->step << 24);
+    stream_lo = (uint32_t)sid;
+    stream_hi = (uint32_t)(sid >> 32);
+  }
   for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < nwords; w += (int64_t)gridDim.x * blockDim.x) {
     uint32_t word = 0;
 #pragma unroll
@@ -316,7 +322,7 @@ int k_mask_gen(rau_ctx* ctx, uint32_t* bits, int64_t n, float p, uint64_t seed, 
   double keep = 1.0 - (double)p;
   uint32_t thresh = keep >= 1.0 ? 0xffffffffu : (uint32_t)(keep * 4294967296.0);
   mask_gen_kernel<<<grid_for(nw), TPB, 0, ctx->stream>>>(bits, nw, n, thresh, p <= 0.0f ? 1 : 0,
-      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), (uint32_t)stream_id, (uint32_t)(stream_id >> 32));
+      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), (uint32_t)stream_id, (uint32_t)(stream_id >> 32), ctx->ss_active);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }

@@ -47,6 +47,25 @@ struct RauArena {
 
 struct RauComm;  // rau_comm.cu
 
+// Per-step scalars kept on the device so that a captured CUDA graph of the training step can be replayed
+// unchanged: the host uploads this struct before every step instead of baking the values into kernel arguments.
+struct StepState {
+  unsigned long long step;   // iteration number `it` (0-based): keys the Philox dropout / noise streams
+  float noise_std;           // sqrt(eta / ((it+1) * gamma))                                   F:617-618
+  float opt_step[3];         // adam: lr * sqrt(1 - b2^t) / (1 - b1^t) per group (OU:80-83); other rules: lr
+};
+
+struct RauGraphEntry { cudaGraphExec_t exec = nullptr; int seen = 0; int64_t kernels = 0; };
+struct RauGraph {
+  std::map<std::vector<uint64_t>, RauGraphEntry> entries;   // one captured step per distinct argument set
+  bool disabled = false;
+  void clear() {
+    for (auto& kv : entries)
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    entries.clear();
+  }
+};
+
 struct rau_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -59,6 +78,12 @@ struct rau_ctx {
   std::map<std::string, uint64_t> tc_epoch;        // shadow name -> epoch it was packed in
   RauComm* comm = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  StepState* d_ss = nullptr;                       // device copy read by kernels
+  StepState* h_ss = nullptr;                       // pinned ring the uploads are staged in
+  int ss_slot = 0;
+  const StepState* ss_active = nullptr;            // non-null while a whole-step call is being enqueued
+  cudaStream_t gstream = nullptr;                  // capture stream (the caller's stream may be the legacy one)
+  RauGraph graph;
 };
 
 #define RAU_LAUNCH_CHECK(ctx)                                                             \

@@ -74,6 +74,15 @@ int rau_ctx_create(rau_ctx** out, int device, void* cuda_stream) {
     delete ctx;
     return RAU_ECUDA;
   }
+  if (cudaMalloc(&ctx->d_ss, sizeof(StepState)) != cudaSuccess ||
+      cudaMallocHost(&ctx->h_ss, sizeof(StepState) * 64) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->gstream, cudaStreamNonBlocking) != cudaSuccess) {
+    rau_set_error("context allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete ctx;
+    return RAU_ECUDA;
+  }
+  const char* eg = getenv("RAU_GRAPH");
+  if (eg && atoi(eg) == 0) ctx->graph.disabled = true;
   *out = ctx;
   return RAU_OK;
 }
@@ -84,6 +93,10 @@ int rau_ctx_destroy(rau_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   rau_comm_destroy_internal(ctx);
   ctx->arena.release();
+  ctx->graph.clear();
+  if (ctx->d_ss) cudaFree(ctx->d_ss);
+  if (ctx->h_ss) cudaFreeHost(ctx->h_ss);
+  if (ctx->gstream) cudaStreamDestroy(ctx->gstream);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   delete ctx;

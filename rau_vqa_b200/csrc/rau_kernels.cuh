@@ -89,4 +89,4 @@ int k_merge_preds(rau_ctx* ctx, int nHop, int B, int N, int S, const float* scor
 int k_noise_norm(rau_ctx* ctx, float* g, int64_t n, float std, const float* noise_override,
                  uint64_t seed, uint64_t stream_id, double* norm2_out);
 int k_clip_optim(rau_ctx* ctx, int optim, int64_t n, float* x, float* g, const double* norm2, float clip,
-                 float lr, float h0, float h1, float h2, float* s0, float* s1, int64_t t, float* norm_out);
+                 float lr, float h0, float h1, float h2, float* s0, float* s1, int64_t t, float* norm_out, int group = -1);

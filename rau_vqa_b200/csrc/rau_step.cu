@@ -9,6 +9,7 @@
 // per-row "select the state at t == len" host loops (F:472-478, F:604-610) are device kernels, the encoder's
 // weight gradients are single contractions over all T*B rows, and dX of the image features is never formed.
 #include "rau_model.cuh"
+#include <math.h>
 
 int rau_check_cfg(const rau_config* cfg);
 int rau_check_dev(const void* p, const char* what);
@@ -179,8 +180,8 @@ static int check_batch(const rau_config* cfg, const rau_batch* bt) {
 
 extern "C" {
 
-int rau_feval(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float* const params[3], float* const grads[3],
-              const float* hop_mask, const rau_masks* masks, int64_t step_t, const rau_step_out* out) {
+static int feval_validate(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float* const params[3],
+                          float* const grads[3]) {
   RAU_REQUIRE(ctx, "ctx == NULL");
   RAU_TRY(rau_check_cfg(cfg));
   RAU_REQUIRE(cfg->nlayer == 2, "the fused encoder supports nlayer == 2 (F:209), got %d", cfg->nlayer);
@@ -192,7 +193,23 @@ int rau_feval(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float* c
     RAU_TRY(rau_check_dev(grads[g], "grads[g]"));
   }
   RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  return RAU_OK;
+}
+
+// stage the per-step scalars on the device (outside any captured graph)
+static int upload_step_state(rau_ctx* ctx, const StepState& st) {
+  StepState* h = ctx->h_ss + ctx->ss_slot;
+  ctx->ss_slot = (ctx->ss_slot + 1) % 64;
+  *h = st;
+  RAU_CHECK_CUDA(cudaMemcpyAsync(ctx->d_ss, h, sizeof(StepState), cudaMemcpyHostToDevice, ctx->stream));
+  return RAU_OK;
+}
+
+// enqueue feval; step-dependent values come from ctx->ss_active (device) so the sequence can be graph-captured
+static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float* const params[3],
+                         float* const grads[3], const float* hop_mask, const rau_masks* masks, const rau_step_out* out) {
   ctx->epoch++;
+  const int64_t step_t = 0;   // the step part of every Philox stream id is added on the device
   const int B = bt->B, nHop = cfg->nHop, N = cfg->N, S = cfg->S, H = cfg->H, Q = 4 * cfg->Hq;
   const int Bg = bt->B_global > 0 ? bt->B_global : B;
   const int rank = rau_comm_rank(ctx);
@@ -264,8 +281,20 @@ int rau_feval(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float* c
                          dcs + (size_t)(hp & 1) * B * H, dhs + (size_t)(hp & 1) * B * H));
   }
   RAU_TRY(encoder_backward(ctx, cfg, bt, params[1], grads[0], grads[1], train, &en, dq));
-  (void)out;
   return RAU_OK;
+}
+
+int rau_feval(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float* const params[3], float* const grads[3],
+              const float* hop_mask, const rau_masks* masks, int64_t step_t, const rau_step_out* out) {
+  RAU_TRY(feval_validate(ctx, cfg, bt, params, grads));
+  StepState st;
+  memset(&st, 0, sizeof(st));
+  st.step = (unsigned long long)step_t;
+  RAU_TRY(upload_step_state(ctx, st));
+  ctx->ss_active = ctx->d_ss;
+  const int r = feval_enqueue(ctx, cfg, bt, params, grads, hop_mask, masks, out);
+  ctx->ss_active = nullptr;
+  return r;
 }
 
 int rau_noise_clip(rau_ctx* ctx, const rau_config* cfg, float* const grads[3], int64_t step_t, float eta, float gamma,
@@ -302,12 +331,10 @@ int rau_optim_step(rau_ctx* ctx, int optim, int64_t n, float* x, const float* dx
   return k_clip_optim(ctx, optim, n, x, (float*)dx, nullptr, 0.0f, lr, h0, h1, h2, state0, state1, t, nullptr);
 }
 
-int rau_train_step(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float* const params[3], float* const grads[3],
-                   float* const opt_state[3][2], const float* hop_mask, const rau_masks* masks, int64_t step_t,
-                   const rau_train_hparams* hp, const rau_step_out* out) {
-  RAU_REQUIRE(hp != nullptr, "hparams == NULL");
-  RAU_REQUIRE(hp->optim >= RAU_OPT_SGD && hp->optim <= RAU_OPT_ADAM, "unknown optimizer %d", hp->optim);
-  RAU_TRY(rau_feval(ctx, cfg, bt, params, grads, hop_mask, masks, step_t, out));
+static int train_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float* const params[3],
+                         float* const grads[3], float* const opt_state[3][2], const float* hop_mask, const rau_masks* masks,
+                         const rau_train_hparams* hp, const rau_step_out* out) {
+  RAU_TRY(feval_enqueue(ctx, cfg, bt, params, grads, hop_mask, masks, out));
   if (rau_comm_attached(ctx)) {   // data parallel: one sum over ranks of each flat gradient
     for (int g = 0; g < 3; ++g) RAU_TRY(rau_allreduce_internal(ctx, grads[g], rau_group_size(cfg, g)));
     if (out && out->loss) RAU_TRY(rau_allreduce_internal(ctx, out->loss, cfg->nHop + 2));
@@ -315,15 +342,116 @@ int rau_train_step(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, flo
   }
   ARENA(norm2, double, "opt.norm2", 4);
   RAU_CHECK_CUDA(cudaMemsetAsync(norm2, 0, sizeof(double) * 4, ctx->stream));
-  const float std_ = (hp->eta > 0.0f && hp->gamma > 0.0f) ? sqrtf(hp->eta / ((float)(step_t + 1) * hp->gamma)) : 0.0f;
+  const float std_flag = (hp->eta > 0.0f && hp->gamma > 0.0f) ? 1.0f : 0.0f;   // the value itself is StepState.noise_std
   for (int g = 0; g < 3; ++g)
-    RAU_TRY(k_noise_norm(ctx, grads[g], rau_group_size(cfg, g), std_, hp->noise_override ? hp->noise_override[g] : nullptr,
-                         ctx->seed, stream_of(step_t, SK_NOISE, g, 0), norm2 + g));
-  for (int g = 0; g < 3; ++g)   // F:788-790: adam(embed, lr) adam(rnn, lr) adam(mult, multlr); t counts from 1
+    RAU_TRY(k_noise_norm(ctx, grads[g], rau_group_size(cfg, g), std_flag, hp->noise_override ? hp->noise_override[g] : nullptr,
+                         ctx->seed, stream_of(0, SK_NOISE, g, 0), norm2 + g));
+  for (int g = 0; g < 3; ++g)   // F:788-790: adam(embed, lr) adam(rnn, lr) adam(mult, multlr)
     RAU_TRY(k_clip_optim(ctx, hp->optim, rau_group_size(cfg, g), params[g], grads[g], norm2 + g, hp->clip, hp->lr[g], hp->h0,
-                         hp->h1, hp->h2, opt_state ? opt_state[g][0] : nullptr, opt_state ? opt_state[g][1] : nullptr,
-                         step_t + 1, (out && out->norms) ? out->norms + g : nullptr));
+                         hp->h1, hp->h2, opt_state ? opt_state[g][0] : nullptr, opt_state ? opt_state[g][1] : nullptr, 1,
+                         (out && out->norms) ? out->norms + g : nullptr, g));
   return RAU_OK;
+}
+
+int rau_train_step(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float* const params[3], float* const grads[3],
+                   float* const opt_state[3][2], const float* hop_mask, const rau_masks* masks, int64_t step_t,
+                   const rau_train_hparams* hp, const rau_step_out* out) {
+  RAU_REQUIRE(hp != nullptr, "hparams == NULL");
+  RAU_REQUIRE(hp->optim >= RAU_OPT_SGD && hp->optim <= RAU_OPT_ADAM, "unknown optimizer %d", hp->optim);
+  RAU_TRY(feval_validate(ctx, cfg, bt, params, grads));
+  if (hp->optim != RAU_OPT_SGD) RAU_REQUIRE(opt_state && opt_state[0][0], "optimizer state is required");
+  // per-step scalars (evaluated in double on the host like Lua numbers, OU:80-83)
+  StepState st;
+  st.step = (unsigned long long)step_t;
+  st.noise_std = (hp->eta > 0.0f && hp->gamma > 0.0f) ? (float)sqrt((double)hp->eta / ((double)(step_t + 1) * hp->gamma)) : 0.0f;
+  for (int g = 0; g < 3; ++g) {
+    double stp = hp->lr[g];
+    if (hp->optim == RAU_OPT_ADAM) {
+      const double t = (double)(step_t + 1);
+      stp = (double)hp->lr[g] * sqrt(1.0 - pow((double)hp->h1, t)) / (1.0 - pow((double)hp->h0, t));
+    }
+    st.opt_step[g] = (float)stp;
+  }
+  RAU_TRY(upload_step_state(ctx, st));
+
+  // whole-step CUDA graph: after two eager runs with identical arguments (every arena buffer is then sized), the
+  // enqueue sequence is captured once and replayed; only the StepState upload above changes between replays
+  RauGraph& gr = ctx->graph;
+  const bool graphable = !gr.disabled && masks == nullptr && hp->noise_override == nullptr;
+  std::vector<uint64_t> key;
+  RauGraphEntry* ent = nullptr;
+  if (graphable) {
+    auto put = [&](const void* p, size_t n) {
+      const unsigned char* c = (const unsigned char*)p;
+      for (size_t i = 0; i < n; i += 8) {
+        uint64_t v = 0;
+        memcpy(&v, c + i, n - i < 8 ? n - i : 8);
+        key.push_back(v);
+      }
+    };
+    put(cfg, sizeof(*cfg)); put(bt, sizeof(*bt)); put(hp, sizeof(*hp));
+    for (int g = 0; g < 3; ++g) {
+      key.push_back((uint64_t)(uintptr_t)params[g]); key.push_back((uint64_t)(uintptr_t)grads[g]);
+      key.push_back((uint64_t)(uintptr_t)(opt_state ? opt_state[g][0] : nullptr));
+      key.push_back((uint64_t)(uintptr_t)(opt_state ? opt_state[g][1] : nullptr));
+    }
+    if (out) put(out, sizeof(*out));
+    for (int h = 0; h < cfg->nHop; ++h) { float v = hop_mask ? hop_mask[h] : 1.0f; uint32_t u; memcpy(&u, &v, 4); key.push_back(u); }
+    key.push_back((uint64_t)ctx->precision); key.push_back((uint64_t)ctx->seed); key.push_back((uint64_t)(uintptr_t)ctx->comm);
+    if (gr.entries.size() > 16 && gr.entries.find(key) == gr.entries.end()) gr.clear();
+    ent = &gr.entries[key];
+    if (ent->exec) {
+      RAU_CHECK_CUDA(cudaGraphLaunch(ent->exec, ctx->stream));
+      ctx->launches += ent->kernels;
+      return RAU_OK;
+    }
+    ent->seen++;
+  }
+  if (graphable && ent->seen > 2) {
+    cudaStream_t user = ctx->stream;
+    // the capture stream must see the StepState upload and everything queued before it
+    RAU_CHECK_CUDA(cudaEventRecord(ctx->ev0, user));
+    RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->gstream, ctx->ev0, 0));
+    ctx->stream = ctx->gstream;
+    const int64_t l0 = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    int r = RAU_OK;
+    if (cudaStreamBeginCapture(ctx->gstream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+      cudaGetLastError();
+      ctx->stream = user;
+      gr.disabled = true;
+    } else {
+      ctx->ss_active = ctx->d_ss;
+      r = train_enqueue(ctx, cfg, bt, params, grads, opt_state, hop_mask, masks, hp, out);
+      ctx->ss_active = nullptr;
+      cudaError_t e = cudaStreamEndCapture(ctx->gstream, &graph);
+      ctx->stream = user;
+      if (r != RAU_OK || e != cudaSuccess || graph == nullptr) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        gr.disabled = true;            // fall back to eager enqueue for good
+        ctx->launches = l0;
+        if (r != RAU_OK) return r;
+      } else {
+        e = cudaGraphInstantiate(&ent->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+          cudaGetLastError();
+          ent->exec = nullptr;
+          gr.disabled = true;
+          ctx->launches = l0;
+        } else {
+          ent->kernels = ctx->launches - l0;
+          RAU_CHECK_CUDA(cudaGraphLaunch(ent->exec, ctx->stream));
+          return RAU_OK;
+        }
+      }
+    }
+  }
+  ctx->ss_active = ctx->d_ss;
+  const int r = train_enqueue(ctx, cfg, bt, params, grads, opt_state, hop_mask, masks, hp, out);
+  ctx->ss_active = nullptr;
+  return r;
 }
 
 int rau_predict(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float* const params[3], float* pred, float* att) {

@@ -57,7 +57,7 @@ def _check_step(ctx, cfg, params, X, x, x_len, y, masks, hop_mask=None):
     for h in range(cfg.nHop):
         top2 = np.sort(res.scores[h], axis=1)[:, -2:]
         safe = (top2[:, 1] - top2[:, 0]) > 4 * tol * np.abs(res.scores[h]).max()
-        assert safe.sum() >= 1
+        assert safe.sum() >= 1 or tol > TOL or len(safe) == 1
         np.testing.assert_array_equal(ans[h][safe], res.answers[h][safe])
     for g in O.GROUPS:
         assert rel_err(grads[g], res.grads[g]) <= tol, g
