@@ -31,6 +31,7 @@ struct TcParams {
   int p_mn, q_mn;                 // 1 = MN-major operand
   int p_zmode, q_zmode;           // 0 = shared (z = 0), 1 = independent batch (z = bz), 2 = reduced batch (z = kb)
   int kbatch, ksplit;
+  int p_zshare, q_zshare;         // operand is identical for every cluster member along z (batch-invariant)
   int BN, stages, tmem_cols;
   int extI, extJ, i_valid, j_valid;
   float* C; long long sci, scj, bC;
@@ -39,6 +40,7 @@ struct TcParams {
   const float *bias_i, *bias_i2, *bias_j, *bias_j2, *bias_bi, *bias_bj;
   const float *addend, *addend2; long long sdi, sdj, bD;
   int act, accumulate, atomic;
+  int dbg;                        // RAU_TC_DBG experiment bits: 1 skip fp32 stores, 2 skip bf16 stores, 4 skip activation
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -68,6 +70,35 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], "
+      "[%2], %6;" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t sreg_cluster(int which) {
+  uint32_t v;
+  switch (which) {
+    case 0: asm volatile("mov.u32 %0, %%cluster_ctaid.x;" : "=r"(v)); break;
+    case 1: asm volatile("mov.u32 %0, %%cluster_ctaid.y;" : "=r"(v)); break;
+    case 2: asm volatile("mov.u32 %0, %%cluster_ctaid.z;" : "=r"(v)); break;
+    case 3: asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(v)); break;
+    case 4: asm volatile("mov.u32 %0, %%cluster_nctaid.y;" : "=r"(v)); break;
+    default: asm volatile("mov.u32 %0, %%cluster_nctaid.z;" : "=r"(v)); break;
+  }
+  return v;
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -91,6 +122,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[k]);
 }
 
+// tanh to ~2e-7 absolute: odd polynomial near zero (no cancellation), 1 - 2/(e^2x + 1) elsewhere
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float ax = fabsf(x);
+  if (ax < 0.15f) {
+    const float x2 = x * x;
+    return x * (1.0f + x2 * (-0.33333334f + x2 * (0.13333334f + x2 * (-0.05396825f + x2 * 0.02186949f))));
+  }
+  const float e = __expf(2.0f * ax);
+  const float t = 1.0f - __fdividef(2.0f, e + 1.0f);
+  return copysignf(t, x);
+}
+
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
 // version=1 [46,48) | layout SWIZZLE_128B=2 [61,64).  8 rows x 128 bytes form one 1024-byte swizzle atom.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -108,8 +151,25 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const __grid_con
   const int BNbox = (BN + 63) / 64 * 64;                 // smem footprint of a Q tile (MN-major chunks are 64 wide)
   const int nt = p.split;                                // tiles per operand per stage (hi [, lo])
   const uint32_t p_bytes = TC_BM * TC_BK * 2, q_bytes = (uint32_t)BNbox * TC_BK * 2;
-  const uint32_t stage_bytes = nt * (p_bytes + q_bytes);
-  const uint32_t tx_bytes = nt * (p_bytes + (p.q_mn ? q_bytes : (uint32_t)BN * TC_BK * 2));   // bytes the TMA boxes deliver
+  const uint32_t stage_bytes = nt * (p_bytes + q_bytes);   // every tile is moved as 8 KB units (64 x 64 bf16 boxes)
+  const uint32_t tx_bytes = stage_bytes;
+  // thread-block cluster: CTAs that need the same operand tile each fetch a share of its units and multicast them
+  const int CX = (int)sreg_cluster(3), CY = (int)sreg_cluster(4), CZ = (int)sreg_cluster(5);
+  const int cx = (int)sreg_cluster(0), cy = (int)sreg_cluster(1), cz = (int)sreg_cluster(2);
+  const int csize = CX * CY * CZ;
+  const uint16_t all_mask = (uint16_t)((1u << csize) - 1u);
+  // P is shared along x (and along z when batch-invariant); Q along y (and z)
+  const int p_gs = CX * (p.p_zshare ? CZ : 1), p_gi = cx + (p.p_zshare ? cz * CX : 0);
+  const int q_gs = CY * (p.q_zshare ? CZ : 1), q_gi = cy + (p.q_zshare ? cz * CY : 0);
+  uint16_t p_mask = 0, q_mask = 0;
+  for (int z = 0; z < CZ; ++z) {
+    if (!p.p_zshare && z != cz) continue;
+    for (int x = 0; x < CX; ++x) p_mask |= (uint16_t)(1u << (x + cy * CX + z * CX * CY));
+  }
+  for (int z = 0; z < CZ; ++z) {
+    if (!p.q_zshare && z != cz) continue;
+    for (int y = 0; y < CY; ++y) q_mask |= (uint16_t)(1u << (cx + y * CX + z * CX * CY));
+  }
   const int i0 = blockIdx.y * TC_BM, j0 = blockIdx.x * BN;
   const int bz = blockIdx.z / p.ksplit, ks = blockIdx.z % p.ksplit;
   int kper = 0;
@@ -125,7 +185,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const __grid_con
   const int total = it_hi - it_lo;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], (uint32_t)csize); }
     mbar_init(&acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -137,6 +197,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const __grid_con
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (csize > 1) cluster_sync_all();   // every member's barriers are initialised before any remote arrive / multicast
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
 
@@ -156,21 +217,22 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const __grid_con
         uint8_t* sp = smem + (size_t)st * stage_bytes;
         uint8_t* sq = sp + nt * p_bytes;
         mbar_expect_tx(&full_bar[st], tx_bytes);
-        for (int h = 0; h < nt; ++h) {
-          uint8_t* dp = sp + h * p_bytes;
-          if (p.p_mn) {   // [k rows][64 i] boxes, one per 64-wide chunk of i
-            tma_load_3d(dp, &p.mapP[s][h], &full_bar[st], i0, kk * TC_BK, zp);
-            tma_load_3d(dp + 8192, &p.mapP[s][h], &full_bar[st], i0 + 64, kk * TC_BK, zp);
-          } else {        // [128 i rows][64 k]
-            tma_load_3d(dp, &p.mapP[s][h], &full_bar[st], kk * TC_BK, i0, zp);
-          }
-          uint8_t* dq = sq + h * q_bytes;
-          if (p.q_mn) {
-            for (int c = 0; c < BNbox / 64; ++c)
-              tma_load_3d(dq + c * 8192, &p.mapQ[s][h], &full_bar[st], j0 + c * 64, kk * TC_BK, zq);
-          } else {
-            tma_load_3d(dq, &p.mapQ[s][h], &full_bar[st], kk * TC_BK, j0, zq);
-          }
+        // unit u of an operand tile = rows / columns [64u, 64u+64) of it, 8 KB at smem offset 8192*u
+        const int up = nt * 2, uq = nt * (BNbox / 64);
+        for (int u = p_gi; u < up; u += p_gs) {
+          const int h = u >> 1, r = u & 1;
+          uint8_t* d = sp + u * 8192;
+          const int c0 = p.p_mn ? i0 + 64 * r : kk * TC_BK, c1 = p.p_mn ? kk * TC_BK : i0 + 64 * r;
+          if (p_gs > 1) tma_load_3d_mc(d, &p.mapP[s][h], &full_bar[st], c0, c1, zp, p_mask);
+          else tma_load_3d(d, &p.mapP[s][h], &full_bar[st], c0, c1, zp);
+        }
+        const int qu = BNbox / 64;
+        for (int u = q_gi; u < uq; u += q_gs) {
+          const int h = u / qu, r = u % qu;
+          uint8_t* d = sq + u * 8192;
+          const int c0 = p.q_mn ? j0 + 64 * r : kk * TC_BK, c1 = p.q_mn ? kk * TC_BK : j0 + 64 * r;
+          if (q_gs > 1) tma_load_3d_mc(d, &p.mapQ[s][h], &full_bar[st], c0, c1, zq, q_mask);
+          else tma_load_3d(d, &p.mapQ[s][h], &full_bar[st], c0, c1, zq);
         }
       }
     }
@@ -200,7 +262,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const __grid_con
           for (int k = 0; k < TC_BK / 16; ++k)
             umma_bf16(tmem_base, da + (uint64_t)(k * ka), db + (uint64_t)(k * kq), idesc, (n > 0 || c > 0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(&empty_bar[st]);   // frees the stage when these MMAs have read it
+        if (csize > 1) umma_commit_mc(&empty_bar[st], all_mask);   // every member may have multicast into this stage
+        else umma_commit(&empty_bar[st]);                          // frees the stage when these MMAs have read it
       }
       umma_commit(&acc_bar);           // accumulator complete
     }
@@ -223,6 +286,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const __grid_con
     float* Crow = p.C + (long long)bz * p.bC + (long long)i * p.sci;
     const float* Drow = p.addend ? p.addend + (long long)bz * p.bD + (long long)i * p.sdi : nullptr;
     const float* D2row = p.addend2 ? p.addend2 + (long long)bz * p.bD + (long long)i * p.sdi : nullptr;
+    // rows of C that are contiguous along j are written as 16-byte vectors: each lane owns 64 contiguous bytes per chunk
+    const bool vec_c = p.scj == 1 && !p.atomic && (p.sci & 3) == 0 && (p.bC & 3) == 0 && (((uintptr_t)p.C) & 15) == 0 && (j0 & 3) == 0;
+    const bool vec_h = vec_c && (p.sci & 7) == 0 && (p.bC & 7) == 0 && (((uintptr_t)p.C_hi) & 15) == 0 &&
+                       (((uintptr_t)p.C_lo) & 15) == 0 && (j0 & 7) == 0;
+    const bool vec_d = Drow != nullptr && p.sdj == 1 && (p.sdi & 3) == 0 && (p.bD & 3) == 0 && (((uintptr_t)p.addend) & 15) == 0 &&
+                       (D2row == nullptr || (((uintptr_t)p.addend2) & 15) == 0) && (j0 & 3) == 0;
     for (int c = c_lo; c < c_hi; ++c) {
       float v[16];
       tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(c * 16), v);
@@ -231,38 +300,105 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const __grid_con
         for (int k = 0; k < 16; ++k) v[k] = 0.0f;
       }
       if (!i_ok) continue;
+      const int jc = j0 + c * 16;
+      const bool full = jc + 15 < p.extJ && c * 16 + 15 < BN;
+      float d[16];
+      if (Drow && lead) {
+        if (vec_d && full) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 t = *reinterpret_cast<const float4*>(Drow + jc + 4 * q);
+            if (D2row) {
+              const float4 t2 = *reinterpret_cast<const float4*>(D2row + jc + 4 * q);
+              t.x += t2.x; t.y += t2.y; t.z += t2.z; t.w += t2.w;
+            }
+            d[4 * q] = t.x; d[4 * q + 1] = t.y; d[4 * q + 2] = t.z; d[4 * q + 3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const int j = jc + k;
+            d[k] = 0.0f;
+            if (j < p.extJ && c * 16 + k < BN) {
+              d[k] = Drow[(long long)j * p.sdj];
+              if (D2row) d[k] += D2row[(long long)j * p.sdj];
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) d[k] = 0.0f;
+      }
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
-        const int j = j0 + c * 16 + k;
-        if (j >= p.extJ || c * 16 + k >= BN) continue;
-        float x = v[k] * p.alpha + bi;
-        if (lead) {
+        const int j = jc + k;
+        float x = v[k] * p.alpha + bi + d[k];
+        if (lead && j < p.extJ) {
           if (p.bias_j) x += p.bias_j[j];
           if (p.bias_j2) x += p.bias_j2[j];
           if (p.bias_bj) x += p.bias_bj[(long long)bz * p.extJ + j];
         }
-        if (Drow && lead) {
-          x += Drow[(long long)j * p.sdj];
-          if (D2row) x += D2row[(long long)j * p.sdj];
-        }
-        if (p.act == 1) x = tanhf(x);
-        else if (p.act == 2) x = 1.0f / (1.0f + expf(-x));
+        if (p.act == 1 && !(p.dbg & 4)) x = tanh_fast(x);
+        else if (p.act == 2) x = 1.0f / (1.0f + __expf(-x));
         if (i >= p.i_valid || j >= p.j_valid) x = 0.0f;
-        float* dst = Crow + (long long)j * p.scj;
-        if (p.atomic) atomicAdd(dst, x);
-        else if (p.accumulate) *dst += x;
-        else *dst = x;
-        if (p.C_hi) {
-          const long long o = (long long)bz * p.bC + (long long)i * p.sci + (long long)j * p.scj;
-          const bf16 h = __float2bfloat16(x);
-          p.C_hi[o] = h;
-          if (p.C_lo) p.C_lo[o] = __float2bfloat16(x - __bfloat162float(h));
+        v[k] = x;
+      }
+      if (p.dbg & 1) {
+      } else if (vec_c && full) {
+        float4* dst = reinterpret_cast<float4*>(Crow + jc);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 t = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          if (p.accumulate) {
+            const float4 o = dst[q];
+            t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+          }
+          dst[q] = t;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int j = jc + k;
+          if (j >= p.extJ || c * 16 + k >= BN) continue;
+          float* dst = Crow + (long long)j * p.scj;
+          if (p.atomic) atomicAdd(dst, v[k]);
+          else if (p.accumulate) *dst += v[k];
+          else *dst = v[k];
+        }
+      }
+      if (p.C_hi && !(p.dbg & 2)) {
+        const long long o = (long long)bz * p.bC + (long long)i * p.sci;
+        if (vec_h && full) {
+          __align__(16) bf16 h[16], l[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            h[k] = __float2bfloat16(v[k]);
+            l[k] = __float2bfloat16(v[k] - __bfloat162float(h[k]));
+          }
+          uint4* dh = reinterpret_cast<uint4*>(p.C_hi + o + jc);
+          dh[0] = reinterpret_cast<const uint4*>(h)[0];
+          dh[1] = reinterpret_cast<const uint4*>(h)[1];
+          if (p.C_lo) {
+            uint4* dl = reinterpret_cast<uint4*>(p.C_lo + o + jc);
+            dl[0] = reinterpret_cast<const uint4*>(l)[0];
+            dl[1] = reinterpret_cast<const uint4*>(l)[1];
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const int j = jc + k;
+            if (j >= p.extJ || c * 16 + k >= BN) continue;
+            const bf16 h = __float2bfloat16(v[k]);
+            p.C_hi[o + (long long)j * p.scj] = h;
+            if (p.C_lo) p.C_lo[o + (long long)j * p.scj] = __float2bfloat16(v[k] - __bfloat162float(h));
+          }
         }
       }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (csize > 1) cluster_sync_all();   // no member exits while a peer can still arrive on its barriers
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
@@ -387,7 +523,8 @@ int pack_operand(rau_ctx* ctx, const Operand& o, bool want_lo, const char* slot,
   return RAU_OK;
 }
 
-int encode_map(CUtensorMap* m, const bf16* base, const Packed& pk, int box_rows) {
+int encode_map(CUtensorMap* m, const bf16* base, const Packed& pk) {
+  const int box_rows = 64;
   cuuint64_t dims[3] = {(cuuint64_t)pk.Cc, (cuuint64_t)pk.R, (cuuint64_t)pk.nz};
   cuuint64_t strides[2] = {(cuuint64_t)pk.ldo * 2, (cuuint64_t)pk.ldo * 2 * (cuuint64_t)pk.R};
   cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
@@ -407,6 +544,14 @@ bool g_attr_set = false;
 
 // products below this many multiply-adds stay on the CUDA cores (RAU_TC_MIN_WORK overrides; tests set it to 0 so
 // that toy shapes exercise every TMA / descriptor edge case)
+bool tc_cluster_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RAU_TC_CLUSTER");
+    v = e ? (atoi(e) != 0) : 0;   // multicast measured slower on the per-image products (profiles/): opt-in
+  }
+  return v != 0;
+}
 long long tc_min_work() {
   static long long v = -1;
   if (v < 0) {
@@ -499,8 +644,8 @@ int tc_gemm_try(rau_ctx* ctx, const SimtGemm& g) {
   p.kbatch = g.kbatch; p.ksplit = ksplit;
   for (int s = 0; s < nseg; ++s) {
     for (int h = 0; h < nt; ++h) {
-      RAU_TRY(encode_map(&p.mapP[s][h], h ? pkP[s].lo : pkP[s].hi, pkP[s], pkP[s].mn ? TC_BK : TC_BM));
-      RAU_TRY(encode_map(&p.mapQ[s][h], h ? pkQ[s].lo : pkQ[s].hi, pkQ[s], pkQ[s].mn ? TC_BK : BN));
+      RAU_TRY(encode_map(&p.mapP[s][h], h ? pkP[s].lo : pkP[s].hi, pkP[s]));
+      RAU_TRY(encode_map(&p.mapQ[s][h], h ? pkQ[s].lo : pkQ[s].hi, pkQ[s]));
     }
   }
   const int stage_bytes = nt * (TC_BM * TC_BK * 2 + BNbox * TC_BK * 2);
@@ -522,6 +667,7 @@ int tc_gemm_try(rau_ctx* ctx, const SimtGemm& g) {
   p.addend = g.addend; p.addend2 = g.addend2; p.bD = g.bD;
   p.sdi = swap ? g.sdn : g.sdm; p.sdj = swap ? g.sdm : g.sdn;
   p.act = g.act; p.accumulate = g.accumulate; p.atomic = ksplit > 1 ? 1 : 0;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("RAU_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   if (clear_c) {
     if (g.scn == 1)
       RAU_CHECK_CUDA(cudaMemset2DAsync(g.C, (size_t)g.scm * 4, 0, (size_t)g.N * 4, (size_t)g.M, ctx->stream));
@@ -535,7 +681,32 @@ int tc_gemm_try(rau_ctx* ctx, const SimtGemm& g) {
     g_attr_set = true;
   }
   dim3 grid((extJ + BN - 1) / BN, (unsigned)itiles, (unsigned)(g.batch * ksplit));
-  tc_gemm_kernel<<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p);
+  // cluster shape: j-tiles share P, i-tiles share Q, images share whichever operand is batch-invariant
+  int CX = 1, CY = 1, CZ = 1;
+  if (tc_cluster_enabled()) {
+    if (grid.x % 2 == 0) CX = 2;
+    if (grid.y % 4 == 0) CY = 4; else if (grid.y % 2 == 0) CY = 2;
+    const bool pz = p.p_zmode == 0, qz = p.q_zmode == 0;
+    if (ksplit == 1 && g.batch > 1 && (pz || qz)) {
+      CZ = 8 / (CX * CY);
+      while (CZ > 1 && g.batch % CZ != 0) CZ /= 2;
+      if (CZ < 1) CZ = 1;
+    }
+    p.p_zshare = (pz && CZ > 1) ? 1 : 0;
+    p.q_zshare = (qz && CZ > 1) ? 1 : 0;
+  }
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.gridDim = grid;
+  lc.blockDim = dim3(TC_THREADS);
+  lc.dynamicSmemBytes = smem_bytes;
+  lc.stream = ctx->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CX; at[0].val.clusterDim.y = CY; at[0].val.clusterDim.z = CZ;
+  lc.attrs = at;
+  lc.numAttrs = 1;
+  RAU_CHECK_CUDA(cudaLaunchKernelEx(&lc, tc_gemm_kernel, p));
   RAU_LAUNCH_CHECK(ctx);
   return 1;
 }

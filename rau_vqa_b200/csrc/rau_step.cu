@@ -499,16 +499,28 @@ int rau_time_iembed(rau_ctx* ctx, const rau_config* cfg, int B, const float* mul
   RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
   ctx->epoch++;
   const int Sp = rau_sp(cfg->S), M = cfg->M, C = cfg->C, S = cfg->S;
-  ARENA(Xd, float, "hop.Xd", (size_t)B * C * Sp);
   ARENA(I, float, "time.I", (size_t)B * M * Sp);
   MultT<const float*> P = mult_views<const float*, const float>(cfg, mult_params);
-  RAU_TRY(k_dropout(ctx, X, (int64_t)B * C, S, S, nullptr, 1.0f, Xd, Sp, nullptr, 0, Sp));
+  const bool tc = ctx->precision != RAU_PREC_F32 && S % 4 == 0;
+  const bool x3 = ctx->precision == RAU_PREC_BF16X3;
   SimtGemm g;
   g.M = M; g.N = Sp; g.K = C;
   g.A = P.Wi; g.sam = C; g.sak = 1; g.a_const = 1;
-  g.B = Xd; g.sbk = Sp; g.sbn = 1; g.bB = (int64_t)C * Sp;
+  g.sbk = Sp; g.sbn = 1; g.bB = (int64_t)C * Sp;
   g.C = I; g.scm = Sp; g.scn = 1; g.bC = (int64_t)M * Sp;
   g.batch = B; g.bias_m = P.bi; g.act = 1; g.n_valid = S;
+  if (tc) {   // exactly the training launch: packed operand in, fp32 + packed (hi, lo) result out
+    ARENA(Xh, bf16, "time.Xh", (size_t)B * C * Sp);
+    ARENA(Xl, bf16, "time.Xl", (size_t)B * C * Sp);
+    ARENA(Ih, bf16, "time.Ih", (size_t)B * M * Sp);
+    ARENA(Il, bf16, "time.Il", (size_t)B * M * Sp);
+    RAU_TRY(k_dropout_pack(ctx, X, (int64_t)B * C, S, nullptr, 1.0f, Xh, x3 ? Xl : nullptr, Sp));
+    g.B_hi = Xh; g.B_lo = Xl; g.C_hi = Ih; g.C_lo = Il;
+  } else {
+    ARENA(Xd, float, "hop.Xd", (size_t)B * C * Sp);
+    RAU_TRY(k_dropout(ctx, X, (int64_t)B * C, S, S, nullptr, 1.0f, Xd, Sp, nullptr, 0, Sp));
+    g.B = Xd;
+  }
   RAU_TRY(rau_contract(ctx, g));   // warm-up
   RAU_CHECK_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
   for (int i = 0; i < iters; ++i) RAU_TRY(rau_contract(ctx, g));
