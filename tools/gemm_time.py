@@ -20,9 +20,11 @@ SHAPES = [  # (M, N, K, ta, tb, what)
     (6656, 2048, 512, 0, 0, "hoisted encoder projection"),
     (8192, 8192, 2048, 0, 0, "square-ish peak check"),
 ]
-for mode, name in ((core.PREC_BF16, "bf16"), (core.PREC_BF16X3, "bf16x3")):
+PICK = [int(i) for i in os.environ.get("GT_SHAPES", "").split(",") if i] or list(range(len(SHAPES)))
+MODES = [m for m in ((core.PREC_BF16, "bf16"), (core.PREC_BF16X3, "bf16x3")) if m[1] in os.environ.get("GT_MODES", "bf16,bf16x3").split(",")]
+for mode, name in MODES:
     ctx = R.Context(0, precision=mode)
-    for (M, N, K, ta, tb, what) in SHAPES:
+    for (M, N, K, ta, tb, what) in [SHAPES[i] for i in PICK]:
         a = torch.randn((K, M) if ta else (M, K), device="cuda")
         b = torch.randn((K, N) if tb else (N, K), device="cuda")
         c = torch.zeros(M, N, device="cuda")
