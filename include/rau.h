@@ -243,6 +243,11 @@ int rau_allreduce(rau_ctx* ctx, float* buf, int64_t n);
  * [rows,K] (K-major), 1 = stored [K,rows].  accumulate != 0 adds into C. */
 int rau_gemm(rau_ctx* ctx, int M, int N, int K, const float* A, int lda, int ta,
              const float* B, int ldb, int tb, float* C, int ldc, int accumulate);
+/* D[M,N] (+)= A B^T on the persistent rows-layout tcgen05 engine that carries the answering unit's image-side products
+ * (bf16 / bf16x3 modes only).  a_mn/b_mn: 0 = operand stored [rows, ld >= K], 1 = stored [K, ld >= rows]; pitches are
+ * multiples of 8 floats.  reduce != 0: split-K partial sums are ADDED into D (TMA reduce-add), else D is overwritten. */
+int rau_rows_gemm(rau_ctx* ctx, int M, int N, int K, const float* A, int lda, int a_mn,
+                  const float* B, int ldb, int b_mn, float* D, int ldd, int reduce);
 /* softmax cross-entropy of score[B,N] against 1-based labels: loss_sum += scale*sum_b nll_b,
  * dscore = scale*(softmax - onehot), answers = argmax (1-based, ties -> lowest index). */
 int rau_softmax_ce(rau_ctx* ctx, int B, int N, const float* score, const float* labels, float scale,

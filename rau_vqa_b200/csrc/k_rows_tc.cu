@@ -1,0 +1,831 @@
+// k_rows_tc.cu -- the persistent tcgen05 engine of the answering unit's heavy products (SURVEY.md 8a rows a6/a7 and
+// their backward).  All image-side activations of a hop live in a "rows" layout: one row per grid cell of one image,
+// r = b*S + s, features contiguous ([R, C] dropped-out features, [R, M] i_embed output I, [R, A] attention hidden E).
+// In that layout the reference's per-image 1x1 convolutions (F:240, F:247) are plain [R, K] x [K, N] products whose
+// 128-row tiles are always full (no 196 -> 256 padding), and the backward weight gradients are [K = R] reductions.
+//
+//   D[M, N] = sum_k A[m, k] * B[n, k]         A, B: bf16 (hi [, lo]) arrays, K-major ([rows, K]) or MN-major ([K, rows])
+//
+// One CTA per SM walks a static list of work items (tile_m, tile_n, k_slice).  Warp roles:
+//   warp 0      TMA producer: 48 KB stages (A 128 x BK, B 256 x BK; hi and lo tiles in bf16x3 mode, BK = 32; BK = 64 else)
+//   warp 1      MMA issuer: tcgen05.mma kind::f16, M = 128, N = 256, fp32 accumulators in TMEM; bf16x3 issues
+//               hi*hi + hi*lo + lo*hi into the same accumulator.  Two 256-column accumulators alternate between items,
+//               so the epilogue of item i overlaps the MMAs of item i+1.
+//   warps 2..5  epilogue: tcgen05.ld (one TMEM lane = one row per thread) -> fused math -> 128B-swizzled staging in
+//               shared memory -> TMA store (bf16 hi/lo or fp32) or TMA reduce-add (split-K weight gradients).
+// Epilogues (template parameter):
+//   EPI_PLAIN  D (tests, dX)                                   EPI_RED   D added into fp32 global (split-K wgrad)
+//   EPI_TANH   tanh(D + bias[n]) -> bf16 hi/lo                 (i_embed F:240-241)
+//   EPI_ATT    E = tanh(D + bias[n] + rowvec[b(r), n]) -> fp32, logit[r] = sum_n colw[n] E[r, n]   (F:246-251)
+//   EPI_DY     dY = (D + rowvec[b(r), n] * rowscale[r]) * (1 - I[r, n]^2) -> bf16 hi/lo, colsum[n] += sum_r dY
+#include "rau_model.cuh"
+#include <cuda.h>
+#include <stdlib.h>
+
+namespace {
+
+constexpr int RT_BM = 128, RT_BN = 256;
+constexpr int RT_STAGE = 48 * 1024;
+constexpr int RT_THREADS = 192;
+constexpr int RT_STG_WARP = 8192;          // per epilogue warp: two 32-row x 128-byte swizzled staging buffers
+constexpr int RT_MAXSTAGES = 4;
+
+enum { EPI_PLAIN = 0, EPI_RED = 1, EPI_TANH = 2, EPI_ATT = 3, EPI_DY = 4 };
+
+struct RtParams {
+  CUtensorMap mapA[2], mapB[2];   // [hi, lo] operand tiles
+  CUtensorMap mapO[2];            // outputs: bf16 (hi, lo) or fp32 ([0])
+  int M, N, K;
+  int a_mn, b_mn, x3, BK, nkb;
+  int ksplit, kb_per;
+  int tiles_m, tiles_n, stages;
+  int out_lo;                      // bf16 outputs: also write the lo array
+  const float* bias;
+  const float* rowvec;             // [B, N]
+  const float* colw;               // [N]
+  float* rowout;                   // [M]
+  const float* rowscale;           // [M]
+  const bf16* aux_hi; const bf16* aux_lo; long long ldaux;
+  float* colsum;                   // [N]
+  int S;
+  float alpha;
+  int fast_tanh;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+}
+
+// tanh to ~2e-7 absolute (bf16x3 mode): odd polynomial near zero, 1 - 2/(e^2x + 1) elsewhere
+__device__ __forceinline__ float tanh_acc(float x) {
+  const float ax = fabsf(x);
+  const float x2 = x * x;
+  const float pol = x * (1.0f + x2 * (-0.33333334f + x2 * (0.13333334f + x2 * (-0.05396825f + x2 * 0.02186949f))));
+  const float e = __expf(2.0f * ax);
+  const float t = copysignf(1.0f - __fdividef(2.0f, e + 1.0f), x);
+  return ax < 0.15f ? pol : t;
+}
+__device__ __forceinline__ float tanh_hw(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
+// version = 1 [46,48) | layout type [61,64): 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46) | ((uint64_t)layout << 61);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+// hi = bf16(a), lo = bf16(a - hi) for a pair
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+  __nv_bfloat162 h2 = __halves2bfloat162(ha, hb);
+  hi = *reinterpret_cast<uint32_t*>(&h2);
+  lo = pack_bf16x2(a - __bfloat162float(ha), b - __bfloat162float(hb));
+}
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+// write 32 consecutive 32-bit words of this lane's row into a 32-row x 128-byte SWIZZLE_128B staging buffer
+__device__ __forceinline__ void stage_row(uint32_t buf, int lane, const uint32_t* w) {
+  const uint32_t base = buf + (uint32_t)lane * 128u;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t a = base + (uint32_t)((j ^ (lane & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[4 * j]), "r"(w[4 * j + 1]), "r"(w[4 * j + 2]),
+                 "r"(w[4 * j + 3])
+                 : "memory");
+  }
+}
+
+// lane L ends with sum over lanes of x[L] (31 shuffles)
+__device__ __forceinline__ float warp_transpose_sum32(float* x, int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? x[i] : x[i + off];
+      const float keep = up ? x[i + off] : x[i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return x[0];
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_constant__ RtParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[RT_MAXSTAGES], empty_bar[RT_MAXSTAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* staging = smem + (size_t)p.stages * RT_STAGE;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int items = p.tiles_m * p.tiles_n * p.ksplit;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.mapA[0]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.mapB[0]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.mapO[0]) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  const uint32_t a_bytes = (uint32_t)RT_BM * p.BK * 2, b_bytes = (uint32_t)RT_BN * p.BK * 2;
+  const int nt = p.x3 ? 2 : 1;
+
+  if (warp == 0) {
+    // ===================== TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int ks = item % p.ksplit;
+        const int tile = item / p.ksplit;
+        const int tn = tile % p.tiles_n, tm = tile / p.tiles_n;
+        const int m0 = tm * RT_BM, n0 = tn * RT_BN;
+        const int kb0 = ks * p.kb_per, kb1 = min(p.nkb, kb0 + p.kb_per);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int st = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1u;
+          mbar_wait(&empty_bar[st], ph ^ 1u);
+          uint8_t* sa = smem + (size_t)st * RT_STAGE;
+          uint8_t* sb = sa + nt * a_bytes;
+          mbar_expect_tx(&full_bar[st], nt * (a_bytes + b_bytes));
+          const int k0 = kb * p.BK;
+          for (int h = 0; h < nt; ++h) {
+            if (p.a_mn) {   // boxes of 64 rows-of-A (contiguous) x BK k
+#pragma unroll
+              for (int u = 0; u < RT_BM / 64; ++u)
+                tma_load_2d(sa + h * a_bytes + u * (p.BK * 128), &p.mapA[h], &full_bar[st], m0 + 64 * u, k0);
+            } else {
+              tma_load_2d(sa + h * a_bytes, &p.mapA[h], &full_bar[st], k0, m0);
+            }
+            if (p.b_mn) {
+#pragma unroll
+              for (int u = 0; u < RT_BN / 64; ++u)
+                tma_load_2d(sb + h * b_bytes + u * (p.BK * 128), &p.mapB[h], &full_bar[st], n0 + 64 * u, k0);
+            } else {
+              tma_load_2d(sb + h * b_bytes, &p.mapB[h], &full_bar[st], k0, n0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6) | A=bf16 [7,10) | B=bf16 [10,13) |
+      // a_major [15] | b_major [16] | N>>3 [17,23) | M>>4 [24,29)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                             ((uint32_t)(RT_BN >> 3) << 17) | ((uint32_t)(RT_BM >> 4) << 24);
+      // K-major tile: rows of BK*2 bytes (64 B -> SWIZZLE_64B, 128 B -> SWIZZLE_128B), 8-row groups SBO apart; a 16-k
+      //   step is +32 bytes inside the swizzled row.
+      // MN-major tile: 64-wide chunks BK*128 bytes apart (LBO), 8-k-row groups 1024 bytes apart (SBO), SWIZZLE_128B;
+      //   a 16-k step is 16 rows = 2048 bytes.
+      const uint32_t k_layout = p.BK == 32 ? 4u : 2u, k_sbo = p.BK == 32 ? 512u : 1024u;
+      const uint32_t a_step = p.a_mn ? (2048u >> 4) : (32u >> 4), b_step = p.b_mn ? (2048u >> 4) : (32u >> 4);
+      const int nsteps = p.BK / 16;
+      uint32_t it = 0, li = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
+        const int ks = item % p.ksplit;
+        const int kb0 = ks * p.kb_per, kb1 = min(p.nkb, kb0 + p.kb_per);
+        const uint32_t ab = li & 1u, aph = (li >> 1) & 1u;
+        mbar_wait(&tempty_bar[ab], aph ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t dcol = tmem_base + ab * (uint32_t)RT_BN;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int st = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1u;
+          mbar_wait(&full_bar[st], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(smem + (size_t)st * RT_STAGE);
+          const uint32_t sb = sa + nt * a_bytes;
+          const uint64_t da_hi = p.a_mn ? make_desc(sa, (uint32_t)p.BK * 128u, 1024u, 2u) : make_desc(sa, 16u, k_sbo, k_layout);
+          const uint64_t db_hi = p.b_mn ? make_desc(sb, (uint32_t)p.BK * 128u, 1024u, 2u) : make_desc(sb, 16u, k_sbo, k_layout);
+          const uint64_t da_lo = da_hi + (uint64_t)(a_bytes >> 4), db_lo = db_hi + (uint64_t)(b_bytes >> 4);
+          for (int k = 0; k < nsteps; ++k) {
+            const uint64_t oa = (uint64_t)(k * a_step), ob = (uint64_t)(k * b_step);
+            umma_f16(dcol, da_hi + oa, db_hi + ob, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (p.x3) {
+              umma_f16(dcol, da_hi + oa, db_lo + ob, idesc, 1u);
+              umma_f16(dcol, da_lo + oa, db_hi + ob, idesc, 1u);
+            }
+          }
+          umma_commit(&empty_bar[st]);     // frees the stage once these MMAs have read it
+        }
+        umma_commit(&tfull_bar[ab]);       // accumulator of this item complete
+      }
+    }
+  } else {
+    // ===================== epilogue warps: TMEM lanes 32*(warp%4) .. +31
+    const int q = warp & 3;
+    const uint32_t stg0 = smem_u32(staging + (size_t)(warp - 2) * RT_STG_WARP), stg1 = stg0 + 4096u;
+    uint32_t li = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
+      const int tile = item / p.ksplit;
+      const int tn = tile % p.tiles_n, tm = tile / p.tiles_n;
+      const int m0 = tm * RT_BM, n0 = tn * RT_BN;
+      const uint32_t ab = li & 1u, aph = (li >> 1) & 1u;
+      const int r = m0 + q * 32 + lane;          // global row of this thread
+      const bool r_ok = r < p.M;
+      const int rr = r_ok ? r : p.M - 1;
+      const int rowbase = m0 + q * 32;           // first row of this warp's 32-row slab
+      mbar_wait(&tfull_bar[ab], aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ab * (uint32_t)RT_BN + ((uint32_t)(q * 32) << 16);
+      float rowacc = 0.0f;
+      const float* rv = nullptr;
+      float rs = 0.0f;
+      if (EPI == EPI_ATT || EPI == EPI_DY) rv = p.rowvec + (long long)(rr / p.S) * p.N;
+      if (EPI == EPI_DY) rs = p.rowscale[rr];
+#pragma unroll 1
+      for (int c = 0; c < RT_BN / 64; ++c) {
+        const int nc = n0 + c * 64;
+        if (nc >= p.N) break;
+        float v[64];
+        tmem_ld32(taddr + (uint32_t)(c * 64), v);
+        tmem_ld32(taddr + (uint32_t)(c * 64 + 32), v + 32);
+        if (c == RT_BN / 64 - 1 || nc + 64 >= p.N) {   // last read of this accumulator: hand it back to the MMA warp
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[ab]);
+        }
+        uint32_t w0[32], w1[32];
+        if (EPI == EPI_PLAIN || EPI == EPI_RED) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) { w0[k] = __float_as_uint(v[k] * p.alpha); w1[k] = __float_as_uint(v[k + 32] * p.alpha); }
+        } else if (EPI == EPI_TANH) {
+#pragma unroll
+          for (int k4 = 0; k4 < 16; ++k4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nc) + k4);
+            v[4 * k4] += b4.x; v[4 * k4 + 1] += b4.y; v[4 * k4 + 2] += b4.z; v[4 * k4 + 3] += b4.w;
+          }
+#pragma unroll
+          for (int k = 0; k < 64; ++k) v[k] = p.fast_tanh ? tanh_hw(v[k]) : tanh_acc(v[k]);
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            if (p.out_lo) split_pair(v[2 * k], v[2 * k + 1], w0[k], w1[k]);
+            else w0[k] = pack_bf16x2(v[2 * k], v[2 * k + 1]);
+          }
+        } else if (EPI == EPI_ATT) {
+#pragma unroll
+          for (int k4 = 0; k4 < 16; ++k4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nc) + k4);
+            const float4 q4 = __ldg(reinterpret_cast<const float4*>(rv + nc) + k4);
+            const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.colw + nc) + k4);
+            float e;
+            e = v[4 * k4] + b4.x + q4.x;     e = p.fast_tanh ? tanh_hw(e) : tanh_acc(e); v[4 * k4] = e;     rowacc = fmaf(c4.x, e, rowacc);
+            e = v[4 * k4 + 1] + b4.y + q4.y; e = p.fast_tanh ? tanh_hw(e) : tanh_acc(e); v[4 * k4 + 1] = e; rowacc = fmaf(c4.y, e, rowacc);
+            e = v[4 * k4 + 2] + b4.z + q4.z; e = p.fast_tanh ? tanh_hw(e) : tanh_acc(e); v[4 * k4 + 2] = e; rowacc = fmaf(c4.z, e, rowacc);
+            e = v[4 * k4 + 3] + b4.w + q4.w; e = p.fast_tanh ? tanh_hw(e) : tanh_acc(e); v[4 * k4 + 3] = e; rowacc = fmaf(c4.w, e, rowacc);
+          }
+#pragma unroll
+          for (int k = 0; k < 32; ++k) { w0[k] = __float_as_uint(v[k]); w1[k] = __float_as_uint(v[k + 32]); }
+        } else {   // EPI_DY
+          const uint4* ih = reinterpret_cast<const uint4*>(p.aux_hi + (long long)rr * p.ldaux + nc);
+          const uint4* il = p.aux_lo ? reinterpret_cast<const uint4*>(p.aux_lo + (long long)rr * p.ldaux + nc) : nullptr;
+#pragma unroll
+          for (int k8 = 0; k8 < 8; ++k8) {
+            const uint4 h = __ldg(ih + k8);
+            uint4 l = make_uint4(0u, 0u, 0u, 0u);
+            if (il) l = __ldg(il + k8);
+            const float4 d0 = __ldg(reinterpret_cast<const float4*>(rv + nc) + 2 * k8);
+            const float4 d1 = __ldg(reinterpret_cast<const float4*>(rv + nc) + 2 * k8 + 1);
+            const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+            const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float y0 = bf_lo(hh[j]) + bf_lo(ll[j]), y1 = bf_hi(hh[j]) + bf_hi(ll[j]);
+              const int k = 8 * k8 + 2 * j;
+              const float g0 = (v[k] + dd[2 * j] * rs) * (1.0f - y0 * y0);
+              const float g1 = (v[k + 1] + dd[2 * j + 1] * rs) * (1.0f - y1 * y1);
+              v[k] = r_ok ? g0 : 0.0f;
+              v[k + 1] = r_ok ? g1 : 0.0f;
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            if (p.out_lo) split_pair(v[2 * k], v[2 * k + 1], w0[k], w1[k]);
+            else w0[k] = pack_bf16x2(v[2 * k], v[2 * k + 1]);
+          }
+          if (p.colsum) {
+            const float s0 = warp_transpose_sum32(v, lane);
+            const float s1 = warp_transpose_sum32(v + 32, lane);
+            if (nc + lane < p.N) atomicAdd(p.colsum + nc + lane, s0);
+            if (nc + 32 + lane < p.N) atomicAdd(p.colsum + nc + 32 + lane, s1);
+          }
+        }
+        // staging buffers are free once the previous chunk's bulk stores have read them
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+        const bool two = (EPI == EPI_PLAIN || EPI == EPI_RED || EPI == EPI_ATT) || p.out_lo;
+        stage_row(stg0, lane, w0);
+        if (two) stage_row(stg1, lane, w1);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const void* s0p = staging + (size_t)(warp - 2) * RT_STG_WARP;
+          const void* s1p = (const uint8_t*)s0p + 4096;
+          if (EPI == EPI_RED) {
+            tma_reduce_add_2d(&p.mapO[0], s0p, nc, rowbase);
+            if (nc + 32 < p.N) tma_reduce_add_2d(&p.mapO[0], s1p, nc + 32, rowbase);
+          } else if (EPI == EPI_PLAIN || EPI == EPI_ATT) {
+            tma_store_2d(&p.mapO[0], s0p, nc, rowbase);
+            if (nc + 32 < p.N) tma_store_2d(&p.mapO[0], s1p, nc + 32, rowbase);
+          } else {
+            tma_store_2d(&p.mapO[0], s0p, nc, rowbase);
+            if (p.out_lo) tma_store_2d(&p.mapO[1], s1p, nc, rowbase);
+          }
+          bulk_commit();
+        }
+      }
+      if (EPI == EPI_ATT && r_ok && p.rowout) p.rowout[r] = rowacc;
+    }
+    if (lane == 0) bulk_wait0();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace
+
+// ================================================================== host side
+#include "rau_rows.cuh"
+
+namespace {
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn g_encode = nullptr;
+
+int get_encode() {
+  if (g_encode) return RAU_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr);
+  if (e != cudaSuccess || fn == nullptr) {
+    rau_set_error("cuTensorMapEncodeTiled is not available: %s", cudaGetErrorString(e));
+    return RAU_ECUDA;
+  }
+  g_encode = (EncodeFn)fn;
+  return RAU_OK;
+}
+
+// 2-D map over a row-major array: dim0 (contiguous) x dim1 rows of pitch ld elements
+int encode_2d(CUtensorMap* m, CUtensorMapDataType dt, int esize, const void* base, uint64_t dim0, uint64_t dim1, uint64_t ld,
+              uint32_t box0, uint32_t box1, CUtensorMapSwizzle sw) {
+  cuuint64_t dims[2] = {dim0, dim1};
+  cuuint64_t strides[1] = {ld * (uint64_t)esize};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_encode(m, dt, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    rau_set_error("cuTensorMapEncodeTiled failed (%d): dims=%llu,%llu ld=%llu box=%u,%u esize=%d", (int)r,
+                  (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)ld, box0, box1, esize);
+    return RAU_ECUDA;
+  }
+  return RAU_OK;
+}
+
+int encode_operand(CUtensorMap* m, const bf16* base, int mn, int rows, int K, int64_t ld, int BK, int box_rows) {
+  if (mn)   // stored [K, rows]: boxes of 64 rows (contiguous) x BK k
+    return encode_2d(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, (uint64_t)rows, (uint64_t)K, (uint64_t)ld, 64, (uint32_t)BK,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+  return encode_2d(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, (uint64_t)K, (uint64_t)rows, (uint64_t)ld, (uint32_t)BK,
+                   (uint32_t)box_rows, BK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+bool g_attr_done[8] = {false, false, false, false, false, false, false, false};
+
+template <int EPI>
+int launch_rows(rau_ctx* ctx, const RtParams& p, int grid, int smem_bytes) {
+  if (!g_attr_done[EPI]) {
+    RAU_CHECK_CUDA(cudaFuncSetAttribute(rows_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    g_attr_done[EPI] = true;
+  }
+  rows_gemm_kernel<EPI><<<grid, RT_THREADS, smem_bytes, ctx->stream>>>(p);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+
+__global__ void pack_hilo_kernel(const float* __restrict__ in, int64_t n4, bf16* __restrict__ hi, bf16* __restrict__ lo) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 x = reinterpret_cast<const float4*>(in)[i];
+    uint32_t h0, l0, h1, l1;
+    split_pair(x.x, x.y, h0, l0);
+    split_pair(x.z, x.w, h1, l1);
+    reinterpret_cast<uint2*>(hi)[i] = make_uint2(h0, h1);
+    if (lo) reinterpret_cast<uint2*>(lo)[i] = make_uint2(l0, l1);
+  }
+}
+
+// X [B, C, S] fp32 -> dropped-out features in rows layout [B*S, C] as bf16 (hi, lo); keep bit index = (b*C + c)*S + s
+__global__ void __launch_bounds__(256) xprep_rows_kernel(const float* __restrict__ X, const uint32_t* __restrict__ bits, float scale,
+                                                         int C, int S, bf16* __restrict__ hi, bf16* __restrict__ lo) {
+  extern __shared__ float sT[];   // [S][66]
+  const int b = blockIdx.y, c0 = blockIdx.x * 64;
+  const int S4 = S >> 2;
+  for (int i = threadIdx.x; i < 64 * S4; i += 256) {
+    const int c = i / S4, s4 = i - c * S4;
+    const int64_t e = ((int64_t)b * C + c0 + c) * S + 4 * s4;
+    float4 t = *reinterpret_cast<const float4*>(X + e);
+    if (bits) {
+      const uint32_t w = bits[e >> 5] >> (e & 31);
+      t.x = (w & 1u) ? t.x * scale : 0.0f;
+      t.y = (w & 2u) ? t.y * scale : 0.0f;
+      t.z = (w & 4u) ? t.z * scale : 0.0f;
+      t.w = (w & 8u) ? t.w * scale : 0.0f;
+    }
+    float* d = sT + (4 * s4) * 66 + c;
+    d[0] = t.x; d[66] = t.y; d[132] = t.z; d[198] = t.w;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int s = warp; s < S; s += 8) {
+    const float2 v = *reinterpret_cast<const float2*>(sT + s * 66 + 2 * lane);
+    uint32_t h, l;
+    split_pair(v.x, v.y, h, l);
+    const int64_t o = (((int64_t)b * S + s) * C + c0) >> 1;
+    reinterpret_cast<uint32_t*>(hi)[o + lane] = h;
+    if (lo) reinterpret_cast<uint32_t*>(lo)[o + lane] = l;
+  }
+}
+
+// dXr [B*S, C] fp32 -> dX [B, C, S] = dXr^T * keep * scale  (backward of the feature dropout, F:239)
+__global__ void __launch_bounds__(256) unprep_rows_kernel(const float* __restrict__ dXr, const uint32_t* __restrict__ bits, float scale,
+                                                          int C, int S, float* __restrict__ dX) {
+  extern __shared__ float sT[];   // [S][66]
+  const int b = blockIdx.y, c0 = blockIdx.x * 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int s = warp; s < S; s += 8) {
+    const float2 v = *reinterpret_cast<const float2*>(dXr + ((int64_t)b * S + s) * C + c0 + 2 * lane);
+    *reinterpret_cast<float2*>(sT + s * 66 + 2 * lane) = v;
+  }
+  __syncthreads();
+  const int S4 = S >> 2;
+  for (int i = threadIdx.x; i < 64 * S4; i += 256) {
+    const int c = i / S4, s4 = i - c * S4;
+    const int64_t e = ((int64_t)b * C + c0 + c) * S + 4 * s4;
+    const float* d = sT + (4 * s4) * 66 + c;
+    float4 t = make_float4(d[0], d[66], d[132], d[198]);
+    if (bits) {
+      const uint32_t w = bits[e >> 5] >> (e & 31);
+      t.x = (w & 1u) ? t.x * scale : 0.0f;
+      t.y = (w & 2u) ? t.y * scale : 0.0f;
+      t.z = (w & 4u) ? t.z * scale : 0.0f;
+      t.w = (w & 8u) ? t.w * scale : 0.0f;
+    }
+    *reinterpret_cast<float4*>(dX + e) = t;
+  }
+}
+
+// attbymemory + attselect on the rows layout (F:285-290, F:254-263): p = softmax(logit + mem), a = sum_s p_s I[b*S+s, :]
+// grid (B, M/256), 128 threads, two channels per thread
+__global__ void __launch_bounds__(128) attn_rows_fwd_kernel(int S, int M, const float* __restrict__ logit,
+                                                            const float* __restrict__ mem, const bf16* __restrict__ I_hi,
+                                                            const bf16* __restrict__ I_lo, float* __restrict__ p_out,
+                                                            float* __restrict__ a_out) {
+  __shared__ float p[256];
+  __shared__ float red[32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int64_t r0 = (int64_t)b * S;
+  const float l0 = tid < S ? logit[r0 + tid] + mem[r0 + tid] : -INFINITY;
+  const float l1 = tid + 128 < S ? logit[r0 + tid + 128] + mem[r0 + tid + 128] : -INFINITY;
+  const float mx = block_max(fmaxf(l0, l1), red);
+  const float e0 = tid < S ? __expf(l0 - mx) : 0.0f, e1 = tid + 128 < S ? __expf(l1 - mx) : 0.0f;
+  const float den = block_sum(e0 + e1, red);
+  p[tid] = e0 / den;
+  p[tid + 128] = e1 / den;
+  if (blockIdx.y == 0) {
+    if (tid < S) p_out[r0 + tid] = e0 / den;
+    if (tid + 128 < S) p_out[r0 + tid + 128] = e1 / den;
+  }
+  __syncthreads();
+  const int wpr = M >> 1;   // 32-bit words per row
+  const uint32_t* ih = reinterpret_cast<const uint32_t*>(I_hi) + r0 * wpr + blockIdx.y * 128 + tid;
+  const uint32_t* il = I_lo ? reinterpret_cast<const uint32_t*>(I_lo) + r0 * wpr + blockIdx.y * 128 + tid : nullptr;
+  float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll 4
+  for (int s = 0; s < S; ++s) {
+    const uint32_t u = __ldg(ih + (int64_t)s * wpr);
+    float y0 = bf_lo(u), y1 = bf_hi(u);
+    if (il) {
+      const uint32_t w = __ldg(il + (int64_t)s * wpr);
+      y0 += bf_lo(w);
+      y1 += bf_hi(w);
+    }
+    a0 = fmaf(p[s], y0, a0);
+    a1 = fmaf(p[s], y1, a1);
+  }
+  const int mc = blockIdx.y * 256 + 2 * tid;
+  *reinterpret_cast<float2*>(a_out + (int64_t)b * M + mc) = make_float2(a0, a1);
+}
+
+// backward of the above for one image (256 threads):
+//   dp = dp_in + I da ; ds = p (dp - <p,dp>) ; dZ[r,n] = ws[n] ds[s] (1 - E[r,n]^2) -> bf16 (hi, lo)
+//   dqa[b,n] = sum_s dZ[r,n] ; gws_part[b,n] = sum_s ds[s] E[r,n]
+__global__ void __launch_bounds__(256) attn_rows_bwd_kernel(int S, int M, int A, const float* __restrict__ E,
+                                                            const bf16* __restrict__ I_hi, const bf16* __restrict__ I_lo,
+                                                            const float* __restrict__ ws, const float* __restrict__ p_in,
+                                                            const float* __restrict__ dp_in, const float* __restrict__ da,
+                                                            float* __restrict__ ds_out, bf16* __restrict__ dZ_hi,
+                                                            bf16* __restrict__ dZ_lo, float* __restrict__ dqa,
+                                                            float* __restrict__ gws_part) {
+  extern __shared__ float sm[];
+  float* ds = sm;            // [256]
+  float* das = sm + 256;     // [M]
+  __shared__ float red[32];
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t r0 = (int64_t)b * S;
+  for (int m = tid; m < M; m += 256) das[m] = da[(int64_t)b * M + m];
+  ds[tid] = 0.0f;
+  __syncthreads();
+  const int wpr = M >> 1;
+  for (int s = warp; s < S; s += 8) {
+    const uint32_t* ih = reinterpret_cast<const uint32_t*>(I_hi) + (r0 + s) * wpr;
+    const uint32_t* il = I_lo ? reinterpret_cast<const uint32_t*>(I_lo) + (r0 + s) * wpr : nullptr;
+    float acc = 0.0f;
+    for (int w = lane; w < wpr; w += 32) {
+      const uint32_t u = __ldg(ih + w);
+      float y0 = bf_lo(u), y1 = bf_hi(u);
+      if (il) {
+        const uint32_t v = __ldg(il + w);
+        y0 += bf_lo(v);
+        y1 += bf_hi(v);
+      }
+      acc = fmaf(das[2 * w], y0, acc);
+      acc = fmaf(das[2 * w + 1], y1, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) ds[s] = acc + (dp_in ? dp_in[r0 + s] : 0.0f);
+  }
+  __syncthreads();
+  const float pv = tid < S ? p_in[r0 + tid] : 0.0f;
+  const float dpv = tid < S ? ds[tid] : 0.0f;
+  const float dot = block_sum(pv * dpv, red);
+  const float dsv = tid < S ? pv * (dpv - dot) : 0.0f;
+  __syncthreads();
+  ds[tid] = dsv;
+  if (tid < S) ds_out[r0 + tid] = dsv;
+  __syncthreads();
+  for (int n = tid; n < A; n += 256) {
+    const float w = ws[n];
+    float sz = 0.0f, sg = 0.0f;
+    const float* er = E + r0 * A + n;
+#pragma unroll 4
+    for (int s = 0; s < S; ++s) {
+      const float e = __ldg(er + (int64_t)s * A);
+      const float d = ds[s];
+      const float dz = w * d * (1.0f - e * e);
+      sg = fmaf(d, e, sg);
+      sz += dz;
+      const bf16 h = __float2bfloat16_rn(dz);
+      dZ_hi[(r0 + s) * A + n] = h;
+      if (dZ_lo) dZ_lo[(r0 + s) * A + n] = __float2bfloat16_rn(dz - __bfloat162float(h));
+    }
+    dqa[(int64_t)b * A + n] = sz;
+    gws_part[(int64_t)b * A + n] = sg;
+  }
+}
+
+bool g_prep_attr = false;
+
+}  // namespace
+
+bool rows_path_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RAU_ROWS");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+
+int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
+  RAU_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "rows_gemm: bad shape %dx%dx%d", g.M, g.N, g.K);
+  RAU_REQUIRE(g.A.hi && g.B.hi, "rows_gemm: operand missing");
+  RAU_REQUIRE((g.A.lo != nullptr) == (g.B.lo != nullptr), "rows_gemm: hi/lo split must be on both operands or neither");
+  RAU_REQUIRE(g.A.ld % 8 == 0 && g.B.ld % 8 == 0, "rows_gemm: operand pitches must be multiples of 8 elements");
+  RAU_REQUIRE((((uintptr_t)g.A.hi | (uintptr_t)g.B.hi | (uintptr_t)g.A.lo | (uintptr_t)g.B.lo) & 15) == 0,
+              "rows_gemm: operands must be 16-byte aligned");
+  RAU_TRY(get_encode());
+  RtParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.a_mn = g.A.mn; p.b_mn = g.B.mn;
+  p.x3 = g.A.lo ? 1 : 0;
+  p.BK = p.x3 ? 32 : 64;
+  p.nkb = (g.K + p.BK - 1) / p.BK;
+  p.tiles_m = (g.M + RT_BM - 1) / RT_BM;
+  p.tiles_n = (g.N + RT_BN - 1) / RT_BN;
+  p.stages = RT_MAXSTAGES;
+  const int tiles = p.tiles_m * p.tiles_n;
+  p.ksplit = 1;
+  if (g.epi == EPI_RED && tiles < ctx->sm_count) {
+    int want = ctx->sm_count / tiles;
+    if (want > p.nkb) want = p.nkb;
+    if (want < 1) want = 1;
+    p.ksplit = want;
+  }
+  p.kb_per = (p.nkb + p.ksplit - 1) / p.ksplit;
+  p.ksplit = (p.nkb + p.kb_per - 1) / p.kb_per;
+  for (int h = 0; h < (p.x3 ? 2 : 1); ++h) {
+    RAU_TRY(encode_operand(&p.mapA[h], h ? g.A.lo : g.A.hi, g.A.mn, g.M, g.K, g.A.ld, p.BK, RT_BM));
+    RAU_TRY(encode_operand(&p.mapB[h], h ? g.B.lo : g.B.hi, g.B.mn, g.N, g.K, g.B.ld, p.BK, RT_BN));
+  }
+  const bool f32_out = g.epi == EPI_PLAIN || g.epi == EPI_RED || g.epi == EPI_ATT;
+  if (f32_out) {
+    RAU_REQUIRE(g.out_f && g.ldo % 4 == 0 && ((uintptr_t)g.out_f & 15) == 0, "rows_gemm: fp32 output must be 16-byte aligned");
+    RAU_TRY(encode_2d(&p.mapO[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.out_f, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldo, 32, 32,
+                      CU_TENSOR_MAP_SWIZZLE_128B));
+  } else {
+    RAU_REQUIRE(g.out_hi && g.ldo % 8 == 0 && (((uintptr_t)g.out_hi | (uintptr_t)g.out_lo) & 15) == 0,
+                "rows_gemm: bf16 output must be 16-byte aligned");
+    RAU_TRY(encode_2d(&p.mapO[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.out_hi, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldo, 64, 32,
+                      CU_TENSOR_MAP_SWIZZLE_128B));
+    if (g.out_lo)
+      RAU_TRY(encode_2d(&p.mapO[1], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.out_lo, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldo, 64, 32,
+                        CU_TENSOR_MAP_SWIZZLE_128B));
+    p.out_lo = g.out_lo ? 1 : 0;
+  }
+  if (g.epi == EPI_TANH || g.epi == EPI_ATT || g.epi == EPI_DY)
+    RAU_REQUIRE(g.N % 64 == 0, "rows_gemm: fused epilogues need N %% 64 == 0 (N = %d)", g.N);
+  if (g.epi == EPI_ATT) RAU_REQUIRE(g.N <= RT_BN && g.S > 0 && g.rowvec && g.colw && g.bias, "rows_gemm: bad EPI_ATT arguments");
+  if (g.epi == EPI_DY) RAU_REQUIRE(g.S > 0 && g.rowvec && g.rowscale && g.aux_hi && g.ldaux % 8 == 0, "rows_gemm: bad EPI_DY arguments");
+  if (g.epi == EPI_TANH) RAU_REQUIRE(g.bias != nullptr, "rows_gemm: EPI_TANH needs a bias");
+  p.bias = g.bias; p.rowvec = g.rowvec; p.colw = g.colw; p.rowout = g.rowout; p.rowscale = g.rowscale;
+  p.aux_hi = g.aux_hi; p.aux_lo = g.aux_lo; p.ldaux = g.ldaux; p.colsum = g.colsum; p.S = g.S > 0 ? g.S : 1;
+  p.alpha = g.alpha;
+  p.fast_tanh = p.x3 ? 0 : 1;   // single-pass bf16: the result is rounded to bf16 anyway, MUFU.TANH (2^-11) is below that
+  const int items = tiles * p.ksplit;
+  const int grid = items < ctx->sm_count ? items : ctx->sm_count;
+  const int smem_bytes = p.stages * RT_STAGE + 4 * RT_STG_WARP + 1024;
+  switch (g.epi) {
+    case EPI_PLAIN: return launch_rows<EPI_PLAIN>(ctx, p, grid, smem_bytes);
+    case EPI_RED: return launch_rows<EPI_RED>(ctx, p, grid, smem_bytes);
+    case EPI_TANH: return launch_rows<EPI_TANH>(ctx, p, grid, smem_bytes);
+    case EPI_ATT: return launch_rows<EPI_ATT>(ctx, p, grid, smem_bytes);
+    case EPI_DY: return launch_rows<EPI_DY>(ctx, p, grid, smem_bytes);
+    default: rau_set_error("rows_gemm: unknown epilogue %d", g.epi); return RAU_EINVAL;
+  }
+}
+
+int rows_pack(rau_ctx* ctx, const float* W, int64_t n, bool want_lo, bool cache, const char* slot, const bf16** hi, const bf16** lo) {
+  RAU_REQUIRE(n % 8 == 0 && ((uintptr_t)W & 15) == 0, "rows_pack: %lld elements / alignment", (long long)n);
+  char name[128];
+  bool cached = false;
+  if (cache) {
+    snprintf(name, sizeof(name), "rw.%p.%lld.%d", (const void*)W, (long long)n, want_lo ? 1 : 0);
+    auto it = ctx->tc_epoch.find(name);
+    cached = it != ctx->tc_epoch.end() && it->second == ctx->epoch;
+  } else {
+    snprintf(name, sizeof(name), "rw.%s", slot);
+  }
+  void* buf = nullptr;
+  const size_t half = ((size_t)n * sizeof(bf16) + 1023) / 1024 * 1024;
+  RAU_TRY(ctx->arena.get(name, half * (want_lo ? 2 : 1), &buf));
+  bf16* h = (bf16*)buf;
+  bf16* l = want_lo ? (bf16*)((char*)buf + half) : nullptr;
+  if (!cached) {
+    int64_t blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    pack_hilo_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(W, n / 4, h, l);
+    RAU_LAUNCH_CHECK(ctx);
+    if (cache) ctx->tc_epoch[name] = ctx->epoch;
+  }
+  *hi = h;
+  *lo = l;
+  return RAU_OK;
+}
+
+static int prep_attr() {
+  if (!g_prep_attr) {
+    RAU_CHECK_CUDA(cudaFuncSetAttribute(xprep_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 66 * 4));
+    RAU_CHECK_CUDA(cudaFuncSetAttribute(unprep_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 66 * 4));
+    g_prep_attr = true;
+  }
+  return RAU_OK;
+}
+
+int k_xprep_rows(rau_ctx* ctx, const float* X, int B, int C, int S, const uint32_t* bits, float scale, bf16* hi, bf16* lo) {
+  RAU_REQUIRE(C % 64 == 0 && S % 4 == 0 && S <= 256 && ((uintptr_t)X & 15) == 0, "k_xprep_rows: C=%d S=%d", C, S);
+  RAU_TRY(prep_attr());
+  xprep_rows_kernel<<<dim3(C / 64, B), 256, S * 66 * 4, ctx->stream>>>(X, bits, scale, C, S, hi, lo);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+
+int k_unprep_rows(rau_ctx* ctx, const float* dXr, int B, int C, int S, const uint32_t* bits, float scale, float* dX) {
+  RAU_REQUIRE(C % 64 == 0 && S % 4 == 0 && S <= 256 && ((uintptr_t)dX & 15) == 0, "k_unprep_rows: C=%d S=%d", C, S);
+  RAU_TRY(prep_attr());
+  unprep_rows_kernel<<<dim3(C / 64, B), 256, S * 66 * 4, ctx->stream>>>(dXr, bits, scale, C, S, dX);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+
+int k_attn_rows_fwd(rau_ctx* ctx, int B, int M, int S, const float* logit, const float* mem, const bf16* I_hi, const bf16* I_lo,
+                    float* p, float* a) {
+  RAU_REQUIRE(M % 256 == 0 && S <= 256, "k_attn_rows_fwd: M=%d S=%d", M, S);
+  attn_rows_fwd_kernel<<<dim3(B, M / 256), 128, 0, ctx->stream>>>(S, M, logit, mem, I_hi, I_lo, p, a);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+
+int k_attn_rows_bwd(rau_ctx* ctx, int B, int M, int A, int S, const float* E, const bf16* I_hi, const bf16* I_lo, const float* ws,
+                    const float* p, const float* dp_in, const float* da, float* ds, bf16* dZ_hi, bf16* dZ_lo, float* dqa,
+                    float* gws_part) {
+  RAU_REQUIRE(M % 2 == 0 && S <= 256, "k_attn_rows_bwd: M=%d S=%d", M, S);
+  attn_rows_bwd_kernel<<<B, 256, (256 + M) * sizeof(float), ctx->stream>>>(S, M, A, E, I_hi, I_lo, ws, p, dp_in, da, ds, dZ_hi,
+                                                                            dZ_lo, dqa, gws_part);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}

@@ -3,6 +3,7 @@
 // LSTM cells of model/ATTLSTM.lua and model/DeepLSTM.lua.  The math is SURVEY.md Appendix A; every
 // contraction goes through rau_contract() so that the precision mode picks the engine.
 #include "rau_model.cuh"
+#include "rau_rows.cuh"
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -39,9 +40,33 @@ size_t hop_saved_layout(const rau_config* cfg, int B, void* base, HopSaved* sv) 
 
 static inline float drop_scale(float p) { return p > 0.0f ? 1.0f / (1.0f - p) : 1.0f; }
 
+// the rows-layout tcgen05 engine (k_rows_tc.cu) takes the heavy image-side products when the shapes fit its tiles
+static inline bool rows_path(const rau_ctx* ctx, const rau_config* cfg) {
+  return ctx->precision != RAU_PREC_F32 && rows_path_enabled() && cfg->C % 64 == 0 && cfg->M % 256 == 0 && cfg->A % 64 == 0 &&
+         cfg->A <= 256 && cfg->S % 4 == 0 && cfg->S <= 256;
+}
+
 #define ARENA(ptr, type, name, count) \
   type* ptr = nullptr;                \
   RAU_TRY(ctx->arena.get(name, sizeof(type) * (size_t)(count), (void**)&ptr))
+
+// split-K weight gradient on the rows engine: dst[M, ldd] += A^T B through TMA reduce-add (needs a 16-byte aligned
+// destination; a misaligned slice of the flat gradient goes through an aligned scratch)
+static int rows_wgrad(rau_ctx* ctx, RowsGemm g, float* dst, int ldd) {
+  g.epi = ROWS_EPI_RED;
+  if ((((uintptr_t)dst) & 15) == 0 && ldd % 4 == 0) {
+    g.out_f = dst; g.ldo = ldd;
+    return rows_gemm(ctx, g);
+  }
+  const int ldt = (g.N + 3) / 4 * 4;
+  float* tmp = nullptr;
+  RAU_TRY(ctx->arena.get("rows.wgrad.tmp", sizeof(float) * (size_t)g.M * ldt, (void**)&tmp));
+  RAU_CHECK_CUDA(cudaMemsetAsync(tmp, 0, sizeof(float) * (size_t)g.M * ldt, ctx->stream));
+  g.out_f = tmp; g.ldo = ldt;
+  RAU_TRY(rows_gemm(ctx, g));
+  for (int m = 0; m < g.M; ++m) RAU_TRY(k_axpy(ctx, 1.0f, tmp + (size_t)m * ldt, g.N, dst + (size_t)m * ldd));
+  return RAU_OK;
+}
 
 int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const float*>& P,
                 const float* q, const float* X, const float* c, const float* h, int train, const HopSaved& sv,
@@ -69,6 +94,44 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
     g.bias_n = P.bq; g.bias_n2 = P.bh; g.act = 1;
     RAU_TRY(rau_contract(ctx, g));
   }
+  if (rows_path(ctx, cfg)) {
+    // rows layout (k_rows_tc.cu): r = b*S + s.  sv.Xd_* = drop(X)^T [R,C], sv.I_* = I [R,M], sv.E = E [R,A] (fp32)
+    const int R = B * S;
+    const bf16 *Wi_h, *Wi_l, *Wa_h, *Wa_l;
+    RAU_TRY(rows_pack(ctx, P.Wi, (int64_t)M * C, x3, true, nullptr, &Wi_h, &Wi_l));
+    RAU_TRY(rows_pack(ctx, P.Wa, (int64_t)A * M, x3, true, nullptr, &Wa_h, &Wa_l));
+    ARENA(slog, float, "hop.slog", R);
+    RAU_TRY(k_xprep_rows(ctx, X, B, C, S, xb, drop_scale(cfg->p_x), sv.Xd_hi, x3 ? sv.Xd_lo : nullptr));
+    {   // i_embed (F:238-242): I = tanh(drop(X)^T Wi^T + bi)
+      RowsGemm g;
+      g.M = R; g.N = M; g.K = C;
+      g.A.hi = sv.Xd_hi; g.A.lo = x3 ? sv.Xd_lo : nullptr; g.A.ld = C;
+      g.B.hi = Wi_h; g.B.lo = Wi_l; g.B.ld = C;
+      g.epi = ROWS_EPI_TANH; g.bias = P.bi;
+      g.out_hi = sv.I_hi; g.out_lo = x3 ? sv.I_lo : nullptr; g.ldo = M;
+      RAU_TRY(rows_gemm(ctx, g));
+    }
+    {
+      SimtGemm g = lin_fwd(B, A, M, sv.qf, M, P.Wqa, qatt, A);
+      g.bias_n = P.bqa;
+      RAU_TRY(rau_contract(ctx, g));
+    }
+    {
+      SimtGemm g = lin_fwd(B, S, H, h, H, P.Wm, mem, S);
+      g.bias_n = P.bm;
+      RAU_TRY(rau_contract(ctx, g));
+    }
+    {   // attbycontent (F:244-252): E = tanh(I Wa^T + ba + qatt[b]) ; logit = ws.E (bs shifts every logit alike)
+      RowsGemm g;
+      g.M = R; g.N = A; g.K = M;
+      g.A.hi = sv.I_hi; g.A.lo = x3 ? sv.I_lo : nullptr; g.A.ld = M;
+      g.B.hi = Wa_h; g.B.lo = Wa_l; g.B.ld = M;
+      g.epi = ROWS_EPI_ATT; g.bias = P.ba; g.rowvec = qatt; g.colw = P.ws; g.rowout = slog; g.S = S;
+      g.out_f = sv.E; g.ldo = A;
+      RAU_TRY(rows_gemm(ctx, g));
+    }
+    RAU_TRY(k_attn_rows_fwd(ctx, B, M, S, slog, mem, sv.I_hi, x3 ? sv.I_lo : nullptr, sv.p, a));
+  } else {
   // i_embed (F:238-242): I[b] = tanh(Wi drop(X[b]) + bi), 1x1 convolution = per-image [M,C]x[C,S] product
   if (tc) RAU_TRY(k_dropout_pack(ctx, X, (int64_t)B * C, S, xb, drop_scale(cfg->p_x), sv.Xd_hi, x3 ? sv.Xd_lo : nullptr, Sp));
   else RAU_TRY(k_dropout(ctx, X, (int64_t)B * C, S, S, xb, drop_scale(cfg->p_x), Xd, Sp, nullptr, 0, Sp));
@@ -106,6 +169,7 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
     RAU_TRY(rau_contract(ctx, g));
   }
   RAU_TRY(k_attn_fwd<float>(ctx, B, M, A, S, Sp, sv.E, sv.I, P.ws, mem, sv.p, nullptr, 0, a, nullptr));
+  }
   if (p_out && p_out != sv.p)
     RAU_CHECK_CUDA(cudaMemcpyAsync(p_out, sv.p, sizeof(float) * B * S, cudaMemcpyDeviceToDevice, ctx->stream));
   // classifier (F:265-283): j = qf + a + Wp p + bp
@@ -221,8 +285,13 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   RAU_TRY(rau_contract(ctx, lin_wgrad(B, M, S, dj, M, sv.p, S, G.Wp, 1.0f)));
   RAU_TRY(k_colsum(ctx, dj, B, M, M, G.bp, 1));
   // attselect + softmax + score conv + tanh of attbycontent, one CTA per image
-  RAU_TRY(k_attn_bwd<float>(ctx, B, M, A, S, Sp, sv.E, sv.I, P.ws, sv.p, dp, dj, ds, nullptr, 0, dZ, dqa, nullptr, gwsp,
-                            dZ_hi, dZ_lo));
+  const bool rows = rows_path(ctx, cfg);
+  const int R = B * S;
+  if (rows)
+    RAU_TRY(k_attn_rows_bwd(ctx, B, M, A, S, sv.E, sv.I_hi, x3 ? sv.I_lo : nullptr, P.ws, sv.p, dp, dj, ds, dZ_hi, dZ_lo, dqa, gwsp));
+  else
+    RAU_TRY(k_attn_bwd<float>(ctx, B, M, A, S, Sp, sv.E, sv.I, P.ws, sv.p, dp, dj, ds, nullptr, 0, dZ, dqa, nullptr, gwsp,
+                              dZ_hi, dZ_lo));
   {
     SimtGemm g = lin_dgrad(B, S, H, ds, S, P.Wm, dh, H);
     g.accumulate = 1;
@@ -232,6 +301,27 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   RAU_TRY(k_colsum(ctx, ds, B, S, S, G.bm, 1));
   RAU_TRY(k_colsum(ctx, gwsp, B, A, A, G.ws, 1));
   RAU_TRY(k_sum_all(ctx, ds, (int64_t)B * S, G.bs, 1));
+  if (rows) {
+    const bf16 *Wa_h, *Wa_l;
+    RAU_TRY(rows_pack(ctx, P.Wa, (int64_t)A * M, x3, true, nullptr, &Wa_h, &Wa_l));
+    {   // dY = (dZ Wa + da p^T) (1 - I^2) ; gbi += sum_r dY   (dI never leaves the accumulator)
+      RowsGemm g;
+      g.M = R; g.N = M; g.K = A;
+      g.A.hi = dZ_hi; g.A.lo = dZ_lo; g.A.ld = A;
+      g.B.hi = Wa_h; g.B.lo = Wa_l; g.B.mn = 1; g.B.ld = M;
+      g.epi = ROWS_EPI_DY; g.rowvec = dj; g.rowscale = sv.p; g.S = S;
+      g.aux_hi = sv.I_hi; g.aux_lo = x3 ? sv.I_lo : nullptr; g.ldaux = M; g.colsum = G.bi;
+      g.out_hi = dY_hi; g.out_lo = dY_lo; g.ldo = M;
+      RAU_TRY(rows_gemm(ctx, g));
+    }
+    {   // gWa += dZ^T I
+      RowsGemm g;
+      g.M = A; g.N = M; g.K = R;
+      g.A.hi = dZ_hi; g.A.lo = dZ_lo; g.A.mn = 1; g.A.ld = A;
+      g.B.hi = sv.I_hi; g.B.lo = x3 ? sv.I_lo : nullptr; g.B.mn = 1; g.B.ld = M;
+      RAU_TRY(rows_wgrad(ctx, g, G.Wa, M));
+    }
+  } else {
   // dI = Wa^T dZ (+ da p^T inside the pointwise) ; dY = dI (1 - I^2)
   {
     SimtGemm g;
@@ -256,6 +346,7 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
     if (tc) { g.A_hi = dZ_hi; g.A_lo = dZ_lo; g.B_hi = sv.I_hi; g.B_lo = sv.I_lo; }
     RAU_TRY(rau_contract(ctx, g));
   }
+  }
   RAU_TRY(k_colsum(ctx, dqa, B, A, A, G.ba, 1));   // gba = sum_b sum_s dZ = sum_b dqa
   // dqf = dj + Wqa^T dqa ; gWqa += dqa (x) qf
   {
@@ -265,6 +356,27 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   }
   RAU_TRY(rau_contract(ctx, lin_wgrad(B, A, M, dqa, A, sv.qf, M, G.Wqa, 1.0f)));
   RAU_TRY(k_colsum(ctx, dqa, B, A, A, G.bqa, 1));
+  if (rows) {
+    {   // gWi += dY^T drop(X)^T
+      RowsGemm g;
+      g.M = M; g.N = C; g.K = R;
+      g.A.hi = dY_hi; g.A.lo = dY_lo; g.A.mn = 1; g.A.ld = M;
+      g.B.hi = sv.Xd_hi; g.B.lo = x3 ? sv.Xd_lo : nullptr; g.B.mn = 1; g.B.ld = C;
+      RAU_TRY(rows_wgrad(ctx, g, G.Wi, C));
+    }
+    if (dX) {   // dX = (dY Wi)^T * mask / (1-p): only on request, the training step discards it (F:598)
+      const bf16 *Wi_h, *Wi_l;
+      RAU_TRY(rows_pack(ctx, P.Wi, (int64_t)M * C, x3, true, nullptr, &Wi_h, &Wi_l));
+      ARENA(dXr, float, "hopb.dXr", (size_t)R * C);
+      RowsGemm g;
+      g.M = R; g.N = C; g.K = M;
+      g.A.hi = dY_hi; g.A.lo = dY_lo; g.A.ld = M;
+      g.B.hi = Wi_h; g.B.lo = Wi_l; g.B.mn = 1; g.B.ld = C;
+      g.epi = ROWS_EPI_PLAIN; g.out_f = dXr; g.ldo = C;
+      RAU_TRY(rows_gemm(ctx, g));
+      RAU_TRY(k_unprep_rows(ctx, dXr, B, C, S, xb, drop_scale(cfg->p_x), dX));
+    }
+  } else {
   // i_embed: gWi += sum_b dY[b] drop(X[b])^T ; gbi += sum dY ; dX only on request (the caller discards it, F:598)
   if (!tc) RAU_TRY(k_dropout(ctx, X, (int64_t)B * C, S, S, xb, drop_scale(cfg->p_x), Xd, Sp, nullptr, 0, Sp));
   {
@@ -288,6 +400,7 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
     if (tc) { g.B_hi = dY_hi; g.B_lo = dY_lo; }
     RAU_TRY(rau_contract(ctx, g));
     RAU_TRY(k_dropout(ctx, Xd, (int64_t)B * C, S, Sp, xb, drop_scale(cfg->p_x), dX, S, nullptr, 0, S));
+  }
   }
   // q_embed backward
   RAU_TRY(k_tanh_bwd(ctx, dqf, sv.qf, (int64_t)B * M, dpre, nullptr));
@@ -503,6 +616,25 @@ int rau_gemm(rau_ctx* ctx, int M, int N, int K, const float* A, int lda, int ta,
   g.C = C; g.scm = ldc; g.scn = 1;
   g.accumulate = accumulate;
   return rau_contract(ctx, g);
+}
+
+int rau_rows_gemm(rau_ctx* ctx, int M, int N, int K, const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn,
+                  float* D, int ldd, int reduce) {
+  RAU_REQUIRE(ctx, "ctx == NULL");
+  RAU_REQUIRE(ctx->precision != RAU_PREC_F32, "rau_rows_gemm: the rows engine is the tcgen05 path (bf16 / bf16x3 modes)");
+  RAU_REQUIRE(M > 0 && N > 0 && K > 0, "bad gemm shape %dx%dx%d", M, N, K);
+  RAU_TRY(rau_check_dev(A, "A")); RAU_TRY(rau_check_dev(B, "B")); RAU_TRY(rau_check_dev(D, "D"));
+  RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  ctx->epoch++;
+  const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+  RowsGemm g;
+  g.M = M; g.N = N; g.K = K;
+  RAU_TRY(rows_pack(ctx, A, (int64_t)(a_mn ? K : M) * lda, x3, false, "test.A", &g.A.hi, &g.A.lo));
+  RAU_TRY(rows_pack(ctx, B, (int64_t)(b_mn ? K : N) * ldb, x3, false, "test.B", &g.B.hi, &g.B.lo));
+  g.A.mn = a_mn; g.A.ld = lda; g.B.mn = b_mn; g.B.ld = ldb;
+  g.epi = reduce ? ROWS_EPI_RED : ROWS_EPI_PLAIN;
+  g.out_f = D; g.ldo = ldd;
+  return rows_gemm(ctx, g);
 }
 
 int rau_softmax_ce(rau_ctx* ctx, int B, int N, const float* score, const float* labels, float scale, float* loss_sum,

@@ -1,0 +1,38 @@
+// rau_rows.cuh -- host interface of the rows-layout tcgen05 engine (k_rows_tc.cu).
+#pragma once
+#include "rau_common.cuh"
+
+enum { ROWS_EPI_PLAIN = 0, ROWS_EPI_RED = 1, ROWS_EPI_TANH = 2, ROWS_EPI_ATT = 3, ROWS_EPI_DY = 4 };
+
+// one operand: bf16 hi (and lo in bf16x3 mode); mn = 0: stored [rows, ld >= K] (K-major); mn = 1: stored [K, ld >= rows]
+struct RowsOperand { const bf16* hi = nullptr; const bf16* lo = nullptr; int mn = 0; int64_t ld = 0; };
+
+struct RowsGemm {
+  int M = 0, N = 0, K = 0;          // D[M,N] = sum_k A[m,k] B[n,k]
+  RowsOperand A, B;
+  int epi = ROWS_EPI_PLAIN;
+  bf16 *out_hi = nullptr, *out_lo = nullptr;   // EPI_TANH / EPI_DY
+  float* out_f = nullptr;                      // EPI_PLAIN / EPI_RED / EPI_ATT
+  int64_t ldo = 0;
+  const float* bias = nullptr;      // [N]
+  const float* rowvec = nullptr;    // [rows / S, N]
+  const float* colw = nullptr;      // [N]
+  float* rowout = nullptr;          // [M]
+  const float* rowscale = nullptr;  // [M]
+  const bf16 *aux_hi = nullptr, *aux_lo = nullptr; int64_t ldaux = 0;
+  float* colsum = nullptr;          // [N]
+  int S = 0;                        // rows per image
+  float alpha = 1.0f;
+};
+
+bool rows_path_enabled();
+int rows_gemm(rau_ctx* ctx, const RowsGemm& g);
+// fp32 -> bf16 (hi [, lo]) copy of n contiguous elements in an arena buffer; cache: parameter tensor, packed once per epoch
+int rows_pack(rau_ctx* ctx, const float* W, int64_t n, bool want_lo, bool cache, const char* slot, const bf16** hi, const bf16** lo);
+int k_xprep_rows(rau_ctx* ctx, const float* X, int B, int C, int S, const uint32_t* bits, float scale, bf16* hi, bf16* lo);
+int k_unprep_rows(rau_ctx* ctx, const float* dXr, int B, int C, int S, const uint32_t* bits, float scale, float* dX);
+int k_attn_rows_fwd(rau_ctx* ctx, int B, int M, int S, const float* logit, const float* mem, const bf16* I_hi, const bf16* I_lo,
+                    float* p, float* a);
+int k_attn_rows_bwd(rau_ctx* ctx, int B, int M, int A, int S, const float* E, const bf16* I_hi, const bf16* I_lo, const float* ws,
+                    const float* p, const float* dp_in, const float* da, float* ds, bf16* dZ_hi, bf16* dZ_lo, float* dqa,
+                    float* gws_part);
