@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
         if (two) stage_row(stg1, lane, w1);
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && rowbase < p.M) {
           const void* s0p = staging + (size_t)(warp - 2) * RT_STG_WARP;
           const void* s1p = (const uint8_t*)s0p + 4096;
           if (EPI == EPI_RED) {
@@ -489,7 +489,8 @@ bool g_attr_done[8] = {false, false, false, false, false, false, false, false};
 template <int EPI>
 int launch_rows(rau_ctx* ctx, const RtParams& p, int grid, int smem_bytes) {
   if (!g_attr_done[EPI]) {
-    RAU_CHECK_CUDA(cudaFuncSetAttribute(rows_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RAU_CHECK_CUDA(cudaFuncSetAttribute(rows_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        RT_MAXSTAGES * RT_STAGE + 4 * RT_STG_WARP + 1024));
     g_attr_done[EPI] = true;
   }
   rows_gemm_kernel<EPI><<<grid, RT_THREADS, smem_bytes, ctx->stream>>>(p);
