@@ -11,8 +11,9 @@
 //   warp 1      MMA issuer: tcgen05.mma kind::f16, M = 128, N = 256, fp32 accumulators in TMEM; bf16x3 issues
 //               hi*hi + hi*lo + lo*hi into the same accumulator.  Two 256-column accumulators alternate between items,
 //               so the epilogue of item i overlaps the MMAs of item i+1.
-//   warps 2..5  epilogue: tcgen05.ld (one TMEM lane = one row per thread) -> fused math -> 128B-swizzled staging in
-//               shared memory -> TMA store (bf16 hi/lo or fp32) or TMA reduce-add (split-K weight gradients).
+//   warps 2..9  epilogue: tcgen05.ld (one TMEM lane = one row per thread, 32 columns at a time; the two warps of a lane
+//               quarter split the 256 columns) -> fused math -> swizzled staging in shared memory -> TMA store (bf16
+//               hi/lo or fp32) or TMA reduce-add (split-K weight gradients).
 // Epilogues (template parameter):
 //   EPI_PLAIN  D (tests, dX)                                   EPI_RED   D added into fp32 global (split-K wgrad)
 //   EPI_TANH   tanh(D + bias[n]) -> bf16 hi/lo                 (i_embed F:240-241)
@@ -26,8 +27,8 @@ namespace {
 
 constexpr int RT_BM = 128, RT_BN = 256;
 constexpr int RT_STAGE = 48 * 1024;
-constexpr int RT_THREADS = 192;
-constexpr int RT_STG_WARP = 8192;          // per epilogue warp: two 32-row x 128-byte swizzled staging buffers
+constexpr int RT_THREADS = 320;          // producer + MMA issuer + 8 epilogue warps
+constexpr int RT_STG_WARP = 4096;          // per epilogue warp: one 32 x 128 B (fp32) or two 32 x 64 B (bf16 hi, lo) buffers
 constexpr int RT_MAXSTAGES = 4;
 
 enum { EPI_PLAIN = 0, EPI_RED = 1, EPI_TANH = 2, EPI_ATT = 3, EPI_DY = 4 };
@@ -122,14 +123,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
 }
 
-// tanh to ~2e-7 absolute (bf16x3 mode): odd polynomial near zero, 1 - 2/(e^2x + 1) elsewhere
+__device__ __forceinline__ float exp2f_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// tanh to ~1e-7 ABSOLUTE (bf16x3 mode): 1 - 2/(e^2|x| + 1).  Near zero the relative error grows, which is harmless here:
+// the result feeds contractions and (1 - y^2), both of which see the absolute error only.
 __device__ __forceinline__ float tanh_acc(float x) {
-  const float ax = fabsf(x);
-  const float x2 = x * x;
-  const float pol = x * (1.0f + x2 * (-0.33333334f + x2 * (0.13333334f + x2 * (-0.05396825f + x2 * 0.02186949f))));
-  const float e = __expf(2.0f * ax);
-  const float t = copysignf(1.0f - __fdividef(2.0f, e + 1.0f), x);
-  return ax < 0.15f ? pol : t;
+  const float e = exp2f_ftz(2.8853900817779268f * fabsf(x));
+  const float t = 1.0f - 2.0f * rcp_ftz(e + 1.0f);
+  return copysignf(t, x);
 }
 __device__ __forceinline__ float tanh_hw(float x) {
   float y;
@@ -159,11 +168,22 @@ __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u <<
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
 // write 32 consecutive 32-bit words of this lane's row into a 32-row x 128-byte SWIZZLE_128B staging buffer
-__device__ __forceinline__ void stage_row(uint32_t buf, int lane, const uint32_t* w) {
+__device__ __forceinline__ void stage_row128(uint32_t buf, int lane, const uint32_t* w) {
   const uint32_t base = buf + (uint32_t)lane * 128u;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const uint32_t a = base + (uint32_t)((j ^ (lane & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[4 * j]), "r"(w[4 * j + 1]), "r"(w[4 * j + 2]),
+                 "r"(w[4 * j + 3])
+                 : "memory");
+  }
+}
+// write 16 consecutive 32-bit words (32 bf16) of this lane's row into a 32-row x 64-byte SWIZZLE_64B staging buffer
+__device__ __forceinline__ void stage_row64(uint32_t buf, int lane, const uint32_t* w) {
+  const uint32_t base = buf + (uint32_t)lane * 64u;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t a = base + (uint32_t)((j ^ ((lane >> 1) & 3)) << 4);
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[4 * j]), "r"(w[4 * j + 1]), "r"(w[4 * j + 2]),
                  "r"(w[4 * j + 3])
                  : "memory");
@@ -197,7 +217,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
@@ -301,9 +321,11 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
       }
     }
   } else {
-    // ===================== epilogue warps: TMEM lanes 32*(warp%4) .. +31
-    const int q = warp & 3;
-    const uint32_t stg0 = smem_u32(staging + (size_t)(warp - 2) * RT_STG_WARP), stg1 = stg0 + 4096u;
+    // ===================== epilogue warps 2..9: TMEM lanes 32*(warp%4) .. +31; the two warps of a lane quarter split
+    // the 256 accumulator columns in halves and walk them in 32-column chunks
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    uint8_t* stg_p = staging + (size_t)(warp - 2) * RT_STG_WARP;
+    const uint32_t stg0 = smem_u32(stg_p), stg1 = stg0 + 2048u;
     uint32_t li = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
       const int tile = item / p.ksplit;
@@ -322,54 +344,71 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
       float rs = 0.0f;
       if (EPI == EPI_ATT || EPI == EPI_DY) rv = p.rowvec + (long long)(rr / p.S) * p.N;
       if (EPI == EPI_DY) rs = p.rowscale[rr];
+      const int c_lo = half * (RT_BN / 64), c_hi = c_lo + RT_BN / 64;
+      bool released = false;
 #pragma unroll 1
-      for (int c = 0; c < RT_BN / 64; ++c) {
-        const int nc = n0 + c * 64;
+      for (int c = c_lo; c < c_hi; ++c) {
+        const int nc = n0 + c * 32;
         if (nc >= p.N) break;
-        float v[64];
-        tmem_ld32(taddr + (uint32_t)(c * 64), v);
-        tmem_ld32(taddr + (uint32_t)(c * 64 + 32), v + 32);
-        if (c == RT_BN / 64 - 1 || nc + 64 >= p.N) {   // last read of this accumulator: hand it back to the MMA warp
+        float v[32];
+        tmem_ld32(taddr + (uint32_t)(c * 32), v);
+        if (c == c_hi - 1 || nc + 32 >= p.N) {   // last read of this accumulator: hand it back to the MMA warp
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[ab]);
+          released = true;
         }
-        uint32_t w0[32], w1[32];
+        uint32_t w0[32];     // fp32 outputs: 32 words; bf16 outputs: w0[0..15] = hi pairs, w0[16..31] = lo pairs
         if (EPI == EPI_PLAIN || EPI == EPI_RED) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) { w0[k] = __float_as_uint(v[k] * p.alpha); w1[k] = __float_as_uint(v[k + 32] * p.alpha); }
+          for (int k = 0; k < 32; ++k) w0[k] = __float_as_uint(v[k] * p.alpha);
         } else if (EPI == EPI_TANH) {
 #pragma unroll
-          for (int k4 = 0; k4 < 16; ++k4) {
+          for (int k4 = 0; k4 < 8; ++k4) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nc) + k4);
             v[4 * k4] += b4.x; v[4 * k4 + 1] += b4.y; v[4 * k4 + 2] += b4.z; v[4 * k4 + 3] += b4.w;
           }
+          if (p.fast_tanh) {
 #pragma unroll
-          for (int k = 0; k < 64; ++k) v[k] = p.fast_tanh ? tanh_hw(v[k]) : tanh_acc(v[k]);
+            for (int k = 0; k < 32; ++k) v[k] = tanh_hw(v[k]);
+          } else {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            if (p.out_lo) split_pair(v[2 * k], v[2 * k + 1], w0[k], w1[k]);
-            else w0[k] = pack_bf16x2(v[2 * k], v[2 * k + 1]);
+            for (int k = 0; k < 32; ++k) v[k] = tanh_acc(v[k]);
+          }
+          if (p.out_lo) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) split_pair(v[2 * k], v[2 * k + 1], w0[k], w0[16 + k]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) w0[k] = pack_bf16x2(v[2 * k], v[2 * k + 1]);
           }
         } else if (EPI == EPI_ATT) {
 #pragma unroll
-          for (int k4 = 0; k4 < 16; ++k4) {
+          for (int k4 = 0; k4 < 8; ++k4) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nc) + k4);
             const float4 q4 = __ldg(reinterpret_cast<const float4*>(rv + nc) + k4);
-            const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.colw + nc) + k4);
-            float e;
-            e = v[4 * k4] + b4.x + q4.x;     e = p.fast_tanh ? tanh_hw(e) : tanh_acc(e); v[4 * k4] = e;     rowacc = fmaf(c4.x, e, rowacc);
-            e = v[4 * k4 + 1] + b4.y + q4.y; e = p.fast_tanh ? tanh_hw(e) : tanh_acc(e); v[4 * k4 + 1] = e; rowacc = fmaf(c4.y, e, rowacc);
-            e = v[4 * k4 + 2] + b4.z + q4.z; e = p.fast_tanh ? tanh_hw(e) : tanh_acc(e); v[4 * k4 + 2] = e; rowacc = fmaf(c4.z, e, rowacc);
-            e = v[4 * k4 + 3] + b4.w + q4.w; e = p.fast_tanh ? tanh_hw(e) : tanh_acc(e); v[4 * k4 + 3] = e; rowacc = fmaf(c4.w, e, rowacc);
+            v[4 * k4] += b4.x + q4.x; v[4 * k4 + 1] += b4.y + q4.y; v[4 * k4 + 2] += b4.z + q4.z; v[4 * k4 + 3] += b4.w + q4.w;
+          }
+          if (p.fast_tanh) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = tanh_hw(v[k]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = tanh_acc(v[k]);
           }
 #pragma unroll
-          for (int k = 0; k < 32; ++k) { w0[k] = __float_as_uint(v[k]); w1[k] = __float_as_uint(v[k + 32]); }
+          for (int k4 = 0; k4 < 8; ++k4) {
+            const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.colw + nc) + k4);
+            rowacc = fmaf(c4.x, v[4 * k4], rowacc); rowacc = fmaf(c4.y, v[4 * k4 + 1], rowacc);
+            rowacc = fmaf(c4.z, v[4 * k4 + 2], rowacc); rowacc = fmaf(c4.w, v[4 * k4 + 3], rowacc);
+          }
+#pragma unroll
+          for (int k = 0; k < 32; ++k) w0[k] = __float_as_uint(v[k]);
         } else {   // EPI_DY
           const uint4* ih = reinterpret_cast<const uint4*>(p.aux_hi + (long long)rr * p.ldaux + nc);
           const uint4* il = p.aux_lo ? reinterpret_cast<const uint4*>(p.aux_lo + (long long)rr * p.ldaux + nc) : nullptr;
 #pragma unroll
-          for (int k8 = 0; k8 < 8; ++k8) {
+          for (int k8 = 0; k8 < 4; ++k8) {
             const uint4 h = __ldg(ih + k8);
             uint4 l = make_uint4(0u, 0u, 0u, 0u);
             if (il) l = __ldg(il + k8);
@@ -387,43 +426,48 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
               v[k + 1] = r_ok ? g1 : 0.0f;
             }
           }
+          if (p.out_lo) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            if (p.out_lo) split_pair(v[2 * k], v[2 * k + 1], w0[k], w1[k]);
-            else w0[k] = pack_bf16x2(v[2 * k], v[2 * k + 1]);
+            for (int k = 0; k < 16; ++k) split_pair(v[2 * k], v[2 * k + 1], w0[k], w0[16 + k]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) w0[k] = pack_bf16x2(v[2 * k], v[2 * k + 1]);
           }
           if (p.colsum) {
             const float s0 = warp_transpose_sum32(v, lane);
-            const float s1 = warp_transpose_sum32(v + 32, lane);
             if (nc + lane < p.N) atomicAdd(p.colsum + nc + lane, s0);
-            if (nc + 32 + lane < p.N) atomicAdd(p.colsum + nc + 32 + lane, s1);
           }
         }
-        // staging buffers are free once the previous chunk's bulk stores have read them
+        // the staging buffer is free once the previous chunk's bulk stores have read it
         if (lane == 0) bulk_wait_read0();
         __syncwarp();
-        const bool two = (EPI == EPI_PLAIN || EPI == EPI_RED || EPI == EPI_ATT) || p.out_lo;
-        stage_row(stg0, lane, w0);
-        if (two) stage_row(stg1, lane, w1);
+        const bool f32_out = (EPI == EPI_PLAIN || EPI == EPI_RED || EPI == EPI_ATT);
+        if (f32_out) {
+          stage_row128(stg0, lane, w0);
+        } else {
+          stage_row64(stg0, lane, w0);
+          if (p.out_lo) stage_row64(stg1, lane, w0 + 16);
+        }
         fence_async_smem();
         __syncwarp();
         if (lane == 0 && rowbase < p.M) {
-          const void* s0p = staging + (size_t)(warp - 2) * RT_STG_WARP;
-          const void* s1p = (const uint8_t*)s0p + 4096;
           if (EPI == EPI_RED) {
-            tma_reduce_add_2d(&p.mapO[0], s0p, nc, rowbase);
-            if (nc + 32 < p.N) tma_reduce_add_2d(&p.mapO[0], s1p, nc + 32, rowbase);
-          } else if (EPI == EPI_PLAIN || EPI == EPI_ATT) {
-            tma_store_2d(&p.mapO[0], s0p, nc, rowbase);
-            if (nc + 32 < p.N) tma_store_2d(&p.mapO[0], s1p, nc + 32, rowbase);
+            tma_reduce_add_2d(&p.mapO[0], stg_p, nc, rowbase);
+          } else if (f32_out) {
+            tma_store_2d(&p.mapO[0], stg_p, nc, rowbase);
           } else {
-            tma_store_2d(&p.mapO[0], s0p, nc, rowbase);
-            if (p.out_lo) tma_store_2d(&p.mapO[1], s1p, nc, rowbase);
+            tma_store_2d(&p.mapO[0], stg_p, nc, rowbase);
+            if (p.out_lo) tma_store_2d(&p.mapO[1], stg_p + 2048, nc, rowbase);
           }
           bulk_commit();
         }
       }
-      if (EPI == EPI_ATT && r_ok && p.rowout) p.rowout[r] = rowacc;
+      if (!released) {   // this half had no columns inside N: still hand the accumulator back
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[ab]);
+      }
+      if (EPI == EPI_ATT && r_ok && p.rowout && n0 + c_lo * 32 < p.N) atomicAdd(p.rowout + r, rowacc);
     }
     if (lane == 0) bulk_wait0();
   }
@@ -490,7 +534,7 @@ template <int EPI>
 int launch_rows(rau_ctx* ctx, const RtParams& p, int grid, int smem_bytes) {
   if (!g_attr_done[EPI]) {
     RAU_CHECK_CUDA(cudaFuncSetAttribute(rows_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        RT_MAXSTAGES * RT_STAGE + 4 * RT_STG_WARP + 1024));
+                                        RT_MAXSTAGES * RT_STAGE + 8 * RT_STG_WARP + 1024));
     g_attr_done[EPI] = true;
   }
   rows_gemm_kernel<EPI><<<grid, RT_THREADS, smem_bytes, ctx->stream>>>(p);
@@ -731,15 +775,15 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   } else {
     RAU_REQUIRE(g.out_hi && g.ldo % 8 == 0 && (((uintptr_t)g.out_hi | (uintptr_t)g.out_lo) & 15) == 0,
                 "rows_gemm: bf16 output must be 16-byte aligned");
-    RAU_TRY(encode_2d(&p.mapO[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.out_hi, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldo, 64, 32,
-                      CU_TENSOR_MAP_SWIZZLE_128B));
+    RAU_TRY(encode_2d(&p.mapO[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.out_hi, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldo, 32, 32,
+                      CU_TENSOR_MAP_SWIZZLE_64B));
     if (g.out_lo)
-      RAU_TRY(encode_2d(&p.mapO[1], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.out_lo, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldo, 64, 32,
-                        CU_TENSOR_MAP_SWIZZLE_128B));
+      RAU_TRY(encode_2d(&p.mapO[1], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.out_lo, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldo, 32, 32,
+                        CU_TENSOR_MAP_SWIZZLE_64B));
     p.out_lo = g.out_lo ? 1 : 0;
   }
   if (g.epi == EPI_TANH || g.epi == EPI_ATT || g.epi == EPI_DY)
-    RAU_REQUIRE(g.N % 64 == 0, "rows_gemm: fused epilogues need N %% 64 == 0 (N = %d)", g.N);
+    RAU_REQUIRE(g.N % 32 == 0, "rows_gemm: fused epilogues need N %% 32 == 0 (N = %d)", g.N);
   if (g.epi == EPI_ATT) RAU_REQUIRE(g.N <= RT_BN && g.S > 0 && g.rowvec && g.colw && g.bias, "rows_gemm: bad EPI_ATT arguments");
   if (g.epi == EPI_DY) RAU_REQUIRE(g.S > 0 && g.rowvec && g.rowscale && g.aux_hi && g.ldaux % 8 == 0, "rows_gemm: bad EPI_DY arguments");
   if (g.epi == EPI_TANH) RAU_REQUIRE(g.bias != nullptr, "rows_gemm: EPI_TANH needs a bias");
@@ -749,7 +793,7 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   p.fast_tanh = p.x3 ? 0 : 1;   // single-pass bf16: the result is rounded to bf16 anyway, MUFU.TANH (2^-11) is below that
   const int items = tiles * p.ksplit;
   const int grid = items < ctx->sm_count ? items : ctx->sm_count;
-  const int smem_bytes = p.stages * RT_STAGE + 4 * RT_STG_WARP + 1024;
+  const int smem_bytes = p.stages * RT_STAGE + 8 * RT_STG_WARP + 1024;
   switch (g.epi) {
     case EPI_PLAIN: return launch_rows<EPI_PLAIN>(ctx, p, grid, smem_bytes);
     case EPI_RED: return launch_rows<EPI_RED>(ctx, p, grid, smem_bytes);

@@ -127,6 +127,7 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
       g.A.hi = sv.I_hi; g.A.lo = x3 ? sv.I_lo : nullptr; g.A.ld = M;
       g.B.hi = Wa_h; g.B.lo = Wa_l; g.B.ld = M;
       g.epi = ROWS_EPI_ATT; g.bias = P.ba; g.rowvec = qatt; g.colw = P.ws; g.rowout = slog; g.S = S;
+      RAU_CHECK_CUDA(cudaMemsetAsync(slog, 0, sizeof(float) * (size_t)R, ctx->stream));   // two column halves add into it
       g.out_f = sv.E; g.ldo = A;
       RAU_TRY(rows_gemm(ctx, g));
     }

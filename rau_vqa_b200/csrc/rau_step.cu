@@ -9,6 +9,7 @@
 // per-row "select the state at t == len" host loops (F:472-478, F:604-610) are device kernels, the encoder's
 // weight gradients are single contractions over all T*B rows, and dX of the image features is never formed.
 #include "rau_model.cuh"
+#include "rau_rows.cuh"
 #include <math.h>
 
 int rau_check_cfg(const rau_config* cfg);
@@ -499,10 +500,36 @@ int rau_time_iembed(rau_ctx* ctx, const rau_config* cfg, int B, const float* mul
   RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
   ctx->epoch++;
   const int Sp = rau_sp(cfg->S), M = cfg->M, C = cfg->C, S = cfg->S;
-  ARENA(I, float, "time.I", (size_t)B * M * Sp);
   MultT<const float*> P = mult_views<const float*, const float>(cfg, mult_params);
   const bool tc = ctx->precision != RAU_PREC_F32 && S % 4 == 0;
   const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+  if (tc && rows_path_enabled() && C % 64 == 0 && M % 64 == 0) {
+    // the training launch of the rows engine: packed dropped-out features in, tanh epilogue, packed (hi, lo) I out
+    const int R = B * S;
+    ARENA(Xh, bf16, "time.Xh", (size_t)R * C);
+    ARENA(Xl, bf16, "time.Xl", (size_t)R * C);
+    ARENA(Ih, bf16, "time.Ih", (size_t)R * M);
+    ARENA(Il, bf16, "time.Il", (size_t)R * M);
+    const bf16 *Wi_h, *Wi_l;
+    RAU_TRY(rows_pack(ctx, P.Wi, (int64_t)M * C, x3, true, nullptr, &Wi_h, &Wi_l));
+    RAU_TRY(k_xprep_rows(ctx, X, B, C, S, nullptr, 1.0f, Xh, x3 ? Xl : nullptr));
+    RowsGemm rg;
+    rg.M = R; rg.N = M; rg.K = C;
+    rg.A.hi = Xh; rg.A.lo = x3 ? Xl : nullptr; rg.A.ld = C;
+    rg.B.hi = Wi_h; rg.B.lo = Wi_l; rg.B.ld = C;
+    rg.epi = ROWS_EPI_TANH; rg.bias = P.bi;
+    rg.out_hi = Ih; rg.out_lo = x3 ? Il : nullptr; rg.ldo = M;
+    RAU_TRY(rows_gemm(ctx, rg));   // warm-up
+    RAU_CHECK_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int i = 0; i < iters; ++i) RAU_TRY(rows_gemm(ctx, rg));
+    RAU_CHECK_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    RAU_CHECK_CUDA(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.0f;
+    RAU_CHECK_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    *ms_per_launch = ms / iters;
+    return RAU_OK;
+  }
+  ARENA(I, float, "time.I", (size_t)B * M * Sp);
   SimtGemm g;
   g.M = M; g.N = Sp; g.K = C;
   g.A = P.Wi; g.sam = C; g.sak = 1; g.a_const = 1;
