@@ -234,3 +234,30 @@ def test_errors_are_reported_not_thrown(R, ctx):
     with pytest.raises(R.RauError):
         R.feval(ctx, bad, P, [p.clone() for p in P], dev(np.zeros((2, bad.C, bad.S))), dev(np.ones((bad.T, 2))),
                 dev(np.ones(2)), dev(np.ones(2)), out)
+
+
+def test_virtual_ranks_sum_equals_big_batch(R, ctx):
+    """SURVEY.md 8e on one GPU: rau_feval on each half of a batch with B_global = B, summed, equals rau_feval on the
+    whole batch (what the NCCL all-reduce of rau_train_step produces on two ranks)."""
+    from rau_vqa_b200 import parallel
+    cfg = small_cfg(nHop=2)
+    B, world = 6, 2
+    params = O.init_params(cfg, seed=41)
+    X, x, x_len, y = O.synth_batch(cfg, B, seed=42, min_len=1)
+    masks = O.synth_masks(cfg, B, seed=43)
+    full, out_full = run_lib_feval(ctx, cfg, params, X, x, x_len, y, masks=masks)
+    acc = {g: np.zeros_like(full[g]) for g in O.GROUPS}
+    loss = np.zeros(cfg.nHop + 2)
+    for r in range(world):
+        lo, hi = parallel.shard_rows(B, r, world)
+        Xs, xs, ls, ys = parallel.shard_batch(X, x, x_len, y, r, world)
+        ms = dict(embed=masks["embed"][:, lo:hi], rnn=masks["rnn"][:, lo:hi],
+                  hops=[{k: v[lo:hi] for k, v in h.items()} for h in masks["hops"]])
+        g, out = run_lib_feval(ctx, cfg, params, Xs, xs, ls, ys, masks=ms, B_global=B)
+        for k in O.GROUPS:
+            acc[k] += g[k]
+        loss += out.loss.cpu().numpy()
+    tol = tol_for(ctx)
+    for k in O.GROUPS:
+        assert rel_err(acc[k], full[k]) <= tol, k
+    np.testing.assert_allclose(loss[:cfg.nHop], out_full.loss.cpu().numpy()[:cfg.nHop], rtol=tol)
