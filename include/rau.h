@@ -99,7 +99,8 @@ int64_t rau_launch_count(rau_ctx* ctx);
 /* flat parameter layout (our own; nngraph's order is not recoverable):
  *   group 0 "embed": E[V,embed]
  *   group 1 "rnn"  : per layer L: Wi[4Hq,in] bi[4Hq] Wh[4Hq,Hq] bh[4Hq]
- *   group 2 "mult" : Wq bq Wh bh Wi bi Wqa bqa Wa ba ws bs Wm bm Wp bp Wx bx Whh bhh Wo bo Ws bso wd bd */
+ *   group 2 "mult" : Wq bq Wh bh Wi bi Wqa bqa Wa ba ws Wm bm Wp bp Wx bx Whh bhh Wo bo Ws bso wd bs bd
+ *                    (the two scalars last, so that every tensor starts 16-byte aligned when N % 4 == 0) */
 int64_t rau_group_size(const rau_config* cfg, int group);
 /* offset (in floats) of a named tensor inside its group, -1 if unknown; e.g. ("mult","Wi") */
 int64_t rau_param_offset(const rau_config* cfg, int group, const char* name);

@@ -21,8 +21,8 @@ Parameter naming (role -> reference constructor line):
   embed group : E[V,200]                                   F:204
   rnn group   : l{1,2}.Wi[4H,in] l.bi[4H] l.Wh[4H,H] l.bh   D:43-44   gate order (i,f,o,g)
   mult group  : Wq,bq F:233 | Wh,bh F:234 | Wi,bi F:240 | Wqa,bqa F:246 | Wa,ba F:247 |
-                ws,bs F:251 | Wm,bm F:287 | Wp,bp F:271 | Wx,bx A:6 | Whh,bhh A:7 |
-                Wo,bo F:279 | Ws,bso F:280 | wd,bd F:281   ATTLSTM gate order (i,g,f,o)
+                ws F:251 | Wm,bm F:287 | Wp,bp F:271 | Wx,bx A:6 | Whh,bhh A:7 |
+                Wo,bo F:279 | Ws,bso F:280 | wd F:281 | bs F:251 | bd F:281   ATTLSTM gate order (i,g,f,o)
 The flat order inside each group is the order listed above (our own layout; nngraph's
 traversal order is not recoverable from the reference).
 """
@@ -85,14 +85,15 @@ def mult_param_shapes(cfg: RauConfig):
         ("Wi", (cfg.M, cfg.C)), ("bi", (cfg.M,)),
         ("Wqa", (cfg.A, cfg.M)), ("bqa", (cfg.A,)),
         ("Wa", (cfg.A, cfg.M)), ("ba", (cfg.A,)),
-        ("ws", (1, cfg.A)), ("bs", (1,)),
+        ("ws", (1, cfg.A)),
         ("Wm", (cfg.S, cfg.H)), ("bm", (cfg.S,)),
         ("Wp", (cfg.M, cfg.S)), ("bp", (cfg.M,)),
         ("Wx", (4 * cfg.H, cfg.M)), ("bx", (4 * cfg.H,)),
         ("Whh", (4 * cfg.H, cfg.H)), ("bhh", (4 * cfg.H,)),
         ("Wo", (cfg.M, cfg.H)), ("bo", (cfg.M,)),
         ("Ws", (cfg.N, cfg.M)), ("bso", (cfg.N,)),
-        ("wd", (1, cfg.M)), ("bd", (1,)),
+        ("wd", (1, cfg.M)),
+        ("bs", (1,)), ("bd", (1,)),      # the two scalars last: everything above stays 16-byte aligned in the flat buffer
     ]
 
 

@@ -31,13 +31,22 @@ constexpr int RT_THREADS = 320;          // producer + MMA issuer + 8 epilogue w
 constexpr int RT_STG_WARP = 4096;          // per epilogue warp: one 32 x 128 B (fp32) or two 32 x 64 B (bf16 hi, lo) buffers
 constexpr int RT_MAXSTAGES = 4;
 
-enum { EPI_PLAIN = 0, EPI_RED = 1, EPI_TANH = 2, EPI_ATT = 3, EPI_DY = 4 };
+enum { EPI_PLAIN = 0, EPI_RED = 1, EPI_TANH = 2, EPI_ATT = 3, EPI_DY = 4, EPI_LINEAR = 5 };
 
 struct RtParams {
   CUtensorMap mapA[2], mapB[2];   // [hi, lo] operand tiles
-  CUtensorMap mapO[2];            // outputs: bf16 (hi, lo) or fp32 ([0])
+  CUtensorMap mapA2[2], mapB2[2]; // optional second K segment (x Wi^T + h Wh^T of an LSTM layer)
+  CUtensorMap mapO[3];            // outputs: bf16 (hi, lo) or fp32 ([0]); EPI_LINEAR: fp32 [0] + optional bf16 hi [1], lo [2]
   int M, N, K;
   int a_mn, b_mn, x3, BK, nkb;
+  int nkb1;                        // k-blocks of the first segment (== nkb without a second segment)
+  int BN;                          // accumulator columns per tile: 64, 128 or 256
+  int stg_warp;                    // staging bytes per epilogue warp
+  int out_f, out_hi;               // EPI_LINEAR: which outputs exist
+  const float* bias2;              // [N]
+  const float* addend; const float* addend2; long long ldadd;   // [M, ldadd]
+  int act;                         // EPI_LINEAR: 0 none, 1 tanh, 2 sigmoid
+  int vec;                         // EPI_LINEAR: bias / addend pointers are 16-byte aligned and N % 32 == 0
   int ksplit, kb_per;
   int tiles_m, tiles_n, stages;
   int out_lo;                      // bf16 outputs: also write the lo array
@@ -235,7 +244,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
 
-  const uint32_t a_bytes = (uint32_t)RT_BM * p.BK * 2, b_bytes = (uint32_t)RT_BN * p.BK * 2;
+  const uint32_t a_bytes = (uint32_t)RT_BM * p.BK * 2, b_bytes = (uint32_t)p.BN * p.BK * 2;
   const int nt = p.x3 ? 2 : 1;
 
   if (warp == 0) {
@@ -246,30 +255,32 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
         const int ks = item % p.ksplit;
         const int tile = item / p.ksplit;
         const int tn = tile % p.tiles_n, tm = tile / p.tiles_n;
-        const int m0 = tm * RT_BM, n0 = tn * RT_BN;
+        const int m0 = tm * RT_BM, n0 = tn * p.BN;
         const int kb0 = ks * p.kb_per, kb1 = min(p.nkb, kb0 + p.kb_per);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const bool seg2 = kb >= p.nkb1;
+          const CUtensorMap* mA = seg2 ? p.mapA2 : p.mapA;
+          const CUtensorMap* mB = seg2 ? p.mapB2 : p.mapB;
           const int st = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1u;
           mbar_wait(&empty_bar[st], ph ^ 1u);
           uint8_t* sa = smem + (size_t)st * RT_STAGE;
           uint8_t* sb = sa + nt * a_bytes;
           mbar_expect_tx(&full_bar[st], nt * (a_bytes + b_bytes));
-          const int k0 = kb * p.BK;
+          const int k0 = (seg2 ? kb - p.nkb1 : kb) * p.BK;
           for (int h = 0; h < nt; ++h) {
             if (p.a_mn) {   // boxes of 64 rows-of-A (contiguous) x BK k
 #pragma unroll
               for (int u = 0; u < RT_BM / 64; ++u)
-                tma_load_2d(sa + h * a_bytes + u * (p.BK * 128), &p.mapA[h], &full_bar[st], m0 + 64 * u, k0);
+                tma_load_2d(sa + h * a_bytes + u * (p.BK * 128), &mA[h], &full_bar[st], m0 + 64 * u, k0);
             } else {
-              tma_load_2d(sa + h * a_bytes, &p.mapA[h], &full_bar[st], k0, m0);
+              tma_load_2d(sa + h * a_bytes, &mA[h], &full_bar[st], k0, m0);
             }
             if (p.b_mn) {
-#pragma unroll
-              for (int u = 0; u < RT_BN / 64; ++u)
-                tma_load_2d(sb + h * b_bytes + u * (p.BK * 128), &p.mapB[h], &full_bar[st], n0 + 64 * u, k0);
+              for (int u = 0; u < p.BN / 64; ++u)
+                tma_load_2d(sb + h * b_bytes + u * (p.BK * 128), &mB[h], &full_bar[st], n0 + 64 * u, k0);
             } else {
-              tma_load_2d(sb + h * b_bytes, &p.mapB[h], &full_bar[st], k0, n0);
+              tma_load_2d(sb + h * b_bytes, &mB[h], &full_bar[st], k0, n0);
             }
           }
         }
@@ -281,7 +292,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6) | A=bf16 [7,10) | B=bf16 [10,13) |
       // a_major [15] | b_major [16] | N>>3 [17,23) | M>>4 [24,29)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
-                             ((uint32_t)(RT_BN >> 3) << 17) | ((uint32_t)(RT_BM >> 4) << 24);
+                             ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(RT_BM >> 4) << 24);
       // K-major tile: rows of BK*2 bytes (64 B -> SWIZZLE_64B, 128 B -> SWIZZLE_128B), 8-row groups SBO apart; a 16-k
       //   step is +32 bytes inside the swizzled row.
       // MN-major tile: 64-wide chunks BK*128 bytes apart (LBO), 8-k-row groups 1024 bytes apart (SBO), SWIZZLE_128B;
@@ -324,13 +335,13 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
     // ===================== epilogue warps 2..9: TMEM lanes 32*(warp%4) .. +31; the two warps of a lane quarter split
     // the 256 accumulator columns in halves and walk them in 32-column chunks
     const int q = warp & 3, half = (warp - 2) >> 2;
-    uint8_t* stg_p = staging + (size_t)(warp - 2) * RT_STG_WARP;
+    uint8_t* stg_p = staging + (size_t)(warp - 2) * p.stg_warp;
     const uint32_t stg0 = smem_u32(stg_p), stg1 = stg0 + 2048u;
     uint32_t li = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
       const int tile = item / p.ksplit;
       const int tn = tile % p.tiles_n, tm = tile / p.tiles_n;
-      const int m0 = tm * RT_BM, n0 = tn * RT_BN;
+      const int m0 = tm * RT_BM, n0 = tn * p.BN;
       const uint32_t ab = li & 1u, aph = (li >> 1) & 1u;
       const int r = m0 + q * 32 + lane;          // global row of this thread
       const bool r_ok = r < p.M;
@@ -344,7 +355,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
       float rs = 0.0f;
       if (EPI == EPI_ATT || EPI == EPI_DY) rv = p.rowvec + (long long)(rr / p.S) * p.N;
       if (EPI == EPI_DY) rs = p.rowscale[rr];
-      const int c_lo = half * (RT_BN / 64), c_hi = c_lo + RT_BN / 64;
+      const int c_lo = half * (p.BN / 64), c_hi = c_lo + p.BN / 64;
       bool released = false;
 #pragma unroll 1
       for (int c = c_lo; c < c_hi; ++c) {
@@ -404,6 +415,71 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
           }
 #pragma unroll
           for (int k = 0; k < 32; ++k) w0[k] = __float_as_uint(v[k]);
+        } else if (EPI == EPI_LINEAR) {
+          // nn.Linear epilogue: act(alpha*acc + bias + bias2 + addend + addend2), fp32 and/or packed bf16 (hi, lo) out
+          if (!p.vec) {   // ragged or misaligned: guarded scalar loads
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const int n = nc + k;
+              float t = 0.0f;
+              if (n < p.N) {
+                if (p.bias) t += __ldg(p.bias + n);
+                if (p.bias2) t += __ldg(p.bias2 + n);
+                if (p.addend) t += __ldg(p.addend + (long long)rr * p.ldadd + n);
+                if (p.addend2) t += __ldg(p.addend2 + (long long)rr * p.ldadd + n);
+              }
+              v[k] = fmaf(v[k], p.alpha, t);
+            }
+          } else {
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+              float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nc) + k4); t.x += b4.x; t.y += b4.y; t.z += b4.z; t.w += b4.w; }
+              if (p.bias2) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias2 + nc) + k4); t.x += b4.x; t.y += b4.y; t.z += b4.z; t.w += b4.w; }
+              if (p.addend) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.addend + (long long)rr * p.ldadd + nc) + k4); t.x += b4.x; t.y += b4.y; t.z += b4.z; t.w += b4.w; }
+              if (p.addend2) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.addend2 + (long long)rr * p.ldadd + nc) + k4); t.x += b4.x; t.y += b4.y; t.z += b4.z; t.w += b4.w; }
+              v[4 * k4] = fmaf(v[4 * k4], p.alpha, t.x); v[4 * k4 + 1] = fmaf(v[4 * k4 + 1], p.alpha, t.y);
+              v[4 * k4 + 2] = fmaf(v[4 * k4 + 2], p.alpha, t.z); v[4 * k4 + 3] = fmaf(v[4 * k4 + 3], p.alpha, t.w);
+            }
+          }
+          if (p.act == 1) {
+            if (p.fast_tanh) {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) v[k] = tanh_hw(v[k]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) v[k] = tanh_acc(v[k]);
+            }
+          } else if (p.act == 2) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = rcp_ftz(1.0f + exp2f_ftz(-1.4426950408889634f * v[k]));
+          }
+#pragma unroll
+          for (int k = 0; k < 32; ++k) w0[k] = __float_as_uint(v[k]);
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+          if (p.out_f) stage_row128(stg0, lane, w0);
+          if (p.out_hi) {
+            uint32_t wh[32];
+            if (p.out_lo) {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) split_pair(v[2 * k], v[2 * k + 1], wh[k], wh[16 + k]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) wh[k] = pack_bf16x2(v[2 * k], v[2 * k + 1]);
+            }
+            stage_row64(stg0 + 4096u, lane, wh);
+            if (p.out_lo) stage_row64(stg0 + 6144u, lane, wh + 16);
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0 && rowbase < p.M) {
+            if (p.out_f) tma_store_2d(&p.mapO[0], stg_p, nc, rowbase);
+            if (p.out_hi) tma_store_2d(&p.mapO[1], stg_p + 4096, nc, rowbase);
+            if (p.out_hi && p.out_lo) tma_store_2d(&p.mapO[2], stg_p + 6144, nc, rowbase);
+            bulk_commit();
+          }
+          continue;
         } else {   // EPI_DY
           const uint4* ih = reinterpret_cast<const uint4*>(p.aux_hi + (long long)rr * p.ldaux + nc);
           const uint4* il = p.aux_lo ? reinterpret_cast<const uint4*>(p.aux_lo + (long long)rr * p.ldaux + nc) : nullptr;
@@ -751,8 +827,30 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   p.BK = p.x3 ? 32 : 64;
   p.nkb = (g.K + p.BK - 1) / p.BK;
   p.tiles_m = (g.M + RT_BM - 1) / RT_BM;
-  p.tiles_n = (g.N + RT_BN - 1) / RT_BN;
-  p.stages = RT_MAXSTAGES;
+  const bool seg2 = g.K2 > 0;
+  if (seg2) {
+    RAU_REQUIRE(g.A2.hi && g.B2.hi && g.A2.mn == g.A.mn && g.B2.mn == g.B.mn && (g.A2.lo != nullptr) == (g.A.lo != nullptr) &&
+                    (g.B2.lo != nullptr) == (g.B.lo != nullptr) && g.A2.ld % 8 == 0 && g.B2.ld % 8 == 0,
+                "rows_gemm: bad second K segment");
+    RAU_REQUIRE((((uintptr_t)g.A2.hi | (uintptr_t)g.B2.hi | (uintptr_t)g.A2.lo | (uintptr_t)g.B2.lo) & 15) == 0,
+                "rows_gemm: operands must be 16-byte aligned");
+  }
+  p.nkb1 = p.nkb;
+  if (seg2) p.nkb += (g.K2 + p.BK - 1) / p.BK;
+  // accumulator width: whole 256-column tiles when there is enough work to fill the SMs, narrower tiles for the skinny
+  // nn.Linear products (M = batch rows) so that more CTAs share the latency-bound work
+  int BN = g.BN;
+  if (BN == 0) {
+    BN = 256;
+    if (g.epi == EPI_LINEAR || g.epi == EPI_PLAIN)
+      while (BN > 64 && (long long)p.tiles_m * ((g.N + BN - 1) / BN) < ctx->sm_count) BN >>= 1;
+    while (BN > 64 && g.N <= BN / 2) BN >>= 1;
+  }
+  RAU_REQUIRE(BN == 64 || BN == 128 || BN == 256, "rows_gemm: BN = %d", BN);
+  p.BN = BN;
+  p.tiles_n = (g.N + BN - 1) / BN;
+  p.stages = g.epi == EPI_LINEAR ? 3 : RT_MAXSTAGES;
+  p.stg_warp = g.epi == EPI_LINEAR ? 8192 : RT_STG_WARP;
   const int tiles = p.tiles_m * p.tiles_n;
   p.ksplit = 1;
   if (g.epi == EPI_RED && tiles < ctx->sm_count) {
@@ -765,10 +863,35 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   p.ksplit = (p.nkb + p.kb_per - 1) / p.kb_per;
   for (int h = 0; h < (p.x3 ? 2 : 1); ++h) {
     RAU_TRY(encode_operand(&p.mapA[h], h ? g.A.lo : g.A.hi, g.A.mn, g.M, g.K, g.A.ld, p.BK, RT_BM));
-    RAU_TRY(encode_operand(&p.mapB[h], h ? g.B.lo : g.B.hi, g.B.mn, g.N, g.K, g.B.ld, p.BK, RT_BN));
+    RAU_TRY(encode_operand(&p.mapB[h], h ? g.B.lo : g.B.hi, g.B.mn, g.N, g.K, g.B.ld, p.BK, BN));
+    if (seg2) {
+      RAU_TRY(encode_operand(&p.mapA2[h], h ? g.A2.lo : g.A2.hi, g.A2.mn, g.M, g.K2, g.A2.ld, p.BK, RT_BM));
+      RAU_TRY(encode_operand(&p.mapB2[h], h ? g.B2.lo : g.B2.hi, g.B2.mn, g.N, g.K2, g.B2.ld, p.BK, BN));
+    }
   }
   const bool f32_out = g.epi == EPI_PLAIN || g.epi == EPI_RED || g.epi == EPI_ATT;
-  if (f32_out) {
+  if (g.epi == EPI_LINEAR) {
+    RAU_REQUIRE(g.out_f || g.out_hi, "rows_gemm: EPI_LINEAR without an output");
+    if (g.out_f) {
+      RAU_REQUIRE(g.ldo % 4 == 0 && ((uintptr_t)g.out_f & 15) == 0, "rows_gemm: fp32 output must be 16-byte aligned");
+      RAU_TRY(encode_2d(&p.mapO[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.out_f, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldo, 32, 32,
+                        CU_TENSOR_MAP_SWIZZLE_128B));
+      p.out_f = 1;
+    }
+    if (g.out_hi) {
+      RAU_REQUIRE(g.ldo_b % 8 == 0 && (((uintptr_t)g.out_hi | (uintptr_t)g.out_lo) & 15) == 0, "rows_gemm: bf16 output alignment");
+      RAU_TRY(encode_2d(&p.mapO[1], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.out_hi, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldo_b, 32,
+                        32, CU_TENSOR_MAP_SWIZZLE_64B));
+      if (g.out_lo)
+        RAU_TRY(encode_2d(&p.mapO[2], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.out_lo, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldo_b,
+                          32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+      p.out_hi = 1;
+      p.out_lo = g.out_lo ? 1 : 0;
+    }
+    p.bias2 = g.bias2; p.addend = g.addend; p.addend2 = g.addend2; p.ldadd = g.ldadd; p.act = g.act;
+    p.vec = (g.N % 32 == 0) && ((((uintptr_t)g.bias | (uintptr_t)g.bias2 | (uintptr_t)g.addend | (uintptr_t)g.addend2) & 15) == 0) &&
+            (g.ldadd % 4 == 0);
+  } else if (f32_out) {
     RAU_REQUIRE(g.out_f && g.ldo % 4 == 0 && ((uintptr_t)g.out_f & 15) == 0, "rows_gemm: fp32 output must be 16-byte aligned");
     RAU_TRY(encode_2d(&p.mapO[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.out_f, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldo, 32, 32,
                       CU_TENSOR_MAP_SWIZZLE_128B));
@@ -784,7 +907,7 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   }
   if (g.epi == EPI_TANH || g.epi == EPI_ATT || g.epi == EPI_DY)
     RAU_REQUIRE(g.N % 32 == 0, "rows_gemm: fused epilogues need N %% 32 == 0 (N = %d)", g.N);
-  if (g.epi == EPI_ATT) RAU_REQUIRE(g.N <= RT_BN && g.S > 0 && g.rowvec && g.colw && g.bias, "rows_gemm: bad EPI_ATT arguments");
+  if (g.epi == EPI_ATT) RAU_REQUIRE(g.N <= BN && g.S > 0 && g.rowvec && g.colw && g.bias, "rows_gemm: bad EPI_ATT arguments");
   if (g.epi == EPI_DY) RAU_REQUIRE(g.S > 0 && g.rowvec && g.rowscale && g.aux_hi && g.ldaux % 8 == 0, "rows_gemm: bad EPI_DY arguments");
   if (g.epi == EPI_TANH) RAU_REQUIRE(g.bias != nullptr, "rows_gemm: EPI_TANH needs a bias");
   p.bias = g.bias; p.rowvec = g.rowvec; p.colw = g.colw; p.rowout = g.rowout; p.rowscale = g.rowscale;
@@ -793,13 +916,14 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   p.fast_tanh = p.x3 ? 0 : 1;   // single-pass bf16: the result is rounded to bf16 anyway, MUFU.TANH (2^-11) is below that
   const int items = tiles * p.ksplit;
   const int grid = items < ctx->sm_count ? items : ctx->sm_count;
-  const int smem_bytes = p.stages * RT_STAGE + 8 * RT_STG_WARP + 1024;
+  const int smem_bytes = p.stages * RT_STAGE + 8 * p.stg_warp + 1024;
   switch (g.epi) {
     case EPI_PLAIN: return launch_rows<EPI_PLAIN>(ctx, p, grid, smem_bytes);
     case EPI_RED: return launch_rows<EPI_RED>(ctx, p, grid, smem_bytes);
     case EPI_TANH: return launch_rows<EPI_TANH>(ctx, p, grid, smem_bytes);
     case EPI_ATT: return launch_rows<EPI_ATT>(ctx, p, grid, smem_bytes);
     case EPI_DY: return launch_rows<EPI_DY>(ctx, p, grid, smem_bytes);
+    case EPI_LINEAR: return launch_rows<EPI_LINEAR>(ctx, p, grid, smem_bytes);
     default: rau_set_error("rows_gemm: unknown epilogue %d", g.epi); return RAU_EINVAL;
   }
 }
@@ -873,4 +997,119 @@ int k_attn_rows_bwd(rau_ctx* ctx, int B, int M, int A, int S, const float* E, co
                                                                             dZ_lo, dqa, gws_part);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
+}
+
+
+// ================================================================== nn.Linear adapter
+namespace {
+// fp32 [rows, cols] (pitch ld) -> packed bf16 (hi [, lo]) [rows, ldo] with ldo = cols rounded up to 8, zero padded
+__global__ void pack2d_kernel(const float* __restrict__ in, int64_t ld, int rows, int cols, int ldo, bf16* __restrict__ hi,
+                              bf16* __restrict__ lo) {
+  const int q = ldo >> 1;   // pairs per packed row
+  const int64_t total = (int64_t)rows * q;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % q) * 2;
+    const int64_t r = i / q;
+    const float a = c < cols ? in[r * ld + c] : 0.0f;
+    const float b = c + 1 < cols ? in[r * ld + c + 1] : 0.0f;
+    uint32_t h, l;
+    split_pair(a, b, h, l);
+    reinterpret_cast<uint32_t*>(hi)[i] = h;
+    if (lo) reinterpret_cast<uint32_t*>(lo)[i] = l;
+  }
+}
+
+struct Packed2D { const bf16* hi = nullptr; const bf16* lo = nullptr; int64_t ld = 0; };
+
+// pack a strided fp32 matrix; parameter tensors (is_const) are packed once per epoch
+int pack2d(rau_ctx* ctx, const float* src, int64_t ld, int rows, int cols, bool want_lo, bool is_const, const char* slot,
+           Packed2D* out) {
+  const int ldo = (cols + 7) / 8 * 8;
+  char name[128];
+  bool cached = false;
+  if (is_const) {
+    snprintf(name, sizeof(name), "rp.%p.%d.%d.%lld.%d", (const void*)src, rows, cols, (long long)ld, want_lo ? 1 : 0);
+    auto it = ctx->tc_epoch.find(name);
+    cached = it != ctx->tc_epoch.end() && it->second == ctx->epoch;
+  } else {
+    snprintf(name, sizeof(name), "rp.%s", slot);
+  }
+  const size_t half = ((size_t)rows * ldo * sizeof(bf16) + 1023) / 1024 * 1024;
+  void* buf = nullptr;
+  RAU_TRY(ctx->arena.get(name, half * (want_lo ? 2 : 1), &buf));
+  out->hi = (bf16*)buf;
+  out->lo = want_lo ? (bf16*)((char*)buf + half) : nullptr;
+  out->ld = ldo;
+  if (!cached) {
+    const int64_t work = (int64_t)rows * (ldo / 2);
+    int64_t blocks = (work + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    pack2d_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(src, ld, rows, cols, ldo, (bf16*)out->hi, (bf16*)out->lo);
+    RAU_LAUNCH_CHECK(ctx);
+    if (is_const) ctx->tc_epoch[name] = ctx->epoch;
+  }
+  return RAU_OK;
+}
+
+long long rows_min_work() {
+  static long long v = -1;
+  if (v < 0) {
+    const char* e = getenv("RAU_TC_MIN_WORK");
+    v = e ? atoll(e) : (1ll << 18);
+  }
+  return v;
+}
+}  // namespace
+
+int rows_contract_try(rau_ctx* ctx, const SimtGemm& g) {
+  if (ctx->precision == RAU_PREC_F32 || !rows_path_enabled()) return 0;
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
+  if (g.batch != 1 || g.kbatch != 1) return 0;
+  if (g.bias_m || g.bias_bm || g.n_valid >= 0) return 0;
+  if (g.A_hi || g.B_hi) return 0;                     // producers of the generic engine's packed forms
+  if ((long long)g.M * g.N * (long long)(g.K + g.K2) < rows_min_work()) return 0;
+  // output: fp32 row-major, TMA-addressable
+  if (g.scn != 1 || g.scm % 4 != 0 || ((uintptr_t)g.C & 15) != 0) return 0;
+  if (g.C_hi && (g.scm % 8 != 0 || (((uintptr_t)g.C_hi | (uintptr_t)g.C_lo) & 15) != 0)) return 0;
+  const bool plain_acc = g.accumulate != 0;
+  if (plain_acc && (g.bias_n || g.bias_n2 || g.addend || g.addend2 || g.act != 0 || g.C_hi)) return 0;
+  if (!plain_acc && g.ksplit > 1) return 0;
+  if (g.addend && g.sdn != 1) return 0;
+  // operands: one contiguous dimension each
+  const int a_mn = (g.sak == 1) ? 0 : (g.sam == 1 ? 1 : -1);
+  const int b_mn = (g.sbk == 1) ? 0 : (g.sbn == 1 ? 1 : -1);
+  if (a_mn < 0 || b_mn < 0) return 0;
+  const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+  RowsGemm r;
+  r.M = g.M; r.N = g.N; r.K = g.K;
+  Packed2D pa, pb, pa2, pb2;
+  // K-major: stored [rows, K]; MN-major: stored [K, rows]
+  RAU_TRY(pack2d(ctx, g.A, a_mn ? g.sak : g.sam, a_mn ? g.K : g.M, a_mn ? g.M : g.K, x3, g.a_const != 0, "A", &pa));
+  RAU_TRY(pack2d(ctx, g.B, b_mn ? g.sbk : g.sbn, b_mn ? g.K : g.N, b_mn ? g.N : g.K, x3, g.b_const != 0, "B", &pb));
+  r.A.hi = pa.hi; r.A.lo = pa.lo; r.A.mn = a_mn; r.A.ld = pa.ld;
+  r.B.hi = pb.hi; r.B.lo = pb.lo; r.B.mn = b_mn; r.B.ld = pb.ld;
+  if (g.A2) {
+    const int a2_mn = (g.sak2 == 1) ? 0 : (g.sam2 == 1 ? 1 : -1);
+    const int b2_mn = (g.sbk2 == 1) ? 0 : (g.sbn2 == 1 ? 1 : -1);
+    if (a2_mn != a_mn || b2_mn != b_mn) return 0;
+    RAU_TRY(pack2d(ctx, g.A2, a_mn ? g.sak2 : g.sam2, a_mn ? g.K2 : g.M, a_mn ? g.M : g.K2, x3, g.a_const != 0, "A2", &pa2));
+    RAU_TRY(pack2d(ctx, g.B2, b_mn ? g.sbk2 : g.sbn2, b_mn ? g.K2 : g.N, b_mn ? g.N : g.K2, x3, g.b_const != 0, "B2", &pb2));
+    r.A2.hi = pa2.hi; r.A2.lo = pa2.lo; r.A2.mn = a_mn; r.A2.ld = pa2.ld;
+    r.B2.hi = pb2.hi; r.B2.lo = pb2.lo; r.B2.mn = b_mn; r.B2.ld = pb2.ld;
+    r.K2 = g.K2;
+  }
+  r.alpha = g.alpha;
+  r.out_f = g.C; r.ldo = g.scm;
+  if (plain_acc) {
+    r.epi = ROWS_EPI_RED;
+  } else {
+    r.epi = ROWS_EPI_LINEAR;
+    r.bias = g.bias_n; r.bias2 = g.bias_n2;
+    r.addend = g.addend; r.addend2 = g.addend2; r.ldadd = g.sdm;
+    r.act = g.act;
+    r.out_hi = g.C_hi; r.out_lo = x3 ? g.C_lo : nullptr; r.ldo_b = g.scm;
+  }
+  RAU_TRY(rows_gemm(ctx, r));
+  return 1;
 }

@@ -181,14 +181,16 @@ int64_t rau_layout(const rau_config* cfg, int group, std::vector<ParamEntry>* ou
       add("Wi", cfg->M, cfg->C);       add("bi", cfg->M, 1);
       add("Wqa", cfg->A, cfg->M);      add("bqa", cfg->A, 1);
       add("Wa", cfg->A, cfg->M);       add("ba", cfg->A, 1);
-      add("ws", 1, cfg->A);            add("bs", 1, 1);
+      add("ws", 1, cfg->A);
       add("Wm", cfg->S, cfg->H);       add("bm", cfg->S, 1);
       add("Wp", cfg->M, cfg->S);       add("bp", cfg->M, 1);
       add("Wx", 4 * cfg->H, cfg->M);   add("bx", 4 * cfg->H, 1);
       add("Whh", 4 * cfg->H, cfg->H);  add("bhh", 4 * cfg->H, 1);
       add("Wo", cfg->M, cfg->H);       add("bo", cfg->M, 1);
       add("Ws", cfg->N, cfg->M);       add("bso", cfg->N, 1);
-      add("wd", 1, cfg->M);            add("bd", 1, 1);
+      add("wd", 1, cfg->M);
+      // the two scalars last: every matrix and vector above starts on a 16-byte boundary (TMA / float4 access)
+      add("bs", 1, 1);                 add("bd", 1, 1);
       break;
     default:
       return -1;

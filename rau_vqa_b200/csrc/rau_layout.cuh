@@ -8,8 +8,8 @@ constexpr int RAU_SP_ALIGN = 16;   // spatial pad granularity (UMMA N % 16, 16-b
 static inline int rau_sp(int S) { return (S + RAU_SP_ALIGN - 1) / RAU_SP_ALIGN * RAU_SP_ALIGN; }
 
 #define RAU_MULT_FIELDS(X) \
-  X(Wq) X(bq) X(Wh) X(bh) X(Wi) X(bi) X(Wqa) X(bqa) X(Wa) X(ba) X(ws) X(bs) X(Wm) X(bm) X(Wp) X(bp) \
-  X(Wx) X(bx) X(Whh) X(bhh) X(Wo) X(bo) X(Ws) X(bso) X(wd) X(bd)
+  X(Wq) X(bq) X(Wh) X(bh) X(Wi) X(bi) X(Wqa) X(bqa) X(Wa) X(ba) X(ws) X(Wm) X(bm) X(Wp) X(bp) \
+  X(Wx) X(bx) X(Whh) X(bhh) X(Wo) X(bo) X(Ws) X(bso) X(wd) X(bs) X(bd)
 
 template <typename P>
 struct MultT {

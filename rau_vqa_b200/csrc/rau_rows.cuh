@@ -2,7 +2,7 @@
 #pragma once
 #include "rau_common.cuh"
 
-enum { ROWS_EPI_PLAIN = 0, ROWS_EPI_RED = 1, ROWS_EPI_TANH = 2, ROWS_EPI_ATT = 3, ROWS_EPI_DY = 4 };
+enum { ROWS_EPI_PLAIN = 0, ROWS_EPI_RED = 1, ROWS_EPI_TANH = 2, ROWS_EPI_ATT = 3, ROWS_EPI_DY = 4, ROWS_EPI_LINEAR = 5 };
 
 // one operand: bf16 hi (and lo in bf16x3 mode); mn = 0: stored [rows, ld >= K] (K-major); mn = 1: stored [K, ld >= rows]
 struct RowsOperand { const bf16* hi = nullptr; const bf16* lo = nullptr; int mn = 0; int64_t ld = 0; };
@@ -10,11 +10,16 @@ struct RowsOperand { const bf16* hi = nullptr; const bf16* lo = nullptr; int mn 
 struct RowsGemm {
   int M = 0, N = 0, K = 0;          // D[M,N] = sum_k A[m,k] B[n,k]
   RowsOperand A, B;
+  RowsOperand A2, B2; int K2 = 0;   // optional second K segment with the same major-ness (x Wi^T + h Wh^T)
   int epi = ROWS_EPI_PLAIN;
-  bf16 *out_hi = nullptr, *out_lo = nullptr;   // EPI_TANH / EPI_DY
-  float* out_f = nullptr;                      // EPI_PLAIN / EPI_RED / EPI_ATT
-  int64_t ldo = 0;
+  int BN = 0;                       // accumulator columns per tile (64 / 128 / 256), 0 = chosen from the shape
+  bf16 *out_hi = nullptr, *out_lo = nullptr;   // EPI_TANH / EPI_DY; optional extra outputs of EPI_LINEAR (pitch ldo_b)
+  float* out_f = nullptr;                      // EPI_PLAIN / EPI_RED / EPI_ATT / EPI_LINEAR
+  int64_t ldo = 0, ldo_b = 0;
   const float* bias = nullptr;      // [N]
+  const float* bias2 = nullptr;     // [N]           (EPI_LINEAR)
+  const float *addend = nullptr, *addend2 = nullptr; int64_t ldadd = 0;   // [M, ldadd] (EPI_LINEAR)
+  int act = 0;                      // EPI_LINEAR: 0 none, 1 tanh, 2 sigmoid
   const float* rowvec = nullptr;    // [rows / S, N]
   const float* colw = nullptr;      // [N]
   float* rowout = nullptr;          // [M]
@@ -27,6 +32,10 @@ struct RowsGemm {
 
 bool rows_path_enabled();
 int rows_gemm(rau_ctx* ctx, const RowsGemm& g);
+struct SimtGemm;
+// nn.Linear-shaped products (forward, dgrad, wgrad) described as a SimtGemm: returns 1 when the rows engine ran it,
+// 0 when the description does not fit (the caller falls back to the generic engines), < 0 on error
+int rows_contract_try(rau_ctx* ctx, const SimtGemm& g);
 // fp32 -> bf16 (hi [, lo]) copy of n contiguous elements in an arena buffer; cache: parameter tensor, packed once per epoch
 int rows_pack(rau_ctx* ctx, const float* W, int64_t n, bool want_lo, bool cache, const char* slot, const bf16** hi, const bf16** lo);
 int k_xprep_rows(rau_ctx* ctx, const float* X, int B, int C, int S, const uint32_t* bits, float scale, bf16* hi, bf16* lo);

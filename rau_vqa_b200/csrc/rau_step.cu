@@ -563,6 +563,9 @@ int rau_time_iembed(rau_ctx* ctx, const rau_config* cfg, int B, const float* mul
 
 int rau_contract(rau_ctx* ctx, const SimtGemm& g) {
   if (ctx->precision != RAU_PREC_F32) {
+    const int rr = rows_contract_try(ctx, g);   // nn.Linear-shaped products: the persistent rows engine
+    if (rr < 0) return rr;
+    if (rr == 1) return RAU_OK;
     const int r = tc_gemm_try(ctx, g);
     if (r < 0) return r;
     if (r == 1) return RAU_OK;

@@ -56,8 +56,11 @@ class WordEmbed(nn.Module):
                                     core.bptr(self.noise_override), self._stream, _p(g), _p(self.gradWeight)))
 
 
-_MULT_LAYERS = (("Wq", "bq"), ("Wh", "bh"), ("Wi", "bi"), ("Wqa", "bqa"), ("Wa", "ba"), ("ws", "bs"), ("Wm", "bm"),
-                ("Wp", "bp"), ("Wx", "bx"), ("Whh", "bhh"), ("Wo", "bo"), ("Ws", "bso"), ("wd", "bd"))
+# flat layout of the mult group (include/rau.h): the two scalar biases bs, bd come last so that every tensor above them
+# starts on a 16-byte boundary; ws and wd are therefore bias-less Linear holders followed by two nn.Add-style holders
+_MULT_LAYERS = (("Wq", "bq"), ("Wh", "bh"), ("Wi", "bi"), ("Wqa", "bqa"), ("Wa", "ba"), ("ws", None), ("Wm", "bm"),
+                ("Wp", "bp"), ("Wx", "bx"), ("Whh", "bhh"), ("Wo", "bo"), ("Ws", "bso"), ("wd", None))
+_MULT_TAIL_BIASES = ("bs", "bd")
 
 
 def mult_shapes(cfg: core.RauConfig):
@@ -71,8 +74,10 @@ class Multimodal(nn.Module):
         super().__init__()
         self.cfg = cfg
         shp = mult_shapes(cfg)
-        for w, _ in _MULT_LAYERS:
-            self.modules.append(nn.Linear(shp[w][1], shp[w][0], device=device))
+        for w, b in _MULT_LAYERS:
+            self.modules.append(nn.Linear(shp[w][1], shp[w][0], device=device, bias=b is not None))
+        for _ in _MULT_TAIL_BIASES:
+            self.modules.append(nn.Add(1, device=device))
         self._flat = self._gflat = None
         self.masks = None              # optional dict(q=, x=, m=) of uint8 keep masks (parity tests)
         self._stream = 0

@@ -141,9 +141,19 @@ class Module:
 class Linear(Module):
     """Parameter holder with nn.Linear's field names; the arithmetic happens in the owning module's native call."""
 
-    def __init__(self, in_size, out_size, device="cpu"):
+    def __init__(self, in_size, out_size, device="cpu", bias=True):
         super().__init__()
         self.weight = torch.zeros(out_size, in_size, dtype=torch.float32, device=device)
-        self.bias = torch.zeros(out_size, dtype=torch.float32, device=device)
         self.gradWeight = torch.zeros_like(self.weight)
+        if bias:                       # nn.Linear(i, o, false) has no bias field
+            self.bias = torch.zeros(out_size, dtype=torch.float32, device=device)
+            self.gradBias = torch.zeros_like(self.bias)
+
+
+class Add(Module):
+    """Parameter holder with nn.Add's field names (a bias without a weight)."""
+
+    def __init__(self, size, device="cpu"):
+        super().__init__()
+        self.bias = torch.zeros(size, dtype=torch.float32, device=device)
         self.gradBias = torch.zeros_like(self.bias)

@@ -127,6 +127,13 @@ def test_train_step_matches_golden_fixture(R, ctx, name):
         # the update is lr-sized: compare the parameter DELTA, not the parameters
         d_lib = P[i].cpu().numpy().astype(np.float64) - z[f"p0_{g}"].astype(np.float32).astype(np.float64)
         d_ref = z[f"p1_{g}"] - z[f"p0_{g}"]
+        if ctx.mode == "bf16":
+            # adam's first step is lr * sign(g) wherever |g| is above the eps knee: in the single-pass bf16 mode (3e-2
+            # gradient tolerance) only elements whose gradient is well above that error have a defined sign
+            big = np.abs(z[f"g_{g}"]) > 10 * tol * np.abs(z[f"g_{g}"]).max()
+            if big.any():
+                assert rel_err(d_lib[big], d_ref[big]) <= tol, g
+            continue
         assert rel_err(d_lib, d_ref) <= max(tol, 2e-3), g     # fp32 parameter storage rounds the delta itself
 
 
