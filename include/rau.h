@@ -93,6 +93,9 @@ int rau_set_seed(rau_ctx* ctx, uint64_t seed);         /* Philox key for dropout
 int rau_set_precision(rau_ctx* ctx, int precision);    /* rau_precision */
 int rau_get_precision(rau_ctx* ctx);
 int rau_sync(rau_ctx* ctx);
+/* debugging aid: with RAU_PHASES=1 in the environment every step runs eagerly with an event at each phase boundary
+ * (encoder, answering units, loss, BPTT, weight gradients, update); this prints the split to stderr and clears it */
+int rau_phase_report(rau_ctx* ctx);
 /* number of kernels this library launched on ctx since creation (bench.py's gpu_launches) */
 int64_t rau_launch_count(rau_ctx* ctx);
 

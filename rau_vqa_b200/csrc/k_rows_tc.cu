@@ -29,9 +29,10 @@ constexpr int RT_BM = 128, RT_BN = 256;
 constexpr int RT_STAGE = 48 * 1024;
 constexpr int RT_THREADS = 320;          // producer + MMA issuer + 8 epilogue warps
 constexpr int RT_STG_WARP = 4096;          // per epilogue warp: one 32 x 128 B (fp32) or two 32 x 64 B (bf16 hi, lo) buffers
-constexpr int RT_MAXSTAGES = 4;
+constexpr int RT_MAXSTAGES = 8;
+constexpr int RT_SMEM_BUDGET = 4 * RT_STAGE + 8 * RT_STG_WARP;   // pipeline + staging bytes a CTA may use (224 KB)
 
-enum { EPI_PLAIN = 0, EPI_RED = 1, EPI_TANH = 2, EPI_ATT = 3, EPI_DY = 4, EPI_LINEAR = 5 };
+enum { EPI_PLAIN = 0, EPI_RED = 1, EPI_TANH = 2, EPI_ATT = 3, EPI_DY = 4, EPI_LINEAR = 5, EPI_LSTM = 6 };
 
 struct RtParams {
   CUtensorMap mapA[2], mapB[2];   // [hi, lo] operand tiles
@@ -47,8 +48,15 @@ struct RtParams {
   const float* addend; const float* addend2; long long ldadd;   // [M, ldadd]
   int act;                         // EPI_LINEAR: 0 none, 1 tanh, 2 sigmoid
   int vec;                         // EPI_LINEAR: bias / addend pointers are 16-byte aligned and N % 32 == 0
+  // EPI_LSTM: the cell update fused behind the gate product (A:12-25, D:47-61).  Accumulator columns are permuted gate
+  // pre-activations: every 32-column chunk holds (i, f, o, g) of 8 consecutive hidden units.
+  const float* c_prev; long long ldcp;         // [M, H] (NULL = zeros)
+  float* c_out; long long ldc;                 // [M, H]
+  float* h_out; long long ldh;                 // [M, H]
+  float* lsaved; long long plane;              // 5 planes (i, f, o, g, tanh c) of M*H floats
+  bf16* hpk_hi; bf16* hpk_lo; long long ldhp;  // packed h for the next product (optional)
   int ksplit, kb_per;
-  int tiles_m, tiles_n, stages;
+  int tiles_m, tiles_n, stages, stage_bytes;
   int out_lo;                      // bf16 outputs: also write the lo array
   const float* bias;
   const float* rowvec;             // [B, N]
@@ -220,7 +228,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
   __shared__ uint64_t full_bar[RT_MAXSTAGES], empty_bar[RT_MAXSTAGES], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* staging = smem + (size_t)p.stages * RT_STAGE;
+  uint8_t* staging = smem + (size_t)p.stages * p.stage_bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int items = p.tiles_m * p.tiles_n * p.ksplit;
 
@@ -264,7 +272,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
           const int st = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1u;
           mbar_wait(&empty_bar[st], ph ^ 1u);
-          uint8_t* sa = smem + (size_t)st * RT_STAGE;
+          uint8_t* sa = smem + (size_t)st * p.stage_bytes;
           uint8_t* sb = sa + nt * a_bytes;
           mbar_expect_tx(&full_bar[st], nt * (a_bytes + b_bytes));
           const int k0 = (seg2 ? kb - p.nkb1 : kb) * p.BK;
@@ -313,7 +321,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
           const uint32_t ph = (it / p.stages) & 1u;
           mbar_wait(&full_bar[st], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sa = smem_u32(smem + (size_t)st * RT_STAGE);
+          const uint32_t sa = smem_u32(smem + (size_t)st * p.stage_bytes);
           const uint32_t sb = sa + nt * a_bytes;
           const uint64_t da_hi = p.a_mn ? make_desc(sa, (uint32_t)p.BK * 128u, 1024u, 2u) : make_desc(sa, 16u, k_sbo, k_layout);
           const uint64_t db_hi = p.b_mn ? make_desc(sb, (uint32_t)p.BK * 128u, 1024u, 2u) : make_desc(sb, 16u, k_sbo, k_layout);
@@ -415,6 +423,64 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
           }
 #pragma unroll
           for (int k = 0; k < 32; ++k) w0[k] = __float_as_uint(v[k]);
+        } else if (EPI == EPI_LSTM) {
+          const int u0 = (nc >> 5) << 3;   // first of the 8 hidden units of this chunk
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nc) + k4); t.x += b4.x; t.y += b4.y; t.z += b4.z; t.w += b4.w; }
+            if (p.addend) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.addend + (long long)rr * p.ldadd + nc) + k4); t.x += b4.x; t.y += b4.y; t.z += b4.z; t.w += b4.w; }
+            v[4 * k4] += t.x; v[4 * k4 + 1] += t.y; v[4 * k4 + 2] += t.z; v[4 * k4 + 3] += t.w;
+          }
+          float cp[8];
+          if (p.c_prev) {
+            const float4 c0 = __ldg(reinterpret_cast<const float4*>(p.c_prev + (long long)rr * p.ldcp + u0));
+            const float4 c1 = __ldg(reinterpret_cast<const float4*>(p.c_prev + (long long)rr * p.ldcp + u0) + 1);
+            cp[0] = c0.x; cp[1] = c0.y; cp[2] = c0.z; cp[3] = c0.w; cp[4] = c1.x; cp[5] = c1.y; cp[6] = c1.z; cp[7] = c1.w;
+          } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) cp[u] = 0.0f;
+          }
+          float gi[8], gf[8], go[8], gg[8], tc[8], cn[8], hn[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            gi[u] = rcp_ftz(1.0f + exp2f_ftz(-1.4426950408889634f * v[u]));
+            gf[u] = rcp_ftz(1.0f + exp2f_ftz(-1.4426950408889634f * v[8 + u]));
+            go[u] = rcp_ftz(1.0f + exp2f_ftz(-1.4426950408889634f * v[16 + u]));
+            gg[u] = tanh_acc(v[24 + u]);
+            cn[u] = fmaf(gf[u], cp[u], gi[u] * gg[u]);
+            tc[u] = tanh_acc(cn[u]);
+            hn[u] = go[u] * tc[u];
+          }
+          if (r_ok) {
+            float4* d;
+            d = reinterpret_cast<float4*>(p.c_out + (long long)r * p.ldc + u0);
+            d[0] = make_float4(cn[0], cn[1], cn[2], cn[3]); d[1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
+            d = reinterpret_cast<float4*>(p.h_out + (long long)r * p.ldh + u0);
+            d[0] = make_float4(hn[0], hn[1], hn[2], hn[3]); d[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+            if (p.lsaved) {
+              const long long H_ = p.N >> 2;
+              float* sbase = p.lsaved + (long long)r * H_ + u0;
+              d = reinterpret_cast<float4*>(sbase);
+              d[0] = make_float4(gi[0], gi[1], gi[2], gi[3]); d[1] = make_float4(gi[4], gi[5], gi[6], gi[7]);
+              d = reinterpret_cast<float4*>(sbase + p.plane);
+              d[0] = make_float4(gf[0], gf[1], gf[2], gf[3]); d[1] = make_float4(gf[4], gf[5], gf[6], gf[7]);
+              d = reinterpret_cast<float4*>(sbase + 2 * p.plane);
+              d[0] = make_float4(go[0], go[1], go[2], go[3]); d[1] = make_float4(go[4], go[5], go[6], go[7]);
+              d = reinterpret_cast<float4*>(sbase + 3 * p.plane);
+              d[0] = make_float4(gg[0], gg[1], gg[2], gg[3]); d[1] = make_float4(gg[4], gg[5], gg[6], gg[7]);
+              d = reinterpret_cast<float4*>(sbase + 4 * p.plane);
+              d[0] = make_float4(tc[0], tc[1], tc[2], tc[3]); d[1] = make_float4(tc[4], tc[5], tc[6], tc[7]);
+            }
+            if (p.hpk_hi) {
+              uint32_t hh[4], hl[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) split_pair(hn[2 * u], hn[2 * u + 1], hh[u], hl[u]);
+              *reinterpret_cast<uint4*>(p.hpk_hi + (long long)r * p.ldhp + u0) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+              if (p.hpk_lo) *reinterpret_cast<uint4*>(p.hpk_lo + (long long)r * p.ldhp + u0) = make_uint4(hl[0], hl[1], hl[2], hl[3]);
+            }
+          }
+          continue;
         } else if (EPI == EPI_LINEAR) {
           // nn.Linear epilogue: act(alpha*acc + bias + bias2 + addend + addend2), fp32 and/or packed bf16 (hi, lo) out
           if (!p.vec) {   // ragged or misaligned: guarded scalar loads
@@ -610,7 +676,7 @@ template <int EPI>
 int launch_rows(rau_ctx* ctx, const RtParams& p, int grid, int smem_bytes) {
   if (!g_attr_done[EPI]) {
     RAU_CHECK_CUDA(cudaFuncSetAttribute(rows_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        RT_MAXSTAGES * RT_STAGE + 8 * RT_STG_WARP + 1024));
+                                        RT_SMEM_BUDGET + 1024));
     g_attr_done[EPI] = true;
   }
   rows_gemm_kernel<EPI><<<grid, RT_THREADS, smem_bytes, ctx->stream>>>(p);
@@ -842,15 +908,19 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   int BN = g.BN;
   if (BN == 0) {
     BN = 256;
-    if (g.epi == EPI_LINEAR || g.epi == EPI_PLAIN)
+    if (g.epi == EPI_LINEAR || g.epi == EPI_PLAIN || g.epi == EPI_LSTM)
       while (BN > 64 && (long long)p.tiles_m * ((g.N + BN - 1) / BN) < ctx->sm_count) BN >>= 1;
     while (BN > 64 && g.N <= BN / 2) BN >>= 1;
   }
   RAU_REQUIRE(BN == 64 || BN == 128 || BN == 256, "rows_gemm: BN = %d", BN);
   p.BN = BN;
   p.tiles_n = (g.N + BN - 1) / BN;
-  p.stages = g.epi == EPI_LINEAR ? 3 : RT_MAXSTAGES;
-  p.stg_warp = g.epi == EPI_LINEAR ? 8192 : RT_STG_WARP;
+  // shared memory: 8 staging buffers for the epilogue warps + as many operand stages as fit (latency-bound skinny
+  // products want many small stages in flight, the big ones four 48 KB stages)
+  p.stg_warp = (g.epi == EPI_LINEAR && g.out_hi) ? 8192 : RT_STG_WARP;
+  p.stage_bytes = (p.x3 ? 2 : 1) * (RT_BM + BN) * p.BK * 2;
+  p.stages = (RT_SMEM_BUDGET - 8 * p.stg_warp) / p.stage_bytes;
+  if (p.stages > RT_MAXSTAGES) p.stages = RT_MAXSTAGES;
   const int tiles = p.tiles_m * p.tiles_n;
   p.ksplit = 1;
   if (g.epi == EPI_RED && tiles < ctx->sm_count) {
@@ -891,6 +961,17 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
     p.bias2 = g.bias2; p.addend = g.addend; p.addend2 = g.addend2; p.ldadd = g.ldadd; p.act = g.act;
     p.vec = (g.N % 32 == 0) && ((((uintptr_t)g.bias | (uintptr_t)g.bias2 | (uintptr_t)g.addend | (uintptr_t)g.addend2) & 15) == 0) &&
             (g.ldadd % 4 == 0);
+  } else if (g.epi == EPI_LSTM) {
+    const int H_ = g.N / 4;
+    RAU_REQUIRE(g.N % 32 == 0 && g.c_out && g.h_out, "rows_gemm: bad EPI_LSTM arguments (4H = %d)", g.N);
+    RAU_REQUIRE(g.ldc % 4 == 0 && g.ldh % 4 == 0 && g.ldcp % 4 == 0 && g.ldadd % 4 == 0 && g.ldhp % 8 == 0 &&
+                    ((((uintptr_t)g.c_out | (uintptr_t)g.h_out | (uintptr_t)g.c_prev | (uintptr_t)g.lsaved | (uintptr_t)g.bias |
+                       (uintptr_t)g.addend | (uintptr_t)g.hpk_hi | (uintptr_t)g.hpk_lo) & 15) == 0),
+                "rows_gemm: EPI_LSTM tensors must be 16-byte aligned");
+    p.addend = g.addend; p.ldadd = g.ldadd;
+    p.c_prev = g.c_prev; p.ldcp = g.ldcp; p.c_out = g.c_out; p.ldc = g.ldc; p.h_out = g.h_out; p.ldh = g.ldh;
+    p.lsaved = g.lsaved; p.plane = (long long)g.M * H_;
+    p.hpk_hi = g.hpk_hi; p.hpk_lo = g.hpk_lo; p.ldhp = g.ldhp;
   } else if (f32_out) {
     RAU_REQUIRE(g.out_f && g.ldo % 4 == 0 && ((uintptr_t)g.out_f & 15) == 0, "rows_gemm: fp32 output must be 16-byte aligned");
     RAU_TRY(encode_2d(&p.mapO[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.out_f, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldo, 32, 32,
@@ -916,7 +997,7 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   p.fast_tanh = p.x3 ? 0 : 1;   // single-pass bf16: the result is rounded to bf16 anyway, MUFU.TANH (2^-11) is below that
   const int items = tiles * p.ksplit;
   const int grid = items < ctx->sm_count ? items : ctx->sm_count;
-  const int smem_bytes = p.stages * RT_STAGE + 8 * p.stg_warp + 1024;
+  const int smem_bytes = p.stages * p.stage_bytes + 8 * p.stg_warp + 1024;
   switch (g.epi) {
     case EPI_PLAIN: return launch_rows<EPI_PLAIN>(ctx, p, grid, smem_bytes);
     case EPI_RED: return launch_rows<EPI_RED>(ctx, p, grid, smem_bytes);
@@ -924,6 +1005,7 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
     case EPI_ATT: return launch_rows<EPI_ATT>(ctx, p, grid, smem_bytes);
     case EPI_DY: return launch_rows<EPI_DY>(ctx, p, grid, smem_bytes);
     case EPI_LINEAR: return launch_rows<EPI_LINEAR>(ctx, p, grid, smem_bytes);
+    case EPI_LSTM: return launch_rows<EPI_LSTM>(ctx, p, grid, smem_bytes);
     default: rau_set_error("rows_gemm: unknown epilogue %d", g.epi); return RAU_EINVAL;
   }
 }
@@ -1052,6 +1134,92 @@ int pack2d(rau_ctx* ctx, const float* src, int64_t ld, int rows, int cols, bool 
   return RAU_OK;
 }
 
+}  // namespace
+int rows_pack2d(rau_ctx* ctx, const float* src, int64_t ld, int rows, int cols, bool want_lo, bool is_const, const char* slot,
+                const bf16** hi, const bf16** lo, int64_t* ldo) {
+  Packed2D pk;
+  RAU_TRY(pack2d(ctx, src, ld, rows, cols, want_lo, is_const, slot, &pk));
+  *hi = pk.hi; *lo = pk.lo; *ldo = pk.ld;
+  return RAU_OK;
+}
+namespace {
+// LSTM layer weights for the fused cell epilogue: rows permuted so that packed row n' = (u/8)*32 + k*8 + u%8 is gate k
+// (k = 0..3 = i, f, o, g) of hidden unit u; bsum[n'] = bi + bh in the same order
+__global__ void pack_lstm_kernel(const float* __restrict__ W, int H, int K, int ldo, int c_i, int c_f, int c_o, int c_g,
+                                 bf16* __restrict__ hi, bf16* __restrict__ lo) {
+  const int q = ldo >> 1;
+  const int64_t total = (int64_t)4 * H * q;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % q) * 2;
+    const int np = (int)(i / q);
+    const int grp = np >> 5, k = (np & 31) >> 3, uu = np & 7;
+    const int chunk = k == 0 ? c_i : (k == 1 ? c_f : (k == 2 ? c_o : c_g));
+    const int64_t src = (int64_t)(chunk * H + grp * 8 + uu) * K;
+    const float a = c < K ? W[src + c] : 0.0f;
+    const float b = c + 1 < K ? W[src + c + 1] : 0.0f;
+    uint32_t h, l;
+    split_pair(a, b, h, l);
+    reinterpret_cast<uint32_t*>(hi)[i] = h;
+    if (lo) reinterpret_cast<uint32_t*>(lo)[i] = l;
+  }
+}
+__global__ void perm_bias_kernel(const float* __restrict__ b1, const float* __restrict__ b2, int H, int c_i, int c_f, int c_o,
+                                 int c_g, float* __restrict__ out) {
+  const int np = blockIdx.x * blockDim.x + threadIdx.x;
+  if (np >= 4 * H) return;
+  const int grp = np >> 5, k = (np & 31) >> 3, uu = np & 7;
+  const int chunk = k == 0 ? c_i : (k == 1 ? c_f : (k == 2 ? c_o : c_g));
+  const int src = chunk * H + grp * 8 + uu;
+  out[np] = (b1 ? b1[src] : 0.0f) + (b2 ? b2[src] : 0.0f);
+}
+}  // namespace
+
+int rows_pack_lstm(rau_ctx* ctx, const float* W, int H, int K, int gate_order, bool want_lo, const bf16** hi, const bf16** lo,
+                   int64_t* ldo) {
+  RAU_REQUIRE(H % 8 == 0, "rows_pack_lstm: H = %d must be a multiple of 8", H);
+  int ci = 0, cf = 1, co = 2, cg = 3;                         // RAU_GATES_IFOG (D:47-54)
+  if (gate_order == RAU_GATES_IGFO) { ci = 0; cg = 1; cf = 2; co = 3; }   // A:12-19
+  const int ld = (K + 7) / 8 * 8;
+  char name[128];
+  snprintf(name, sizeof(name), "rl.%p.%d.%d.%d.%d", (const void*)W, H, K, gate_order, want_lo ? 1 : 0);
+  auto it = ctx->tc_epoch.find(name);
+  const bool cached = it != ctx->tc_epoch.end() && it->second == ctx->epoch;
+  const size_t half = ((size_t)4 * H * ld * sizeof(bf16) + 1023) / 1024 * 1024;
+  void* buf = nullptr;
+  RAU_TRY(ctx->arena.get(name, half * (want_lo ? 2 : 1), &buf));
+  *hi = (bf16*)buf;
+  *lo = want_lo ? (bf16*)((char*)buf + half) : nullptr;
+  *ldo = ld;
+  if (!cached) {
+    const int64_t work = (int64_t)4 * H * (ld / 2);
+    int64_t blocks = (work + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    pack_lstm_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(W, H, K, ld, ci, cf, co, cg, (bf16*)*hi, (bf16*)*lo);
+    RAU_LAUNCH_CHECK(ctx);
+    ctx->tc_epoch[name] = ctx->epoch;
+  }
+  return RAU_OK;
+}
+
+int rows_perm_lstm_bias(rau_ctx* ctx, const float* b1, const float* b2, int H, int gate_order, const float** out) {
+  int ci = 0, cf = 1, co = 2, cg = 3;
+  if (gate_order == RAU_GATES_IGFO) { ci = 0; cg = 1; cf = 2; co = 3; }
+  char name[128];
+  snprintf(name, sizeof(name), "rlb.%p.%p.%d.%d", (const void*)b1, (const void*)b2, H, gate_order);
+  auto it = ctx->tc_epoch.find(name);
+  const bool cached = it != ctx->tc_epoch.end() && it->second == ctx->epoch;
+  void* buf = nullptr;
+  RAU_TRY(ctx->arena.get(name, sizeof(float) * 4 * (size_t)H, &buf));
+  *out = (const float*)buf;
+  if (!cached) {
+    perm_bias_kernel<<<(4 * H + 255) / 256, 256, 0, ctx->stream>>>(b1, b2, H, ci, cf, co, cg, (float*)buf);
+    RAU_LAUNCH_CHECK(ctx);
+    ctx->tc_epoch[name] = ctx->epoch;
+  }
+  return RAU_OK;
+}
+
+namespace {
 long long rows_min_work() {
   static long long v = -1;
   if (v < 0) {

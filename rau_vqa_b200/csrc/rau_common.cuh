@@ -84,7 +84,11 @@ struct rau_ctx {
   const StepState* ss_active = nullptr;            // non-null while a whole-step call is being enqueued
   cudaStream_t gstream = nullptr;                  // capture stream (the caller's stream may be the legacy one)
   RauGraph graph;
+  // RAU_PHASES=1: eager steps with an event at every phase boundary; rau_phase_report() prints the split
+  int phases = -1;
+  std::vector<std::pair<std::string, cudaEvent_t>> phase_ev;
 };
+void rau_phase_mark(rau_ctx* ctx, const char* name);
 
 #define RAU_LAUNCH_CHECK(ctx)                                                             \
   do {                                                                                    \

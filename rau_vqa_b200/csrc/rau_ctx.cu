@@ -42,9 +42,36 @@ void RauArena::release() {
 
 int rau_comm_destroy_internal(rau_ctx* ctx);  // rau_comm.cu
 
+void rau_phase_mark(rau_ctx* ctx, const char* name) {
+  if (ctx->phases < 0) {
+    const char* e = getenv("RAU_PHASES");
+    ctx->phases = e ? atoi(e) : 0;
+  }
+  if (!ctx->phases) return;
+  cudaEvent_t ev;
+  if (cudaEventCreate(&ev) != cudaSuccess) return;
+  cudaEventRecord(ev, ctx->stream);
+  ctx->phase_ev.push_back({name, ev});
+}
+
 extern "C" {
 
 int rau_version(void) { return 100; }
+
+/* debugging aid (RAU_PHASES=1): prints the milliseconds between the phase marks recorded since the last report */
+int rau_phase_report(rau_ctx* ctx) {
+  if (ctx == nullptr) return RAU_EINVAL;
+  if (ctx->phase_ev.empty()) return RAU_OK;
+  cudaStreamSynchronize(ctx->stream);
+  for (size_t i = 1; i < ctx->phase_ev.size(); ++i) {
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, ctx->phase_ev[i - 1].second, ctx->phase_ev[i].second);
+    fprintf(stderr, "[rau phase] %-28s %8.3f ms\n", ctx->phase_ev[i].first.c_str(), ms);
+  }
+  for (auto& kv : ctx->phase_ev) cudaEventDestroy(kv.second);
+  ctx->phase_ev.clear();
+  return RAU_OK;
+}
 
 const char* rau_last_error(void) { return g_err; }
 

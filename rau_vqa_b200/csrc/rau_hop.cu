@@ -180,14 +180,33 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
     RAU_TRY(rau_contract(ctx, g));
   }
   // attlstm (A:4-28): gates (i,g,f,o)
-  {
+  const bool fused_cell = ctx->precision != RAU_PREC_F32 && rows_path_enabled() && H % 8 == 0 && M % 8 == 0 &&
+                          (int64_t)B * 4 * H * (M + H) >= (1 << 18) &&
+                          ((((uintptr_t)c | (uintptr_t)c_out | (uintptr_t)sv.hout | (uintptr_t)sv.lsav) & 15) == 0);
+  if (fused_cell) {   // one launch: [j | h] [Wx | Whh]^T with the cell update in the epilogue (k_rows_tc.cu EPI_LSTM)
+    const bf16 *Wx_h, *Wx_l, *Wh_h, *Wh_l, *j_h, *j_l, *h_h, *h_l;
+    int64_t ldwx, ldwh, ldj, ldh_;
+    const float* bperm;
+    RAU_TRY(rows_pack_lstm(ctx, P.Wx, H, M, RAU_GATES_IGFO, x3, &Wx_h, &Wx_l, &ldwx));
+    RAU_TRY(rows_pack_lstm(ctx, P.Whh, H, H, RAU_GATES_IGFO, x3, &Wh_h, &Wh_l, &ldwh));
+    RAU_TRY(rows_perm_lstm_bias(ctx, P.bx, P.bhh, H, RAU_GATES_IGFO, &bperm));
+    RAU_TRY(rows_pack2d(ctx, sv.j, M, B, M, x3, false, "cell.j", &j_h, &j_l, &ldj));
+    RAU_TRY(rows_pack2d(ctx, h, H, B, H, x3, false, "cell.h", &h_h, &h_l, &ldh_));
+    RowsGemm g;
+    g.M = B; g.N = 4 * H; g.K = M;
+    g.A.hi = j_h; g.A.lo = j_l; g.A.ld = ldj; g.B.hi = Wx_h; g.B.lo = Wx_l; g.B.ld = ldwx;
+    g.A2.hi = h_h; g.A2.lo = h_l; g.A2.ld = ldh_; g.B2.hi = Wh_h; g.B2.lo = Wh_l; g.B2.ld = ldwh; g.K2 = H;
+    g.epi = ROWS_EPI_LSTM; g.bias = bperm;
+    g.c_prev = c; g.ldcp = H; g.c_out = c_out; g.ldc = H; g.h_out = sv.hout; g.ldh = H; g.lsaved = sv.lsav;
+    RAU_TRY(rows_gemm(ctx, g));
+  } else {
     SimtGemm g = lin_fwd(B, 4 * H, M, sv.j, M, P.Wx, Gt, 4 * H);
     lin_seg2(g, H, h, H, P.Whh);
     g.bias_n = P.bx; g.bias_n2 = P.bhh;
     RAU_TRY(rau_contract(ctx, g));
+    RAU_TRY(k_lstm_fwd(ctx, B, H, RAU_GATES_IGFO, Gt, 4 * H, c, H, c_out, H, sv.hout, H, nullptr, 0, sv.lsav));
   }
-  RAU_TRY(k_lstm_fwd(ctx, B, H, RAU_GATES_IGFO, Gt, 4 * H, c, H, c_out, H, sv.hout, H, nullptr, 0, sv.lsav));
-  if (h_out)
+  if (h_out && h_out != sv.hout)
     RAU_CHECK_CUDA(cudaMemcpyAsync(h_out, sv.hout, sizeof(float) * B * H, cudaMemcpyDeviceToDevice, ctx->stream));
   // m = drop(j + Wo h' + bo) ; score = Ws m + bs ; do_pred = sigmoid(wd.m + bd)   (F:276-281)
   {
@@ -202,7 +221,7 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
     RAU_TRY(rau_contract(ctx, g));
   }
   RAU_TRY(k_rowdot_sigmoid(ctx, sv.m, B, M, P.wd, P.bd, sv.dop));
-  if (do_pred)
+  if (do_pred && do_pred != sv.dop)
     RAU_CHECK_CUDA(cudaMemcpyAsync(do_pred, sv.dop, sizeof(float) * B, cudaMemcpyDeviceToDevice, ctx->stream));
   return RAU_OK;
 }
@@ -210,7 +229,7 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
 int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const float*>& P, const MultT<float*>& G,
                  const float* X, const float* c, const float* h, int train, const HopSaved& sv,
                  const float* dscore, const float* ddo_pred, const float* dp_att, const float* dc_out, const float* dh_out,
-                 float* dq, int dq_accumulate, float* dX, float* dc, float* dh) {
+                 float* dq, int dq_accumulate, float* dX, float* dc, float* dh, const HopGrads* deferred) {
   const int Q = 2 * cfg->Hq * cfg->nlayer, M = cfg->M, A = cfg->A, H = cfg->H, S = cfg->S, C = cfg->C, N = cfg->N;
   const int Sp = rau_sp(S);
   const uint32_t* qb = (train && cfg->p_q > 0) ? sv.qbits : nullptr;
@@ -218,14 +237,19 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   const uint32_t* mb = (train && cfg->p_m > 0) ? sv.mbits : nullptr;
   const bool tc = ctx->precision != RAU_PREC_F32 && S % 4 == 0;
   const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+  const bool now = deferred == nullptr;   // accumulate the nn.Linear weight / bias gradients inside this call
   float* Xd = nullptr;
   if (!tc || dX) RAU_TRY(ctx->arena.get("hop.Xd", sizeof(float) * (size_t)B * C * Sp, (void**)&Xd));
-  ARENA(du, float, "hopb.du", B * M);
+  ARENA(du_own, float, "hopb.du", B * M);
   ARENA(dh2, float, "hopb.dh2", B * H);
-  ARENA(dG, float, "hopb.dG", B * 4 * H);
-  ARENA(dj, float, "hopb.dj", B * M);
+  ARENA(dG_own, float, "hopb.dG", B * 4 * H);
+  ARENA(dj_own, float, "hopb.dj", B * M);
   ARENA(dp, float, "hopb.dp", B * S);
-  ARENA(ds, float, "hopb.ds", B * S);
+  ARENA(ds_own, float, "hopb.ds", B * S);
+  float* du = now ? du_own : deferred->du;
+  float* dG = now ? dG_own : deferred->dG;
+  float* dj = now ? dj_own : deferred->dj;
+  float* ds = now ? ds_own : deferred->ds;
   float* dZ = nullptr;
   bf16 *dZ_hi = nullptr, *dZ_lo = nullptr, *dY_hi = nullptr, *dY_lo = nullptr;
   if (tc) {
@@ -238,19 +262,24 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   } else {
     RAU_TRY(ctx->arena.get("hopb.dZ", sizeof(float) * (size_t)B * A * Sp, (void**)&dZ));
   }
-  ARENA(dqa, float, "hopb.dqa", B * A);
-  ARENA(gwsp, float, "hopb.gwsp", B * A);
+  ARENA(dqa_own, float, "hopb.dqa", B * A);
+  ARENA(gwsp_own, float, "hopb.gwsp", B * A);
   ARENA(dI, float, "hopb.dI", (size_t)B * M * Sp);
   ARENA(dqf, float, "hopb.dqf", B * M);
-  ARENA(dpre, float, "hopb.dpre", B * M);
+  ARENA(dpre_own, float, "hopb.dpre", B * M);
+  float* dqa = now ? dqa_own : deferred->dqa;
+  float* gwsp = now ? gwsp_own : deferred->gwsp;
+  float* dpre = now ? dpre_own : deferred->dpre;
   ARENA(dqt, float, "hopb.dqt", B * Q);
   const int ks_img = B >= 64 ? 32 : (B >= 8 ? 8 : 1);   // split of the per-image reductions
 
   // heads: dm = Ws^T dscore (+ do_pred head) ; gWs += dscore (x) m
   if (dscore) {
     RAU_TRY(rau_contract(ctx, lin_dgrad(B, N, M, dscore, N, P.Ws, du, M)));
-    RAU_TRY(rau_contract(ctx, lin_wgrad(B, N, M, dscore, N, sv.m, M, G.Ws, 1.0f)));
-    RAU_TRY(k_colsum(ctx, dscore, B, N, N, G.bso, 1));
+    if (now) {
+      RAU_TRY(rau_contract(ctx, lin_wgrad(B, N, M, dscore, N, sv.m, M, G.Ws, 1.0f)));
+      RAU_TRY(k_colsum(ctx, dscore, B, N, N, G.bso, 1));
+    }
   } else {
     RAU_TRY(k_fill(ctx, du, (int64_t)B * M, 0.0f));
   }
@@ -262,8 +291,10 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
     if (dh_out) { g.addend = dh_out; g.sdm = H; g.sdn = 1; }
     RAU_TRY(rau_contract(ctx, g));
   }
-  RAU_TRY(rau_contract(ctx, lin_wgrad(B, M, H, du, M, sv.hout, H, G.Wo, 1.0f)));
-  RAU_TRY(k_colsum(ctx, du, B, M, M, G.bo, 1));
+  if (now) {
+    RAU_TRY(rau_contract(ctx, lin_wgrad(B, M, H, du, M, sv.hout, H, G.Wo, 1.0f)));
+    RAU_TRY(k_colsum(ctx, du, B, M, M, G.bo, 1));
+  }
   // attlstm backward
   RAU_TRY(k_lstm_bwd(ctx, B, H, RAU_GATES_IGFO, dc_out, H, dh2, H, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, c, H,
                      sv.lsav, dG, nullptr, dc, H));
@@ -273,18 +304,22 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
     RAU_TRY(rau_contract(ctx, g));
   }
   RAU_TRY(rau_contract(ctx, lin_dgrad(B, 4 * H, H, dG, 4 * H, P.Whh, dh, H)));
-  RAU_TRY(rau_contract(ctx, lin_wgrad(B, 4 * H, M, dG, 4 * H, sv.j, M, G.Wx, 1.0f)));
-  RAU_TRY(rau_contract(ctx, lin_wgrad(B, 4 * H, H, dG, 4 * H, h, H, G.Whh, 1.0f)));
-  RAU_TRY(k_colsum(ctx, dG, B, 4 * H, 4 * H, G.bx, 1));
-  RAU_TRY(k_colsum(ctx, dG, B, 4 * H, 4 * H, G.bhh, 1));
+  if (now) {
+    RAU_TRY(rau_contract(ctx, lin_wgrad(B, 4 * H, M, dG, 4 * H, sv.j, M, G.Wx, 1.0f)));
+    RAU_TRY(rau_contract(ctx, lin_wgrad(B, 4 * H, H, dG, 4 * H, h, H, G.Whh, 1.0f)));
+    RAU_TRY(k_colsum(ctx, dG, B, 4 * H, 4 * H, G.bx, 1));
+    RAU_TRY(k_colsum(ctx, dG, B, 4 * H, 4 * H, G.bhh, 1));
+  }
   // join: dqf = da = dj ; dp = dp_att + Wp^T dj ; gWp += dj (x) p
   {
     SimtGemm g = lin_dgrad(B, M, S, dj, M, P.Wp, dp, S);
     if (dp_att) { g.addend = dp_att; g.sdm = S; g.sdn = 1; }
     RAU_TRY(rau_contract(ctx, g));
   }
-  RAU_TRY(rau_contract(ctx, lin_wgrad(B, M, S, dj, M, sv.p, S, G.Wp, 1.0f)));
-  RAU_TRY(k_colsum(ctx, dj, B, M, M, G.bp, 1));
+  if (now) {
+    RAU_TRY(rau_contract(ctx, lin_wgrad(B, M, S, dj, M, sv.p, S, G.Wp, 1.0f)));
+    RAU_TRY(k_colsum(ctx, dj, B, M, M, G.bp, 1));
+  }
   // attselect + softmax + score conv + tanh of attbycontent, one CTA per image
   const bool rows = rows_path(ctx, cfg);
   const int R = B * S;
@@ -298,10 +333,12 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
     g.accumulate = 1;
     RAU_TRY(rau_contract(ctx, g));
   }
-  RAU_TRY(rau_contract(ctx, lin_wgrad(B, S, H, ds, S, h, H, G.Wm, 1.0f)));
-  RAU_TRY(k_colsum(ctx, ds, B, S, S, G.bm, 1));
-  RAU_TRY(k_colsum(ctx, gwsp, B, A, A, G.ws, 1));
-  RAU_TRY(k_sum_all(ctx, ds, (int64_t)B * S, G.bs, 1));
+  if (now) {
+    RAU_TRY(rau_contract(ctx, lin_wgrad(B, S, H, ds, S, h, H, G.Wm, 1.0f)));
+    RAU_TRY(k_colsum(ctx, ds, B, S, S, G.bm, 1));
+    RAU_TRY(k_colsum(ctx, gwsp, B, A, A, G.ws, 1));
+    RAU_TRY(k_sum_all(ctx, ds, (int64_t)B * S, G.bs, 1));
+  }
   if (rows) {
     const bf16 *Wa_h, *Wa_l;
     RAU_TRY(rows_pack(ctx, P.Wa, (int64_t)A * M, x3, true, nullptr, &Wa_h, &Wa_l));
@@ -348,15 +385,17 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
     RAU_TRY(rau_contract(ctx, g));
   }
   }
-  RAU_TRY(k_colsum(ctx, dqa, B, A, A, G.ba, 1));   // gba = sum_b sum_s dZ = sum_b dqa
+  if (now) RAU_TRY(k_colsum(ctx, dqa, B, A, A, G.ba, 1));   // gba = sum_b sum_s dZ = sum_b dqa
   // dqf = dj + Wqa^T dqa ; gWqa += dqa (x) qf
   {
     SimtGemm g = lin_dgrad(B, A, M, dqa, A, P.Wqa, dqf, M);
     g.addend = dj; g.sdm = M; g.sdn = 1;
     RAU_TRY(rau_contract(ctx, g));
   }
-  RAU_TRY(rau_contract(ctx, lin_wgrad(B, A, M, dqa, A, sv.qf, M, G.Wqa, 1.0f)));
-  RAU_TRY(k_colsum(ctx, dqa, B, A, A, G.bqa, 1));
+  if (now) {
+    RAU_TRY(rau_contract(ctx, lin_wgrad(B, A, M, dqa, A, sv.qf, M, G.Wqa, 1.0f)));
+    RAU_TRY(k_colsum(ctx, dqa, B, A, A, G.bqa, 1));
+  }
   if (rows) {
     {   // gWi += dY^T drop(X)^T
       RowsGemm g;
@@ -412,10 +451,39 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
     g.accumulate = 1;
     RAU_TRY(rau_contract(ctx, g));
   }
-  RAU_TRY(rau_contract(ctx, lin_wgrad(B, M, Q, dpre, M, sv.qd, Q, G.Wq, 1.0f)));
-  RAU_TRY(rau_contract(ctx, lin_wgrad(B, M, H, dpre, M, h, H, G.Wh, 1.0f)));
-  RAU_TRY(k_colsum(ctx, dpre, B, M, M, G.bq, 1));
-  RAU_TRY(k_colsum(ctx, dpre, B, M, M, G.bh, 1));
+  if (now) {
+    RAU_TRY(rau_contract(ctx, lin_wgrad(B, M, Q, dpre, M, sv.qd, Q, G.Wq, 1.0f)));
+    RAU_TRY(rau_contract(ctx, lin_wgrad(B, M, H, dpre, M, h, H, G.Wh, 1.0f)));
+    RAU_TRY(k_colsum(ctx, dpre, B, M, M, G.bq, 1));
+    RAU_TRY(k_colsum(ctx, dpre, B, M, M, G.bh, 1));
+  }
+  return RAU_OK;
+}
+
+// accGradParameters of every nn.Linear of the answering unit, once over the rows of all hops (rows = nHop * B)
+int hop_wgrads(rau_ctx* ctx, const rau_config* cfg, int rows, const MultT<float*>& G, const HopStacks& st) {
+  const int Q = 2 * cfg->Hq * cfg->nlayer, M = cfg->M, A = cfg->A, H = cfg->H, S = cfg->S, N = cfg->N;
+  RAU_TRY(rau_contract(ctx, lin_wgrad(rows, N, M, st.dscore, N, st.m, M, G.Ws, 1.0f)));
+  RAU_TRY(k_colsum(ctx, st.dscore, rows, N, N, G.bso, 1));
+  RAU_TRY(rau_contract(ctx, lin_wgrad(rows, M, H, st.du, M, st.hout, H, G.Wo, 1.0f)));
+  RAU_TRY(k_colsum(ctx, st.du, rows, M, M, G.bo, 1));
+  RAU_TRY(rau_contract(ctx, lin_wgrad(rows, 4 * H, M, st.dG, 4 * H, st.j, M, G.Wx, 1.0f)));
+  RAU_TRY(rau_contract(ctx, lin_wgrad(rows, 4 * H, H, st.dG, 4 * H, st.h_in, H, G.Whh, 1.0f)));
+  RAU_TRY(k_colsum(ctx, st.dG, rows, 4 * H, 4 * H, G.bx, 1));
+  RAU_TRY(k_colsum(ctx, st.dG, rows, 4 * H, 4 * H, G.bhh, 1));
+  RAU_TRY(rau_contract(ctx, lin_wgrad(rows, M, S, st.dj, M, st.p, S, G.Wp, 1.0f)));
+  RAU_TRY(k_colsum(ctx, st.dj, rows, M, M, G.bp, 1));
+  RAU_TRY(rau_contract(ctx, lin_wgrad(rows, S, H, st.ds, S, st.h_in, H, G.Wm, 1.0f)));
+  RAU_TRY(k_colsum(ctx, st.ds, rows, S, S, G.bm, 1));
+  RAU_TRY(k_colsum(ctx, st.gwsp, rows, A, A, G.ws, 1));
+  RAU_TRY(k_sum_all(ctx, st.ds, (int64_t)rows * S, G.bs, 1));
+  RAU_TRY(k_colsum(ctx, st.dqa, rows, A, A, G.ba, 1));
+  RAU_TRY(rau_contract(ctx, lin_wgrad(rows, A, M, st.dqa, A, st.qf, M, G.Wqa, 1.0f)));
+  RAU_TRY(k_colsum(ctx, st.dqa, rows, A, A, G.bqa, 1));
+  RAU_TRY(rau_contract(ctx, lin_wgrad(rows, M, Q, st.dpre, M, st.qd, Q, G.Wq, 1.0f)));
+  RAU_TRY(rau_contract(ctx, lin_wgrad(rows, M, H, st.dpre, M, st.h_in, H, G.Wh, 1.0f)));
+  RAU_TRY(k_colsum(ctx, st.dpre, rows, M, M, G.bq, 1));
+  RAU_TRY(k_colsum(ctx, st.dpre, rows, M, M, G.bh, 1));
   return RAU_OK;
 }
 

@@ -53,10 +53,20 @@ struct HopSaved {
 };
 size_t hop_saved_layout(const rau_config* cfg, int B, void* base, HopSaved* sv);
 
+// Backward scratch of one hop that the weight-gradient products read.  In the training step these point into
+// tensor-major stacks [nHop][B][dim], hop_backward skips every nn.Linear accGradParameters, and hop_wgrads() issues
+// each of them ONCE over all nHop*B rows after the last hop (the clones share one gradWeight, F:344, so the sum over
+// hops is what the reference accumulates anyway).
+struct HopGrads { float *du, *dG, *dj, *ds, *dqa, *dpre, *gwsp; };
+struct HopStacks {   // every member is [nHop][B][dim]
+  const float *dscore, *m, *du, *hout, *dG, *j, *h_in, *dj, *p, *ds, *dqa, *qf, *dpre, *qd, *gwsp;
+};
+int hop_wgrads(rau_ctx* ctx, const rau_config* cfg, int rows, const MultT<float*>& G, const HopStacks& st);
+
 int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const float*>& P,
                 const float* q, const float* X, const float* c, const float* h, int train, const HopSaved& sv,
                 float* score, float* do_pred, float* p_out, float* c_out, float* h_out);
 int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const float*>& P, const MultT<float*>& G,
                  const float* X, const float* c, const float* h, int train, const HopSaved& sv,
                  const float* dscore, const float* ddo_pred, const float* dp_att, const float* dc_out, const float* dh_out,
-                 float* dq, int dq_accumulate, float* dX, float* dc, float* dh);
+                 float* dq, int dq_accumulate, float* dX, float* dc, float* dh, const HopGrads* deferred = nullptr);

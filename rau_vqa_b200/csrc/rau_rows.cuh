@@ -2,7 +2,7 @@
 #pragma once
 #include "rau_common.cuh"
 
-enum { ROWS_EPI_PLAIN = 0, ROWS_EPI_RED = 1, ROWS_EPI_TANH = 2, ROWS_EPI_ATT = 3, ROWS_EPI_DY = 4, ROWS_EPI_LINEAR = 5 };
+enum { ROWS_EPI_PLAIN = 0, ROWS_EPI_RED = 1, ROWS_EPI_TANH = 2, ROWS_EPI_ATT = 3, ROWS_EPI_DY = 4, ROWS_EPI_LINEAR = 5, ROWS_EPI_LSTM = 6 };
 
 // one operand: bf16 hi (and lo in bf16x3 mode); mn = 0: stored [rows, ld >= K] (K-major); mn = 1: stored [K, ld >= rows]
 struct RowsOperand { const bf16* hi = nullptr; const bf16* lo = nullptr; int mn = 0; int64_t ld = 0; };
@@ -20,6 +20,12 @@ struct RowsGemm {
   const float* bias2 = nullptr;     // [N]           (EPI_LINEAR)
   const float *addend = nullptr, *addend2 = nullptr; int64_t ldadd = 0;   // [M, ldadd] (EPI_LINEAR)
   int act = 0;                      // EPI_LINEAR: 0 none, 1 tanh, 2 sigmoid
+  // EPI_LSTM (N = 4H permuted gate columns, see rows_pack_lstm): bias/addend as above, plus
+  const float* c_prev = nullptr; int64_t ldcp = 0;
+  float* c_out = nullptr; int64_t ldc = 0;
+  float* h_out = nullptr; int64_t ldh = 0;
+  float* lsaved = nullptr;          // [5][M][H] planes i, f, o, g, tanh(c)
+  bf16 *hpk_hi = nullptr, *hpk_lo = nullptr; int64_t ldhp = 0;
   const float* rowvec = nullptr;    // [rows / S, N]
   const float* colw = nullptr;      // [N]
   float* rowout = nullptr;          // [M]
@@ -37,6 +43,13 @@ struct SimtGemm;
 // 0 when the description does not fit (the caller falls back to the generic engines), < 0 on error
 int rows_contract_try(rau_ctx* ctx, const SimtGemm& g);
 // fp32 -> bf16 (hi [, lo]) copy of n contiguous elements in an arena buffer; cache: parameter tensor, packed once per epoch
+// fp32 [rows, cols] of pitch ld -> packed bf16 (hi [, lo]) of pitch *ldo (cols rounded up to 8) in an arena buffer
+int rows_pack2d(rau_ctx* ctx, const float* src, int64_t ld, int rows, int cols, bool want_lo, bool is_const, const char* slot,
+                const bf16** hi, const bf16** lo, int64_t* ldo);
+// LSTM weights [4H, K] with rows permuted for the fused cell epilogue (cached per epoch), and the permuted bias sum
+int rows_pack_lstm(rau_ctx* ctx, const float* W, int H, int K, int gate_order, bool want_lo, const bf16** hi, const bf16** lo,
+                   int64_t* ldo);
+int rows_perm_lstm_bias(rau_ctx* ctx, const float* b1, const float* b2, int H, int gate_order, const float** out);
 int rows_pack(rau_ctx* ctx, const float* W, int64_t n, bool want_lo, bool cache, const char* slot, const bf16** hi, const bf16** lo);
 int k_xprep_rows(rau_ctx* ctx, const float* X, int B, int C, int S, const uint32_t* bits, float scale, bf16* hi, bf16* lo);
 int k_unprep_rows(rau_ctx* ctx, const float* dXr, int B, int C, int S, const uint32_t* bits, float scale, float* dX);

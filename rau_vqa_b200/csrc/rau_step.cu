@@ -72,13 +72,63 @@ static int encoder_forward(rau_ctx* ctx, const rau_config* cfg, const rau_batch*
   // word_embed for every step at once (F:203-206, F:468)
   RAU_TRY(k_embed_fwd(ctx, bt->tokens, Tm * B, E, cfg->V, Pe, de ? en->ebits : nullptr, drop_scale(cfg->p_embed),
                       en->e_all, nullptr, 0));
+  const bool fused = ctx->precision != RAU_PREC_F32 && rows_path_enabled() && Hq % 8 == 0 && E % 4 == 0 &&
+                     (int64_t)B * G4 * Hq >= (1 << 18);
   // layer 1 input projection hoisted over time: G1x = e Wi1^T + bi1 + bh1
-  {
+  if (!fused) {
     SimtGemm g = lin_fwd(Tm * B, G4, E, en->e_all, E, Pr + L[0].Wi, en->G1x, G4);
     g.bias_n = Pr + L[0].bi; g.bias_n2 = Pr + L[0].bh;
     RAU_TRY(rau_contract(ctx, g));
   }
   RAU_TRY(k_fill(ctx, en->S_all, (int64_t)B * Q, 0.0f));
+  if (fused) {
+    // tcgen05 path: each recurrent step is ONE launch -- gate product h_{t-1} Wh^T (+ hoisted input projection) with the
+    // cell update fused behind it in the epilogue (EPI_LSTM), which also emits h_t packed for the next step
+    const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+    const size_t hb = (size_t)B * Hq;
+    ARENA(hpk_hi, bf16, "enc.hpk.hi", (size_t)(Tm + 1) * hb);
+    ARENA(hpk_lo, bf16, "enc.hpk.lo", (size_t)(Tm + 1) * hb);
+    for (int layer = 0; layer < 2; ++layer) {
+      const int in = layer == 0 ? E : Hq;
+      const bf16 *Wi_h, *Wi_l, *Wh_h, *Wh_l, *x_h, *x_l;
+      int64_t ldwi, ldwh, ldx;
+      const float* bperm;
+      RAU_TRY(rows_pack_lstm(ctx, Pr + L[layer].Wi, Hq, in, RAU_GATES_IFOG, x3, &Wi_h, &Wi_l, &ldwi));
+      RAU_TRY(rows_pack_lstm(ctx, Pr + L[layer].Wh, Hq, Hq, RAU_GATES_IFOG, x3, &Wh_h, &Wh_l, &ldwh));
+      RAU_TRY(rows_perm_lstm_bias(ctx, Pr + L[layer].bi, Pr + L[layer].bh, Hq, RAU_GATES_IFOG, &bperm));
+      float* Gx = layer == 0 ? en->G1x : en->G2x;
+      if (layer == 1)   // u2 = drop(h1) for every step (D:38-39)
+        RAU_TRY(k_dropout(ctx, en->S_all + (size_t)B * Q + Hq, (int64_t)Tm * B, Hq, Q, dr ? en->rbits : nullptr,
+                          drop_scale(cfg->p_rnn), en->u2, Hq, nullptr, 0, Hq));
+      RAU_TRY(rows_pack2d(ctx, layer == 0 ? en->e_all : en->u2, in, Tm * B, in, x3, false, "enc.x", &x_h, &x_l, &ldx));
+      {   // input projection of every step at once, columns in the permuted gate order
+        RowsGemm g;
+        g.M = Tm * B; g.N = G4; g.K = in;
+        g.A.hi = x_h; g.A.lo = x_l; g.A.ld = ldx;
+        g.B.hi = Wi_h; g.B.lo = Wi_l; g.B.ld = ldwi;
+        g.epi = ROWS_EPI_LINEAR; g.bias = bperm; g.out_f = Gx; g.ldo = G4;
+        RAU_TRY(rows_gemm(ctx, g));
+      }
+      RAU_CHECK_CUDA(cudaMemsetAsync(hpk_hi, 0, hb * sizeof(bf16), ctx->stream));
+      if (x3) RAU_CHECK_CUDA(cudaMemsetAsync(hpk_lo, 0, hb * sizeof(bf16), ctx->stream));
+      for (int t = 1; t <= Tm; ++t) {
+        float* Sp_ = en->S_all + (size_t)(t - 1) * B * Q + 2 * layer * Hq;
+        float* Sn = en->S_all + (size_t)t * B * Q + 2 * layer * Hq;
+        RowsGemm g;
+        g.M = B; g.N = G4; g.K = Hq;
+        g.A.hi = hpk_hi + (size_t)(t - 1) * hb; g.A.lo = x3 ? hpk_lo + (size_t)(t - 1) * hb : nullptr; g.A.ld = Hq;
+        g.B.hi = Wh_h; g.B.lo = Wh_l; g.B.ld = ldwh;
+        g.epi = ROWS_EPI_LSTM;
+        g.addend = Gx + (size_t)(t - 1) * B * G4; g.ldadd = G4;
+        g.c_prev = Sp_; g.ldcp = Q; g.c_out = Sn; g.ldc = Q; g.h_out = Sn + Hq; g.ldh = Q;
+        g.lsaved = (layer == 0 ? en->sav1 : en->sav2) + (size_t)(t - 1) * 5 * B * Hq;
+        g.hpk_hi = hpk_hi + (size_t)t * hb; g.hpk_lo = x3 ? hpk_lo + (size_t)t * hb : nullptr; g.ldhp = Hq;
+        RAU_TRY(rows_gemm(ctx, g));
+      }
+    }
+    RAU_TRY(k_select_state(ctx, en->S_all, Tm, B, Q, bt->lengths, en->rnn_out));
+    return RAU_OK;
+  }
   for (int t = 1; t <= Tm; ++t) {   // layer 1 recurrence
     float* Sp_ = en->S_all + (size_t)(t - 1) * B * Q;
     float* Sn = en->S_all + (size_t)t * B * Q;
@@ -219,9 +269,11 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   for (int g = 0; g < 3; ++g)   // F:446-448
     RAU_TRY(k_fill(ctx, grads[g], rau_group_size(cfg, g), 0.0f));
 
+  rau_phase_mark(ctx, "begin");
   Encoder en;
   RAU_TRY(encoder_alloc(ctx, cfg, B, &en));
   RAU_TRY(encoder_forward(ctx, cfg, bt, params[0], params[1], train, masks, step_t, &en));
+  rau_phase_mark(ctx, "encoder forward");
 
   // answering units (F:495-537)
   const size_t sv_bytes = hop_saved_layout(cfg, B, nullptr, nullptr);
@@ -246,9 +298,30 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   RAU_TRY(k_fill(ctx, loss_dp, nHop, 0.0f));
   MultT<const float*> P = mult_views<const float*, const float>(cfg, params[2]);
   MultT<float*> G = mult_views<float*, float>(cfg, grads[2]);
+  // small saved activations and backward scratch as tensor-major stacks [nHop][B][dim]: the nn.Linear weight gradients
+  // of all hops are then single contractions over nHop*B rows (hop_wgrads)
+  const int M_ = cfg->M, A_ = cfg->A;
+  ARENA(st_qd, float, "stack.qd", (size_t)nHop * B * Q);
+  ARENA(st_qf, float, "stack.qf", (size_t)nHop * B * M_);
+  ARENA(st_j, float, "stack.j", (size_t)nHop * B * M_);
+  ARENA(st_m, float, "stack.m", (size_t)nHop * B * M_);
+  ARENA(st_du, float, "stack.du", (size_t)nHop * B * M_);
+  ARENA(st_dG, float, "stack.dG", (size_t)nHop * B * 4 * H);
+  ARENA(st_dj, float, "stack.dj", (size_t)nHop * B * M_);
+  ARENA(st_ds, float, "stack.ds", (size_t)nHop * B * S);
+  ARENA(st_dqa, float, "stack.dqa", (size_t)nHop * B * A_);
+  ARENA(st_dpre, float, "stack.dpre", (size_t)nHop * B * M_);
+  ARENA(st_gwsp, float, "stack.gwsp", (size_t)nHop * B * A_);
   std::vector<HopSaved> sv(nHop);
   for (int hp = 0; hp < nHop; ++hp) {
     hop_saved_layout(cfg, B, sv_base + sv_bytes * hp, &sv[hp]);
+    sv[hp].qd = st_qd + (size_t)hp * B * Q;
+    sv[hp].qf = st_qf + (size_t)hp * B * M_;
+    sv[hp].p = att + (size_t)hp * B * S;                 // the module outputs double as the saved copies
+    sv[hp].j = st_j + (size_t)hp * B * M_;
+    sv[hp].hout = h_all + (size_t)(hp + 1) * B * H;
+    sv[hp].dop = dop + (size_t)hp * B;
+    sv[hp].m = st_m + (size_t)hp * B * M_;
     RAU_TRY(rau_prepare_mask(ctx, sv[hp].qbits, (int64_t)B * Q, cfg->p_q, train,
                              masks && masks->q ? masks->q + (size_t)hp * B * Q : nullptr, stream_of(step_t, SK_Q, hp, rank)));
     RAU_TRY(rau_prepare_mask(ctx, sv[hp].xbits, (int64_t)B * cfg->C * S, cfg->p_x, train,
@@ -265,10 +338,12 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     RAU_TRY(k_softmax_ce(ctx, B, N, scores + (size_t)hp * B * N, bt->labels, 1.0f / Bg, hm / Bg, loss + hp,
                          dscore + (size_t)hp * B * N, nullptr, 0, ans + (size_t)hp * B));
   }
+  rau_phase_mark(ctx, "answering units forward");
   // logging-only losses on the averaged / selected predictions and the do_pred BCE (F:539-574)
   RAU_TRY(k_merge_preds(ctx, nHop, B, N, S, scores, dop, nullptr, bt->labels, ans, 0, 1.0f / Bg, loss + nHop, loss_dp,
                         ans + (size_t)nHop * B, nullptr, nullptr, nullptr, nullptr));
 
+  rau_phase_mark(ctx, "merged losses");
   // BPTT through the hops (F:578-597); do_pred and attprob receive zero gradient (F:582-583, F:592)
   ARENA(dcs, float, "step.dc", (size_t)2 * B * H);
   ARENA(dhs, float, "step.dh", (size_t)2 * B * H);
@@ -277,11 +352,25 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     const bool last = hp == nHop - 1;
     const float* dc_in = last ? nullptr : dcs + (size_t)((hp + 1) & 1) * B * H;
     const float* dh_in = last ? nullptr : dhs + (size_t)((hp + 1) & 1) * B * H;
+    HopGrads hg;
+    hg.du = st_du + (size_t)hp * B * M_; hg.dG = st_dG + (size_t)hp * B * 4 * H; hg.dj = st_dj + (size_t)hp * B * M_;
+    hg.ds = st_ds + (size_t)hp * B * S; hg.dqa = st_dqa + (size_t)hp * B * A_; hg.dpre = st_dpre + (size_t)hp * B * M_;
+    hg.gwsp = st_gwsp + (size_t)hp * B * A_;
     RAU_TRY(hop_backward(ctx, cfg, B, P, G, bt->feats, c_all + (size_t)hp * B * H, h_all + (size_t)hp * B * H, train, sv[hp],
                          dscore + (size_t)hp * B * N, nullptr, nullptr, dc_in, dh_in, dq, last ? 0 : 1, nullptr,
-                         dcs + (size_t)(hp & 1) * B * H, dhs + (size_t)(hp & 1) * B * H));
+                         dcs + (size_t)(hp & 1) * B * H, dhs + (size_t)(hp & 1) * B * H, &hg));
   }
+  rau_phase_mark(ctx, "answering units backward");
+  {
+    HopStacks st;
+    st.dscore = dscore; st.m = st_m; st.du = st_du; st.hout = h_all + (size_t)B * H; st.dG = st_dG; st.j = st_j; st.h_in = h_all;
+    st.dj = st_dj; st.p = att; st.ds = st_ds; st.dqa = st_dqa; st.qf = st_qf; st.dpre = st_dpre; st.qd = st_qd;
+    st.gwsp = st_gwsp;
+    RAU_TRY(hop_wgrads(ctx, cfg, nHop * B, G, st));
+  }
+  rau_phase_mark(ctx, "unit weight gradients");
   RAU_TRY(encoder_backward(ctx, cfg, bt, params[1], grads[0], grads[1], train, &en, dq));
+  rau_phase_mark(ctx, "encoder backward");
   return RAU_OK;
 }
 
@@ -351,6 +440,7 @@ static int train_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     RAU_TRY(k_clip_optim(ctx, hp->optim, rau_group_size(cfg, g), params[g], grads[g], norm2 + g, hp->clip, hp->lr[g], hp->h0,
                          hp->h1, hp->h2, opt_state ? opt_state[g][0] : nullptr, opt_state ? opt_state[g][1] : nullptr, 1,
                          (out && out->norms) ? out->norms + g : nullptr, g));
+  rau_phase_mark(ctx, "noise + clip + optimizer");
   return RAU_OK;
 }
 
@@ -378,7 +468,8 @@ int rau_train_step(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, flo
   // whole-step CUDA graph: after two eager runs with identical arguments (every arena buffer is then sized), the
   // enqueue sequence is captured once and replayed; only the StepState upload above changes between replays
   RauGraph& gr = ctx->graph;
-  const bool graphable = !gr.disabled && masks == nullptr && hp->noise_override == nullptr;
+  if (ctx->phases < 0) rau_phase_mark(ctx, "init");
+  const bool graphable = !gr.disabled && masks == nullptr && hp->noise_override == nullptr && ctx->phases <= 0;
   std::vector<uint64_t> key;
   RauGraphEntry* ent = nullptr;
   if (graphable) {
