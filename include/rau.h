@@ -252,6 +252,10 @@ int rau_gemm(rau_ctx* ctx, int M, int N, int K, const float* A, int lda, int ta,
  * multiples of 8 floats.  reduce != 0: split-K partial sums are ADDED into D (TMA reduce-add), else D is overwritten. */
 int rau_rows_gemm(rau_ctx* ctx, int M, int N, int K, const float* A, int lda, int a_mn,
                   const float* B, int ldb, int b_mn, float* D, int ldd, int reduce);
+/* debugging aid (RAU_ROWS_TRACE=1): copies the per-CTA clock stamps [148][16] of the last rows-engine launch to HOST
+ * memory `out` (n 64-bit words): 0 start, 1 prologue done, 2 first TMA issue, 3/4 first/second stage landed, 5 MMAs
+ * of the first item issued, 6 first accumulator ready, 7 epilogue issued, 8 stores drained, 9 end */
+int rau_rows_trace(rau_ctx* ctx, uint64_t* out, int n);
 /* softmax cross-entropy of score[B,N] against 1-based labels: loss_sum += scale*sum_b nll_b,
  * dscore = scale*(softmax - onehot), answers = argmax (1-based, ties -> lowest index). */
 int rau_softmax_ce(rau_ctx* ctx, int B, int N, const float* score, const float* labels, float scale,

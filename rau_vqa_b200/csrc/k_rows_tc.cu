@@ -27,7 +27,7 @@ namespace {
 
 constexpr int RT_BM = 128, RT_BN = 256;
 constexpr int RT_STAGE = 48 * 1024;
-constexpr int RT_THREADS = 320;          // producer + MMA issuer + 8 epilogue warps
+constexpr int RT_THREADS = 352;          // A producer, MMA issuer, 8 epilogue warps, B producer
 constexpr int RT_STG_WARP = 4096;          // per epilogue warp: one 32 x 128 B (fp32) or two 32 x 64 B (bf16 hi, lo) buffers
 constexpr int RT_MAXSTAGES = 8;
 constexpr int RT_SMEM_BUDGET = 4 * RT_STAGE + 8 * RT_STG_WARP;   // pipeline + staging bytes a CTA may use (224 KB)
@@ -41,6 +41,7 @@ struct RtParams {
   int M, N, K;
   int a_mn, b_mn, x3, BK, nkb;
   int nkb1;                        // k-blocks of the first segment (== nkb without a second segment)
+  int a_swap, b_swap;              // bf16x3: plane 0 of the operand's 3-D box is the lo array (lo lies below hi in memory)
   int BN;                          // accumulator columns per tile: 64, 128 or 256
   int stg_warp;                    // staging bytes per epilogue warp
   int out_f, out_hi;               // EPI_LINEAR: which outputs exist
@@ -48,6 +49,7 @@ struct RtParams {
   const float* addend; const float* addend2; long long ldadd;   // [M, ldadd]
   int act;                         // EPI_LINEAR: 0 none, 1 tanh, 2 sigmoid
   int vec;                         // EPI_LINEAR: bias / addend pointers are 16-byte aligned and N % 32 == 0
+  unsigned long long* dbg;         // RAU_ROWS_TRACE: per-CTA clock stamps [16] (tools/rows_trace.py), else NULL
   // EPI_LSTM: the cell update fused behind the gate product (A:12-25, D:47-61).  Accumulator columns are permuted gate
   // pre-activations: every 32-column chunk holds (i, f, o, g) of 8 consecutive hidden units.
   const float* c_prev; long long ldcp;         // [M, H] (NULL = zeros)
@@ -92,11 +94,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
+// one lane of a converged warp (the CUTLASS elect_one_sync idiom): lets the compiler keep the surrounding loop
+// warp-uniform, so the single-thread TMA / MMA instructions are issued without a per-instruction lane loop
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred;
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
           smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
@@ -222,7 +243,7 @@ __device__ __forceinline__ float warp_transpose_sum32(float* x, int lane) {
   return x[0];
 }
 
-template <int EPI>
+template <int EPI, int X3, int NSTEPS>
 __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_constant__ RtParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t full_bar[RT_MAXSTAGES], empty_bar[RT_MAXSTAGES], tfull_bar[2], tempty_bar[2];
@@ -231,9 +252,12 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
   uint8_t* staging = smem + (size_t)p.stages * p.stage_bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int items = p.tiles_m * p.tiles_n * p.ksplit;
+  unsigned long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 16 : nullptr;
+#define RT_STAMP(slot) do { if (dbg) dbg[slot] = clock64(); } while (0)
+  if (threadIdx.x == 0) RT_STAMP(0);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -251,63 +275,76 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
+  if (threadIdx.x == 0) RT_STAMP(1);   // prologue done
 
   const uint32_t a_bytes = (uint32_t)RT_BM * p.BK * 2, b_bytes = (uint32_t)p.BN * p.BK * 2;
-  const int nt = p.x3 ? 2 : 1;
+  constexpr int nt = X3 ? 2 : 1;
 
-  if (warp == 0) {
-    // ===================== TMA producer
-    if (lane == 0) {
+  if (warp == 0 || warp == 10) {
+    // ===================== TMA producers: warp 0 feeds operand A, warp 10 operand B (one thread issues roughly one
+    // cp.async.bulk.tensor per 250 cycles, so the two operands are issued from different warps, and the hi and lo
+    // tiles of the bf16x3 split travel as the two planes of ONE 3-D box)
+    {
+      const bool isB = warp == 10;
+      const int mn = isB ? p.b_mn : p.a_mn;
+      const uint32_t my_bytes = nt * (isB ? b_bytes : a_bytes);
+      const int nchunk = (isB ? p.BN : RT_BM) / 64;
       uint32_t it = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int ks = item % p.ksplit;
         const int tile = item / p.ksplit;
         const int tn = tile % p.tiles_n, tm = tile / p.tiles_n;
-        const int m0 = tm * RT_BM, n0 = tn * p.BN;
+        const int r0 = isB ? tn * p.BN : tm * RT_BM;
         const int kb0 = ks * p.kb_per, kb1 = min(p.nkb, kb0 + p.kb_per);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const bool seg2 = kb >= p.nkb1;
-          const CUtensorMap* mA = seg2 ? p.mapA2 : p.mapA;
-          const CUtensorMap* mB = seg2 ? p.mapB2 : p.mapB;
+          const CUtensorMap* map = isB ? (seg2 ? &p.mapB2[0] : &p.mapB[0]) : (seg2 ? &p.mapA2[0] : &p.mapA[0]);
           const int st = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1u;
           mbar_wait(&empty_bar[st], ph ^ 1u);
-          uint8_t* sa = smem + (size_t)st * p.stage_bytes;
-          uint8_t* sb = sa + nt * a_bytes;
-          mbar_expect_tx(&full_bar[st], nt * (a_bytes + b_bytes));
-          const int k0 = (seg2 ? kb - p.nkb1 : kb) * p.BK;
-          for (int h = 0; h < nt; ++h) {
-            if (p.a_mn) {   // boxes of 64 rows-of-A (contiguous) x BK k
-#pragma unroll
-              for (int u = 0; u < RT_BM / 64; ++u)
-                tma_load_2d(sa + h * a_bytes + u * (p.BK * 128), &mA[h], &full_bar[st], m0 + 64 * u, k0);
+          if (elect_one()) {
+            if (it == 0 && !isB) RT_STAMP(2);      // first TMA about to issue
+            uint8_t* dst = smem + (size_t)st * p.stage_bytes + (isB ? nt * a_bytes : 0);
+            mbar_expect_tx(&full_bar[st], my_bytes);
+            const int k0 = (seg2 ? kb - p.nkb1 : kb) * p.BK;
+            if (mn) {   // boxes of 64 rows (contiguous) x BK k [x 2 planes]
+              for (int u = 0; u < nchunk; ++u) {
+                if (X3) tma_load_3d(dst + u * (nt * p.BK * 128), map, &full_bar[st], r0 + 64 * u, k0, 0);
+                else tma_load_2d(dst + u * (p.BK * 128), map, &full_bar[st], r0 + 64 * u, k0);
+              }
             } else {
-              tma_load_2d(sa + h * a_bytes, &mA[h], &full_bar[st], k0, m0);
+              if (X3) tma_load_3d(dst, map, &full_bar[st], k0, r0, 0);
+              else tma_load_2d(dst, map, &full_bar[st], k0, r0);
             }
-            if (p.b_mn) {
-              for (int u = 0; u < p.BN / 64; ++u)
-                tma_load_2d(sb + h * b_bytes + u * (p.BK * 128), &mB[h], &full_bar[st], n0 + 64 * u, k0);
-            } else {
-              tma_load_2d(sb + h * b_bytes, &mB[h], &full_bar[st], k0, n0);
-            }
+            if (it == 0 && !isB) RT_STAMP(10);     // stage 0 fully issued
+            if (it == 1 && !isB) RT_STAMP(11);     // stage 1 fully issued
+            if (it == 7 && !isB) RT_STAMP(13);     // stage 7 fully issued
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer
-    if (lane == 0) {
+    // ===================== MMA issuer: the warp walks the loops converged, one elected lane issues
+    {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6) | A=bf16 [7,10) | B=bf16 [10,13) |
       // a_major [15] | b_major [16] | N>>3 [17,23) | M>>4 [24,29)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
                              ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(RT_BM >> 4) << 24);
       // K-major tile: rows of BK*2 bytes (64 B -> SWIZZLE_64B, 128 B -> SWIZZLE_128B), 8-row groups SBO apart; a 16-k
       //   step is +32 bytes inside the swizzled row.
-      // MN-major tile: 64-wide chunks BK*128 bytes apart (LBO), 8-k-row groups 1024 bytes apart (SBO), SWIZZLE_128B;
-      //   a 16-k step is 16 rows = 2048 bytes.
-      const uint32_t k_layout = p.BK == 32 ? 4u : 2u, k_sbo = p.BK == 32 ? 512u : 1024u;
-      const uint32_t a_step = p.a_mn ? (2048u >> 4) : (32u >> 4), b_step = p.b_mn ? (2048u >> 4) : (32u >> 4);
-      const int nsteps = p.BK / 16;
+      // MN-major tile: 64-wide chunks (LBO apart), 8-k-row groups 1024 bytes apart (SBO), SWIZZLE_128B; a 16-k step is
+      //   16 rows = 2048 bytes.
+      constexpr uint32_t BK_ = NSTEPS * 16;
+      constexpr uint32_t k_layout = BK_ == 32 ? 4u : 2u, k_sbo = BK_ == 32 ? 512u : 1024u;
+      constexpr uint32_t mn_chunk = BK_ * 128u;
+      constexpr uint32_t NT = X3 ? 2u : 1u;
+      const uint64_t a_step = p.a_mn ? (2048u >> 4) : (32u >> 4), b_step = p.b_mn ? (2048u >> 4) : (32u >> 4);
+      // plane 0 / plane 1 of an operand's box: K-major tiles a_bytes (b_bytes) apart; MN-major chunks interleave the
+      // planes, so a chunk pitch (LBO) spans both and plane 1 starts BK*128 bytes in.  p.a_swap: plane 0 is `lo`.
+      const uint64_t a_p1 = (uint64_t)((p.a_mn ? mn_chunk : a_bytes) >> 4), b_p1 = (uint64_t)((p.b_mn ? mn_chunk : b_bytes) >> 4);
+      const uint64_t a_hi_off = p.a_swap ? a_p1 : 0, a_lo_off = p.a_swap ? 0 : a_p1;
+      const uint64_t b_hi_off = p.b_swap ? b_p1 : 0, b_lo_off = p.b_swap ? 0 : b_p1;
       uint32_t it = 0, li = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
         const int ks = item % p.ksplit;
@@ -321,22 +358,35 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
           const uint32_t ph = (it / p.stages) & 1u;
           mbar_wait(&full_bar[st], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sa = smem_u32(smem + (size_t)st * p.stage_bytes);
-          const uint32_t sb = sa + nt * a_bytes;
-          const uint64_t da_hi = p.a_mn ? make_desc(sa, (uint32_t)p.BK * 128u, 1024u, 2u) : make_desc(sa, 16u, k_sbo, k_layout);
-          const uint64_t db_hi = p.b_mn ? make_desc(sb, (uint32_t)p.BK * 128u, 1024u, 2u) : make_desc(sb, 16u, k_sbo, k_layout);
-          const uint64_t da_lo = da_hi + (uint64_t)(a_bytes >> 4), db_lo = db_hi + (uint64_t)(b_bytes >> 4);
-          for (int k = 0; k < nsteps; ++k) {
-            const uint64_t oa = (uint64_t)(k * a_step), ob = (uint64_t)(k * b_step);
-            umma_f16(dcol, da_hi + oa, db_hi + ob, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            if (p.x3) {
-              umma_f16(dcol, da_hi + oa, db_lo + ob, idesc, 1u);
-              umma_f16(dcol, da_lo + oa, db_hi + ob, idesc, 1u);
+          if (elect_one()) {
+            if (it == 0) RT_STAMP(3);      // first stage landed
+            if (it == 1) RT_STAMP(4);      // second stage landed
+            const uint32_t sa = smem_u32(smem + (size_t)st * p.stage_bytes);
+            const uint32_t sb = sa + NT * a_bytes;
+            const uint64_t da0 = p.a_mn ? make_desc(sa, NT * mn_chunk, 1024u, 2u) : make_desc(sa, 16u, k_sbo, k_layout);
+            const uint64_t db0 = p.b_mn ? make_desc(sb, NT * mn_chunk, 1024u, 2u) : make_desc(sb, 16u, k_sbo, k_layout);
+            const uint64_t da_hi = da0 + a_hi_off, da_lo = da0 + a_lo_off, db_hi = db0 + b_hi_off, db_lo = db0 + b_lo_off;
+            const uint32_t acc0 = kb > kb0 ? 1u : 0u;
+#pragma unroll
+            for (int k = 0; k < NSTEPS; ++k) {
+              const uint64_t oa = (uint64_t)k * a_step, ob = (uint64_t)k * b_step;
+              umma_f16(dcol, da_hi + oa, db_hi + ob, idesc, k == 0 ? acc0 : 1u);
+              if (X3) {
+                umma_f16(dcol, da_hi + oa, db_lo + ob, idesc, 1u);
+                umma_f16(dcol, da_lo + oa, db_hi + ob, idesc, 1u);
+              }
             }
+            umma_commit(&empty_bar[st]);     // frees the stage once these MMAs have read it
+            if (it == 0) RT_STAMP(12);       // MMAs of k-block 0 issued
+            if (it == 7) RT_STAMP(14);       // MMAs of k-block 7 issued
           }
-          umma_commit(&empty_bar[st]);     // frees the stage once these MMAs have read it
+          __syncwarp();
         }
-        umma_commit(&tfull_bar[ab]);       // accumulator of this item complete
+        if (elect_one()) {
+          umma_commit(&tfull_bar[ab]);       // accumulator of this item complete
+          if (li == 0) RT_STAMP(5);          // all MMAs of the first item issued
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -356,6 +406,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
       const int rr = r_ok ? r : p.M - 1;
       const int rowbase = m0 + q * 32;           // first row of this warp's 32-row slab
       mbar_wait(&tfull_bar[ab], aph);
+      if (li == 0 && warp == 2 && lane == 0) RT_STAMP(6);   // first accumulator ready
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ab * (uint32_t)RT_BN + ((uint32_t)(q * 32) << 16);
       float rowacc = 0.0f;
@@ -611,10 +662,13 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
       }
       if (EPI == EPI_ATT && r_ok && p.rowout && n0 + c_lo * 32 < p.N) atomicAdd(p.rowout + r, rowacc);
     }
+    if (warp == 2 && lane == 0) RT_STAMP(7);   // epilogue math + stores issued
     if (lane == 0) bulk_wait0();
+    if (warp == 2 && lane == 0) RT_STAMP(8);   // bulk stores drained
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (threadIdx.x == 0) RT_STAMP(9);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
@@ -662,26 +716,55 @@ int encode_2d(CUtensorMap* m, CUtensorMapDataType dt, int esize, const void* bas
   return RAU_OK;
 }
 
-int encode_operand(CUtensorMap* m, const bf16* base, int mn, int rows, int K, int64_t ld, int BK, int box_rows) {
-  if (mn)   // stored [K, rows]: boxes of 64 rows (contiguous) x BK k
-    return encode_2d(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, (uint64_t)rows, (uint64_t)K, (uint64_t)ld, 64, (uint32_t)BK,
-                     CU_TENSOR_MAP_SWIZZLE_128B);
-  return encode_2d(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, (uint64_t)K, (uint64_t)rows, (uint64_t)ld, (uint32_t)BK,
-                   (uint32_t)box_rows, BK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+// operand tiles: 2-D over one bf16 array, or (bf16x3) 3-D over the hi and lo arrays as two planes `plane` bytes apart
+int encode_operand(CUtensorMap* m, const bf16* hi, const bf16* lo, int* swap, int mn, int rows, int K, int64_t ld, int BK,
+                   int box_rows) {
+  const uint64_t d0 = mn ? (uint64_t)rows : (uint64_t)K, d1 = mn ? (uint64_t)K : (uint64_t)rows;
+  const uint32_t b0 = mn ? 64u : (uint32_t)BK, b1 = mn ? (uint32_t)BK : (uint32_t)box_rows;
+  const CUtensorMapSwizzle sw = (mn || BK == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  *swap = 0;
+  if (lo == nullptr) return encode_2d(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, hi, d0, d1, (uint64_t)ld, b0, b1, sw);
+  const bf16* base = hi;
+  if (lo < hi) { base = lo; *swap = 1; }
+  const uint64_t plane = (uint64_t)((const char*)(*swap ? hi : lo) - (const char*)base);
+  if (plane % 16 != 0 || plane >= (1ull << 40)) {
+    rau_set_error("rows_gemm: the hi and lo arrays of an operand are %llu bytes apart (need a multiple of 16 below 2^40)",
+                  (unsigned long long)plane);
+    return RAU_EINVAL;
+  }
+  cuuint64_t dims[3] = {d0, d1, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, plane};
+  cuuint32_t box[3] = {b0, b1, 2};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    rau_set_error("cuTensorMapEncodeTiled (3-D operand) failed (%d): dims=%llu,%llu ld=%lld plane=%llu box=%u,%u", (int)r,
+                  (unsigned long long)d0, (unsigned long long)d1, (long long)ld, (unsigned long long)plane, b0, b1);
+    return RAU_ECUDA;
+  }
+  return RAU_OK;
 }
 
 bool g_attr_done[8] = {false, false, false, false, false, false, false, false};
 
-template <int EPI>
-int launch_rows(rau_ctx* ctx, const RtParams& p, int grid, int smem_bytes) {
-  if (!g_attr_done[EPI]) {
-    RAU_CHECK_CUDA(cudaFuncSetAttribute(rows_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <int EPI, int X3, int NSTEPS>
+int launch_rows_v(rau_ctx* ctx, const RtParams& p, int grid, int smem_bytes) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    RAU_CHECK_CUDA(cudaFuncSetAttribute(rows_gemm_kernel<EPI, X3, NSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         RT_SMEM_BUDGET + 1024));
-    g_attr_done[EPI] = true;
+    attr_done = true;
   }
-  rows_gemm_kernel<EPI><<<grid, RT_THREADS, smem_bytes, ctx->stream>>>(p);
+  rows_gemm_kernel<EPI, X3, NSTEPS><<<grid, RT_THREADS, smem_bytes, ctx->stream>>>(p);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
+}
+// variants: bf16x3 with 32-wide k-blocks (256-column tiles) or 64-wide (narrow tiles); single-pass bf16 with 64-wide
+template <int EPI>
+int launch_rows(rau_ctx* ctx, const RtParams& p, int grid, int smem_bytes) {
+  if (p.x3) return p.BK == 32 ? launch_rows_v<EPI, 1, 2>(ctx, p, grid, smem_bytes) : launch_rows_v<EPI, 1, 4>(ctx, p, grid, smem_bytes);
+  return launch_rows_v<EPI, 0, 4>(ctx, p, grid, smem_bytes);
 }
 
 __global__ void pack_hilo_kernel(const float* __restrict__ in, int64_t n4, bf16* __restrict__ hi, bf16* __restrict__ lo) {
@@ -890,19 +973,7 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.a_mn = g.A.mn; p.b_mn = g.B.mn;
   p.x3 = g.A.lo ? 1 : 0;
-  p.BK = p.x3 ? 32 : 64;
-  p.nkb = (g.K + p.BK - 1) / p.BK;
   p.tiles_m = (g.M + RT_BM - 1) / RT_BM;
-  const bool seg2 = g.K2 > 0;
-  if (seg2) {
-    RAU_REQUIRE(g.A2.hi && g.B2.hi && g.A2.mn == g.A.mn && g.B2.mn == g.B.mn && (g.A2.lo != nullptr) == (g.A.lo != nullptr) &&
-                    (g.B2.lo != nullptr) == (g.B.lo != nullptr) && g.A2.ld % 8 == 0 && g.B2.ld % 8 == 0,
-                "rows_gemm: bad second K segment");
-    RAU_REQUIRE((((uintptr_t)g.A2.hi | (uintptr_t)g.B2.hi | (uintptr_t)g.A2.lo | (uintptr_t)g.B2.lo) & 15) == 0,
-                "rows_gemm: operands must be 16-byte aligned");
-  }
-  p.nkb1 = p.nkb;
-  if (seg2) p.nkb += (g.K2 + p.BK - 1) / p.BK;
   // accumulator width: whole 256-column tiles when there is enough work to fill the SMs, narrower tiles for the skinny
   // nn.Linear products (M = batch rows) so that more CTAs share the latency-bound work
   int BN = g.BN;
@@ -915,6 +986,20 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   RAU_REQUIRE(BN == 64 || BN == 128 || BN == 256, "rows_gemm: BN = %d", BN);
   p.BN = BN;
   p.tiles_n = (g.N + BN - 1) / BN;
+  // k elements per stage: one TMA instruction costs its issuing thread ~250 cycles whatever the box size, so the narrow
+  // tiles (little MMA time per k-block) take 64-wide k-blocks even in bf16x3; 256-wide bf16x3 tiles keep 48 KB stages
+  p.BK = (p.x3 && BN == 256) ? 32 : 64;
+  p.nkb = (g.K + p.BK - 1) / p.BK;
+  const bool seg2 = g.K2 > 0;
+  if (seg2) {
+    RAU_REQUIRE(g.A2.hi && g.B2.hi && g.A2.mn == g.A.mn && g.B2.mn == g.B.mn && (g.A2.lo != nullptr) == (g.A.lo != nullptr) &&
+                    (g.B2.lo != nullptr) == (g.B.lo != nullptr) && g.A2.ld % 8 == 0 && g.B2.ld % 8 == 0,
+                "rows_gemm: bad second K segment");
+    RAU_REQUIRE((((uintptr_t)g.A2.hi | (uintptr_t)g.B2.hi | (uintptr_t)g.A2.lo | (uintptr_t)g.B2.lo) & 15) == 0,
+                "rows_gemm: operands must be 16-byte aligned");
+  }
+  p.nkb1 = p.nkb;
+  if (seg2) p.nkb += (g.K2 + p.BK - 1) / p.BK;
   // shared memory: 8 staging buffers for the epilogue warps + as many operand stages as fit (latency-bound skinny
   // products want many small stages in flight, the big ones four 48 KB stages)
   p.stg_warp = (g.epi == EPI_LINEAR && g.out_hi) ? 8192 : RT_STG_WARP;
@@ -931,13 +1016,13 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   }
   p.kb_per = (p.nkb + p.ksplit - 1) / p.ksplit;
   p.ksplit = (p.nkb + p.kb_per - 1) / p.kb_per;
-  for (int h = 0; h < (p.x3 ? 2 : 1); ++h) {
-    RAU_TRY(encode_operand(&p.mapA[h], h ? g.A.lo : g.A.hi, g.A.mn, g.M, g.K, g.A.ld, p.BK, RT_BM));
-    RAU_TRY(encode_operand(&p.mapB[h], h ? g.B.lo : g.B.hi, g.B.mn, g.N, g.K, g.B.ld, p.BK, BN));
-    if (seg2) {
-      RAU_TRY(encode_operand(&p.mapA2[h], h ? g.A2.lo : g.A2.hi, g.A2.mn, g.M, g.K2, g.A2.ld, p.BK, RT_BM));
-      RAU_TRY(encode_operand(&p.mapB2[h], h ? g.B2.lo : g.B2.hi, g.B2.mn, g.N, g.K2, g.B2.ld, p.BK, BN));
-    }
+  RAU_TRY(encode_operand(&p.mapA[0], g.A.hi, g.A.lo, &p.a_swap, g.A.mn, g.M, g.K, g.A.ld, p.BK, RT_BM));
+  RAU_TRY(encode_operand(&p.mapB[0], g.B.hi, g.B.lo, &p.b_swap, g.B.mn, g.N, g.K, g.B.ld, p.BK, BN));
+  if (seg2) {
+    int sa2 = 0, sb2 = 0;
+    RAU_TRY(encode_operand(&p.mapA2[0], g.A2.hi, g.A2.lo, &sa2, g.A2.mn, g.M, g.K2, g.A2.ld, p.BK, RT_BM));
+    RAU_TRY(encode_operand(&p.mapB2[0], g.B2.hi, g.B2.lo, &sb2, g.B2.mn, g.N, g.K2, g.B2.ld, p.BK, BN));
+    RAU_REQUIRE(sa2 == p.a_swap && sb2 == p.b_swap, "rows_gemm: the two K segments order their hi/lo arrays differently");
   }
   const bool f32_out = g.epi == EPI_PLAIN || g.epi == EPI_RED || g.epi == EPI_ATT;
   if (g.epi == EPI_LINEAR) {
@@ -997,6 +1082,16 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   p.fast_tanh = p.x3 ? 0 : 1;   // single-pass bf16: the result is rounded to bf16 anyway, MUFU.TANH (2^-11) is below that
   const int items = tiles * p.ksplit;
   const int grid = items < ctx->sm_count ? items : ctx->sm_count;
+  {
+    static int trace = -1;
+    if (trace < 0) { const char* e = getenv("RAU_ROWS_TRACE"); trace = e ? atoi(e) : 0; }
+    if (trace) {   // debugging aid: the stamps of the LAST launch are left in the arena buffer "rows.trace"
+      void* buf = nullptr;
+      RAU_TRY(ctx->arena.get("rows.trace", sizeof(unsigned long long) * 16 * 148, &buf));
+      RAU_CHECK_CUDA(cudaMemsetAsync(buf, 0, sizeof(unsigned long long) * 16 * 148, ctx->stream));
+      p.dbg = (unsigned long long*)buf;
+    }
+  }
   const int smem_bytes = p.stages * p.stage_bytes + 8 * p.stg_warp + 1024;
   switch (g.epi) {
     case EPI_PLAIN: return launch_rows<EPI_PLAIN>(ctx, p, grid, smem_bytes);

@@ -706,6 +706,15 @@ int rau_rows_gemm(rau_ctx* ctx, int M, int N, int K, const float* A, int lda, in
   return rows_gemm(ctx, g);
 }
 
+int rau_rows_trace(rau_ctx* ctx, uint64_t* out, int n) {
+  RAU_REQUIRE(ctx && out && n > 0, "bad arguments");
+  void* buf = nullptr;
+  RAU_TRY(ctx->arena.get("rows.trace", sizeof(unsigned long long) * 16 * 148, &buf));
+  RAU_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  RAU_CHECK_CUDA(cudaMemcpy(out, buf, sizeof(uint64_t) * (size_t)(n < 16 * 148 ? n : 16 * 148), cudaMemcpyDeviceToHost));
+  return RAU_OK;
+}
+
 int rau_softmax_ce(rau_ctx* ctx, int B, int N, const float* score, const float* labels, float scale, float* loss_sum,
                    float* dscore, float* answers) {
   RAU_REQUIRE(ctx, "ctx == NULL");
