@@ -115,7 +115,8 @@ __global__ void lstm_bwd_kernel(int B, int H, int order, const float* __restrict
                                 const float* __restrict__ lengths, int t, const float* __restrict__ dq_c,
                                 const float* __restrict__ dq_h, int lddq,
                                 const float* __restrict__ c_prev, int ldcp, const float* __restrict__ saved,
-                                float* __restrict__ dG, bf16* __restrict__ dG_b, float* __restrict__ dc_prev, int lddcp) {
+                                float* __restrict__ dG, bf16* __restrict__ dG_b, float* __restrict__ dc_prev, int lddcp,
+                                bf16* __restrict__ dG_lo) {
   int ci, cf, co, cg;
   gate_chunks(order, ci, cf, co, cg);
   const int64_t total = (int64_t)B * H, plane = total;
@@ -144,6 +145,12 @@ __global__ void lstm_bwd_kernel(int B, int H, int order, const float* __restrict
     if (dG_b) {
       dG_b[row + ci * H + j] = __float2bfloat16(gi); dG_b[row + cf * H + j] = __float2bfloat16(gf);
       dG_b[row + co * H + j] = __float2bfloat16(go); dG_b[row + cg * H + j] = __float2bfloat16(gg);
+      if (dG_lo) {   // bf16x3 operand: lo = bf16(x - hi)
+        dG_lo[row + ci * H + j] = __float2bfloat16(gi - __bfloat162float(__float2bfloat16(gi)));
+        dG_lo[row + cf * H + j] = __float2bfloat16(gf - __bfloat162float(__float2bfloat16(gf)));
+        dG_lo[row + co * H + j] = __float2bfloat16(go - __bfloat162float(__float2bfloat16(go)));
+        dG_lo[row + cg * H + j] = __float2bfloat16(gg - __bfloat162float(__float2bfloat16(gg)));
+      }
     }
   }
 }
@@ -260,20 +267,30 @@ __global__ void dopred_bwd_kernel(const float* __restrict__ ddo, const float* __
 }
 
 // ---------------------------------------------------------------- reductions
-// out[c] (+)= sum_r x[r, c]; block = 32 columns x 8 row-lanes
-__global__ void colsum_kernel(const float* __restrict__ x, int64_t rows, int cols, int ld, float* __restrict__ out, int accumulate) {
+// out[c] (+)= sum_r x[r, c]; block = 32 columns x 8 row-lanes; gridDim.y row slices add atomically (accumulate mode only);
+// out2 (optional) receives the same sums: the two biases of an LSTM layer (i2h, h2h) share one gradient
+__global__ void colsum_kernel(const float* __restrict__ x, int64_t rows, int cols, int ld, float* __restrict__ out, int accumulate,
+                              float* __restrict__ out2) {
   __shared__ float red[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
+  const int64_t per = (rows + gridDim.y - 1) / gridDim.y;
+  const int64_t r_lo = blockIdx.y * per, r_hi = r_lo + per < rows ? r_lo + per : rows;
   float s = 0.0f;
   if (c < cols)
-    for (int64_t r = threadIdx.y; r < rows; r += 8) s += x[r * ld + c];
+    for (int64_t r = r_lo + threadIdx.y; r < r_hi; r += 8) s += x[r * ld + c];
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && c < cols) {
     float t = 0.0f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
-    out[c] = accumulate ? out[c] + t : t;
+    if (gridDim.y > 1) {
+      atomicAdd(out + c, t);
+      if (out2) atomicAdd(out2 + c, t);
+    } else {
+      out[c] = accumulate ? out[c] + t : t;
+      if (out2) out2[c] = accumulate ? out2[c] + t : t;
+    }
   }
 }
 
@@ -352,9 +369,9 @@ int k_lstm_fwd(rau_ctx* ctx, int B, int H, int order, const float* G, int ldg, c
 }
 int k_lstm_bwd(rau_ctx* ctx, int B, int H, int order, const float* dc_out, int lddc, const float* dh_out, int lddh,
                const float* dh_extra, int ldhe, const float* lengths, int t, const float* dq_c, const float* dq_h, int lddq,
-               const float* c_prev, int ldcp, const float* saved, float* dG, bf16* dG_b, float* dc_prev, int lddcp) {
+               const float* c_prev, int ldcp, const float* saved, float* dG, bf16* dG_b, float* dc_prev, int lddcp, bf16* dG_lo) {
   lstm_bwd_kernel<<<grid_for((int64_t)B * H), TPB, 0, ctx->stream>>>(B, H, order, dc_out, lddc, dh_out, lddh, dh_extra, ldhe,
-      lengths, t, dq_c, dq_h, lddq, c_prev, ldcp, saved, dG, dG_b, dc_prev, lddcp);
+      lengths, t, dq_c, dq_h, lddq, c_prev, ldcp, saved, dG, dG_b, dc_prev, lddcp, dG_lo);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
@@ -416,8 +433,15 @@ int k_dopred_bwd(rau_ctx* ctx, const float* ddo, const float* dop, const float* 
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
-int k_colsum(rau_ctx* ctx, const float* x, int64_t rows, int cols, int ld, float* out, int accumulate) {
-  colsum_kernel<<<cdiv(cols, 32), dim3(32, 8), 0, ctx->stream>>>(x, rows, cols, ld, out, accumulate);
+int k_colsum(rau_ctx* ctx, const float* x, int64_t rows, int cols, int ld, float* out, int accumulate, float* out2) {
+  int slices = 1;
+  if (accumulate && rows >= 512) {   // enough rows to spread over the SMs
+    slices = (int)(rows / 128);
+    const int want = 148 * 4 / cdiv(cols, 32);
+    if (slices > want) slices = want;
+    if (slices < 1) slices = 1;
+  }
+  colsum_kernel<<<dim3(cdiv(cols, 32), slices), dim3(32, 8), 0, ctx->stream>>>(x, rows, cols, ld, out, accumulate, out2);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }

@@ -779,16 +779,32 @@ __global__ void pack_hilo_kernel(const float* __restrict__ in, int64_t n4, bf16*
 }
 
 // X [B, C, S] fp32 -> dropped-out features in rows layout [B*S, C] as bf16 (hi, lo); keep bit index = (b*C + c)*S + s
+// gen != 0: the keep bits are drawn here (Philox4x32-10, the same counter -> bit mapping as mask_gen_kernel: element e
+// takes lane e & 3 of the draw with counter e >> 2), so the training step needs no separate mask pass over [B, C, S]
 __global__ void __launch_bounds__(256) xprep_rows_kernel(const float* __restrict__ X, const uint32_t* __restrict__ bits, float scale,
-                                                         int C, int S, bf16* __restrict__ hi, bf16* __restrict__ lo) {
+                                                         int C, int S, bf16* __restrict__ hi, bf16* __restrict__ lo, int gen,
+                                                         uint32_t thresh, uint2 key, uint32_t stream_lo, uint32_t stream_hi,
+                                                         const StepState* __restrict__ ss) {
   extern __shared__ float sT[];   // [S][66]
   const int b = blockIdx.y, c0 = blockIdx.x * 64;
   const int S4 = S >> 2;
+  if (gen && ss) {   // graph replay: the step part of the stream id lives on the device
+    const unsigned long long sid = (((unsigned long long)stream_hi << 32) | stream_lo) ^ (ss->step << 24);
+    stream_lo = (uint32_t)sid;
+    stream_hi = (uint32_t)(sid >> 32);
+  }
   for (int i = threadIdx.x; i < 64 * S4; i += 256) {
     const int c = i / S4, s4 = i - c * S4;
     const int64_t e = ((int64_t)b * C + c0 + c) * S + 4 * s4;
     float4 t = *reinterpret_cast<const float4*>(X + e);
-    if (bits) {
+    if (gen) {
+      const uint64_t ctr = (uint64_t)e >> 2;
+      const uint4 r = philox4x32(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), stream_lo, stream_hi), key);
+      t.x = r.x < thresh ? t.x * scale : 0.0f;
+      t.y = r.y < thresh ? t.y * scale : 0.0f;
+      t.z = r.z < thresh ? t.z * scale : 0.0f;
+      t.w = r.w < thresh ? t.w * scale : 0.0f;
+    } else if (bits) {
       const uint32_t w = bits[e >> 5] >> (e & 31);
       t.x = (w & 1u) ? t.x * scale : 0.0f;
       t.y = (w & 2u) ? t.y * scale : 0.0f;
@@ -839,50 +855,55 @@ __global__ void __launch_bounds__(256) unprep_rows_kernel(const float* __restric
 }
 
 // attbymemory + attselect on the rows layout (F:285-290, F:254-263): p = softmax(logit + mem), a = sum_s p_s I[b*S+s, :]
-// grid (B, M/256), 128 threads, two channels per thread
-__global__ void __launch_bounds__(128) attn_rows_fwd_kernel(int S, int M, const float* __restrict__ logit,
+// one CTA of 256 threads per image: M/8 threads cover a row of I with 16-byte loads, 256/(M/8) row groups in parallel
+__global__ void __launch_bounds__(256) attn_rows_fwd_kernel(int S, int M, const float* __restrict__ logit,
                                                             const float* __restrict__ mem, const bf16* __restrict__ I_hi,
                                                             const bf16* __restrict__ I_lo, float* __restrict__ p_out,
                                                             float* __restrict__ a_out) {
-  __shared__ float p[256];
+  extern __shared__ float sm[];
+  float* p = sm;           // [256]
+  float* part = sm + 256;  // [ngroups][M]
   __shared__ float red[32];
   const int b = blockIdx.x, tid = threadIdx.x;
   const int64_t r0 = (int64_t)b * S;
   const float l0 = tid < S ? logit[r0 + tid] + mem[r0 + tid] : -INFINITY;
-  const float l1 = tid + 128 < S ? logit[r0 + tid + 128] + mem[r0 + tid + 128] : -INFINITY;
-  const float mx = block_max(fmaxf(l0, l1), red);
-  const float e0 = tid < S ? __expf(l0 - mx) : 0.0f, e1 = tid + 128 < S ? __expf(l1 - mx) : 0.0f;
-  const float den = block_sum(e0 + e1, red);
+  const float mx = block_max(l0, red);
+  const float e0 = tid < S ? __expf(l0 - mx) : 0.0f;
+  const float den = block_sum(e0, red);
   p[tid] = e0 / den;
-  p[tid + 128] = e1 / den;
-  if (blockIdx.y == 0) {
-    if (tid < S) p_out[r0 + tid] = e0 / den;
-    if (tid + 128 < S) p_out[r0 + tid + 128] = e1 / den;
-  }
+  if (tid < S) p_out[r0 + tid] = e0 / den;
   __syncthreads();
-  const int wpr = M >> 1;   // 32-bit words per row
-  const uint32_t* ih = reinterpret_cast<const uint32_t*>(I_hi) + r0 * wpr + blockIdx.y * 128 + tid;
-  const uint32_t* il = I_lo ? reinterpret_cast<const uint32_t*>(I_lo) + r0 * wpr + blockIdx.y * 128 + tid : nullptr;
-  float a0 = 0.0f, a1 = 0.0f;
+  const int tpr = M >> 3, ngroups = 256 / tpr;
+  const int cg = tid % tpr, rg = tid / tpr;
+  float a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = 0.0f;
 #pragma unroll 4
-  for (int s = 0; s < S; ++s) {
-    const uint32_t u = __ldg(ih + (int64_t)s * wpr);
-    float y0 = bf_lo(u), y1 = bf_hi(u);
-    if (il) {
-      const uint32_t w = __ldg(il + (int64_t)s * wpr);
-      y0 += bf_lo(w);
-      y1 += bf_hi(w);
-    }
-    a0 = fmaf(p[s], y0, a0);
-    a1 = fmaf(p[s], y1, a1);
+  for (int s = rg; s < S; s += ngroups) {
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(I_hi + (r0 + s) * M) + cg);
+    uint4 l = make_uint4(0u, 0u, 0u, 0u);
+    if (I_lo) l = __ldg(reinterpret_cast<const uint4*>(I_lo + (r0 + s) * M) + cg);
+    const float w = p[s];
+    a[0] = fmaf(w, bf_lo(h.x) + bf_lo(l.x), a[0]); a[1] = fmaf(w, bf_hi(h.x) + bf_hi(l.x), a[1]);
+    a[2] = fmaf(w, bf_lo(h.y) + bf_lo(l.y), a[2]); a[3] = fmaf(w, bf_hi(h.y) + bf_hi(l.y), a[3]);
+    a[4] = fmaf(w, bf_lo(h.z) + bf_lo(l.z), a[4]); a[5] = fmaf(w, bf_hi(h.z) + bf_hi(l.z), a[5]);
+    a[6] = fmaf(w, bf_lo(h.w) + bf_lo(l.w), a[6]); a[7] = fmaf(w, bf_hi(h.w) + bf_hi(l.w), a[7]);
   }
-  const int mc = blockIdx.y * 256 + 2 * tid;
-  *reinterpret_cast<float2*>(a_out + (int64_t)b * M + mc) = make_float2(a0, a1);
+  float4* dst = reinterpret_cast<float4*>(part + rg * M + 8 * cg);
+  dst[0] = make_float4(a[0], a[1], a[2], a[3]);
+  dst[1] = make_float4(a[4], a[5], a[6], a[7]);
+  __syncthreads();
+  for (int m = tid; m < M; m += 256) {
+    float v = 0.0f;
+    for (int k = 0; k < ngroups; ++k) v += part[k * M + m];
+    a_out[(int64_t)b * M + m] = v;
+  }
 }
 
 // backward of the above for one image (256 threads):
 //   dp = dp_in + I da ; ds = p (dp - <p,dp>) ; dZ[r,n] = ws[n] ds[s] (1 - E[r,n]^2) -> bf16 (hi, lo)
 //   dqa[b,n] = sum_s dZ[r,n] ; gws_part[b,n] = sum_s ds[s] E[r,n]
+// HBM-bound (I hi+lo and E read once, dZ written once = 0.8 MB per image): every loop keeps >= 64 bytes per thread in flight
 __global__ void __launch_bounds__(256) attn_rows_bwd_kernel(int S, int M, int A, const float* __restrict__ E,
                                                             const bf16* __restrict__ I_hi, const bf16* __restrict__ I_lo,
                                                             const float* __restrict__ ws, const float* __restrict__ p_in,
@@ -893,32 +914,35 @@ __global__ void __launch_bounds__(256) attn_rows_bwd_kernel(int S, int M, int A,
   extern __shared__ float sm[];
   float* ds = sm;            // [256]
   float* das = sm + 256;     // [M]
+  float* red2 = das + M;     // [2][256] cross-row-group partial sums
   __shared__ float red[32];
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t r0 = (int64_t)b * S;
   for (int m = tid; m < M; m += 256) das[m] = da[(int64_t)b * M + m];
   ds[tid] = 0.0f;
   __syncthreads();
-  const int wpr = M >> 1;
+  // (1) dp[s] = dp_in[s] + sum_m da[m] I[r0+s, m]: a warp per row, 8 channels (one 16-byte word) per lane and step
+  const int w8 = M >> 3;   // 16-byte words per row
   for (int s = warp; s < S; s += 8) {
-    const uint32_t* ih = reinterpret_cast<const uint32_t*>(I_hi) + (r0 + s) * wpr;
-    const uint32_t* il = I_lo ? reinterpret_cast<const uint32_t*>(I_lo) + (r0 + s) * wpr : nullptr;
+    const uint4* ih = reinterpret_cast<const uint4*>(I_hi + (r0 + s) * M);
+    const uint4* il = I_lo ? reinterpret_cast<const uint4*>(I_lo + (r0 + s) * M) : nullptr;
     float acc = 0.0f;
-    for (int w = lane; w < wpr; w += 32) {
-      const uint32_t u = __ldg(ih + w);
-      float y0 = bf_lo(u), y1 = bf_hi(u);
-      if (il) {
-        const uint32_t v = __ldg(il + w);
-        y0 += bf_lo(v);
-        y1 += bf_hi(v);
-      }
-      acc = fmaf(das[2 * w], y0, acc);
-      acc = fmaf(das[2 * w + 1], y1, acc);
+    for (int w = lane; w < w8; w += 32) {
+      const uint4 h = __ldg(ih + w);
+      uint4 l = make_uint4(0u, 0u, 0u, 0u);
+      if (il) l = __ldg(il + w);
+      const float4 d0 = *reinterpret_cast<const float4*>(das + 8 * w);
+      const float4 d1 = *reinterpret_cast<const float4*>(das + 8 * w + 4);
+      acc = fmaf(d0.x, bf_lo(h.x) + bf_lo(l.x), acc); acc = fmaf(d0.y, bf_hi(h.x) + bf_hi(l.x), acc);
+      acc = fmaf(d0.z, bf_lo(h.y) + bf_lo(l.y), acc); acc = fmaf(d0.w, bf_hi(h.y) + bf_hi(l.y), acc);
+      acc = fmaf(d1.x, bf_lo(h.z) + bf_lo(l.z), acc); acc = fmaf(d1.y, bf_hi(h.z) + bf_hi(l.z), acc);
+      acc = fmaf(d1.z, bf_lo(h.w) + bf_lo(l.w), acc); acc = fmaf(d1.w, bf_hi(h.w) + bf_hi(l.w), acc);
     }
     acc = warp_sum(acc);
     if (lane == 0) ds[s] = acc + (dp_in ? dp_in[r0 + s] : 0.0f);
   }
   __syncthreads();
+  // (2) softmax backward
   const float pv = tid < S ? p_in[r0 + tid] : 0.0f;
   const float dpv = tid < S ? ds[tid] : 0.0f;
   const float dot = block_sum(pv * dpv, red);
@@ -927,23 +951,36 @@ __global__ void __launch_bounds__(256) attn_rows_bwd_kernel(int S, int M, int A,
   ds[tid] = dsv;
   if (tid < S) ds_out[r0 + tid] = dsv;
   __syncthreads();
-  for (int n = tid; n < A; n += 256) {
-    const float w = ws[n];
-    float sz = 0.0f, sg = 0.0f;
-    const float* er = E + r0 * A + n;
+  // (3) dZ: A/4 threads cover a row of E with float4 loads, 256/(A/4) row groups walk the image in parallel
+  const int tpr = A >> 2, ngroups = 256 / tpr;
+  const int ng = tid % tpr, rg = tid / tpr;
+  const float4 w4 = *reinterpret_cast<const float4*>(ws + 4 * ng);
+  float sz0 = 0.f, sz1 = 0.f, sz2 = 0.f, sz3 = 0.f, sg0 = 0.f, sg1 = 0.f, sg2 = 0.f, sg3 = 0.f;
 #pragma unroll 4
-    for (int s = 0; s < S; ++s) {
-      const float e = __ldg(er + (int64_t)s * A);
-      const float d = ds[s];
-      const float dz = w * d * (1.0f - e * e);
-      sg = fmaf(d, e, sg);
-      sz += dz;
-      const bf16 h = __float2bfloat16_rn(dz);
-      dZ_hi[(r0 + s) * A + n] = h;
-      if (dZ_lo) dZ_lo[(r0 + s) * A + n] = __float2bfloat16_rn(dz - __bfloat162float(h));
-    }
-    dqa[(int64_t)b * A + n] = sz;
-    gws_part[(int64_t)b * A + n] = sg;
+  for (int s = rg; s < S; s += ngroups) {
+    const float4 e = __ldg(reinterpret_cast<const float4*>(E + (r0 + s) * A) + ng);
+    const float d = ds[s];
+    const float z0 = w4.x * d * (1.0f - e.x * e.x), z1 = w4.y * d * (1.0f - e.y * e.y);
+    const float z2 = w4.z * d * (1.0f - e.z * e.z), z3 = w4.w * d * (1.0f - e.w * e.w);
+    sg0 = fmaf(d, e.x, sg0); sg1 = fmaf(d, e.y, sg1); sg2 = fmaf(d, e.z, sg2); sg3 = fmaf(d, e.w, sg3);
+    sz0 += z0; sz1 += z1; sz2 += z2; sz3 += z3;
+    uint32_t h0, l0, h1, l1;
+    split_pair(z0, z1, h0, l0);
+    split_pair(z2, z3, h1, l1);
+    reinterpret_cast<uint2*>(dZ_hi + (r0 + s) * A)[ng] = make_uint2(h0, h1);
+    if (dZ_lo) reinterpret_cast<uint2*>(dZ_lo + (r0 + s) * A)[ng] = make_uint2(l0, l1);
+  }
+  // reduce the row groups: red2[0][rg][n] / red2[1][rg][n] with rg-major layout of A floats each (ngroups * A = 1024)
+  float* rz = red2;
+  float* rgs = red2 + 1024;
+  *reinterpret_cast<float4*>(rz + rg * A + 4 * ng) = make_float4(sz0, sz1, sz2, sz3);
+  *reinterpret_cast<float4*>(rgs + rg * A + 4 * ng) = make_float4(sg0, sg1, sg2, sg3);
+  __syncthreads();
+  for (int n = tid; n < A; n += 256) {
+    float z = 0.0f, g = 0.0f;
+    for (int k = 0; k < ngroups; ++k) { z += rz[k * A + n]; g += rgs[k * A + n]; }
+    dqa[(int64_t)b * A + n] = z;
+    gws_part[(int64_t)b * A + n] = g;
   }
 }
 
@@ -979,7 +1016,7 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   int BN = g.BN;
   if (BN == 0) {
     BN = 256;
-    if (g.epi == EPI_LINEAR || g.epi == EPI_PLAIN || g.epi == EPI_LSTM)
+    if (g.epi == EPI_LINEAR || g.epi == EPI_PLAIN || g.epi == EPI_LSTM || g.epi == EPI_RED)
       while (BN > 64 && (long long)p.tiles_m * ((g.N + BN - 1) / BN) < ctx->sm_count) BN >>= 1;
     while (BN > 64 && g.N <= BN / 2) BN >>= 1;
   }
@@ -1142,10 +1179,15 @@ static int prep_attr() {
   return RAU_OK;
 }
 
-int k_xprep_rows(rau_ctx* ctx, const float* X, int B, int C, int S, const uint32_t* bits, float scale, bf16* hi, bf16* lo) {
+int k_xprep_rows(rau_ctx* ctx, const float* X, int B, int C, int S, const uint32_t* bits, float scale, bf16* hi, bf16* lo,
+                 int gen, float p_drop, uint64_t stream_id) {
   RAU_REQUIRE(C % 64 == 0 && S % 4 == 0 && S <= 256 && ((uintptr_t)X & 15) == 0, "k_xprep_rows: C=%d S=%d", C, S);
   RAU_TRY(prep_attr());
-  xprep_rows_kernel<<<dim3(C / 64, B), 256, S * 66 * 4, ctx->stream>>>(X, bits, scale, C, S, hi, lo);
+  const double keep = 1.0 - (double)p_drop;
+  const uint32_t thresh = keep >= 1.0 ? 0xffffffffu : (uint32_t)(keep * 4294967296.0);
+  xprep_rows_kernel<<<dim3(C / 64, B), 256, S * 66 * 4, ctx->stream>>>(
+      X, bits, scale, C, S, hi, lo, gen, thresh, make_uint2((uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32)), (uint32_t)stream_id,
+      (uint32_t)(stream_id >> 32), ctx->ss_active);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
@@ -1160,8 +1202,8 @@ int k_unprep_rows(rau_ctx* ctx, const float* dXr, int B, int C, int S, const uin
 
 int k_attn_rows_fwd(rau_ctx* ctx, int B, int M, int S, const float* logit, const float* mem, const bf16* I_hi, const bf16* I_lo,
                     float* p, float* a) {
-  RAU_REQUIRE(M % 256 == 0 && S <= 256, "k_attn_rows_fwd: M=%d S=%d", M, S);
-  attn_rows_fwd_kernel<<<dim3(B, M / 256), 128, 0, ctx->stream>>>(S, M, logit, mem, I_hi, I_lo, p, a);
+  RAU_REQUIRE((M == 256 || M == 512 || M == 1024 || M == 2048) && S <= 256, "k_attn_rows_fwd: M=%d S=%d", M, S);
+  attn_rows_fwd_kernel<<<B, 256, (256 + 256 / (M / 8) * M) * sizeof(float), ctx->stream>>>(S, M, logit, mem, I_hi, I_lo, p, a);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
@@ -1169,8 +1211,8 @@ int k_attn_rows_fwd(rau_ctx* ctx, int B, int M, int S, const float* logit, const
 int k_attn_rows_bwd(rau_ctx* ctx, int B, int M, int A, int S, const float* E, const bf16* I_hi, const bf16* I_lo, const float* ws,
                     const float* p, const float* dp_in, const float* da, float* ds, bf16* dZ_hi, bf16* dZ_lo, float* dqa,
                     float* gws_part) {
-  RAU_REQUIRE(M % 2 == 0 && S <= 256, "k_attn_rows_bwd: M=%d S=%d", M, S);
-  attn_rows_bwd_kernel<<<B, 256, (256 + M) * sizeof(float), ctx->stream>>>(S, M, A, E, I_hi, I_lo, ws, p, dp_in, da, ds, dZ_hi,
+  RAU_REQUIRE(M % 8 == 0 && S <= 256 && (A == 64 || A == 128 || A == 256), "k_attn_rows_bwd: M=%d A=%d S=%d", M, A, S);
+  attn_rows_bwd_kernel<<<B, 256, (256 + M + 2048) * sizeof(float), ctx->stream>>>(S, M, A, E, I_hi, I_lo, ws, p, dp_in, da, ds, dZ_hi,
                                                                             dZ_lo, dqa, gws_part);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
@@ -1315,6 +1357,23 @@ int rows_perm_lstm_bias(rau_ctx* ctx, const float* b1, const float* b2, int H, i
 }
 
 namespace {
+// C[m, n] = bias[n] + bias2[n] + addend[m, n] + addend2[m, n]: what a split-K product then adds its partial sums into
+__global__ void linear_init_kernel(float* __restrict__ C, long long ldc, int M, int N, const float* __restrict__ bias,
+                                   const float* __restrict__ bias2, const float* __restrict__ addend,
+                                   const float* __restrict__ addend2, long long ldadd) {
+  const long long total = (long long)M * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i % N);
+    const long long m = i / N;
+    float t = 0.0f;
+    if (bias) t += bias[n];
+    if (bias2) t += bias2[n];
+    if (addend) t += addend[m * ldadd + n];
+    if (addend2) t += addend2[m * ldadd + n];
+    C[m * ldc + n] = t;
+  }
+}
+
 long long rows_min_work() {
   static long long v = -1;
   if (v < 0) {
@@ -1364,7 +1423,23 @@ int rows_contract_try(rau_ctx* ctx, const SimtGemm& g) {
   }
   r.alpha = g.alpha;
   r.out_f = g.C; r.ldo = g.scm;
-  if (plain_acc) {
+  // long reductions into a few output tiles (dgrads with K = 4H, the 2000-way head): one CTA per tile would stream its
+  // whole K range through a single SM's ~64 B/clk L2 port, so the K range is split over the SMs and the partial sums are
+  // added (TMA reduce) into an output that a tiny kernel pre-loads with bias + addend
+  const int skinny_tiles = ((g.M + RT_BM - 1) / RT_BM) * ((g.N + 63) / 64);
+  const bool split = !plain_acc && g.act == 0 && g.C_hi == nullptr && (g.K + g.K2) >= 1024 && skinny_tiles * 4 <= ctx->sm_count;
+  if (split) {
+    if (g.bias_n || g.bias_n2 || g.addend || g.addend2) {
+      const long long total = (long long)g.M * g.N;
+      int blocks = (int)((total + 1023) / 1024);
+      if (blocks > 148 * 4) blocks = 148 * 4;
+      linear_init_kernel<<<blocks, 256, 0, ctx->stream>>>(g.C, g.scm, g.M, g.N, g.bias_n, g.bias_n2, g.addend, g.addend2, g.sdm);
+      RAU_LAUNCH_CHECK(ctx);
+    } else {
+      RAU_CHECK_CUDA(cudaMemset2DAsync(g.C, (size_t)g.scm * 4, 0, (size_t)g.N * 4, (size_t)g.M, ctx->stream));
+    }
+    r.epi = ROWS_EPI_RED;
+  } else if (plain_acc) {
     r.epi = ROWS_EPI_RED;
   } else {
     r.epi = ROWS_EPI_LINEAR;

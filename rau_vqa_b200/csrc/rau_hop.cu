@@ -42,9 +42,12 @@ static inline float drop_scale(float p) { return p > 0.0f ? 1.0f / (1.0f - p) : 
 
 // the rows-layout tcgen05 engine (k_rows_tc.cu) takes the heavy image-side products when the shapes fit its tiles
 static inline bool rows_path(const rau_ctx* ctx, const rau_config* cfg) {
-  return ctx->precision != RAU_PREC_F32 && rows_path_enabled() && cfg->C % 64 == 0 && cfg->M % 256 == 0 && cfg->A % 64 == 0 &&
-         cfg->A <= 256 && cfg->S % 4 == 0 && cfg->S <= 256;
+  return ctx->precision != RAU_PREC_F32 && rows_path_enabled() && cfg->C % 64 == 0 &&
+         (cfg->M == 256 || cfg->M == 512 || cfg->M == 1024 || cfg->M == 2048) &&
+         (cfg->A == 64 || cfg->A == 128 || cfg->A == 256) && cfg->S % 4 == 0 && cfg->S <= 256;
 }
+
+bool hop_rows_path(const rau_ctx* ctx, const rau_config* cfg) { return rows_path(ctx, cfg); }
 
 #define ARENA(ptr, type, name, count) \
   type* ptr = nullptr;                \
@@ -101,7 +104,8 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
     RAU_TRY(rows_pack(ctx, P.Wi, (int64_t)M * C, x3, true, nullptr, &Wi_h, &Wi_l));
     RAU_TRY(rows_pack(ctx, P.Wa, (int64_t)A * M, x3, true, nullptr, &Wa_h, &Wa_l));
     ARENA(slog, float, "hop.slog", R);
-    RAU_TRY(k_xprep_rows(ctx, X, B, C, S, xb, drop_scale(cfg->p_x), sv.Xd_hi, x3 ? sv.Xd_lo : nullptr));
+    RAU_TRY(k_xprep_rows(ctx, X, B, C, S, xb, drop_scale(cfg->p_x), sv.Xd_hi, x3 ? sv.Xd_lo : nullptr,
+                         (train && cfg->p_x > 0 && sv.x_philox) ? 1 : 0, cfg->p_x, sv.x_stream));
     {   // i_embed (F:238-242): I = tanh(drop(X)^T Wi^T + bi)
       RowsGemm g;
       g.M = R; g.N = M; g.K = C;

@@ -26,7 +26,7 @@ int k_lstm_bwd(rau_ctx* ctx, int B, int H, int order,
                const float* dh_extra, int ldhe,
                const float* lengths, int t, const float* dq_c, const float* dq_h, int lddq,
                const float* c_prev, int ldcp, const float* saved,
-               float* dG, bf16* dG_b, float* dc_prev, int lddcp);
+               float* dG, bf16* dG_b, float* dc_prev, int lddcp, bf16* dG_lo = nullptr);   // dG_b / dG_lo: packed (hi, lo) copy
 
 // ---- generic elementwise
 // y = x * keep(bits) * scale over a [rows, cols] matrix (mask indexed by row*cols+col); padded output pitch
@@ -49,7 +49,7 @@ int k_dopred_bwd(rau_ctx* ctx, const float* ddo, const float* dop, const float* 
 
 // ---- reductions
 // out[c] (+)= sum_r x[r*ld + c]
-int k_colsum(rau_ctx* ctx, const float* x, int64_t rows, int cols, int ld, float* out, int accumulate);
+int k_colsum(rau_ctx* ctx, const float* x, int64_t rows, int cols, int ld, float* out, int accumulate, float* out2 = nullptr);
 // out[m] += sum_b sum_s x[(b*M + m)*Sp + s], s < S   (bias grads of the 1x1 convolutions)
 template <typename T>
 int k_rowsum_bms(rau_ctx* ctx, const T* x, int B, int M, int S, int Sp, float* out);

@@ -50,7 +50,12 @@ struct HopSaved {
   uint32_t *qbits, *xbits, *mbits;   // packed keep bits of the three dropouts (F:233, F:239, F:277)
   float *qd, *qf, *I, *E, *p, *j, *lsav, *hout, *m, *dop;
   bf16 *Xd_hi, *Xd_lo, *I_hi, *I_lo;   // tcgen05 modes: packed operands kept for the backward pass
+  // training step on the rows engine: the feature-dropout bits are drawn inside the transposing pack kernel from this
+  // Philox stream instead of being materialised in xbits first (nothing in the step reads them again: dX is not formed)
+  int x_philox = 0;
+  uint64_t x_stream = 0;
 };
+bool hop_rows_path(const rau_ctx* ctx, const rau_config* cfg);
 size_t hop_saved_layout(const rau_config* cfg, int B, void* base, HopSaved* sv);
 
 // Backward scratch of one hop that the weight-gradient products read.  In the training step these point into

@@ -51,7 +51,9 @@ int rows_pack_lstm(rau_ctx* ctx, const float* W, int H, int K, int gate_order, b
                    int64_t* ldo);
 int rows_perm_lstm_bias(rau_ctx* ctx, const float* b1, const float* b2, int H, int gate_order, const float** out);
 int rows_pack(rau_ctx* ctx, const float* W, int64_t n, bool want_lo, bool cache, const char* slot, const bf16** hi, const bf16** lo);
-int k_xprep_rows(rau_ctx* ctx, const float* X, int B, int C, int S, const uint32_t* bits, float scale, bf16* hi, bf16* lo);
+// gen != 0: draw the keep bits inline from Philox stream `stream_id` with drop rate p_drop (bits is then ignored)
+int k_xprep_rows(rau_ctx* ctx, const float* X, int B, int C, int S, const uint32_t* bits, float scale, bf16* hi, bf16* lo,
+                 int gen = 0, float p_drop = 0.0f, uint64_t stream_id = 0);
 int k_unprep_rows(rau_ctx* ctx, const float* dXr, int B, int C, int S, const uint32_t* bits, float scale, float* dX);
 int k_attn_rows_fwd(rau_ctx* ctx, int B, int M, int S, const float* logit, const float* mem, const bf16* I_hi, const bf16* I_lo,
                     float* p, float* a);

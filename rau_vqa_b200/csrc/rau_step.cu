@@ -72,7 +72,7 @@ static int encoder_forward(rau_ctx* ctx, const rau_config* cfg, const rau_batch*
   // word_embed for every step at once (F:203-206, F:468)
   RAU_TRY(k_embed_fwd(ctx, bt->tokens, Tm * B, E, cfg->V, Pe, de ? en->ebits : nullptr, drop_scale(cfg->p_embed),
                       en->e_all, nullptr, 0));
-  const bool fused = ctx->precision != RAU_PREC_F32 && rows_path_enabled() && Hq % 8 == 0 && E % 4 == 0 &&
+  const bool fused = ctx->precision != RAU_PREC_F32 && rows_path_enabled() && Hq % 8 == 0 && E % 8 == 0 &&
                      (int64_t)B * G4 * Hq >= (1 << 18);
   // layer 1 input projection hoisted over time: G1x = e Wi1^T + bi1 + bh1
   if (!fused) {
@@ -86,9 +86,10 @@ static int encoder_forward(rau_ctx* ctx, const rau_config* cfg, const rau_batch*
     // cell update fused behind it in the epilogue (EPI_LSTM), which also emits h_t packed for the next step
     const bool x3 = ctx->precision == RAU_PREC_BF16X3;
     const size_t hb = (size_t)B * Hq;
-    ARENA(hpk_hi, bf16, "enc.hpk.hi", (size_t)(Tm + 1) * hb);
-    ARENA(hpk_lo, bf16, "enc.hpk.lo", (size_t)(Tm + 1) * hb);
+    ARENA(hpk_all, bf16, "enc.hpk", (size_t)4 * (cfg->T + 1) * hb);   // [layer][hi, lo][T+1][B][Hq], kept for the backward pass
     for (int layer = 0; layer < 2; ++layer) {
+      bf16* hpk_hi = hpk_all + (size_t)(2 * layer) * (cfg->T + 1) * hb;
+      bf16* hpk_lo = hpk_hi + (size_t)(cfg->T + 1) * hb;
       const int in = layer == 0 ? E : Hq;
       const bf16 *Wi_h, *Wi_l, *Wh_h, *Wh_l, *x_h, *x_l;
       int64_t ldwi, ldwh, ldx;
@@ -100,7 +101,8 @@ static int encoder_forward(rau_ctx* ctx, const rau_config* cfg, const rau_batch*
       if (layer == 1)   // u2 = drop(h1) for every step (D:38-39)
         RAU_TRY(k_dropout(ctx, en->S_all + (size_t)B * Q + Hq, (int64_t)Tm * B, Hq, Q, dr ? en->rbits : nullptr,
                           drop_scale(cfg->p_rnn), en->u2, Hq, nullptr, 0, Hq));
-      RAU_TRY(rows_pack2d(ctx, layer == 0 ? en->e_all : en->u2, in, Tm * B, in, x3, false, "enc.x", &x_h, &x_l, &ldx));
+      RAU_TRY(rows_pack2d(ctx, layer == 0 ? en->e_all : en->u2, in, Tm * B, in, x3, false, layer == 0 ? "enc.x0" : "enc.x1", &x_h,
+                          &x_l, &ldx));
       {   // input projection of every step at once, columns in the permuted gate order
         RowsGemm g;
         g.M = Tm * B; g.N = G4; g.K = in;
@@ -173,6 +175,77 @@ static int encoder_backward(rau_ctx* ctx, const rau_config* cfg, const rau_batch
   ARENA(dH, float, "encb.dH", (size_t)B * Hq);
   ARENA(du2, float, "encb.du2", (size_t)cfg->T * B * Hq);
   ARENA(de_all, float, "encb.de", (size_t)cfg->T * B * E);
+  const bool fused = ctx->precision != RAU_PREC_F32 && rows_path_enabled() && Hq % 8 == 0 && E % 8 == 0 &&
+                     (int64_t)B * G4 * Hq >= (1 << 18);
+  if (fused) {
+    // tcgen05 path: the pointwise cell backward writes dG packed (hi, lo) next to the fp32 copy, the recurrent dgrad is a
+    // split-K product on the rows engine straight from it, and the four weight gradients reuse the packed operands the
+    // forward pass left behind (x, h_{t-1}) -- no pack kernels in the time loop
+    const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+    const size_t gb = (size_t)B * G4, hb = (size_t)B * Hq;
+    const int R = Tm * B;
+    ARENA(dGp, bf16, "encb.dGp", (size_t)4 * cfg->T * gb);   // [layer][hi, lo][T][B][4H]
+    bf16* hpk_all = nullptr;
+    RAU_TRY(ctx->arena.get("enc.hpk", sizeof(bf16) * (size_t)4 * (cfg->T + 1) * hb, (void**)&hpk_all));
+    for (int layer = 1; layer >= 0; --layer) {
+      float* dG = layer == 1 ? dG2 : dG1;
+      bf16* dG_hi = dGp + (size_t)(2 * layer) * cfg->T * gb;
+      bf16* dG_lo = x3 ? dG_hi + (size_t)cfg->T * gb : nullptr;
+      const bf16 *Wh_h, *Wh_l, *Wi_h, *Wi_l;
+      int64_t ldwh, ldwi;
+      const int in = layer == 0 ? E : Hq;
+      RAU_TRY(rows_pack2d(ctx, Pr + L[layer].Wh, Hq, G4, Hq, x3, true, nullptr, &Wh_h, &Wh_l, &ldwh));
+      RAU_TRY(rows_pack2d(ctx, Pr + L[layer].Wi, in, G4, in, x3, true, nullptr, &Wi_h, &Wi_l, &ldwi));
+      for (int t = Tm; t >= 1; --t) {
+        const bool last = t == Tm;
+        const float* Sp_ = en->S_all + (size_t)(t - 1) * B * Q + 2 * layer * Hq;
+        RAU_TRY(k_lstm_bwd(ctx, B, Hq, RAU_GATES_IFOG, last ? nullptr : dC, Hq, last ? nullptr : dH, Hq,
+                           layer == 0 ? du2 + (size_t)(t - 1) * hb : nullptr, Hq, bt->lengths, t, dq + 2 * layer * Hq,
+                           dq + (2 * layer + 1) * Hq, Q, Sp_, Q,
+                           (layer == 1 ? en->sav2 : en->sav1) + (size_t)(t - 1) * 5 * hb, dG + (size_t)(t - 1) * gb,
+                           dG_hi + (size_t)(t - 1) * gb, dC, Hq, dG_lo ? dG_lo + (size_t)(t - 1) * gb : nullptr));
+        if (t > 1) {   // dH = dG_t Wh: K = 4H over a [B, Hq] output -> split over the SMs, partial sums TMA-reduced
+          RAU_CHECK_CUDA(cudaMemsetAsync(dH, 0, sizeof(float) * hb, ctx->stream));
+          RowsGemm g;
+          g.M = B; g.N = Hq; g.K = G4;
+          g.A.hi = dG_hi + (size_t)(t - 1) * gb; g.A.lo = dG_lo ? dG_lo + (size_t)(t - 1) * gb : nullptr; g.A.ld = G4;
+          g.B.hi = Wh_h; g.B.lo = Wh_l; g.B.mn = 1; g.B.ld = ldwh;
+          g.epi = ROWS_EPI_RED; g.out_f = dH; g.ldo = Hq;
+          RAU_TRY(rows_gemm(ctx, g));
+        }
+      }
+      {   // gradient into the layer input for every step at once: dX = dG Wi
+        RowsGemm g;
+        g.M = R; g.N = in; g.K = G4;
+        g.A.hi = dG_hi; g.A.lo = dG_lo; g.A.ld = G4;
+        g.B.hi = Wi_h; g.B.lo = Wi_l; g.B.mn = 1; g.B.ld = ldwi;
+        g.epi = ROWS_EPI_LINEAR; g.out_f = layer == 1 ? du2 : de_all; g.ldo = in;
+        RAU_TRY(rows_gemm(ctx, g));
+      }
+      if (layer == 1)
+        RAU_TRY(k_dropout_bwd_acc(ctx, du2, (int64_t)R * Hq, dr ? en->rbits : nullptr, drop_scale(cfg->p_rnn), du2, 0));
+      // weight gradients over all R = Tm*B rows: gWi += dG^T x, gWh += dG^T h_{t-1} (packed operands of the forward pass)
+      const bf16* x_h = nullptr;
+      const int64_t ldx = (in + 7) / 8 * 8;
+      const size_t xhalf = ((size_t)R * ldx * sizeof(bf16) + 1023) / 1024 * 1024;
+      RAU_TRY(ctx->arena.get(layer == 0 ? "rp.enc.x0" : "rp.enc.x1", xhalf * (x3 ? 2 : 1), (void**)&x_h));
+      const bf16* x_l = x3 ? (const bf16*)((const char*)x_h + xhalf) : nullptr;
+      const bf16* hp_h = hpk_all + (size_t)(2 * layer) * (cfg->T + 1) * hb;
+      const bf16* hp_l = x3 ? hp_h + (size_t)(cfg->T + 1) * hb : nullptr;
+      for (int which = 0; which < 2; ++which) {
+        RowsGemm g;
+        g.M = G4; g.N = which == 0 ? in : Hq; g.K = R;
+        g.A.hi = dG_hi; g.A.lo = dG_lo; g.A.mn = 1; g.A.ld = G4;
+        g.B.hi = which == 0 ? x_h : hp_h; g.B.lo = which == 0 ? x_l : hp_l; g.B.mn = 1; g.B.ld = which == 0 ? ldx : Hq;
+        g.epi = ROWS_EPI_RED; g.out_f = gR + (which == 0 ? L[layer].Wi : L[layer].Wh); g.ldo = which == 0 ? in : Hq;
+        RAU_TRY(rows_gemm(ctx, g));
+      }
+      RAU_TRY(k_colsum(ctx, dG, R, G4, G4, gR + L[layer].bi, 1, gR + L[layer].bh));
+    }
+    RAU_TRY(k_embed_bwd(ctx, bt->tokens, Tm * B, E, cfg->V, en->e_all, de ? en->ebits : nullptr, drop_scale(cfg->p_embed),
+                        de_all, E, gE));
+    return RAU_OK;
+  }
   // layer 2, t = Tm..1
   for (int t = Tm; t >= 1; --t) {
     const bool last = t == Tm;
@@ -324,9 +397,14 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     sv[hp].m = st_m + (size_t)hp * B * M_;
     RAU_TRY(rau_prepare_mask(ctx, sv[hp].qbits, (int64_t)B * Q, cfg->p_q, train,
                              masks && masks->q ? masks->q + (size_t)hp * B * Q : nullptr, stream_of(step_t, SK_Q, hp, rank)));
-    RAU_TRY(rau_prepare_mask(ctx, sv[hp].xbits, (int64_t)B * cfg->C * S, cfg->p_x, train,
-                             masks && masks->x ? masks->x + (size_t)hp * B * cfg->C * S : nullptr,
-                             stream_of(step_t, SK_X, hp, rank)));
+    if (hop_rows_path(ctx, cfg) && !(masks && masks->x)) {   // drawn inline by the rows pack kernel
+      sv[hp].x_philox = 1;
+      sv[hp].x_stream = stream_of(step_t, SK_X, hp, rank);
+    } else {
+      RAU_TRY(rau_prepare_mask(ctx, sv[hp].xbits, (int64_t)B * cfg->C * S, cfg->p_x, train,
+                               masks && masks->x ? masks->x + (size_t)hp * B * cfg->C * S : nullptr,
+                               stream_of(step_t, SK_X, hp, rank)));
+    }
     RAU_TRY(rau_prepare_mask(ctx, sv[hp].mbits, (int64_t)B * cfg->M, cfg->p_m, train,
                              masks && masks->m ? masks->m + (size_t)hp * B * cfg->M : nullptr,
                              stream_of(step_t, SK_M, hp, rank)));
