@@ -252,6 +252,9 @@ int rau_gemm(rau_ctx* ctx, int M, int N, int K, const float* A, int lda, int ta,
  * multiples of 8 floats.  reduce != 0: split-K partial sums are ADDED into D (TMA reduce-add), else D is overwritten. */
 int rau_rows_gemm(rau_ctx* ctx, int M, int N, int K, const float* A, int lda, int a_mn,
                   const float* B, int ldb, int b_mn, float* D, int ldd, int reduce);
+/* GPU microseconds per launch of one rows-engine product on synthetic operands (iters launches replayed from a CUDA
+ * graph, so host launch cost is excluded); reduce != 0 selects the split-K TMA-reduce form */
+int rau_rows_gemm_time(rau_ctx* ctx, int M, int N, int K, int a_mn, int b_mn, int reduce, int iters, float* us_per_launch);
 /* debugging aid (RAU_ROWS_TRACE=1): copies the per-CTA clock stamps [148][16] of the last rows-engine launch to HOST
  * memory `out` (n 64-bit words): 0 start, 1 prologue done, 2 first TMA issue, 3/4 first/second stage landed, 5 MMAs
  * of the first item issued, 6 first accumulator ready, 7 epilogue issued, 8 stores drained, 9 end */

@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(ATT_T) attn_fwd_kernel(int M, int A, int S, in
                                                          const float* __restrict__ mem, float* __restrict__ p_out,
                                                          bf16* __restrict__ p_b, int ldpb, float* __restrict__ a_out,
                                                          bf16* __restrict__ a_b) {
+  RAU_PDL_ENTRY();
   extern __shared__ float sm[];
   float* p = sm;            // [Sp]
   float* wsm = sm + Sp;     // [A]
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(ATT_T) attn_bwd_kernel(int M, int A, int S, in
                                                          float* __restrict__ dqa, bf16* __restrict__ dqa_b,
                                                          float* __restrict__ gws_part, bf16* __restrict__ dZ_hi,
                                                          bf16* __restrict__ dZ_lo) {
+  RAU_PDL_ENTRY();
   extern __shared__ float sm[];
   float* ds = sm;          // [Sp]
   float* das = sm + Sp;    // [M]
@@ -132,6 +134,7 @@ template <typename T>
 __global__ void iembed_bwd_pw_kernel(int64_t total, int M, int S, int Sp, const float* __restrict__ dI,
                                      const T* __restrict__ I, const float* __restrict__ da,
                                      const float* __restrict__ p, T* __restrict__ dY) {
+  RAU_PDL_ENTRY();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int s = (int)(i % Sp);
     const int64_t bm = i / Sp;
@@ -151,6 +154,7 @@ __global__ void __launch_bounds__(256) iembed_bwd_rows_kernel(int64_t rows, int 
                                                               const float* __restrict__ p, float* __restrict__ dY,
                                                               bf16* __restrict__ hi, bf16* __restrict__ lo,
                                                               float* __restrict__ gbi) {
+  RAU_PDL_ENTRY();
   const int lane = threadIdx.x & 31;
   const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t row = w0; row < rows; row += nw) {
@@ -184,6 +188,7 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(int N, const float* __r
                                                          float loss_scale, float grad_scale, float* __restrict__ loss_sum,
                                                          float* __restrict__ dscore_f, bf16* __restrict__ dscore_b, int lddb,
                                                          float* __restrict__ answers) {
+  RAU_PDL_ENTRY();
   __shared__ float red[32];
   __shared__ int redi[32];
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -246,6 +251,7 @@ __global__ void __launch_bounds__(256) merge_preds_kernel(int nHop, int B, int N
                                                           float* __restrict__ loss_do_pred, float* __restrict__ answers_uni_sel,
                                                           float* __restrict__ pred_uni, float* __restrict__ pred_sel,
                                                           float* __restrict__ att_uni, float* __restrict__ att_sel) {
+  RAU_PDL_ENTRY();
   __shared__ float red[32];
   __shared__ int redi[32];
   __shared__ float cur[64];
@@ -340,7 +346,7 @@ template <typename T>
 int k_attn_fwd(rau_ctx* ctx, int B, int M, int A, int S, int Sp, const T* E, const T* I, const float* ws, const float* mem,
                float* p, bf16* p_b, int ldpb, float* a, bf16* a_b) {
   if (S > ATT_T || Sp > ATT_T || ldpb > ATT_T) { rau_set_error("attention grid S=%d too large", S); return RAU_EINVAL; }
-  attn_fwd_kernel<T><<<B, ATT_T, (Sp + A) * sizeof(float), ctx->stream>>>(M, A, S, Sp, E, I, ws, mem, p, p_b, ldpb, a, a_b);
+  RAU_LAUNCH_PDL(ctx->stream, (attn_fwd_kernel<T>), B, ATT_T, (Sp + A) * sizeof(float), M, A, S, Sp, E, I, ws, mem, p, p_b, ldpb, a, a_b);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
@@ -352,7 +358,7 @@ int k_attn_bwd(rau_ctx* ctx, int B, int M, int A, int S, int Sp, const T* E, con
                const float* dp_in, const float* da, float* ds, bf16* ds_b, int lddsb, T* dZ, float* dqa, bf16* dqa_b,
                float* gws_part, bf16* dZ_hi, bf16* dZ_lo) {
   if (S > ATT_T || Sp > ATT_T || lddsb > ATT_T) { rau_set_error("attention grid S=%d too large", S); return RAU_EINVAL; }
-  attn_bwd_kernel<T><<<B, ATT_T, (Sp + M) * sizeof(float), ctx->stream>>>(M, A, S, Sp, E, I, ws, p, dp_in, da, ds, ds_b, lddsb,
+  RAU_LAUNCH_PDL(ctx->stream, (attn_bwd_kernel<T>), B, ATT_T, (Sp + M) * sizeof(float), M, A, S, Sp, E, I, ws, p, dp_in, da, ds, ds_b, lddsb,
                                                                           dZ, dqa, dqa_b, gws_part, dZ_hi, dZ_lo);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
@@ -365,7 +371,7 @@ int k_iembed_bwd_pw(rau_ctx* ctx, int B, int M, int S, int Sp, const float* dI, 
   const int64_t total = (int64_t)B * M * Sp;
   int64_t blocks = (total + 1023) / 1024;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  iembed_bwd_pw_kernel<T><<<(int)blocks, 256, 0, ctx->stream>>>(total, M, S, Sp, dI, I, da, p, dY);
+  RAU_LAUNCH_PDL(ctx->stream, (iembed_bwd_pw_kernel<T>), (int)blocks, 256, 0, total, M, S, Sp, dI, I, da, p, dY);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
@@ -377,14 +383,14 @@ int k_iembed_bwd_rows(rau_ctx* ctx, int B, int M, int S, int Sp, const float* dI
   const int64_t rows = (int64_t)B * M;
   int64_t blocks = (rows + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  iembed_bwd_rows_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(rows, M, S, Sp, dI, I, da, p, dY, dY_hi, dY_lo, gbi);
+  RAU_LAUNCH_PDL(ctx->stream, (iembed_bwd_rows_kernel), (int)blocks, 256, 0, rows, M, S, Sp, dI, I, da, p, dY, dY_hi, dY_lo, gbi);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 
 int k_softmax_ce(rau_ctx* ctx, int B, int N, const float* score, const float* labels, float loss_scale, float grad_scale,
                  float* loss_sum, float* dscore_f, bf16* dscore_b, int lddb, float* answers) {
-  softmax_ce_kernel<<<B, 256, 0, ctx->stream>>>(N, score, labels, loss_scale, grad_scale, loss_sum, dscore_f, dscore_b, lddb, answers);
+  RAU_LAUNCH_PDL(ctx->stream, (softmax_ce_kernel), B, 256, 0, N, score, labels, loss_scale, grad_scale, loss_sum, dscore_f, dscore_b, lddb, answers);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
@@ -393,7 +399,7 @@ int k_merge_preds(rau_ctx* ctx, int nHop, int B, int N, int S, const float* scor
                   const float* labels, const float* answers_hop, int force_last, float inv_bglobal, float* loss_uni_sel,
                   float* loss_do_pred, float* answers_uni_sel, float* pred_uni, float* pred_sel, float* att_uni, float* att_sel) {
   if (nHop > 64) { rau_set_error("nHop=%d > 64", nHop); return RAU_EINVAL; }
-  merge_preds_kernel<<<B, 256, 0, ctx->stream>>>(nHop, B, N, S, scores, do_pred, attprob, labels, answers_hop, force_last,
+  RAU_LAUNCH_PDL(ctx->stream, (merge_preds_kernel), B, 256, 0, nHop, B, N, S, scores, do_pred, attprob, labels, answers_hop, force_last,
                                                  inv_bglobal, loss_uni_sel, loss_do_pred, answers_uni_sel, pred_uni, pred_sel,
                                                  att_uni, att_sel);
   RAU_LAUNCH_CHECK(ctx);

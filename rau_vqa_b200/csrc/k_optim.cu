@@ -10,6 +10,7 @@ __global__ void __launch_bounds__(256) noise_norm_kernel(float* __restrict__ g, 
                                                          const float* __restrict__ noise, uint2 key,
                                                          uint32_t stream_lo, uint32_t stream_hi, double* __restrict__ norm2,
                                                          const StepState* __restrict__ ss) {
+  RAU_PDL_ENTRY();
   __shared__ float red[32];
   if (ss) {
     const unsigned long long sid = (((unsigned long long)stream_hi << 32) | stream_lo) ^ (ss->step << 24);
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(256) clip_optim_kernel(OptArgs a, float* __res
                                                          const double* __restrict__ norm2, float* __restrict__ s0,
                                                          float* __restrict__ s1, float* __restrict__ norm_out,
                                                          const StepState* __restrict__ ss, int group) {
+  RAU_PDL_ENTRY();
   float scale = 1.0f;
   if (ss && group >= 0) a.step = ss->opt_step[group];
   if (norm2 != nullptr) {
@@ -98,7 +100,7 @@ int k_noise_norm(rau_ctx* ctx, float* g, int64_t n, float std, const float* nois
   int64_t blocks = (n / 4 + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  noise_norm_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(g, n, std, noise_override,
+  RAU_LAUNCH_PDL(ctx->stream, (noise_norm_kernel), (int)blocks, 256, 0, g, n, std, noise_override,
       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), (uint32_t)stream_id, (uint32_t)(stream_id >> 32), norm2_out,
       ctx->ss_active);
   RAU_LAUNCH_CHECK(ctx);
@@ -116,7 +118,7 @@ int k_clip_optim(rau_ctx* ctx, int optim, int64_t n, float* x, float* g, const d
   int64_t blocks = (n + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  clip_optim_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(a, x, g, norm2, s0, s1, norm_out, ctx->ss_active, group);
+  RAU_LAUNCH_PDL(ctx->stream, (clip_optim_kernel), (int)blocks, 256, 0, a, x, g, norm2, s0, s1, norm_out, ctx->ss_active, group);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }

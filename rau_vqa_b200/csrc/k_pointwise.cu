@@ -16,6 +16,7 @@ inline int grid_for(int64_t n, int per_thread = 1) {
 __global__ void mask_gen_kernel(uint32_t* __restrict__ bits, int64_t nwords, int64_t n, uint32_t thresh,
                                 int keep_all, uint2 key, uint32_t stream_lo, uint32_t stream_hi,
                                 const StepState* __restrict__ ss) {
+  RAU_PDL_ENTRY();
   if (ss) {   // graph replay: the step part of the stream id lives on the device
     const unsigned long long sid = (((unsigned long long)stream_hi << 32) | stream_lo) ^ (ss->step << 24);
     stream_lo = (uint32_t)sid;
@@ -37,6 +38,7 @@ __global__ void mask_gen_kernel(uint32_t* __restrict__ bits, int64_t nwords, int
 }
 
 __global__ void mask_pack_kernel(uint32_t* __restrict__ bits, const uint8_t* __restrict__ bytes, int64_t nwords, int64_t n) {
+  RAU_PDL_ENTRY();
   for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < nwords; w += (int64_t)gridDim.x * blockDim.x) {
     uint32_t word = 0;
     for (int k = 0; k < 32; ++k) {
@@ -51,6 +53,7 @@ __global__ void mask_pack_kernel(uint32_t* __restrict__ bits, const uint8_t* __r
 __global__ void embed_fwd_kernel(const float* __restrict__ ids, int n, int D, int V, const float* __restrict__ E,
                                  const uint32_t* __restrict__ bits, float scale, float* __restrict__ out_f,
                                  bf16* __restrict__ out_b, int ldb) {
+  RAU_PDL_ENTRY();
   const int64_t total = (int64_t)n * D;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / D), d = (int)(i % D);
@@ -65,6 +68,7 @@ __global__ void embed_fwd_kernel(const float* __restrict__ ids, int n, int D, in
 __global__ void embed_bwd_kernel(const float* __restrict__ ids, int n, int D, int V, const float* __restrict__ out,
                                  const uint32_t* __restrict__ bits, float scale, const float* __restrict__ dout, int lddout,
                                  float* __restrict__ gE) {
+  RAU_PDL_ENTRY();
   const int64_t total = (int64_t)n * D;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / D), d = (int)(i % D);
@@ -86,6 +90,7 @@ __device__ __forceinline__ void gate_chunks(int order, int& ci, int& cf, int& co
 __global__ void lstm_fwd_kernel(int B, int H, int order, const float* __restrict__ G, int ldg,
                                 const float* __restrict__ c_prev, int ldcp, float* __restrict__ c, int ldc,
                                 float* __restrict__ h, int ldh, bf16* __restrict__ h_b, int ldhb, float* __restrict__ saved) {
+  RAU_PDL_ENTRY();
   int ci, cf, co, cg;
   gate_chunks(order, ci, cf, co, cg);
   const int64_t total = (int64_t)B * H, plane = total;
@@ -117,6 +122,7 @@ __global__ void lstm_bwd_kernel(int B, int H, int order, const float* __restrict
                                 const float* __restrict__ c_prev, int ldcp, const float* __restrict__ saved,
                                 float* __restrict__ dG, bf16* __restrict__ dG_b, float* __restrict__ dc_prev, int lddcp,
                                 bf16* __restrict__ dG_lo) {
+  RAU_PDL_ENTRY();
   int ci, cf, co, cg;
   gate_chunks(order, ci, cf, co, cg);
   const int64_t total = (int64_t)B * H, plane = total;
@@ -159,6 +165,7 @@ __global__ void lstm_bwd_kernel(int B, int H, int order, const float* __restrict
 __global__ void dropout_kernel(const float* __restrict__ x, int64_t rows, int cols, int ldx,
                                const uint32_t* __restrict__ bits, float scale,
                                float* __restrict__ y_f, int ldyf, bf16* __restrict__ y_b, int ldyb, int cols_pad) {
+  RAU_PDL_ENTRY();
   const int64_t total = rows * cols_pad;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cols_pad;
@@ -174,6 +181,7 @@ __global__ void dropout_kernel(const float* __restrict__ x, int64_t rows, int co
 // pitch cols_pad (zero padded).  Four columns per thread: 128-bit loads, 64-bit stores.
 __global__ void dropout_pack_kernel(const float* __restrict__ x, int64_t rows, int cols, const uint32_t* __restrict__ bits,
                                     float scale, bf16* __restrict__ hi, bf16* __restrict__ lo, int cols_pad) {
+  RAU_PDL_ENTRY();
   const int q = cols_pad >> 2;
   const int64_t total = rows * q;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -202,6 +210,7 @@ __global__ void dropout_pack_kernel(const float* __restrict__ x, int64_t rows, i
 
 __global__ void dropout_bwd_acc_kernel(const float* __restrict__ dx, int64_t n, const uint32_t* __restrict__ bits,
                                        float scale, float* __restrict__ y, int accumulate) {
+  RAU_PDL_ENTRY();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float v = dx[i] * keep_scale(bits, i, scale);
     y[i] = accumulate ? y[i] + v : v;
@@ -210,6 +219,7 @@ __global__ void dropout_bwd_acc_kernel(const float* __restrict__ dx, int64_t n, 
 
 __global__ void tanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int64_t n,
                                 float* __restrict__ dx_f, bf16* __restrict__ dx_b) {
+  RAU_PDL_ENTRY();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float v = dy[i] * (1.0f - y[i] * y[i]);
     if (dx_f) dx_f[i] = v;
@@ -218,17 +228,21 @@ __global__ void tanh_bwd_kernel(const float* __restrict__ dy, const float* __res
 }
 
 __global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, float* __restrict__ y) {
+  RAU_PDL_ENTRY();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = a[i] + b[i];
 }
 __global__ void axpy_kernel(float alpha, const float* __restrict__ x, int64_t n, float* __restrict__ y) {
+  RAU_PDL_ENTRY();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] += alpha * x[i];
 }
 __global__ void fill_kernel(float* __restrict__ x, int64_t n, float v) {
+  RAU_PDL_ENTRY();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] = v;
 }
 __global__ void to_bf16_kernel(const float* __restrict__ x, int64_t rows, int cols, int ldx, bf16* __restrict__ y, int ldy, int cols_pad) {
+  RAU_PDL_ENTRY();
   const int64_t total = rows * cols_pad;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cols_pad;
@@ -240,6 +254,7 @@ __global__ void to_bf16_kernel(const float* __restrict__ x, int64_t rows, int co
 // y[b] = sigmoid(x[b,:] . w + bias)   -- the do_pred head, F:281 (Linear(M,1) -> Sigmoid -> Sum(2))
 __global__ void rowdot_sigmoid_kernel(const float* __restrict__ x, int B, int K, const float* __restrict__ w,
                                       const float* __restrict__ bias, float* __restrict__ y) {
+  RAU_PDL_ENTRY();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= B) return;
   float s = 0.0f;
@@ -251,6 +266,7 @@ __global__ void rowdot_sigmoid_kernel(const float* __restrict__ x, int B, int K,
 __global__ void dopred_bwd_kernel(const float* __restrict__ ddo, const float* __restrict__ dop, const float* __restrict__ m,
                                   const float* __restrict__ wd, int B, int K, float* __restrict__ dm_acc,
                                   float* __restrict__ gwd, float* __restrict__ gbd) {
+  RAU_PDL_ENTRY();
   // one block per feature chunk; loops over the batch (tiny: only used when a caller passes a do_pred gradient)
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   float gw = 0.0f, gb = 0.0f;
@@ -271,6 +287,7 @@ __global__ void dopred_bwd_kernel(const float* __restrict__ ddo, const float* __
 // out2 (optional) receives the same sums: the two biases of an LSTM layer (i2h, h2h) share one gradient
 __global__ void colsum_kernel(const float* __restrict__ x, int64_t rows, int cols, int ld, float* __restrict__ out, int accumulate,
                               float* __restrict__ out2) {
+  RAU_PDL_ENTRY();
   __shared__ float red[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int64_t per = (rows + gridDim.y - 1) / gridDim.y;
@@ -300,6 +317,7 @@ template <> __device__ __forceinline__ float ldf<bf16>(const bf16* p) { return _
 
 template <typename T>
 __global__ void rowsum_bms_kernel(const T* __restrict__ x, int B, int M, int S, int Sp, float* __restrict__ out) {
+  RAU_PDL_ENTRY();
   __shared__ float red[32];
   const int m = blockIdx.x;
   float s = 0.0f;
@@ -312,6 +330,7 @@ __global__ void rowsum_bms_kernel(const T* __restrict__ x, int B, int M, int S, 
 }
 
 __global__ void sum_all_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out, int accumulate) {
+  RAU_PDL_ENTRY();
   __shared__ float red[32];
   float s = 0.0f;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
@@ -322,6 +341,7 @@ __global__ void sum_all_kernel(const float* __restrict__ x, int64_t n, float* __
 // rnn_out[b] = state_{t = len_b}[b]   (F:472-478 host loop, fused)
 __global__ void select_state_kernel(const float* __restrict__ S_all, int T, int B, int Q,
                                     const float* __restrict__ lengths, float* __restrict__ out) {
+  RAU_PDL_ENTRY();
   const int64_t total = (int64_t)B * Q;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int b = (int)(i / Q);
@@ -338,46 +358,46 @@ int k_mask_gen(rau_ctx* ctx, uint32_t* bits, int64_t n, float p, uint64_t seed, 
   const int64_t nw = (n + 31) / 32;
   double keep = 1.0 - (double)p;
   uint32_t thresh = keep >= 1.0 ? 0xffffffffu : (uint32_t)(keep * 4294967296.0);
-  mask_gen_kernel<<<grid_for(nw), TPB, 0, ctx->stream>>>(bits, nw, n, thresh, p <= 0.0f ? 1 : 0,
+  RAU_LAUNCH_PDL(ctx->stream, (mask_gen_kernel), grid_for(nw), TPB, 0, bits, nw, n, thresh, p <= 0.0f ? 1 : 0,
       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), (uint32_t)stream_id, (uint32_t)(stream_id >> 32), ctx->ss_active);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 int k_mask_pack(rau_ctx* ctx, uint32_t* bits, const uint8_t* bytes, int64_t n) {
   const int64_t nw = (n + 31) / 32;
-  mask_pack_kernel<<<grid_for(nw), TPB, 0, ctx->stream>>>(bits, bytes, nw, n);
+  RAU_LAUNCH_PDL(ctx->stream, (mask_pack_kernel), grid_for(nw), TPB, 0, bits, bytes, nw, n);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 int k_embed_fwd(rau_ctx* ctx, const float* ids, int n, int D, int V, const float* E, const uint32_t* bits, float scale,
                 float* out_f, bf16* out_b, int ldb) {
-  embed_fwd_kernel<<<grid_for((int64_t)n * D), TPB, 0, ctx->stream>>>(ids, n, D, V, E, bits, scale, out_f, out_b, ldb);
+  RAU_LAUNCH_PDL(ctx->stream, (embed_fwd_kernel), grid_for((int64_t)n * D), TPB, 0, ids, n, D, V, E, bits, scale, out_f, out_b, ldb);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 int k_embed_bwd(rau_ctx* ctx, const float* ids, int n, int D, int V, const float* out, const uint32_t* bits, float scale,
                 const float* dout, int lddout, float* gE) {
-  embed_bwd_kernel<<<grid_for((int64_t)n * D), TPB, 0, ctx->stream>>>(ids, n, D, V, out, bits, scale, dout, lddout, gE);
+  RAU_LAUNCH_PDL(ctx->stream, (embed_bwd_kernel), grid_for((int64_t)n * D), TPB, 0, ids, n, D, V, out, bits, scale, dout, lddout, gE);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 int k_lstm_fwd(rau_ctx* ctx, int B, int H, int order, const float* G, int ldg, const float* c_prev, int ldcp,
                float* c, int ldc, float* h, int ldh, bf16* h_b, int ldhb, float* saved) {
-  lstm_fwd_kernel<<<grid_for((int64_t)B * H), TPB, 0, ctx->stream>>>(B, H, order, G, ldg, c_prev, ldcp, c, ldc, h, ldh, h_b, ldhb, saved);
+  RAU_LAUNCH_PDL(ctx->stream, (lstm_fwd_kernel), grid_for((int64_t)B * H), TPB, 0, B, H, order, G, ldg, c_prev, ldcp, c, ldc, h, ldh, h_b, ldhb, saved);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 int k_lstm_bwd(rau_ctx* ctx, int B, int H, int order, const float* dc_out, int lddc, const float* dh_out, int lddh,
                const float* dh_extra, int ldhe, const float* lengths, int t, const float* dq_c, const float* dq_h, int lddq,
                const float* c_prev, int ldcp, const float* saved, float* dG, bf16* dG_b, float* dc_prev, int lddcp, bf16* dG_lo) {
-  lstm_bwd_kernel<<<grid_for((int64_t)B * H), TPB, 0, ctx->stream>>>(B, H, order, dc_out, lddc, dh_out, lddh, dh_extra, ldhe,
+  RAU_LAUNCH_PDL(ctx->stream, (lstm_bwd_kernel), grid_for((int64_t)B * H), TPB, 0, B, H, order, dc_out, lddc, dh_out, lddh, dh_extra, ldhe,
       lengths, t, dq_c, dq_h, lddq, c_prev, ldcp, saved, dG, dG_b, dc_prev, lddcp, dG_lo);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 int k_dropout(rau_ctx* ctx, const float* x, int64_t rows, int cols, int ldx, const uint32_t* bits, float scale,
               float* y_f, int ldyf, bf16* y_b, int ldyb, int cols_pad) {
-  dropout_kernel<<<grid_for(rows * cols_pad, 4), TPB, 0, ctx->stream>>>(x, rows, cols, ldx, bits, scale, y_f, ldyf, y_b, ldyb, cols_pad);
+  RAU_LAUNCH_PDL(ctx->stream, (dropout_kernel), grid_for(rows * cols_pad, 4), TPB, 0, x, rows, cols, ldx, bits, scale, y_f, ldyf, y_b, ldyb, cols_pad);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
@@ -387,49 +407,49 @@ int k_dropout_pack(rau_ctx* ctx, const float* x, int64_t rows, int cols, const u
     rau_set_error("k_dropout_pack: cols=%d cols_pad=%d must be multiples of 4 and x 16-byte aligned", cols, cols_pad);
     return RAU_EINVAL;
   }
-  dropout_pack_kernel<<<grid_for(rows * (cols_pad / 4), 2), TPB, 0, ctx->stream>>>(x, rows, cols, bits, scale, hi, lo, cols_pad);
+  RAU_LAUNCH_PDL(ctx->stream, (dropout_pack_kernel), grid_for(rows * (cols_pad / 4), 2), TPB, 0, x, rows, cols, bits, scale, hi, lo, cols_pad);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 int k_dropout_bwd_acc(rau_ctx* ctx, const float* dx, int64_t n, const uint32_t* bits, float scale, float* y, int accumulate) {
-  dropout_bwd_acc_kernel<<<grid_for(n, 4), TPB, 0, ctx->stream>>>(dx, n, bits, scale, y, accumulate);
+  RAU_LAUNCH_PDL(ctx->stream, (dropout_bwd_acc_kernel), grid_for(n, 4), TPB, 0, dx, n, bits, scale, y, accumulate);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 int k_tanh_bwd(rau_ctx* ctx, const float* dy, const float* y, int64_t n, float* dx_f, bf16* dx_b) {
-  tanh_bwd_kernel<<<grid_for(n, 4), TPB, 0, ctx->stream>>>(dy, y, n, dx_f, dx_b);
+  RAU_LAUNCH_PDL(ctx->stream, (tanh_bwd_kernel), grid_for(n, 4), TPB, 0, dy, y, n, dx_f, dx_b);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 int k_add(rau_ctx* ctx, const float* a, const float* b, int64_t n, float* y) {
-  add_kernel<<<grid_for(n, 4), TPB, 0, ctx->stream>>>(a, b, n, y);
+  RAU_LAUNCH_PDL(ctx->stream, (add_kernel), grid_for(n, 4), TPB, 0, a, b, n, y);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 int k_axpy(rau_ctx* ctx, float alpha, const float* x, int64_t n, float* y) {
-  axpy_kernel<<<grid_for(n, 4), TPB, 0, ctx->stream>>>(alpha, x, n, y);
+  RAU_LAUNCH_PDL(ctx->stream, (axpy_kernel), grid_for(n, 4), TPB, 0, alpha, x, n, y);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 int k_fill(rau_ctx* ctx, float* x, int64_t n, float v) {
   if (n <= 0) return RAU_OK;
-  fill_kernel<<<grid_for(n, 4), TPB, 0, ctx->stream>>>(x, n, v);
+  RAU_LAUNCH_PDL(ctx->stream, (fill_kernel), grid_for(n, 4), TPB, 0, x, n, v);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 int k_to_bf16(rau_ctx* ctx, const float* x, int64_t rows, int cols, int ldx, bf16* y, int ldy, int cols_pad) {
-  to_bf16_kernel<<<grid_for(rows * cols_pad, 4), TPB, 0, ctx->stream>>>(x, rows, cols, ldx, y, ldy, cols_pad);
+  RAU_LAUNCH_PDL(ctx->stream, (to_bf16_kernel), grid_for(rows * cols_pad, 4), TPB, 0, x, rows, cols, ldx, y, ldy, cols_pad);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 int k_rowdot_sigmoid(rau_ctx* ctx, const float* x, int B, int K, const float* w, const float* b, float* y) {
-  rowdot_sigmoid_kernel<<<cdiv((int64_t)B * 32, TPB), TPB, 0, ctx->stream>>>(x, B, K, w, b, y);
+  RAU_LAUNCH_PDL(ctx->stream, (rowdot_sigmoid_kernel), cdiv((int64_t)B * 32, TPB), TPB, 0, x, B, K, w, b, y);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 int k_dopred_bwd(rau_ctx* ctx, const float* ddo, const float* dop, const float* m, const float* wd, int B, int K,
                  float* dm_acc, float* gwd, float* gbd) {
-  dopred_bwd_kernel<<<cdiv(K, TPB), TPB, 0, ctx->stream>>>(ddo, dop, m, wd, B, K, dm_acc, gwd, gbd);
+  RAU_LAUNCH_PDL(ctx->stream, (dopred_bwd_kernel), cdiv(K, TPB), TPB, 0, ddo, dop, m, wd, B, K, dm_acc, gwd, gbd);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
@@ -441,25 +461,25 @@ int k_colsum(rau_ctx* ctx, const float* x, int64_t rows, int cols, int ld, float
     if (slices > want) slices = want;
     if (slices < 1) slices = 1;
   }
-  colsum_kernel<<<dim3(cdiv(cols, 32), slices), dim3(32, 8), 0, ctx->stream>>>(x, rows, cols, ld, out, accumulate, out2);
+  RAU_LAUNCH_PDL(ctx->stream, (colsum_kernel), dim3(cdiv(cols, 32), slices), dim3(32, 8), 0, x, rows, cols, ld, out, accumulate, out2);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 template <typename T>
 int k_rowsum_bms(rau_ctx* ctx, const T* x, int B, int M, int S, int Sp, float* out) {
-  rowsum_bms_kernel<T><<<dim3(M, B >= 16 ? 16 : 1), 64, 0, ctx->stream>>>(x, B, M, S, Sp, out);
+  RAU_LAUNCH_PDL(ctx->stream, (rowsum_bms_kernel<T>), dim3(M, B >= 16 ? 16 : 1), 64, 0, x, B, M, S, Sp, out);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 template int k_rowsum_bms<float>(rau_ctx*, const float*, int, int, int, int, float*);
 template int k_rowsum_bms<bf16>(rau_ctx*, const bf16*, int, int, int, int, float*);
 int k_sum_all(rau_ctx* ctx, const float* x, int64_t n, float* out, int accumulate) {
-  sum_all_kernel<<<1, 1024, 0, ctx->stream>>>(x, n, out, accumulate);
+  RAU_LAUNCH_PDL(ctx->stream, (sum_all_kernel), 1, 1024, 0, x, n, out, accumulate);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 int k_select_state(rau_ctx* ctx, const float* S_all, int T, int B, int Q, const float* lengths, float* out) {
-  select_state_kernel<<<grid_for((int64_t)B * Q), TPB, 0, ctx->stream>>>(S_all, T, B, Q, lengths, out);
+  RAU_LAUNCH_PDL(ctx->stream, (select_state_kernel), grid_for((int64_t)B * Q), TPB, 0, S_all, T, B, Q, lengths, out);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }

@@ -245,6 +245,7 @@ __device__ __forceinline__ float warp_transpose_sum32(float* x, int lane) {
 
 template <int EPI, int X3, int NSTEPS>
 __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_constant__ RtParams p) {
+  asm volatile("griddepcontrol.launch_dependents;");   // PDL: the next kernel may begin its prologue
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t full_bar[RT_MAXSTAGES], empty_bar[RT_MAXSTAGES], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
@@ -276,6 +277,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
   if (threadIdx.x == 0) RT_STAMP(1);   // prologue done
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // PDL: everything earlier kernels wrote is visible from here on
 
   const uint32_t a_bytes = (uint32_t)RT_BM * p.BK * 2, b_bytes = (uint32_t)p.BN * p.BK * 2;
   constexpr int nt = X3 ? 2 : 1;
@@ -756,7 +758,7 @@ int launch_rows_v(rau_ctx* ctx, const RtParams& p, int grid, int smem_bytes) {
                                         RT_SMEM_BUDGET + 1024));
     attr_done = true;
   }
-  rows_gemm_kernel<EPI, X3, NSTEPS><<<grid, RT_THREADS, smem_bytes, ctx->stream>>>(p);
+  RAU_LAUNCH_PDL(ctx->stream, (rows_gemm_kernel<EPI, X3, NSTEPS>), grid, RT_THREADS, smem_bytes, p);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
@@ -768,6 +770,7 @@ int launch_rows(rau_ctx* ctx, const RtParams& p, int grid, int smem_bytes) {
 }
 
 __global__ void pack_hilo_kernel(const float* __restrict__ in, int64_t n4, bf16* __restrict__ hi, bf16* __restrict__ lo) {
+  RAU_PDL_ENTRY();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 x = reinterpret_cast<const float4*>(in)[i];
     uint32_t h0, l0, h1, l1;
@@ -785,6 +788,7 @@ __global__ void __launch_bounds__(256) xprep_rows_kernel(const float* __restrict
                                                          int C, int S, bf16* __restrict__ hi, bf16* __restrict__ lo, int gen,
                                                          uint32_t thresh, uint2 key, uint32_t stream_lo, uint32_t stream_hi,
                                                          const StepState* __restrict__ ss) {
+  RAU_PDL_ENTRY();
   extern __shared__ float sT[];   // [S][66]
   const int b = blockIdx.y, c0 = blockIdx.x * 64;
   const int S4 = S >> 2;
@@ -829,6 +833,7 @@ __global__ void __launch_bounds__(256) xprep_rows_kernel(const float* __restrict
 // dXr [B*S, C] fp32 -> dX [B, C, S] = dXr^T * keep * scale  (backward of the feature dropout, F:239)
 __global__ void __launch_bounds__(256) unprep_rows_kernel(const float* __restrict__ dXr, const uint32_t* __restrict__ bits, float scale,
                                                           int C, int S, float* __restrict__ dX) {
+  RAU_PDL_ENTRY();
   extern __shared__ float sT[];   // [S][66]
   const int b = blockIdx.y, c0 = blockIdx.x * 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -860,6 +865,7 @@ __global__ void __launch_bounds__(256) attn_rows_fwd_kernel(int S, int M, const 
                                                             const float* __restrict__ mem, const bf16* __restrict__ I_hi,
                                                             const bf16* __restrict__ I_lo, float* __restrict__ p_out,
                                                             float* __restrict__ a_out) {
+  RAU_PDL_ENTRY();
   extern __shared__ float sm[];
   float* p = sm;           // [256]
   float* part = sm + 256;  // [ngroups][M]
@@ -911,6 +917,7 @@ __global__ void __launch_bounds__(256) attn_rows_bwd_kernel(int S, int M, int A,
                                                             float* __restrict__ ds_out, bf16* __restrict__ dZ_hi,
                                                             bf16* __restrict__ dZ_lo, float* __restrict__ dqa,
                                                             float* __restrict__ gws_part) {
+  RAU_PDL_ENTRY();
   extern __shared__ float sm[];
   float* ds = sm;            // [256]
   float* das = sm + 256;     // [M]
@@ -1016,7 +1023,9 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   int BN = g.BN;
   if (BN == 0) {
     BN = 256;
-    if (g.epi == EPI_LINEAR || g.epi == EPI_PLAIN || g.epi == EPI_LSTM || g.epi == EPI_RED)
+    // (split-K reductions keep 256-wide tiles unless the output is a thin [<= 256, N] slab: their SM fill comes from
+    // the K split, and wide tiles re-read less of the A operand)
+    if (g.epi == EPI_LINEAR || g.epi == EPI_PLAIN || g.epi == EPI_LSTM || (g.epi == EPI_RED && p.tiles_m <= 2))
       while (BN > 64 && (long long)p.tiles_m * ((g.N + BN - 1) / BN) < ctx->sm_count) BN >>= 1;
     while (BN > 64 && g.N <= BN / 2) BN >>= 1;
   }
@@ -1161,7 +1170,7 @@ int rows_pack(rau_ctx* ctx, const float* W, int64_t n, bool want_lo, bool cache,
   if (!cached) {
     int64_t blocks = (n / 4 + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    pack_hilo_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(W, n / 4, h, l);
+    RAU_LAUNCH_PDL(ctx->stream, (pack_hilo_kernel), (int)blocks, 256, 0, W, n / 4, h, l);
     RAU_LAUNCH_CHECK(ctx);
     if (cache) ctx->tc_epoch[name] = ctx->epoch;
   }
@@ -1185,7 +1194,7 @@ int k_xprep_rows(rau_ctx* ctx, const float* X, int B, int C, int S, const uint32
   RAU_TRY(prep_attr());
   const double keep = 1.0 - (double)p_drop;
   const uint32_t thresh = keep >= 1.0 ? 0xffffffffu : (uint32_t)(keep * 4294967296.0);
-  xprep_rows_kernel<<<dim3(C / 64, B), 256, S * 66 * 4, ctx->stream>>>(
+  RAU_LAUNCH_PDL(ctx->stream, (xprep_rows_kernel), dim3(C / 64, B), 256, S * 66 * 4, 
       X, bits, scale, C, S, hi, lo, gen, thresh, make_uint2((uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32)), (uint32_t)stream_id,
       (uint32_t)(stream_id >> 32), ctx->ss_active);
   RAU_LAUNCH_CHECK(ctx);
@@ -1195,7 +1204,7 @@ int k_xprep_rows(rau_ctx* ctx, const float* X, int B, int C, int S, const uint32
 int k_unprep_rows(rau_ctx* ctx, const float* dXr, int B, int C, int S, const uint32_t* bits, float scale, float* dX) {
   RAU_REQUIRE(C % 64 == 0 && S % 4 == 0 && S <= 256 && ((uintptr_t)dX & 15) == 0, "k_unprep_rows: C=%d S=%d", C, S);
   RAU_TRY(prep_attr());
-  unprep_rows_kernel<<<dim3(C / 64, B), 256, S * 66 * 4, ctx->stream>>>(dXr, bits, scale, C, S, dX);
+  RAU_LAUNCH_PDL(ctx->stream, (unprep_rows_kernel), dim3(C / 64, B), 256, S * 66 * 4, dXr, bits, scale, C, S, dX);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
@@ -1203,7 +1212,7 @@ int k_unprep_rows(rau_ctx* ctx, const float* dXr, int B, int C, int S, const uin
 int k_attn_rows_fwd(rau_ctx* ctx, int B, int M, int S, const float* logit, const float* mem, const bf16* I_hi, const bf16* I_lo,
                     float* p, float* a) {
   RAU_REQUIRE((M == 256 || M == 512 || M == 1024 || M == 2048) && S <= 256, "k_attn_rows_fwd: M=%d S=%d", M, S);
-  attn_rows_fwd_kernel<<<B, 256, (256 + 256 / (M / 8) * M) * sizeof(float), ctx->stream>>>(S, M, logit, mem, I_hi, I_lo, p, a);
+  RAU_LAUNCH_PDL(ctx->stream, (attn_rows_fwd_kernel), B, 256, (256 + 256 / (M / 8) * M) * sizeof(float), S, M, logit, mem, I_hi, I_lo, p, a);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
@@ -1212,7 +1221,7 @@ int k_attn_rows_bwd(rau_ctx* ctx, int B, int M, int A, int S, const float* E, co
                     const float* p, const float* dp_in, const float* da, float* ds, bf16* dZ_hi, bf16* dZ_lo, float* dqa,
                     float* gws_part) {
   RAU_REQUIRE(M % 8 == 0 && S <= 256 && (A == 64 || A == 128 || A == 256), "k_attn_rows_bwd: M=%d A=%d S=%d", M, A, S);
-  attn_rows_bwd_kernel<<<B, 256, (256 + M + 2048) * sizeof(float), ctx->stream>>>(S, M, A, E, I_hi, I_lo, ws, p, dp_in, da, ds, dZ_hi,
+  RAU_LAUNCH_PDL(ctx->stream, (attn_rows_bwd_kernel), B, 256, (256 + M + 2048) * sizeof(float), S, M, A, E, I_hi, I_lo, ws, p, dp_in, da, ds, dZ_hi,
                                                                             dZ_lo, dqa, gws_part);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
@@ -1224,6 +1233,7 @@ namespace {
 // fp32 [rows, cols] (pitch ld) -> packed bf16 (hi [, lo]) [rows, ldo] with ldo = cols rounded up to 8, zero padded
 __global__ void pack2d_kernel(const float* __restrict__ in, int64_t ld, int rows, int cols, int ldo, bf16* __restrict__ hi,
                               bf16* __restrict__ lo) {
+  RAU_PDL_ENTRY();
   const int q = ldo >> 1;   // pairs per packed row
   const int64_t total = (int64_t)rows * q;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1264,7 +1274,16 @@ int pack2d(rau_ctx* ctx, const float* src, int64_t ld, int rows, int cols, bool 
     int64_t blocks = (work + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
-    pack2d_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(src, ld, rows, cols, ldo, (bf16*)out->hi, (bf16*)out->lo);
+    {
+      static bool carve = false;
+      if (!carve) {
+        const char* e = getenv("RAU_CARVEOUT");
+        if (!e || atoi(e) != 0)
+          cudaFuncSetAttribute(pack2d_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carve = true;
+      }
+    }
+    RAU_LAUNCH_PDL(ctx->stream, (pack2d_kernel), (int)blocks, 256, 0, src, ld, rows, cols, ldo, (bf16*)out->hi, (bf16*)out->lo);
     RAU_LAUNCH_CHECK(ctx);
     if (is_const) ctx->tc_epoch[name] = ctx->epoch;
   }
@@ -1284,6 +1303,7 @@ namespace {
 // (k = 0..3 = i, f, o, g) of hidden unit u; bsum[n'] = bi + bh in the same order
 __global__ void pack_lstm_kernel(const float* __restrict__ W, int H, int K, int ldo, int c_i, int c_f, int c_o, int c_g,
                                  bf16* __restrict__ hi, bf16* __restrict__ lo) {
+  RAU_PDL_ENTRY();
   const int q = ldo >> 1;
   const int64_t total = (int64_t)4 * H * q;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1302,6 +1322,7 @@ __global__ void pack_lstm_kernel(const float* __restrict__ W, int H, int K, int 
 }
 __global__ void perm_bias_kernel(const float* __restrict__ b1, const float* __restrict__ b2, int H, int c_i, int c_f, int c_o,
                                  int c_g, float* __restrict__ out) {
+  RAU_PDL_ENTRY();
   const int np = blockIdx.x * blockDim.x + threadIdx.x;
   if (np >= 4 * H) return;
   const int grp = np >> 5, k = (np & 31) >> 3, uu = np & 7;
@@ -1331,7 +1352,7 @@ int rows_pack_lstm(rau_ctx* ctx, const float* W, int H, int K, int gate_order, b
     const int64_t work = (int64_t)4 * H * (ld / 2);
     int64_t blocks = (work + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    pack_lstm_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(W, H, K, ld, ci, cf, co, cg, (bf16*)*hi, (bf16*)*lo);
+    RAU_LAUNCH_PDL(ctx->stream, (pack_lstm_kernel), (int)blocks, 256, 0, W, H, K, ld, ci, cf, co, cg, (bf16*)*hi, (bf16*)*lo);
     RAU_LAUNCH_CHECK(ctx);
     ctx->tc_epoch[name] = ctx->epoch;
   }
@@ -1349,7 +1370,7 @@ int rows_perm_lstm_bias(rau_ctx* ctx, const float* b1, const float* b2, int H, i
   RAU_TRY(ctx->arena.get(name, sizeof(float) * 4 * (size_t)H, &buf));
   *out = (const float*)buf;
   if (!cached) {
-    perm_bias_kernel<<<(4 * H + 255) / 256, 256, 0, ctx->stream>>>(b1, b2, H, ci, cf, co, cg, (float*)buf);
+    RAU_LAUNCH_PDL(ctx->stream, (perm_bias_kernel), (4 * H + 255) / 256, 256, 0, b1, b2, H, ci, cf, co, cg, (float*)buf);
     RAU_LAUNCH_CHECK(ctx);
     ctx->tc_epoch[name] = ctx->epoch;
   }
@@ -1361,6 +1382,7 @@ namespace {
 __global__ void linear_init_kernel(float* __restrict__ C, long long ldc, int M, int N, const float* __restrict__ bias,
                                    const float* __restrict__ bias2, const float* __restrict__ addend,
                                    const float* __restrict__ addend2, long long ldadd) {
+  RAU_PDL_ENTRY();
   const long long total = (long long)M * N;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int n = (int)(i % N);
@@ -1433,7 +1455,7 @@ int rows_contract_try(rau_ctx* ctx, const SimtGemm& g) {
       const long long total = (long long)g.M * g.N;
       int blocks = (int)((total + 1023) / 1024);
       if (blocks > 148 * 4) blocks = 148 * 4;
-      linear_init_kernel<<<blocks, 256, 0, ctx->stream>>>(g.C, g.scm, g.M, g.N, g.bias_n, g.bias_n2, g.addend, g.addend2, g.sdm);
+      RAU_LAUNCH_PDL(ctx->stream, (linear_init_kernel), blocks, 256, 0, g.C, g.scm, g.M, g.N, g.bias_n, g.bias_n2, g.addend, g.addend2, g.sdm);
       RAU_LAUNCH_CHECK(ctx);
     } else {
       RAU_CHECK_CUDA(cudaMemset2DAsync(g.C, (size_t)g.scm * 4, 0, (size_t)g.N * 4, (size_t)g.M, ctx->stream));

@@ -102,6 +102,40 @@ void rau_phase_mark(rau_ctx* ctx, const char* name);
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// The step is a chain of ~700 short dependent kernels.  Every kernel of the library starts with RAU_PDL_ENTRY(): it lets
+// the NEXT kernel of the stream be scheduled early (griddepcontrol.launch_dependents) and then waits until everything
+// the PREVIOUS kernels wrote is visible (griddepcontrol.wait) before touching memory.  Launches carry the
+// programmatic-stream-serialization attribute, so launch latency, CTA scheduling, instruction fetch and the tcgen05
+// prologue (barrier init, TMEM allocation, tensor-map prefetch) of kernel i+1 overlap the tail of kernel i; data
+// dependencies stay exactly those of a serial stream.  The attribute is OFF by default (RAU_PDL=1 turns it on): inside
+// the replayed CUDA graph of the step it measured slightly slower than plain serial edges (profiles/README.md).
+#define RAU_PDL_ENTRY()                                              \
+  do {                                                               \
+    asm volatile("griddepcontrol.launch_dependents;");               \
+    asm volatile("griddepcontrol.wait;" ::: "memory");               \
+  } while (0)
+
+bool rau_pdl_enabled();
+
+template <typename... Exp, typename... Act>
+static inline cudaError_t rau_launch_pdl(cudaStream_t st, void (*kern)(Exp...), dim3 grid, dim3 block, size_t smem, Act&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = rau_pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<Act&&>(args)...);
+}
+#define RAU_LAUNCH_PDL(stream, kern, grid, block, smem, ...) \
+  (void)rau_launch_pdl(stream, kern, dim3(grid), dim3(block), (size_t)(smem), __VA_ARGS__)
+
 // ------------------------------------------------------------------ device helpers
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 

@@ -42,6 +42,15 @@ void RauArena::release() {
 
 int rau_comm_destroy_internal(rau_ctx* ctx);  // rau_comm.cu
 
+bool rau_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RAU_PDL");
+    v = e ? (atoi(e) != 0) : 0;   // opt-in: measured 4 % SLOWER on the graph-replayed Ours_Full step (8.13 vs 7.79 ms)
+  }
+  return v != 0;
+}
+
 void rau_phase_mark(rau_ctx* ctx, const char* name) {
   if (ctx->phases < 0) {
     const char* e = getenv("RAU_PHASES");

@@ -710,6 +710,57 @@ int rau_rows_gemm(rau_ctx* ctx, int M, int N, int K, const float* A, int lda, in
   return rows_gemm(ctx, g);
 }
 
+int rau_rows_gemm_time(rau_ctx* ctx, int M, int N, int K, int a_mn, int b_mn, int reduce, int iters, float* us_per_launch) {
+  RAU_REQUIRE(ctx && us_per_launch && iters > 0, "bad arguments");
+  RAU_REQUIRE(ctx->precision != RAU_PREC_F32, "rau_rows_gemm_time: tcgen05 modes only");
+  RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  ctx->epoch++;
+  const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+  const int64_t lda = a_mn ? (M + 7) / 8 * 8 : (K + 7) / 8 * 8, ldb = b_mn ? (N + 7) / 8 * 8 : (K + 7) / 8 * 8;
+  const int64_t na = (int64_t)(a_mn ? K : M) * lda, nb = (int64_t)(b_mn ? K : N) * ldb;
+  float *A = nullptr, *B = nullptr, *D = nullptr;
+  RAU_TRY(ctx->arena.get("gt.A", sizeof(float) * na, (void**)&A));
+  RAU_TRY(ctx->arena.get("gt.B", sizeof(float) * nb, (void**)&B));
+  RAU_TRY(ctx->arena.get("gt.D", sizeof(float) * (size_t)M * ((N + 3) / 4 * 4), (void**)&D));
+  RAU_TRY(k_fill(ctx, A, na, 0.01f));
+  RAU_TRY(k_fill(ctx, B, nb, 0.02f));
+  RAU_TRY(k_fill(ctx, D, (int64_t)M * ((N + 3) / 4 * 4), 0.0f));
+  RowsGemm g;
+  g.M = M; g.N = N; g.K = K;
+  RAU_TRY(rows_pack(ctx, A, na, x3, false, "gt.A", &g.A.hi, &g.A.lo));
+  RAU_TRY(rows_pack(ctx, B, nb, x3, false, "gt.B", &g.B.hi, &g.B.lo));
+  g.A.mn = a_mn; g.A.ld = lda; g.B.mn = b_mn; g.B.ld = ldb;
+  g.epi = reduce ? ROWS_EPI_RED : ROWS_EPI_PLAIN;
+  g.out_f = D; g.ldo = (N + 3) / 4 * 4;
+  RAU_TRY(rows_gemm(ctx, g));   // warm-up (function attributes, arena)
+  RAU_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  // the launches go into one CUDA graph so that the host's launch cost does not bound the measurement
+  cudaStream_t user = ctx->stream;
+  ctx->stream = ctx->gstream;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int r = RAU_OK;
+  if (cudaStreamBeginCapture(ctx->gstream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { ctx->stream = user; rau_set_error("capture failed"); return RAU_ECUDA; }
+  for (int i = 0; i < iters && r == RAU_OK; ++i) r = rows_gemm(ctx, g);
+  cudaError_t e = cudaStreamEndCapture(ctx->gstream, &graph);
+  ctx->stream = user;
+  if (r != RAU_OK) return r;
+  RAU_CHECK_CUDA(e);
+  RAU_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+  RAU_CHECK_CUDA(cudaGraphLaunch(exec, user));
+  RAU_CHECK_CUDA(cudaStreamSynchronize(user));
+  RAU_CHECK_CUDA(cudaEventRecord(ctx->ev0, user));
+  RAU_CHECK_CUDA(cudaGraphLaunch(exec, user));
+  RAU_CHECK_CUDA(cudaEventRecord(ctx->ev1, user));
+  RAU_CHECK_CUDA(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.0f;
+  RAU_CHECK_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *us_per_launch = ms * 1000.0f / iters;
+  cudaGraphExecDestroy(exec);
+  cudaGraphDestroy(graph);
+  return RAU_OK;
+}
+
 int rau_rows_trace(rau_ctx* ctx, uint64_t* out, int n) {
   RAU_REQUIRE(ctx && out && n > 0, "bad arguments");
   void* buf = nullptr;
