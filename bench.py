@@ -302,6 +302,9 @@ def main():
                     gpu_launches=int(launches), launches_per_step=launches / args.steps, clocks=clocks, roofline=roof,
                     cpu_baseline=cpu)
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

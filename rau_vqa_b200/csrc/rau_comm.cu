@@ -70,6 +70,10 @@ int rau_allreduce_internal(rau_ctx* ctx, float* buf, int64_t n) {
 
 int rau_comm_destroy_internal(rau_ctx* ctx) {
   if (ctx->comm) {
+    // CUDA graphs that captured an all-reduce reference the communicator: destroy them first (ncclCommDestroy
+    // otherwise waits forever), and let every queued collective finish
+    ctx->graph.clear();
+    cudaStreamSynchronize(ctx->stream);
     if (ctx->comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm->comm);
     delete ctx->comm;
     ctx->comm = nullptr;

@@ -127,9 +127,10 @@ int rau_ctx_destroy(rau_ctx* ctx) {
   if (ctx == nullptr) return RAU_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  ctx->graph.clear();            // captured steps hold NCCL kernels: they must be gone before the communicator is
+  cudaDeviceSynchronize();
   rau_comm_destroy_internal(ctx);
   ctx->arena.release();
-  ctx->graph.clear();
   if (ctx->d_ss) cudaFree(ctx->d_ss);
   if (ctx->h_ss) cudaFreeHost(ctx->h_ss);
   if (ctx->gstream) cudaStreamDestroy(ctx->gstream);
