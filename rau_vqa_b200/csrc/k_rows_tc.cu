@@ -1014,6 +1014,8 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   RAU_TRY(get_encode());
   RtParams p;
   memset(&p, 0, sizeof(p));
+  // work enqueued on the side stream shares the GPU with the critical chain: it gets rows_cta_cap SMs
+  const int sm_avail = (ctx->rows_cta_cap > 0 && ctx->rows_cta_cap < ctx->sm_count) ? ctx->rows_cta_cap : ctx->sm_count;
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.a_mn = g.A.mn; p.b_mn = g.B.mn;
   p.x3 = g.A.lo ? 1 : 0;
@@ -1054,8 +1056,8 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   if (p.stages > RT_MAXSTAGES) p.stages = RT_MAXSTAGES;
   const int tiles = p.tiles_m * p.tiles_n;
   p.ksplit = 1;
-  if (g.epi == EPI_RED && tiles < ctx->sm_count) {
-    int want = ctx->sm_count / tiles;
+  if (g.epi == EPI_RED && tiles < sm_avail) {
+    int want = sm_avail / tiles;
     if (want > p.nkb) want = p.nkb;
     if (want < 1) want = 1;
     p.ksplit = want;
@@ -1127,7 +1129,7 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   p.alpha = g.alpha;
   p.fast_tanh = p.x3 ? 0 : 1;   // single-pass bf16: the result is rounded to bf16 anyway, MUFU.TANH (2^-11) is below that
   const int items = tiles * p.ksplit;
-  const int grid = items < ctx->sm_count ? items : ctx->sm_count;
+  const int grid = items < sm_avail ? items : sm_avail;
   {
     static int trace = -1;
     if (trace < 0) { const char* e = getenv("RAU_ROWS_TRACE"); trace = e ? atoi(e) : 0; }

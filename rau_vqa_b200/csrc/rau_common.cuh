@@ -84,6 +84,13 @@ struct rau_ctx {
   const StepState* ss_active = nullptr;            // non-null while a whole-step call is being enqueued
   cudaStream_t gstream = nullptr;                  // capture stream (the caller's stream may be the legacy one)
   RauGraph graph;
+  // side stream for the heavy image-side products that are off the recurrence's critical path (rau_step.cu): they run
+  // on at most side_ctas SMs next to the chain of small dependent kernels.  RAU_OVERLAP=0 disables it.
+  cudaStream_t side = nullptr;
+  std::vector<cudaEvent_t> side_ev;
+  int side_ev_next = 0;
+  int side_ctas = 0;
+  int rows_cta_cap = 0;                            // > 0 while work is being enqueued on the side stream
   // RAU_PHASES=1: eager steps with an event at every phase boundary; rau_phase_report() prints the split
   int phases = -1;
   std::vector<std::pair<std::string, cudaEvent_t>> phase_ev;

@@ -71,9 +71,38 @@ static int rows_wgrad(rau_ctx* ctx, RowsGemm g, float* dst, int ldd) {
   return RAU_OK;
 }
 
+cudaEvent_t rau_side_event(rau_ctx* ctx) {
+  if (ctx->side_ev_next >= (int)ctx->side_ev.size()) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ctx->side_ev.push_back(e);
+  }
+  return ctx->side_ev[ctx->side_ev_next++];
+}
+
+// feature dropout + transpose to rows + bf16 split, then I = tanh(drop(X)^T Wi^T + bi) (F:238-242): the part of a hop's
+// forward that does not depend on the recurrent state
+int hop_forward_pre(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const float*>& P, const float* X, int train,
+                    const HopSaved& sv) {
+  const int M = cfg->M, S = cfg->S, C = cfg->C, R = B * S;
+  const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+  const uint32_t* xb = (train && cfg->p_x > 0) ? sv.xbits : nullptr;
+  const bf16 *Wi_h, *Wi_l;
+  RAU_TRY(rows_pack(ctx, P.Wi, (int64_t)M * C, x3, true, nullptr, &Wi_h, &Wi_l));
+  RAU_TRY(k_xprep_rows(ctx, X, B, C, S, xb, drop_scale(cfg->p_x), sv.Xd_hi, x3 ? sv.Xd_lo : nullptr,
+                       (train && cfg->p_x > 0 && sv.x_philox) ? 1 : 0, cfg->p_x, sv.x_stream));
+  RowsGemm g;
+  g.M = R; g.N = M; g.K = C;
+  g.A.hi = sv.Xd_hi; g.A.lo = x3 ? sv.Xd_lo : nullptr; g.A.ld = C;
+  g.B.hi = Wi_h; g.B.lo = Wi_l; g.B.ld = C;
+  g.epi = ROWS_EPI_TANH; g.bias = P.bi;
+  g.out_hi = sv.I_hi; g.out_lo = x3 ? sv.I_lo : nullptr; g.ldo = M;
+  return rows_gemm(ctx, g);
+}
+
 int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const float*>& P,
                 const float* q, const float* X, const float* c, const float* h, int train, const HopSaved& sv,
-                float* score, float* do_pred, float* p_out, float* c_out, float* h_out) {
+                float* score, float* do_pred, float* p_out, float* c_out, float* h_out, const HopAsync* as) {
   const int Q = 2 * cfg->Hq * cfg->nlayer, M = cfg->M, A = cfg->A, H = cfg->H, S = cfg->S, C = cfg->C, N = cfg->N;
   const int Sp = rau_sp(S);
   const uint32_t* qb = (train && cfg->p_q > 0) ? sv.qbits : nullptr;
@@ -104,16 +133,10 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
     RAU_TRY(rows_pack(ctx, P.Wi, (int64_t)M * C, x3, true, nullptr, &Wi_h, &Wi_l));
     RAU_TRY(rows_pack(ctx, P.Wa, (int64_t)A * M, x3, true, nullptr, &Wa_h, &Wa_l));
     ARENA(slog, float, "hop.slog", R);
-    RAU_TRY(k_xprep_rows(ctx, X, B, C, S, xb, drop_scale(cfg->p_x), sv.Xd_hi, x3 ? sv.Xd_lo : nullptr,
-                         (train && cfg->p_x > 0 && sv.x_philox) ? 1 : 0, cfg->p_x, sv.x_stream));
-    {   // i_embed (F:238-242): I = tanh(drop(X)^T Wi^T + bi)
-      RowsGemm g;
-      g.M = R; g.N = M; g.K = C;
-      g.A.hi = sv.Xd_hi; g.A.lo = x3 ? sv.Xd_lo : nullptr; g.A.ld = C;
-      g.B.hi = Wi_h; g.B.lo = Wi_l; g.B.ld = C;
-      g.epi = ROWS_EPI_TANH; g.bias = P.bi;
-      g.out_hi = sv.I_hi; g.out_lo = x3 ? sv.I_lo : nullptr; g.ldo = M;
-      RAU_TRY(rows_gemm(ctx, g));
+    if (as && as->pre_done) {
+      (void)Wi_h; (void)Wi_l;   // hop_forward_pre() ran the feature pack and the i_embed product on the side stream
+    } else {
+      RAU_TRY(hop_forward_pre(ctx, cfg, B, P, X, train, sv));
     }
     {
       SimtGemm g = lin_fwd(B, A, M, sv.qf, M, P.Wqa, qatt, A);
@@ -125,6 +148,7 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
       g.bias_n = P.bm;
       RAU_TRY(rau_contract(ctx, g));
     }
+    if (as && as->pre_done) RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, as->pre_done, 0));
     {   // attbycontent (F:244-252): E = tanh(I Wa^T + ba + qatt[b]) ; logit = ws.E (bs shifts every logit alike)
       RowsGemm g;
       g.M = R; g.N = A; g.K = M;
@@ -233,7 +257,7 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
 int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const float*>& P, const MultT<float*>& G,
                  const float* X, const float* c, const float* h, int train, const HopSaved& sv,
                  const float* dscore, const float* ddo_pred, const float* dp_att, const float* dc_out, const float* dh_out,
-                 float* dq, int dq_accumulate, float* dX, float* dc, float* dh, const HopGrads* deferred) {
+                 float* dq, int dq_accumulate, float* dX, float* dc, float* dh, const HopGrads* deferred, const HopAsync* as) {
   const int Q = 2 * cfg->Hq * cfg->nlayer, M = cfg->M, A = cfg->A, H = cfg->H, S = cfg->S, C = cfg->C, N = cfg->N;
   const int Sp = rau_sp(S);
   const uint32_t* qb = (train && cfg->p_q > 0) ? sv.qbits : nullptr;
@@ -256,11 +280,15 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   float* ds = now ? ds_own : deferred->ds;
   float* dZ = nullptr;
   bf16 *dZ_hi = nullptr, *dZ_lo = nullptr, *dY_hi = nullptr, *dY_lo = nullptr;
+  const bool side = as && as->bwd_side && ctx->side != nullptr && dX == nullptr;
   if (tc) {
-    RAU_TRY(ctx->arena.get("hopb.dZh", sizeof(bf16) * (size_t)B * A * Sp, (void**)&dZ_hi));
+    // the side stream may still be reading hop h's dZ while the chain writes hop h-1's: one dZ per hop in that mode
+    char zh[32] = "hopb.dZh", zl[32] = "hopb.dZl";
+    if (side) { snprintf(zh, sizeof(zh), "hopb.dZh.%d", as->hop); snprintf(zl, sizeof(zl), "hopb.dZl.%d", as->hop); }
+    RAU_TRY(ctx->arena.get(zh, sizeof(bf16) * (size_t)B * A * Sp, (void**)&dZ_hi));
     RAU_TRY(ctx->arena.get("hopb.dYh", sizeof(bf16) * (size_t)B * M * Sp, (void**)&dY_hi));
     if (x3) {
-      RAU_TRY(ctx->arena.get("hopb.dZl", sizeof(bf16) * (size_t)B * A * Sp, (void**)&dZ_lo));
+      RAU_TRY(ctx->arena.get(zl, sizeof(bf16) * (size_t)B * A * Sp, (void**)&dZ_lo));
       RAU_TRY(ctx->arena.get("hopb.dYl", sizeof(bf16) * (size_t)B * M * Sp, (void**)&dY_lo));
     }
   } else {
@@ -346,6 +374,19 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   if (rows) {
     const bf16 *Wa_h, *Wa_l;
     RAU_TRY(rows_pack(ctx, P.Wa, (int64_t)A * M, x3, true, nullptr, &Wa_h, &Wa_l));
+    // nothing below feeds the previous hop's backward: in the training step these three products go to the side stream
+    // (capped to ctx->side_ctas SMs) and overlap the chain of small kernels; the caller joins the stream at the end
+    cudaStream_t chain = ctx->stream;
+    if (side) {
+      cudaEvent_t ev = rau_side_event(ctx);
+      RAU_REQUIRE(ev != nullptr, "cudaEventCreate failed");
+      RAU_CHECK_CUDA(cudaEventRecord(ev, chain));
+      RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->side, ev, 0));
+      ctx->stream = ctx->side;
+      ctx->rows_cta_cap = ctx->side_ctas;
+    }
+    int side_rc = RAU_OK;
+    do {
     {   // dY = (dZ Wa + da p^T) (1 - I^2) ; gbi += sum_r dY   (dI never leaves the accumulator)
       RowsGemm g;
       g.M = R; g.N = M; g.K = A;
@@ -354,15 +395,26 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
       g.epi = ROWS_EPI_DY; g.rowvec = dj; g.rowscale = sv.p; g.S = S;
       g.aux_hi = sv.I_hi; g.aux_lo = x3 ? sv.I_lo : nullptr; g.ldaux = M; g.colsum = G.bi;
       g.out_hi = dY_hi; g.out_lo = dY_lo; g.ldo = M;
-      RAU_TRY(rows_gemm(ctx, g));
+      if ((side_rc = rows_gemm(ctx, g)) != RAU_OK) break;
     }
     {   // gWa += dZ^T I
       RowsGemm g;
       g.M = A; g.N = M; g.K = R;
       g.A.hi = dZ_hi; g.A.lo = dZ_lo; g.A.mn = 1; g.A.ld = A;
       g.B.hi = sv.I_hi; g.B.lo = x3 ? sv.I_lo : nullptr; g.B.mn = 1; g.B.ld = M;
-      RAU_TRY(rows_wgrad(ctx, g, G.Wa, M));
+      if ((side_rc = rows_wgrad(ctx, g, G.Wa, M)) != RAU_OK) break;
     }
+    if (side) {   // gWi += dY^T drop(X)^T (issued further down in the synchronous mode)
+      RowsGemm g;
+      g.M = M; g.N = C; g.K = R;
+      g.A.hi = dY_hi; g.A.lo = dY_lo; g.A.mn = 1; g.A.ld = M;
+      g.B.hi = sv.Xd_hi; g.B.lo = x3 ? sv.Xd_lo : nullptr; g.B.mn = 1; g.B.ld = C;
+      if ((side_rc = rows_wgrad(ctx, g, G.Wi, C)) != RAU_OK) break;
+    }
+    } while (0);
+    ctx->stream = chain;
+    ctx->rows_cta_cap = 0;
+    RAU_TRY(side_rc);
   } else {
   // dI = Wa^T dZ (+ da p^T inside the pointwise) ; dY = dI (1 - I^2)
   {
@@ -401,7 +453,7 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
     RAU_TRY(k_colsum(ctx, dqa, B, A, A, G.bqa, 1));
   }
   if (rows) {
-    {   // gWi += dY^T drop(X)^T
+    if (!side) {   // gWi += dY^T drop(X)^T
       RowsGemm g;
       g.M = M; g.N = C; g.K = R;
       g.A.hi = dY_hi; g.A.lo = dY_lo; g.A.mn = 1; g.A.ld = M;

@@ -56,6 +56,18 @@ struct HopSaved {
   uint64_t x_stream = 0;
 };
 bool hop_rows_path(const rau_ctx* ctx, const rau_config* cfg);
+
+// Cross-stream scheduling of one hop inside the training step (rows path only).  The i_embed product (feature pack +
+// tanh(Wi X + bi)) does not depend on the recurrent state, and the three heavy backward products (dY, gWa, gWi) feed
+// nothing the previous hop's backward needs: both run on ctx->side while the chain of small kernels advances.
+struct HopAsync {
+  cudaEvent_t pre_done = nullptr;    // forward: I of this hop is ready (recorded on the side stream); NULL = compute inline
+  int bwd_side = 0;                  // backward: put dY / gWa / gWi on the side stream
+  int hop = 0;                       // selects the per-hop dZ buffer when bwd_side
+};
+int hop_forward_pre(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const float*>& P, const float* X, int train,
+                    const HopSaved& sv);
+cudaEvent_t rau_side_event(rau_ctx* ctx);
 size_t hop_saved_layout(const rau_config* cfg, int B, void* base, HopSaved* sv);
 
 // Backward scratch of one hop that the weight-gradient products read.  In the training step these point into
@@ -70,8 +82,9 @@ int hop_wgrads(rau_ctx* ctx, const rau_config* cfg, int rows, const MultT<float*
 
 int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const float*>& P,
                 const float* q, const float* X, const float* c, const float* h, int train, const HopSaved& sv,
-                float* score, float* do_pred, float* p_out, float* c_out, float* h_out);
+                float* score, float* do_pred, float* p_out, float* c_out, float* h_out, const HopAsync* as = nullptr);
 int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const float*>& P, const MultT<float*>& G,
                  const float* X, const float* c, const float* h, int train, const HopSaved& sv,
                  const float* dscore, const float* ddo_pred, const float* dp_att, const float* dc_out, const float* dh_out,
-                 float* dq, int dq_accumulate, float* dX, float* dc, float* dh, const HopGrads* deferred = nullptr);
+                 float* dq, int dq_accumulate, float* dX, float* dc, float* dh, const HopGrads* deferred = nullptr,
+                 const HopAsync* as = nullptr);

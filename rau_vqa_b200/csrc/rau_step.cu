@@ -343,10 +343,22 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     RAU_TRY(k_fill(ctx, grads[g], rau_group_size(cfg, g), 0.0f));
 
   rau_phase_mark(ctx, "begin");
+  // cross-stream overlap (rows path): RAU_OVERLAP bit 0 = heavy backward products on the side stream, bit 1 = the
+  // state-independent i_embed products of all hops on the side stream, next to the encoder and the chain
+  static int overlap_mode = -1;
+  if (overlap_mode < 0) { const char* e = getenv("RAU_OVERLAP"); overlap_mode = e ? atoi(e) : 3; }
+  const bool rows_hops = hop_rows_path(ctx, cfg) && ctx->side != nullptr;
+  const bool ov_bwd = rows_hops && (overlap_mode & 1);
+  const bool ov_fwd = rows_hops && (overlap_mode & 2);
+  if (ctx->side_ctas == 0) {
+    const char* e = getenv("RAU_SIDE_CTAS");
+    ctx->side_ctas = e ? atoi(e) : (ctx->sm_count * 4) / 7;   // 84 of 148 SMs measured best on Ours_Full (profiles/README.md)
+    if (ctx->side_ctas < 8 || ctx->side_ctas > ctx->sm_count) ctx->side_ctas = ctx->sm_count;
+  }
+  ctx->side_ev_next = 0;
+  bool side_used = false;
   Encoder en;
   RAU_TRY(encoder_alloc(ctx, cfg, B, &en));
-  RAU_TRY(encoder_forward(ctx, cfg, bt, params[0], params[1], train, masks, step_t, &en));
-  rau_phase_mark(ctx, "encoder forward");
 
   // answering units (F:495-537)
   const size_t sv_bytes = hop_saved_layout(cfg, B, nullptr, nullptr);
@@ -386,8 +398,11 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   ARENA(st_dpre, float, "stack.dpre", (size_t)nHop * B * M_);
   ARENA(st_gwsp, float, "stack.gwsp", (size_t)nHop * B * A_);
   std::vector<HopSaved> sv(nHop);
+  std::vector<HopAsync> as(nHop);
   for (int hp = 0; hp < nHop; ++hp) {
     hop_saved_layout(cfg, B, sv_base + sv_bytes * hp, &sv[hp]);
+    as[hp].hop = hp;
+    as[hp].bwd_side = ov_bwd ? 1 : 0;
     sv[hp].qd = st_qd + (size_t)hp * B * Q;
     sv[hp].qf = st_qf + (size_t)hp * B * M_;
     sv[hp].p = att + (size_t)hp * B * S;                 // the module outputs double as the saved copies
@@ -395,8 +410,6 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     sv[hp].hout = h_all + (size_t)(hp + 1) * B * H;
     sv[hp].dop = dop + (size_t)hp * B;
     sv[hp].m = st_m + (size_t)hp * B * M_;
-    RAU_TRY(rau_prepare_mask(ctx, sv[hp].qbits, (int64_t)B * Q, cfg->p_q, train,
-                             masks && masks->q ? masks->q + (size_t)hp * B * Q : nullptr, stream_of(step_t, SK_Q, hp, rank)));
     if (hop_rows_path(ctx, cfg) && !(masks && masks->x)) {   // drawn inline by the rows pack kernel
       sv[hp].x_philox = 1;
       sv[hp].x_stream = stream_of(step_t, SK_X, hp, rank);
@@ -405,12 +418,41 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
                                masks && masks->x ? masks->x + (size_t)hp * B * cfg->C * S : nullptr,
                                stream_of(step_t, SK_X, hp, rank)));
     }
+  }
+  if (ov_fwd) {
+    // the i_embed product of every hop depends on the features only: all of them go to the side stream now and run
+    // next to the encoder unroll and the hops' chains; each hop waits for its own event before it reads I
+    cudaEvent_t fork = rau_side_event(ctx);
+    RAU_REQUIRE(fork != nullptr, "cudaEventCreate failed");
+    RAU_CHECK_CUDA(cudaEventRecord(fork, ctx->stream));
+    RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->side, fork, 0));
+    cudaStream_t chain = ctx->stream;
+    ctx->stream = ctx->side;
+    ctx->rows_cta_cap = ctx->side_ctas;
+    int rc = RAU_OK;
+    for (int hp = 0; hp < nHop && rc == RAU_OK; ++hp) {
+      rc = hop_forward_pre(ctx, cfg, B, P, bt->feats, train, sv[hp]);
+      if (rc == RAU_OK) {
+        as[hp].pre_done = rau_side_event(ctx);
+        if (as[hp].pre_done == nullptr || cudaEventRecord(as[hp].pre_done, ctx->side) != cudaSuccess) rc = RAU_ECUDA;
+      }
+    }
+    ctx->stream = chain;
+    ctx->rows_cta_cap = 0;
+    RAU_TRY(rc);
+    side_used = true;
+  }
+  RAU_TRY(encoder_forward(ctx, cfg, bt, params[0], params[1], train, masks, step_t, &en));
+  rau_phase_mark(ctx, "encoder forward");
+  for (int hp = 0; hp < nHop; ++hp) {
+    RAU_TRY(rau_prepare_mask(ctx, sv[hp].qbits, (int64_t)B * Q, cfg->p_q, train,
+                             masks && masks->q ? masks->q + (size_t)hp * B * Q : nullptr, stream_of(step_t, SK_Q, hp, rank)));
     RAU_TRY(rau_prepare_mask(ctx, sv[hp].mbits, (int64_t)B * cfg->M, cfg->p_m, train,
                              masks && masks->m ? masks->m + (size_t)hp * B * cfg->M : nullptr,
                              stream_of(step_t, SK_M, hp, rank)));
     RAU_TRY(hop_forward(ctx, cfg, B, P, en.rnn_out, bt->feats, c_all + (size_t)hp * B * H, h_all + (size_t)hp * B * H, train,
                         sv[hp], scores + (size_t)hp * B * N, dop + (size_t)hp * B, att + (size_t)hp * B * S,
-                        c_all + (size_t)(hp + 1) * B * H, h_all + (size_t)(hp + 1) * B * H));
+                        c_all + (size_t)(hp + 1) * B * H, h_all + (size_t)(hp + 1) * B * H, &as[hp]));
     // criterion forward + backward + argmax in one pass (F:505, F:535, F:585-589)
     const float hm = hop_mask ? hop_mask[hp] : 1.0f;
     RAU_TRY(k_softmax_ce(ctx, B, N, scores + (size_t)hp * B * N, bt->labels, 1.0f / Bg, hm / Bg, loss + hp,
@@ -436,7 +478,8 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     hg.gwsp = st_gwsp + (size_t)hp * B * A_;
     RAU_TRY(hop_backward(ctx, cfg, B, P, G, bt->feats, c_all + (size_t)hp * B * H, h_all + (size_t)hp * B * H, train, sv[hp],
                          dscore + (size_t)hp * B * N, nullptr, nullptr, dc_in, dh_in, dq, last ? 0 : 1, nullptr,
-                         dcs + (size_t)(hp & 1) * B * H, dhs + (size_t)(hp & 1) * B * H, &hg));
+                         dcs + (size_t)(hp & 1) * B * H, dhs + (size_t)(hp & 1) * B * H, &hg, &as[hp]));
+    if (ov_bwd) side_used = true;
   }
   rau_phase_mark(ctx, "answering units backward");
   {
@@ -448,6 +491,12 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   }
   rau_phase_mark(ctx, "unit weight gradients");
   RAU_TRY(encoder_backward(ctx, cfg, bt, params[1], grads[0], grads[1], train, &en, dq));
+  if (side_used) {   // join: the side stream's gradients (gWi, gWa, gbi) are complete before anything downstream
+    cudaEvent_t join = rau_side_event(ctx);
+    RAU_REQUIRE(join != nullptr, "cudaEventCreate failed");
+    RAU_CHECK_CUDA(cudaEventRecord(join, ctx->side));
+    RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, join, 0));
+  }
   rau_phase_mark(ctx, "encoder backward");
   return RAU_OK;
 }
