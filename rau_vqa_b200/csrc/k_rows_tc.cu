@@ -860,111 +860,109 @@ __global__ void __launch_bounds__(256) unprep_rows_kernel(const float* __restric
 }
 
 // attbymemory + attselect on the rows layout (F:285-290, F:254-263): p = softmax(logit + mem), a = sum_s p_s I[b*S+s, :]
-// one CTA of 256 threads per image: M/8 threads cover a row of I with 16-byte loads, 256/(M/8) row groups in parallel
+// grid (B, M/256), 256 threads: a CTA owns 256 channels of one image; 32 threads cover a row slice with 16-byte loads,
+// 8 row groups walk the image in parallel (HBM-bound: I hi+lo is read exactly once)
 __global__ void __launch_bounds__(256) attn_rows_fwd_kernel(int S, int M, const float* __restrict__ logit,
                                                             const float* __restrict__ mem, const bf16* __restrict__ I_hi,
                                                             const bf16* __restrict__ I_lo, float* __restrict__ p_out,
                                                             float* __restrict__ a_out) {
   RAU_PDL_ENTRY();
-  extern __shared__ float sm[];
-  float* p = sm;           // [256]
-  float* part = sm + 256;  // [ngroups][M]
+  __shared__ float p[256];
+  __shared__ float part[8][256];
   __shared__ float red[32];
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int b = blockIdx.x, tid = threadIdx.x, c0 = blockIdx.y * 256;
   const int64_t r0 = (int64_t)b * S;
   const float l0 = tid < S ? logit[r0 + tid] + mem[r0 + tid] : -INFINITY;
   const float mx = block_max(l0, red);
   const float e0 = tid < S ? __expf(l0 - mx) : 0.0f;
   const float den = block_sum(e0, red);
   p[tid] = e0 / den;
-  if (tid < S) p_out[r0 + tid] = e0 / den;
+  if (blockIdx.y == 0 && tid < S) p_out[r0 + tid] = e0 / den;
   __syncthreads();
-  const int tpr = M >> 3, ngroups = 256 / tpr;
-  const int cg = tid % tpr, rg = tid / tpr;
+  const int cg = tid & 31, rg = tid >> 5;
   float a[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) a[k] = 0.0f;
-#pragma unroll 4
-  for (int s = rg; s < S; s += ngroups) {
-    const uint4 h = __ldg(reinterpret_cast<const uint4*>(I_hi + (r0 + s) * M) + cg);
+#pragma unroll 5
+  for (int s = rg; s < S; s += 8) {
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(I_hi + (r0 + s) * M + c0) + cg);
     uint4 l = make_uint4(0u, 0u, 0u, 0u);
-    if (I_lo) l = __ldg(reinterpret_cast<const uint4*>(I_lo + (r0 + s) * M) + cg);
+    if (I_lo) l = __ldg(reinterpret_cast<const uint4*>(I_lo + (r0 + s) * M + c0) + cg);
     const float w = p[s];
     a[0] = fmaf(w, bf_lo(h.x) + bf_lo(l.x), a[0]); a[1] = fmaf(w, bf_hi(h.x) + bf_hi(l.x), a[1]);
     a[2] = fmaf(w, bf_lo(h.y) + bf_lo(l.y), a[2]); a[3] = fmaf(w, bf_hi(h.y) + bf_hi(l.y), a[3]);
     a[4] = fmaf(w, bf_lo(h.z) + bf_lo(l.z), a[4]); a[5] = fmaf(w, bf_hi(h.z) + bf_hi(l.z), a[5]);
     a[6] = fmaf(w, bf_lo(h.w) + bf_lo(l.w), a[6]); a[7] = fmaf(w, bf_hi(h.w) + bf_hi(l.w), a[7]);
   }
-  float4* dst = reinterpret_cast<float4*>(part + rg * M + 8 * cg);
+  float4* dst = reinterpret_cast<float4*>(&part[rg][8 * cg]);
   dst[0] = make_float4(a[0], a[1], a[2], a[3]);
   dst[1] = make_float4(a[4], a[5], a[6], a[7]);
   __syncthreads();
-  for (int m = tid; m < M; m += 256) {
-    float v = 0.0f;
-    for (int k = 0; k < ngroups; ++k) v += part[k * M + m];
-    a_out[(int64_t)b * M + m] = v;
-  }
+  float v = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v += part[k][tid];
+  a_out[(int64_t)b * M + c0 + tid] = v;
 }
 
-// backward of the above for one image (256 threads):
-//   dp = dp_in + I da ; ds = p (dp - <p,dp>) ; dZ[r,n] = ws[n] ds[s] (1 - E[r,n]^2) -> bf16 (hi, lo)
-//   dqa[b,n] = sum_s dZ[r,n] ; gws_part[b,n] = sum_s ds[s] E[r,n]
-// HBM-bound (I hi+lo and E read once, dZ written once = 0.8 MB per image): every loop keeps >= 64 bytes per thread in flight
-__global__ void __launch_bounds__(256) attn_rows_bwd_kernel(int S, int M, int A, const float* __restrict__ E,
-                                                            const bf16* __restrict__ I_hi, const bf16* __restrict__ I_lo,
-                                                            const float* __restrict__ ws, const float* __restrict__ p_in,
-                                                            const float* __restrict__ dp_in, const float* __restrict__ da,
-                                                            float* __restrict__ ds_out, bf16* __restrict__ dZ_hi,
-                                                            bf16* __restrict__ dZ_lo, float* __restrict__ dqa,
-                                                            float* __restrict__ gws_part) {
+// backward, part 1 (a warp per row of I, fully parallel over the B*S rows): dp[r] = dp_in[r] + sum_m da[b(r), m] I[r, m]
+__global__ void __launch_bounds__(256) attn_rows_dp_kernel(int R, int S, int M, const bf16* __restrict__ I_hi,
+                                                           const bf16* __restrict__ I_lo, const float* __restrict__ da,
+                                                           const float* __restrict__ dp_in, float* __restrict__ dp) {
   RAU_PDL_ENTRY();
-  extern __shared__ float sm[];
-  float* ds = sm;            // [256]
-  float* das = sm + 256;     // [M]
-  float* red2 = das + M;     // [2][256] cross-row-group partial sums
-  __shared__ float red[32];
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t r0 = (int64_t)b * S;
-  for (int m = tid; m < M; m += 256) das[m] = da[(int64_t)b * M + m];
-  ds[tid] = 0.0f;
-  __syncthreads();
-  // (1) dp[s] = dp_in[s] + sum_m da[m] I[r0+s, m]: a warp per row, 8 channels (one 16-byte word) per lane and step
-  const int w8 = M >> 3;   // 16-byte words per row
-  for (int s = warp; s < S; s += 8) {
-    const uint4* ih = reinterpret_cast<const uint4*>(I_hi + (r0 + s) * M);
-    const uint4* il = I_lo ? reinterpret_cast<const uint4*>(I_lo + (r0 + s) * M) : nullptr;
-    float acc = 0.0f;
-    for (int w = lane; w < w8; w += 32) {
-      const uint4 h = __ldg(ih + w);
-      uint4 l = make_uint4(0u, 0u, 0u, 0u);
-      if (il) l = __ldg(il + w);
-      const float4 d0 = *reinterpret_cast<const float4*>(das + 8 * w);
-      const float4 d1 = *reinterpret_cast<const float4*>(das + 8 * w + 4);
-      acc = fmaf(d0.x, bf_lo(h.x) + bf_lo(l.x), acc); acc = fmaf(d0.y, bf_hi(h.x) + bf_hi(l.x), acc);
-      acc = fmaf(d0.z, bf_lo(h.y) + bf_lo(l.y), acc); acc = fmaf(d0.w, bf_hi(h.y) + bf_hi(l.y), acc);
-      acc = fmaf(d1.x, bf_lo(h.z) + bf_lo(l.z), acc); acc = fmaf(d1.y, bf_hi(h.z) + bf_hi(l.z), acc);
-      acc = fmaf(d1.z, bf_lo(h.w) + bf_lo(l.w), acc); acc = fmaf(d1.w, bf_hi(h.w) + bf_hi(l.w), acc);
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) ds[s] = acc + (dp_in ? dp_in[r0 + s] : 0.0f);
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const int b = r / S;
+  const uint4* ih = reinterpret_cast<const uint4*>(I_hi + (int64_t)r * M);
+  const uint4* il = I_lo ? reinterpret_cast<const uint4*>(I_lo + (int64_t)r * M) : nullptr;
+  const float* d = da + (int64_t)b * M;
+  const int w8 = M >> 3;
+  float acc = 0.0f;
+#pragma unroll 2
+  for (int w = lane; w < w8; w += 32) {
+    const uint4 h = __ldg(ih + w);
+    uint4 l = make_uint4(0u, 0u, 0u, 0u);
+    if (il) l = __ldg(il + w);
+    const float4 d0 = __ldg(reinterpret_cast<const float4*>(d + 8 * w));
+    const float4 d1 = __ldg(reinterpret_cast<const float4*>(d + 8 * w) + 1);
+    acc = fmaf(d0.x, bf_lo(h.x) + bf_lo(l.x), acc); acc = fmaf(d0.y, bf_hi(h.x) + bf_hi(l.x), acc);
+    acc = fmaf(d0.z, bf_lo(h.y) + bf_lo(l.y), acc); acc = fmaf(d0.w, bf_hi(h.y) + bf_hi(l.y), acc);
+    acc = fmaf(d1.x, bf_lo(h.z) + bf_lo(l.z), acc); acc = fmaf(d1.y, bf_hi(h.z) + bf_hi(l.z), acc);
+    acc = fmaf(d1.z, bf_lo(h.w) + bf_lo(l.w), acc); acc = fmaf(d1.w, bf_hi(h.w) + bf_hi(l.w), acc);
   }
-  __syncthreads();
-  // (2) softmax backward
+  acc = warp_sum(acc);
+  if (lane == 0) dp[r] = acc + (dp_in ? dp_in[r] : 0.0f);
+}
+
+// backward, part 2: grid (B, NSL) -- every CTA redoes the image's softmax backward (196 scalars), then emits dZ for its
+// slice of the image's rows:  ds = p (dp - <p,dp>) ; dZ[r,n] = ws[n] ds[s] (1 - E[r,n]^2) -> bf16 (hi, lo) ;
+// dqa[b,n] += sum_s dZ[r,n] ; gws_part[b,n] += sum_s ds[s] E[r,n]   (both zeroed by the caller, slices add atomically)
+__global__ void __launch_bounds__(256) attn_rows_dz_kernel(int S, int A, const float* __restrict__ E,
+                                                           const float* __restrict__ ws, const float* __restrict__ p_in,
+                                                           const float* __restrict__ dp, float* __restrict__ ds_out,
+                                                           bf16* __restrict__ dZ_hi, bf16* __restrict__ dZ_lo,
+                                                           float* __restrict__ dqa, float* __restrict__ gws_part) {
+  RAU_PDL_ENTRY();
+  __shared__ float ds[256];
+  __shared__ float red[32];
+  __shared__ float red2[2][1024];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int64_t r0 = (int64_t)b * S;
   const float pv = tid < S ? p_in[r0 + tid] : 0.0f;
-  const float dpv = tid < S ? ds[tid] : 0.0f;
+  const float dpv = tid < S ? dp[r0 + tid] : 0.0f;
   const float dot = block_sum(pv * dpv, red);
   const float dsv = tid < S ? pv * (dpv - dot) : 0.0f;
-  __syncthreads();
   ds[tid] = dsv;
-  if (tid < S) ds_out[r0 + tid] = dsv;
+  if (blockIdx.y == 0 && tid < S) ds_out[r0 + tid] = dsv;
   __syncthreads();
-  // (3) dZ: A/4 threads cover a row of E with float4 loads, 256/(A/4) row groups walk the image in parallel
+  const int per = (S + gridDim.y - 1) / gridDim.y;
+  const int s_lo = blockIdx.y * per, s_hi = min(S, s_lo + per);
   const int tpr = A >> 2, ngroups = 256 / tpr;
   const int ng = tid % tpr, rg = tid / tpr;
   const float4 w4 = *reinterpret_cast<const float4*>(ws + 4 * ng);
   float sz0 = 0.f, sz1 = 0.f, sz2 = 0.f, sz3 = 0.f, sg0 = 0.f, sg1 = 0.f, sg2 = 0.f, sg3 = 0.f;
 #pragma unroll 4
-  for (int s = rg; s < S; s += ngroups) {
+  for (int s = s_lo + rg; s < s_hi; s += ngroups) {
     const float4 e = __ldg(reinterpret_cast<const float4*>(E + (r0 + s) * A) + ng);
     const float d = ds[s];
     const float z0 = w4.x * d * (1.0f - e.x * e.x), z1 = w4.y * d * (1.0f - e.y * e.y);
@@ -977,17 +975,14 @@ __global__ void __launch_bounds__(256) attn_rows_bwd_kernel(int S, int M, int A,
     reinterpret_cast<uint2*>(dZ_hi + (r0 + s) * A)[ng] = make_uint2(h0, h1);
     if (dZ_lo) reinterpret_cast<uint2*>(dZ_lo + (r0 + s) * A)[ng] = make_uint2(l0, l1);
   }
-  // reduce the row groups: red2[0][rg][n] / red2[1][rg][n] with rg-major layout of A floats each (ngroups * A = 1024)
-  float* rz = red2;
-  float* rgs = red2 + 1024;
-  *reinterpret_cast<float4*>(rz + rg * A + 4 * ng) = make_float4(sz0, sz1, sz2, sz3);
-  *reinterpret_cast<float4*>(rgs + rg * A + 4 * ng) = make_float4(sg0, sg1, sg2, sg3);
+  *reinterpret_cast<float4*>(&red2[0][rg * A + 4 * ng]) = make_float4(sz0, sz1, sz2, sz3);
+  *reinterpret_cast<float4*>(&red2[1][rg * A + 4 * ng]) = make_float4(sg0, sg1, sg2, sg3);
   __syncthreads();
   for (int n = tid; n < A; n += 256) {
     float z = 0.0f, g = 0.0f;
-    for (int k = 0; k < ngroups; ++k) { z += rz[k * A + n]; g += rgs[k * A + n]; }
-    dqa[(int64_t)b * A + n] = z;
-    gws_part[(int64_t)b * A + n] = g;
+    for (int k = 0; k < ngroups; ++k) { z += red2[0][k * A + n]; g += red2[1][k * A + n]; }
+    atomicAdd(dqa + (int64_t)b * A + n, z);
+    atomicAdd(gws_part + (int64_t)b * A + n, g);
   }
 }
 
@@ -1213,8 +1208,8 @@ int k_unprep_rows(rau_ctx* ctx, const float* dXr, int B, int C, int S, const uin
 
 int k_attn_rows_fwd(rau_ctx* ctx, int B, int M, int S, const float* logit, const float* mem, const bf16* I_hi, const bf16* I_lo,
                     float* p, float* a) {
-  RAU_REQUIRE((M == 256 || M == 512 || M == 1024 || M == 2048) && S <= 256, "k_attn_rows_fwd: M=%d S=%d", M, S);
-  RAU_LAUNCH_PDL(ctx->stream, (attn_rows_fwd_kernel), B, 256, (256 + 256 / (M / 8) * M) * sizeof(float), S, M, logit, mem, I_hi, I_lo, p, a);
+  RAU_REQUIRE(M % 256 == 0 && S <= 256, "k_attn_rows_fwd: M=%d S=%d", M, S);
+  RAU_LAUNCH_PDL(ctx->stream, (attn_rows_fwd_kernel), dim3(B, M / 256), 256, 0, S, M, logit, mem, I_hi, I_lo, p, a);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
@@ -1223,8 +1218,15 @@ int k_attn_rows_bwd(rau_ctx* ctx, int B, int M, int A, int S, const float* E, co
                     const float* p, const float* dp_in, const float* da, float* ds, bf16* dZ_hi, bf16* dZ_lo, float* dqa,
                     float* gws_part) {
   RAU_REQUIRE(M % 8 == 0 && S <= 256 && (A == 64 || A == 128 || A == 256), "k_attn_rows_bwd: M=%d A=%d S=%d", M, A, S);
-  RAU_LAUNCH_PDL(ctx->stream, (attn_rows_bwd_kernel), B, 256, (256 + M + 2048) * sizeof(float), S, M, A, E, I_hi, I_lo, ws, p, dp_in, da, ds, dZ_hi,
-                                                                            dZ_lo, dqa, gws_part);
+  const int R = B * S;
+  float* dp = nullptr;
+  RAU_TRY(ctx->arena.get("attn.dp", sizeof(float) * (size_t)R, (void**)&dp));
+  RAU_LAUNCH_PDL(ctx->stream, (attn_rows_dp_kernel), (R + 7) / 8, 256, 0, R, S, M, I_hi, I_lo, da, dp_in, dp);
+  RAU_LAUNCH_CHECK(ctx);
+  RAU_CHECK_CUDA(cudaMemsetAsync(dqa, 0, sizeof(float) * (size_t)B * A, ctx->stream));
+  RAU_CHECK_CUDA(cudaMemsetAsync(gws_part, 0, sizeof(float) * (size_t)B * A, ctx->stream));
+  const int nsl = B >= 128 ? 4 : (B >= 32 ? 8 : 16);   // row slices per image: ~1000 CTAs
+  RAU_LAUNCH_PDL(ctx->stream, (attn_rows_dz_kernel), dim3(B, nsl), 256, 0, S, A, E, ws, p, dp, ds, dZ_hi, dZ_lo, dqa, gws_part);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
