@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) iembed_bwd_rows_kernel(int64_t rows, int 
 __global__ void __launch_bounds__(256) softmax_ce_kernel(int N, const float* __restrict__ score, const float* __restrict__ labels,
                                                          float loss_scale, float grad_scale, float* __restrict__ loss_sum,
                                                          float* __restrict__ dscore_f, bf16* __restrict__ dscore_b, int lddb,
-                                                         float* __restrict__ answers) {
+                                                         float* __restrict__ answers, bf16* __restrict__ dscore_lo) {
   RAU_PDL_ENTRY();
   __shared__ float red[32];
   __shared__ int redi[32];
@@ -238,7 +238,11 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(int N, const float* __r
       float g = 0.0f;
       if (n < N) g = grad_scale * (__expf(row[n] - mx) * inv - (n == y ? 1.0f : 0.0f));
       if (dscore_f && n < N) dscore_f[(int64_t)b * N + n] = g;
-      if (dscore_b) dscore_b[(int64_t)b * lddb + n] = __float2bfloat16(g);
+      if (dscore_b) {
+        const bf16 h = __float2bfloat16(g);
+        dscore_b[(int64_t)b * lddb + n] = h;
+        if (dscore_lo) dscore_lo[(int64_t)b * lddb + n] = __float2bfloat16(g - __bfloat162float(h));
+      }
     }
   }
 }
@@ -389,8 +393,9 @@ int k_iembed_bwd_rows(rau_ctx* ctx, int B, int M, int S, int Sp, const float* dI
 }
 
 int k_softmax_ce(rau_ctx* ctx, int B, int N, const float* score, const float* labels, float loss_scale, float grad_scale,
-                 float* loss_sum, float* dscore_f, bf16* dscore_b, int lddb, float* answers) {
-  RAU_LAUNCH_PDL(ctx->stream, (softmax_ce_kernel), B, 256, 0, N, score, labels, loss_scale, grad_scale, loss_sum, dscore_f, dscore_b, lddb, answers);
+                 float* loss_sum, float* dscore_f, bf16* dscore_b, int lddb, float* answers, bf16* dscore_lo) {
+  RAU_LAUNCH_PDL(ctx->stream, (softmax_ce_kernel), B, 256, 0, N, score, labels, loss_scale, grad_scale, loss_sum, dscore_f, dscore_b, lddb, answers,
+                 dscore_lo);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }

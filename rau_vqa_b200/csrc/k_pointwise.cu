@@ -121,8 +121,12 @@ __global__ void lstm_bwd_kernel(int B, int H, int order, const float* __restrict
                                 const float* __restrict__ dq_h, int lddq,
                                 const float* __restrict__ c_prev, int ldcp, const float* __restrict__ saved,
                                 float* __restrict__ dG, bf16* __restrict__ dG_b, float* __restrict__ dc_prev, int lddcp,
-                                bf16* __restrict__ dG_lo) {
+                                bf16* __restrict__ dG_lo, float* __restrict__ zero_out) {
   RAU_PDL_ENTRY();
+  // zero_out ([B, H] contiguous): the buffer the split-K dgrad that follows reduces into (saves a memset node per step)
+  if (zero_out)
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < (int64_t)B * H; idx += (int64_t)gridDim.x * blockDim.x)
+      zero_out[idx] = 0.0f;
   int ci, cf, co, cg;
   gate_chunks(order, ci, cf, co, cg);
   const int64_t total = (int64_t)B * H, plane = total;
@@ -164,7 +168,8 @@ __global__ void lstm_bwd_kernel(int B, int H, int order, const float* __restrict
 // ---------------------------------------------------------------- elementwise
 __global__ void dropout_kernel(const float* __restrict__ x, int64_t rows, int cols, int ldx,
                                const uint32_t* __restrict__ bits, float scale,
-                               float* __restrict__ y_f, int ldyf, bf16* __restrict__ y_b, int ldyb, int cols_pad) {
+                               float* __restrict__ y_f, int ldyf, bf16* __restrict__ y_b, int ldyb, int cols_pad,
+                               bf16* __restrict__ y_lo) {
   RAU_PDL_ENTRY();
   const int64_t total = rows * cols_pad;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -173,7 +178,11 @@ __global__ void dropout_kernel(const float* __restrict__ x, int64_t rows, int co
     float v = 0.0f;
     if (c < cols) v = x[r * ldx + c] * keep_scale(bits, r * cols + c, scale);
     if (y_f) y_f[r * ldyf + c] = v;
-    if (y_b) y_b[r * ldyb + c] = __float2bfloat16(v);
+    if (y_b) {
+      const bf16 h = __float2bfloat16(v);
+      y_b[r * ldyb + c] = h;
+      if (y_lo) y_lo[r * ldyb + c] = __float2bfloat16(v - __bfloat162float(h));   // bf16x3 operand: (hi, lo)
+    }
   }
 }
 
@@ -209,21 +218,32 @@ __global__ void dropout_pack_kernel(const float* __restrict__ x, int64_t rows, i
 }
 
 __global__ void dropout_bwd_acc_kernel(const float* __restrict__ dx, int64_t n, const uint32_t* __restrict__ bits,
-                                       float scale, float* __restrict__ y, int accumulate) {
+                                       float scale, float* __restrict__ y, int accumulate, bf16* __restrict__ y_hi,
+                                       bf16* __restrict__ y_lo) {
   RAU_PDL_ENTRY();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float v = dx[i] * keep_scale(bits, i, scale);
-    y[i] = accumulate ? y[i] + v : v;
+    float v = dx[i] * keep_scale(bits, i, scale);
+    if (accumulate) v += y[i];
+    y[i] = v;
+    if (y_hi) {
+      const bf16 h = __float2bfloat16(v);
+      y_hi[i] = h;
+      if (y_lo) y_lo[i] = __float2bfloat16(v - __bfloat162float(h));
+    }
   }
 }
 
 __global__ void tanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int64_t n,
-                                float* __restrict__ dx_f, bf16* __restrict__ dx_b) {
+                                float* __restrict__ dx_f, bf16* __restrict__ dx_b, bf16* __restrict__ dx_lo) {
   RAU_PDL_ENTRY();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float v = dy[i] * (1.0f - y[i] * y[i]);
     if (dx_f) dx_f[i] = v;
-    if (dx_b) dx_b[i] = __float2bfloat16(v);
+    if (dx_b) {
+      const bf16 h = __float2bfloat16(v);
+      dx_b[i] = h;
+      if (dx_lo) dx_lo[i] = __float2bfloat16(v - __bfloat162float(h));
+    }
   }
 }
 
@@ -389,15 +409,16 @@ int k_lstm_fwd(rau_ctx* ctx, int B, int H, int order, const float* G, int ldg, c
 }
 int k_lstm_bwd(rau_ctx* ctx, int B, int H, int order, const float* dc_out, int lddc, const float* dh_out, int lddh,
                const float* dh_extra, int ldhe, const float* lengths, int t, const float* dq_c, const float* dq_h, int lddq,
-               const float* c_prev, int ldcp, const float* saved, float* dG, bf16* dG_b, float* dc_prev, int lddcp, bf16* dG_lo) {
+               const float* c_prev, int ldcp, const float* saved, float* dG, bf16* dG_b, float* dc_prev, int lddcp, bf16* dG_lo,
+               float* zero_out) {
   RAU_LAUNCH_PDL(ctx->stream, (lstm_bwd_kernel), grid_for((int64_t)B * H), TPB, 0, B, H, order, dc_out, lddc, dh_out, lddh, dh_extra, ldhe,
-      lengths, t, dq_c, dq_h, lddq, c_prev, ldcp, saved, dG, dG_b, dc_prev, lddcp, dG_lo);
+      lengths, t, dq_c, dq_h, lddq, c_prev, ldcp, saved, dG, dG_b, dc_prev, lddcp, dG_lo, zero_out);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 int k_dropout(rau_ctx* ctx, const float* x, int64_t rows, int cols, int ldx, const uint32_t* bits, float scale,
-              float* y_f, int ldyf, bf16* y_b, int ldyb, int cols_pad) {
-  RAU_LAUNCH_PDL(ctx->stream, (dropout_kernel), grid_for(rows * cols_pad, 4), TPB, 0, x, rows, cols, ldx, bits, scale, y_f, ldyf, y_b, ldyb, cols_pad);
+              float* y_f, int ldyf, bf16* y_b, int ldyb, int cols_pad, bf16* y_lo) {
+  RAU_LAUNCH_PDL(ctx->stream, (dropout_kernel), grid_for(rows * cols_pad, 4), TPB, 0, x, rows, cols, ldx, bits, scale, y_f, ldyf, y_b, ldyb, cols_pad, y_lo);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
@@ -411,13 +432,14 @@ int k_dropout_pack(rau_ctx* ctx, const float* x, int64_t rows, int cols, const u
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
-int k_dropout_bwd_acc(rau_ctx* ctx, const float* dx, int64_t n, const uint32_t* bits, float scale, float* y, int accumulate) {
-  RAU_LAUNCH_PDL(ctx->stream, (dropout_bwd_acc_kernel), grid_for(n, 4), TPB, 0, dx, n, bits, scale, y, accumulate);
+int k_dropout_bwd_acc(rau_ctx* ctx, const float* dx, int64_t n, const uint32_t* bits, float scale, float* y, int accumulate,
+                      bf16* y_hi, bf16* y_lo) {
+  RAU_LAUNCH_PDL(ctx->stream, (dropout_bwd_acc_kernel), grid_for(n, 4), TPB, 0, dx, n, bits, scale, y, accumulate, y_hi, y_lo);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
-int k_tanh_bwd(rau_ctx* ctx, const float* dy, const float* y, int64_t n, float* dx_f, bf16* dx_b) {
-  RAU_LAUNCH_PDL(ctx->stream, (tanh_bwd_kernel), grid_for(n, 4), TPB, 0, dy, y, n, dx_f, dx_b);
+int k_tanh_bwd(rau_ctx* ctx, const float* dy, const float* y, int64_t n, float* dx_f, bf16* dx_b, bf16* dx_lo) {
+  RAU_LAUNCH_PDL(ctx->stream, (tanh_bwd_kernel), grid_for(n, 4), TPB, 0, dy, y, n, dx_f, dx_b, dx_lo);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }

@@ -865,7 +865,8 @@ __global__ void __launch_bounds__(256) unprep_rows_kernel(const float* __restric
 __global__ void __launch_bounds__(256) attn_rows_fwd_kernel(int S, int M, const float* __restrict__ logit,
                                                             const float* __restrict__ mem, const bf16* __restrict__ I_hi,
                                                             const bf16* __restrict__ I_lo, float* __restrict__ p_out,
-                                                            float* __restrict__ a_out) {
+                                                            float* __restrict__ a_out, bf16* __restrict__ p_hi,
+                                                            bf16* __restrict__ p_lo, int ldp) {
   RAU_PDL_ENTRY();
   __shared__ float p[256];
   __shared__ float part[8][256];
@@ -878,6 +879,12 @@ __global__ void __launch_bounds__(256) attn_rows_fwd_kernel(int S, int M, const 
   const float den = block_sum(e0, red);
   p[tid] = e0 / den;
   if (blockIdx.y == 0 && tid < S) p_out[r0 + tid] = e0 / den;
+  if (blockIdx.y == 0 && p_hi && tid < ldp) {   // packed twin of p (pitch ldp >= S, zero padded) for the Wp product
+    const float v = tid < S ? e0 / den : 0.0f;
+    const bf16 h = __float2bfloat16_rn(v);
+    p_hi[(int64_t)b * ldp + tid] = h;
+    if (p_lo) p_lo[(int64_t)b * ldp + tid] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
   __syncthreads();
   const int cg = tid & 31, rg = tid >> 5;
   float a[8];
@@ -941,7 +948,8 @@ __global__ void __launch_bounds__(256) attn_rows_dz_kernel(int S, int A, const f
                                                            const float* __restrict__ ws, const float* __restrict__ p_in,
                                                            const float* __restrict__ dp, float* __restrict__ ds_out,
                                                            bf16* __restrict__ dZ_hi, bf16* __restrict__ dZ_lo,
-                                                           float* __restrict__ dqa, float* __restrict__ gws_part) {
+                                                           float* __restrict__ dqa, float* __restrict__ gws_part,
+                                                           bf16* __restrict__ ds_hi, bf16* __restrict__ ds_lo, int ldds) {
   RAU_PDL_ENTRY();
   __shared__ float ds[256];
   __shared__ float red[32];
@@ -954,6 +962,11 @@ __global__ void __launch_bounds__(256) attn_rows_dz_kernel(int S, int A, const f
   const float dsv = tid < S ? pv * (dpv - dot) : 0.0f;
   ds[tid] = dsv;
   if (blockIdx.y == 0 && tid < S) ds_out[r0 + tid] = dsv;
+  if (blockIdx.y == 0 && ds_hi && tid < ldds) {   // packed twin of ds for the Wm products
+    const bf16 h = __float2bfloat16_rn(dsv);
+    ds_hi[(int64_t)b * ldds + tid] = h;
+    if (ds_lo) ds_lo[(int64_t)b * ldds + tid] = __float2bfloat16_rn(dsv - __bfloat162float(h));
+  }
   __syncthreads();
   const int per = (S + gridDim.y - 1) / gridDim.y;
   const int s_lo = blockIdx.y * per, s_hi = min(S, s_lo + per);
@@ -1207,17 +1220,17 @@ int k_unprep_rows(rau_ctx* ctx, const float* dXr, int B, int C, int S, const uin
 }
 
 int k_attn_rows_fwd(rau_ctx* ctx, int B, int M, int S, const float* logit, const float* mem, const bf16* I_hi, const bf16* I_lo,
-                    float* p, float* a) {
-  RAU_REQUIRE(M % 256 == 0 && S <= 256, "k_attn_rows_fwd: M=%d S=%d", M, S);
-  RAU_LAUNCH_PDL(ctx->stream, (attn_rows_fwd_kernel), dim3(B, M / 256), 256, 0, S, M, logit, mem, I_hi, I_lo, p, a);
+                    float* p, float* a, bf16* p_hi, bf16* p_lo, int ldp) {
+  RAU_REQUIRE(M % 256 == 0 && S <= 256 && ldp <= 256, "k_attn_rows_fwd: M=%d S=%d", M, S);
+  RAU_LAUNCH_PDL(ctx->stream, (attn_rows_fwd_kernel), dim3(B, M / 256), 256, 0, S, M, logit, mem, I_hi, I_lo, p, a, p_hi, p_lo, ldp);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 
 int k_attn_rows_bwd(rau_ctx* ctx, int B, int M, int A, int S, const float* E, const bf16* I_hi, const bf16* I_lo, const float* ws,
                     const float* p, const float* dp_in, const float* da, float* ds, bf16* dZ_hi, bf16* dZ_lo, float* dqa,
-                    float* gws_part) {
-  RAU_REQUIRE(M % 8 == 0 && S <= 256 && (A == 64 || A == 128 || A == 256), "k_attn_rows_bwd: M=%d A=%d S=%d", M, A, S);
+                    float* gws_part, bf16* ds_hi, bf16* ds_lo, int ldds) {
+  RAU_REQUIRE(M % 8 == 0 && S <= 256 && ldds <= 256 && (A == 64 || A == 128 || A == 256), "k_attn_rows_bwd: M=%d A=%d S=%d", M, A, S);
   const int R = B * S;
   float* dp = nullptr;
   RAU_TRY(ctx->arena.get("attn.dp", sizeof(float) * (size_t)R, (void**)&dp));
@@ -1226,7 +1239,8 @@ int k_attn_rows_bwd(rau_ctx* ctx, int B, int M, int A, int S, const float* E, co
   RAU_CHECK_CUDA(cudaMemsetAsync(dqa, 0, sizeof(float) * (size_t)B * A, ctx->stream));
   RAU_CHECK_CUDA(cudaMemsetAsync(gws_part, 0, sizeof(float) * (size_t)B * A, ctx->stream));
   const int nsl = B >= 128 ? 4 : (B >= 32 ? 8 : 16);   // row slices per image: ~1000 CTAs
-  RAU_LAUNCH_PDL(ctx->stream, (attn_rows_dz_kernel), dim3(B, nsl), 256, 0, S, A, E, ws, p, dp, ds, dZ_hi, dZ_lo, dqa, gws_part);
+  RAU_LAUNCH_PDL(ctx->stream, (attn_rows_dz_kernel), dim3(B, nsl), 256, 0, S, A, E, ws, p, dp, ds, dZ_hi, dZ_lo, dqa, gws_part, ds_hi,
+                 ds_lo, ldds);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
@@ -1278,15 +1292,6 @@ int pack2d(rau_ctx* ctx, const float* src, int64_t ld, int rows, int cols, bool 
     int64_t blocks = (work + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
-    {
-      static bool carve = false;
-      if (!carve) {
-        const char* e = getenv("RAU_CARVEOUT");
-        if (!e || atoi(e) != 0)
-          cudaFuncSetAttribute(pack2d_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        carve = true;
-      }
-    }
     RAU_LAUNCH_PDL(ctx->stream, (pack2d_kernel), (int)blocks, 256, 0, src, ld, rows, cols, ldo, (bf16*)out->hi, (bf16*)out->lo);
     RAU_LAUNCH_CHECK(ctx);
     if (is_const) ctx->tc_epoch[name] = ctx->epoch;
@@ -1295,6 +1300,17 @@ int pack2d(rau_ctx* ctx, const float* src, int64_t ld, int rows, int cols, bool 
 }
 
 }  // namespace
+int rows_pack_into(rau_ctx* ctx, const float* src, int64_t ld, int rows, int cols, bf16* hi, bf16* lo, int64_t ldo) {
+  RAU_REQUIRE(hi != nullptr && ldo % 2 == 0 && ldo >= cols, "rows_pack_into: bad destination (ldo = %lld)", (long long)ldo);
+  const int64_t work = (int64_t)rows * (ldo / 2);
+  int64_t blocks = (work + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  RAU_LAUNCH_PDL(ctx->stream, (pack2d_kernel), (int)blocks, 256, 0, src, ld, rows, cols, (int)ldo, hi, lo);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+
 int rows_pack2d(rau_ctx* ctx, const float* src, int64_t ld, int rows, int cols, bool want_lo, bool is_const, const char* slot,
                 const bf16** hi, const bf16** lo, int64_t* ldo) {
   Packed2D pk;
@@ -1432,16 +1448,22 @@ int rows_contract_try(rau_ctx* ctx, const SimtGemm& g) {
   RowsGemm r;
   r.M = g.M; r.N = g.N; r.K = g.K;
   Packed2D pa, pb, pa2, pb2;
-  // K-major: stored [rows, K]; MN-major: stored [K, rows]
-  RAU_TRY(pack2d(ctx, g.A, a_mn ? g.sak : g.sam, a_mn ? g.K : g.M, a_mn ? g.M : g.K, x3, g.a_const != 0, "A", &pa));
-  RAU_TRY(pack2d(ctx, g.B, b_mn ? g.sbk : g.sbn, b_mn ? g.K : g.N, b_mn ? g.N : g.K, x3, g.b_const != 0, "B", &pb));
+  // K-major: stored [rows, K]; MN-major: stored [K, rows].  A producer may have left a packed twin of the operand.
+  auto twin_ok = [&](const bf16* hi, const bf16* lo, int64_t ld) {
+    return hi != nullptr && (!x3 || lo != nullptr) && ld % 8 == 0 && (((uintptr_t)hi | (uintptr_t)lo) & 15) == 0;
+  };
+  if (twin_ok(g.Ar_hi, g.Ar_lo, g.Ar_ld)) { pa.hi = g.Ar_hi; pa.lo = x3 ? g.Ar_lo : nullptr; pa.ld = g.Ar_ld; }
+  else RAU_TRY(pack2d(ctx, g.A, a_mn ? g.sak : g.sam, a_mn ? g.K : g.M, a_mn ? g.M : g.K, x3, g.a_const != 0, "A", &pa));
+  if (twin_ok(g.Br_hi, g.Br_lo, g.Br_ld)) { pb.hi = g.Br_hi; pb.lo = x3 ? g.Br_lo : nullptr; pb.ld = g.Br_ld; }
+  else RAU_TRY(pack2d(ctx, g.B, b_mn ? g.sbk : g.sbn, b_mn ? g.K : g.N, b_mn ? g.N : g.K, x3, g.b_const != 0, "B", &pb));
   r.A.hi = pa.hi; r.A.lo = pa.lo; r.A.mn = a_mn; r.A.ld = pa.ld;
   r.B.hi = pb.hi; r.B.lo = pb.lo; r.B.mn = b_mn; r.B.ld = pb.ld;
   if (g.A2) {
     const int a2_mn = (g.sak2 == 1) ? 0 : (g.sam2 == 1 ? 1 : -1);
     const int b2_mn = (g.sbk2 == 1) ? 0 : (g.sbn2 == 1 ? 1 : -1);
     if (a2_mn != a_mn || b2_mn != b_mn) return 0;
-    RAU_TRY(pack2d(ctx, g.A2, a_mn ? g.sak2 : g.sam2, a_mn ? g.K2 : g.M, a_mn ? g.M : g.K2, x3, g.a_const != 0, "A2", &pa2));
+    if (twin_ok(g.A2r_hi, g.A2r_lo, g.A2r_ld)) { pa2.hi = g.A2r_hi; pa2.lo = x3 ? g.A2r_lo : nullptr; pa2.ld = g.A2r_ld; }
+    else RAU_TRY(pack2d(ctx, g.A2, a_mn ? g.sak2 : g.sam2, a_mn ? g.K2 : g.M, a_mn ? g.M : g.K2, x3, g.a_const != 0, "A2", &pa2));
     RAU_TRY(pack2d(ctx, g.B2, b_mn ? g.sbk2 : g.sbn2, b_mn ? g.K2 : g.N, b_mn ? g.N : g.K2, x3, g.b_const != 0, "B2", &pb2));
     r.A2.hi = pa2.hi; r.A2.lo = pa2.lo; r.A2.mn = a_mn; r.A2.ld = pa2.ld;
     r.B2.hi = pb2.hi; r.B2.lo = pb2.lo; r.B2.mn = b_mn; r.B2.ld = pb2.ld;

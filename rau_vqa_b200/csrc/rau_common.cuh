@@ -227,6 +227,11 @@ struct SimtGemm {
   // indexing, and optional bf16 (hi, lo) copies of the result indexed like C
   const bf16 *A_hi = nullptr, *A_lo = nullptr, *B_hi = nullptr, *B_lo = nullptr;
   bf16 *C_hi = nullptr, *C_lo = nullptr;
+  // rows engine only: packed bf16 (hi, lo) twins of the operands AS STORED ([M or K rows, pitch ld], ld % 8 == 0), written
+  // by the producing kernel; with them the product needs no pack launch
+  const bf16 *Ar_hi = nullptr, *Ar_lo = nullptr; int64_t Ar_ld = 0;
+  const bf16 *A2r_hi = nullptr, *A2r_lo = nullptr; int64_t A2r_ld = 0;
+  const bf16 *Br_hi = nullptr, *Br_lo = nullptr; int64_t Br_ld = 0;
   int accumulate = 0;
   float alpha = 1.0f;
   int act = 0;                     // 0 none, 1 tanh, 2 sigmoid

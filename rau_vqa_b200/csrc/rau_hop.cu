@@ -119,11 +119,16 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
   ARENA(prem, float, "hop.prem", B * M);
 
   // q_embed (F:231-236): qf = tanh(Wq drop(q) + bq + Wh h + bh)
-  RAU_TRY(k_dropout(ctx, q, B, Q, Q, qb, drop_scale(cfg->p_q), sv.qd, Q, nullptr, 0, Q));
+  // (packed twins, training step only: every producer below also writes the bf16 (hi, lo) form its consumers' tcgen05
+  // products read, so the chain carries no pack launches)
+  RAU_TRY(k_dropout(ctx, q, B, Q, Q, qb, drop_scale(cfg->p_q), sv.qd, Q, sv.qd_pk.hi, (int)sv.qd_pk.ld, Q, x3 ? sv.qd_pk.lo : nullptr));
   {
     SimtGemm g = lin_fwd(B, M, Q, sv.qd, Q, P.Wq, sv.qf, M);
     lin_seg2(g, H, h, H, P.Wh);
     g.bias_n = P.bq; g.bias_n2 = P.bh; g.act = 1;
+    g.Ar_hi = sv.qd_pk.hi; g.Ar_lo = sv.qd_pk.lo; g.Ar_ld = sv.qd_pk.ld;
+    g.A2r_hi = sv.hin_pk.hi; g.A2r_lo = sv.hin_pk.lo; g.A2r_ld = sv.hin_pk.ld;
+    if (sv.qf_pk.hi && sv.qf_pk.ld == M) { g.C_hi = sv.qf_pk.hi; g.C_lo = sv.qf_pk.lo; }
     RAU_TRY(rau_contract(ctx, g));
   }
   if (rows_path(ctx, cfg)) {
@@ -141,11 +146,13 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
     {
       SimtGemm g = lin_fwd(B, A, M, sv.qf, M, P.Wqa, qatt, A);
       g.bias_n = P.bqa;
+      g.Ar_hi = sv.qf_pk.hi; g.Ar_lo = sv.qf_pk.lo; g.Ar_ld = sv.qf_pk.ld;
       RAU_TRY(rau_contract(ctx, g));
     }
     {
       SimtGemm g = lin_fwd(B, S, H, h, H, P.Wm, mem, S);
       g.bias_n = P.bm;
+      g.Ar_hi = sv.hin_pk.hi; g.Ar_lo = sv.hin_pk.lo; g.Ar_ld = sv.hin_pk.ld;
       RAU_TRY(rau_contract(ctx, g));
     }
     if (as && as->pre_done) RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, as->pre_done, 0));
@@ -159,7 +166,8 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
       g.out_f = sv.E; g.ldo = A;
       RAU_TRY(rows_gemm(ctx, g));
     }
-    RAU_TRY(k_attn_rows_fwd(ctx, B, M, S, slog, mem, sv.I_hi, x3 ? sv.I_lo : nullptr, sv.p, a));
+    RAU_TRY(k_attn_rows_fwd(ctx, B, M, S, slog, mem, sv.I_hi, x3 ? sv.I_lo : nullptr, sv.p, a, sv.p_pk.hi,
+                            x3 ? sv.p_pk.lo : nullptr, (int)sv.p_pk.ld));
   } else {
   // i_embed (F:238-242): I[b] = tanh(Wi drop(X[b]) + bi), 1x1 convolution = per-image [M,C]x[C,S] product
   if (tc) RAU_TRY(k_dropout_pack(ctx, X, (int64_t)B * C, S, xb, drop_scale(cfg->p_x), sv.Xd_hi, x3 ? sv.Xd_lo : nullptr, Sp));
@@ -205,6 +213,8 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
   {
     SimtGemm g = lin_fwd(B, M, S, sv.p, S, P.Wp, sv.j, M);
     g.bias_n = P.bp; g.addend = sv.qf; g.sdm = M; g.sdn = 1; g.addend2 = a;
+    if (rows_path(ctx, cfg)) { g.Ar_hi = sv.p_pk.hi; g.Ar_lo = sv.p_pk.lo; g.Ar_ld = sv.p_pk.ld; }   // (written by the rows attention kernel)
+    if (sv.j_pk.hi && sv.j_pk.ld == M) { g.C_hi = sv.j_pk.hi; g.C_lo = sv.j_pk.lo; }
     RAU_TRY(rau_contract(ctx, g));
   }
   // attlstm (A:4-28): gates (i,g,f,o)
@@ -218,14 +228,17 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
     RAU_TRY(rows_pack_lstm(ctx, P.Wx, H, M, RAU_GATES_IGFO, x3, &Wx_h, &Wx_l, &ldwx));
     RAU_TRY(rows_pack_lstm(ctx, P.Whh, H, H, RAU_GATES_IGFO, x3, &Wh_h, &Wh_l, &ldwh));
     RAU_TRY(rows_perm_lstm_bias(ctx, P.bx, P.bhh, H, RAU_GATES_IGFO, &bperm));
-    RAU_TRY(rows_pack2d(ctx, sv.j, M, B, M, x3, false, "cell.j", &j_h, &j_l, &ldj));
-    RAU_TRY(rows_pack2d(ctx, h, H, B, H, x3, false, "cell.h", &h_h, &h_l, &ldh_));
+    if (sv.j_pk.hi && (!x3 || sv.j_pk.lo)) { j_h = sv.j_pk.hi; j_l = x3 ? sv.j_pk.lo : nullptr; ldj = sv.j_pk.ld; }
+    else RAU_TRY(rows_pack2d(ctx, sv.j, M, B, M, x3, false, "cell.j", &j_h, &j_l, &ldj));
+    if (sv.hin_pk.hi && (!x3 || sv.hin_pk.lo)) { h_h = sv.hin_pk.hi; h_l = x3 ? sv.hin_pk.lo : nullptr; ldh_ = sv.hin_pk.ld; }
+    else RAU_TRY(rows_pack2d(ctx, h, H, B, H, x3, false, "cell.h", &h_h, &h_l, &ldh_));
     RowsGemm g;
     g.M = B; g.N = 4 * H; g.K = M;
     g.A.hi = j_h; g.A.lo = j_l; g.A.ld = ldj; g.B.hi = Wx_h; g.B.lo = Wx_l; g.B.ld = ldwx;
     g.A2.hi = h_h; g.A2.lo = h_l; g.A2.ld = ldh_; g.B2.hi = Wh_h; g.B2.lo = Wh_l; g.B2.ld = ldwh; g.K2 = H;
     g.epi = ROWS_EPI_LSTM; g.bias = bperm;
     g.c_prev = c; g.ldcp = H; g.c_out = c_out; g.ldc = H; g.h_out = sv.hout; g.ldh = H; g.lsaved = sv.lsav;
+    if (sv.hout_pk.hi && sv.hout_pk.ld % 8 == 0) { g.hpk_hi = sv.hout_pk.hi; g.hpk_lo = x3 ? sv.hout_pk.lo : nullptr; g.ldhp = sv.hout_pk.ld; }
     RAU_TRY(rows_gemm(ctx, g));
   } else {
     SimtGemm g = lin_fwd(B, 4 * H, M, sv.j, M, P.Wx, Gt, 4 * H);
@@ -233,6 +246,8 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
     g.bias_n = P.bx; g.bias_n2 = P.bhh;
     RAU_TRY(rau_contract(ctx, g));
     RAU_TRY(k_lstm_fwd(ctx, B, H, RAU_GATES_IGFO, Gt, 4 * H, c, H, c_out, H, sv.hout, H, nullptr, 0, sv.lsav));
+    if (sv.hout_pk.hi)   // the next hop reads h' through its packed twin: the unfused cell does not write it
+      RAU_TRY(rows_pack_into(ctx, sv.hout, H, B, H, sv.hout_pk.hi, x3 ? sv.hout_pk.lo : nullptr, sv.hout_pk.ld));
   }
   if (h_out && h_out != sv.hout)
     RAU_CHECK_CUDA(cudaMemcpyAsync(h_out, sv.hout, sizeof(float) * B * H, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -240,12 +255,14 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
   {
     SimtGemm g = lin_fwd(B, M, H, sv.hout, H, P.Wo, prem, M);
     g.bias_n = P.bo; g.addend = sv.j; g.sdm = M; g.sdn = 1;
+    g.Ar_hi = sv.hout_pk.hi; g.Ar_lo = sv.hout_pk.lo; g.Ar_ld = sv.hout_pk.ld;   // (written by the cell epilogue / the pack above)
     RAU_TRY(rau_contract(ctx, g));
   }
-  RAU_TRY(k_dropout(ctx, prem, B, M, M, mb, drop_scale(cfg->p_m), sv.m, M, nullptr, 0, M));
+  RAU_TRY(k_dropout(ctx, prem, B, M, M, mb, drop_scale(cfg->p_m), sv.m, M, sv.m_pk.hi, (int)sv.m_pk.ld, M, x3 ? sv.m_pk.lo : nullptr));
   {
     SimtGemm g = lin_fwd(B, N, M, sv.m, M, P.Ws, score, N);
     g.bias_n = P.bso;
+    g.Ar_hi = sv.m_pk.hi; g.Ar_lo = sv.m_pk.lo; g.Ar_ld = sv.m_pk.ld;
     RAU_TRY(rau_contract(ctx, g));
   }
   RAU_TRY(k_rowdot_sigmoid(ctx, sv.m, B, M, P.wd, P.bd, sv.dop));
@@ -304,10 +321,19 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   float* dpre = now ? dpre_own : deferred->dpre;
   ARENA(dqt, float, "hopb.dqt", B * Q);
   const int ks_img = B >= 64 ? 32 : (B >= 8 ? 8 : 1);   // split of the per-image reductions
+  // packed twins written by the producers (training step; NULL members fall back to a pack launch per product)
+  const PK no_pk;
+  const PK& dscore_pk = deferred ? deferred->dscore_pk : no_pk;
+  const PK& du_pk = deferred ? deferred->du_pk : no_pk;
+  const PK& dG_pk = deferred ? deferred->dG_pk : no_pk;
+  const PK& ds_pk = deferred ? deferred->ds_pk : no_pk;
+  const PK& dpre_pk = deferred ? deferred->dpre_pk : no_pk;
 
   // heads: dm = Ws^T dscore (+ do_pred head) ; gWs += dscore (x) m
   if (dscore) {
-    RAU_TRY(rau_contract(ctx, lin_dgrad(B, N, M, dscore, N, P.Ws, du, M)));
+    SimtGemm gd = lin_dgrad(B, N, M, dscore, N, P.Ws, du, M);
+    gd.Ar_hi = dscore_pk.hi; gd.Ar_lo = dscore_pk.lo; gd.Ar_ld = dscore_pk.ld;
+    RAU_TRY(rau_contract(ctx, gd));
     if (now) {
       RAU_TRY(rau_contract(ctx, lin_wgrad(B, N, M, dscore, N, sv.m, M, G.Ws, 1.0f)));
       RAU_TRY(k_colsum(ctx, dscore, B, N, N, G.bso, 1));
@@ -316,11 +342,13 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
     RAU_TRY(k_fill(ctx, du, (int64_t)B * M, 0.0f));
   }
   if (ddo_pred) RAU_TRY(k_dopred_bwd(ctx, ddo_pred, sv.dop, sv.m, P.wd, B, M, du, G.wd, G.bd));
-  RAU_TRY(k_dropout_bwd_acc(ctx, du, (int64_t)B * M, mb, drop_scale(cfg->p_m), du, 0));
+  RAU_TRY(k_dropout_bwd_acc(ctx, du, (int64_t)B * M, mb, drop_scale(cfg->p_m), du, 0, du_pk.ld == M ? du_pk.hi : nullptr,
+                            (du_pk.ld == M && x3) ? du_pk.lo : nullptr));
   // dh' = dh_next + Wo^T du ; gWo += du (x) h'
   {
     SimtGemm g = lin_dgrad(B, M, H, du, M, P.Wo, dh2, H);
     if (dh_out) { g.addend = dh_out; g.sdm = H; g.sdn = 1; }
+    if (du_pk.ld == M) { g.Ar_hi = du_pk.hi; g.Ar_lo = du_pk.lo; g.Ar_ld = M; }
     RAU_TRY(rau_contract(ctx, g));
   }
   if (now) {
@@ -328,14 +356,20 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
     RAU_TRY(k_colsum(ctx, du, B, M, M, G.bo, 1));
   }
   // attlstm backward
+  const bool dG_twin = dG_pk.hi != nullptr && dG_pk.ld == 4 * H;
   RAU_TRY(k_lstm_bwd(ctx, B, H, RAU_GATES_IGFO, dc_out, H, dh2, H, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, c, H,
-                     sv.lsav, dG, nullptr, dc, H));
+                     sv.lsav, dG, dG_twin ? dG_pk.hi : nullptr, dc, H, (dG_twin && x3) ? dG_pk.lo : nullptr));
   {
     SimtGemm g = lin_dgrad(B, 4 * H, M, dG, 4 * H, P.Wx, dj, M);
     g.addend = du; g.sdm = M; g.sdn = 1;
+    if (dG_twin) { g.Ar_hi = dG_pk.hi; g.Ar_lo = dG_pk.lo; g.Ar_ld = 4 * H; }
     RAU_TRY(rau_contract(ctx, g));
   }
-  RAU_TRY(rau_contract(ctx, lin_dgrad(B, 4 * H, H, dG, 4 * H, P.Whh, dh, H)));
+  {
+    SimtGemm g = lin_dgrad(B, 4 * H, H, dG, 4 * H, P.Whh, dh, H);
+    if (dG_twin) { g.Ar_hi = dG_pk.hi; g.Ar_lo = dG_pk.lo; g.Ar_ld = 4 * H; }
+    RAU_TRY(rau_contract(ctx, g));
+  }
   if (now) {
     RAU_TRY(rau_contract(ctx, lin_wgrad(B, 4 * H, M, dG, 4 * H, sv.j, M, G.Wx, 1.0f)));
     RAU_TRY(rau_contract(ctx, lin_wgrad(B, 4 * H, H, dG, 4 * H, h, H, G.Whh, 1.0f)));
@@ -356,13 +390,15 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   const bool rows = rows_path(ctx, cfg);
   const int R = B * S;
   if (rows)
-    RAU_TRY(k_attn_rows_bwd(ctx, B, M, A, S, sv.E, sv.I_hi, x3 ? sv.I_lo : nullptr, P.ws, sv.p, dp, dj, ds, dZ_hi, dZ_lo, dqa, gwsp));
+    RAU_TRY(k_attn_rows_bwd(ctx, B, M, A, S, sv.E, sv.I_hi, x3 ? sv.I_lo : nullptr, P.ws, sv.p, dp, dj, ds, dZ_hi, dZ_lo, dqa, gwsp,
+                            ds_pk.hi, x3 ? ds_pk.lo : nullptr, (int)ds_pk.ld));
   else
     RAU_TRY(k_attn_bwd<float>(ctx, B, M, A, S, Sp, sv.E, sv.I, P.ws, sv.p, dp, dj, ds, nullptr, 0, dZ, dqa, nullptr, gwsp,
                               dZ_hi, dZ_lo));
   {
     SimtGemm g = lin_dgrad(B, S, H, ds, S, P.Wm, dh, H);
     g.accumulate = 1;
+    if (rows) { g.Ar_hi = ds_pk.hi; g.Ar_lo = ds_pk.lo; g.Ar_ld = ds_pk.ld; }   // (written by the rows attention backward)
     RAU_TRY(rau_contract(ctx, g));
   }
   if (now) {
@@ -499,12 +535,18 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   }
   }
   // q_embed backward
-  RAU_TRY(k_tanh_bwd(ctx, dqf, sv.qf, (int64_t)B * M, dpre, nullptr));
-  RAU_TRY(rau_contract(ctx, lin_dgrad(B, M, Q, dpre, M, P.Wq, dqt, Q)));
+  const bool dpre_twin = dpre_pk.hi != nullptr && dpre_pk.ld == M;
+  RAU_TRY(k_tanh_bwd(ctx, dqf, sv.qf, (int64_t)B * M, dpre, dpre_twin ? dpre_pk.hi : nullptr, (dpre_twin && x3) ? dpre_pk.lo : nullptr));
+  {
+    SimtGemm g = lin_dgrad(B, M, Q, dpre, M, P.Wq, dqt, Q);
+    if (dpre_twin) { g.Ar_hi = dpre_pk.hi; g.Ar_lo = dpre_pk.lo; g.Ar_ld = M; }
+    RAU_TRY(rau_contract(ctx, g));
+  }
   RAU_TRY(k_dropout_bwd_acc(ctx, dqt, (int64_t)B * Q, qb, drop_scale(cfg->p_q), dq, dq_accumulate));
   {
     SimtGemm g = lin_dgrad(B, M, H, dpre, M, P.Wh, dh, H);
     g.accumulate = 1;
+    if (dpre_twin) { g.Ar_hi = dpre_pk.hi; g.Ar_lo = dpre_pk.lo; g.Ar_ld = M; }
     RAU_TRY(rau_contract(ctx, g));
   }
   if (now) {
@@ -519,27 +561,33 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
 // accGradParameters of every nn.Linear of the answering unit, once over the rows of all hops (rows = nHop * B)
 int hop_wgrads(rau_ctx* ctx, const rau_config* cfg, int rows, const MultT<float*>& G, const HopStacks& st) {
   const int Q = 2 * cfg->Hq * cfg->nlayer, M = cfg->M, A = cfg->A, H = cfg->H, S = cfg->S, N = cfg->N;
-  RAU_TRY(rau_contract(ctx, lin_wgrad(rows, N, M, st.dscore, N, st.m, M, G.Ws, 1.0f)));
+  // gW[N_out, K_in] += dY[rows, N_out]^T X[rows, K_in]; both operands are read as stored (MN-major), from their packed
+  // twins when the producers left them
+  auto wg = [&](int Nout, int Kin, const float* dY, const PK& dYp, const float* X, const PK& Xp, float* gW) {
+    SimtGemm g = lin_wgrad(rows, Nout, Kin, dY, Nout, X, Kin, gW, 1.0f);
+    if (dYp.ld == Nout) { g.Ar_hi = dYp.hi; g.Ar_lo = dYp.lo; g.Ar_ld = dYp.ld; }
+    if (Xp.ld == Kin) { g.Br_hi = Xp.hi; g.Br_lo = Xp.lo; g.Br_ld = Xp.ld; }
+    return rau_contract(ctx, g);
+  };
+  const PK none;
+  RAU_TRY(wg(N, M, st.dscore, st.dscore_pk, st.m, st.m_pk, G.Ws));
   RAU_TRY(k_colsum(ctx, st.dscore, rows, N, N, G.bso, 1));
-  RAU_TRY(rau_contract(ctx, lin_wgrad(rows, M, H, st.du, M, st.hout, H, G.Wo, 1.0f)));
+  RAU_TRY(wg(M, H, st.du, st.du_pk, st.hout, st.hout_pk, G.Wo));
   RAU_TRY(k_colsum(ctx, st.du, rows, M, M, G.bo, 1));
-  RAU_TRY(rau_contract(ctx, lin_wgrad(rows, 4 * H, M, st.dG, 4 * H, st.j, M, G.Wx, 1.0f)));
-  RAU_TRY(rau_contract(ctx, lin_wgrad(rows, 4 * H, H, st.dG, 4 * H, st.h_in, H, G.Whh, 1.0f)));
-  RAU_TRY(k_colsum(ctx, st.dG, rows, 4 * H, 4 * H, G.bx, 1));
-  RAU_TRY(k_colsum(ctx, st.dG, rows, 4 * H, 4 * H, G.bhh, 1));
-  RAU_TRY(rau_contract(ctx, lin_wgrad(rows, M, S, st.dj, M, st.p, S, G.Wp, 1.0f)));
+  RAU_TRY(wg(4 * H, M, st.dG, st.dG_pk, st.j, st.j_pk, G.Wx));
+  RAU_TRY(wg(4 * H, H, st.dG, st.dG_pk, st.h_in, st.hin_pk, G.Whh));
+  RAU_TRY(k_colsum(ctx, st.dG, rows, 4 * H, 4 * H, G.bx, 1, G.bhh));
+  RAU_TRY(wg(M, S, st.dj, none, st.p, none, G.Wp));            // (p's twin has pitch 200, not S: packed on demand)
   RAU_TRY(k_colsum(ctx, st.dj, rows, M, M, G.bp, 1));
-  RAU_TRY(rau_contract(ctx, lin_wgrad(rows, S, H, st.ds, S, st.h_in, H, G.Wm, 1.0f)));
+  RAU_TRY(wg(S, H, st.ds, none, st.h_in, st.hin_pk, G.Wm));
   RAU_TRY(k_colsum(ctx, st.ds, rows, S, S, G.bm, 1));
   RAU_TRY(k_colsum(ctx, st.gwsp, rows, A, A, G.ws, 1));
   RAU_TRY(k_sum_all(ctx, st.ds, (int64_t)rows * S, G.bs, 1));
-  RAU_TRY(k_colsum(ctx, st.dqa, rows, A, A, G.ba, 1));
-  RAU_TRY(rau_contract(ctx, lin_wgrad(rows, A, M, st.dqa, A, st.qf, M, G.Wqa, 1.0f)));
-  RAU_TRY(k_colsum(ctx, st.dqa, rows, A, A, G.bqa, 1));
-  RAU_TRY(rau_contract(ctx, lin_wgrad(rows, M, Q, st.dpre, M, st.qd, Q, G.Wq, 1.0f)));
-  RAU_TRY(rau_contract(ctx, lin_wgrad(rows, M, H, st.dpre, M, st.h_in, H, G.Wh, 1.0f)));
-  RAU_TRY(k_colsum(ctx, st.dpre, rows, M, M, G.bq, 1));
-  RAU_TRY(k_colsum(ctx, st.dpre, rows, M, M, G.bh, 1));
+  RAU_TRY(wg(A, M, st.dqa, none, st.qf, st.qf_pk, G.Wqa));
+  RAU_TRY(k_colsum(ctx, st.dqa, rows, A, A, G.ba, 1, G.bqa));
+  RAU_TRY(wg(M, Q, st.dpre, st.dpre_pk, st.qd, st.qd_pk, G.Wq));
+  RAU_TRY(wg(M, H, st.dpre, st.dpre_pk, st.h_in, st.hin_pk, G.Wh));
+  RAU_TRY(k_colsum(ctx, st.dpre, rows, M, M, G.bq, 1, G.bh));
   return RAU_OK;
 }
 

@@ -26,18 +26,20 @@ int k_lstm_bwd(rau_ctx* ctx, int B, int H, int order,
                const float* dh_extra, int ldhe,
                const float* lengths, int t, const float* dq_c, const float* dq_h, int lddq,
                const float* c_prev, int ldcp, const float* saved,
-               float* dG, bf16* dG_b, float* dc_prev, int lddcp, bf16* dG_lo = nullptr);   // dG_b / dG_lo: packed (hi, lo) copy
+               float* dG, bf16* dG_b, float* dc_prev, int lddcp, bf16* dG_lo = nullptr,   // dG_b / dG_lo: packed (hi, lo) copy
+               float* zero_out = nullptr);   // optional [B, H] buffer cleared on the way (target of the next split-K dgrad)
 
 // ---- generic elementwise
 // y = x * keep(bits) * scale over a [rows, cols] matrix (mask indexed by row*cols+col); padded output pitch
 int k_dropout(rau_ctx* ctx, const float* x, int64_t rows, int cols, int ldx, const uint32_t* bits, float scale,
-              float* y_f, int ldyf, bf16* y_b, int ldyb, int cols_pad);
+              float* y_f, int ldyf, bf16* y_b, int ldyb, int cols_pad, bf16* y_lo = nullptr);   // y_b / y_lo: packed (hi, lo)
 // y = x*keep*scale written only as packed bf16 (hi, lo) rows of pitch cols_pad: a tcgen05 operand (cols % 4 == 0)
 int k_dropout_pack(rau_ctx* ctx, const float* x, int64_t rows, int cols, const uint32_t* bits, float scale, bf16* hi, bf16* lo,
                    int cols_pad);
 // y (+)= x*keep*scale  (used for dq accumulation over hops and dX)
-int k_dropout_bwd_acc(rau_ctx* ctx, const float* dx, int64_t n, const uint32_t* bits, float scale, float* y, int accumulate);
-int k_tanh_bwd(rau_ctx* ctx, const float* dy, const float* y, int64_t n, float* dx_f, bf16* dx_b);
+int k_dropout_bwd_acc(rau_ctx* ctx, const float* dx, int64_t n, const uint32_t* bits, float scale, float* y, int accumulate,
+                      bf16* y_hi = nullptr, bf16* y_lo = nullptr);
+int k_tanh_bwd(rau_ctx* ctx, const float* dy, const float* y, int64_t n, float* dx_f, bf16* dx_b, bf16* dx_lo = nullptr);
 int k_add(rau_ctx* ctx, const float* a, const float* b, int64_t n, float* y);              // y = a + b
 int k_axpy(rau_ctx* ctx, float alpha, const float* x, int64_t n, float* y);                // y += alpha x
 int k_fill(rau_ctx* ctx, float* x, int64_t n, float v);
@@ -78,7 +80,7 @@ int k_iembed_bwd_rows(rau_ctx* ctx, int B, int M, int S, int Sp, const float* dI
 
 // ---- criteria (a12)
 int k_softmax_ce(rau_ctx* ctx, int B, int N, const float* score, const float* labels, float loss_scale, float grad_scale,
-                 float* loss_sum, float* dscore_f, bf16* dscore_b, int lddb, float* answers);
+                 float* loss_sum, float* dscore_f, bf16* dscore_b, int lddb, float* answers, bf16* dscore_lo = nullptr);
 // logging-only merged predictions (F:539-574) over all hops; also writes uni/select when requested (predict)
 int k_merge_preds(rau_ctx* ctx, int nHop, int B, int N, int S, const float* scores, const float* do_pred,
                   const float* attprob, const float* labels, const float* answers_hop, int force_last, float inv_bglobal,

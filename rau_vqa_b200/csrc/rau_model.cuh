@@ -45,6 +45,9 @@ static inline SimtGemm lin_wgrad(int rows, int N, int K, const float* dY, int ld
   return g;
 }
 
+// packed bf16 (hi, lo) twin of an fp32 activation [rows, ld]: the tcgen05 operand form, written by the producing kernel
+struct PK { bf16* hi = nullptr; bf16* lo = nullptr; int64_t ld = 0; };
+
 // activations one answering unit keeps for its backward pass (carved out of one caller- or arena-owned block)
 struct HopSaved {
   uint32_t *qbits, *xbits, *mbits;   // packed keep bits of the three dropouts (F:233, F:239, F:277)
@@ -54,6 +57,8 @@ struct HopSaved {
   // Philox stream instead of being materialised in xbits first (nothing in the step reads them again: dX is not formed)
   int x_philox = 0;
   uint64_t x_stream = 0;
+  // training step: packed twins of the small activations (all NULL through the module-level API, which packs on demand)
+  PK qd_pk, qf_pk, p_pk, j_pk, hin_pk, hout_pk, m_pk;
 };
 bool hop_rows_path(const rau_ctx* ctx, const rau_config* cfg);
 
@@ -74,9 +79,13 @@ size_t hop_saved_layout(const rau_config* cfg, int B, void* base, HopSaved* sv);
 // tensor-major stacks [nHop][B][dim], hop_backward skips every nn.Linear accGradParameters, and hop_wgrads() issues
 // each of them ONCE over all nHop*B rows after the last hop (the clones share one gradWeight, F:344, so the sum over
 // hops is what the reference accumulates anyway).
-struct HopGrads { float *du, *dG, *dj, *ds, *dqa, *dpre, *gwsp; };
+struct HopGrads {
+  float *du, *dG, *dj, *ds, *dqa, *dpre, *gwsp;
+  PK dscore_pk, du_pk, dG_pk, ds_pk, dpre_pk;   // packed twins written by the producing kernels (may be NULL)
+};
 struct HopStacks {   // every member is [nHop][B][dim]
   const float *dscore, *m, *du, *hout, *dG, *j, *h_in, *dj, *p, *ds, *dqa, *qf, *dpre, *qd, *gwsp;
+  PK dscore_pk, m_pk, du_pk, hout_pk, dG_pk, j_pk, hin_pk, p_pk, ds_pk, qf_pk, dpre_pk, qd_pk;   // packed stacks (may be NULL)
 };
 int hop_wgrads(rau_ctx* ctx, const rau_config* cfg, int rows, const MultT<float*>& G, const HopStacks& st);
 

@@ -50,13 +50,15 @@ int rows_pack2d(rau_ctx* ctx, const float* src, int64_t ld, int rows, int cols, 
 int rows_pack_lstm(rau_ctx* ctx, const float* W, int H, int K, int gate_order, bool want_lo, const bf16** hi, const bf16** lo,
                    int64_t* ldo);
 int rows_perm_lstm_bias(rau_ctx* ctx, const float* b1, const float* b2, int H, int gate_order, const float** out);
+// same, into a caller-owned packed twin (pitch ldo >= cols, zero padded)
+int rows_pack_into(rau_ctx* ctx, const float* src, int64_t ld, int rows, int cols, bf16* hi, bf16* lo, int64_t ldo);
 int rows_pack(rau_ctx* ctx, const float* W, int64_t n, bool want_lo, bool cache, const char* slot, const bf16** hi, const bf16** lo);
 // gen != 0: draw the keep bits inline from Philox stream `stream_id` with drop rate p_drop (bits is then ignored)
 int k_xprep_rows(rau_ctx* ctx, const float* X, int B, int C, int S, const uint32_t* bits, float scale, bf16* hi, bf16* lo,
                  int gen = 0, float p_drop = 0.0f, uint64_t stream_id = 0);
 int k_unprep_rows(rau_ctx* ctx, const float* dXr, int B, int C, int S, const uint32_t* bits, float scale, float* dX);
 int k_attn_rows_fwd(rau_ctx* ctx, int B, int M, int S, const float* logit, const float* mem, const bf16* I_hi, const bf16* I_lo,
-                    float* p, float* a);
+                    float* p, float* a, bf16* p_hi = nullptr, bf16* p_lo = nullptr, int ldp = 0);   // p_hi/p_lo: packed twin of p
 int k_attn_rows_bwd(rau_ctx* ctx, int B, int M, int A, int S, const float* E, const bf16* I_hi, const bf16* I_lo, const float* ws,
                     const float* p, const float* dp_in, const float* da, float* ds, bf16* dZ_hi, bf16* dZ_lo, float* dqa,
-                    float* gws_part);
+                    float* gws_part, bf16* ds_hi = nullptr, bf16* ds_lo = nullptr, int ldds = 0);

@@ -185,6 +185,8 @@ static int encoder_backward(rau_ctx* ctx, const rau_config* cfg, const rau_batch
     const size_t gb = (size_t)B * G4, hb = (size_t)B * Hq;
     const int R = Tm * B;
     ARENA(dGp, bf16, "encb.dGp", (size_t)4 * cfg->T * gb);   // [layer][hi, lo][T][B][4H]
+    ARENA(dH2, float, "encb.dH2", (size_t)2 * hb);            // ping-pong: the cell backward of step t clears the buffer
+    float* dHb[2] = {dH2, dH2 + hb};                          // the dgrad of step t reduces into, while reading the other
     bf16* hpk_all = nullptr;
     RAU_TRY(ctx->arena.get("enc.hpk", sizeof(bf16) * (size_t)4 * (cfg->T + 1) * hb, (void**)&hpk_all));
     for (int layer = 1; layer >= 0; --layer) {
@@ -199,18 +201,20 @@ static int encoder_backward(rau_ctx* ctx, const rau_config* cfg, const rau_batch
       for (int t = Tm; t >= 1; --t) {
         const bool last = t == Tm;
         const float* Sp_ = en->S_all + (size_t)(t - 1) * B * Q + 2 * layer * Hq;
+        float* dH = dHb[t & 1];            // written by step t+1's dgrad
+        float* dH_next = dHb[(t + 1) & 1];   // cleared here, reduced into by this step's dgrad
         RAU_TRY(k_lstm_bwd(ctx, B, Hq, RAU_GATES_IFOG, last ? nullptr : dC, Hq, last ? nullptr : dH, Hq,
                            layer == 0 ? du2 + (size_t)(t - 1) * hb : nullptr, Hq, bt->lengths, t, dq + 2 * layer * Hq,
                            dq + (2 * layer + 1) * Hq, Q, Sp_, Q,
                            (layer == 1 ? en->sav2 : en->sav1) + (size_t)(t - 1) * 5 * hb, dG + (size_t)(t - 1) * gb,
-                           dG_hi + (size_t)(t - 1) * gb, dC, Hq, dG_lo ? dG_lo + (size_t)(t - 1) * gb : nullptr));
+                           dG_hi + (size_t)(t - 1) * gb, dC, Hq, dG_lo ? dG_lo + (size_t)(t - 1) * gb : nullptr,
+                           t > 1 ? dH_next : nullptr));
         if (t > 1) {   // dH = dG_t Wh: K = 4H over a [B, Hq] output -> split over the SMs, partial sums TMA-reduced
-          RAU_CHECK_CUDA(cudaMemsetAsync(dH, 0, sizeof(float) * hb, ctx->stream));
           RowsGemm g;
           g.M = B; g.N = Hq; g.K = G4;
           g.A.hi = dG_hi + (size_t)(t - 1) * gb; g.A.lo = dG_lo ? dG_lo + (size_t)(t - 1) * gb : nullptr; g.A.ld = G4;
           g.B.hi = Wh_h; g.B.lo = Wh_l; g.B.mn = 1; g.B.ld = ldwh;
-          g.epi = ROWS_EPI_RED; g.out_f = dH; g.ldo = Hq;
+          g.epi = ROWS_EPI_RED; g.out_f = dH_next; g.ldo = Hq;
           RAU_TRY(rows_gemm(ctx, g));
         }
       }
@@ -397,12 +401,42 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   ARENA(st_dqa, float, "stack.dqa", (size_t)nHop * B * A_);
   ARENA(st_dpre, float, "stack.dpre", (size_t)nHop * B * M_);
   ARENA(st_gwsp, float, "stack.gwsp", (size_t)nHop * B * A_);
+  // packed bf16 (hi, lo) twins of the same stacks, written by the producing kernels: the tcgen05 products of the chain
+  // and the deferred weight gradients read them directly (no pack launches)
+  const bool twins = ctx->precision != RAU_PREC_F32 && rows_path_enabled();
+  const int Sp8 = (S + 7) / 8 * 8;
+  PK pk_qd, pk_qf, pk_p, pk_j, pk_h, pk_m, pk_dscore, pk_du, pk_dG, pk_ds, pk_dpre;
+  auto mkpk = [&](const char* name, size_t rows, int64_t ld, PK* out) -> int {
+    if (!twins || ld % 8 != 0) return RAU_OK;
+    bf16* base = nullptr;
+    const size_t n = rows * (size_t)ld;
+    RAU_TRY(ctx->arena.get(name, sizeof(bf16) * 2 * n, (void**)&base));
+    out->hi = base; out->lo = base + n; out->ld = ld;
+    return RAU_OK;
+  };
+  auto slice = [](const PK& pk, size_t row) {
+    PK r;
+    if (pk.hi) { r.hi = pk.hi + row * pk.ld; r.lo = pk.lo + row * pk.ld; r.ld = pk.ld; }
+    return r;
+  };
+  const size_t nb = (size_t)nHop * B;
+  RAU_TRY(mkpk("pk.qd", nb, Q, &pk_qd));      RAU_TRY(mkpk("pk.qf", nb, M_, &pk_qf));   RAU_TRY(mkpk("pk.p", nb, Sp8, &pk_p));
+  RAU_TRY(mkpk("pk.j", nb, M_, &pk_j));       RAU_TRY(mkpk("pk.h", nb + B, H, &pk_h));  RAU_TRY(mkpk("pk.m", nb, M_, &pk_m));
+  RAU_TRY(mkpk("pk.dscore", nb, N, &pk_dscore)); RAU_TRY(mkpk("pk.du", nb, M_, &pk_du)); RAU_TRY(mkpk("pk.dG", nb, 4 * H, &pk_dG));
+  RAU_TRY(mkpk("pk.ds", nb, Sp8, &pk_ds));    RAU_TRY(mkpk("pk.dpre", nb, M_, &pk_dpre));
+  if (pk_h.hi) {   // h_0 = 0 (F:362-364)
+    RAU_CHECK_CUDA(cudaMemsetAsync(pk_h.hi, 0, sizeof(bf16) * (size_t)B * H, ctx->stream));
+    RAU_CHECK_CUDA(cudaMemsetAsync(pk_h.lo, 0, sizeof(bf16) * (size_t)B * H, ctx->stream));
+  }
   std::vector<HopSaved> sv(nHop);
   std::vector<HopAsync> as(nHop);
   for (int hp = 0; hp < nHop; ++hp) {
     hop_saved_layout(cfg, B, sv_base + sv_bytes * hp, &sv[hp]);
     as[hp].hop = hp;
     as[hp].bwd_side = ov_bwd ? 1 : 0;
+    const size_t r0 = (size_t)hp * B;
+    sv[hp].qd_pk = slice(pk_qd, r0); sv[hp].qf_pk = slice(pk_qf, r0); sv[hp].p_pk = slice(pk_p, r0); sv[hp].j_pk = slice(pk_j, r0);
+    sv[hp].hin_pk = slice(pk_h, r0); sv[hp].hout_pk = slice(pk_h, r0 + B); sv[hp].m_pk = slice(pk_m, r0);
     sv[hp].qd = st_qd + (size_t)hp * B * Q;
     sv[hp].qf = st_qf + (size_t)hp * B * M_;
     sv[hp].p = att + (size_t)hp * B * S;                 // the module outputs double as the saved copies
@@ -455,8 +489,10 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
                         c_all + (size_t)(hp + 1) * B * H, h_all + (size_t)(hp + 1) * B * H, &as[hp]));
     // criterion forward + backward + argmax in one pass (F:505, F:535, F:585-589)
     const float hm = hop_mask ? hop_mask[hp] : 1.0f;
+    const PK dsc = slice(pk_dscore, (size_t)hp * B);
     RAU_TRY(k_softmax_ce(ctx, B, N, scores + (size_t)hp * B * N, bt->labels, 1.0f / Bg, hm / Bg, loss + hp,
-                         dscore + (size_t)hp * B * N, nullptr, 0, ans + (size_t)hp * B));
+                         dscore + (size_t)hp * B * N, dsc.hi, N, ans + (size_t)hp * B,
+                         ctx->precision == RAU_PREC_BF16X3 ? dsc.lo : nullptr));
   }
   rau_phase_mark(ctx, "answering units forward");
   // logging-only losses on the averaged / selected predictions and the do_pred BCE (F:539-574)
@@ -476,6 +512,8 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     hg.du = st_du + (size_t)hp * B * M_; hg.dG = st_dG + (size_t)hp * B * 4 * H; hg.dj = st_dj + (size_t)hp * B * M_;
     hg.ds = st_ds + (size_t)hp * B * S; hg.dqa = st_dqa + (size_t)hp * B * A_; hg.dpre = st_dpre + (size_t)hp * B * M_;
     hg.gwsp = st_gwsp + (size_t)hp * B * A_;
+    hg.dscore_pk = slice(pk_dscore, (size_t)hp * B); hg.du_pk = slice(pk_du, (size_t)hp * B); hg.dG_pk = slice(pk_dG, (size_t)hp * B);
+    hg.ds_pk = slice(pk_ds, (size_t)hp * B); hg.dpre_pk = slice(pk_dpre, (size_t)hp * B);
     RAU_TRY(hop_backward(ctx, cfg, B, P, G, bt->feats, c_all + (size_t)hp * B * H, h_all + (size_t)hp * B * H, train, sv[hp],
                          dscore + (size_t)hp * B * N, nullptr, nullptr, dc_in, dh_in, dq, last ? 0 : 1, nullptr,
                          dcs + (size_t)(hp & 1) * B * H, dhs + (size_t)(hp & 1) * B * H, &hg, &as[hp]));
@@ -487,6 +525,8 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     st.dscore = dscore; st.m = st_m; st.du = st_du; st.hout = h_all + (size_t)B * H; st.dG = st_dG; st.j = st_j; st.h_in = h_all;
     st.dj = st_dj; st.p = att; st.ds = st_ds; st.dqa = st_dqa; st.qf = st_qf; st.dpre = st_dpre; st.qd = st_qd;
     st.gwsp = st_gwsp;
+    st.dscore_pk = pk_dscore; st.m_pk = pk_m; st.du_pk = pk_du; st.hout_pk = slice(pk_h, B); st.dG_pk = pk_dG; st.j_pk = pk_j;
+    st.hin_pk = pk_h; st.p_pk = pk_p; st.ds_pk = pk_ds; st.qf_pk = pk_qf; st.dpre_pk = pk_dpre; st.qd_pk = pk_qd;
     RAU_TRY(hop_wgrads(ctx, cfg, nHop * B, G, st));
   }
   rau_phase_mark(ctx, "unit weight gradients");
@@ -792,5 +832,8 @@ int rau_contract(rau_ctx* ctx, const SimtGemm& g) {
       return RAU_EINVAL;
     }
   }
-  return simt_gemm(ctx, g);
+  RAU_TRY(simt_gemm(ctx, g));
+  if (ctx->precision != RAU_PREC_F32 && g.C_hi && g.scn == 1 && g.batch == 1)   // keep the result's packed twin in step
+    RAU_TRY(rows_pack_into(ctx, g.C, g.scm, g.M, g.N, g.C_hi, ctx->precision == RAU_PREC_BF16X3 ? g.C_lo : nullptr, g.scm));
+  return RAU_OK;
 }
