@@ -282,9 +282,20 @@ def main():
         ms_k = ffi_time_iembed(ctx, cfg, B, P[2], resident[0][0])
         flops = 2.0 * cfg.M * cfg.C * 196 * B
         ach = flops / (ms_k * 1e-3) / 1e12
-        roof = dict(bound="tensor", kernel="i_embed projection (F:240), engine " + prec, achieved=ach, peak=pk["tensor_burst"],
-                    unit="TFLOP/s", frac=ach / pk["tensor_burst"], traffic=None, peak_source=pk["src"] + " bf16 burst",
-                    ms_per_launch=ms_k, flop_per_launch=flops)
+        # DRAM bytes of that kernel per launch from the committed `ncu --set full` capture (profiles/roofline_traffic.json,
+        # keyed by workload and precision mode); null when no capture of this configuration is committed
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+            traffic = tj.get(f"{args.workload}:{prec}:B{B}")
+        except Exception:
+            pass
+        executed = 3 if prec == "bf16x3" else 1
+        roof = dict(bound="tensor", kernel="rows_gemm_kernel<EPI_TANH>: i_embed product I = tanh(Wi drop(X) + bi) (F:238-242), engine " + prec,
+                    achieved=ach, peak=pk["tensor_burst"], unit="TFLOP/s", frac=ach / pk["tensor_burst"], traffic=traffic,
+                    peak_source=pk["src"] + " bf16 burst (kernel timed alone, 20 back-to-back launches, CUDA events)",
+                    ms_per_launch=ms_k, flop_per_launch=flops, algorithmic="2*196*B*M*C flop per launch (SURVEY 8d)",
+                    mma_passes=executed, executed_frac=executed * ach / pk["tensor_burst"])
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             sb = args.cpu_sample or 16
