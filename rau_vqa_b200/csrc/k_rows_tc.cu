@@ -41,6 +41,7 @@ struct RtParams {
   int M, N, K;
   int a_mn, b_mn, x3, BK, nkb;
   int nkb1;                        // k-blocks of the first segment (== nkb without a second segment)
+  int cg2;                         // launched as CTA pairs (cta_group::2, M = 256 per item)
   int a_swap, b_swap;              // bf16x3: plane 0 of the operand's 3-D box is the lo array (lo lies below hi in memory)
   int BN;                          // accumulator columns per tile: 64, 128 or 256
   int stg_warp;                    // staging bytes per epilogue warp
@@ -119,6 +120,50 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
           smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+// ---- cta_group::2 (a CTA pair on one TPC runs M = 256 MMAs; each CTA stages its own 128 rows of A and HALF of B):
+// the peer's TMA loads signal the LEADER's barrier (peer bit of the shared::cluster address cleared), tcgen05.commit
+// multicasts its arrival to both CTAs, and accumulator-drained arrivals go to the leader.  PTX forms as in CUTLASS
+// (cute/arch/copy_sm100_tma.hpp SM100_TMA_2SM_LOAD_*, cutlass/arch/barrier.h umma_arrive_multicast_2x1SM).
+constexpr uint32_t RT_PEER_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & RT_PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & RT_PEER_MASK), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {   // arrives on this barrier in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive on the even CTA's copy of this barrier
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & RT_PEER_MASK) : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
@@ -243,23 +288,30 @@ __device__ __forceinline__ float warp_transpose_sum32(float* x, int lane) {
   return x[0];
 }
 
-template <int EPI, int X3, int NSTEPS>
+template <int EPI, int X3, int NSTEPS, int CG2>
 __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_constant__ RtParams p) {
   asm volatile("griddepcontrol.launch_dependents;");   // PDL: the next kernel may begin its prologue
+  // CG2: launched as clusters of two CTAs (one TPC).  The pair owns 256 rows x BN columns per item: each CTA stages its own
+  // 128 rows of A and its half of the B tile, the leader (cluster rank 0) issues cta_group::2 MMAs with M = 256, each CTA
+  // drains its own 128 accumulator lanes.  Halves the B-operand shared-memory traffic per SM (the 1-CTA bound).
+  const uint32_t cta_rank = CG2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int worker = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nworkers = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t full_bar[RT_MAXSTAGES], empty_bar[RT_MAXSTAGES], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* staging = smem + (size_t)p.stages * p.stage_bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int items = p.tiles_m * p.tiles_n * p.ksplit;
+  const int items = (CG2 ? (p.tiles_m + 1) / 2 : p.tiles_m) * p.tiles_n * p.ksplit;
   unsigned long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 16 : nullptr;
 #define RT_STAMP(slot) do { if (dbg) dbg[slot] = clock64(); } while (0)
   if (threadIdx.x == 0) RT_STAMP(0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], CG2 ? 16 : 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
@@ -268,18 +320,25 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.mapO[0]) : "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CG2) cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / peer TMA completion
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
   if (threadIdx.x == 0) RT_STAMP(1);   // prologue done
   asm volatile("griddepcontrol.wait;" ::: "memory");   // PDL: everything earlier kernels wrote is visible from here on
 
-  const uint32_t a_bytes = (uint32_t)RT_BM * p.BK * 2, b_bytes = (uint32_t)p.BN * p.BK * 2;
+  const uint32_t a_bytes = (uint32_t)RT_BM * p.BK * 2, b_bytes = (uint32_t)(CG2 ? p.BN / 2 : p.BN) * p.BK * 2;
   constexpr int nt = X3 ? 2 : 1;
 
   if (warp == 0 || warp == 10) {
@@ -292,11 +351,12 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
       const uint32_t my_bytes = nt * (isB ? b_bytes : a_bytes);
       const int nchunk = (isB ? p.BN : RT_BM) / 64;
       uint32_t it = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      for (int item = worker; item < items; item += nworkers) {
         const int ks = item % p.ksplit;
         const int tile = item / p.ksplit;
         const int tn = tile % p.tiles_n, tm = tile / p.tiles_n;
-        const int r0 = isB ? tn * p.BN : tm * RT_BM;
+        const int r0 = CG2 ? (isB ? tn * p.BN + (int)cta_rank * (p.BN / 2) : tm * 2 * RT_BM + (int)cta_rank * RT_BM)
+                           : (isB ? tn * p.BN : tm * RT_BM);
         const int kb0 = ks * p.kb_per, kb1 = min(p.nkb, kb0 + p.kb_per);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const bool seg2 = kb >= p.nkb1;
@@ -307,9 +367,13 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
           if (elect_one()) {
             if (it == 0 && !isB) RT_STAMP(2);      // first TMA about to issue
             uint8_t* dst = smem + (size_t)st * p.stage_bytes + (isB ? nt * a_bytes : 0);
-            mbar_expect_tx(&full_bar[st], my_bytes);
+            if (!CG2) mbar_expect_tx(&full_bar[st], my_bytes);
+            else if (leader) mbar_expect_tx(&full_bar[st], 2 * my_bytes);   // own tile + the peer's, both land on this barrier
             const int k0 = (seg2 ? kb - p.nkb1 : kb) * p.BK;
-            if (mn) {   // boxes of 64 rows (contiguous) x BK k [x 2 planes]
+            if (CG2) {   // K-major only (host-checked)
+              if (X3) tma_load_3d_2sm(dst, map, &full_bar[st], k0, r0, 0);
+              else tma_load_2d_2sm(dst, map, &full_bar[st], k0, r0);
+            } else if (mn) {   // boxes of 64 rows (contiguous) x BK k [x 2 planes]
               for (int u = 0; u < nchunk; ++u) {
                 if (X3) tma_load_3d(dst + u * (nt * p.BK * 128), map, &full_bar[st], r0 + 64 * u, k0, 0);
                 else tma_load_2d(dst + u * (p.BK * 128), map, &full_bar[st], r0 + 64 * u, k0);
@@ -327,12 +391,12 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer: the warp walks the loops converged, one elected lane issues
-    {
+    // ===================== MMA issuer: the warp walks the loops converged, one elected lane issues (pair leader only)
+    if (!CG2 || leader) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6) | A=bf16 [7,10) | B=bf16 [10,13) |
       // a_major [15] | b_major [16] | N>>3 [17,23) | M>>4 [24,29)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
-                             ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(RT_BM >> 4) << 24);
+                             ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((CG2 ? 2 * RT_BM : RT_BM) >> 4) << 24);
       // K-major tile: rows of BK*2 bytes (64 B -> SWIZZLE_64B, 128 B -> SWIZZLE_128B), 8-row groups SBO apart; a 16-k
       //   step is +32 bytes inside the swizzled row.
       // MN-major tile: 64-wide chunks (LBO apart), 8-k-row groups 1024 bytes apart (SBO), SWIZZLE_128B; a 16-k step is
@@ -348,7 +412,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
       const uint64_t a_hi_off = p.a_swap ? a_p1 : 0, a_lo_off = p.a_swap ? 0 : a_p1;
       const uint64_t b_hi_off = p.b_swap ? b_p1 : 0, b_lo_off = p.b_swap ? 0 : b_p1;
       uint32_t it = 0, li = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
+      for (int item = worker; item < items; item += nworkers, ++li) {
         const int ks = item % p.ksplit;
         const int kb0 = ks * p.kb_per, kb1 = min(p.nkb, kb0 + p.kb_per);
         const uint32_t ab = li & 1u, aph = (li >> 1) & 1u;
@@ -372,20 +436,30 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
 #pragma unroll
             for (int k = 0; k < NSTEPS; ++k) {
               const uint64_t oa = (uint64_t)k * a_step, ob = (uint64_t)k * b_step;
-              umma_f16(dcol, da_hi + oa, db_hi + ob, idesc, k == 0 ? acc0 : 1u);
-              if (X3) {
-                umma_f16(dcol, da_hi + oa, db_lo + ob, idesc, 1u);
-                umma_f16(dcol, da_lo + oa, db_hi + ob, idesc, 1u);
+              if (CG2) {
+                umma_f16_2sm(dcol, da_hi + oa, db_hi + ob, idesc, k == 0 ? acc0 : 1u);
+                if (X3) {
+                  umma_f16_2sm(dcol, da_hi + oa, db_lo + ob, idesc, 1u);
+                  umma_f16_2sm(dcol, da_lo + oa, db_hi + ob, idesc, 1u);
+                }
+              } else {
+                umma_f16(dcol, da_hi + oa, db_hi + ob, idesc, k == 0 ? acc0 : 1u);
+                if (X3) {
+                  umma_f16(dcol, da_hi + oa, db_lo + ob, idesc, 1u);
+                  umma_f16(dcol, da_lo + oa, db_hi + ob, idesc, 1u);
+                }
               }
             }
-            umma_commit(&empty_bar[st]);     // frees the stage once these MMAs have read it
+            if (CG2) umma_commit_2sm(&empty_bar[st]);   // frees the stage in both CTAs
+            else umma_commit(&empty_bar[st]);           // frees the stage once these MMAs have read it
             if (it == 0) RT_STAMP(12);       // MMAs of k-block 0 issued
             if (it == 7) RT_STAMP(14);       // MMAs of k-block 7 issued
           }
           __syncwarp();
         }
         if (elect_one()) {
-          umma_commit(&tfull_bar[ab]);       // accumulator of this item complete
+          if (CG2) umma_commit_2sm(&tfull_bar[ab]);   // both CTAs' epilogues
+          else umma_commit(&tfull_bar[ab]);           // accumulator of this item complete
           if (li == 0) RT_STAMP(5);          // all MMAs of the first item issued
         }
         __syncwarp();
@@ -398,10 +472,10 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
     uint8_t* stg_p = staging + (size_t)(warp - 2) * p.stg_warp;
     const uint32_t stg0 = smem_u32(stg_p), stg1 = stg0 + 2048u;
     uint32_t li = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
+    for (int item = worker; item < items; item += nworkers, ++li) {
       const int tile = item / p.ksplit;
       const int tn = tile % p.tiles_n, tm = tile / p.tiles_n;
-      const int m0 = tm * RT_BM, n0 = tn * p.BN;
+      const int m0 = CG2 ? tm * 2 * RT_BM + (int)cta_rank * RT_BM : tm * RT_BM, n0 = tn * p.BN;
       const uint32_t ab = li & 1u, aph = (li >> 1) & 1u;
       const int r = m0 + q * 32 + lane;          // global row of this thread
       const bool r_ok = r < p.M;
@@ -427,7 +501,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
         if (c == c_hi - 1 || nc + 32 >= p.N) {   // last read of this accumulator: hand it back to the MMA warp
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[ab]);
+          if (lane == 0) { if (CG2) mbar_arrive_leader(&tempty_bar[ab]); else mbar_arrive(&tempty_bar[ab]); }
           released = true;
         }
         uint32_t w0[32];     // fp32 outputs: 32 words; bf16 outputs: w0[0..15] = hi pairs, w0[16..31] = lo pairs
@@ -660,7 +734,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
       if (!released) {   // this half had no columns inside N: still hand the accumulator back
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[ab]);
+        if (lane == 0) { if (CG2) mbar_arrive_leader(&tempty_bar[ab]); else mbar_arrive(&tempty_bar[ab]); }
       }
       if (EPI == EPI_ATT && r_ok && p.rowout && n0 + c_lo * 32 < p.N) atomicAdd(p.rowout + r, rowacc);
     }
@@ -671,8 +745,10 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (threadIdx.x == 0) RT_STAMP(9);
+  if (CG2) cluster_sync_all();   // no CTA of the pair leaves while the other may still signal its barriers / read its smem
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (CG2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -750,23 +826,46 @@ int encode_operand(CUtensorMap* m, const bf16* hi, const bf16* lo, int* swap, in
 
 bool g_attr_done[8] = {false, false, false, false, false, false, false, false};
 
-template <int EPI, int X3, int NSTEPS>
+template <int EPI, int X3, int NSTEPS, int CG2>
 int launch_rows_v(rau_ctx* ctx, const RtParams& p, int grid, int smem_bytes) {
   static bool attr_done = false;
   if (!attr_done) {
-    RAU_CHECK_CUDA(cudaFuncSetAttribute(rows_gemm_kernel<EPI, X3, NSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RAU_CHECK_CUDA(cudaFuncSetAttribute(rows_gemm_kernel<EPI, X3, NSTEPS, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         RT_SMEM_BUDGET + 1024));
     attr_done = true;
   }
-  RAU_LAUNCH_PDL(ctx->stream, (rows_gemm_kernel<EPI, X3, NSTEPS>), grid, RT_THREADS, smem_bytes, p);
+  if (CG2) {   // clusters of two CTAs (one TPC): the cta_group::2 pair
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(RT_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = rau_pdl_enabled() ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 2;
+    (void)cudaLaunchKernelEx(&cfg, rows_gemm_kernel<EPI, X3, NSTEPS, CG2>, p);
+  } else {
+    RAU_LAUNCH_PDL(ctx->stream, (rows_gemm_kernel<EPI, X3, NSTEPS, CG2>), grid, RT_THREADS, smem_bytes, p);
+  }
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
-// variants: bf16x3 with 32-wide k-blocks (256-column tiles) or 64-wide (narrow tiles); single-pass bf16 with 64-wide
+// variants: bf16x3 with 32-wide k-blocks (256-column tiles) or 64-wide (narrow tiles); single-pass bf16 with 64-wide;
+// the CTA-pair form exists for the big K-major products with fused epilogues
 template <int EPI>
 int launch_rows(rau_ctx* ctx, const RtParams& p, int grid, int smem_bytes) {
-  if (p.x3) return p.BK == 32 ? launch_rows_v<EPI, 1, 2>(ctx, p, grid, smem_bytes) : launch_rows_v<EPI, 1, 4>(ctx, p, grid, smem_bytes);
-  return launch_rows_v<EPI, 0, 4>(ctx, p, grid, smem_bytes);
+  constexpr bool pairable = EPI == EPI_PLAIN || EPI == EPI_TANH || EPI == EPI_ATT || EPI == EPI_DY;
+  if (pairable && p.cg2) {
+    if (p.x3) return launch_rows_v<EPI, 1, 2, pairable ? 1 : 0>(ctx, p, grid, smem_bytes);
+    return launch_rows_v<EPI, 0, 4, pairable ? 1 : 0>(ctx, p, grid, smem_bytes);
+  }
+  if (p.x3) return p.BK == 32 ? launch_rows_v<EPI, 1, 2, 0>(ctx, p, grid, smem_bytes) : launch_rows_v<EPI, 1, 4, 0>(ctx, p, grid, smem_bytes);
+  return launch_rows_v<EPI, 0, 4, 0>(ctx, p, grid, smem_bytes);
 }
 
 __global__ void pack_hilo_kernel(const float* __restrict__ in, int64_t n4, bf16* __restrict__ hi, bf16* __restrict__ lo) {
@@ -1047,6 +1146,12 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   p.BK = (p.x3 && BN == 256) ? 32 : 64;
   p.nkb = (g.K + p.BK - 1) / p.BK;
   const bool seg2 = g.K2 > 0;
+  {   // CTA pairs (cta_group::2) for the big K-major products: RAU_CG2=0 keeps everything on single CTAs
+    static int cg2_on = -1;
+    if (cg2_on < 0) { const char* e = getenv("RAU_CG2"); cg2_on = e ? atoi(e) : 1; }
+    p.cg2 = (cg2_on && (g.epi == EPI_PLAIN || g.epi == EPI_TANH || g.epi == EPI_ATT || g.epi == EPI_DY) && !g.A.mn && !g.B.mn &&
+             BN == 256 && !seg2 && p.tiles_m >= 8 && sm_avail >= 2) ? 1 : 0;
+  }
   if (seg2) {
     RAU_REQUIRE(g.A2.hi && g.B2.hi && g.A2.mn == g.A.mn && g.B2.mn == g.B.mn && (g.A2.lo != nullptr) == (g.A.lo != nullptr) &&
                     (g.B2.lo != nullptr) == (g.B.lo != nullptr) && g.A2.ld % 8 == 0 && g.B2.ld % 8 == 0,
@@ -1059,10 +1164,10 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   // shared memory: 8 staging buffers for the epilogue warps + as many operand stages as fit (latency-bound skinny
   // products want many small stages in flight, the big ones four 48 KB stages)
   p.stg_warp = (g.epi == EPI_LINEAR && g.out_hi) ? 8192 : RT_STG_WARP;
-  p.stage_bytes = (p.x3 ? 2 : 1) * (RT_BM + BN) * p.BK * 2;
+  p.stage_bytes = (p.x3 ? 2 : 1) * (RT_BM + (p.cg2 ? BN / 2 : BN)) * p.BK * 2;
   p.stages = (RT_SMEM_BUDGET - 8 * p.stg_warp) / p.stage_bytes;
   if (p.stages > RT_MAXSTAGES) p.stages = RT_MAXSTAGES;
-  const int tiles = p.tiles_m * p.tiles_n;
+  const int tiles = (p.cg2 ? (p.tiles_m + 1) / 2 : p.tiles_m) * p.tiles_n;   // work items before any K split
   p.ksplit = 1;
   if (g.epi == EPI_RED && tiles < sm_avail) {
     int want = sm_avail / tiles;
@@ -1073,7 +1178,7 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   p.kb_per = (p.nkb + p.ksplit - 1) / p.ksplit;
   p.ksplit = (p.nkb + p.kb_per - 1) / p.kb_per;
   RAU_TRY(encode_operand(&p.mapA[0], g.A.hi, g.A.lo, &p.a_swap, g.A.mn, g.M, g.K, g.A.ld, p.BK, RT_BM));
-  RAU_TRY(encode_operand(&p.mapB[0], g.B.hi, g.B.lo, &p.b_swap, g.B.mn, g.N, g.K, g.B.ld, p.BK, BN));
+  RAU_TRY(encode_operand(&p.mapB[0], g.B.hi, g.B.lo, &p.b_swap, g.B.mn, g.N, g.K, g.B.ld, p.BK, p.cg2 ? BN / 2 : BN));
   if (seg2) {
     int sa2 = 0, sb2 = 0;
     RAU_TRY(encode_operand(&p.mapA2[0], g.A2.hi, g.A2.lo, &sa2, g.A2.mn, g.M, g.K2, g.A2.ld, p.BK, RT_BM));
@@ -1137,7 +1242,8 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   p.alpha = g.alpha;
   p.fast_tanh = p.x3 ? 0 : 1;   // single-pass bf16: the result is rounded to bf16 anyway, MUFU.TANH (2^-11) is below that
   const int items = tiles * p.ksplit;
-  const int grid = items < sm_avail ? items : sm_avail;
+  int grid = items < sm_avail ? items : sm_avail;
+  if (p.cg2) grid = 2 * (items < sm_avail / 2 ? items : sm_avail / 2);   // whole CTA pairs
   {
     static int trace = -1;
     if (trace < 0) { const char* e = getenv("RAU_ROWS_TRACE"); trace = e ? atoi(e) : 0; }
