@@ -1385,7 +1385,8 @@ int pack2d(rau_ctx* ctx, const float* src, int64_t ld, int rows, int cols, bool 
     auto it = ctx->tc_epoch.find(name);
     cached = it != ctx->tc_epoch.end() && it->second == ctx->epoch;
   } else {
-    snprintf(name, sizeof(name), "rp.%s", slot);
+    // scratch slots are per stream: work enqueued on the side stream must not share them with the chain
+    snprintf(name, sizeof(name), ctx->rows_cta_cap > 0 ? "rp.side.%s" : "rp.%s", slot);
   }
   const size_t half = ((size_t)rows * ldo * sizeof(bf16) + 1023) / 1024 * 1024;
   void* buf = nullptr;

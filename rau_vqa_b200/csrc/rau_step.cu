@@ -527,7 +527,24 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     st.gwsp = st_gwsp;
     st.dscore_pk = pk_dscore; st.m_pk = pk_m; st.du_pk = pk_du; st.hout_pk = slice(pk_h, B); st.dG_pk = pk_dG; st.j_pk = pk_j;
     st.hin_pk = pk_h; st.p_pk = pk_p; st.ds_pk = pk_ds; st.qf_pk = pk_qf; st.dpre_pk = pk_dpre; st.qd_pk = pk_qd;
-    RAU_TRY(hop_wgrads(ctx, cfg, nHop * B, G, st));
+    if (ov_bwd) {
+      // the deferred nn.Linear weight gradients feed nothing in the encoder backward: side stream, behind the last hop's
+      // heavy products, while the chain walks the encoder
+      cudaEvent_t ev = rau_side_event(ctx);
+      RAU_REQUIRE(ev != nullptr, "cudaEventCreate failed");
+      RAU_CHECK_CUDA(cudaEventRecord(ev, ctx->stream));
+      RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->side, ev, 0));
+      cudaStream_t chain = ctx->stream;
+      ctx->stream = ctx->side;
+      ctx->rows_cta_cap = ctx->side_ctas;
+      const int rc = hop_wgrads(ctx, cfg, nHop * B, G, st);
+      ctx->stream = chain;
+      ctx->rows_cta_cap = 0;
+      RAU_TRY(rc);
+      side_used = true;
+    } else {
+      RAU_TRY(hop_wgrads(ctx, cfg, nHop * B, G, st));
+    }
   }
   rau_phase_mark(ctx, "unit weight gradients");
   RAU_TRY(encoder_backward(ctx, cfg, bt, params[1], grads[0], grads[1], train, &en, dq));
