@@ -252,23 +252,43 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
   if (h_out && h_out != sv.hout)
     RAU_CHECK_CUDA(cudaMemcpyAsync(h_out, sv.hout, sizeof(float) * B * H, cudaMemcpyDeviceToDevice, ctx->stream));
   // m = drop(j + Wo h' + bo) ; score = Ws m + bs ; do_pred = sigmoid(wd.m + bd)   (F:276-281)
+  // Only the loss reads these: in the training step the head leaves the chain for the side stream right here.
+  cudaStream_t chain = ctx->stream;
+  const bool head_side = as && as->head_side && ctx->side != nullptr;
+  if (head_side) {
+    cudaEvent_t ev = rau_side_event(ctx);
+    RAU_REQUIRE(ev != nullptr, "cudaEventCreate failed");
+    RAU_CHECK_CUDA(cudaEventRecord(ev, chain));
+    RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->side, ev, 0));
+    ctx->stream = ctx->side;
+    ctx->rows_cta_cap = ctx->side_ctas;
+  }
+  int head_rc = RAU_OK;
+  do {
   {
     SimtGemm g = lin_fwd(B, M, H, sv.hout, H, P.Wo, prem, M);
     g.bias_n = P.bo; g.addend = sv.j; g.sdm = M; g.sdn = 1;
     g.Ar_hi = sv.hout_pk.hi; g.Ar_lo = sv.hout_pk.lo; g.Ar_ld = sv.hout_pk.ld;   // (written by the cell epilogue / the pack above)
-    RAU_TRY(rau_contract(ctx, g));
+    if ((head_rc = rau_contract(ctx, g)) != RAU_OK) break;
   }
-  RAU_TRY(k_dropout(ctx, prem, B, M, M, mb, drop_scale(cfg->p_m), sv.m, M, sv.m_pk.hi, (int)sv.m_pk.ld, M, x3 ? sv.m_pk.lo : nullptr));
+  if ((head_rc = k_dropout(ctx, prem, B, M, M, mb, drop_scale(cfg->p_m), sv.m, M, sv.m_pk.hi, (int)sv.m_pk.ld, M,
+                           x3 ? sv.m_pk.lo : nullptr)) != RAU_OK) break;
   {
     SimtGemm g = lin_fwd(B, N, M, sv.m, M, P.Ws, score, N);
     g.bias_n = P.bso;
     g.Ar_hi = sv.m_pk.hi; g.Ar_lo = sv.m_pk.lo; g.Ar_ld = sv.m_pk.ld;
-    RAU_TRY(rau_contract(ctx, g));
+    if ((head_rc = rau_contract(ctx, g)) != RAU_OK) break;
   }
-  RAU_TRY(k_rowdot_sigmoid(ctx, sv.m, B, M, P.wd, P.bd, sv.dop));
-  if (do_pred && do_pred != sv.dop)
-    RAU_CHECK_CUDA(cudaMemcpyAsync(do_pred, sv.dop, sizeof(float) * B, cudaMemcpyDeviceToDevice, ctx->stream));
-  return RAU_OK;
+  if ((head_rc = k_rowdot_sigmoid(ctx, sv.m, B, M, P.wd, P.bd, sv.dop)) != RAU_OK) break;
+  if (do_pred && do_pred != sv.dop &&
+      cudaMemcpyAsync(do_pred, sv.dop, sizeof(float) * B, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) {
+    rau_set_error("cudaMemcpyAsync(do_pred) failed");
+    head_rc = RAU_ECUDA;
+  }
+  } while (0);
+  ctx->stream = chain;
+  ctx->rows_cta_cap = 0;
+  return head_rc;
 }
 
 int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const float*>& P, const MultT<float*>& G,

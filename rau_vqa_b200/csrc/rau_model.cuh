@@ -68,6 +68,7 @@ bool hop_rows_path(const rau_ctx* ctx, const rau_config* cfg);
 struct HopAsync {
   cudaEvent_t pre_done = nullptr;    // forward: I of this hop is ready (recorded on the side stream); NULL = compute inline
   int bwd_side = 0;                  // backward: put dY / gWa / gWi on the side stream
+  int head_side = 0;                 // forward: the answer head (Wo, dropout, score, do_pred) does not feed the next hop: side stream
   int hop = 0;                       // selects the per-hop dZ buffer when bwd_side
 };
 int hop_forward_pre(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const float*>& P, const float* X, int train,

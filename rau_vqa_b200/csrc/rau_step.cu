@@ -350,10 +350,11 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   // cross-stream overlap (rows path): RAU_OVERLAP bit 0 = heavy backward products on the side stream, bit 1 = the
   // state-independent i_embed products of all hops on the side stream, next to the encoder and the chain
   static int overlap_mode = -1;
-  if (overlap_mode < 0) { const char* e = getenv("RAU_OVERLAP"); overlap_mode = e ? atoi(e) : 3; }
+  if (overlap_mode < 0) { const char* e = getenv("RAU_OVERLAP"); overlap_mode = e ? atoi(e) : 7; }
   const bool rows_hops = hop_rows_path(ctx, cfg) && ctx->side != nullptr;
   const bool ov_bwd = rows_hops && (overlap_mode & 1);
   const bool ov_fwd = rows_hops && (overlap_mode & 2);
+  const bool ov_head = rows_hops && (overlap_mode & 4);   // bit 2: the answer heads + criteria of the forward unroll
   if (ctx->side_ctas == 0) {
     const char* e = getenv("RAU_SIDE_CTAS");
     ctx->side_ctas = e ? atoi(e) : (ctx->sm_count * 4) / 7;   // 84 of 148 SMs measured best on Ours_Full (profiles/README.md)
@@ -434,6 +435,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     hop_saved_layout(cfg, B, sv_base + sv_bytes * hp, &sv[hp]);
     as[hp].hop = hp;
     as[hp].bwd_side = ov_bwd ? 1 : 0;
+    as[hp].head_side = ov_head ? 1 : 0;
     const size_t r0 = (size_t)hp * B;
     sv[hp].qd_pk = slice(pk_qd, r0); sv[hp].qf_pk = slice(pk_qf, r0); sv[hp].p_pk = slice(pk_p, r0); sv[hp].j_pk = slice(pk_j, r0);
     sv[hp].hin_pk = slice(pk_h, r0); sv[hp].hout_pk = slice(pk_h, r0 + B); sv[hp].m_pk = slice(pk_m, r0);
@@ -490,9 +492,19 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     // criterion forward + backward + argmax in one pass (F:505, F:535, F:585-589)
     const float hm = hop_mask ? hop_mask[hp] : 1.0f;
     const PK dsc = slice(pk_dscore, (size_t)hp * B);
-    RAU_TRY(k_softmax_ce(ctx, B, N, scores + (size_t)hp * B * N, bt->labels, 1.0f / Bg, hm / Bg, loss + hp,
-                         dscore + (size_t)hp * B * N, dsc.hi, N, ans + (size_t)hp * B,
-                         ctx->precision == RAU_PREC_BF16X3 ? dsc.lo : nullptr));
+    cudaStream_t chain = ctx->stream;
+    if (ov_head) { ctx->stream = ctx->side; side_used = true; }   // behind this hop's head on the side stream
+    const int rc_ce = k_softmax_ce(ctx, B, N, scores + (size_t)hp * B * N, bt->labels, 1.0f / Bg, hm / Bg, loss + hp,
+                                   dscore + (size_t)hp * B * N, dsc.hi, N, ans + (size_t)hp * B,
+                                   ctx->precision == RAU_PREC_BF16X3 ? dsc.lo : nullptr);
+    ctx->stream = chain;
+    RAU_TRY(rc_ce);
+  }
+  if (ov_head) {   // scores, do_pred, losses and dscore of every hop are complete before the merge and the backward unroll
+    cudaEvent_t ev = rau_side_event(ctx);
+    RAU_REQUIRE(ev != nullptr, "cudaEventCreate failed");
+    RAU_CHECK_CUDA(cudaEventRecord(ev, ctx->side));
+    RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, ev, 0));
   }
   rau_phase_mark(ctx, "answering units forward");
   // logging-only losses on the averaged / selected predictions and the do_pred BCE (F:539-574)
