@@ -217,6 +217,53 @@ __global__ void dropout_pack_kernel(const float* __restrict__ x, int64_t rows, i
   }
 }
 
+// The same input dropped out once per hop with that hop's keep bits (hop h's bits start bits_stride words after hop
+// h-1's): y[h][i] = x[i] * keep_h(i) * scale, fp32 + packed (hi, lo).  One launch for the q_embed inputs of all hops.
+__global__ void dropout_hops_kernel(const float* __restrict__ x, int64_t n, int nHop, const uint32_t* __restrict__ bits,
+                                    int64_t bits_stride, float scale, float* __restrict__ y, bf16* __restrict__ y_hi,
+                                    bf16* __restrict__ y_lo) {
+  RAU_PDL_ENTRY();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float xv = x[i];
+    for (int h = 0; h < nHop; ++h) {
+      const float v = xv * keep_scale(bits ? bits + h * bits_stride : nullptr, i, scale);
+      y[h * n + i] = v;
+      if (y_hi) {
+        const bf16 hb = __float2bfloat16(v);
+        y_hi[h * n + i] = hb;
+        if (y_lo) y_lo[h * n + i] = __float2bfloat16(v - __bfloat162float(hb));
+      }
+    }
+  }
+}
+// In-place dropout backward over a [nHop][n] stack with per-hop keep bits, fp32 + packed twin
+__global__ void dropout_bwd_hops_kernel(float* __restrict__ y, int64_t n, int nHop, const uint32_t* __restrict__ bits,
+                                        int64_t bits_stride, float scale, bf16* __restrict__ y_hi, bf16* __restrict__ y_lo) {
+  RAU_PDL_ENTRY();
+  const int64_t total = n * nHop;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int h = (int)(idx / n);
+    const int64_t i = idx - h * n;
+    const float v = y[idx] * keep_scale(bits ? bits + h * bits_stride : nullptr, i, scale);
+    y[idx] = v;
+    if (y_hi) {
+      const bf16 hb = __float2bfloat16(v);
+      y_hi[idx] = hb;
+      if (y_lo) y_lo[idx] = __float2bfloat16(v - __bfloat162float(hb));
+    }
+  }
+}
+// out[i] = sum_h dx[h][i] * keep_h(i) * scale: the gradient of the shared input of the per-hop dropouts
+__global__ void dropout_bwd_sum_hops_kernel(const float* __restrict__ dx, int64_t n, int nHop, const uint32_t* __restrict__ bits,
+                                            int64_t bits_stride, float scale, float* __restrict__ out) {
+  RAU_PDL_ENTRY();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float acc = 0.0f;
+    for (int h = 0; h < nHop; ++h) acc += dx[h * n + i] * keep_scale(bits ? bits + h * bits_stride : nullptr, i, scale);
+    out[i] = acc;
+  }
+}
+
 __global__ void dropout_bwd_acc_kernel(const float* __restrict__ dx, int64_t n, const uint32_t* __restrict__ bits,
                                        float scale, float* __restrict__ y, int accumulate, bf16* __restrict__ y_hi,
                                        bf16* __restrict__ y_lo) {
@@ -435,6 +482,24 @@ int k_dropout_pack(rau_ctx* ctx, const float* x, int64_t rows, int cols, const u
 int k_dropout_bwd_acc(rau_ctx* ctx, const float* dx, int64_t n, const uint32_t* bits, float scale, float* y, int accumulate,
                       bf16* y_hi, bf16* y_lo) {
   RAU_LAUNCH_PDL(ctx->stream, (dropout_bwd_acc_kernel), grid_for(n, 4), TPB, 0, dx, n, bits, scale, y, accumulate, y_hi, y_lo);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+int k_dropout_hops(rau_ctx* ctx, const float* x, int64_t n, int nHop, const uint32_t* bits, int64_t bits_stride, float scale,
+                   float* y, bf16* y_hi, bf16* y_lo) {
+  RAU_LAUNCH_PDL(ctx->stream, (dropout_hops_kernel), grid_for(n, 2), TPB, 0, x, n, nHop, bits, bits_stride, scale, y, y_hi, y_lo);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+int k_dropout_bwd_hops(rau_ctx* ctx, float* y, int64_t n, int nHop, const uint32_t* bits, int64_t bits_stride, float scale,
+                       bf16* y_hi, bf16* y_lo) {
+  RAU_LAUNCH_PDL(ctx->stream, (dropout_bwd_hops_kernel), grid_for(n * nHop, 4), TPB, 0, y, n, nHop, bits, bits_stride, scale, y_hi, y_lo);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+int k_dropout_bwd_sum_hops(rau_ctx* ctx, const float* dx, int64_t n, int nHop, const uint32_t* bits, int64_t bits_stride,
+                           float scale, float* out) {
+  RAU_LAUNCH_PDL(ctx->stream, (dropout_bwd_sum_hops_kernel), grid_for(n, 2), TPB, 0, dx, n, nHop, bits, bits_stride, scale, out);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }

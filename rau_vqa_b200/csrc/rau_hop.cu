@@ -121,8 +121,14 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
   // q_embed (F:231-236): qf = tanh(Wq drop(q) + bq + Wh h + bh)
   // (packed twins, training step only: every producer below also writes the bf16 (hi, lo) form its consumers' tcgen05
   // products read, so the chain carries no pack launches)
-  RAU_TRY(k_dropout(ctx, q, B, Q, Q, qb, drop_scale(cfg->p_q), sv.qd, Q, sv.qd_pk.hi, (int)sv.qd_pk.ld, Q, x3 ? sv.qd_pk.lo : nullptr));
-  {
+  if (sv.qpre) {   // Wq drop(q) + bq was hoisted out of the unroll: only the recurrent half is left
+    SimtGemm g = lin_fwd(B, M, H, h, H, P.Wh, sv.qf, M);
+    g.bias_n = P.bh; g.addend = sv.qpre; g.sdm = M; g.sdn = 1; g.act = 1;
+    g.Ar_hi = sv.hin_pk.hi; g.Ar_lo = sv.hin_pk.lo; g.Ar_ld = sv.hin_pk.ld;
+    if (sv.qf_pk.hi && sv.qf_pk.ld == M) { g.C_hi = sv.qf_pk.hi; g.C_lo = sv.qf_pk.lo; }
+    RAU_TRY(rau_contract(ctx, g));
+  } else {
+    RAU_TRY(k_dropout(ctx, q, B, Q, Q, qb, drop_scale(cfg->p_q), sv.qd, Q, sv.qd_pk.hi, (int)sv.qd_pk.ld, Q, x3 ? sv.qd_pk.lo : nullptr));
     SimtGemm g = lin_fwd(B, M, Q, sv.qd, Q, P.Wq, sv.qf, M);
     lin_seg2(g, H, h, H, P.Wh);
     g.bias_n = P.bq; g.bias_n2 = P.bh; g.act = 1;
@@ -349,6 +355,8 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   const PK& ds_pk = deferred ? deferred->ds_pk : no_pk;
   const PK& dpre_pk = deferred ? deferred->dpre_pk : no_pk;
 
+  const bool hoisted = deferred != nullptr && deferred->dh2h != nullptr;   // head backward + dq formed outside the unroll
+  if (!hoisted) {
   // heads: dm = Ws^T dscore (+ do_pred head) ; gWs += dscore (x) m
   if (dscore) {
     SimtGemm gd = lin_dgrad(B, N, M, dscore, N, P.Ws, du, M);
@@ -375,8 +383,13 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
     RAU_TRY(rau_contract(ctx, lin_wgrad(B, M, H, du, M, sv.hout, H, G.Wo, 1.0f)));
     RAU_TRY(k_colsum(ctx, du, B, M, M, G.bo, 1));
   }
+  }
   // attlstm backward
   const bool dG_twin = dG_pk.hi != nullptr && dG_pk.ld == 4 * H;
+  if (hoisted)   // dh' = dh_next + (Wo^T du of this hop, precomputed)
+    RAU_TRY(k_lstm_bwd(ctx, B, H, RAU_GATES_IGFO, dc_out, H, dh_out, H, deferred->dh2h, H, nullptr, 0, nullptr, nullptr, 0, c, H,
+                       sv.lsav, dG, dG_twin ? dG_pk.hi : nullptr, dc, H, (dG_twin && x3) ? dG_pk.lo : nullptr));
+  else
   RAU_TRY(k_lstm_bwd(ctx, B, H, RAU_GATES_IGFO, dc_out, H, dh2, H, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, c, H,
                      sv.lsav, dG, dG_twin ? dG_pk.hi : nullptr, dc, H, (dG_twin && x3) ? dG_pk.lo : nullptr));
   {
@@ -557,12 +570,12 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   // q_embed backward
   const bool dpre_twin = dpre_pk.hi != nullptr && dpre_pk.ld == M;
   RAU_TRY(k_tanh_bwd(ctx, dqf, sv.qf, (int64_t)B * M, dpre, dpre_twin ? dpre_pk.hi : nullptr, (dpre_twin && x3) ? dpre_pk.lo : nullptr));
-  {
+  if (!hoisted) {
     SimtGemm g = lin_dgrad(B, M, Q, dpre, M, P.Wq, dqt, Q);
     if (dpre_twin) { g.Ar_hi = dpre_pk.hi; g.Ar_lo = dpre_pk.lo; g.Ar_ld = M; }
     RAU_TRY(rau_contract(ctx, g));
+    RAU_TRY(k_dropout_bwd_acc(ctx, dqt, (int64_t)B * Q, qb, drop_scale(cfg->p_q), dq, dq_accumulate));
   }
-  RAU_TRY(k_dropout_bwd_acc(ctx, dqt, (int64_t)B * Q, qb, drop_scale(cfg->p_q), dq, dq_accumulate));
   {
     SimtGemm g = lin_dgrad(B, M, H, dpre, M, P.Wh, dh, H);
     g.accumulate = 1;

@@ -39,6 +39,13 @@ int k_dropout_pack(rau_ctx* ctx, const float* x, int64_t rows, int cols, const u
 // y (+)= x*keep*scale  (used for dq accumulation over hops and dX)
 int k_dropout_bwd_acc(rau_ctx* ctx, const float* dx, int64_t n, const uint32_t* bits, float scale, float* y, int accumulate,
                       bf16* y_hi = nullptr, bf16* y_lo = nullptr);
+// batched over the hops of the unroll (hop h's keep bits start bits_stride words after hop h-1's; bits == NULL = keep all)
+int k_dropout_hops(rau_ctx* ctx, const float* x, int64_t n, int nHop, const uint32_t* bits, int64_t bits_stride, float scale,
+                   float* y, bf16* y_hi, bf16* y_lo);
+int k_dropout_bwd_hops(rau_ctx* ctx, float* y, int64_t n, int nHop, const uint32_t* bits, int64_t bits_stride, float scale,
+                       bf16* y_hi, bf16* y_lo);
+int k_dropout_bwd_sum_hops(rau_ctx* ctx, const float* dx, int64_t n, int nHop, const uint32_t* bits, int64_t bits_stride,
+                           float scale, float* out);
 int k_tanh_bwd(rau_ctx* ctx, const float* dy, const float* y, int64_t n, float* dx_f, bf16* dx_b, bf16* dx_lo = nullptr);
 int k_add(rau_ctx* ctx, const float* a, const float* b, int64_t n, float* y);              // y = a + b
 int k_axpy(rau_ctx* ctx, float alpha, const float* x, int64_t n, float* y);                // y += alpha x

@@ -59,6 +59,9 @@ struct HopSaved {
   uint64_t x_stream = 0;
   // training step: packed twins of the small activations (all NULL through the module-level API, which packs on demand)
   PK qd_pk, qf_pk, p_pk, j_pk, hin_pk, hout_pk, m_pk;
+  // training step: Wq drop_h(q) + bq of this hop, computed for all hops in one product before the unroll (q is the same
+  // encoder state for every hop); hop_forward then skips the q dropout and the Wq segment
+  const float* qpre = nullptr;
 };
 bool hop_rows_path(const rau_ctx* ctx, const rau_config* cfg);
 
@@ -83,6 +86,10 @@ size_t hop_saved_layout(const rau_config* cfg, int B, void* base, HopSaved* sv);
 struct HopGrads {
   float *du, *dG, *dj, *ds, *dqa, *dpre, *gwsp;
   PK dscore_pk, du_pk, dG_pk, ds_pk, dpre_pk;   // packed twins written by the producing kernels (may be NULL)
+  // training step: the answer head's backward depends on forward results only, so du = drop'(Ws^T dscore) and
+  // dh2h = Wo^T du are computed for all hops in two products before the backward unroll; likewise dq is formed once
+  // after it from the stacked dpre.  Non-NULL dh2h switches hop_backward to that form.
+  const float* dh2h = nullptr;
 };
 struct HopStacks {   // every member is [nHop][B][dim]
   const float *dscore, *m, *du, *hout, *dG, *j, *h_in, *dj, *p, *ds, *dqa, *qf, *dpre, *qd, *gwsp;

@@ -446,6 +446,11 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     sv[hp].hout = h_all + (size_t)(hp + 1) * B * H;
     sv[hp].dop = dop + (size_t)hp * B;
     sv[hp].m = st_m + (size_t)hp * B * M_;
+    RAU_TRY(rau_prepare_mask(ctx, sv[hp].qbits, (int64_t)B * Q, cfg->p_q, train,
+                             masks && masks->q ? masks->q + (size_t)hp * B * Q : nullptr, stream_of(step_t, SK_Q, hp, rank)));
+    RAU_TRY(rau_prepare_mask(ctx, sv[hp].mbits, (int64_t)B * cfg->M, cfg->p_m, train,
+                             masks && masks->m ? masks->m + (size_t)hp * B * cfg->M : nullptr,
+                             stream_of(step_t, SK_M, hp, rank)));
     if (hop_rows_path(ctx, cfg) && !(masks && masks->x)) {   // drawn inline by the rows pack kernel
       sv[hp].x_philox = 1;
       sv[hp].x_stream = stream_of(step_t, SK_X, hp, rank);
@@ -480,12 +485,21 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   }
   RAU_TRY(encoder_forward(ctx, cfg, bt, params[0], params[1], train, masks, step_t, &en));
   rau_phase_mark(ctx, "encoder forward");
+  // Everything of the unroll that depends on the encoder state only is hoisted out of the per-hop chains: the q dropout
+  // of every hop (one launch) and Wq drop_h(q) + bq of every hop (one [nHop*B, Q] x [Q, M] product).
+  ARENA(st_qpre, float, "stack.qpre", (size_t)nHop * B * M_);
+  const int64_t bits_stride = (int64_t)(sv_bytes / 4);   // keep bits of consecutive hops are sv_bytes apart
+  {
+    const bool dq_ = train && cfg->p_q > 0;
+    RAU_TRY(k_dropout_hops(ctx, en.rnn_out, (int64_t)B * Q, nHop, dq_ ? sv[0].qbits : nullptr, bits_stride, drop_scale(cfg->p_q),
+                           st_qd, pk_qd.hi, ctx->precision == RAU_PREC_BF16X3 ? pk_qd.lo : nullptr));
+    SimtGemm g = lin_fwd(nHop * B, M_, Q, st_qd, Q, P.Wq, st_qpre, M_);
+    g.bias_n = P.bq;
+    g.Ar_hi = pk_qd.hi; g.Ar_lo = pk_qd.lo; g.Ar_ld = pk_qd.ld;
+    RAU_TRY(rau_contract(ctx, g));
+    for (int hp = 0; hp < nHop; ++hp) sv[hp].qpre = st_qpre + (size_t)hp * B * M_;
+  }
   for (int hp = 0; hp < nHop; ++hp) {
-    RAU_TRY(rau_prepare_mask(ctx, sv[hp].qbits, (int64_t)B * Q, cfg->p_q, train,
-                             masks && masks->q ? masks->q + (size_t)hp * B * Q : nullptr, stream_of(step_t, SK_Q, hp, rank)));
-    RAU_TRY(rau_prepare_mask(ctx, sv[hp].mbits, (int64_t)B * cfg->M, cfg->p_m, train,
-                             masks && masks->m ? masks->m + (size_t)hp * B * cfg->M : nullptr,
-                             stream_of(step_t, SK_M, hp, rank)));
     RAU_TRY(hop_forward(ctx, cfg, B, P, en.rnn_out, bt->feats, c_all + (size_t)hp * B * H, h_all + (size_t)hp * B * H, train,
                         sv[hp], scores + (size_t)hp * B * N, dop + (size_t)hp * B, att + (size_t)hp * B * S,
                         c_all + (size_t)(hp + 1) * B * H, h_all + (size_t)(hp + 1) * B * H, &as[hp]));
@@ -516,6 +530,21 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   ARENA(dcs, float, "step.dc", (size_t)2 * B * H);
   ARENA(dhs, float, "step.dh", (size_t)2 * B * H);
   ARENA(dq, float, "step.dq", (size_t)B * Q);
+  // The answer head's backward needs forward results only: du = drop'(dscore Ws) and Wo^T du of every hop in two products
+  // over nHop*B rows before the unroll (dscore already carries the hop mask and 1/B_global)
+  ARENA(st_dh2h, float, "stack.dh2h", (size_t)nHop * B * H);
+  ARENA(st_dqt, float, "stack.dqt", (size_t)nHop * B * Q);
+  {
+    SimtGemm g = lin_dgrad(nHop * B, N, M_, dscore, N, P.Ws, st_du, M_);
+    g.Ar_hi = pk_dscore.hi; g.Ar_lo = pk_dscore.lo; g.Ar_ld = pk_dscore.ld;
+    RAU_TRY(rau_contract(ctx, g));
+    const bool dm_ = train && cfg->p_m > 0;
+    RAU_TRY(k_dropout_bwd_hops(ctx, st_du, (int64_t)B * M_, nHop, dm_ ? sv[0].mbits : nullptr, bits_stride, drop_scale(cfg->p_m),
+                               pk_du.hi, ctx->precision == RAU_PREC_BF16X3 ? pk_du.lo : nullptr));
+    SimtGemm g2 = lin_dgrad(nHop * B, M_, H, st_du, M_, P.Wo, st_dh2h, H);
+    g2.Ar_hi = pk_du.hi; g2.Ar_lo = pk_du.lo; g2.Ar_ld = pk_du.ld;
+    RAU_TRY(rau_contract(ctx, g2));
+  }
   for (int hp = nHop - 1; hp >= 0; --hp) {
     const bool last = hp == nHop - 1;
     const float* dc_in = last ? nullptr : dcs + (size_t)((hp + 1) & 1) * B * H;
@@ -526,10 +555,18 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     hg.gwsp = st_gwsp + (size_t)hp * B * A_;
     hg.dscore_pk = slice(pk_dscore, (size_t)hp * B); hg.du_pk = slice(pk_du, (size_t)hp * B); hg.dG_pk = slice(pk_dG, (size_t)hp * B);
     hg.ds_pk = slice(pk_ds, (size_t)hp * B); hg.dpre_pk = slice(pk_dpre, (size_t)hp * B);
+    hg.dh2h = st_dh2h + (size_t)hp * B * H;
     RAU_TRY(hop_backward(ctx, cfg, B, P, G, bt->feats, c_all + (size_t)hp * B * H, h_all + (size_t)hp * B * H, train, sv[hp],
                          dscore + (size_t)hp * B * N, nullptr, nullptr, dc_in, dh_in, dq, last ? 0 : 1, nullptr,
                          dcs + (size_t)(hp & 1) * B * H, dhs + (size_t)(hp & 1) * B * H, &hg, &as[hp]));
     if (ov_bwd) side_used = true;
+  }
+  {   // dq = sum_h drop_h'(dpre_h Wq): one product over the stacked dpre, one masked sum over the hops
+    SimtGemm g = lin_dgrad(nHop * B, M_, Q, st_dpre, M_, P.Wq, st_dqt, Q);
+    g.Ar_hi = pk_dpre.hi; g.Ar_lo = pk_dpre.lo; g.Ar_ld = pk_dpre.ld;
+    RAU_TRY(rau_contract(ctx, g));
+    const bool dq_ = train && cfg->p_q > 0;
+    RAU_TRY(k_dropout_bwd_sum_hops(ctx, st_dqt, (int64_t)B * Q, nHop, dq_ ? sv[0].qbits : nullptr, bits_stride, drop_scale(cfg->p_q), dq));
   }
   rau_phase_mark(ctx, "answering units backward");
   {
