@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
       const bool isB = warp == 10;
       const int mn = isB ? p.b_mn : p.a_mn;
       const uint32_t my_bytes = nt * (isB ? b_bytes : a_bytes);
-      const int nchunk = (isB ? p.BN : RT_BM) / 64;
+      const int nchunk = (isB ? (CG2 ? p.BN / 2 : p.BN) : RT_BM) / 64;
       uint32_t it = 0;
       for (int item = worker; item < items; item += nworkers) {
         const int ks = item % p.ksplit;
@@ -370,7 +370,12 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
             if (!CG2) mbar_expect_tx(&full_bar[st], my_bytes);
             else if (leader) mbar_expect_tx(&full_bar[st], 2 * my_bytes);   // own tile + the peer's, both land on this barrier
             const int k0 = (seg2 ? kb - p.nkb1 : kb) * p.BK;
-            if (CG2) {   // K-major only (host-checked)
+            if (CG2 && mn) {   // boxes of 64 rows (contiguous) x BK k [x 2 planes], completing on the leader's barrier
+              for (int u = 0; u < nchunk; ++u) {
+                if (X3) tma_load_3d_2sm(dst + u * (nt * p.BK * 128), map, &full_bar[st], r0 + 64 * u, k0, 0);
+                else tma_load_2d_2sm(dst + u * (p.BK * 128), map, &full_bar[st], r0 + 64 * u, k0);
+              }
+            } else if (CG2) {
               if (X3) tma_load_3d_2sm(dst, map, &full_bar[st], k0, r0, 0);
               else tma_load_2d_2sm(dst, map, &full_bar[st], k0, r0);
             } else if (mn) {   // boxes of 64 rows (contiguous) x BK k [x 2 planes]
@@ -859,7 +864,7 @@ int launch_rows_v(rau_ctx* ctx, const RtParams& p, int grid, int smem_bytes) {
 // the CTA-pair form exists for the big K-major products with fused epilogues
 template <int EPI>
 int launch_rows(rau_ctx* ctx, const RtParams& p, int grid, int smem_bytes) {
-  constexpr bool pairable = EPI == EPI_PLAIN || EPI == EPI_TANH || EPI == EPI_ATT || EPI == EPI_DY;
+  constexpr bool pairable = EPI == EPI_PLAIN || EPI == EPI_TANH || EPI == EPI_ATT || EPI == EPI_DY || EPI == EPI_RED;
   if (pairable && p.cg2) {
     if (p.x3) return launch_rows_v<EPI, 1, 2, pairable ? 1 : 0>(ctx, p, grid, smem_bytes);
     return launch_rows_v<EPI, 0, 4, pairable ? 1 : 0>(ctx, p, grid, smem_bytes);
@@ -1149,8 +1154,10 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   {   // CTA pairs (cta_group::2) for the big K-major products: RAU_CG2=0 keeps everything on single CTAs
     static int cg2_on = -1;
     if (cg2_on < 0) { const char* e = getenv("RAU_CG2"); cg2_on = e ? atoi(e) : 1; }
-    p.cg2 = (cg2_on && (g.epi == EPI_PLAIN || g.epi == EPI_TANH || g.epi == EPI_ATT || g.epi == EPI_DY) && !g.A.mn && !g.B.mn &&
-             BN == 256 && !seg2 && p.tiles_m >= 8 && sm_avail >= 2) ? 1 : 0;
+    const bool pair_epi = g.epi == EPI_PLAIN || g.epi == EPI_TANH || g.epi == EPI_ATT || g.epi == EPI_DY || g.epi == EPI_RED;
+    // big row counts (the image-side products), or split-K reductions with at least one pair of row tiles
+    const bool pair_shape = g.epi == EPI_RED ? (p.tiles_m >= 2 && p.tiles_m % 2 == 0 && p.nkb >= 64) : p.tiles_m >= 8;
+    p.cg2 = (cg2_on && pair_epi && pair_shape && BN == 256 && !seg2 && sm_avail >= 2) ? 1 : 0;
   }
   if (seg2) {
     RAU_REQUIRE(g.A2.hi && g.B2.hi && g.A2.mn == g.A.mn && g.B2.mn == g.B.mn && (g.A2.lo != nullptr) == (g.A.lo != nullptr) &&
@@ -1169,8 +1176,9 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   if (p.stages > RT_MAXSTAGES) p.stages = RT_MAXSTAGES;
   const int tiles = (p.cg2 ? (p.tiles_m + 1) / 2 : p.tiles_m) * p.tiles_n;   // work items before any K split
   p.ksplit = 1;
-  if (g.epi == EPI_RED && tiles < sm_avail) {
-    int want = sm_avail / tiles;
+  const int workers = p.cg2 ? sm_avail / 2 : sm_avail;   // CTAs, or CTA pairs
+  if (g.epi == EPI_RED && tiles < workers) {
+    int want = workers / tiles;
     if (want > p.nkb) want = p.nkb;
     if (want < 1) want = 1;
     p.ksplit = want;
