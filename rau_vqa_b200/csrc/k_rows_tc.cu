@@ -497,6 +497,23 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
       if (EPI == EPI_DY) rs = p.rowscale[rr];
       const int c_lo = half * (p.BN / 64), c_hi = c_lo + p.BN / 64;
       bool released = false;
+      // EPI_DY: the saved activation (1 - y^2 factor) of a chunk is fetched one chunk ahead, so its latency hides behind
+      // the previous chunk's split / staging / store instead of sitting between the accumulator read and the math
+      uint4 ah[4], al[4];
+      if (EPI == EPI_DY) {
+        const int nc0 = min(n0 + c_lo * 32, p.N - 32);
+        const uint4* ih = reinterpret_cast<const uint4*>(p.aux_hi + (long long)rr * p.ldaux + nc0);
+#pragma unroll
+        for (int k8 = 0; k8 < 4; ++k8) ah[k8] = __ldg(ih + k8);
+        if (p.aux_lo) {
+          const uint4* il = reinterpret_cast<const uint4*>(p.aux_lo + (long long)rr * p.ldaux + nc0);
+#pragma unroll
+          for (int k8 = 0; k8 < 4; ++k8) al[k8] = __ldg(il + k8);
+        } else {
+#pragma unroll
+          for (int k8 = 0; k8 < 4; ++k8) al[k8] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
 #pragma unroll 1
       for (int c = c_lo; c < c_hi; ++c) {
         const int nc = n0 + c * 32;
@@ -679,13 +696,10 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
           }
           continue;
         } else {   // EPI_DY
-          const uint4* ih = reinterpret_cast<const uint4*>(p.aux_hi + (long long)rr * p.ldaux + nc);
-          const uint4* il = p.aux_lo ? reinterpret_cast<const uint4*>(p.aux_lo + (long long)rr * p.ldaux + nc) : nullptr;
 #pragma unroll
           for (int k8 = 0; k8 < 4; ++k8) {
-            const uint4 h = __ldg(ih + k8);
-            uint4 l = make_uint4(0u, 0u, 0u, 0u);
-            if (il) l = __ldg(il + k8);
+            const uint4 h = ah[k8];
+            const uint4 l = al[k8];
             const float4 d0 = __ldg(reinterpret_cast<const float4*>(rv + nc) + 2 * k8);
             const float4 d1 = __ldg(reinterpret_cast<const float4*>(rv + nc) + 2 * k8 + 1);
             const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
@@ -698,6 +712,16 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
               const float g1 = (v[k + 1] + dd[2 * j + 1] * rs) * (1.0f - y1 * y1);
               v[k] = r_ok ? g0 : 0.0f;
               v[k + 1] = r_ok ? g1 : 0.0f;
+            }
+          }
+          if (c + 1 < c_hi && nc + 32 < p.N) {   // next chunk's activation
+            const uint4* ih = reinterpret_cast<const uint4*>(p.aux_hi + (long long)rr * p.ldaux + nc + 32);
+#pragma unroll
+            for (int k8 = 0; k8 < 4; ++k8) ah[k8] = __ldg(ih + k8);
+            if (p.aux_lo) {
+              const uint4* il = reinterpret_cast<const uint4*>(p.aux_lo + (long long)rr * p.ldaux + nc + 32);
+#pragma unroll
+              for (int k8 = 0; k8 < 4; ++k8) al[k8] = __ldg(il + k8);
             }
           }
           if (p.out_lo) {
@@ -963,6 +987,43 @@ __global__ void __launch_bounds__(256) unprep_rows_kernel(const float* __restric
   }
 }
 
+// attbycontent, the state-dependent half (F:244-252): logit[r] = sum_n ws[n] tanh(Z[r,n] + qadd[b(r),n]) where
+// Z = I Wa^T was formed ahead of the recurrence (it does not depend on the state) and qadd = Wqa qf + bqa + ba.
+// A warp per 4 rows, 16-byte loads; HBM-bound (Z is read once, nothing but the R logits is written)
+template <int FAST>
+__global__ void __launch_bounds__(256) attn_rows_score_kernel(int R, int S, int A, const float* __restrict__ Z,
+                                                              const float* __restrict__ qadd, const float* __restrict__ ws,
+                                                              float* __restrict__ logit) {
+  RAU_PDL_ENTRY();
+  const int lane = threadIdx.x & 31;
+  const int rbase = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 4;
+  const int a4 = A >> 2;
+  float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  for (int w = lane; w < a4; w += 32) {
+    const float4 w4 = __ldg(reinterpret_cast<const float4*>(ws) + w);
+    float4 z[4], qv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = min(rbase + i, R - 1);
+      z[i] = __ldg(reinterpret_cast<const float4*>(Z + (int64_t)r * A) + w);
+      qv[i] = __ldg(reinterpret_cast<const float4*>(qadd + (int64_t)(r / S) * A) + w);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float x0 = z[i].x + qv[i].x, x1 = z[i].y + qv[i].y, x2 = z[i].z + qv[i].z, x3 = z[i].w + qv[i].w;
+      acc[i] = fmaf(w4.x, FAST ? tanh_hw(x0) : tanh_acc(x0), acc[i]);
+      acc[i] = fmaf(w4.y, FAST ? tanh_hw(x1) : tanh_acc(x1), acc[i]);
+      acc[i] = fmaf(w4.z, FAST ? tanh_hw(x2) : tanh_acc(x2), acc[i]);
+      acc[i] = fmaf(w4.w, FAST ? tanh_hw(x3) : tanh_acc(x3), acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float v = warp_sum(acc[i]);
+    if (lane == 0 && rbase + i < R) logit[rbase + i] = v;
+  }
+}
+
 // attbymemory + attselect on the rows layout (F:285-290, F:254-263): p = softmax(logit + mem), a = sum_s p_s I[b*S+s, :]
 // grid (B, M/256), 256 threads: a CTA owns 256 channels of one image; 32 threads cover a row slice with 16-byte loads,
 // 8 row groups walk the image in parallel (HBM-bound: I hi+lo is read exactly once)
@@ -1048,7 +1109,9 @@ __global__ void __launch_bounds__(256) attn_rows_dp_kernel(int R, int S, int M, 
 // backward, part 2: grid (B, NSL) -- every CTA redoes the image's softmax backward (196 scalars), then emits dZ for its
 // slice of the image's rows:  ds = p (dp - <p,dp>) ; dZ[r,n] = ws[n] ds[s] (1 - E[r,n]^2) -> bf16 (hi, lo) ;
 // dqa[b,n] += sum_s dZ[r,n] ; gws_part[b,n] += sum_s ds[s] E[r,n]   (both zeroed by the caller, slices add atomically)
+template <int RECOMP>   // 0: E holds tanh(.) ; 1: E holds Z = I Wa^T, e = tanh(Z + qadd[b]) ; 2: same with MUFU.TANH
 __global__ void __launch_bounds__(256) attn_rows_dz_kernel(int S, int A, const float* __restrict__ E,
+                                                           const float* __restrict__ qadd,
                                                            const float* __restrict__ ws, const float* __restrict__ p_in,
                                                            const float* __restrict__ dp, float* __restrict__ ds_out,
                                                            bf16* __restrict__ dZ_hi, bf16* __restrict__ dZ_lo,
@@ -1077,10 +1140,14 @@ __global__ void __launch_bounds__(256) attn_rows_dz_kernel(int S, int A, const f
   const int tpr = A >> 2, ngroups = 256 / tpr;
   const int ng = tid % tpr, rg = tid / tpr;
   const float4 w4 = *reinterpret_cast<const float4*>(ws + 4 * ng);
+  float4 qa = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (RECOMP) qa = __ldg(reinterpret_cast<const float4*>(qadd + (int64_t)b * A) + ng);
   float sz0 = 0.f, sz1 = 0.f, sz2 = 0.f, sz3 = 0.f, sg0 = 0.f, sg1 = 0.f, sg2 = 0.f, sg3 = 0.f;
 #pragma unroll 4
   for (int s = s_lo + rg; s < s_hi; s += ngroups) {
-    const float4 e = __ldg(reinterpret_cast<const float4*>(E + (r0 + s) * A) + ng);
+    float4 e = __ldg(reinterpret_cast<const float4*>(E + (r0 + s) * A) + ng);
+    if (RECOMP == 1) { e.x = tanh_acc(e.x + qa.x); e.y = tanh_acc(e.y + qa.y); e.z = tanh_acc(e.z + qa.z); e.w = tanh_acc(e.w + qa.w); }
+    if (RECOMP == 2) { e.x = tanh_hw(e.x + qa.x); e.y = tanh_hw(e.y + qa.y); e.z = tanh_hw(e.z + qa.z); e.w = tanh_hw(e.w + qa.w); }
     const float d = ds[s];
     const float z0 = w4.x * d * (1.0f - e.x * e.x), z1 = w4.y * d * (1.0f - e.y * e.y);
     const float z2 = w4.z * d * (1.0f - e.z * e.z), z3 = w4.w * d * (1.0f - e.w * e.w);
@@ -1100,6 +1167,220 @@ __global__ void __launch_bounds__(256) attn_rows_dz_kernel(int S, int A, const f
     for (int k = 0; k < ngroups; ++k) { z += red2[0][k * A + n]; g += red2[1][k * A + n]; }
     atomicAdd(dqa + (int64_t)b * A + n, z);
     atomicAdd(gws_part + (int64_t)b * A + n, g);
+  }
+}
+
+
+// ================================================================== persistent LSTM recurrence (question encoder)
+// One launch walks ALL time steps of one LSTM layer: G_t = Gx_t + h_{t-1} Wh^T, cell update, h_t (D:22-45, the encoder's
+// recurrent half; the input half Gx was hoisted over time).  A CTA owns 128 batch rows x 64 permuted gate columns (16
+// hidden units) for the whole sequence: its slice of Wh stays in shared memory (hi and lo planes, 128 KB at Hq = 512) and
+// its cell state in registers, so a step moves only h_{t-1} (L2 -> smem by TMA) and the step's outputs.  The CTAs of one
+// row tile exchange h_t through global memory: writers release a per-tile counter, the TMA producer acquires it.
+struct LsParams {
+  CUtensorMap mapA, mapB;          // h stack [(T+1)*B, H] (hi, lo planes) ; Wh permuted [4H, H] (hi, lo planes)
+  int B, H, T, tiles_n, nkb, stages, a_swap, b_swap;
+  const float* Gx; long long gx_t; int ldg;     // [T][B][4H] hoisted input projection (+ biases), permuted columns
+  float* c_out; float* h_out; long long s_t; int lds;   // state rows of step 1 (fp32), step stride, row pitch
+  float* lsaved; long long ls_t, plane;         // saved gates of step 1: 5 planes (i, f, o, g, tanh c') of [B, H]
+  bf16* hpk_hi; bf16* hpk_lo; long long hp_t;   // packed h of step 0 (zeros); step t at + t*hp_t
+  unsigned int* counter;                        // [tiles_m] zeroed by the caller
+  unsigned int* err;
+};
+constexpr int LS_THREADS = 320;   // TMA producer, MMA issuer, 8 epilogue warps
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int X3>
+__global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_constant__ LsParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[RT_MAXSTAGES], empty_bar[RT_MAXSTAGES], w_bar, tfull_bar, tempty_bar;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr uint32_t NT = X3 ? 2u : 1u;
+  constexpr uint32_t w_plane = 64u * 64u * 2u, w_tile = NT * w_plane;        // per k-block of the weight slice
+  constexpr uint32_t a_plane = 128u * 64u * 2u, a_stage = NT * a_plane;
+  uint8_t* wsm = smem;
+  uint8_t* ast = smem + (size_t)p.nkb * w_tile;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tn = blockIdx.x % p.tiles_n, tm = blockIdx.x / p.tiles_n;
+  const int m0 = tm * 128, n0 = tn * 64;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&w_bar, 1); mbar_init(&tfull_bar, 1); mbar_init(&tempty_bar, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.mapB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(64u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer: the weight slice once, then h_{t-1} of every step through the stage ring
+    if (elect_one()) {
+      mbar_expect_tx(&w_bar, (uint32_t)p.nkb * w_tile);
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        if (X3) tma_load_3d(wsm + (size_t)kb * w_tile, &p.mapB, &w_bar, kb * 64, n0, 0);
+        else tma_load_2d(wsm + (size_t)kb * w_tile, &p.mapB, &w_bar, kb * 64, n0);
+      }
+    }
+    __syncwarp();
+    uint32_t it = 0;
+    for (int t = 1; t <= p.T; ++t) {
+      if (t > 1) {   // every CTA of this row tile has published its columns of h_{t-1}
+        const unsigned int need = (unsigned int)p.tiles_n * (unsigned int)(t - 1);
+        if (lane == 0) {
+          const long long t0 = clock64();
+          while (ld_acquire_u32(p.counter + tm) < need) {
+            if (clock64() - t0 > 4000000000ll) { *p.err = 1u; break; }   // never hang the device on a lost peer
+          }
+        }
+        __syncwarp();
+        asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy writes of the peers -> this thread's TMA reads
+      }
+      for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+        const int st = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1u;
+        mbar_wait(&empty_bar[st], ph ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[st], a_stage);
+          if (X3) tma_load_3d(ast + (size_t)st * a_stage, &p.mapA, &full_bar[st], kb * 64, (t - 1) * p.B + m0, 0);
+          else tma_load_2d(ast + (size_t)st * a_stage, &p.mapA, &full_bar[st], kb * 64, (t - 1) * p.B + m0);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: M = 128, N = 64, K-major SWIZZLE_128B operands (see rows_gemm_kernel)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint64_t a_p1 = (uint64_t)(a_plane >> 4), b_p1 = (uint64_t)(w_plane >> 4);
+    const uint64_t a_hi_off = p.a_swap ? a_p1 : 0, a_lo_off = p.a_swap ? 0 : a_p1;
+    const uint64_t b_hi_off = p.b_swap ? b_p1 : 0, b_lo_off = p.b_swap ? 0 : b_p1;
+    mbar_wait(&w_bar, 0u);
+    uint32_t it = 0;
+    for (int t = 1; t <= p.T; ++t) {
+      mbar_wait(&tempty_bar, ((uint32_t)(t - 1) & 1u) ^ 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+        const int st = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1u;
+        mbar_wait(&full_bar[st], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint64_t da0 = make_desc(smem_u32(ast + (size_t)st * a_stage), 16u, 1024u, 2u);
+          const uint64_t db0 = make_desc(smem_u32(wsm + (size_t)kb * w_tile), 16u, 1024u, 2u);
+          const uint64_t da_hi = da0 + a_hi_off, da_lo = da0 + a_lo_off, db_hi = db0 + b_hi_off, db_lo = db0 + b_lo_off;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t o = (uint64_t)k * (32u >> 4);
+            umma_f16(tmem_base, da_hi + o, db_hi + o, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (X3) {
+              umma_f16(tmem_base, da_hi + o, db_lo + o, idesc, 1u);
+              umma_f16(tmem_base, da_lo + o, db_hi + o, idesc, 1u);
+            }
+          }
+          umma_commit(&empty_bar[st]);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&tfull_bar);
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue warps 2..9: TMEM lanes 32*(warp%4).., one 32-column chunk (8 hidden units x
+    // i, f, o, g) per warp; the cell state of those units lives in registers for the whole sequence
+    const int q = warp & 3, c = (warp - 2) >> 2;
+    const int r = m0 + q * 32 + lane;
+    const bool r_ok = r < p.B;
+    const int rr = r_ok ? r : p.B - 1;
+    const int nc = n0 + c * 32;            // first permuted gate column
+    const int u0 = (nc >> 5) << 3;         // first hidden unit
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+    float cs[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) cs[u] = 0.0f;
+    for (int t = 1; t <= p.T; ++t) {
+      float4 gx[8];   // the input half of this step's gates does not depend on the recurrence: fetch before waiting
+      const float4* gsrc = reinterpret_cast<const float4*>(p.Gx + (long long)(t - 1) * p.gx_t + (long long)rr * p.ldg + nc);
+#pragma unroll
+      for (int k4 = 0; k4 < 8; ++k4) gx[k4] = __ldg(gsrc + k4);
+      mbar_wait(&tfull_bar, (uint32_t)(t - 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float v[32];
+      tmem_ld32(taddr, v);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar);
+#pragma unroll
+      for (int k4 = 0; k4 < 8; ++k4) {
+        v[4 * k4] += gx[k4].x; v[4 * k4 + 1] += gx[k4].y; v[4 * k4 + 2] += gx[k4].z; v[4 * k4 + 3] += gx[k4].w;
+      }
+      float gi[8], gf[8], go[8], gg[8], tc[8], hn[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        gi[u] = rcp_ftz(1.0f + exp2f_ftz(-1.4426950408889634f * v[u]));
+        gf[u] = rcp_ftz(1.0f + exp2f_ftz(-1.4426950408889634f * v[8 + u]));
+        go[u] = rcp_ftz(1.0f + exp2f_ftz(-1.4426950408889634f * v[16 + u]));
+        gg[u] = tanh_acc(v[24 + u]);
+        cs[u] = fmaf(gf[u], cs[u], gi[u] * gg[u]);
+        tc[u] = tanh_acc(cs[u]);
+        hn[u] = go[u] * tc[u];
+      }
+      if (r_ok) {
+        // h_t packed first: it is what the peers are waiting for
+        uint32_t hh[4], hl[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) split_pair(hn[2 * u], hn[2 * u + 1], hh[u], hl[u]);
+        const long long ho = (long long)t * p.hp_t + (long long)r * p.H + u0;
+        *reinterpret_cast<uint4*>(p.hpk_hi + ho) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+        if (X3) *reinterpret_cast<uint4*>(p.hpk_lo + ho) = make_uint4(hl[0], hl[1], hl[2], hl[3]);
+      }
+      // publish: every writer fences, the epilogue warps meet, one thread releases the tile counter
+      __threadfence();
+      asm volatile("fence.proxy.async;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp == 2 && lane == 0) red_release_add_u32(p.counter + tm, 1u);
+      if (r_ok) {
+        float4* d;
+        const long long so = (long long)(t - 1) * p.s_t + (long long)r * p.lds + u0;
+        d = reinterpret_cast<float4*>(p.c_out + so);
+        d[0] = make_float4(cs[0], cs[1], cs[2], cs[3]); d[1] = make_float4(cs[4], cs[5], cs[6], cs[7]);
+        d = reinterpret_cast<float4*>(p.h_out + so);
+        d[0] = make_float4(hn[0], hn[1], hn[2], hn[3]); d[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+        float* sbase = p.lsaved + (long long)(t - 1) * p.ls_t + (long long)r * p.H + u0;
+        d = reinterpret_cast<float4*>(sbase);
+        d[0] = make_float4(gi[0], gi[1], gi[2], gi[3]); d[1] = make_float4(gi[4], gi[5], gi[6], gi[7]);
+        d = reinterpret_cast<float4*>(sbase + p.plane);
+        d[0] = make_float4(gf[0], gf[1], gf[2], gf[3]); d[1] = make_float4(gf[4], gf[5], gf[6], gf[7]);
+        d = reinterpret_cast<float4*>(sbase + 2 * p.plane);
+        d[0] = make_float4(go[0], go[1], go[2], go[3]); d[1] = make_float4(go[4], go[5], go[6], go[7]);
+        d = reinterpret_cast<float4*>(sbase + 3 * p.plane);
+        d[0] = make_float4(gg[0], gg[1], gg[2], gg[3]); d[1] = make_float4(gg[4], gg[5], gg[6], gg[7]);
+        d = reinterpret_cast<float4*>(sbase + 4 * p.plane);
+        d[0] = make_float4(tc[0], tc[1], tc[2], tc[3]); d[1] = make_float4(tc[4], tc[5], tc[6], tc[7]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
   }
 }
 
@@ -1341,9 +1622,19 @@ int k_attn_rows_fwd(rau_ctx* ctx, int B, int M, int S, const float* logit, const
   return RAU_OK;
 }
 
+int k_attn_rows_score(rau_ctx* ctx, int B, int A, int S, const float* Z, const float* qadd, const float* ws, int fast_tanh,
+                      float* logit) {
+  RAU_REQUIRE(A % 4 == 0, "k_attn_rows_score: A=%d", A);
+  const int R = B * S;
+  if (fast_tanh) RAU_LAUNCH_PDL(ctx->stream, (attn_rows_score_kernel<1>), (R + 31) / 32, 256, 0, R, S, A, Z, qadd, ws, logit);
+  else RAU_LAUNCH_PDL(ctx->stream, (attn_rows_score_kernel<0>), (R + 31) / 32, 256, 0, R, S, A, Z, qadd, ws, logit);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+
 int k_attn_rows_bwd(rau_ctx* ctx, int B, int M, int A, int S, const float* E, const bf16* I_hi, const bf16* I_lo, const float* ws,
                     const float* p, const float* dp_in, const float* da, float* ds, bf16* dZ_hi, bf16* dZ_lo, float* dqa,
-                    float* gws_part, bf16* ds_hi, bf16* ds_lo, int ldds) {
+                    float* gws_part, bf16* ds_hi, bf16* ds_lo, int ldds, const float* qadd, int fast_tanh) {
   RAU_REQUIRE(M % 8 == 0 && S <= 256 && ldds <= 256 && (A == 64 || A == 128 || A == 256), "k_attn_rows_bwd: M=%d A=%d S=%d", M, A, S);
   const int R = B * S;
   float* dp = nullptr;
@@ -1353,12 +1644,65 @@ int k_attn_rows_bwd(rau_ctx* ctx, int B, int M, int A, int S, const float* E, co
   RAU_CHECK_CUDA(cudaMemsetAsync(dqa, 0, sizeof(float) * (size_t)B * A, ctx->stream));
   RAU_CHECK_CUDA(cudaMemsetAsync(gws_part, 0, sizeof(float) * (size_t)B * A, ctx->stream));
   const int nsl = B >= 128 ? 4 : (B >= 32 ? 8 : 16);   // row slices per image: ~1000 CTAs
-  RAU_LAUNCH_PDL(ctx->stream, (attn_rows_dz_kernel), dim3(B, nsl), 256, 0, S, A, E, ws, p, dp, ds, dZ_hi, dZ_lo, dqa, gws_part, ds_hi,
-                 ds_lo, ldds);
+  if (!qadd)
+    RAU_LAUNCH_PDL(ctx->stream, (attn_rows_dz_kernel<0>), dim3(B, nsl), 256, 0, S, A, E, qadd, ws, p, dp, ds, dZ_hi, dZ_lo, dqa,
+                   gws_part, ds_hi, ds_lo, ldds);
+  else if (!fast_tanh)
+    RAU_LAUNCH_PDL(ctx->stream, (attn_rows_dz_kernel<1>), dim3(B, nsl), 256, 0, S, A, E, qadd, ws, p, dp, ds, dZ_hi, dZ_lo, dqa,
+                   gws_part, ds_hi, ds_lo, ldds);
+  else
+    RAU_LAUNCH_PDL(ctx->stream, (attn_rows_dz_kernel<2>), dim3(B, nsl), 256, 0, S, A, E, qadd, ws, p, dp, ds, dZ_hi, dZ_lo, dqa,
+                   gws_part, ds_hi, ds_lo, ldds);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 
+
+
+// The whole recurrence of one encoder LSTM layer in one persistent launch (lstm_seq_kernel).  Returns RAU_OK with *done = 0
+// when the shape does not fit (the caller then unrolls the per-step EPI_LSTM launches).
+int rows_lstm_seq(rau_ctx* ctx, const LstmSeq& d, int* done) {
+  *done = 0;
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("RAU_LSTM_SEQ"); on = e ? atoi(e) : 1; }
+  const int B = d.B, H = d.H, T = d.T;
+  const bool x3 = d.hpk_lo != nullptr;
+  if (!on || H % 64 != 0 || T < 1 || !d.hpk_hi || !d.Wh_hi || (x3 != (d.Wh_lo != nullptr))) return RAU_OK;
+  const int nkb = H / 64, tiles_m = (B + 127) / 128, tiles_n = 4 * H / 64;
+  const int w_bytes = nkb * (x3 ? 2 : 1) * 64 * 64 * 2, a_stage = (x3 ? 2 : 1) * 128 * 64 * 2;
+  int stages = (RT_SMEM_BUDGET - w_bytes) / a_stage;
+  if (stages > RT_MAXSTAGES) stages = RT_MAXSTAGES;
+  // every CTA of the grid must be resident at once (they wait for each other): one CTA per SM
+  if (stages < 2 || tiles_m * tiles_n > ctx->sm_count) return RAU_OK;
+  RAU_REQUIRE(d.ldwh % 8 == 0 && d.ldg % 4 == 0 && d.lds % 4 == 0, "rows_lstm_seq: pitches");
+  RAU_TRY(get_encode());
+  LsParams p;
+  memset(&p, 0, sizeof(p));
+  RAU_TRY(encode_operand(&p.mapA, d.hpk_hi, d.hpk_lo, &p.a_swap, 0, (T + 1) * B, H, H, 64, 128));
+  RAU_TRY(encode_operand(&p.mapB, d.Wh_hi, d.Wh_lo, &p.b_swap, 0, 4 * H, H, d.ldwh, 64, 64));
+  p.B = B; p.H = H; p.T = T; p.tiles_n = tiles_n; p.nkb = nkb; p.stages = stages;
+  p.Gx = d.Gx; p.gx_t = d.gx_t; p.ldg = d.ldg;
+  p.c_out = d.c_out; p.h_out = d.h_out; p.s_t = d.s_t; p.lds = d.lds;
+  p.lsaved = d.lsaved; p.ls_t = d.ls_t; p.plane = d.plane;
+  p.hpk_hi = d.hpk_hi; p.hpk_lo = d.hpk_lo; p.hp_t = (long long)B * H;
+  unsigned int* cnt = nullptr;
+  RAU_TRY(ctx->arena.get("lstmseq.cnt", sizeof(unsigned int) * 64, (void**)&cnt));
+  RAU_REQUIRE(tiles_m < 63, "rows_lstm_seq: %d row tiles", tiles_m);
+  RAU_CHECK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * 64, ctx->stream));
+  p.counter = cnt; p.err = cnt + 63;
+  const int smem_bytes = w_bytes + stages * a_stage + 1024;
+  static bool attr_done[2] = {false, false};
+  if (!attr_done[x3 ? 1 : 0]) {
+    if (x3) RAU_CHECK_CUDA(cudaFuncSetAttribute(lstm_seq_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM_BUDGET + 1024));
+    else RAU_CHECK_CUDA(cudaFuncSetAttribute(lstm_seq_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM_BUDGET + 1024));
+    attr_done[x3 ? 1 : 0] = true;
+  }
+  if (x3) lstm_seq_kernel<1><<<tiles_m * tiles_n, LS_THREADS, smem_bytes, ctx->stream>>>(p);
+  else lstm_seq_kernel<0><<<tiles_m * tiles_n, LS_THREADS, smem_bytes, ctx->stream>>>(p);
+  RAU_LAUNCH_CHECK(ctx);
+  *done = 1;
+  return RAU_OK;
+}
 
 // ================================================================== nn.Linear adapter
 namespace {

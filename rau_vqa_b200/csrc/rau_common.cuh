@@ -90,10 +90,15 @@ struct rau_ctx {
   std::vector<cudaEvent_t> side_ev;
   int side_ev_next = 0;
   int side_ctas = 0;
+  int side_ctas_fwd = 0;                           // the cap while the forward's state-independent products run
   int rows_cta_cap = 0;                            // > 0 while work is being enqueued on the side stream
   // RAU_PHASES=1: eager steps with an event at every phase boundary; rau_phase_report() prints the split
   int phases = -1;
   std::vector<std::pair<std::string, cudaEvent_t>> phase_ev;
+  // RAU_PHASES=2: a one-thread kernel per mark writes %globaltimer, so the marks survive graph capture and show the
+  // replayed step's timeline on both streams
+  unsigned long long* stamp_buf = nullptr;
+  std::vector<std::string> stamp_names;
 };
 void rau_phase_mark(rau_ctx* ctx, const char* name);
 

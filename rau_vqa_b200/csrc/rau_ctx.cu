@@ -1,4 +1,5 @@
 // rau_ctx.cu -- context lifetime, error text, device arena and the flat parameter layout of include/rau.h.
+#include <algorithm>
 #include "rau_layout.cuh"
 #include <stdarg.h>
 #include <stdlib.h>
@@ -51,12 +52,28 @@ bool rau_pdl_enabled() {
   return v != 0;
 }
 
+namespace {
+__global__ void stamp_kernel(unsigned long long* out) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *out = t;
+}
+}  // namespace
+
 void rau_phase_mark(rau_ctx* ctx, const char* name) {
   if (ctx->phases < 0) {
     const char* e = getenv("RAU_PHASES");
     ctx->phases = e ? atoi(e) : 0;
   }
   if (!ctx->phases) return;
+  if (ctx->phases == 2) {
+    if (!ctx->stamp_buf && cudaMalloc(&ctx->stamp_buf, sizeof(unsigned long long) * 1024) != cudaSuccess) return;
+    if (strcmp(name, "begin") == 0) ctx->stamp_names.clear();
+    if (ctx->stamp_names.size() >= 1024) return;
+    stamp_kernel<<<1, 1, 0, ctx->stream>>>(ctx->stamp_buf + ctx->stamp_names.size());
+    ctx->stamp_names.push_back(std::string(ctx->stream == ctx->side ? "S " : "M ") + name);
+    return;
+  }
   cudaEvent_t ev;
   if (cudaEventCreate(&ev) != cudaSuccess) return;
   cudaEventRecord(ev, ctx->stream);
@@ -70,6 +87,17 @@ int rau_version(void) { return 100; }
 /* debugging aid (RAU_PHASES=1): prints the milliseconds between the phase marks recorded since the last report */
 int rau_phase_report(rau_ctx* ctx) {
   if (ctx == nullptr) return RAU_EINVAL;
+  if (ctx->phases == 2 && ctx->stamp_buf && !ctx->stamp_names.empty()) {
+    cudaDeviceSynchronize();
+    std::vector<unsigned long long> t(ctx->stamp_names.size());
+    cudaMemcpy(t.data(), ctx->stamp_buf, sizeof(unsigned long long) * t.size(), cudaMemcpyDeviceToHost);
+    std::vector<size_t> order(t.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return t[a] < t[b]; });
+    for (size_t i : order)
+      fprintf(stderr, "[rau stamp] %9.1f us  %s\n", (double)(t[i] - t[0]) * 1e-3, ctx->stamp_names[i].c_str());
+    return RAU_OK;
+  }
   if (ctx->phase_ev.empty()) return RAU_OK;
   cudaStreamSynchronize(ctx->stream);
   for (size_t i = 1; i < ctx->phase_ev.size(); ++i) {
@@ -132,6 +160,7 @@ int rau_ctx_destroy(rau_ctx* ctx) {
   cudaDeviceSynchronize();
   rau_comm_destroy_internal(ctx);
   ctx->arena.release();
+  if (ctx->stamp_buf) cudaFree(ctx->stamp_buf);
   if (ctx->d_ss) cudaFree(ctx->d_ss);
   if (ctx->h_ss) cudaFreeHost(ctx->h_ss);
   if (ctx->gstream) cudaStreamDestroy(ctx->gstream);

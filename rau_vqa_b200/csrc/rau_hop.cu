@@ -34,6 +34,7 @@ size_t hop_saved_layout(const rau_config* cfg, int B, void* base, HopSaved* sv) 
   s.Xd_lo = (bf16*)take(sizeof(bf16) * (size_t)B * cfg->C * Sp);
   s.I_hi = (bf16*)take(sizeof(bf16) * (size_t)B * cfg->M * Sp);
   s.I_lo = (bf16*)take(sizeof(bf16) * (size_t)B * cfg->M * Sp);
+  s.qatt = (float*)take(sizeof(float) * B * cfg->A);
   if (sv) *sv = s;
   return off;
 }
@@ -97,7 +98,19 @@ int hop_forward_pre(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<cons
   g.B.hi = Wi_h; g.B.lo = Wi_l; g.B.ld = C;
   g.epi = ROWS_EPI_TANH; g.bias = P.bi;
   g.out_hi = sv.I_hi; g.out_lo = x3 ? sv.I_lo : nullptr; g.ldo = M;
-  return rows_gemm(ctx, g);
+  RAU_TRY(rows_gemm(ctx, g));
+  // attbycontent (F:244-252), the half the state does not reach: Z = I Wa^T.  hop_forward() adds the query term per image
+  // and takes tanh and the ws reduction in a bandwidth-bound pass, so no tensor product is left on the recurrent chain.
+  const int A = cfg->A;
+  const bf16 *Wa_h, *Wa_l;
+  RAU_TRY(rows_pack(ctx, P.Wa, (int64_t)A * M, x3, true, nullptr, &Wa_h, &Wa_l));
+  RowsGemm z;
+  z.M = R; z.N = A; z.K = M;
+  z.A.hi = sv.I_hi; z.A.lo = x3 ? sv.I_lo : nullptr; z.A.ld = M;
+  z.B.hi = Wa_h; z.B.lo = Wa_l; z.B.ld = M;
+  z.epi = ROWS_EPI_PLAIN;
+  z.out_f = sv.E; z.ldo = A;
+  return rows_gemm(ctx, z);
 }
 
 int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const float*>& P,
@@ -138,20 +151,15 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
     RAU_TRY(rau_contract(ctx, g));
   }
   if (rows_path(ctx, cfg)) {
-    // rows layout (k_rows_tc.cu): r = b*S + s.  sv.Xd_* = drop(X)^T [R,C], sv.I_* = I [R,M], sv.E = E [R,A] (fp32)
+    // rows layout (k_rows_tc.cu): r = b*S + s.  sv.Xd_* = drop(X)^T [R,C], sv.I_* = I [R,M], sv.E = Z = I Wa^T [R,A] (fp32)
     const int R = B * S;
-    const bf16 *Wi_h, *Wi_l, *Wa_h, *Wa_l;
-    RAU_TRY(rows_pack(ctx, P.Wi, (int64_t)M * C, x3, true, nullptr, &Wi_h, &Wi_l));
-    RAU_TRY(rows_pack(ctx, P.Wa, (int64_t)A * M, x3, true, nullptr, &Wa_h, &Wa_l));
     ARENA(slog, float, "hop.slog", R);
-    if (as && as->pre_done) {
-      (void)Wi_h; (void)Wi_l;   // hop_forward_pre() ran the feature pack and the i_embed product on the side stream
-    } else {
-      RAU_TRY(hop_forward_pre(ctx, cfg, B, P, X, train, sv));
-    }
+    // the feature pack, I = tanh(Wi X + bi) and Z = I Wa^T do not depend on the state: in the training step
+    // hop_forward_pre() already ran them on the side stream
+    if (!(as && as->pre_done)) RAU_TRY(hop_forward_pre(ctx, cfg, B, P, X, train, sv));
     {
-      SimtGemm g = lin_fwd(B, A, M, sv.qf, M, P.Wqa, qatt, A);
-      g.bias_n = P.bqa;
+      SimtGemm g = lin_fwd(B, A, M, sv.qf, M, P.Wqa, sv.qatt, A);
+      g.bias_n = P.bqa; g.bias_n2 = P.ba;
       g.Ar_hi = sv.qf_pk.hi; g.Ar_lo = sv.qf_pk.lo; g.Ar_ld = sv.qf_pk.ld;
       RAU_TRY(rau_contract(ctx, g));
     }
@@ -162,16 +170,8 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
       RAU_TRY(rau_contract(ctx, g));
     }
     if (as && as->pre_done) RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, as->pre_done, 0));
-    {   // attbycontent (F:244-252): E = tanh(I Wa^T + ba + qatt[b]) ; logit = ws.E (bs shifts every logit alike)
-      RowsGemm g;
-      g.M = R; g.N = A; g.K = M;
-      g.A.hi = sv.I_hi; g.A.lo = x3 ? sv.I_lo : nullptr; g.A.ld = M;
-      g.B.hi = Wa_h; g.B.lo = Wa_l; g.B.ld = M;
-      g.epi = ROWS_EPI_ATT; g.bias = P.ba; g.rowvec = qatt; g.colw = P.ws; g.rowout = slog; g.S = S;
-      RAU_CHECK_CUDA(cudaMemsetAsync(slog, 0, sizeof(float) * (size_t)R, ctx->stream));   // two column halves add into it
-      g.out_f = sv.E; g.ldo = A;
-      RAU_TRY(rows_gemm(ctx, g));
-    }
+    // attbycontent (F:244-252): logit = ws . tanh(Z + ba + qatt[b])  (bs shifts every logit alike: the softmax drops it)
+    RAU_TRY(k_attn_rows_score(ctx, B, A, S, sv.E, sv.qatt, P.ws, x3 ? 0 : 1, slog));
     RAU_TRY(k_attn_rows_fwd(ctx, B, M, S, slog, mem, sv.I_hi, x3 ? sv.I_lo : nullptr, sv.p, a, sv.p_pk.hi,
                             x3 ? sv.p_pk.lo : nullptr, (int)sv.p_pk.ld));
   } else {
@@ -424,7 +424,7 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   const int R = B * S;
   if (rows)
     RAU_TRY(k_attn_rows_bwd(ctx, B, M, A, S, sv.E, sv.I_hi, x3 ? sv.I_lo : nullptr, P.ws, sv.p, dp, dj, ds, dZ_hi, dZ_lo, dqa, gwsp,
-                            ds_pk.hi, x3 ? ds_pk.lo : nullptr, (int)ds_pk.ld));
+                            ds_pk.hi, x3 ? ds_pk.lo : nullptr, (int)ds_pk.ld, sv.qatt, x3 ? 0 : 1));
   else
     RAU_TRY(k_attn_bwd<float>(ctx, B, M, A, S, Sp, sv.E, sv.I, P.ws, sv.p, dp, dj, ds, nullptr, 0, dZ, dqa, nullptr, gwsp,
                               dZ_hi, dZ_lo));

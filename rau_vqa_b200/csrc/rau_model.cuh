@@ -52,6 +52,7 @@ struct PK { bf16* hi = nullptr; bf16* lo = nullptr; int64_t ld = 0; };
 struct HopSaved {
   uint32_t *qbits, *xbits, *mbits;   // packed keep bits of the three dropouts (F:233, F:239, F:277)
   float *qd, *qf, *I, *E, *p, *j, *lsav, *hout, *m, *dop;
+  float* qatt;   // rows path: Wqa qf + bqa + ba [B, A]; E then holds Z = I Wa^T and tanh(Z + qatt[b]) is redone where it is read
   bf16 *Xd_hi, *Xd_lo, *I_hi, *I_lo;   // tcgen05 modes: packed operands kept for the backward pass
   // training step on the rows engine: the feature-dropout bits are drawn inside the transposing pack kernel from this
   // Philox stream instead of being materialised in xbits first (nothing in the step reads them again: dX is not formed)

@@ -59,6 +59,21 @@ int k_xprep_rows(rau_ctx* ctx, const float* X, int B, int C, int S, const uint32
 int k_unprep_rows(rau_ctx* ctx, const float* dXr, int B, int C, int S, const uint32_t* bits, float scale, float* dX);
 int k_attn_rows_fwd(rau_ctx* ctx, int B, int M, int S, const float* logit, const float* mem, const bf16* I_hi, const bf16* I_lo,
                     float* p, float* a, bf16* p_hi = nullptr, bf16* p_lo = nullptr, int ldp = 0);   // p_hi/p_lo: packed twin of p
+// one encoder LSTM layer over all T steps in a single persistent launch (k_rows_tc.cu lstm_seq_kernel)
+struct LstmSeq {
+  int B = 0, H = 0, T = 0;
+  const bf16* Wh_hi = nullptr; const bf16* Wh_lo = nullptr; int64_t ldwh = 0;   // rows_pack_lstm layout [4H, H]
+  const float* Gx = nullptr; int64_t gx_t = 0; int ldg = 0;                    // hoisted input projection [T][B][4H]
+  float* c_out = nullptr; float* h_out = nullptr; int64_t s_t = 0; int lds = 0;   // state rows of step 1, step stride, pitch
+  float* lsaved = nullptr; int64_t ls_t = 0, plane = 0;                         // saved gates of step 1
+  bf16* hpk_hi = nullptr; bf16* hpk_lo = nullptr;                               // packed h stack [(T+1)][B][H], step 0 = zeros
+};
+int rows_lstm_seq(rau_ctx* ctx, const LstmSeq& d, int* done);
+
+// logit[r] = ws . tanh(Z[r,:] + qadd[b(r),:])  (Z = I Wa^T precomputed; qadd = Wqa qf + bqa + ba)
+int k_attn_rows_score(rau_ctx* ctx, int B, int A, int S, const float* Z, const float* qadd, const float* ws, int fast_tanh,
+                      float* logit);
 int k_attn_rows_bwd(rau_ctx* ctx, int B, int M, int A, int S, const float* E, const bf16* I_hi, const bf16* I_lo, const float* ws,
                     const float* p, const float* dp_in, const float* da, float* ds, bf16* dZ_hi, bf16* dZ_lo, float* dqa,
-                    float* gws_part, bf16* ds_hi = nullptr, bf16* ds_lo = nullptr, int ldds = 0);
+                    float* gws_part, bf16* ds_hi = nullptr, bf16* ds_lo = nullptr, int ldds = 0,
+                    const float* qadd = nullptr, int fast_tanh = 0);

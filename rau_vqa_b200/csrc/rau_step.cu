@@ -72,6 +72,7 @@ static int encoder_forward(rau_ctx* ctx, const rau_config* cfg, const rau_batch*
   // word_embed for every step at once (F:203-206, F:468)
   RAU_TRY(k_embed_fwd(ctx, bt->tokens, Tm * B, E, cfg->V, Pe, de ? en->ebits : nullptr, drop_scale(cfg->p_embed),
                       en->e_all, nullptr, 0));
+  if (ctx->phases == 2) rau_phase_mark(ctx, "enc embed done");
   const bool fused = ctx->precision != RAU_PREC_F32 && rows_path_enabled() && Hq % 8 == 0 && E % 8 == 0 &&
                      (int64_t)B * G4 * Hq >= (1 << 18);
   // layer 1 input projection hoisted over time: G1x = e Wi1^T + bi1 + bh1
@@ -113,7 +114,20 @@ static int encoder_forward(rau_ctx* ctx, const rau_config* cfg, const rau_batch*
       }
       RAU_CHECK_CUDA(cudaMemsetAsync(hpk_hi, 0, hb * sizeof(bf16), ctx->stream));
       if (x3) RAU_CHECK_CUDA(cudaMemsetAsync(hpk_lo, 0, hb * sizeof(bf16), ctx->stream));
-      for (int t = 1; t <= Tm; ++t) {
+      if (ctx->phases == 2) rau_phase_mark(ctx, "enc layer input projection done");
+      int seq_done = 0;
+      {   // the whole recurrence in one persistent launch when the layer fits (weights resident in shared memory)
+        LstmSeq d;
+        d.B = B; d.H = Hq; d.T = Tm;
+        d.Wh_hi = Wh_h; d.Wh_lo = Wh_l; d.ldwh = ldwh;
+        d.Gx = Gx; d.gx_t = (int64_t)B * G4; d.ldg = G4;
+        d.c_out = en->S_all + (size_t)B * Q + 2 * layer * Hq; d.h_out = d.c_out + Hq; d.s_t = (int64_t)B * Q; d.lds = Q;
+        d.lsaved = layer == 0 ? en->sav1 : en->sav2; d.ls_t = (int64_t)5 * B * Hq; d.plane = (int64_t)B * Hq;
+        d.hpk_hi = hpk_hi; d.hpk_lo = x3 ? hpk_lo : nullptr;
+        RAU_TRY(rows_lstm_seq(ctx, d, &seq_done));
+        if (ctx->phases == 2) rau_phase_mark(ctx, "enc layer recurrence done");
+      }
+      for (int t = 1; t <= Tm && !seq_done; ++t) {
         float* Sp_ = en->S_all + (size_t)(t - 1) * B * Q + 2 * layer * Hq;
         float* Sn = en->S_all + (size_t)t * B * Q + 2 * layer * Hq;
         RowsGemm g;
@@ -359,6 +373,9 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     const char* e = getenv("RAU_SIDE_CTAS");
     ctx->side_ctas = e ? atoi(e) : (ctx->sm_count * 4) / 7;   // 84 of 148 SMs measured best on Ours_Full (profiles/README.md)
     if (ctx->side_ctas < 8 || ctx->side_ctas > ctx->sm_count) ctx->side_ctas = ctx->sm_count;
+    const char* ef = getenv("RAU_SIDE_CTAS_FWD");
+    ctx->side_ctas_fwd = ef ? atoi(ef) : ctx->side_ctas;
+    if (ctx->side_ctas_fwd < 8 || ctx->side_ctas_fwd > ctx->sm_count) ctx->side_ctas_fwd = ctx->sm_count;
   }
   ctx->side_ev_next = 0;
   bool side_used = false;
@@ -469,13 +486,14 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->side, fork, 0));
     cudaStream_t chain = ctx->stream;
     ctx->stream = ctx->side;
-    ctx->rows_cta_cap = ctx->side_ctas;
+    ctx->rows_cta_cap = ctx->side_ctas_fwd;
     int rc = RAU_OK;
     for (int hp = 0; hp < nHop && rc == RAU_OK; ++hp) {
       rc = hop_forward_pre(ctx, cfg, B, P, bt->feats, train, sv[hp]);
       if (rc == RAU_OK) {
         as[hp].pre_done = rau_side_event(ctx);
         if (as[hp].pre_done == nullptr || cudaEventRecord(as[hp].pre_done, ctx->side) != cudaSuccess) rc = RAU_ECUDA;
+        if (ctx->phases == 2) rau_phase_mark(ctx, "hop pre done");
       }
     }
     ctx->stream = chain;
@@ -503,6 +521,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     RAU_TRY(hop_forward(ctx, cfg, B, P, en.rnn_out, bt->feats, c_all + (size_t)hp * B * H, h_all + (size_t)hp * B * H, train,
                         sv[hp], scores + (size_t)hp * B * N, dop + (size_t)hp * B, att + (size_t)hp * B * S,
                         c_all + (size_t)(hp + 1) * B * H, h_all + (size_t)(hp + 1) * B * H, &as[hp]));
+    if (ctx->phases == 2) rau_phase_mark(ctx, "hop forward chain done");
     // criterion forward + backward + argmax in one pass (F:505, F:535, F:585-589)
     const float hm = hop_mask ? hop_mask[hp] : 1.0f;
     const PK dsc = slice(pk_dscore, (size_t)hp * B);
@@ -511,6 +530,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     const int rc_ce = k_softmax_ce(ctx, B, N, scores + (size_t)hp * B * N, bt->labels, 1.0f / Bg, hm / Bg, loss + hp,
                                    dscore + (size_t)hp * B * N, dsc.hi, N, ans + (size_t)hp * B,
                                    ctx->precision == RAU_PREC_BF16X3 ? dsc.lo : nullptr);
+    if (ctx->phases == 2) rau_phase_mark(ctx, "hop head + criterion done");
     ctx->stream = chain;
     RAU_TRY(rc_ce);
   }
@@ -560,6 +580,10 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
                          dscore + (size_t)hp * B * N, nullptr, nullptr, dc_in, dh_in, dq, last ? 0 : 1, nullptr,
                          dcs + (size_t)(hp & 1) * B * H, dhs + (size_t)(hp & 1) * B * H, &hg, &as[hp]));
     if (ov_bwd) side_used = true;
+    if (ctx->phases == 2) {
+      rau_phase_mark(ctx, "hop backward chain done");
+      if (ov_bwd) { cudaStream_t c = ctx->stream; ctx->stream = ctx->side; rau_phase_mark(ctx, "hop backward products done"); ctx->stream = c; }
+    }
   }
   {   // dq = sum_h drop_h'(dpre_h Wq): one product over the stacked dpre, one masked sum over the hops
     SimtGemm g = lin_dgrad(nHop * B, M_, Q, st_dpre, M_, P.Wq, st_dqt, Q);
@@ -587,6 +611,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
       ctx->stream = ctx->side;
       ctx->rows_cta_cap = ctx->side_ctas;
       const int rc = hop_wgrads(ctx, cfg, nHop * B, G, st);
+      if (ctx->phases == 2) rau_phase_mark(ctx, "deferred weight gradients done");
       ctx->stream = chain;
       ctx->rows_cta_cap = 0;
       RAU_TRY(rc);
@@ -597,6 +622,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   }
   rau_phase_mark(ctx, "unit weight gradients");
   RAU_TRY(encoder_backward(ctx, cfg, bt, params[1], grads[0], grads[1], train, &en, dq));
+  if (ctx->phases == 2) rau_phase_mark(ctx, "encoder backward chain done");
   if (side_used) {   // join: the side stream's gradients (gWi, gWa, gbi) are complete before anything downstream
     cudaEvent_t join = rau_side_event(ctx);
     RAU_REQUIRE(join != nullptr, "cudaEventCreate failed");
@@ -702,7 +728,7 @@ int rau_train_step(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, flo
   // enqueue sequence is captured once and replayed; only the StepState upload above changes between replays
   RauGraph& gr = ctx->graph;
   if (ctx->phases < 0) rau_phase_mark(ctx, "init");
-  const bool graphable = !gr.disabled && masks == nullptr && hp->noise_override == nullptr && ctx->phases <= 0;
+  const bool graphable = !gr.disabled && masks == nullptr && hp->noise_override == nullptr && ctx->phases != 1;
   std::vector<uint64_t> key;
   RauGraphEntry* ent = nullptr;
   if (graphable) {

@@ -1,6 +1,6 @@
 """RAU_PHASES=1 python tools/phases.py [workload] [precision]: per-phase milliseconds of one eager training step."""
 import os, sys
-os.environ["RAU_PHASES"] = "1"
+os.environ.setdefault("RAU_PHASES", "1")   # 2 = %globaltimer stamps that survive graph capture (both streams)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import rau_vqa_b200 as R
@@ -28,7 +28,7 @@ for b in range(B):
 tok = torch.from_numpy(tok.astype(np.float32)).to(dev)
 lens_t = torch.from_numpy(lens.astype(np.float32)).to(dev)
 y = torch.from_numpy(rng.integers(1, cfg.N + 1, B).astype(np.float32)).to(dev)
-for it in range(4):
+for it in range(8 if os.environ["RAU_PHASES"] == "2" else 4):
     core.train_step(ctx, cfg, P, G, ST, X, tok, lens_t, y, out, optim=core.OPT_ADAM, lrs=(3e-3, 3e-3, 3e-4),
                     hyper=(0.9, 0.999, 1e-8), eta=0.01, gamma=0.55, clip=0.1, step_t=it, max_len=26, B_global=B)
     ctx.sync()
