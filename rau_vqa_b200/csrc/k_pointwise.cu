@@ -15,8 +15,11 @@ inline int grid_for(int64_t n, int per_thread = 1) {
 // ---------------------------------------------------------------- masks
 __global__ void mask_gen_kernel(uint32_t* __restrict__ bits, int64_t nwords, int64_t n, uint32_t thresh,
                                 int keep_all, uint2 key, uint32_t stream_lo, uint32_t stream_hi,
-                                const StepState* __restrict__ ss) {
+                                const StepState* __restrict__ ss, int64_t hop_stride) {
   RAU_PDL_ENTRY();
+  // blockIdx.y = hop: the masks of all hops in one launch (streams differ in their index field, words hop_stride apart)
+  bits += (int64_t)blockIdx.y * hop_stride;
+  stream_lo ^= blockIdx.y;
   if (ss) {   // graph replay: the step part of the stream id lives on the device
     const unsigned long long sid = (((unsigned long long)stream_hi << 32) | stream_lo) ^ (ss->step << 24);
     stream_lo = (uint32_t)sid;
@@ -421,12 +424,14 @@ __global__ void select_state_kernel(const float* __restrict__ S_all, int T, int 
 }  // namespace
 
 // ================================================================== host wrappers
-int k_mask_gen(rau_ctx* ctx, uint32_t* bits, int64_t n, float p, uint64_t seed, uint64_t stream_id) {
+int k_mask_gen(rau_ctx* ctx, uint32_t* bits, int64_t n, float p, uint64_t seed, uint64_t stream_id, int nHop,
+               int64_t hop_stride) {
   const int64_t nw = (n + 31) / 32;
   double keep = 1.0 - (double)p;
   uint32_t thresh = keep >= 1.0 ? 0xffffffffu : (uint32_t)(keep * 4294967296.0);
-  RAU_LAUNCH_PDL(ctx->stream, (mask_gen_kernel), grid_for(nw), TPB, 0, bits, nw, n, thresh, p <= 0.0f ? 1 : 0,
-      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), (uint32_t)stream_id, (uint32_t)(stream_id >> 32), ctx->ss_active);
+  RAU_LAUNCH_PDL(ctx->stream, (mask_gen_kernel), dim3(grid_for(nw), nHop), TPB, 0, bits, nw, n, thresh, p <= 0.0f ? 1 : 0,
+      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), (uint32_t)stream_id, (uint32_t)(stream_id >> 32), ctx->ss_active,
+      hop_stride);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }

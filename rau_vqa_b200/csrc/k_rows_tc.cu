@@ -497,23 +497,21 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
       if (EPI == EPI_DY) rs = p.rowscale[rr];
       const int c_lo = half * (p.BN / 64), c_hi = c_lo + p.BN / 64;
       bool released = false;
-      // EPI_DY: the saved activation (1 - y^2 factor) of a chunk is fetched one chunk ahead, so its latency hides behind
-      // the previous chunk's split / staging / store instead of sitting between the accumulator read and the math
+      // EPI_DY: the saved activation (1 - y^2 factor) of a chunk is fetched one chunk ahead and COALESCED: a lane reads
+      // 16 bytes of row (lane/4 + 8i), so one instruction covers 8 rows x 64 B instead of 32 rows x 16 B (8x fewer L1
+      // wavefronts than a lane-per-row fetch); the warp's scratch then hands every lane its own row
       uint4 ah[4], al[4];
-      if (EPI == EPI_DY) {
-        const int nc0 = min(n0 + c_lo * 32, p.N - 32);
-        const uint4* ih = reinterpret_cast<const uint4*>(p.aux_hi + (long long)rr * p.ldaux + nc0);
+      const int arow = lane >> 2, aseg = lane & 3;
+      auto aux_fetch = [&](int ncx) {
 #pragma unroll
-        for (int k8 = 0; k8 < 4; ++k8) ah[k8] = __ldg(ih + k8);
-        if (p.aux_lo) {
-          const uint4* il = reinterpret_cast<const uint4*>(p.aux_lo + (long long)rr * p.ldaux + nc0);
-#pragma unroll
-          for (int k8 = 0; k8 < 4; ++k8) al[k8] = __ldg(il + k8);
-        } else {
-#pragma unroll
-          for (int k8 = 0; k8 < 4; ++k8) al[k8] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = 0; i < 4; ++i) {
+          const int row = min(rowbase + arow + 8 * i, p.M - 1);
+          ah[i] = __ldg(reinterpret_cast<const uint4*>(p.aux_hi + (long long)row * p.ldaux + ncx) + aseg);
+          al[i] = p.aux_lo ? __ldg(reinterpret_cast<const uint4*>(p.aux_lo + (long long)row * p.ldaux + ncx) + aseg)
+                           : make_uint4(0u, 0u, 0u, 0u);
         }
-      }
+      };
+      if (EPI == EPI_DY) aux_fetch(min(n0 + c_lo * 32, p.N - 32));
 #pragma unroll 1
       for (int c = c_lo; c < c_hi; ++c) {
         const int nc = n0 + c * 32;
@@ -696,10 +694,28 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
           }
           continue;
         } else {   // EPI_DY
+          const uint32_t ax = stg0 + 4096u;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r_ = arow + 8 * i;
+            const uint32_t a = ax + (uint32_t)r_ * 64u + (uint32_t)((aseg ^ ((r_ >> 1) & 3)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(ah[i].x), "r"(ah[i].y), "r"(ah[i].z), "r"(ah[i].w) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 2048u), "r"(al[i].x), "r"(al[i].y), "r"(al[i].z), "r"(al[i].w) : "memory");
+          }
+          __syncwarp();
+          uint4 yh[4], yl[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t a = ax + (uint32_t)lane * 64u + (uint32_t)((j ^ ((lane >> 1) & 3)) << 4);
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(yh[j].x), "=r"(yh[j].y), "=r"(yh[j].z), "=r"(yh[j].w) : "r"(a) : "memory");
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(yl[j].x), "=r"(yl[j].y), "=r"(yl[j].z), "=r"(yl[j].w) : "r"(a + 2048u) : "memory");
+          }
+          __syncwarp();
+          if (c + 1 < c_hi && nc + 32 < p.N) aux_fetch(nc + 32);   // next chunk's activation, in flight during the math
 #pragma unroll
           for (int k8 = 0; k8 < 4; ++k8) {
-            const uint4 h = ah[k8];
-            const uint4 l = al[k8];
+            const uint4 h = yh[k8];
+            const uint4 l = yl[k8];
             const float4 d0 = __ldg(reinterpret_cast<const float4*>(rv + nc) + 2 * k8);
             const float4 d1 = __ldg(reinterpret_cast<const float4*>(rv + nc) + 2 * k8 + 1);
             const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
@@ -712,16 +728,6 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
               const float g1 = (v[k + 1] + dd[2 * j + 1] * rs) * (1.0f - y1 * y1);
               v[k] = r_ok ? g0 : 0.0f;
               v[k + 1] = r_ok ? g1 : 0.0f;
-            }
-          }
-          if (c + 1 < c_hi && nc + 32 < p.N) {   // next chunk's activation
-            const uint4* ih = reinterpret_cast<const uint4*>(p.aux_hi + (long long)rr * p.ldaux + nc + 32);
-#pragma unroll
-            for (int k8 = 0; k8 < 4; ++k8) ah[k8] = __ldg(ih + k8);
-            if (p.aux_lo) {
-              const uint4* il = reinterpret_cast<const uint4*>(p.aux_lo + (long long)rr * p.ldaux + nc + 32);
-#pragma unroll
-              for (int k8 = 0; k8 < 4; ++k8) al[k8] = __ldg(il + k8);
             }
           }
           if (p.out_lo) {
@@ -1408,7 +1414,8 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   RtParams p;
   memset(&p, 0, sizeof(p));
   // work enqueued on the side stream shares the GPU with the critical chain: it gets rows_cta_cap SMs
-  const int sm_avail = (ctx->rows_cta_cap > 0 && ctx->rows_cta_cap < ctx->sm_count) ? ctx->rows_cta_cap : ctx->sm_count;
+  const int sm_avail = (ctx->rows_cta_cap > 0 && ctx->rows_cta_cap < ctx->sm_count) ? ctx->rows_cta_cap
+                       : (ctx->main_cta_cap > 0 && ctx->main_cta_cap < ctx->sm_count) ? ctx->main_cta_cap : ctx->sm_count;
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.a_mn = g.A.mn; p.b_mn = g.B.mn;
   p.x3 = g.A.lo ? 1 : 0;
@@ -1420,7 +1427,7 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
     BN = 256;
     // (split-K reductions keep 256-wide tiles unless the output is a thin [<= 256, N] slab: their SM fill comes from
     // the K split, and wide tiles re-read less of the A operand)
-    if (g.epi == EPI_LINEAR || g.epi == EPI_PLAIN || g.epi == EPI_LSTM || (g.epi == EPI_RED && p.tiles_m <= 2))
+    if (g.epi == EPI_LINEAR || g.epi == EPI_PLAIN || g.epi == EPI_LSTM || (g.epi == EPI_RED && p.tiles_m <= 2 && g.K < 8192))
       while (BN > 64 && (long long)p.tiles_m * ((g.N + BN - 1) / BN) < ctx->sm_count) BN >>= 1;
     while (BN > 64 && g.N <= BN / 2) BN >>= 1;
   }
@@ -1453,6 +1460,7 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   // products want many small stages in flight, the big ones four 48 KB stages)
   p.stg_warp = (g.epi == EPI_LINEAR && g.out_hi) ? 8192 : RT_STG_WARP;
   p.stage_bytes = (p.x3 ? 2 : 1) * (RT_BM + (p.cg2 ? BN / 2 : BN)) * p.BK * 2;
+  if (g.epi == EPI_DY) p.stg_warp = 8192;   // + a 32 x 64 B (hi, lo) scratch per warp: the saved activation is fetched coalesced
   p.stages = (RT_SMEM_BUDGET - 8 * p.stg_warp) / p.stage_bytes;
   if (p.stages > RT_MAXSTAGES) p.stages = RT_MAXSTAGES;
   const int tiles = (p.cg2 ? (p.tiles_m + 1) / 2 : p.tiles_m) * p.tiles_n;   // work items before any K split

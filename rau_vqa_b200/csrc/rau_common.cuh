@@ -87,10 +87,12 @@ struct rau_ctx {
   // side stream for the heavy image-side products that are off the recurrence's critical path (rau_step.cu): they run
   // on at most side_ctas SMs next to the chain of small dependent kernels.  RAU_OVERLAP=0 disables it.
   cudaStream_t side = nullptr;
+  cudaStream_t aux = nullptr;                      // short state-independent preparation (fills, masks) next to the encoder
   std::vector<cudaEvent_t> side_ev;
   int side_ev_next = 0;
   int side_ctas = 0;
   int side_ctas_fwd = 0;                           // the cap while the forward's state-independent products run
+  int main_cta_cap = 0;                            // > 0 while the side stream is in use: SMs the chain's split-K products size for
   int rows_cta_cap = 0;                            // > 0 while work is being enqueued on the side stream
   // RAU_PHASES=1: eager steps with an event at every phase boundary; rau_phase_report() prints the split
   int phases = -1;

@@ -863,8 +863,39 @@ int rau_rows_gemm_time(rau_ctx* ctx, int M, int N, int K, int a_mn, int b_mn, in
   RAU_TRY(rows_pack(ctx, A, na, x3, false, "gt.A", &g.A.hi, &g.A.lo));
   RAU_TRY(rows_pack(ctx, B, nb, x3, false, "gt.B", &g.B.hi, &g.B.lo));
   g.A.mn = a_mn; g.A.ld = lda; g.B.mn = b_mn; g.B.ld = ldb;
-  g.epi = reduce ? ROWS_EPI_RED : ROWS_EPI_PLAIN;
+  g.epi = reduce == 1 ? ROWS_EPI_RED : ROWS_EPI_PLAIN;
   g.out_f = D; g.ldo = (N + 3) / 4 * 4;
+  // reduce = 2 / 3: the hop backward's dY epilogue (with / without the bias-gradient column sums), 4: the tanh epilogue;
+  // RAU_TIME_CAP limits the CTAs like the side stream's cap does
+  if (reduce >= 2) {
+    RAU_REQUIRE(N % 32 == 0 && M % 196 == 0, "rau_rows_gemm_time: epilogue variants need N %% 32 == 0 and M %% 196 == 0");
+    bf16 *aux = nullptr, *outp = nullptr;
+    float *rv = nullptr, *rs = nullptr, *cs = nullptr;
+    const size_t mn = (size_t)M * N;
+    RAU_TRY(ctx->arena.get("gt.aux", sizeof(bf16) * 2 * mn, (void**)&aux));
+    RAU_TRY(ctx->arena.get("gt.outp", sizeof(bf16) * 2 * mn, (void**)&outp));
+    RAU_TRY(ctx->arena.get("gt.rv", sizeof(float) * (size_t)(M / 196) * N, (void**)&rv));
+    RAU_TRY(ctx->arena.get("gt.rs", sizeof(float) * (size_t)M, (void**)&rs));
+    RAU_TRY(ctx->arena.get("gt.cs", sizeof(float) * (size_t)N, (void**)&cs));
+    RAU_CHECK_CUDA(cudaMemsetAsync(aux, 0, sizeof(bf16) * 2 * mn, ctx->stream));
+    RAU_TRY(k_fill(ctx, rv, (int64_t)(M / 196) * N, 0.5f));
+    RAU_TRY(k_fill(ctx, rs, M, 0.25f));
+    RAU_TRY(k_fill(ctx, cs, N, 0.0f));
+    g.out_f = nullptr;
+    g.out_hi = outp; g.out_lo = x3 ? outp + mn : nullptr; g.ldo = N;
+    if (reduce == 4) {
+      g.epi = ROWS_EPI_TANH; g.bias = cs;
+    } else {
+      g.epi = ROWS_EPI_DY; g.rowvec = rv; g.rowscale = rs; g.S = 196;
+      g.aux_hi = aux; g.aux_lo = x3 ? aux + mn : nullptr; g.ldaux = N;
+      g.colsum = reduce == 2 ? cs : nullptr;
+    }
+  }
+  {
+    const char* e = getenv("RAU_TIME_CAP");
+    ctx->rows_cta_cap = e ? atoi(e) : 0;
+  }
+  struct CapReset { rau_ctx* c; ~CapReset() { c->rows_cta_cap = 0; } } cap_reset{ctx};
   RAU_TRY(rows_gemm(ctx, g));   // warm-up (function attributes, arena)
   RAU_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
   // the launches go into one CUDA graph so that the host's launch cost does not bound the measurement

@@ -5,7 +5,9 @@
 #include "rau_common.cuh"
 
 // ---- dropout masks (packed keep bits, bit i of word i>>5)
-int k_mask_gen(rau_ctx* ctx, uint32_t* bits, int64_t n, float p, uint64_t seed, uint64_t stream_id);
+// nHop > 1: the masks of hops 0..nHop-1 in one launch (stream ids stream_id ^ hop, bit words hop_stride apart)
+int k_mask_gen(rau_ctx* ctx, uint32_t* bits, int64_t n, float p, uint64_t seed, uint64_t stream_id, int nHop = 1,
+               int64_t hop_stride = 0);
 int k_mask_pack(rau_ctx* ctx, uint32_t* bits, const uint8_t* bytes, int64_t n);
 static inline int64_t mask_words(int64_t n) { return (n + 31) / 32 + 4; }
 

@@ -378,6 +378,21 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     if (ctx->side_ctas_fwd < 8 || ctx->side_ctas_fwd > ctx->sm_count) ctx->side_ctas_fwd = ctx->sm_count;
   }
   ctx->side_ev_next = 0;
+  {
+    // the chain's split-K products size themselves for the SMs the side stream leaves free (one wave, not two)
+    static int mc = -1;
+    if (mc < 0) { const char* e = getenv("RAU_MAIN_CTAS"); mc = e ? atoi(e) : 0; }
+    const int auto_cap = ctx->sm_count - ctx->side_ctas >= 32 ? ctx->sm_count - ctx->side_ctas : 0;
+    ctx->main_cta_cap = (ov_bwd || ov_fwd) ? (mc > 0 ? mc : auto_cap) : 0;
+  }
+  struct CapGuard { rau_ctx* c; ~CapGuard() { c->main_cta_cap = 0; } } cap_guard{ctx};
+  // the side stream's forward work (feature packs, i_embed, Z) needs nothing the chain enqueues below: it forks here
+  cudaEvent_t fork0 = nullptr;
+  if (ov_fwd) {
+    fork0 = rau_side_event(ctx);
+    RAU_REQUIRE(fork0 != nullptr, "cudaEventCreate failed");
+    RAU_CHECK_CUDA(cudaEventRecord(fork0, ctx->stream));
+  }
   bool side_used = false;
   Encoder en;
   RAU_TRY(encoder_alloc(ctx, cfg, B, &en));
@@ -399,6 +414,15 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   float* ans = (out && out->answers) ? out->answers : ans_own;
   float* loss = (out && out->loss) ? out->loss : loss_own;
   float* loss_dp = (out && out->loss_do_pred) ? out->loss_do_pred : loss_own + nHop + 2;
+  // zero fills and the hops' dropout masks feed nothing before the first hop: they run on the aux stream next to the
+  // encoder (joined after it)
+  cudaStream_t prep_chain = ctx->stream;
+  const bool prep_aux = fork0 != nullptr && ctx->aux != nullptr;
+  if (prep_aux) {
+    RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->aux, fork0, 0));
+    ctx->stream = ctx->aux;
+  }
+  struct StreamGuard { rau_ctx* c; cudaStream_t s; ~StreamGuard() { if (c->stream == c->aux) c->stream = s; } } prep_guard{ctx, prep_chain};
   RAU_TRY(k_fill(ctx, c_all, (int64_t)B * H, 0.0f));   // F:362-364
   RAU_TRY(k_fill(ctx, h_all, (int64_t)B * H, 0.0f));
   RAU_TRY(k_fill(ctx, loss, nHop + 2, 0.0f));
@@ -448,6 +472,16 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   }
   std::vector<HopSaved> sv(nHop);
   std::vector<HopAsync> as(nHop);
+  // drawn masks (no host-provided ones): the q and m keep bits of all hops come from one launch each
+  const bool batched_masks = train && masks == nullptr && nHop < 65536;
+  if (batched_masks) {
+    HopSaved s0;
+    hop_saved_layout(cfg, B, sv_base, &s0);
+    if (cfg->p_q > 0)
+      RAU_TRY(k_mask_gen(ctx, s0.qbits, (int64_t)B * Q, cfg->p_q, ctx->seed, stream_of(step_t, SK_Q, 0, rank), nHop, (int64_t)(sv_bytes / 4)));
+    if (cfg->p_m > 0)
+      RAU_TRY(k_mask_gen(ctx, s0.mbits, (int64_t)B * cfg->M, cfg->p_m, ctx->seed, stream_of(step_t, SK_M, 0, rank), nHop, (int64_t)(sv_bytes / 4)));
+  }
   for (int hp = 0; hp < nHop; ++hp) {
     hop_saved_layout(cfg, B, sv_base + sv_bytes * hp, &sv[hp]);
     as[hp].hop = hp;
@@ -463,11 +497,13 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     sv[hp].hout = h_all + (size_t)(hp + 1) * B * H;
     sv[hp].dop = dop + (size_t)hp * B;
     sv[hp].m = st_m + (size_t)hp * B * M_;
-    RAU_TRY(rau_prepare_mask(ctx, sv[hp].qbits, (int64_t)B * Q, cfg->p_q, train,
-                             masks && masks->q ? masks->q + (size_t)hp * B * Q : nullptr, stream_of(step_t, SK_Q, hp, rank)));
-    RAU_TRY(rau_prepare_mask(ctx, sv[hp].mbits, (int64_t)B * cfg->M, cfg->p_m, train,
-                             masks && masks->m ? masks->m + (size_t)hp * B * cfg->M : nullptr,
-                             stream_of(step_t, SK_M, hp, rank)));
+    if (!batched_masks) {
+      RAU_TRY(rau_prepare_mask(ctx, sv[hp].qbits, (int64_t)B * Q, cfg->p_q, train,
+                               masks && masks->q ? masks->q + (size_t)hp * B * Q : nullptr, stream_of(step_t, SK_Q, hp, rank)));
+      RAU_TRY(rau_prepare_mask(ctx, sv[hp].mbits, (int64_t)B * cfg->M, cfg->p_m, train,
+                               masks && masks->m ? masks->m + (size_t)hp * B * cfg->M : nullptr,
+                               stream_of(step_t, SK_M, hp, rank)));
+    }
     if (hop_rows_path(ctx, cfg) && !(masks && masks->x)) {   // drawn inline by the rows pack kernel
       sv[hp].x_philox = 1;
       sv[hp].x_stream = stream_of(step_t, SK_X, hp, rank);
@@ -477,12 +513,25 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
                                stream_of(step_t, SK_X, hp, rank)));
     }
   }
+  cudaEvent_t prep_done = nullptr;
+  if (prep_aux) {
+    prep_done = rau_side_event(ctx);
+    RAU_REQUIRE(prep_done != nullptr, "cudaEventCreate failed");
+    RAU_CHECK_CUDA(cudaEventRecord(prep_done, ctx->aux));
+    ctx->stream = prep_chain;
+  }
   if (ov_fwd) {
     // the i_embed product of every hop depends on the features only: all of them go to the side stream now and run
     // next to the encoder unroll and the hops' chains; each hop waits for its own event before it reads I
-    cudaEvent_t fork = rau_side_event(ctx);
-    RAU_REQUIRE(fork != nullptr, "cudaEventCreate failed");
-    RAU_CHECK_CUDA(cudaEventRecord(fork, ctx->stream));
+    bool early = fork0 != nullptr;   // (materialised feature masks are written on the chain: fork after them)
+    for (int hp = 0; hp < nHop; ++hp) early = early && (sv[hp].x_philox || !(train && cfg->p_x > 0));
+    cudaEvent_t fork = fork0;
+    if (!early) {
+      if (prep_done) RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->side, prep_done, 0));   // the materialised masks
+      fork = rau_side_event(ctx);
+      RAU_REQUIRE(fork != nullptr, "cudaEventCreate failed");
+      RAU_CHECK_CUDA(cudaEventRecord(fork, ctx->stream));
+    }
     RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->side, fork, 0));
     cudaStream_t chain = ctx->stream;
     ctx->stream = ctx->side;
@@ -502,6 +551,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     side_used = true;
   }
   RAU_TRY(encoder_forward(ctx, cfg, bt, params[0], params[1], train, masks, step_t, &en));
+  if (prep_done) RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, prep_done, 0));
   rau_phase_mark(ctx, "encoder forward");
   // Everything of the unroll that depends on the encoder state only is hoisted out of the per-hop chains: the q dropout
   // of every hop (one launch) and Wq drop_h(q) + bq of every hop (one [nHop*B, Q] x [Q, M] product).
