@@ -477,6 +477,37 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
     uint8_t* stg_p = staging + (size_t)(warp - 2) * p.stg_warp;
     const uint32_t stg0 = smem_u32(stg_p), stg1 = stg0 + 2048u;
     uint32_t li = 0;
+    // EPI_DY operand prefetch (registers, filled one chunk / one item ahead): ah/al = the saved activation of the next
+    // chunk, fetched COALESCED (a lane reads 16 bytes of row lane/4 + 8i: one instruction covers 8 rows x 64 B instead of
+    // 32 rows x 16 B, 8x fewer L1 wavefronts than a lane-per-row fetch; the warp's scratch then hands every lane its own
+    // row); rvp = this warp's slice of the per-image row vector for the (at most two) images its 32 rows belong to
+    uint4 ah[4], al[4];
+    float4 rvp[2];
+    bool dy_ready = false;
+    const int arow = lane >> 2, aseg = lane & 3;
+    const int ncols_w = p.BN / 2;   // accumulator columns of this warp
+    auto aux_fetch = [&](int rowbase_x, int ncx) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = min(rowbase_x + arow + 8 * i, p.M - 1);
+        ah[i] = __ldg(reinterpret_cast<const uint4*>(p.aux_hi + (long long)row * p.ldaux + ncx) + aseg);
+        al[i] = p.aux_lo ? __ldg(reinterpret_cast<const uint4*>(p.aux_lo + (long long)row * p.ldaux + ncx) + aseg)
+                         : make_uint4(0u, 0u, 0u, 0u);
+      }
+    };
+    auto rv_fetch = [&](int rowbase_x, int nbase) {
+      const int b0 = min(rowbase_x, p.M - 1) / p.S, b1 = min(rowbase_x + 31, p.M - 1) / p.S;
+      const int per = ncols_w >> 2;   // float4 per image
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int idx = lane + 32 * j;
+        rvp[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < 2 * per) {
+          const int col = min(nbase + (idx % per) * 4, p.N - 4);
+          rvp[j] = __ldg(reinterpret_cast<const float4*>(p.rowvec + (long long)(idx < per ? b0 : b1) * p.N + col));
+        }
+      }
+    };
     for (int item = worker; item < items; item += nworkers, ++li) {
       const int tile = item / p.ksplit;
       const int tn = tile % p.tiles_n, tm = tile / p.tiles_n;
@@ -497,21 +528,26 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
       if (EPI == EPI_DY) rs = p.rowscale[rr];
       const int c_lo = half * (p.BN / 64), c_hi = c_lo + p.BN / 64;
       bool released = false;
-      // EPI_DY: the saved activation (1 - y^2 factor) of a chunk is fetched one chunk ahead and COALESCED: a lane reads
-      // 16 bytes of row (lane/4 + 8i), so one instruction covers 8 rows x 64 B instead of 32 rows x 16 B (8x fewer L1
-      // wavefronts than a lane-per-row fetch); the warp's scratch then hands every lane its own row
-      uint4 ah[4], al[4];
-      const int arow = lane >> 2, aseg = lane & 3;
-      auto aux_fetch = [&](int ncx) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int row = min(rowbase + arow + 8 * i, p.M - 1);
-          ah[i] = __ldg(reinterpret_cast<const uint4*>(p.aux_hi + (long long)row * p.ldaux + ncx) + aseg);
-          al[i] = p.aux_lo ? __ldg(reinterpret_cast<const uint4*>(p.aux_lo + (long long)row * p.ldaux + ncx) + aseg)
-                           : make_uint4(0u, 0u, 0u, 0u);
+      uint32_t rv_s = 0;
+      if (EPI == EPI_DY && n0 + c_lo * 32 >= p.N) dy_ready = false;   // (no columns for this warp: nothing consumes the prefetch)
+      else if (EPI == EPI_DY) {
+        if (!dy_ready) {   // first item of this CTA: nothing was prefetched
+          aux_fetch(rowbase, min(n0 + c_lo * 32, p.N - 32));
+          rv_fetch(rowbase, n0 + c_lo * 32);
         }
-      };
-      if (EPI == EPI_DY) aux_fetch(min(n0 + c_lo * 32, p.N - 32));
+        // row vector slice -> scratch [2 images][ncols_w] (after the previous item's readers are done with it)
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int idx = lane + 32 * j;
+          if (idx < 2 * (ncols_w >> 2))
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg0 + 8192u + (uint32_t)idx * 16u), "f"(rvp[j].x),
+                         "f"(rvp[j].y), "f"(rvp[j].z), "f"(rvp[j].w) : "memory");
+        }
+        __syncwarp();
+        const int b0 = min(rowbase, p.M - 1) / p.S;
+        rv_s = stg0 + 8192u + (uint32_t)((rr / p.S == b0) ? 0 : ncols_w * 4);
+      }
 #pragma unroll 1
       for (int c = c_lo; c < c_hi; ++c) {
         const int nc = n0 + c * 32;
@@ -703,21 +739,31 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 2048u), "r"(al[i].x), "r"(al[i].y), "r"(al[i].z), "r"(al[i].w) : "memory");
           }
           __syncwarp();
-          uint4 yh[4], yl[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t a = ax + (uint32_t)lane * 64u + (uint32_t)((j ^ ((lane >> 1) & 3)) << 4);
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(yh[j].x), "=r"(yh[j].y), "=r"(yh[j].z), "=r"(yh[j].w) : "r"(a) : "memory");
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(yl[j].x), "=r"(yl[j].y), "=r"(yl[j].z), "=r"(yl[j].w) : "r"(a + 2048u) : "memory");
+          // the registers are free again: next chunk's activation (or the next item's first chunk and row-vector slice)
+          // is in flight during the math below
+          if (c + 1 < c_hi && nc + 32 < p.N) {
+            aux_fetch(rowbase, nc + 32);
+          } else {
+            const int item2 = item + nworkers;
+            dy_ready = item2 < items;
+            if (dy_ready) {
+              const int tile2 = item2 / p.ksplit;
+              const int tn2 = tile2 % p.tiles_n, tm2 = tile2 / p.tiles_n;
+              const int rb2 = (CG2 ? tm2 * 2 * RT_BM + (int)cta_rank * RT_BM : tm2 * RT_BM) + q * 32;
+              aux_fetch(rb2, min(tn2 * p.BN + c_lo * 32, p.N - 32));
+              rv_fetch(rb2, tn2 * p.BN + c_lo * 32);
+            }
           }
-          __syncwarp();
-          if (c + 1 < c_hi && nc + 32 < p.N) aux_fetch(nc + 32);   // next chunk's activation, in flight during the math
 #pragma unroll
-          for (int k8 = 0; k8 < 4; ++k8) {
-            const uint4 h = yh[k8];
-            const uint4 l = yl[k8];
-            const float4 d0 = __ldg(reinterpret_cast<const float4*>(rv + nc) + 2 * k8);
-            const float4 d1 = __ldg(reinterpret_cast<const float4*>(rv + nc) + 2 * k8 + 1);
+          for (int k8 = 0; k8 < 4; ++k8) {   // 8 columns per pass: own row's activation and the row-vector slice from smem
+            uint4 h, l;
+            float4 d0, d1;
+            const uint32_t ya = ax + (uint32_t)lane * 64u + (uint32_t)((k8 ^ ((lane >> 1) & 3)) << 4);
+            const uint32_t da = rv_s + (uint32_t)((c - c_lo) * 128 + k8 * 32);
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w) : "r"(ya) : "memory");
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(l.x), "=r"(l.y), "=r"(l.z), "=r"(l.w) : "r"(ya + 2048u) : "memory");
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(d0.x), "=f"(d0.y), "=f"(d0.z), "=f"(d0.w) : "r"(da) : "memory");
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(d1.x), "=f"(d1.y), "=f"(d1.z), "=f"(d1.w) : "r"(da + 16u) : "memory");
             const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
             const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
@@ -730,6 +776,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
               v[k + 1] = r_ok ? g1 : 0.0f;
             }
           }
+          __syncwarp();   // every lane has read its row before the next chunk overwrites the scratch
           if (p.out_lo) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) split_pair(v[2 * k], v[2 * k + 1], w0[k], w0[16 + k]);
@@ -1460,7 +1507,7 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   // products want many small stages in flight, the big ones four 48 KB stages)
   p.stg_warp = (g.epi == EPI_LINEAR && g.out_hi) ? 8192 : RT_STG_WARP;
   p.stage_bytes = (p.x3 ? 2 : 1) * (RT_BM + (p.cg2 ? BN / 2 : BN)) * p.BK * 2;
-  if (g.epi == EPI_DY) p.stg_warp = 8192;   // + a 32 x 64 B (hi, lo) scratch per warp: the saved activation is fetched coalesced
+  if (g.epi == EPI_DY) p.stg_warp = 9216;   // + a 32 x 64 B (hi, lo) scratch per warp (the saved activation is fetched coalesced) + 1 KB row vector
   p.stages = (RT_SMEM_BUDGET - 8 * p.stg_warp) / p.stage_bytes;
   if (p.stages > RT_MAXSTAGES) p.stages = RT_MAXSTAGES;
   const int tiles = (p.cg2 ? (p.tiles_m + 1) / 2 : p.tiles_m) * p.tiles_n;   // work items before any K split
