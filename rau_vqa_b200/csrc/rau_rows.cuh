@@ -70,6 +70,19 @@ struct LstmSeq {
 };
 int rows_lstm_seq(rau_ctx* ctx, const LstmSeq& d, int* done);
 
+// the backward recurrence of one encoder LSTM layer, t = T..1, in a single persistent launch (lstm_seq_bwd_kernel);
+// gate chunks in the order i, f, o, g (RAU_GATES_IFOG)
+struct LstmSeqBwd {
+  int B = 0, H = 0, T = 0;
+  const bf16* Wh_hi = nullptr; const bf16* Wh_lo = nullptr; int64_t ldwh = 0;   // rows_pack2d layout [4H, H]
+  const float* lengths = nullptr; const float* dq_c = nullptr; const float* dq_h = nullptr; int lddq = 0;
+  const float* dh_extra = nullptr;                                              // [T][B][H] or NULL
+  const float* c_prev = nullptr; int64_t s_t = 0; int lds = 0;                  // c of step 0, step stride, pitch
+  const float* saved = nullptr;                                                 // saved gates of step 1, [T][5][B][H]
+  float* dG = nullptr; bf16* dG_hi = nullptr; bf16* dG_lo = nullptr;            // [T][B][4H]
+};
+int rows_lstm_seq_bwd(rau_ctx* ctx, const LstmSeqBwd& d, int* done);
+
 // logit[r] = ws . tanh(Z[r,:] + qadd[b(r),:])  (Z = I Wa^T precomputed; qadd = Wqa qf + bqa + ba)
 int k_attn_rows_score(rau_ctx* ctx, int B, int A, int S, const float* Z, const float* qadd, const float* ws, int fast_tanh,
                       float* logit);

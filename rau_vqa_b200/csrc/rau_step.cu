@@ -212,7 +212,19 @@ static int encoder_backward(rau_ctx* ctx, const rau_config* cfg, const rau_batch
       const int in = layer == 0 ? E : Hq;
       RAU_TRY(rows_pack2d(ctx, Pr + L[layer].Wh, Hq, G4, Hq, x3, true, nullptr, &Wh_h, &Wh_l, &ldwh));
       RAU_TRY(rows_pack2d(ctx, Pr + L[layer].Wi, in, G4, in, x3, true, nullptr, &Wi_h, &Wi_l, &ldwi));
-      for (int t = Tm; t >= 1; --t) {
+      int seq_done = 0;
+      {   // the whole backward recurrence in one persistent launch when the layer fits
+        LstmSeqBwd d;
+        d.B = B; d.H = Hq; d.T = Tm;
+        d.Wh_hi = Wh_h; d.Wh_lo = Wh_l; d.ldwh = ldwh;
+        d.lengths = bt->lengths; d.dq_c = dq + 2 * layer * Hq; d.dq_h = dq + (2 * layer + 1) * Hq; d.lddq = Q;
+        d.dh_extra = layer == 0 ? du2 : nullptr;
+        d.c_prev = en->S_all + 2 * layer * Hq; d.s_t = (int64_t)B * Q; d.lds = Q;
+        d.saved = layer == 1 ? en->sav2 : en->sav1;
+        d.dG = dG; d.dG_hi = dG_hi; d.dG_lo = dG_lo;
+        RAU_TRY(rows_lstm_seq_bwd(ctx, d, &seq_done));
+      }
+      for (int t = Tm; t >= 1 && !seq_done; --t) {
         const bool last = t == Tm;
         const float* Sp_ = en->S_all + (size_t)(t - 1) * B * Q + 2 * layer * Hq;
         float* dH = dHb[t & 1];            // written by step t+1's dgrad
