@@ -1915,15 +1915,17 @@ int k_attn_rows_score(rau_ctx* ctx, int B, int A, int S, const float* Z, const f
 
 int k_attn_rows_bwd(rau_ctx* ctx, int B, int M, int A, int S, const float* E, const bf16* I_hi, const bf16* I_lo, const float* ws,
                     const float* p, const float* dp_in, const float* da, float* ds, bf16* dZ_hi, bf16* dZ_lo, float* dqa,
-                    float* gws_part, bf16* ds_hi, bf16* ds_lo, int ldds, const float* qadd, int fast_tanh) {
+                    float* gws_part, bf16* ds_hi, bf16* ds_lo, int ldds, const float* qadd, int fast_tanh, int acc_zeroed) {
   RAU_REQUIRE(M % 8 == 0 && S <= 256 && ldds <= 256 && (A == 64 || A == 128 || A == 256), "k_attn_rows_bwd: M=%d A=%d S=%d", M, A, S);
   const int R = B * S;
   float* dp = nullptr;
   RAU_TRY(ctx->arena.get("attn.dp", sizeof(float) * (size_t)R, (void**)&dp));
   RAU_LAUNCH_PDL(ctx->stream, (attn_rows_dp_kernel), (R + 7) / 8, 256, 0, R, S, M, I_hi, I_lo, da, dp_in, dp);
   RAU_LAUNCH_CHECK(ctx);
-  RAU_CHECK_CUDA(cudaMemsetAsync(dqa, 0, sizeof(float) * (size_t)B * A, ctx->stream));
-  RAU_CHECK_CUDA(cudaMemsetAsync(gws_part, 0, sizeof(float) * (size_t)B * A, ctx->stream));
+  if (!acc_zeroed) {
+    RAU_CHECK_CUDA(cudaMemsetAsync(dqa, 0, sizeof(float) * (size_t)B * A, ctx->stream));
+    RAU_CHECK_CUDA(cudaMemsetAsync(gws_part, 0, sizeof(float) * (size_t)B * A, ctx->stream));
+  }
   const int nsl = B >= 128 ? 4 : (B >= 32 ? 8 : 16);   // row slices per image: ~1000 CTAs
   if (!qadd)
     RAU_LAUNCH_PDL(ctx->stream, (attn_rows_dz_kernel<0>), dim3(B, nsl), 256, 0, S, A, E, qadd, ws, p, dp, ds, dZ_hi, dZ_lo, dqa,

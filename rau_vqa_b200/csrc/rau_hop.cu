@@ -424,7 +424,8 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   const int R = B * S;
   if (rows)
     RAU_TRY(k_attn_rows_bwd(ctx, B, M, A, S, sv.E, sv.I_hi, x3 ? sv.I_lo : nullptr, P.ws, sv.p, dp, dj, ds, dZ_hi, dZ_lo, dqa, gwsp,
-                            ds_pk.hi, x3 ? ds_pk.lo : nullptr, (int)ds_pk.ld, sv.qatt, x3 ? 0 : 1));
+                            ds_pk.hi, x3 ? ds_pk.lo : nullptr, (int)ds_pk.ld, sv.qatt, x3 ? 0 : 1,
+                            deferred ? deferred->acc_zeroed : 0));
   else
     RAU_TRY(k_attn_bwd<float>(ctx, B, M, A, S, Sp, sv.E, sv.I, P.ws, sv.p, dp, dj, ds, nullptr, 0, dZ, dqa, nullptr, gwsp,
                               dZ_hi, dZ_lo));

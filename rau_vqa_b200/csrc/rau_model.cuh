@@ -91,6 +91,7 @@ struct HopGrads {
   // dh2h = Wo^T du are computed for all hops in two products before the backward unroll; likewise dq is formed once
   // after it from the stacked dpre.  Non-NULL dh2h switches hop_backward to that form.
   const float* dh2h = nullptr;
+  int acc_zeroed = 0;   // dqa / gwsp (atomic accumulators of the attention backward) were cleared for all hops at once
 };
 struct HopStacks {   // every member is [nHop][B][dim]
   const float *dscore, *m, *du, *hout, *dG, *j, *h_in, *dj, *p, *ds, *dqa, *qf, *dpre, *qd, *gwsp;

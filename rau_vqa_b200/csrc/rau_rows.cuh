@@ -89,4 +89,4 @@ int k_attn_rows_score(rau_ctx* ctx, int B, int A, int S, const float* Z, const f
 int k_attn_rows_bwd(rau_ctx* ctx, int B, int M, int A, int S, const float* E, const bf16* I_hi, const bf16* I_lo, const float* ws,
                     const float* p, const float* dp_in, const float* da, float* ds, bf16* dZ_hi, bf16* dZ_lo, float* dqa,
                     float* gws_part, bf16* ds_hi = nullptr, bf16* ds_lo = nullptr, int ldds = 0,
-                    const float* qadd = nullptr, int fast_tanh = 0);
+                    const float* qadd = nullptr, int fast_tanh = 0, int acc_zeroed = 0);

@@ -178,7 +178,7 @@ static int encoder_forward(rau_ctx* ctx, const rau_config* cfg, const rau_batch*
 
 // F:600-615 with dq = sum over hops of the answering units' gradient w.r.t. rnn_out (branch:backward, F:598)
 static int encoder_backward(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, const float* Pr, float* gE,
-                            float* gR, int train, const Encoder* en, const float* dq) {
+                            float* gR, int train, const Encoder* en, const float* dq, bool side_ok = false) {
   const int B = bt->B, Hq = cfg->Hq, E = cfg->embed, Q = 4 * Hq, G4 = 4 * Hq, Tm = en->Tm;
   RnnLayerOff L[4];
   rnn_offsets(cfg, L);
@@ -254,7 +254,19 @@ static int encoder_backward(rau_ctx* ctx, const rau_config* cfg, const rau_batch
       }
       if (layer == 1)
         RAU_TRY(k_dropout_bwd_acc(ctx, du2, (int64_t)R * Hq, dr ? en->rbits : nullptr, drop_scale(cfg->p_rnn), du2, 0));
-      // weight gradients over all R = Tm*B rows: gWi += dG^T x, gWh += dG^T h_{t-1} (packed operands of the forward pass)
+      // weight gradients over all R = Tm*B rows: gWi += dG^T x, gWh += dG^T h_{t-1} (packed operands of the forward pass).
+      // Nothing on the chain reads them: in the training step they go to the side stream (joined by the caller).
+      cudaStream_t chain = ctx->stream;
+      const bool wg_side = side_ok && ctx->side != nullptr;
+      if (wg_side) {
+        cudaEvent_t ev = rau_side_event(ctx);
+        RAU_REQUIRE(ev != nullptr, "cudaEventCreate failed");
+        RAU_CHECK_CUDA(cudaEventRecord(ev, chain));
+        RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->side, ev, 0));
+        ctx->stream = ctx->side;
+        ctx->rows_cta_cap = ctx->side_ctas;
+      }
+      struct Back { rau_ctx* c; cudaStream_t s; ~Back() { c->stream = s; c->rows_cta_cap = 0; } } back{ctx, chain};
       const bf16* x_h = nullptr;
       const int64_t ldx = (in + 7) / 8 * 8;
       const size_t xhalf = ((size_t)R * ldx * sizeof(bf16) + 1023) / 1024 * 1024;
@@ -271,6 +283,7 @@ static int encoder_backward(rau_ctx* ctx, const rau_config* cfg, const rau_batch
         RAU_TRY(rows_gemm(ctx, g));
       }
       RAU_TRY(k_colsum(ctx, dG, R, G4, G4, gR + L[layer].bi, 1, gR + L[layer].bh));
+      if (wg_side && ctx->phases == 2) rau_phase_mark(ctx, "enc layer weight gradients done");
     }
     RAU_TRY(k_embed_bwd(ctx, bt->tokens, Tm * B, E, cfg->V, en->e_all, de ? en->ebits : nullptr, drop_scale(cfg->p_embed),
                         de_all, E, gE));
@@ -627,6 +640,9 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     g2.Ar_hi = pk_du.hi; g2.Ar_lo = pk_du.lo; g2.Ar_ld = pk_du.ld;
     RAU_TRY(rau_contract(ctx, g2));
   }
+  // the attention backward's atomic accumulators of every hop, cleared at once (not two memsets inside every hop's chain)
+  RAU_CHECK_CUDA(cudaMemsetAsync(st_dqa, 0, sizeof(float) * (size_t)nHop * B * A_, ctx->stream));
+  RAU_CHECK_CUDA(cudaMemsetAsync(st_gwsp, 0, sizeof(float) * (size_t)nHop * B * A_, ctx->stream));
   for (int hp = nHop - 1; hp >= 0; --hp) {
     const bool last = hp == nHop - 1;
     const float* dc_in = last ? nullptr : dcs + (size_t)((hp + 1) & 1) * B * H;
@@ -638,6 +654,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     hg.dscore_pk = slice(pk_dscore, (size_t)hp * B); hg.du_pk = slice(pk_du, (size_t)hp * B); hg.dG_pk = slice(pk_dG, (size_t)hp * B);
     hg.ds_pk = slice(pk_ds, (size_t)hp * B); hg.dpre_pk = slice(pk_dpre, (size_t)hp * B);
     hg.dh2h = st_dh2h + (size_t)hp * B * H;
+    hg.acc_zeroed = 1;
     RAU_TRY(hop_backward(ctx, cfg, B, P, G, bt->feats, c_all + (size_t)hp * B * H, h_all + (size_t)hp * B * H, train, sv[hp],
                          dscore + (size_t)hp * B * N, nullptr, nullptr, dc_in, dh_in, dq, last ? 0 : 1, nullptr,
                          dcs + (size_t)(hp & 1) * B * H, dhs + (size_t)(hp & 1) * B * H, &hg, &as[hp]));
@@ -683,7 +700,8 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     }
   }
   rau_phase_mark(ctx, "unit weight gradients");
-  RAU_TRY(encoder_backward(ctx, cfg, bt, params[1], grads[0], grads[1], train, &en, dq));
+  RAU_TRY(encoder_backward(ctx, cfg, bt, params[1], grads[0], grads[1], train, &en, dq, ov_bwd));
+  if (ov_bwd) side_used = true;
   if (ctx->phases == 2) rau_phase_mark(ctx, "encoder backward chain done");
   if (side_used) {   // join: the side stream's gradients (gWi, gWa, gbi) are complete before anything downstream
     cudaEvent_t join = rau_side_event(ctx);
