@@ -1012,6 +1012,56 @@ __global__ void __launch_bounds__(256) xprep_rows_kernel(const float* __restrict
 }
 
 // dXr [B*S, C] fp32 -> dX [B, C, S] = dXr^T * keep * scale  (backward of the feature dropout, F:239)
+// The same pack for ALL hops of the training step in one launch: every hop drops out the SAME features with its own
+// Philox stream (stream id ^ hop), so the fp32 tile is read and transposed once and written nHop times (hop h's arrays are
+// hop_stride elements after hop 0's).  Identical bits to nHop launches of xprep_rows_kernel.
+__global__ void __launch_bounds__(256) xprep_rows_hops_kernel(const float* __restrict__ X, float scale, int C, int S, int nHop,
+                                                              bf16* __restrict__ hi, bf16* __restrict__ lo, long long hop_stride,
+                                                              uint32_t thresh, uint2 key, uint32_t stream_lo, uint32_t stream_hi,
+                                                              const StepState* __restrict__ ss) {
+  RAU_PDL_ENTRY();
+  extern __shared__ float sT[];   // [S][66]
+  const int b = blockIdx.y, c0 = blockIdx.x * 64;
+  const int S4 = S >> 2;
+  if (ss) {
+    const unsigned long long sid = (((unsigned long long)stream_hi << 32) | stream_lo) ^ (ss->step << 24);
+    stream_lo = (uint32_t)sid;
+    stream_hi = (uint32_t)(sid >> 32);
+  }
+  for (int i = threadIdx.x; i < 64 * S4; i += 256) {
+    const int c = i / S4, s4 = i - c * S4;
+    const float4 t = __ldg(reinterpret_cast<const float4*>(X + ((int64_t)b * C + c0 + c) * S + 4 * s4));
+    float* d = sT + (4 * s4) * 66 + c;
+    d[0] = t.x; d[66] = t.y; d[132] = t.z; d[198] = t.w;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // a lane owns channels 2*lane, 2*lane+1; one Philox call covers 4 consecutive grid cells of one channel
+  const uint64_t e0 = ((uint64_t)b * C + c0 + 2 * lane) * (uint64_t)S, e1 = e0 + (uint64_t)S;
+  for (int s4 = warp; s4 < S4; s4 += 8) {
+    float2 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const float2*>(sT + (4 * s4 + k) * 66 + 2 * lane);
+    const uint64_t ct0 = (e0 + 4 * s4) >> 2, ct1 = (e1 + 4 * s4) >> 2;
+    for (int h = 0; h < nHop; ++h) {
+      const uint4 r0 = philox4x32(make_uint4((uint32_t)ct0, (uint32_t)(ct0 >> 32), stream_lo ^ (uint32_t)h, stream_hi), key);
+      const uint4 r1 = philox4x32(make_uint4((uint32_t)ct1, (uint32_t)(ct1 >> 32), stream_lo ^ (uint32_t)h, stream_hi), key);
+      const uint32_t q0[4] = {r0.x, r0.y, r0.z, r0.w}, q1[4] = {r1.x, r1.y, r1.z, r1.w};
+      uint32_t* ph = reinterpret_cast<uint32_t*>(hi + (long long)h * hop_stride);
+      uint32_t* pl = lo ? reinterpret_cast<uint32_t*>(lo + (long long)h * hop_stride) : nullptr;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float a = q0[k] < thresh ? v[k].x * scale : 0.0f, c = q1[k] < thresh ? v[k].y * scale : 0.0f;
+        uint32_t hh, ll;
+        split_pair(a, c, hh, ll);
+        const int64_t o = (((int64_t)b * S + 4 * s4 + k) * C + c0) >> 1;
+        ph[o + lane] = hh;
+        if (pl) pl[o + lane] = ll;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) unprep_rows_kernel(const float* __restrict__ dXr, const uint32_t* __restrict__ bits, float scale,
                                                           int C, int S, float* __restrict__ dX) {
   RAU_PDL_ENTRY();
@@ -1871,6 +1921,23 @@ static int prep_attr() {
     RAU_CHECK_CUDA(cudaFuncSetAttribute(unprep_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 66 * 4));
     g_prep_attr = true;
   }
+  return RAU_OK;
+}
+
+int k_xprep_rows_hops(rau_ctx* ctx, const float* X, int B, int C, int S, int nHop, float scale, bf16* hi, bf16* lo,
+                      int64_t hop_stride, float p_drop, uint64_t stream_id) {
+  RAU_REQUIRE(C % 64 == 0 && S % 4 == 0 && S <= 256 && ((uintptr_t)X & 15) == 0 && hop_stride % 2 == 0, "k_xprep_rows_hops: C=%d S=%d", C, S);
+  static bool attr = false;
+  if (!attr) {
+    RAU_CHECK_CUDA(cudaFuncSetAttribute(xprep_rows_hops_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 66 * 4));
+    attr = true;
+  }
+  const double keep = 1.0 - (double)p_drop;
+  const uint32_t thresh = keep >= 1.0 ? 0xffffffffu : (uint32_t)(keep * 4294967296.0);
+  RAU_LAUNCH_PDL(ctx->stream, (xprep_rows_hops_kernel), dim3(C / 64, B), 256, S * 66 * 4,
+      X, scale, C, S, nHop, hi, lo, (long long)hop_stride, thresh, make_uint2((uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32)),
+      (uint32_t)stream_id, (uint32_t)(stream_id >> 32), ctx->ss_active);
+  RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 

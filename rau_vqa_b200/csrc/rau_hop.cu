@@ -90,8 +90,9 @@ int hop_forward_pre(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<cons
   const uint32_t* xb = (train && cfg->p_x > 0) ? sv.xbits : nullptr;
   const bf16 *Wi_h, *Wi_l;
   RAU_TRY(rows_pack(ctx, P.Wi, (int64_t)M * C, x3, true, nullptr, &Wi_h, &Wi_l));
-  RAU_TRY(k_xprep_rows(ctx, X, B, C, S, xb, drop_scale(cfg->p_x), sv.Xd_hi, x3 ? sv.Xd_lo : nullptr,
-                       (train && cfg->p_x > 0 && sv.x_philox) ? 1 : 0, cfg->p_x, sv.x_stream));
+  if (!sv.x_done)
+    RAU_TRY(k_xprep_rows(ctx, X, B, C, S, xb, drop_scale(cfg->p_x), sv.Xd_hi, x3 ? sv.Xd_lo : nullptr,
+                         (train && cfg->p_x > 0 && sv.x_philox) ? 1 : 0, cfg->p_x, sv.x_stream));
   RowsGemm g;
   g.M = R; g.N = M; g.K = C;
   g.A.hi = sv.Xd_hi; g.A.lo = x3 ? sv.Xd_lo : nullptr; g.A.ld = C;

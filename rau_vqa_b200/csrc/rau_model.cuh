@@ -57,6 +57,7 @@ struct HopSaved {
   // training step on the rows engine: the feature-dropout bits are drawn inside the transposing pack kernel from this
   // Philox stream instead of being materialised in xbits first (nothing in the step reads them again: dX is not formed)
   int x_philox = 0;
+  int x_done = 0;        // the pack already ran (all hops in one launch)
   uint64_t x_stream = 0;
   // training step: packed twins of the small activations (all NULL through the module-level API, which packs on demand)
   PK qd_pk, qf_pk, p_pk, j_pk, hin_pk, hout_pk, m_pk;

@@ -562,6 +562,16 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     ctx->stream = ctx->side;
     ctx->rows_cta_cap = ctx->side_ctas_fwd;
     int rc = RAU_OK;
+    // drawn feature masks: the feature pack of all hops in one launch (the fp32 features are read once, not nHop times)
+    const char* e_xh = getenv("RAU_XPREP_HOPS");   // =0: one pack launch per hop (same bits; tests compare the two)
+    bool all_philox = train && cfg->p_x > 0 && nHop > 1 && nHop < 65536 && !(e_xh && atoi(e_xh) == 0);
+    for (int hp = 0; hp < nHop; ++hp) all_philox = all_philox && sv[hp].x_philox;
+    if (all_philox) {
+      rc = k_xprep_rows_hops(ctx, bt->feats, B, cfg->C, S, nHop, drop_scale(cfg->p_x), sv[0].Xd_hi,
+                             ctx->precision == RAU_PREC_BF16X3 ? sv[0].Xd_lo : nullptr, (int64_t)(sv_bytes / sizeof(bf16)), cfg->p_x,
+                             sv[0].x_stream);
+      for (int hp = 0; hp < nHop; ++hp) sv[hp].x_done = 1;
+    }
     for (int hp = 0; hp < nHop && rc == RAU_OK; ++hp) {
       rc = hop_forward_pre(ctx, cfg, B, P, bt->feats, train, sv[hp]);
       if (rc == RAU_OK) {

@@ -268,3 +268,28 @@ def test_virtual_ranks_sum_equals_big_batch(R, ctx):
     for k in O.GROUPS:
         assert rel_err(acc[k], full[k]) <= tol, k
     np.testing.assert_allclose(loss[:cfg.nHop], out_full.loss.cpu().numpy()[:cfg.nHop], rtol=tol)
+
+
+def test_all_hops_feature_pack_draws_the_same_masks(R):
+    """The training step packs the dropped-out features of all hops in one launch (k_xprep_rows_hops); the per-hop launches
+    (RAU_XPREP_HOPS=0) must see bit-identical Philox masks: losses and gradients then agree to summation-order noise
+    (atomics), while a single differing keep bit moves them by orders of magnitude more."""
+    import os
+    cfg = O.RauConfig(V=300, C=128, nHop=3, N=40)
+    B = 3
+    params = O.init_params(cfg, seed=61)
+    X, x, x_len, y = O.synth_batch(cfg, B, seed=62)
+    res = []
+    for flag in ("1", "0"):
+        os.environ["RAU_XPREP_HOPS"] = flag
+        try:
+            c = R.Context(0, seed=77)
+            g, out = run_lib_feval(c, cfg, params, X, x, x_len, y, masks=None, step_t=5)
+            res.append((g, out.loss.cpu().numpy().copy()))
+            c.close()
+        finally:
+            os.environ.pop("RAU_XPREP_HOPS", None)
+    np.testing.assert_allclose(res[0][1], res[1][1], rtol=2e-6)
+    for k in O.GROUPS:
+        assert rel_err(res[0][0][k], res[1][0][k]) <= 1e-5, k
+    assert np.abs(res[0][0]["mult"]).max() > 0
