@@ -255,6 +255,12 @@ int rau_rows_gemm(rau_ctx* ctx, int M, int N, int K, const float* A, int lda, in
 /* GPU microseconds per launch of one rows-engine product on synthetic operands (iters launches replayed from a CUDA
  * graph, so host launch cost is excluded); reduce != 0 selects the split-K TMA-reduce form */
 int rau_rows_gemm_time(rau_ctx* ctx, int M, int N, int K, int a_mn, int b_mn, int reduce, int iters, float* us_per_launch);
+/* The feature dropout + rows transpose + bf16 split of the hop forward (replaces nn.Dropout on the image features,
+ * train_rau_vqa.lua:239) with keep bits drawn inline from the context's Philox streams (stream_id ^ hop), for nHop hops:
+ * out[h][b*S+s][c] = the packed value (hi + lo) as fp32.  all_hops != 0 runs the one-launch form the training step uses,
+ * 0 one launch per hop; both draw identical bits.  Test / inspection hook. */
+int rau_feature_pack(rau_ctx* ctx, const float* X, int B, int C, int S, int nHop, float p, uint64_t stream_id, int all_hops,
+                     float* out);
 /* debugging aid (RAU_ROWS_TRACE=1): copies the per-CTA clock stamps [148][16] of the last rows-engine launch to HOST
  * memory `out` (n 64-bit words): 0 start, 1 prologue done, 2 first TMA issue, 3/4 first/second stage landed, 5 MMAs
  * of the first item issued, 6 first accumulator ready, 7 epilogue issued, 8 stores drained, 9 end */

@@ -950,6 +950,11 @@ int launch_rows(rau_ctx* ctx, const RtParams& p, int grid, int smem_bytes) {
   return launch_rows_v<EPI, 0, 4, 0>(ctx, p, grid, smem_bytes);
 }
 
+__global__ void unpack_hilo_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, int64_t n, float* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __bfloat162float(hi[i]) + (lo ? __bfloat162float(lo[i]) : 0.0f);
+}
+
 __global__ void pack_hilo_kernel(const float* __restrict__ in, int64_t n4, bf16* __restrict__ hi, bf16* __restrict__ lo) {
   RAU_PDL_ENTRY();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -983,12 +988,16 @@ __global__ void __launch_bounds__(256) xprep_rows_kernel(const float* __restrict
     const int64_t e = ((int64_t)b * C + c0 + c) * S + 4 * s4;
     float4 t = *reinterpret_cast<const float4*>(X + e);
     if (gen) {
-      const uint64_t ctr = (uint64_t)e >> 2;
+      // inline-drawn keep bits: one Philox call serves a channel PAIR (even, odd) x 4 grid cells -- word k of the call
+      // decides cell 4*s4+k, its low half for the even channel, its high half for the odd one (16-bit threshold)
+      const int cc = c0 + c;
+      const uint64_t ctr = (uint64_t)(((int64_t)b * C + (cc & ~1)) * S + 4 * s4) >> 2;
       const uint4 r = philox4x32(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), stream_lo, stream_hi), key);
-      t.x = r.x < thresh ? t.x * scale : 0.0f;
-      t.y = r.y < thresh ? t.y * scale : 0.0f;
-      t.z = r.z < thresh ? t.z * scale : 0.0f;
-      t.w = r.w < thresh ? t.w * scale : 0.0f;
+      const int sh = (cc & 1) * 16;
+      t.x = ((r.x >> sh) & 0xffffu) < thresh ? t.x * scale : 0.0f;
+      t.y = ((r.y >> sh) & 0xffffu) < thresh ? t.y * scale : 0.0f;
+      t.z = ((r.z >> sh) & 0xffffu) < thresh ? t.z * scale : 0.0f;
+      t.w = ((r.w >> sh) & 0xffffu) < thresh ? t.w * scale : 0.0f;
     } else if (bits) {
       const uint32_t w = bits[e >> 5] >> (e & 31);
       t.x = (w & 1u) ? t.x * scale : 0.0f;
@@ -1015,50 +1024,73 @@ __global__ void __launch_bounds__(256) xprep_rows_kernel(const float* __restrict
 // The same pack for ALL hops of the training step in one launch: every hop drops out the SAME features with its own
 // Philox stream (stream id ^ hop), so the fp32 tile is read and transposed once and written nHop times (hop h's arrays are
 // hop_stride elements after hop 0's).  Identical bits to nHop launches of xprep_rows_kernel.
-__global__ void __launch_bounds__(256) xprep_rows_hops_kernel(const float* __restrict__ X, float scale, int C, int S, int nHop,
-                                                              bf16* __restrict__ hi, bf16* __restrict__ lo, long long hop_stride,
-                                                              uint32_t thresh, uint2 key, uint32_t stream_lo, uint32_t stream_hi,
-                                                              const StepState* __restrict__ ss) {
+// Persistent: one 1024-thread CTA per SM it may use (four 256-thread groups, each with its own [S][66] slab and named
+// barrier, walk the (image, 64-channel) tiles).  The big CTAs keep the launch on `gridDim.x` SMs, so the chain's tcgen05
+// launches still find free SMs next to it (a grid of small CTAs spread over every SM and filled their shared memory).
+__global__ void __launch_bounds__(1024, 1) xprep_rows_hops_kernel(const float* __restrict__ X, float scale, int C, int S, int B, int nHop,
+                                                                  bf16* __restrict__ hi, bf16* __restrict__ lo, long long hop_stride,
+                                                                  uint32_t thresh, uint2 key, uint32_t stream_lo, uint32_t stream_hi,
+                                                                  const StepState* __restrict__ ss) {
   RAU_PDL_ENTRY();
-  extern __shared__ float sT[];   // [S][66]
-  const int b = blockIdx.y, c0 = blockIdx.x * 64;
-  const int S4 = S >> 2;
+  extern __shared__ float sT_all[];   // 4 x [S][66]
+  const int sub = threadIdx.x >> 8, tid = threadIdx.x & 255;
+  float* sT = sT_all + (size_t)sub * S * 66;
+  const int S4 = S >> 2, ctiles = C / 64, ntiles = ctiles * B;
   if (ss) {
     const unsigned long long sid = (((unsigned long long)stream_hi << 32) | stream_lo) ^ (ss->step << 24);
     stream_lo = (uint32_t)sid;
     stream_hi = (uint32_t)(sid >> 32);
   }
-  for (int i = threadIdx.x; i < 64 * S4; i += 256) {
-    const int c = i / S4, s4 = i - c * S4;
-    const float4 t = __ldg(reinterpret_cast<const float4*>(X + ((int64_t)b * C + c0 + c) * S + 4 * s4));
-    float* d = sT + (4 * s4) * 66 + c;
-    d[0] = t.x; d[66] = t.y; d[132] = t.z; d[198] = t.w;
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // a lane owns channels 2*lane, 2*lane+1; one Philox call covers 4 consecutive grid cells of one channel
-  const uint64_t e0 = ((uint64_t)b * C + c0 + 2 * lane) * (uint64_t)S, e1 = e0 + (uint64_t)S;
-  for (int s4 = warp; s4 < S4; s4 += 8) {
-    float2 v[4];
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int tile = blockIdx.x * 4 + sub; tile < ntiles; tile += gridDim.x * 4) {
+    const int b = tile / ctiles, c0 = (tile - b * ctiles) * 64;
+    // the tile's 64 x S floats are contiguous in X: batches of 7 independent 16-byte loads per thread, then the
+    // transposing stores (a load -> store loop exposes one memory latency per iteration)
+    const float4* src = reinterpret_cast<const float4*>(X + ((int64_t)b * C + c0) * S);
+    const int n4 = 64 * S4;
+    for (int i0 = tid; i0 < n4; i0 += 256 * 7) {
+      float4 t[7];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const float2*>(sT + (4 * s4 + k) * 66 + 2 * lane);
-    const uint64_t ct0 = (e0 + 4 * s4) >> 2, ct1 = (e1 + 4 * s4) >> 2;
-    for (int h = 0; h < nHop; ++h) {
-      const uint4 r0 = philox4x32(make_uint4((uint32_t)ct0, (uint32_t)(ct0 >> 32), stream_lo ^ (uint32_t)h, stream_hi), key);
-      const uint4 r1 = philox4x32(make_uint4((uint32_t)ct1, (uint32_t)(ct1 >> 32), stream_lo ^ (uint32_t)h, stream_hi), key);
-      const uint32_t q0[4] = {r0.x, r0.y, r0.z, r0.w}, q1[4] = {r1.x, r1.y, r1.z, r1.w};
-      uint32_t* ph = reinterpret_cast<uint32_t*>(hi + (long long)h * hop_stride);
-      uint32_t* pl = lo ? reinterpret_cast<uint32_t*>(lo + (long long)h * hop_stride) : nullptr;
+      for (int k = 0; k < 7; ++k) {
+        const int i = i0 + 256 * k;
+        if (i < n4) t[k] = __ldg(src + i);
+      }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float a = q0[k] < thresh ? v[k].x * scale : 0.0f, c = q1[k] < thresh ? v[k].y * scale : 0.0f;
-        uint32_t hh, ll;
-        split_pair(a, c, hh, ll);
-        const int64_t o = (((int64_t)b * S + 4 * s4 + k) * C + c0) >> 1;
-        ph[o + lane] = hh;
-        if (pl) pl[o + lane] = ll;
+      for (int k = 0; k < 7; ++k) {
+        const int i = i0 + 256 * k;
+        if (i < n4) {
+          const int c = i / S4, s4 = i - c * S4;
+          float* d = sT + (4 * s4) * 66 + c;
+          d[0] = t[k].x; d[66] = t[k].y; d[132] = t[k].z; d[198] = t[k].w;
+        }
       }
     }
+    asm volatile("bar.sync %0, 256;" ::"r"(1 + sub) : "memory");
+    // a lane owns the channel pair 2*lane, 2*lane+1: one Philox call covers the pair x 4 consecutive grid cells
+    const uint64_t e0 = ((uint64_t)b * C + c0 + 2 * lane) * (uint64_t)S;
+    for (int s4 = warp; s4 < S4; s4 += 8) {
+      float2 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const float2*>(sT + (4 * s4 + k) * 66 + 2 * lane);
+      const uint64_t ct0 = (e0 + 4 * s4) >> 2;
+      for (int h = 0; h < nHop; ++h) {
+        const uint4 r0 = philox4x32(make_uint4((uint32_t)ct0, (uint32_t)(ct0 >> 32), stream_lo ^ (uint32_t)h, stream_hi), key);
+        const uint32_t q0[4] = {r0.x & 0xffffu, r0.y & 0xffffu, r0.z & 0xffffu, r0.w & 0xffffu};
+        const uint32_t q1[4] = {r0.x >> 16, r0.y >> 16, r0.z >> 16, r0.w >> 16};
+        uint32_t* ph = reinterpret_cast<uint32_t*>(hi + (long long)h * hop_stride);
+        uint32_t* pl = lo ? reinterpret_cast<uint32_t*>(lo + (long long)h * hop_stride) : nullptr;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float a = q0[k] < thresh ? v[k].x * scale : 0.0f, c = q1[k] < thresh ? v[k].y * scale : 0.0f;
+          uint32_t hh, ll;
+          split_pair(a, c, hh, ll);
+          const int64_t o = (((int64_t)b * S + 4 * s4 + k) * C + c0) >> 1;
+          ph[o + lane] = hh;
+          if (pl) pl[o + lane] = ll;
+        }
+      }
+    }
+    asm volatile("bar.sync %0, 256;" ::"r"(1 + sub) : "memory");   // the slab is free for the group's next tile
   }
 }
 
@@ -1924,18 +1956,28 @@ static int prep_attr() {
   return RAU_OK;
 }
 
+int k_unpack_hilo(rau_ctx* ctx, const bf16* hi, const bf16* lo, int64_t n, float* out) {
+  unpack_hilo_kernel<<<(int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256, 0, ctx->stream>>>(hi, lo, n, out);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+
 int k_xprep_rows_hops(rau_ctx* ctx, const float* X, int B, int C, int S, int nHop, float scale, bf16* hi, bf16* lo,
                       int64_t hop_stride, float p_drop, uint64_t stream_id) {
-  RAU_REQUIRE(C % 64 == 0 && S % 4 == 0 && S <= 256 && ((uintptr_t)X & 15) == 0 && hop_stride % 2 == 0, "k_xprep_rows_hops: C=%d S=%d", C, S);
+  RAU_REQUIRE(C % 64 == 0 && S % 4 == 0 && S <= 200 && ((uintptr_t)X & 15) == 0 && hop_stride % 2 == 0, "k_xprep_rows_hops: C=%d S=%d", C, S);
+  const int smem = 4 * S * 66 * 4;
   static bool attr = false;
   if (!attr) {
-    RAU_CHECK_CUDA(cudaFuncSetAttribute(xprep_rows_hops_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 66 * 4));
+    RAU_CHECK_CUDA(cudaFuncSetAttribute(xprep_rows_hops_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 200 * 66 * 4));
     attr = true;
   }
   const double keep = 1.0 - (double)p_drop;
-  const uint32_t thresh = keep >= 1.0 ? 0xffffffffu : (uint32_t)(keep * 4294967296.0);
-  RAU_LAUNCH_PDL(ctx->stream, (xprep_rows_hops_kernel), dim3(C / 64, B), 256, S * 66 * 4,
-      X, scale, C, S, nHop, hi, lo, (long long)hop_stride, thresh, make_uint2((uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32)),
+  const uint32_t thresh = keep >= 1.0 ? 65536u : (uint32_t)(keep * 65536.0 + 0.5);   // 16-bit keep threshold
+  const int cap = (ctx->rows_cta_cap > 0 && ctx->rows_cta_cap < ctx->sm_count) ? ctx->rows_cta_cap : ctx->sm_count;
+  const int ntiles = (C / 64) * B;
+  const int grid = (ntiles + 3) / 4 < cap ? (ntiles + 3) / 4 : cap;
+  RAU_LAUNCH_PDL(ctx->stream, (xprep_rows_hops_kernel), grid, 1024, smem,
+      X, scale, C, S, B, nHop, hi, lo, (long long)hop_stride, thresh, make_uint2((uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32)),
       (uint32_t)stream_id, (uint32_t)(stream_id >> 32), ctx->ss_active);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
@@ -1946,7 +1988,7 @@ int k_xprep_rows(rau_ctx* ctx, const float* X, int B, int C, int S, const uint32
   RAU_REQUIRE(C % 64 == 0 && S % 4 == 0 && S <= 256 && ((uintptr_t)X & 15) == 0, "k_xprep_rows: C=%d S=%d", C, S);
   RAU_TRY(prep_attr());
   const double keep = 1.0 - (double)p_drop;
-  const uint32_t thresh = keep >= 1.0 ? 0xffffffffu : (uint32_t)(keep * 4294967296.0);
+  const uint32_t thresh = keep >= 1.0 ? 65536u : (uint32_t)(keep * 65536.0 + 0.5);   // 16-bit keep threshold (gen path)
   RAU_LAUNCH_PDL(ctx->stream, (xprep_rows_kernel), dim3(C / 64, B), 256, S * 66 * 4, 
       X, bits, scale, C, S, hi, lo, gen, thresh, make_uint2((uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32)), (uint32_t)stream_id,
       (uint32_t)(stream_id >> 32), ctx->ss_active);

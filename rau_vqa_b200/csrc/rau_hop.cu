@@ -927,6 +927,27 @@ int rau_rows_gemm_time(rau_ctx* ctx, int M, int N, int K, int a_mn, int b_mn, in
   return RAU_OK;
 }
 
+int rau_feature_pack(rau_ctx* ctx, const float* X, int B, int C, int S, int nHop, float p, uint64_t stream_id, int all_hops,
+                     float* out) {
+  RAU_REQUIRE(ctx && X && out && B > 0 && nHop > 0 && nHop < 65536, "bad arguments");
+  RAU_REQUIRE(ctx->precision != RAU_PREC_F32, "rau_feature_pack: tcgen05 modes only");
+  RAU_REQUIRE(p > 0.0f && p < 1.0f, "rau_feature_pack: 0 < p < 1");
+  RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+  const size_t n = (size_t)B * S * C;
+  bf16* buf = nullptr;
+  RAU_TRY(ctx->arena.get("fp.buf", sizeof(bf16) * 2 * n * nHop, (void**)&buf));
+  bf16* hi = buf;
+  bf16* lo = buf + n * nHop;
+  if (all_hops) {
+    RAU_TRY(k_xprep_rows_hops(ctx, X, B, C, S, nHop, drop_scale(p), hi, x3 ? lo : nullptr, (int64_t)n, p, stream_id));
+  } else {
+    for (int h = 0; h < nHop; ++h)
+      RAU_TRY(k_xprep_rows(ctx, X, B, C, S, nullptr, drop_scale(p), hi + n * h, x3 ? lo + n * h : nullptr, 1, p, stream_id ^ (uint64_t)h));
+  }
+  return k_unpack_hilo(ctx, hi, x3 ? lo : nullptr, (int64_t)n * nHop, out);
+}
+
 int rau_rows_trace(rau_ctx* ctx, uint64_t* out, int n) {
   RAU_REQUIRE(ctx && out && n > 0, "bad arguments");
   void* buf = nullptr;

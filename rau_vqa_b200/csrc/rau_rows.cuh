@@ -57,6 +57,7 @@ int rows_pack(rau_ctx* ctx, const float* W, int64_t n, bool want_lo, bool cache,
 // the same for nHop hops in one launch (training step, drawn masks): hop h writes hi/lo + h*hop_stride, stream id ^ h
 int k_xprep_rows_hops(rau_ctx* ctx, const float* X, int B, int C, int S, int nHop, float scale, bf16* hi, bf16* lo,
                       int64_t hop_stride, float p_drop, uint64_t stream_id);
+int k_unpack_hilo(rau_ctx* ctx, const bf16* hi, const bf16* lo, int64_t n, float* out);   // out = hi + lo (tests)
 int k_xprep_rows(rau_ctx* ctx, const float* X, int B, int C, int S, const uint32_t* bits, float scale, bf16* hi, bf16* lo,
                  int gen = 0, float p_drop = 0.0f, uint64_t stream_id = 0);
 int k_unprep_rows(rau_ctx* ctx, const float* dXr, int B, int C, int S, const uint32_t* bits, float scale, float* dX);

@@ -56,8 +56,9 @@ static int encoder_alloc(rau_ctx* ctx, const rau_config* cfg, int B, Encoder* en
 }
 
 // F:460-479.  State rows are [c1|h1|c2|h2] (D:23-24, D:68); S_all[t] is the state after step t, S_all[0] = 0.
+// part: 0 = everything, 1 = masks + word embedding only, 2 = the rest (after a part-1 call)
 static int encoder_forward(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, const float* Pe, const float* Pr,
-                           int train, const rau_masks* masks, int64_t step_t, Encoder* en) {
+                           int train, const rau_masks* masks, int64_t step_t, Encoder* en, int part = 0) {
   const int B = bt->B, Hq = cfg->Hq, E = cfg->embed, Q = 4 * Hq, G4 = 4 * Hq;
   const int Tm = (bt->max_len > 0 && bt->max_len <= cfg->T) ? bt->max_len : cfg->T;
   en->Tm = Tm;
@@ -65,14 +66,17 @@ static int encoder_forward(rau_ctx* ctx, const rau_config* cfg, const rau_batch*
   rnn_offsets(cfg, L);
   const int rank = rau_comm_rank(ctx);
   const bool de = train && cfg->p_embed > 0, dr = train && cfg->p_rnn > 0;
-  RAU_TRY(rau_prepare_mask(ctx, en->ebits, (int64_t)Tm * B * E, cfg->p_embed, train, masks ? masks->embed : nullptr,
-                           stream_of(step_t, SK_EMBED, 0, rank)));
-  RAU_TRY(rau_prepare_mask(ctx, en->rbits, (int64_t)Tm * B * Hq, cfg->p_rnn, train, masks ? masks->rnn : nullptr,
-                           stream_of(step_t, SK_RNN, 0, rank)));
-  // word_embed for every step at once (F:203-206, F:468)
-  RAU_TRY(k_embed_fwd(ctx, bt->tokens, Tm * B, E, cfg->V, Pe, de ? en->ebits : nullptr, drop_scale(cfg->p_embed),
-                      en->e_all, nullptr, 0));
-  if (ctx->phases == 2) rau_phase_mark(ctx, "enc embed done");
+  if (part != 2) {
+    RAU_TRY(rau_prepare_mask(ctx, en->ebits, (int64_t)Tm * B * E, cfg->p_embed, train, masks ? masks->embed : nullptr,
+                             stream_of(step_t, SK_EMBED, 0, rank)));
+    RAU_TRY(rau_prepare_mask(ctx, en->rbits, (int64_t)Tm * B * Hq, cfg->p_rnn, train, masks ? masks->rnn : nullptr,
+                             stream_of(step_t, SK_RNN, 0, rank)));
+    // word_embed for every step at once (F:203-206, F:468)
+    RAU_TRY(k_embed_fwd(ctx, bt->tokens, Tm * B, E, cfg->V, Pe, de ? en->ebits : nullptr, drop_scale(cfg->p_embed),
+                        en->e_all, nullptr, 0));
+    if (ctx->phases == 2) rau_phase_mark(ctx, "enc embed done");
+    if (part == 1) return RAU_OK;
+  }
   const bool fused = ctx->precision != RAU_PREC_F32 && rows_path_enabled() && Hq % 8 == 0 && E % 8 == 0 &&
                      (int64_t)B * G4 * Hq >= (1 << 18);
   // layer 1 input projection hoisted over time: G1x = e Wi1^T + bi1 + bh1
@@ -421,6 +425,15 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   bool side_used = false;
   Encoder en;
   RAU_TRY(encoder_alloc(ctx, cfg, B, &en));
+  // The chain's first launches (masks + word embedding) go out before the side stream is released: the all-hops feature
+  // pack saturates HBM for its first ~250 us and would stretch these latency-bound launches threefold.
+  cudaEvent_t fork_side = fork0;
+  if (ov_fwd) {
+    RAU_TRY(encoder_forward(ctx, cfg, bt, params[0], params[1], train, masks, step_t, &en, 1));
+    fork_side = rau_side_event(ctx);
+    RAU_REQUIRE(fork_side != nullptr, "cudaEventCreate failed");
+    RAU_CHECK_CUDA(cudaEventRecord(fork_side, ctx->stream));
+  }
 
   // answering units (F:495-537)
   const size_t sv_bytes = hop_saved_layout(cfg, B, nullptr, nullptr);
@@ -550,7 +563,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     // next to the encoder unroll and the hops' chains; each hop waits for its own event before it reads I
     bool early = fork0 != nullptr;   // (materialised feature masks are written on the chain: fork after them)
     for (int hp = 0; hp < nHop; ++hp) early = early && (sv[hp].x_philox || !(train && cfg->p_x > 0));
-    cudaEvent_t fork = fork0;
+    cudaEvent_t fork = fork_side;
     if (!early) {
       if (prep_done) RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->side, prep_done, 0));   // the materialised masks
       fork = rau_side_event(ctx);
@@ -585,7 +598,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     RAU_TRY(rc);
     side_used = true;
   }
-  RAU_TRY(encoder_forward(ctx, cfg, bt, params[0], params[1], train, masks, step_t, &en));
+  RAU_TRY(encoder_forward(ctx, cfg, bt, params[0], params[1], train, masks, step_t, &en, ov_fwd ? 2 : 0));
   if (prep_done) RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, prep_done, 0));
   rau_phase_mark(ctx, "encoder forward");
   // Everything of the unroll that depends on the encoder state only is hoisted out of the per-hop chains: the q dropout

@@ -55,3 +55,43 @@ def test_rows_gemm_matches_numpy(R, mode, tol, a_mn, b_mn, shape):
     got = _rows_gemm(ctx, A, B, a_mn, b_mn, D0)          # split-K reduce-add into an existing buffer
     assert rel_err(got, ref + D0) <= tol
     ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+def test_feature_pack_inline_masks(R, mode):
+    """rau_feature_pack: dropout (keep bits drawn inline) + transpose to rows + bf16 split of the image features.
+    Kept cells hold x/(1-p), dropped ones 0, the keep rate is 1-p, hops draw different masks, and the one-launch
+    all-hops form draws exactly the bits of the per-hop launches."""
+    import torch
+    from rau_vqa_b200 import core
+    from rau_vqa_b200._ffi import check, ffi
+    ctx = R.Context(0, seed=5, precision=dict(bf16x3=core.PREC_BF16X3, bf16=core.PREC_BF16)[mode])
+    B, C, S, nHop, p = 5, 128, 196, 3, 0.3
+    rng = np.random.default_rng(11)
+    X = (rng.standard_normal((B, C, S)).astype(np.float32) + 3.0)      # no zeros: a zero output means "dropped"
+    Xd = torch.from_numpy(X).cuda()
+    outs = []
+    for all_hops in (1, 0):
+        out = torch.empty((nHop, B * S, C), dtype=torch.float32, device="cuda")
+        check(ctx.lib.rau_feature_pack(ctx.h, ffi.cast("const float*", Xd.data_ptr()), B, C, S, nHop, p, 0x1234500, all_hops,
+                                       ffi.cast("float*", out.data_ptr())))
+        ctx.sync()
+        outs.append(out.cpu().numpy())
+    np.testing.assert_array_equal(outs[0], outs[1])
+    got = outs[0]
+    ref = np.transpose(X, (0, 2, 1)).reshape(B * S, C) / (1.0 - p)
+    keep = got != 0.0
+    tol = 1e-5 if mode == "bf16x3" else 1e-2
+    for h in range(nHop):
+        np.testing.assert_allclose(got[h][keep[h]], ref[keep[h]], rtol=tol)
+        rate = keep[h].mean()
+        n = keep[h].size
+        assert abs(rate - (1.0 - p)) < 5.0 * np.sqrt(p * (1.0 - p) / n) + 1e-4, rate
+        # both channels of a pair and all four cells of a Philox call are used independently
+        assert abs(keep[h][:, 0::2].mean() - keep[h][:, 1::2].mean()) < 0.01
+    assert (keep[0] != keep[1]).mean() > 0.3 and (keep[1] != keep[2]).mean() > 0.3
+    # neighbouring channels / cells are not copies of each other
+    assert (keep[0][:, 0] != keep[0][:, 1]).mean() > 0.3
+    assert (keep[0][0::4] != keep[0][1::4]).mean() > 0.3
+    ctx.close()
