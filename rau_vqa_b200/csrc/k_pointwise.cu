@@ -565,7 +565,22 @@ int k_rowsum_bms(rau_ctx* ctx, const T* x, int B, int M, int S, int Sp, float* o
 }
 template int k_rowsum_bms<float>(rau_ctx*, const float*, int, int, int, int, float*);
 template int k_rowsum_bms<bf16>(rau_ctx*, const bf16*, int, int, int, int, float*);
+// out[0] += sum x: many CTAs, one atomic each (the single-CTA form below took 60 us for the 0.4 M-element gbs reduction)
+__global__ void sum_all_acc_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+  RAU_PDL_ENTRY();
+  __shared__ float red[32];
+  float s = 0.0f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += x[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
 int k_sum_all(rau_ctx* ctx, const float* x, int64_t n, float* out, int accumulate) {
+  if (accumulate && n >= 65536) {
+    RAU_LAUNCH_PDL(ctx->stream, (sum_all_acc_kernel), (int)((n + 4095) / 4096 < 148 ? (n + 4095) / 4096 : 148), 256, 0, x, n, out);
+    RAU_LAUNCH_CHECK(ctx);
+    return RAU_OK;
+  }
   RAU_LAUNCH_PDL(ctx->stream, (sum_all_kernel), 1, 1024, 0, x, n, out, accumulate);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;

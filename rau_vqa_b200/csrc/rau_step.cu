@@ -551,6 +551,33 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
                                stream_of(step_t, SK_X, hp, rank)));
     }
   }
+  if (prep_aux && ctx->precision != RAU_PREC_F32 && hop_rows_path(ctx, cfg) && rows_path_enabled()) {
+    // the bf16 (hi, lo) shadows of the weights the chain's products read: packed here, next to the encoder, instead of
+    // inline at their first use on the chain (the per-epoch cache makes the later calls no-ops)
+    const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+    const bf16 *ph, *pl;
+    int64_t pld;
+    const float* pb;
+    auto prepack = [&](const float* W, int Nout, int Kin) {
+      return Kin % 8 == 0 ? rows_pack2d(ctx, W, Kin, Nout, Kin, x3, true, nullptr, &ph, &pl, &pld) : RAU_OK;
+    };
+    RAU_TRY(prepack(P.Wq, M_, Q)); RAU_TRY(prepack(P.Wh, M_, H)); RAU_TRY(prepack(P.Wqa, A_, M_)); RAU_TRY(prepack(P.Wm, S, H));
+    RAU_TRY(prepack(P.Wp, M_, S)); RAU_TRY(prepack(P.Wo, M_, H)); RAU_TRY(prepack(P.Ws, N, M_));
+    RAU_TRY(prepack(P.Wx, 4 * H, M_)); RAU_TRY(prepack(P.Whh, 4 * H, H));
+    if (H % 8 == 0 && M_ % 8 == 0) {
+      RAU_TRY(rows_pack_lstm(ctx, P.Wx, H, M_, RAU_GATES_IGFO, x3, &ph, &pl, &pld));
+      RAU_TRY(rows_pack_lstm(ctx, P.Whh, H, H, RAU_GATES_IGFO, x3, &ph, &pl, &pld));
+      RAU_TRY(rows_perm_lstm_bias(ctx, P.bx, P.bhh, H, RAU_GATES_IGFO, &pb));
+    }
+    RnnLayerOff L[4];
+    rnn_offsets(cfg, L);
+    const int Hq = cfg->Hq, E = cfg->embed;
+    if (Hq % 8 == 0 && E % 8 == 0)
+      for (int layer = 0; layer < 2; ++layer) {   // the encoder backward's dgrad operands
+        RAU_TRY(prepack(params[1] + L[layer].Wh, 4 * Hq, Hq));
+        RAU_TRY(prepack(params[1] + L[layer].Wi, 4 * Hq, layer == 0 ? E : Hq));
+      }
+  }
   cudaEvent_t prep_done = nullptr;
   if (prep_aux) {
     prep_done = rau_side_event(ctx);
