@@ -483,6 +483,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
     // row); rvp = this warp's slice of the per-image row vector for the (at most two) images its 32 rows belong to
     uint4 ah[4], al[4];
     float4 rvp[2];
+    float rs_next = 0.0f;   // the next item's row scale (p[r]) for this thread's row
     bool dy_ready = false;
     const int arow = lane >> 2, aseg = lane & 3;
     const int ncols_w = p.BN / 2;   // accumulator columns of this warp
@@ -525,7 +526,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
       const float* rv = nullptr;
       float rs = 0.0f;
       if (EPI == EPI_ATT || EPI == EPI_DY) rv = p.rowvec + (long long)(rr / p.S) * p.N;
-      if (EPI == EPI_DY) rs = p.rowscale[rr];
+      if (EPI == EPI_DY) rs = dy_ready ? rs_next : p.rowscale[rr];
       const int c_lo = half * (p.BN / 64), c_hi = c_lo + p.BN / 64;
       bool released = false;
       uint32_t rv_s = 0;
@@ -752,6 +753,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
               const int rb2 = (CG2 ? tm2 * 2 * RT_BM + (int)cta_rank * RT_BM : tm2 * RT_BM) + q * 32;
               aux_fetch(rb2, min(tn2 * p.BN + c_lo * 32, p.N - 32));
               rv_fetch(rb2, tn2 * p.BN + c_lo * 32);
+              rs_next = p.rowscale[min(rb2 + lane, p.M - 1)];
             }
           }
 #pragma unroll
