@@ -2080,9 +2080,11 @@ int rows_lstm_seq(rau_ctx* ctx, const LstmSeq& d, int* done) {
   p.lsaved = d.lsaved; p.ls_t = d.ls_t; p.plane = d.plane;
   p.hpk_hi = d.hpk_hi; p.hpk_lo = d.hpk_lo; p.hp_t = (long long)B * H;
   unsigned int* cnt = nullptr;
+  const bool cnt_new = ctx->arena.bufs.find("lstmseq.cnt") == ctx->arena.bufs.end();
   RAU_TRY(ctx->arena.get("lstmseq.cnt", sizeof(unsigned int) * 64, (void**)&cnt));
+  if (cnt_new) RAU_CHECK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * 64, ctx->stream));   // (word 63: sticky time-out flag, read by rau_sync)
   RAU_REQUIRE(tiles_m < 63, "rows_lstm_seq: %d row tiles", tiles_m);
-  RAU_CHECK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * 64, ctx->stream));
+  RAU_CHECK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * 63, ctx->stream));
   p.counter = cnt; p.err = cnt + 63;
   const int smem_bytes = w_bytes + stages * a_stage + 1024;
   static bool attr_done[2] = {false, false};
@@ -2133,8 +2135,10 @@ int rows_lstm_seq_bwd(rau_ctx* ctx, const LstmSeqBwd& d, int* done) {
   p.dG = d.dG; p.dG_hi = d.dG_hi; p.dG_lo = d.dG_lo; p.g_t = (long long)B * 4 * H;
   p.dHacc = acc;
   unsigned int* cnt = nullptr;
+  const bool cnt_new = ctx->arena.bufs.find("lstmseq.cntb") == ctx->arena.bufs.end();
   RAU_TRY(ctx->arena.get("lstmseq.cntb", sizeof(unsigned int) * 64, (void**)&cnt));
-  RAU_CHECK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * 64, ctx->stream));
+  if (cnt_new) RAU_CHECK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * 64, ctx->stream));   // (word 63: sticky time-out flag, read by rau_sync)
+  RAU_CHECK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * 63, ctx->stream));
   p.counter = cnt; p.err = cnt + 63;
   static bool attr_done[2] = {false, false};
   if (!attr_done[x3 ? 1 : 0]) {

@@ -198,6 +198,19 @@ int rau_get_precision(rau_ctx* ctx) { return ctx ? ctx->precision : RAU_EINVAL; 
 int rau_sync(rau_ctx* ctx) {
   RAU_REQUIRE(ctx, "ctx == NULL");
   RAU_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  // the persistent recurrence kernels give up on a peer CTA after ~2 s instead of hanging the device: that must not pass
+  // silently (word 63 of their counter blocks)
+  for (const char* name : {"lstmseq.cnt", "lstmseq.cntb"}) {
+    auto it = ctx->arena.bufs.find(name);
+    if (it == ctx->arena.bufs.end() || it->second.p == nullptr) continue;
+    unsigned int flag = 0;
+    RAU_CHECK_CUDA(cudaMemcpy(&flag, (const unsigned int*)it->second.p + 63, sizeof(flag), cudaMemcpyDeviceToHost));
+    if (flag != 0) {
+      cudaMemset((unsigned int*)it->second.p + 63, 0, sizeof(flag));
+      rau_set_error("persistent LSTM recurrence (%s): a CTA timed out waiting for its row tile's peers; results are invalid", name);
+      return RAU_ECUDA;
+    }
+  }
   return RAU_OK;
 }
 

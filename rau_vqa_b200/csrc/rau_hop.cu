@@ -132,6 +132,25 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
   ARENA(Gt, float, "hop.G", B * 4 * H);
   ARENA(prem, float, "hop.prem", B * M);
 
+  // attbymemory's logits Wm h + bm (F:285-290) need the previous state only: in the training step they run on the aux
+  // stream next to q_embed / qatt instead of between them on the chain
+  cudaEvent_t mem_ev = nullptr;
+  if (as && as->head_side && ctx->aux != nullptr && rows_path(ctx, cfg) && sv.hin_pk.hi) {
+    cudaEvent_t ev0 = rau_side_event(ctx);
+    mem_ev = rau_side_event(ctx);
+    RAU_REQUIRE(ev0 != nullptr && mem_ev != nullptr, "cudaEventCreate failed");
+    cudaStream_t chain = ctx->stream;
+    RAU_CHECK_CUDA(cudaEventRecord(ev0, chain));
+    RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->aux, ev0, 0));
+    ctx->stream = ctx->aux;
+    SimtGemm g = lin_fwd(B, S, H, h, H, P.Wm, mem, S);
+    g.bias_n = P.bm;
+    g.Ar_hi = sv.hin_pk.hi; g.Ar_lo = sv.hin_pk.lo; g.Ar_ld = sv.hin_pk.ld;
+    const int rc = rau_contract(ctx, g);
+    ctx->stream = chain;
+    RAU_TRY(rc);
+    RAU_CHECK_CUDA(cudaEventRecord(mem_ev, ctx->aux));
+  }
   // q_embed (F:231-236): qf = tanh(Wq drop(q) + bq + Wh h + bh)
   // (packed twins, training step only: every producer below also writes the bf16 (hi, lo) form its consumers' tcgen05
   // products read, so the chain carries no pack launches)
@@ -164,11 +183,13 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
       g.Ar_hi = sv.qf_pk.hi; g.Ar_lo = sv.qf_pk.lo; g.Ar_ld = sv.qf_pk.ld;
       RAU_TRY(rau_contract(ctx, g));
     }
-    {
+    if (!mem_ev) {
       SimtGemm g = lin_fwd(B, S, H, h, H, P.Wm, mem, S);
       g.bias_n = P.bm;
       g.Ar_hi = sv.hin_pk.hi; g.Ar_lo = sv.hin_pk.lo; g.Ar_ld = sv.hin_pk.ld;
       RAU_TRY(rau_contract(ctx, g));
+    } else {
+      RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, mem_ev, 0));
     }
     if (as && as->pre_done) RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, as->pre_done, 0));
     // attbycontent (F:244-252): logit = ws . tanh(Z + ba + qatt[b])  (bs shifts every logit alike: the softmax drops it)
