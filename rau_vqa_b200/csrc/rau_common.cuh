@@ -91,6 +91,7 @@ struct rau_ctx {
   std::vector<cudaEvent_t> side_ev;
   int side_ev_next = 0;
   int side_ctas = 0;
+  int side_ctas_bwd = 0;                           // the cap for the hops' backward products (dY, gWa, gWi)
   int side_ctas_fwd = 0;                           // the cap while the forward's state-independent products run
   int main_cta_cap = 0;                            // > 0 while the side stream is in use: SMs the chain's split-K products size for
   int rows_cta_cap = 0;                            // > 0 while work is being enqueued on the side stream

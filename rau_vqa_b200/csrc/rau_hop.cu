@@ -475,7 +475,7 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
       RAU_CHECK_CUDA(cudaEventRecord(ev, chain));
       RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->side, ev, 0));
       ctx->stream = ctx->side;
-      ctx->rows_cta_cap = ctx->side_ctas;
+      ctx->rows_cta_cap = ctx->side_ctas_bwd > 0 ? ctx->side_ctas_bwd : ctx->side_ctas;
     }
     int side_rc = RAU_OK;
     do {

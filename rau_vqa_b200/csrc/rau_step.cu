@@ -402,6 +402,9 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     const char* e = getenv("RAU_SIDE_CTAS");
     ctx->side_ctas = e ? atoi(e) : (ctx->sm_count * 4) / 7;   // 84 of 148 SMs measured best on Ours_Full (profiles/README.md)
     if (ctx->side_ctas < 8 || ctx->side_ctas > ctx->sm_count) ctx->side_ctas = ctx->sm_count;
+    const char* eb = getenv("RAU_SIDE_CTAS_BWD");
+    ctx->side_ctas_bwd = eb ? atoi(eb) : 0;
+    if (ctx->side_ctas_bwd < 0 || ctx->side_ctas_bwd > ctx->sm_count) ctx->side_ctas_bwd = 0;
     const char* ef = getenv("RAU_SIDE_CTAS_FWD");
     ctx->side_ctas_fwd = ef ? atoi(ef) : ctx->side_ctas;
     if (ctx->side_ctas_fwd < 8 || ctx->side_ctas_fwd > ctx->sm_count) ctx->side_ctas_fwd = ctx->sm_count;
@@ -690,6 +693,8 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     g2.Ar_hi = pk_du.hi; g2.Ar_lo = pk_du.lo; g2.Ar_ld = pk_du.ld;
     RAU_TRY(rau_contract(ctx, g2));
   }
+  const int main_cap_saved = ctx->main_cta_cap;
+  if (ov_bwd && ctx->side_ctas_bwd > 0 && ctx->sm_count - ctx->side_ctas_bwd >= 16) ctx->main_cta_cap = ctx->sm_count - ctx->side_ctas_bwd;
   // the attention backward's atomic accumulators of every hop, cleared at once (not two memsets inside every hop's chain)
   RAU_CHECK_CUDA(cudaMemsetAsync(st_dqa, 0, sizeof(float) * (size_t)nHop * B * A_, ctx->stream));
   RAU_CHECK_CUDA(cudaMemsetAsync(st_gwsp, 0, sizeof(float) * (size_t)nHop * B * A_, ctx->stream));
@@ -721,6 +726,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     const bool dq_ = train && cfg->p_q > 0;
     RAU_TRY(k_dropout_bwd_sum_hops(ctx, st_dqt, (int64_t)B * Q, nHop, dq_ ? sv[0].qbits : nullptr, bits_stride, drop_scale(cfg->p_q), dq));
   }
+  ctx->main_cta_cap = main_cap_saved;
   rau_phase_mark(ctx, "answering units backward");
   {
     HopStacks st;
