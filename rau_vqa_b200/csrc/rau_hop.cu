@@ -176,7 +176,7 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
     ARENA(slog, float, "hop.slog", R);
     // the feature pack, I = tanh(Wi X + bi) and Z = I Wa^T do not depend on the state: in the training step
     // hop_forward_pre() already ran them on the side stream
-    if (!(as && as->pre_done)) RAU_TRY(hop_forward_pre(ctx, cfg, B, P, X, train, sv));
+    if (!(as && (as->pre_done || as->pre_skip))) RAU_TRY(hop_forward_pre(ctx, cfg, B, P, X, train, sv));
     {
       SimtGemm g = lin_fwd(B, A, M, sv.qf, M, P.Wqa, sv.qatt, A);
       g.bias_n = P.bqa; g.bias_n2 = P.ba;

@@ -72,6 +72,7 @@ bool hop_rows_path(const rau_ctx* ctx, const rau_config* cfg);
 // nothing the previous hop's backward needs: both run on ctx->side while the chain of small kernels advances.
 struct HopAsync {
   cudaEvent_t pre_done = nullptr;    // forward: I of this hop is ready (recorded on the side stream); NULL = compute inline
+  int pre_skip = 0;                  // forward: Xd / I / Z in the saved block are already this hop's (eval mode: hop-invariant)
   int bwd_side = 0;                  // backward: put dY / gWa / gWi on the side stream
   int head_side = 0;                 // forward: the answer head (Wo, dropout, score, do_pred) does not feed the next hop: side stream
   int hop = 0;                       // selects the per-hop dZ buffer when bwd_side

@@ -966,10 +966,18 @@ int rau_predict(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float*
   MultT<const float*> P = mult_views<const float*, const float>(cfg, params[2]);
   HopSaved sv;
   hop_saved_layout(cfg, B, sv_base, &sv);
+  // eval mode has no dropout, so the image side of a hop that does not see the recurrent state -- the feature transpose,
+  // I = tanh(Wi X + bi) and Z = I Wa^T -- is the same for every hop: formed once (nHop x less heavy work)
+  HopAsync shared;
+  const bool hoist = hop_rows_path(ctx, cfg);
+  if (hoist) {
+    RAU_TRY(hop_forward_pre(ctx, cfg, B, P, bt->feats, 0, sv));
+    shared.pre_skip = 1;
+  }
   for (int hp = 0; hp < nHop; ++hp)
     RAU_TRY(hop_forward(ctx, cfg, B, P, en.rnn_out, bt->feats, c_all + (size_t)(hp & 1) * B * H, h_all + (size_t)(hp & 1) * B * H,
                         0, sv, pred + (size_t)hp * B * N, dop + (size_t)hp * B, attp + (size_t)hp * B * S,
-                        c_all + (size_t)((hp + 1) & 1) * B * H, h_all + (size_t)((hp + 1) & 1) * B * H));
+                        c_all + (size_t)((hp + 1) & 1) * B * H, h_all + (size_t)((hp + 1) & 1) * B * H, hoist ? &shared : nullptr));
   // uni = mean over hops, select = first hop with do_pred > 0.5, forced at the last hop (F:699-721)
   RAU_TRY(k_merge_preds(ctx, nHop, B, N, S, pred, dop, attp, nullptr, nullptr, 1, 0.0f, nullptr, nullptr, nullptr,
                         pred + (size_t)nHop * B * N, pred + (size_t)(nHop + 1) * B * N, attp + (size_t)nHop * B * S,
