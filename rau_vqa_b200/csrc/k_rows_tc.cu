@@ -2057,8 +2057,8 @@ int k_attn_rows_bwd(rau_ctx* ctx, int B, int M, int A, int S, const float* E, co
 // when the shape does not fit (the caller then unrolls the per-step EPI_LSTM launches).
 int rows_lstm_seq(rau_ctx* ctx, const LstmSeq& d, int* done) {
   *done = 0;
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("RAU_LSTM_SEQ"); on = e ? atoi(e) : 1; }
+  const char* e_on = getenv("RAU_LSTM_SEQ");   // =0: one launch per recurrent step (read per call: the tests switch it)
+  const int on = e_on ? atoi(e_on) : 1;
   const int B = d.B, H = d.H, T = d.T;
   const bool x3 = d.hpk_lo != nullptr;
   if (!on || H % 64 != 0 || T < 1 || !d.hpk_hi || !d.Wh_hi || (x3 != (d.Wh_lo != nullptr))) return RAU_OK;
@@ -2108,8 +2108,8 @@ int rows_lstm_seq_bwd(rau_ctx* ctx, const LstmSeqBwd& d, int* done) {
   // Opt-in (RAU_LSTM_SEQ_BWD=1): parity-green, but measured SLOWER than the per-step launches (encoder backward 1.05 ms against
   // 0.79 ms alone, 1.29 against 1.23 ms next to the side stream).  With 16 hidden units per CTA the dgrad is a 32-way split-K:
   // 16 MB of fp32 reduce-adds per step against 2-4 MB for the unrolled form, and that traffic, not the launches, is the bound.
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("RAU_LSTM_SEQ_BWD"); on = e ? atoi(e) : 0; }
+  const char* e_on = getenv("RAU_LSTM_SEQ_BWD");   // (read per call: the tests switch it)
+  const int on = e_on ? atoi(e_on) : 0;
   const int B = d.B, H = d.H, T = d.T;
   const bool x3 = d.dG_lo != nullptr;
   if (!on || (H != 256 && H != 512) || T < 1 || !d.dG_hi || !d.Wh_hi || (x3 != (d.Wh_lo != nullptr))) return RAU_OK;

@@ -293,3 +293,31 @@ def test_all_hops_feature_pack_draws_the_same_masks(R):
     for k in O.GROUPS:
         assert rel_err(res[0][0][k], res[1][0][k]) <= 1e-5, k
     assert np.abs(res[0][0]["mult"]).max() > 0
+
+
+@pytest.mark.parametrize("Hq,B,env", [(64, 130, {}), (128, 7, {}), (256, 130, {"RAU_LSTM_SEQ_BWD": "1"}),
+                                      (64, 130, {"RAU_LSTM_SEQ": "0"})])
+def test_persistent_encoder_recurrence(R, Hq, B, env):
+    """The persistent recurrence kernels of the question encoder (lstm_seq_kernel; lstm_seq_bwd_kernel when opted in)
+    against the oracle: two row tiles with a ragged second tile, ragged question lengths, several CTAs per row tile that
+    exchange h_t / dh_t through global memory; and the unrolled per-step form for comparison."""
+    import os
+    from rau_vqa_b200 import core
+    cfg = small_cfg(Hq=Hq, embed=16, T=6, nHop=1)
+    params = O.init_params(cfg, seed=71)
+    X, x, x_len, y = O.synth_batch(cfg, B, seed=72, min_len=1)
+    masks = O.synth_masks(cfg, B, seed=73)
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        c = R.Context(0)
+        c.set_precision(core.PREC_BF16X3)
+        c.mode = "bf16x3"
+        _check_step(c, cfg, params, X, x, x_len, y, masks)
+        c.close()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
