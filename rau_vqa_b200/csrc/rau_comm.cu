@@ -17,6 +17,8 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;   // optional: several all-reduces issued as one launch
+  ncclResult_t (*GroupEnd)() = nullptr;
 };
 
 static NcclApi g_nccl;
@@ -37,6 +39,8 @@ static int nccl_load() {
   a.CommDestroy = (decltype(a.CommDestroy))dlsym(lib, "ncclCommDestroy");
   a.AllReduce = (decltype(a.AllReduce))dlsym(lib, "ncclAllReduce");
   a.GetErrorString = (decltype(a.GetErrorString))dlsym(lib, "ncclGetErrorString");
+  a.GroupStart = (decltype(a.GroupStart))dlsym(lib, "ncclGroupStart");
+  a.GroupEnd = (decltype(a.GroupEnd))dlsym(lib, "ncclGroupEnd");
   if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce || !a.GetErrorString) {
     rau_set_error("libnccl is missing a required symbol");
     return RAU_ENCCL;
@@ -65,6 +69,14 @@ int rau_comm_rank(rau_ctx* ctx) { return ctx->comm ? ctx->comm->rank : 0; }
 int rau_allreduce_internal(rau_ctx* ctx, float* buf, int64_t n) {
   if (!rau_comm_attached(ctx)) return RAU_OK;
   RAU_CHECK_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, ncclFloat32_, ncclSum_, ctx->comm->comm, ctx->stream));
+  return RAU_OK;
+}
+
+// brackets for a batch of rau_allreduce_internal calls: NCCL then launches them as one kernel
+int rau_allreduce_group(rau_ctx* ctx, int begin) {
+  if (!rau_comm_attached(ctx) || !g_nccl.GroupStart || !g_nccl.GroupEnd) return RAU_OK;
+  if (begin) RAU_CHECK_NCCL(g_nccl.GroupStart());
+  else RAU_CHECK_NCCL(g_nccl.GroupEnd());
   return RAU_OK;
 }
 

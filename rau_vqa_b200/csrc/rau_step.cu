@@ -16,6 +16,7 @@ int rau_check_cfg(const rau_config* cfg);
 int rau_check_dev(const void* p, const char* what);
 int rau_prepare_mask(rau_ctx* ctx, uint32_t* bits, int64_t n, float p, int train, const uint8_t* bytes, uint64_t stream_id);
 int rau_allreduce_internal(rau_ctx* ctx, float* buf, int64_t n);   // rau_comm.cu
+int rau_allreduce_group(rau_ctx* ctx, int begin);
 bool rau_comm_attached(rau_ctx* ctx);
 int rau_comm_rank(rau_ctx* ctx);
 
@@ -745,8 +746,22 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
       cudaStream_t chain = ctx->stream;
       ctx->stream = ctx->side;
       ctx->rows_cta_cap = ctx->side_ctas;
-      const int rc = hop_wgrads(ctx, cfg, nHop * B, G, st);
+      int rc = hop_wgrads(ctx, cfg, nHop * B, G, st);
       if (ctx->phases == 2) rau_phase_mark(ctx, "deferred weight gradients done");
+      if (rc == RAU_OK && ctx->ar_early_buf != nullptr && ctx->aux != nullptr) {
+        // every gradient of the answering units is final here (the chain's share was written before the event the side
+        // stream waited for above): all-reduce the group now, on the aux stream, under the encoder backward
+        cudaEvent_t ev_m = rau_side_event(ctx);
+        ctx->ar_early_done = rau_side_event(ctx);
+        if (ev_m == nullptr || ctx->ar_early_done == nullptr || cudaEventRecord(ev_m, ctx->side) != cudaSuccess ||
+            cudaStreamWaitEvent(ctx->aux, ev_m, 0) != cudaSuccess) {
+          rc = RAU_ECUDA;
+        } else {
+          ctx->stream = ctx->aux;
+          rc = rau_allreduce_internal(ctx, ctx->ar_early_buf, ctx->ar_early_n);
+          if (rc == RAU_OK && cudaEventRecord(ctx->ar_early_done, ctx->aux) != cudaSuccess) rc = RAU_ECUDA;
+        }
+      }
       ctx->stream = chain;
       ctx->rows_cta_cap = 0;
       RAU_TRY(rc);
@@ -819,11 +834,22 @@ int rau_optim_step(rau_ctx* ctx, int optim, int64_t n, float* x, const float* dx
 static int train_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float* const params[3],
                          float* const grads[3], float* const opt_state[3][2], const float* hop_mask, const rau_masks* masks,
                          const rau_train_hparams* hp, const rau_step_out* out) {
-  RAU_TRY(feval_enqueue(ctx, cfg, bt, params, grads, hop_mask, masks, out));
-  if (rau_comm_attached(ctx)) {   // data parallel: one sum over ranks of each flat gradient
-    for (int g = 0; g < 3; ++g) RAU_TRY(rau_allreduce_internal(ctx, grads[g], rau_group_size(cfg, g)));
+  const bool dp = rau_comm_attached(ctx);
+  ctx->ar_early_done = nullptr;
+  ctx->ar_early_buf = dp ? grads[2] : nullptr;
+  ctx->ar_early_n = dp ? rau_group_size(cfg, 2) : 0;
+  const int rc_f = feval_enqueue(ctx, cfg, bt, params, grads, hop_mask, masks, out);
+  ctx->ar_early_buf = nullptr;
+  RAU_TRY(rc_f);
+  if (dp) {   // data parallel: one sum over ranks of each flat gradient, the small ones as one launch
+    cudaEvent_t early = ctx->ar_early_done;   // set when the mult group's all-reduce already went out on the aux stream
+    ctx->ar_early_done = nullptr;
+    RAU_TRY(rau_allreduce_group(ctx, 1));
+    for (int g = 0; g < (early ? 2 : 3); ++g) RAU_TRY(rau_allreduce_internal(ctx, grads[g], rau_group_size(cfg, g)));
     if (out && out->loss) RAU_TRY(rau_allreduce_internal(ctx, out->loss, cfg->nHop + 2));
     if (out && out->loss_do_pred) RAU_TRY(rau_allreduce_internal(ctx, out->loss_do_pred, cfg->nHop));
+    RAU_TRY(rau_allreduce_group(ctx, 0));
+    if (early) RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, early, 0));
   }
   ARENA(norm2, double, "opt.norm2", 4);
   RAU_CHECK_CUDA(cudaMemsetAsync(norm2, 0, sizeof(double) * 4, ctx->stream));
