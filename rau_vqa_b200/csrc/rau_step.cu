@@ -646,6 +646,28 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     RAU_TRY(rau_contract(ctx, g));
     for (int hp = 0; hp < nHop; ++hp) sv[hp].qpre = st_qpre + (size_t)hp * B * M_;
   }
+  // The answer head's backward needs forward results only: du = drop'(dscore Ws) and Wo^T du for a range of hops in two
+  // products over their stacked rows (dscore already carries the hop mask and 1/B_global)
+  ARENA(st_dh2h, float, "stack.dh2h", (size_t)nHop * B * H);
+  auto head_backward = [&](int h0, int nh) -> int {
+    const size_t r0 = (size_t)h0 * B;
+    const PK dsc = slice(pk_dscore, r0), dup = slice(pk_du, r0);
+    SimtGemm g = lin_dgrad(nh * B, N, M_, dscore + r0 * N, N, P.Ws, st_du + r0 * M_, M_);
+    g.Ar_hi = dsc.hi; g.Ar_lo = dsc.lo; g.Ar_ld = dsc.ld;
+    RAU_TRY(rau_contract(ctx, g));
+    const bool dm_ = train && cfg->p_m > 0;
+    RAU_TRY(k_dropout_bwd_hops(ctx, st_du + r0 * M_, (int64_t)B * M_, nh, dm_ ? sv[h0].mbits : nullptr, bits_stride,
+                               drop_scale(cfg->p_m), dup.hi, ctx->precision == RAU_PREC_BF16X3 ? dup.lo : nullptr));
+    SimtGemm g2 = lin_dgrad(nh * B, M_, H, st_du + r0 * M_, M_, P.Wo, st_dh2h + r0 * H, H);
+    g2.Ar_hi = dup.hi; g2.Ar_lo = dup.lo; g2.Ar_ld = dup.ld;
+    return rau_contract(ctx, g2);
+  };
+  cudaEvent_t head_early_done = nullptr;
+  // RAU_HEAD_EARLY=1: head backward of hops 0 .. nHop-2 on the aux stream during the last hop's forward and the logging losses
+  // on the side stream.  Measured 1 % SLOWER in three A/B pairs on one box (4.87 vs 4.81 ms: the extra launches contend
+  // with the last hop's chain), so the whole head backward stays between the two unrolls by default.
+  const char* e_he = getenv("RAU_HEAD_EARLY");
+  const bool head_early_on = e_he && atoi(e_he) != 0;
   for (int hp = 0; hp < nHop; ++hp) {
     RAU_TRY(hop_forward(ctx, cfg, B, P, en.rnn_out, bt->feats, c_all + (size_t)hp * B * H, h_all + (size_t)hp * B * H, train,
                         sv[hp], scores + (size_t)hp * B * N, dop + (size_t)hp * B, att + (size_t)hp * B * S,
@@ -662,6 +684,20 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     if (ctx->phases == 2) rau_phase_mark(ctx, "hop head + criterion done");
     ctx->stream = chain;
     RAU_TRY(rc_ce);
+    if (ov_head && hp == nHop - 2 && ctx->aux != nullptr && nHop >= 2 && head_early_on) {
+      // dscore of hops 0 .. nHop-2 is final on the side stream: their head backward runs on the aux stream while the last
+      // hop's forward is still on the chain, so only the last hop's share sits between the two unrolls
+      cudaEvent_t ev = rau_side_event(ctx);
+      head_early_done = rau_side_event(ctx);
+      RAU_REQUIRE(ev != nullptr && head_early_done != nullptr, "cudaEventCreate failed");
+      RAU_CHECK_CUDA(cudaEventRecord(ev, ctx->side));
+      RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->aux, ev, 0));
+      ctx->stream = ctx->aux;
+      const int rc_h = head_backward(0, nHop - 1);
+      ctx->stream = chain;
+      RAU_TRY(rc_h);
+      RAU_CHECK_CUDA(cudaEventRecord(head_early_done, ctx->aux));
+    }
   }
   if (ov_head) {   // scores, do_pred, losses and dscore of every hop are complete before the merge and the backward unroll
     cudaEvent_t ev = rau_side_event(ctx);
@@ -670,9 +706,16 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, ev, 0));
   }
   rau_phase_mark(ctx, "answering units forward");
-  // logging-only losses on the averaged / selected predictions and the do_pred BCE (F:539-574)
-  RAU_TRY(k_merge_preds(ctx, nHop, B, N, S, scores, dop, nullptr, bt->labels, ans, 0, 1.0f / Bg, loss + nHop, loss_dp,
-                        ans + (size_t)nHop * B, nullptr, nullptr, nullptr, nullptr));
+  // logging-only losses on the averaged / selected predictions and the do_pred BCE (F:539-574): nothing in the backward
+  // pass reads them, so with the heads on the side stream they stay there (behind the event the chain just waited for)
+  {
+    cudaStream_t chain = ctx->stream;
+    if (ov_head && head_early_on) ctx->stream = ctx->side;
+    const int rc_m = k_merge_preds(ctx, nHop, B, N, S, scores, dop, nullptr, bt->labels, ans, 0, 1.0f / Bg, loss + nHop, loss_dp,
+                                   ans + (size_t)nHop * B, nullptr, nullptr, nullptr, nullptr);
+    ctx->stream = chain;
+    RAU_TRY(rc_m);
+  }
 
   rau_phase_mark(ctx, "merged losses");
   // BPTT through the hops (F:578-597); do_pred and attprob receive zero gradient (F:582-583, F:592)
@@ -681,18 +724,12 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   ARENA(dq, float, "step.dq", (size_t)B * Q);
   // The answer head's backward needs forward results only: du = drop'(dscore Ws) and Wo^T du of every hop in two products
   // over nHop*B rows before the unroll (dscore already carries the hop mask and 1/B_global)
-  ARENA(st_dh2h, float, "stack.dh2h", (size_t)nHop * B * H);
   ARENA(st_dqt, float, "stack.dqt", (size_t)nHop * B * Q);
-  {
-    SimtGemm g = lin_dgrad(nHop * B, N, M_, dscore, N, P.Ws, st_du, M_);
-    g.Ar_hi = pk_dscore.hi; g.Ar_lo = pk_dscore.lo; g.Ar_ld = pk_dscore.ld;
-    RAU_TRY(rau_contract(ctx, g));
-    const bool dm_ = train && cfg->p_m > 0;
-    RAU_TRY(k_dropout_bwd_hops(ctx, st_du, (int64_t)B * M_, nHop, dm_ ? sv[0].mbits : nullptr, bits_stride, drop_scale(cfg->p_m),
-                               pk_du.hi, ctx->precision == RAU_PREC_BF16X3 ? pk_du.lo : nullptr));
-    SimtGemm g2 = lin_dgrad(nHop * B, M_, H, st_du, M_, P.Wo, st_dh2h, H);
-    g2.Ar_hi = pk_du.hi; g2.Ar_lo = pk_du.lo; g2.Ar_ld = pk_du.ld;
-    RAU_TRY(rau_contract(ctx, g2));
+  if (head_early_done) {   // hops 0 .. nHop-2 were done on the aux stream during the last hop's forward: only the last hop is left
+    RAU_TRY(head_backward(nHop - 1, 1));
+    RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, head_early_done, 0));
+  } else {
+    RAU_TRY(head_backward(0, nHop));
   }
   const int main_cap_saved = ctx->main_cta_cap;
   if (ov_bwd && ctx->side_ctas_bwd > 0 && ctx->sm_count - ctx->side_ctas_bwd >= 16) ctx->main_cta_cap = ctx->sm_count - ctx->side_ctas_bwd;
