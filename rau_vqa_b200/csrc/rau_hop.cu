@@ -135,7 +135,8 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
   // attbymemory's logits Wm h + bm (F:285-290) need the previous state only: in the training step they run on the aux
   // stream next to q_embed / qatt instead of between them on the chain
   cudaEvent_t mem_ev = nullptr;
-  if (as && as->head_side && ctx->aux != nullptr && rows_path(ctx, cfg) && sv.hin_pk.hi) {
+  const char* e_ma = getenv("RAU_MEM_AUX");   // =0: keep the memory logits on the chain (A/B switch)
+  if (as && as->head_side && ctx->aux != nullptr && rows_path(ctx, cfg) && sv.hin_pk.hi && !(e_ma && atoi(e_ma) == 0)) {
     cudaEvent_t ev0 = rau_side_event(ctx);
     mem_ev = rau_side_event(ctx);
     RAU_REQUIRE(ev0 != nullptr && mem_ev != nullptr, "cudaEventCreate failed");

@@ -555,7 +555,8 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
                                stream_of(step_t, SK_X, hp, rank)));
     }
   }
-  if (prep_aux && ctx->precision != RAU_PREC_F32 && hop_rows_path(ctx, cfg) && rows_path_enabled()) {
+  const char* e_pp = getenv("RAU_PREPACK");   // =0: pack each weight shadow at its first use (A/B switch)
+  if (prep_aux && ctx->precision != RAU_PREC_F32 && hop_rows_path(ctx, cfg) && rows_path_enabled() && !(e_pp && atoi(e_pp) == 0)) {
     // the bf16 (hi, lo) shadows of the weights the chain's products read: packed here, next to the encoder, instead of
     // inline at their first use on the chain (the per-epoch cache makes the later calls no-ops)
     const bool x3 = ctx->precision == RAU_PREC_BF16X3;
