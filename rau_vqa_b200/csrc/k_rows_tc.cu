@@ -1164,18 +1164,47 @@ __global__ void __launch_bounds__(256) attn_rows_score_kernel(int R, int S, int 
 // attbymemory + attselect on the rows layout (F:285-290, F:254-263): p = softmax(logit + mem), a = sum_s p_s I[b*S+s, :]
 // grid (B, M/256), 256 threads: a CTA owns 256 channels of one image; 32 threads cover a row slice with 16-byte loads,
 // 8 row groups walk the image in parallel (HBM-bound: I hi+lo is read exactly once)
+// SCORE != 0: `logit` is not read; the CTA first forms its image's content logits itself, ws . tanh(Z[r,:] + qadd[b,:])
+// (the attn_rows_score_kernel pass fused in: one launch less on the recurrent chain; both channel halves of an image redo
+// the 196 logits, the second read of Z comes out of L2).  1 = accurate tanh, 2 = MUFU.TANH.
+template <int SCORE>
 __global__ void __launch_bounds__(256) attn_rows_fwd_kernel(int S, int M, const float* __restrict__ logit,
                                                             const float* __restrict__ mem, const bf16* __restrict__ I_hi,
                                                             const bf16* __restrict__ I_lo, float* __restrict__ p_out,
                                                             float* __restrict__ a_out, bf16* __restrict__ p_hi,
-                                                            bf16* __restrict__ p_lo, int ldp) {
+                                                            bf16* __restrict__ p_lo, int ldp, int A, const float* __restrict__ Z,
+                                                            const float* __restrict__ qadd, const float* __restrict__ ws) {
   RAU_PDL_ENTRY();
   __shared__ float p[256];
   __shared__ float part[8][256];
   __shared__ float red[32];
   const int b = blockIdx.x, tid = threadIdx.x, c0 = blockIdx.y * 256;
   const int64_t r0 = (int64_t)b * S;
-  const float l0 = tid < S ? logit[r0 + tid] + mem[r0 + tid] : -INFINITY;
+  if (SCORE) {
+    const int wq = tid >> 5, ln = tid & 31, a4 = A >> 2;
+    for (int s0 = wq * 2; s0 < S; s0 += 16) {   // a warp takes two rows at a time (independent loads in flight)
+      float acc0 = 0.0f, acc1 = 0.0f;
+      const int s1 = min(s0 + 1, S - 1);
+      for (int w = ln; w < a4; w += 32) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(ws) + w);
+        const float4 q4 = __ldg(reinterpret_cast<const float4*>(qadd + (int64_t)b * A) + w);
+        const float4 z0 = __ldg(reinterpret_cast<const float4*>(Z + (r0 + s0) * A) + w);
+        const float4 z1 = __ldg(reinterpret_cast<const float4*>(Z + (r0 + s1) * A) + w);
+#define RAU_T(x) (SCORE == 2 ? tanh_hw(x) : tanh_acc(x))
+        acc0 = fmaf(w4.x, RAU_T(z0.x + q4.x), acc0); acc0 = fmaf(w4.y, RAU_T(z0.y + q4.y), acc0);
+        acc0 = fmaf(w4.z, RAU_T(z0.z + q4.z), acc0); acc0 = fmaf(w4.w, RAU_T(z0.w + q4.w), acc0);
+        acc1 = fmaf(w4.x, RAU_T(z1.x + q4.x), acc1); acc1 = fmaf(w4.y, RAU_T(z1.y + q4.y), acc1);
+        acc1 = fmaf(w4.z, RAU_T(z1.z + q4.z), acc1); acc1 = fmaf(w4.w, RAU_T(z1.w + q4.w), acc1);
+#undef RAU_T
+      }
+      acc0 = warp_sum(acc0); acc1 = warp_sum(acc1);
+      if (ln == 0) { p[s0] = acc0; if (s0 + 1 < S) p[s0 + 1] = acc1; }
+    }
+    __syncthreads();
+  }
+  const float lc = SCORE ? (tid < S ? p[tid] : 0.0f) : (tid < S ? logit[r0 + tid] : 0.0f);
+  if (SCORE) __syncthreads();   // p[] is rewritten with the probabilities below
+  const float l0 = tid < S ? lc + mem[r0 + tid] : -INFINITY;
   const float mx = block_max(l0, red);
   const float e0 = tid < S ? __expf(l0 - mx) : 0.0f;
   const float den = block_sum(e0, red);
@@ -2009,7 +2038,23 @@ int k_unprep_rows(rau_ctx* ctx, const float* dXr, int B, int C, int S, const uin
 int k_attn_rows_fwd(rau_ctx* ctx, int B, int M, int S, const float* logit, const float* mem, const bf16* I_hi, const bf16* I_lo,
                     float* p, float* a, bf16* p_hi, bf16* p_lo, int ldp) {
   RAU_REQUIRE(M % 256 == 0 && S <= 256 && ldp <= 256, "k_attn_rows_fwd: M=%d S=%d", M, S);
-  RAU_LAUNCH_PDL(ctx->stream, (attn_rows_fwd_kernel), dim3(B, M / 256), 256, 0, S, M, logit, mem, I_hi, I_lo, p, a, p_hi, p_lo, ldp);
+  RAU_LAUNCH_PDL(ctx->stream, (attn_rows_fwd_kernel<0>), dim3(B, M / 256), 256, 0, S, M, logit, mem, I_hi, I_lo, p, a, p_hi, p_lo, ldp,
+                 0, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+
+// content logits + attbymemory + attselect in one launch (see attn_rows_fwd_kernel<SCORE>)
+int k_attn_rows_fwd_scored(rau_ctx* ctx, int B, int M, int A, int S, const float* Z, const float* qadd, const float* ws,
+                           int fast_tanh, const float* mem, const bf16* I_hi, const bf16* I_lo, float* p, float* a, bf16* p_hi,
+                           bf16* p_lo, int ldp) {
+  RAU_REQUIRE(M % 256 == 0 && S <= 256 && ldp <= 256 && A % 4 == 0, "k_attn_rows_fwd_scored: M=%d A=%d S=%d", M, A, S);
+  if (fast_tanh)
+    RAU_LAUNCH_PDL(ctx->stream, (attn_rows_fwd_kernel<2>), dim3(B, M / 256), 256, 0, S, M, (const float*)nullptr, mem, I_hi, I_lo, p, a,
+                   p_hi, p_lo, ldp, A, Z, qadd, ws);
+  else
+    RAU_LAUNCH_PDL(ctx->stream, (attn_rows_fwd_kernel<1>), dim3(B, M / 256), 256, 0, S, M, (const float*)nullptr, mem, I_hi, I_lo, p, a,
+                   p_hi, p_lo, ldp, A, Z, qadd, ws);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }

@@ -194,9 +194,18 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
     }
     if (as && as->pre_done) RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, as->pre_done, 0));
     // attbycontent (F:244-252): logit = ws . tanh(Z + ba + qatt[b])  (bs shifts every logit alike: the softmax drops it)
-    RAU_TRY(k_attn_rows_score(ctx, B, A, S, sv.E, sv.qatt, P.ws, x3 ? 0 : 1, slog));
-    RAU_TRY(k_attn_rows_fwd(ctx, B, M, S, slog, mem, sv.I_hi, x3 ? sv.I_lo : nullptr, sv.p, a, sv.p_pk.hi,
-                            x3 ? sv.p_pk.lo : nullptr, (int)sv.p_pk.ld));
+    // RAU_ATTN_FUSED=1 folds the content-logit pass into the softmax / weighted-sum launch (one launch less per hop): three
+    // A/B pairs on one box measured it SLOWER (5.00 vs 4.90 ms: both channel halves of an image redo the logits and the
+    // two phases no longer overlap across CTAs), so the two launches stay
+    const char* e_af = getenv("RAU_ATTN_FUSED");
+    if (!(e_af && atoi(e_af) != 0)) {
+      RAU_TRY(k_attn_rows_score(ctx, B, A, S, sv.E, sv.qatt, P.ws, x3 ? 0 : 1, slog));
+      RAU_TRY(k_attn_rows_fwd(ctx, B, M, S, slog, mem, sv.I_hi, x3 ? sv.I_lo : nullptr, sv.p, a, sv.p_pk.hi,
+                              x3 ? sv.p_pk.lo : nullptr, (int)sv.p_pk.ld));
+    } else {
+      RAU_TRY(k_attn_rows_fwd_scored(ctx, B, M, A, S, sv.E, sv.qatt, P.ws, x3 ? 0 : 1, mem, sv.I_hi, x3 ? sv.I_lo : nullptr, sv.p, a,
+                                     sv.p_pk.hi, x3 ? sv.p_pk.lo : nullptr, (int)sv.p_pk.ld));
+    }
   } else {
   // i_embed (F:238-242): I[b] = tanh(Wi drop(X[b]) + bi), 1x1 convolution = per-image [M,C]x[C,S] product
   if (tc) RAU_TRY(k_dropout_pack(ctx, X, (int64_t)B * C, S, xb, drop_scale(cfg->p_x), sv.Xd_hi, x3 ? sv.Xd_lo : nullptr, Sp));

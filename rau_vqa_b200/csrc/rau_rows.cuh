@@ -90,6 +90,9 @@ int rows_lstm_seq_bwd(rau_ctx* ctx, const LstmSeqBwd& d, int* done);
 // logit[r] = ws . tanh(Z[r,:] + qadd[b(r),:])  (Z = I Wa^T precomputed; qadd = Wqa qf + bqa + ba)
 int k_attn_rows_score(rau_ctx* ctx, int B, int A, int S, const float* Z, const float* qadd, const float* ws, int fast_tanh,
                       float* logit);
+int k_attn_rows_fwd_scored(rau_ctx* ctx, int B, int M, int A, int S, const float* Z, const float* qadd, const float* ws,
+                           int fast_tanh, const float* mem, const bf16* I_hi, const bf16* I_lo, float* p, float* a,
+                           bf16* p_hi = nullptr, bf16* p_lo = nullptr, int ldp = 0);
 int k_attn_rows_bwd(rau_ctx* ctx, int B, int M, int A, int S, const float* E, const bf16* I_hi, const bf16* I_lo, const float* ws,
                     const float* p, const float* dp_in, const float* da, float* ds, bf16* dZ_hi, bf16* dZ_lo, float* dqa,
                     float* gws_part, bf16* ds_hi = nullptr, bf16* ds_lo = nullptr, int ldds = 0,
