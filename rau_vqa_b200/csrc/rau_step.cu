@@ -393,8 +393,8 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   rau_phase_mark(ctx, "begin");
   // cross-stream overlap (rows path): RAU_OVERLAP bit 0 = heavy backward products on the side stream, bit 1 = the
   // state-independent i_embed products of all hops on the side stream, next to the encoder and the chain
-  static int overlap_mode = -1;
-  if (overlap_mode < 0) { const char* e = getenv("RAU_OVERLAP"); overlap_mode = e ? atoi(e) : 7; }
+  const char* e_ov = getenv("RAU_OVERLAP");   // (read per call: the tests switch it)
+  const int overlap_mode = e_ov ? atoi(e_ov) : 7;
   const bool rows_hops = hop_rows_path(ctx, cfg) && ctx->side != nullptr;
   const bool ov_bwd = rows_hops && (overlap_mode & 1);
   const bool ov_fwd = rows_hops && (overlap_mode & 2);

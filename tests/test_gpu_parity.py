@@ -321,3 +321,31 @@ def test_persistent_encoder_recurrence(R, Hq, B, env):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+
+
+@pytest.mark.parametrize("env", [{"RAU_ATTN_FUSED": "1"}, {"RAU_HEAD_EARLY": "1"}, {"RAU_MEM_AUX": "0", "RAU_PREPACK": "0"},
+                                 {"RAU_OVERLAP": "0"}])
+def test_opt_in_schedules_match_oracle(R, env):
+    """The alternative schedules kept behind switches (fused content logits, early head backward, no aux-stream work, a
+    single stream) compute the same step: Ours_SS-shaped step against the oracle."""
+    import os
+    from rau_vqa_b200 import core
+    cfg = O.RauConfig(V=2000, C=512, nHop=2, N=2000)
+    B = 4
+    params = O.init_params(cfg, seed=123)
+    X, x, x_len, y = O.synth_batch(cfg, B, seed=124)
+    masks = O.synth_masks(cfg, B, seed=125)
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        c = R.Context(0)
+        c.set_precision(core.PREC_BF16X3)
+        c.mode = "bf16x3"
+        _check_step(c, cfg, params, X, x, x_len, y, masks)
+        c.close()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
