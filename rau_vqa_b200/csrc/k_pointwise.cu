@@ -576,7 +576,7 @@ __global__ void sum_all_acc_kernel(const float* __restrict__ x, int64_t n, float
 }
 
 int k_sum_all(rau_ctx* ctx, const float* x, int64_t n, float* out, int accumulate) {
-  if (accumulate && n >= 65536) {
+  if (accumulate && n >= 1024) {
     RAU_LAUNCH_PDL(ctx->stream, (sum_all_acc_kernel), (int)((n + 4095) / 4096 < 148 ? (n + 4095) / 4096 : 148), 256, 0, x, n, out);
     RAU_LAUNCH_CHECK(ctx);
     return RAU_OK;
