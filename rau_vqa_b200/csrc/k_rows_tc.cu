@@ -1133,8 +1133,11 @@ __global__ void __launch_bounds__(256) attn_rows_score_kernel(int R, int S, int 
                                                               float* __restrict__ logit) {
   RAU_PDL_ENTRY();
   const int lane = threadIdx.x & 31;
-  const int rbase = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 4;
   const int a4 = A >> 2;
+  // a warp walks batches of 4 rows, warps_total batches apart (the grid is sized to one resident wave)
+  const int nb = (R + 3) >> 2, wstride = gridDim.x * 8;
+  for (int batch = blockIdx.x * 8 + (threadIdx.x >> 5); batch < nb; batch += wstride) {
+  const int rbase = batch * 4;
   float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   for (int w = lane; w < a4; w += 32) {
     const float4 w4 = __ldg(reinterpret_cast<const float4*>(ws) + w);
@@ -1158,6 +1161,7 @@ __global__ void __launch_bounds__(256) attn_rows_score_kernel(int R, int S, int 
   for (int i = 0; i < 4; ++i) {
     const float v = warp_sum(acc[i]);
     if (lane == 0 && rbase + i < R) logit[rbase + i] = v;
+  }
   }
 }
 
@@ -2063,8 +2067,14 @@ int k_attn_rows_score(rau_ctx* ctx, int B, int A, int S, const float* Z, const f
                       float* logit) {
   RAU_REQUIRE(A % 4 == 0, "k_attn_rows_score: A=%d", A);
   const int R = B * S;
-  if (fast_tanh) RAU_LAUNCH_PDL(ctx->stream, (attn_rows_score_kernel<1>), (R + 31) / 32, 256, 0, R, S, A, Z, qadd, ws, logit);
-  else RAU_LAUNCH_PDL(ctx->stream, (attn_rows_score_kernel<0>), (R + 31) / 32, 256, 0, R, S, A, Z, qadd, ws, logit);
+  int grid = (R + 31) / 32;
+  const char* e_w = getenv("RAU_SCORE_WAVE");   // =0: one batch of 4 rows per warp (1.3 waves at B = 256); default: one wave
+  if (!(e_w && atoi(e_w) == 0)) {
+    const int one_wave = ctx->sm_count * 6;   // 6 CTAs of 256 threads per SM
+    if (grid > one_wave) grid = (grid + 1) / 2 <= one_wave ? (grid + 1) / 2 : one_wave;
+  }
+  if (fast_tanh) RAU_LAUNCH_PDL(ctx->stream, (attn_rows_score_kernel<1>), grid, 256, 0, R, S, A, Z, qadd, ws, logit);
+  else RAU_LAUNCH_PDL(ctx->stream, (attn_rows_score_kernel<0>), grid, 256, 0, R, S, A, Z, qadd, ws, logit);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
