@@ -349,3 +349,60 @@ def test_opt_in_schedules_match_oracle(R, env):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+
+
+def test_full_size_three_stream_schedule_equals_single_stream(R):
+    """The benchmark configuration (Ours_Full, B = 256: 64-CTA persistent recurrence next to 84-CTA side-stream products,
+    the all-hops feature pack, aux-stream work, whole-step CUDA graph) against the same step enqueued eagerly on ONE stream
+    with the unrolled / per-hop forms.  Same Philox streams, so losses and gradients agree to summation-order noise; a
+    missing cross-stream dependency shows up as a much larger difference.  (lr = 0, no noise, no clipping: rau_train_step
+    leaves the raw gradients in place and the parameters unchanged, so the 3rd and 4th call replay the captured graph.)"""
+    import os
+    import torch
+    import rau_vqa_b200 as RR
+    from rau_vqa_b200 import core
+    cfg = RR.RauConfig(V=16384, C=512, nHop=8, N=2000)
+    B = 256
+    rng = np.random.default_rng(5)
+    X = dev(np.maximum(rng.standard_normal((B, 512, 196), dtype=np.float32), 0))
+    lens = rng.integers(4, 27, B)
+    tok = rng.integers(2, cfg.V + 1, (cfg.T, B))
+    for b in range(B):
+        tok[lens[b]:, b] = 1
+    tok, lens_d, y = dev(tok), dev(lens), dev(rng.integers(1, cfg.N + 1, B))
+    gen = torch.Generator(device="cpu").manual_seed(9)
+    P0 = [(torch.rand(cfg.group_size(g), generator=gen) * 0.16 - 0.08) for g in range(3)]
+    single = {"RAU_OVERLAP": "0", "RAU_GRAPH": "0", "RAU_LSTM_SEQ": "0", "RAU_XPREP_HOPS": "0", "RAU_MEM_AUX": "0", "RAU_PREPACK": "0"}
+    res = []
+    for env in ({}, single):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            c = RR.Context(0, seed=21)
+            P = [p.clone().cuda() for p in P0]
+            G = [torch.zeros_like(p) for p in P]
+            ST = [[torch.zeros_like(p), torch.zeros_like(p)] for p in P]
+            out = RR.StepBuffers(cfg, B, X.device, want_scores=False)
+            outs = []
+            for rep in range(4):
+                core.train_step(c, cfg, P, G, ST, X, tok, lens_d, y, out, optim=core.OPT_ADAM, lrs=(0.0, 0.0, 0.0),
+                                hyper=(0.9, 0.999, 1e-8), eta=0.0, gamma=0.55, clip=1e9, step_t=3, max_len=26, B_global=B)
+                c.sync()
+                outs.append(([g.cpu().numpy().astype(np.float64) for g in G], out.loss.cpu().numpy().copy()))
+            for p, p0 in zip(P, P0):
+                assert torch.equal(p.cpu(), p0)
+            res.append(outs)
+            c.close()
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+    ref_g, ref_l = res[1][0]
+    assert np.isfinite(ref_l).all() and ref_l[:cfg.nHop].min() > 1.0
+    for outs in res:
+        for g, l in outs:
+            np.testing.assert_allclose(l, ref_l, rtol=2e-5)
+            for k in range(3):
+                assert rel_err(g[k], ref_g[k]) <= 5e-5, k
