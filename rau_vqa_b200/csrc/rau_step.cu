@@ -609,7 +609,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     int rc = RAU_OK;
     // drawn feature masks: the feature pack of all hops in one launch (the fp32 features are read once, not nHop times)
     const char* e_xh = getenv("RAU_XPREP_HOPS");   // =0: one pack launch per hop (same bits; tests compare the two)
-    bool all_philox = train && cfg->p_x > 0 && nHop > 1 && nHop < 65536 && !(e_xh && atoi(e_xh) == 0);
+    bool all_philox = train && cfg->p_x > 0 && nHop > 1 && nHop < 65536 && S <= 200 && !(e_xh && atoi(e_xh) == 0);   // (S: its smem slabs)
     for (int hp = 0; hp < nHop; ++hp) all_philox = all_philox && sv[hp].x_philox;
     if (all_philox) {
       rc = k_xprep_rows_hops(ctx, bt->feats, B, cfg->C, S, nHop, drop_scale(cfg->p_x), sv[0].Xd_hi,
