@@ -8,6 +8,7 @@
 #include <vector>
 #include <map>
 #include <string>
+#include <functional>
 #include "../../include/rau.h"
 
 typedef __nv_bfloat16 bf16;
@@ -93,11 +94,11 @@ struct rau_ctx {
   int side_ctas = 0;
   int side_ctas_bwd = 0;                           // the cap for the hops' backward products (dY, gWa, gWi)
   int side_ctas_fwd = 0;                           // the cap while the forward's state-independent products run
-  // data parallel: the answering units' gradient group is complete once the side stream has run the deferred weight
-  // gradients, long before the encoder backward ends: its all-reduce is issued there on the aux stream (train step only)
-  float* ar_early_buf = nullptr;
-  int64_t ar_early_n = 0;
-  cudaEvent_t ar_early_done = nullptr;
+  // the answering units' gradient group is complete once the side stream has run the deferred weight gradients, long
+  // before the encoder backward ends: the rest of that group's step (all-reduce when data parallel, gradient noise + norm,
+  // clip + optimizer) is issued there on the aux stream (train step only)
+  std::function<int()> early_tail;          // set by the train step: [all-reduce,] noise + norm, clip + optimizer of group 2
+  cudaEvent_t early_tail_done = nullptr;    // recorded on the aux stream behind it (NULL: it did not run)
   int main_cta_cap = 0;                            // > 0 while the side stream is in use: SMs the chain's split-K products size for
   int rows_cta_cap = 0;                            // > 0 while work is being enqueued on the side stream
   // RAU_PHASES=1: eager steps with an event at every phase boundary; rau_phase_report() prints the split

@@ -786,18 +786,20 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
       ctx->rows_cta_cap = ctx->side_ctas;
       int rc = hop_wgrads(ctx, cfg, nHop * B, G, st);
       if (ctx->phases == 2) rau_phase_mark(ctx, "deferred weight gradients done");
-      if (rc == RAU_OK && ctx->ar_early_buf != nullptr && ctx->aux != nullptr) {
+      if (rc == RAU_OK && ctx->early_tail && ctx->aux != nullptr) {
         // every gradient of the answering units is final here (the chain's share was written before the event the side
-        // stream waited for above): all-reduce the group now, on the aux stream, under the encoder backward
+        // stream waited for above): the rest of this group's step runs now, on the aux stream, under the encoder backward
         cudaEvent_t ev_m = rau_side_event(ctx);
-        ctx->ar_early_done = rau_side_event(ctx);
-        if (ev_m == nullptr || ctx->ar_early_done == nullptr || cudaEventRecord(ev_m, ctx->side) != cudaSuccess ||
+        cudaEvent_t done = rau_side_event(ctx);
+        if (ev_m == nullptr || done == nullptr || cudaEventRecord(ev_m, ctx->side) != cudaSuccess ||
             cudaStreamWaitEvent(ctx->aux, ev_m, 0) != cudaSuccess) {
           rc = RAU_ECUDA;
         } else {
           ctx->stream = ctx->aux;
-          rc = rau_allreduce_internal(ctx, ctx->ar_early_buf, ctx->ar_early_n);
-          if (rc == RAU_OK && cudaEventRecord(ctx->ar_early_done, ctx->aux) != cudaSuccess) rc = RAU_ECUDA;
+          ctx->rows_cta_cap = 0;
+          rc = ctx->early_tail();
+          if (rc == RAU_OK && cudaEventRecord(done, ctx->aux) != cudaSuccess) rc = RAU_ECUDA;
+          if (rc == RAU_OK) ctx->early_tail_done = done;
         }
       }
       ctx->stream = chain;
@@ -873,32 +875,38 @@ static int train_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
                          float* const grads[3], float* const opt_state[3][2], const float* hop_mask, const rau_masks* masks,
                          const rau_train_hparams* hp, const rau_step_out* out) {
   const bool dp = rau_comm_attached(ctx);
-  ctx->ar_early_done = nullptr;
-  ctx->ar_early_buf = dp ? grads[2] : nullptr;
-  ctx->ar_early_n = dp ? rau_group_size(cfg, 2) : 0;
+  ARENA(norm2, double, "opt.norm2", 4);
+  RAU_CHECK_CUDA(cudaMemsetAsync(norm2, 0, sizeof(double) * 4, ctx->stream));
+  const float std_flag = (hp->eta > 0.0f && hp->gamma > 0.0f) ? 1.0f : 0.0f;   // the value itself is StepState.noise_std
+  auto finish_group = [&](int g) -> int {   // gradient noise + norm, then per-group clip + the optimizer rule (F:617-648, F:788-790)
+    RAU_TRY(k_noise_norm(ctx, grads[g], rau_group_size(cfg, g), std_flag, hp->noise_override ? hp->noise_override[g] : nullptr,
+                         ctx->seed, stream_of(0, SK_NOISE, g, 0), norm2 + g));
+    return k_clip_optim(ctx, hp->optim, rau_group_size(cfg, g), params[g], grads[g], norm2 + g, hp->clip, hp->lr[g], hp->h0,
+                        hp->h1, hp->h2, opt_state ? opt_state[g][0] : nullptr, opt_state ? opt_state[g][1] : nullptr, 1,
+                        (out && out->norms) ? out->norms + g : nullptr, g);
+  };
+  // RAU_EARLY_TAIL=0 keeps the whole tail behind the join (A/B switch)
+  const char* e_et = getenv("RAU_EARLY_TAIL");
+  ctx->early_tail_done = nullptr;
+  if (!(e_et && atoi(e_et) == 0))
+    ctx->early_tail = [&]() -> int {   // (called by feval_enqueue with ctx->stream = aux, once group 2's gradients are final)
+      if (dp) RAU_TRY(rau_allreduce_internal(ctx, grads[2], rau_group_size(cfg, 2)));
+      return finish_group(2);
+    };
   const int rc_f = feval_enqueue(ctx, cfg, bt, params, grads, hop_mask, masks, out);
-  ctx->ar_early_buf = nullptr;
+  ctx->early_tail = nullptr;
   RAU_TRY(rc_f);
-  if (dp) {   // data parallel: one sum over ranks of each flat gradient, the small ones as one launch
-    cudaEvent_t early = ctx->ar_early_done;   // set when the mult group's all-reduce already went out on the aux stream
-    ctx->ar_early_done = nullptr;
+  cudaEvent_t early = ctx->early_tail_done;
+  ctx->early_tail_done = nullptr;
+  if (dp) {   // data parallel: one sum over ranks of each flat gradient, the remaining ones as one launch
     RAU_TRY(rau_allreduce_group(ctx, 1));
     for (int g = 0; g < (early ? 2 : 3); ++g) RAU_TRY(rau_allreduce_internal(ctx, grads[g], rau_group_size(cfg, g)));
     if (out && out->loss) RAU_TRY(rau_allreduce_internal(ctx, out->loss, cfg->nHop + 2));
     if (out && out->loss_do_pred) RAU_TRY(rau_allreduce_internal(ctx, out->loss_do_pred, cfg->nHop));
     RAU_TRY(rau_allreduce_group(ctx, 0));
-    if (early) RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, early, 0));
   }
-  ARENA(norm2, double, "opt.norm2", 4);
-  RAU_CHECK_CUDA(cudaMemsetAsync(norm2, 0, sizeof(double) * 4, ctx->stream));
-  const float std_flag = (hp->eta > 0.0f && hp->gamma > 0.0f) ? 1.0f : 0.0f;   // the value itself is StepState.noise_std
-  for (int g = 0; g < 3; ++g)
-    RAU_TRY(k_noise_norm(ctx, grads[g], rau_group_size(cfg, g), std_flag, hp->noise_override ? hp->noise_override[g] : nullptr,
-                         ctx->seed, stream_of(0, SK_NOISE, g, 0), norm2 + g));
-  for (int g = 0; g < 3; ++g)   // F:788-790: adam(embed, lr) adam(rnn, lr) adam(mult, multlr)
-    RAU_TRY(k_clip_optim(ctx, hp->optim, rau_group_size(cfg, g), params[g], grads[g], norm2 + g, hp->clip, hp->lr[g], hp->h0,
-                         hp->h1, hp->h2, opt_state ? opt_state[g][0] : nullptr, opt_state ? opt_state[g][1] : nullptr, 1,
-                         (out && out->norms) ? out->norms + g : nullptr, g));
+  for (int g = 0; g < (early ? 2 : 3); ++g) RAU_TRY(finish_group(g));
+  if (early) RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, early, 0));
   rau_phase_mark(ctx, "noise + clip + optimizer");
   return RAU_OK;
 }
