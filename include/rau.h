@@ -156,6 +156,18 @@ typedef struct {
   const uint8_t* m;       /* [nHop,B,M]  */
 } rau_masks;
 
+/* The keep masks the step with iteration number step_t draws (Philox, this context's seed and rank) as 0/1 bytes in the
+ * rau_masks layouts above; NULL members are skipped.  Test hook: the parity tests run the step with drawn masks -- the
+ * schedule bench.py measures -- and give these bytes to the CPU oracle. */
+typedef struct {
+  uint8_t* embed;   /* [T,B,embed] */
+  uint8_t* rnn;     /* [T,B,Hq]    */
+  uint8_t* q;       /* [nHop,B,Q]  */
+  uint8_t* x;       /* [nHop,B,C,S] */
+  uint8_t* m;       /* [nHop,B,M]  */
+} rau_masks_out;
+int rau_draw_masks(rau_ctx* ctx, const rau_config* cfg, int B, int64_t step_t, const rau_masks_out* out);
+
 typedef struct {
   int B;                    /* local batch */
   int B_global;             /* loss/gradient normaliser (= B on one GPU; world*B under data parallel) */
@@ -198,13 +210,18 @@ int rau_optim_step(rau_ctx* ctx, int optim, int64_t n, float* x, const float* dx
                    float h0, float h1, float h2, float* state0, float* state1, int64_t t);
 
 /* One whole training iteration = rau_feval -> [all-reduce when a communicator is attached] ->
- * rau_noise_clip -> rau_optim_step x3 (F:786-791).  opt_state[g][0..1] as in rau_optim_step. */
+ * rau_noise_clip -> rau_optim_step x3 (F:786-791).  opt_state[g][0..1] as in rau_optim_step.
+ * step_t is the `it` the reference passes to feval (F:445, F:787; its main loop counts from 1, F:783): it keys the Philox
+ * dropout / noise streams and sets the noise variance eta / ((step_t + 1) * gamma) exactly as F:617-618 does.  Adam's
+ * bias correction does NOT use it: the reference keeps its own counter in the optimizer state (OU:79), here hp->opt_t. */
 typedef struct {
   int optim;                 /* rau_optim */
   float lr[3];               /* learningrate, learningrate, multlearningrate (F:788-790) */
   float h0, h1, h2;          /* optimizer hyper-parameters (see rau_optim_step) */
   float eta, gamma, clip;    /* F:54-55, F:49 */
   const float* const* noise_override; /* NULL or [3] */
+  int64_t opt_t;             /* adam: state.t AFTER its increment (OU:79-83), kept by the caller next to opt_state like the
+                              * reference's per-group state table (F:754-756); 0 = step_t + 1 (a run that starts at it = 0) */
 } rau_train_hparams;
 int rau_train_step(rau_ctx* ctx, const rau_config* cfg, const rau_batch* batch,
                    float* const params[3], float* const grads[3], float* const opt_state[3][2],

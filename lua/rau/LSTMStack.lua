@@ -1,14 +1,17 @@
 -- lua/rau/LSTMStack.lua -- nn.RauLSTMStack: the nn.Module behind both LSTM factories (model/ATTLSTM.lua,
 -- model/DeepLSTM.lua).  One rau_lstm_cell_fwd / rau_lstm_cell_bwd call per layer, rau_dropout between layers.
--- Parameters sit in child nn.Linear modules listed in self.modules, so that parameters(), getParameters(),
--- clone('weight','bias','gradWeight','gradBias') and share() of stock nn.Module work unchanged (SURVEY 8b).
+-- Parameters sit in child nn.Linear modules listed in self.modules, and the class derives from nn.Container: stock
+-- nn.Module:share only touches self[name], it is nn.Container:share that recurses into self.modules -- so
+-- proto:clone('weight','bias','gradWeight','gradBias') (F:339-347) and nngraph's recursion into the attlstm node (F:273)
+-- really alias the clones' weights and gradients to the prototype's.  parameters(), getParameters(), training(),
+-- evaluate(), zeroGradParameters() are nn.Container's own (SURVEY 8b).
 -- Python mirror with identical call sequence: rau_vqa_b200/model/_lstm_stack.py.
 require 'nn'
 require 'cutorch'
 local rau = require 'rau.ffi'
 local C, ffi = rau.C, rau.ffi
 
-local Stack, parent = torch.class('nn.RauLSTMStack', 'nn.Module')
+local Stack, parent = torch.class('nn.RauLSTMStack', 'nn.Container')
 
 local GATES_IFOG, GATES_IGFO = 0, 1
 local stream_counter = 0
@@ -19,28 +22,15 @@ function Stack:__init(input_size, rnn_size, num_layers, dropout, gate_order, pac
   self.input_size, self.rnn_size, self.num_layers = input_size, rnn_size, num_layers
   self.dropout = dropout or 0
   self.gate_order, self.packed_state, self.dropout_on_first = gate_order, packed_state, dropout_on_first
-  self.modules = {}
-  for L = 1, num_layers do
-    table.insert(self.modules, nn.Linear(L == 1 and input_size or rnn_size, 4 * rnn_size))   -- i2h (A:6 / D:43)
-    table.insert(self.modules, nn.Linear(rnn_size, 4 * rnn_size))                            -- h2h (A:7 / D:44)
+  for L = 1, num_layers do   -- (nn.Container:add appends to self.modules)
+    self:add(nn.Linear(L == 1 and input_size or rnn_size, 4 * rnn_size))   -- i2h (A:6 / D:43)
+    self:add(nn.Linear(rnn_size, 4 * rnn_size))                            -- h2h (A:7 / D:44)
   end
   self.train = true
   self.stream_id = 0
   self.saved = {}      -- per layer {input after dropout, 5*B*H saved gate activations}; private to each clone
   self.gradInput = {}
 end
-
-function Stack:parameters()
-  local w, g = {}, {}
-  for _, m in ipairs(self.modules) do
-    local mw, mg = m:parameters()
-    for i = 1, #mw do w[#w + 1] = mw[i]; g[#g + 1] = mg[i] end
-  end
-  return w, g
-end
-
-function Stack:training() self.train = true; return self end
-function Stack:evaluate() self.train = false; return self end
 
 local function views(self, state, L)
   local H = self.rnn_size
@@ -150,8 +140,53 @@ local function bwd(self, input, gradOutput, scale, want_input, want_params)
   return self.gradInput
 end
 
-function Stack:updateGradInput(input, gradOutput) return bwd(self, input, gradOutput, 0, true, false) end
-function Stack:accGradParameters(input, gradOutput, scale) bwd(self, input, gradOutput, scale or 1, false, true) end
-function Stack:backward(input, gradOutput, scale) return bwd(self, input, gradOutput, scale or 1, true, true) end
+-- A container that drives its children with updateGradInput and accGradParameters as two calls (instead of
+-- :backward) must not pay for two native backward passes: updateGradInput runs the ONE native call with the weight
+-- gradients directed into a zeroed scratch set (file-local, shared by all clones: the pair of calls for one module is
+-- never interleaved with another module's pair inside one container pass), and the matching accGradParameters only adds
+-- scale * scratch into the shared gradWeight / gradBias.  Any other call order falls back to the native call.
+local pending = {owner = nil, inp = nil, gout = nil, scratch = {}}
+
+local function ptr_of(t)
+  if torch.type(t) == 'table' then return ptr_of(t[1]) end
+  return tonumber(ffi.cast('intptr_t', rau.fptr(t)))
+end
+
+local function scratch_like(key, t)
+  local s = pending.scratch[key]
+  if s == nil or s:nElement() ~= t:nElement() then s = t.new():resizeAs(t); pending.scratch[key] = s end
+  return s:zero()
+end
+
+function Stack:updateGradInput(input, gradOutput)
+  local real = {}
+  for i, m in ipairs(self.modules) do      -- divert the weight gradients of this one call into the scratch set
+    real[i] = {m.gradWeight, m.gradBias}
+    m.gradWeight, m.gradBias = scratch_like(2 * i - 1, m.gradWeight), scratch_like(2 * i, m.gradBias)
+  end
+  local ok, err = pcall(bwd, self, input, gradOutput, 1, true, true)
+  for i, m in ipairs(self.modules) do m.gradWeight, m.gradBias = real[i][1], real[i][2] end
+  if not ok then error(err) end
+  pending.owner, pending.inp, pending.gout = self, ptr_of(input), ptr_of(gradOutput)
+  return self.gradInput
+end
+
+function Stack:accGradParameters(input, gradOutput, scale)
+  scale = scale or 1
+  if pending.owner == self and pending.inp == ptr_of(input) and pending.gout == ptr_of(gradOutput) then
+    for i, m in ipairs(self.modules) do
+      m.gradWeight:add(scale, pending.scratch[2 * i - 1])
+      m.gradBias:add(scale, pending.scratch[2 * i])
+    end
+    pending.owner = nil
+    return
+  end
+  bwd(self, input, gradOutput, scale, false, true)
+end
+
+function Stack:backward(input, gradOutput, scale)
+  pending.owner = nil
+  return bwd(self, input, gradOutput, scale or 1, true, true)
+end
 
 return {Stack = Stack, GATES_IFOG = GATES_IFOG, GATES_IGFO = GATES_IGFO}

@@ -13,11 +13,25 @@ function model_utils.clone_list(tensor_list, zero_too)
   return out
 end
 
--- T copies whose parameter and gradient tensors alias the prototype's
+-- T copies whose parameter and gradient tensors alias the prototype's (MU:15-36).  Like the reference this goes
+-- through parameters() and Tensor:set, NOT through clone(names...)/share: parameters() walks child modules whatever the
+-- container class, so the result does not depend on how share() recurses.
 function model_utils.clone_many_times(net, T)
   local clones = {}
+  local protoW, protoG
+  if net.parameters then protoW, protoG = net:parameters() end
   for t = 1, T do
-    clones[t] = net.parameters and net:clone('weight', 'bias', 'gradWeight', 'gradBias') or net:clone()
+    local c = net:clone()                        -- torch.MemoryFile round trip; nothing is shared yet
+    if protoW then
+      local w, g = c:parameters()
+      assert(#w == #protoW, 'clone_many_times: the clone lists a different number of parameter tensors')
+      for i = 1, #w do
+        w[i]:set(protoW[i])
+        g[i]:set(protoG[i])
+      end
+    end
+    clones[t] = c
+    collectgarbage()
   end
   return clones
 end

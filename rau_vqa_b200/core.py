@@ -208,8 +208,10 @@ def optim_step(ctx, optim, x, dx, lr, h0=0.0, h1=0.0, h2=0.0, state0=None, state
 
 def train_step(ctx: Context, cfg: RauConfig, params, grads, opt_state, feats, tokens, lengths, labels, out: StepBuffers,
                optim=OPT_ADAM, lrs=(3e-3, 3e-3, 3e-4), hyper=(0.9, 0.999, 1e-8), eta=0.01, gamma=0.55, clip=0.1,
-               hop_mask=None, masks=None, noise=None, step_t: int = 0, max_len: int = 0, B_global: int = 0):
-    """feval + [all-reduce] + noise/clip + the three optimizer calls (F:786-791) as one enqueue."""
+               hop_mask=None, masks=None, noise=None, step_t: int = 0, max_len: int = 0, B_global: int = 0, opt_t: int = 0):
+    """feval + [all-reduce] + noise/clip + the three optimizer calls (F:786-791) as one enqueue.
+    step_t = the reference's `it` (keys dropout / noise, noise variance eta/((it+1) gamma), F:617); opt_t = adam's own step
+    count after its increment (OU:79; 0 = step_t + 1)."""
     keep = []
     B = feats.shape[0]
     b = _batch_struct(keep, B, feats, tokens, lengths, labels, max_len, B_global)
@@ -220,6 +222,7 @@ def train_step(ctx: Context, cfg: RauConfig, params, grads, opt_state, feats, to
         hp.lr[g] = lrs[g]
     hp.h0, hp.h1, hp.h2 = hyper
     hp.eta, hp.gamma, hp.clip = eta, gamma, clip
+    hp.opt_t = int(opt_t)
     if noise is not None:
         nz = ffi.new("float*[3]", [fptr(t) for t in noise])
         keep.append(nz)
@@ -230,6 +233,21 @@ def train_step(ctx: Context, cfg: RauConfig, params, grads, opt_state, feats, to
             st[g][k] = fptr(opt_state[g][k]) if opt_state is not None and opt_state[g][k] is not None else ffi.NULL
     check(ctx.lib.rau_train_step(ctx.h, cfg.c(), b, _triple(keep, params), _triple(keep, grads), st, hm,
                                  _masks_struct(keep, masks), step_t, hp, out.c(keep)))
+
+
+def draw_masks(ctx: Context, cfg: RauConfig, B: int, step_t: int, device=None):
+    """The keep masks the step with iteration number step_t draws from this context's Philox streams, as uint8 tensors
+    in the rau_masks layouts (dict embed / rnn / q / x / m).  Test hook (rau_draw_masks)."""
+    dev = device if device is not None else torch.device("cuda", ctx.device)
+    u8 = dict(dtype=torch.uint8, device=dev)
+    out = dict(embed=torch.empty(cfg.T, B, cfg.embed, **u8), rnn=torch.empty(cfg.T, B, cfg.Hq, **u8),
+               q=torch.empty(cfg.nHop, B, cfg.Q, **u8), x=torch.empty(cfg.nHop, B, cfg.C, cfg.S, **u8),
+               m=torch.empty(cfg.nHop, B, cfg.M, **u8))
+    mo = ffi.new("rau_masks_out*")
+    for k, t in out.items():
+        setattr(mo, k, bptr(t))
+    check(ctx.lib.rau_draw_masks(ctx.h, cfg.c(), B, step_t, mo))
+    return out
 
 
 def predict(ctx: Context, cfg: RauConfig, params, feats, tokens, lengths, max_len: int = 0):
@@ -243,5 +261,5 @@ def predict(ctx: Context, cfg: RauConfig, params, feats, tokens, lengths, max_le
     return pred, att
 
 
-__all__ = ["RauConfig", "Context", "StepBuffers", "feval", "noise_clip", "optim_step", "train_step", "predict",
+__all__ = ["RauConfig", "Context", "StepBuffers", "feval", "noise_clip", "optim_step", "train_step", "predict", "draw_masks",
            "RauError", "fptr", "bptr", "GROUPS"]

@@ -54,8 +54,12 @@ struct OptArgs {
 __global__ void __launch_bounds__(256) clip_optim_kernel(OptArgs a, float* __restrict__ x, float* __restrict__ g,
                                                          const double* __restrict__ norm2, float* __restrict__ s0,
                                                          float* __restrict__ s1, float* __restrict__ norm_out,
-                                                         const StepState* __restrict__ ss, int group) {
+                                                         const StepState* __restrict__ ss, int group,
+                                                         const unsigned int* __restrict__ failed) {
   RAU_PDL_ENTRY();
+  // a persistent recurrence kernel of this step gave up on a peer CTA: the gradients are garbage, leave x and the
+  // optimizer state alone (the host reports the failure at its next call into the library)
+  if (failed != nullptr && a.optim >= 0 && *failed != 0u) return;
   float scale = 1.0f;
   if (ss && group >= 0) a.step = ss->opt_step[group];
   if (norm2 != nullptr) {
@@ -118,7 +122,8 @@ int k_clip_optim(rau_ctx* ctx, int optim, int64_t n, float* x, float* g, const d
   int64_t blocks = (n + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  RAU_LAUNCH_PDL(ctx->stream, (clip_optim_kernel), (int)blocks, 256, 0, a, x, g, norm2, s0, s1, norm_out, ctx->ss_active, group);
+  RAU_LAUNCH_PDL(ctx->stream, (clip_optim_kernel), (int)blocks, 256, 0, a, x, g, norm2, s0, s1, norm_out, ctx->ss_active, group,
+      (const unsigned int*)ctx->d_err);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }

@@ -52,6 +52,36 @@ __global__ void mask_pack_kernel(uint32_t* __restrict__ bits, const uint8_t* __r
   }
 }
 
+// packed keep bits -> 0/1 bytes (rau_draw_masks: the masks a step draws, exported for the parity tests)
+__global__ void mask_unpack_kernel(const uint32_t* __restrict__ bits, int64_t n, uint8_t* __restrict__ bytes) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    bytes[i] = (uint8_t)((bits[i >> 5] >> (i & 31)) & 1u);
+}
+
+// The feature-dropout keep decisions of the rows pack kernels (k_rows_tc.cu xprep_rows_kernel / xprep_rows_hops_kernel)
+// as 0/1 bytes in the [nHop, B, C, S] layout of rau_masks.x: element (b, c, s) of hop h takes 16 bits of one Philox draw
+// shared by the channel pair (c & ~1, c | 1) x 4 consecutive grid cells -- word s & 3, low half for the even channel.
+__global__ void xmask16_bytes_kernel(uint8_t* __restrict__ out, int B, int C, int S, int nHop, uint32_t thresh, uint2 key,
+                                     uint32_t stream_lo, uint32_t stream_hi, const StepState* __restrict__ ss) {
+  if (ss) {
+    const unsigned long long sid = (((unsigned long long)stream_hi << 32) | stream_lo) ^ (ss->step << 24);
+    stream_lo = (uint32_t)sid;
+    stream_hi = (uint32_t)(sid >> 32);
+  }
+  const int64_t per_hop = (int64_t)B * C * S, total = per_hop * nHop;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int h = (int)(i / per_hop);
+    const int64_t e = i - (int64_t)h * per_hop;          // (b*C + c)*S + s
+    const int s = (int)(e % S);
+    const int64_t bc = e / S;
+    const int c = (int)(bc % C);
+    const uint64_t ctr = (uint64_t)(((bc - (c & 1)) * S) + (s & ~3)) >> 2;
+    const uint4 r = philox4x32(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), stream_lo ^ (uint32_t)h, stream_hi), key);
+    const uint32_t w = (s & 3) == 0 ? r.x : (s & 3) == 1 ? r.y : (s & 3) == 2 ? r.z : r.w;
+    out[i] = (uint8_t)((((w >> ((c & 1) * 16)) & 0xffffu) < thresh) ? 1 : 0);
+  }
+}
+
 // ---------------------------------------------------------------- embedding
 __global__ void embed_fwd_kernel(const float* __restrict__ ids, int n, int D, int V, const float* __restrict__ E,
                                  const uint32_t* __restrict__ bits, float scale, float* __restrict__ out_f,
@@ -432,6 +462,20 @@ int k_mask_gen(rau_ctx* ctx, uint32_t* bits, int64_t n, float p, uint64_t seed, 
   RAU_LAUNCH_PDL(ctx->stream, (mask_gen_kernel), dim3(grid_for(nw), nHop), TPB, 0, bits, nw, n, thresh, p <= 0.0f ? 1 : 0,
       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), (uint32_t)stream_id, (uint32_t)(stream_id >> 32), ctx->ss_active,
       hop_stride);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+int k_mask_unpack(rau_ctx* ctx, const uint32_t* bits, int64_t n, uint8_t* bytes) {
+  mask_unpack_kernel<<<grid_for(n), TPB, 0, ctx->stream>>>(bits, n, bytes);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+int k_xmask16_bytes(rau_ctx* ctx, uint8_t* out, int B, int C, int S, int nHop, float p_drop, uint64_t stream_id) {
+  const double keep = 1.0 - (double)p_drop;
+  const uint32_t thresh = keep >= 1.0 ? 65536u : (uint32_t)(keep * 65536.0 + 0.5);   // as k_xprep_rows_hops
+  xmask16_bytes_kernel<<<grid_for((int64_t)B * C * S * nHop), TPB, 0, ctx->stream>>>(
+      out, B, C, S, nHop, thresh, make_uint2((uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32)), (uint32_t)stream_id,
+      (uint32_t)(stream_id >> 32), ctx->ss_active);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }

@@ -1355,7 +1355,8 @@ struct LsParams {
   float* lsaved; long long ls_t, plane;         // saved gates of step 1: 5 planes (i, f, o, g, tanh c') of [B, H]
   bf16* hpk_hi; bf16* hpk_lo; long long hp_t;   // packed h of step 0 (zeros); step t at + t*hp_t
   unsigned int* counter;                        // [tiles_m] zeroed by the caller
-  unsigned int* err;
+  unsigned int* err;                            // sticky failure word (device: the optimizer kernel reads it)
+  unsigned int* err_host;                       // the same, host-mapped: checked at every public entry point
   int fence_all;                                // every epilogue thread fences before the publish barrier (A/B)
 };
 constexpr int LS_THREADS = 320;   // TMA producer, MMA issuer, 8 epilogue warps
@@ -1418,7 +1419,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
         if (lane == 0) {
           const long long t0 = clock64();
           while (ld_acquire_u32(p.counter + tm) < need) {
-            if (clock64() - t0 > 4000000000ll) { *p.err = 1u; break; }   // never hang the device on a lost peer
+            if (clock64() - t0 > 4000000000ll) { *p.err = 1u; *p.err_host = 1u; break; }   // never hang the device on a lost peer
           }
         }
         __syncwarp();
@@ -1577,7 +1578,7 @@ struct LbParams {
   const float* saved; long long ls_t, plane;    // saved gates of step 1: 5 planes (i, f, o, g, tanh c') of [B, H]
   float* dG; bf16* dG_hi; bf16* dG_lo; long long g_t;   // [T][B][4H] (chunks i, f, o, g), step stride
   const float* dHacc;                           // [(T+1)][B][H]: slab t = d loss / d h_t through the recurrence (zeroed by the caller)
-  unsigned int* counter; unsigned int* err;
+  unsigned int* counter; unsigned int* err; unsigned int* err_host;
 };
 
 template <int X3>
@@ -1690,7 +1691,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_bwd_kernel(const __gri
           const unsigned int need = (unsigned int)p.tiles_n * (unsigned int)(p.T - t);
           const long long t0 = clock64();
           while (ld_acquire_u32(p.counter + tm) < need) {
-            if (clock64() - t0 > 4000000000ll) { *p.err = 1u; break; }   // never hang the device on a lost peer
+            if (clock64() - t0 > 4000000000ll) { *p.err = 1u; *p.err_host = 1u; break; }   // never hang the device on a lost peer
           }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -2111,6 +2112,22 @@ int k_attn_rows_bwd(rau_ctx* ctx, int B, int M, int A, int S, const float* E, co
 
 
 
+template <typename P>
+static cudaError_t launch_cooperative(cudaStream_t st, void (*kern)(P), int grid, int block, int smem, const P& p) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
 // The whole recurrence of one encoder LSTM layer in one persistent launch (lstm_seq_kernel).  Returns RAU_OK with *done = 0
 // when the shape does not fit (the caller then unrolls the per-step EPI_LSTM launches).
 int rows_lstm_seq(rau_ctx* ctx, const LstmSeq& d, int* done) {
@@ -2138,12 +2155,10 @@ int rows_lstm_seq(rau_ctx* ctx, const LstmSeq& d, int* done) {
   p.lsaved = d.lsaved; p.ls_t = d.ls_t; p.plane = d.plane;
   p.hpk_hi = d.hpk_hi; p.hpk_lo = d.hpk_lo; p.hp_t = (long long)B * H;
   unsigned int* cnt = nullptr;
-  const bool cnt_new = ctx->arena.bufs.find("lstmseq.cnt") == ctx->arena.bufs.end();
   RAU_TRY(ctx->arena.get("lstmseq.cnt", sizeof(unsigned int) * 64, (void**)&cnt));
-  if (cnt_new) RAU_CHECK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * 64, ctx->stream));   // (word 63: sticky time-out flag, read by rau_sync)
-  RAU_REQUIRE(tiles_m < 63, "rows_lstm_seq: %d row tiles", tiles_m);
-  RAU_CHECK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * 63, ctx->stream));
-  p.counter = cnt; p.err = cnt + 63;
+  RAU_REQUIRE(tiles_m <= 64, "rows_lstm_seq: %d row tiles", tiles_m);
+  RAU_CHECK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * 64, ctx->stream));
+  p.counter = cnt; p.err = ctx->d_err; p.err_host = ctx->h_err_dev;
   { const char* e_f = getenv("RAU_SEQ_FENCE"); p.fence_all = e_f ? atoi(e_f) : 1; }
   const int smem_bytes = w_bytes + stages * a_stage + 1024;
   static bool attr_done[2] = {false, false};
@@ -2152,8 +2167,10 @@ int rows_lstm_seq(rau_ctx* ctx, const LstmSeq& d, int* done) {
     else RAU_CHECK_CUDA(cudaFuncSetAttribute(lstm_seq_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM_BUDGET + 1024));
     attr_done[x3 ? 1 : 0] = true;
   }
-  if (x3) lstm_seq_kernel<1><<<tiles_m * tiles_n, LS_THREADS, smem_bytes, ctx->stream>>>(p);
-  else lstm_seq_kernel<0><<<tiles_m * tiles_n, LS_THREADS, smem_bytes, ctx->stream>>>(p);
+  // the CTAs wait for each other: a cooperative launch makes the driver guarantee that the whole grid is co-resident
+  // (next to whatever the side and aux streams keep on the device) or refuse the launch
+  if (x3) RAU_CHECK_CUDA(launch_cooperative(ctx->stream, lstm_seq_kernel<1>, tiles_m * tiles_n, LS_THREADS, smem_bytes, p));
+  else RAU_CHECK_CUDA(launch_cooperative(ctx->stream, lstm_seq_kernel<0>, tiles_m * tiles_n, LS_THREADS, smem_bytes, p));
   RAU_LAUNCH_CHECK(ctx);
   *done = 1;
   return RAU_OK;
@@ -2194,19 +2211,17 @@ int rows_lstm_seq_bwd(rau_ctx* ctx, const LstmSeqBwd& d, int* done) {
   p.dG = d.dG; p.dG_hi = d.dG_hi; p.dG_lo = d.dG_lo; p.g_t = (long long)B * 4 * H;
   p.dHacc = acc;
   unsigned int* cnt = nullptr;
-  const bool cnt_new = ctx->arena.bufs.find("lstmseq.cntb") == ctx->arena.bufs.end();
   RAU_TRY(ctx->arena.get("lstmseq.cntb", sizeof(unsigned int) * 64, (void**)&cnt));
-  if (cnt_new) RAU_CHECK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * 64, ctx->stream));   // (word 63: sticky time-out flag, read by rau_sync)
-  RAU_CHECK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * 63, ctx->stream));
-  p.counter = cnt; p.err = cnt + 63;
+  RAU_CHECK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * 64, ctx->stream));
+  p.counter = cnt; p.err = ctx->d_err; p.err_host = ctx->h_err_dev;
   static bool attr_done[2] = {false, false};
   if (!attr_done[x3 ? 1 : 0]) {
     if (x3) RAU_CHECK_CUDA(cudaFuncSetAttribute(lstm_seq_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM_BUDGET + 1024));
     else RAU_CHECK_CUDA(cudaFuncSetAttribute(lstm_seq_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM_BUDGET + 1024));
     attr_done[x3 ? 1 : 0] = true;
   }
-  if (x3) lstm_seq_bwd_kernel<1><<<tiles_m * tiles_n, LS_THREADS, smem_bytes, ctx->stream>>>(p);
-  else lstm_seq_bwd_kernel<0><<<tiles_m * tiles_n, LS_THREADS, smem_bytes, ctx->stream>>>(p);
+  if (x3) RAU_CHECK_CUDA(launch_cooperative(ctx->stream, lstm_seq_bwd_kernel<1>, tiles_m * tiles_n, LS_THREADS, smem_bytes, p));
+  else RAU_CHECK_CUDA(launch_cooperative(ctx->stream, lstm_seq_bwd_kernel<0>, tiles_m * tiles_n, LS_THREADS, smem_bytes, p));
   RAU_LAUNCH_CHECK(ctx);
   *done = 1;
   return RAU_OK;

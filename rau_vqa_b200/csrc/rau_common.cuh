@@ -42,6 +42,7 @@ void rau_set_error(const char* fmt, ...);
 struct RauArena {
   struct Buf { void* p = nullptr; size_t bytes = 0; };
   std::map<std::string, Buf> bufs;
+  uint64_t generation = 0;   // bumped whenever a buffer is re-allocated: device addresses a captured graph baked in are stale
   int get(const char* name, size_t bytes, void** out);
   void release();
 };
@@ -60,6 +61,7 @@ struct RauGraphEntry { cudaGraphExec_t exec = nullptr; int seen = 0; int64_t ker
 struct RauGraph {
   std::map<std::vector<uint64_t>, RauGraphEntry> entries;   // one captured step per distinct argument set
   bool disabled = false;
+  uint64_t arena_generation = 0;   // RauArena::generation the entries were captured under
   void clear() {
     for (auto& kv : entries)
       if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
@@ -82,6 +84,13 @@ struct rau_ctx {
   StepState* d_ss = nullptr;                       // device copy read by kernels
   StepState* h_ss = nullptr;                       // pinned ring the uploads are staged in
   int ss_slot = 0;
+  cudaEvent_t ss_ev[64] = {};                      // recorded behind each slot's upload: a slot is reused only after its copy ran
+  // sticky failure word of the persistent recurrence kernels (a CTA gave up waiting for its row tile's peers): d_err is
+  // read by the optimizer kernel, which then leaves the parameters untouched; the kernels also set the host-mapped copy,
+  // which every public entry point checks without a device synchronisation
+  unsigned int* d_err = nullptr;
+  volatile unsigned int* h_err = nullptr;          // cudaHostAllocMapped
+  unsigned int* h_err_dev = nullptr;               // its device alias
   const StepState* ss_active = nullptr;            // non-null while a whole-step call is being enqueued
   cudaStream_t gstream = nullptr;                  // capture stream (the caller's stream may be the legacy one)
   RauGraph graph;

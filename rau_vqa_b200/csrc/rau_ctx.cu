@@ -22,6 +22,7 @@ int RauArena::get(const char* name, size_t bytes, void** out) {
       cudaFree(b.p);
       b.p = nullptr;
       b.bytes = 0;
+      generation++;   // captured graphs that baked the old address in must be dropped (rau_train_step checks)
     }
     size_t want = (bytes + 255) & ~(size_t)255;
     cudaError_t e = cudaMalloc(&b.p, want);
@@ -79,6 +80,8 @@ void rau_phase_mark(rau_ctx* ctx, const char* name) {
   cudaEventRecord(ev, ctx->stream);
   ctx->phase_ev.push_back({name, ev});
 }
+
+int rau_check_async_error(rau_ctx* ctx);
 
 extern "C" {
 
@@ -138,6 +141,14 @@ int rau_ctx_create(rau_ctx** out, int device, void* cuda_stream) {
     delete ctx;
     return RAU_ECUDA;
   }
+  if (cudaMalloc(&ctx->d_err, sizeof(unsigned int)) != cudaSuccess || cudaMemset(ctx->d_err, 0, sizeof(unsigned int)) != cudaSuccess ||
+      cudaHostAlloc((void**)&ctx->h_err, sizeof(unsigned int), cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer((void**)&ctx->h_err_dev, (void*)ctx->h_err, 0) != cudaSuccess) {
+    rau_set_error("context allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete ctx;
+    return RAU_ECUDA;
+  }
+  *ctx->h_err = 0;
   if (cudaMalloc(&ctx->d_ss, sizeof(StepState)) != cudaSuccess ||
       cudaMallocHost(&ctx->h_ss, sizeof(StepState) * 64) != cudaSuccess ||
       cudaStreamCreateWithPriority(&ctx->gstream, cudaStreamNonBlocking, -1) != cudaSuccess ||
@@ -164,6 +175,9 @@ int rau_ctx_destroy(rau_ctx* ctx) {
   if (ctx->stamp_buf) cudaFree(ctx->stamp_buf);
   if (ctx->d_ss) cudaFree(ctx->d_ss);
   if (ctx->h_ss) cudaFreeHost(ctx->h_ss);
+  if (ctx->d_err) cudaFree(ctx->d_err);
+  if (ctx->h_err) cudaFreeHost((void*)ctx->h_err);
+  for (cudaEvent_t e : ctx->ss_ev) if (e) cudaEventDestroy(e);
   if (ctx->gstream) cudaStreamDestroy(ctx->gstream);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->aux) cudaStreamDestroy(ctx->aux);
@@ -198,20 +212,7 @@ int rau_get_precision(rau_ctx* ctx) { return ctx ? ctx->precision : RAU_EINVAL; 
 int rau_sync(rau_ctx* ctx) {
   RAU_REQUIRE(ctx, "ctx == NULL");
   RAU_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
-  // the persistent recurrence kernels give up on a peer CTA after ~2 s instead of hanging the device: that must not pass
-  // silently (word 63 of their counter blocks)
-  for (const char* name : {"lstmseq.cnt", "lstmseq.cntb"}) {
-    auto it = ctx->arena.bufs.find(name);
-    if (it == ctx->arena.bufs.end() || it->second.p == nullptr) continue;
-    unsigned int flag = 0;
-    RAU_CHECK_CUDA(cudaMemcpy(&flag, (const unsigned int*)it->second.p + 63, sizeof(flag), cudaMemcpyDeviceToHost));
-    if (flag != 0) {
-      cudaMemset((unsigned int*)it->second.p + 63, 0, sizeof(flag));
-      rau_set_error("persistent LSTM recurrence (%s): a CTA timed out waiting for its row tile's peers; results are invalid", name);
-      return RAU_ECUDA;
-    }
-  }
-  return RAU_OK;
+  return rau_check_async_error(ctx);
 }
 
 int64_t rau_launch_count(rau_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -231,6 +232,18 @@ int64_t rau_param_offset(const rau_config* cfg, int group, const char* name) {
 }
 
 }  // extern "C"
+
+// A persistent recurrence kernel gave up on a peer CTA (instead of hanging the device): its results and everything
+// computed from them are invalid.  The optimizer kernel saw the same word and left the parameters untouched.
+int rau_check_async_error(rau_ctx* ctx) {
+  if (ctx->h_err == nullptr || *ctx->h_err == 0) return RAU_OK;
+  cudaStreamSynchronize(ctx->stream);
+  *ctx->h_err = 0;
+  cudaMemset(ctx->d_err, 0, sizeof(unsigned int));
+  rau_set_error("persistent LSTM recurrence: a CTA timed out waiting for its row tile's peers; the step's results are invalid "
+                "and its parameter update was skipped");
+  return RAU_ECUDA;
+}
 
 // ------------------------------------------------------------------ layout
 static const char* kRnnNames[4][4] = {{"l1.Wi", "l1.bi", "l1.Wh", "l1.bh"},

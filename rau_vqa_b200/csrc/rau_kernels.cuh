@@ -9,6 +9,9 @@
 int k_mask_gen(rau_ctx* ctx, uint32_t* bits, int64_t n, float p, uint64_t seed, uint64_t stream_id, int nHop = 1,
                int64_t hop_stride = 0);
 int k_mask_pack(rau_ctx* ctx, uint32_t* bits, const uint8_t* bytes, int64_t n);
+int k_mask_unpack(rau_ctx* ctx, const uint32_t* bits, int64_t n, uint8_t* bytes);
+// keep decisions of the rows pack kernels' inline 16-bit Philox draws as bytes [nHop, B, C, S]
+int k_xmask16_bytes(rau_ctx* ctx, uint8_t* out, int B, int C, int S, int nHop, float p_drop, uint64_t stream_id);
 static inline int64_t mask_words(int64_t n) { return (n + 31) / 32 + 4; }
 
 // ---- word embedding (F:203-206)

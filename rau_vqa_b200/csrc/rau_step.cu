@@ -19,6 +19,7 @@ int rau_allreduce_internal(rau_ctx* ctx, float* buf, int64_t n);   // rau_comm.c
 int rau_allreduce_group(rau_ctx* ctx, int begin);
 bool rau_comm_attached(rau_ctx* ctx);
 int rau_comm_rank(rau_ctx* ctx);
+int rau_check_async_error(rau_ctx* ctx);   // rau_ctx.cu
 
 #define ARENA(ptr, type, name, count) \
   type* ptr = nullptr;                \
@@ -370,10 +371,16 @@ static int feval_validate(rau_ctx* ctx, const rau_config* cfg, const rau_batch* 
 
 // stage the per-step scalars on the device (outside any captured graph)
 static int upload_step_state(rau_ctx* ctx, const StepState& st) {
-  StepState* h = ctx->h_ss + ctx->ss_slot;
+  const int slot = ctx->ss_slot;
   ctx->ss_slot = (ctx->ss_slot + 1) % 64;
+  // a caller may enqueue more than 64 steps without synchronising (graph replay costs the host microseconds): the slot
+  // is rewritten only after the copy that read it has run
+  if (ctx->ss_ev[slot] == nullptr) RAU_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->ss_ev[slot], cudaEventDisableTiming));
+  else RAU_CHECK_CUDA(cudaEventSynchronize(ctx->ss_ev[slot]));
+  StepState* h = ctx->h_ss + slot;
   *h = st;
   RAU_CHECK_CUDA(cudaMemcpyAsync(ctx->d_ss, h, sizeof(StepState), cudaMemcpyHostToDevice, ctx->stream));
+  RAU_CHECK_CUDA(cudaEventRecord(ctx->ss_ev[slot], ctx->stream));
   return RAU_OK;
 }
 
@@ -827,6 +834,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
 int rau_feval(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float* const params[3], float* const grads[3],
               const float* hop_mask, const rau_masks* masks, int64_t step_t, const rau_step_out* out) {
   RAU_TRY(feval_validate(ctx, cfg, bt, params, grads));
+  RAU_TRY(rau_check_async_error(ctx));
   StepState st;
   memset(&st, 0, sizeof(st));
   st.step = (unsigned long long)step_t;
@@ -835,6 +843,45 @@ int rau_feval(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float* c
   const int r = feval_enqueue(ctx, cfg, bt, params, grads, hop_mask, masks, out);
   ctx->ss_active = nullptr;
   return r;
+}
+
+// The keep masks rau_feval / rau_train_step draw from the context's Philox streams for iteration step_t (same seed, same
+// rank), written as 0/1 bytes in the layouts of rau_masks.  Parity tests run the step with drawn masks (the benchmarked
+// schedule: all-hops feature pack, batched mask launches, graph replay) and hand these bytes to the oracle.
+int rau_draw_masks(rau_ctx* ctx, const rau_config* cfg, int B, int64_t step_t, const rau_masks_out* out) {
+  RAU_REQUIRE(ctx && out, "ctx/out == NULL");
+  RAU_TRY(rau_check_cfg(cfg));
+  RAU_REQUIRE(B > 0, "B = %d", B);
+  RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  StepState st;
+  memset(&st, 0, sizeof(st));
+  st.step = (unsigned long long)step_t;
+  RAU_TRY(upload_step_state(ctx, st));
+  ctx->ss_active = ctx->d_ss;
+  struct Off { rau_ctx* c; ~Off() { c->ss_active = nullptr; } } off{ctx};
+  const int T = cfg->T, E = cfg->embed, Hq = cfg->Hq, Q = 4 * Hq, nHop = cfg->nHop, rank = rau_comm_rank(ctx);
+  auto one = [&](uint8_t* dst, int64_t n, float p, int kind, int hops) -> int {
+    if (dst == nullptr) return RAU_OK;
+    RAU_TRY(rau_check_dev(dst, "mask output"));
+    const int64_t stride = mask_words(n);
+    ARENA(bits, uint32_t, "draw.bits", (size_t)stride * hops);
+    RAU_TRY(k_mask_gen(ctx, bits, n, p, ctx->seed, stream_of(0, kind, 0, rank), hops, stride));
+    for (int h = 0; h < hops; ++h) RAU_TRY(k_mask_unpack(ctx, bits + (size_t)h * stride, n, dst + (size_t)h * n));
+    return RAU_OK;
+  };
+  RAU_TRY(one(out->embed, (int64_t)T * B * E, cfg->p_embed, SK_EMBED, 1));
+  RAU_TRY(one(out->rnn, (int64_t)T * B * Hq, cfg->p_rnn, SK_RNN, 1));
+  RAU_TRY(one(out->q, (int64_t)B * Q, cfg->p_q, SK_Q, nHop));
+  RAU_TRY(one(out->m, (int64_t)B * cfg->M, cfg->p_m, SK_M, nHop));
+  if (out->x) {
+    if (hop_rows_path(ctx, cfg)) {   // drawn inline by the rows pack kernels (16-bit draws shared by channel pairs)
+      RAU_TRY(rau_check_dev(out->x, "mask output"));
+      RAU_TRY(k_xmask16_bytes(ctx, out->x, B, cfg->C, cfg->S, nHop, cfg->p_x, stream_of(0, SK_X, 0, rank)));
+    } else {
+      RAU_TRY(one(out->x, (int64_t)B * cfg->C * cfg->S, cfg->p_x, SK_X, nHop));
+    }
+  }
+  return RAU_OK;
 }
 
 int rau_noise_clip(rau_ctx* ctx, const rau_config* cfg, float* const grads[3], int64_t step_t, float eta, float gamma,
@@ -917,6 +964,7 @@ int rau_train_step(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, flo
   RAU_REQUIRE(hp != nullptr, "hparams == NULL");
   RAU_REQUIRE(hp->optim >= RAU_OPT_SGD && hp->optim <= RAU_OPT_ADAM, "unknown optimizer %d", hp->optim);
   RAU_TRY(feval_validate(ctx, cfg, bt, params, grads));
+  RAU_TRY(rau_check_async_error(ctx));   // a failed recurrence of an EARLIER step surfaces here without a device sync
   if (hp->optim != RAU_OPT_SGD) RAU_REQUIRE(opt_state && opt_state[0][0], "optimizer state is required");
   // per-step scalars (evaluated in double on the host like Lua numbers, OU:80-83)
   StepState st;
@@ -925,7 +973,7 @@ int rau_train_step(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, flo
   for (int g = 0; g < 3; ++g) {
     double stp = hp->lr[g];
     if (hp->optim == RAU_OPT_ADAM) {
-      const double t = (double)(step_t + 1);
+      const double t = hp->opt_t > 0 ? (double)hp->opt_t : (double)(step_t + 1);   // state.t after its increment (OU:79)
       stp = (double)hp->lr[g] * sqrt(1.0 - pow((double)hp->h1, t)) / (1.0 - pow((double)hp->h0, t));
     }
     st.opt_step[g] = (float)stp;
@@ -948,7 +996,9 @@ int rau_train_step(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, flo
         key.push_back(v);
       }
     };
-    put(cfg, sizeof(*cfg)); put(bt, sizeof(*bt)); put(hp, sizeof(*hp));
+    rau_train_hparams hk = *hp;
+    hk.opt_t = 0;   // per-step scalar: travels in StepState, not in the captured launch arguments
+    put(cfg, sizeof(*cfg)); put(bt, sizeof(*bt)); put(&hk, sizeof(hk));
     for (int g = 0; g < 3; ++g) {
       key.push_back((uint64_t)(uintptr_t)params[g]); key.push_back((uint64_t)(uintptr_t)grads[g]);
       key.push_back((uint64_t)(uintptr_t)(opt_state ? opt_state[g][0] : nullptr));
@@ -957,6 +1007,9 @@ int rau_train_step(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, flo
     if (out) put(out, sizeof(*out));
     for (int h = 0; h < cfg->nHop; ++h) { float v = hop_mask ? hop_mask[h] : 1.0f; uint32_t u; memcpy(&u, &v, 4); key.push_back(u); }
     key.push_back((uint64_t)ctx->precision); key.push_back((uint64_t)ctx->seed); key.push_back((uint64_t)(uintptr_t)ctx->comm);
+    // a re-allocated arena buffer (a larger validation batch, another configuration) invalidates every captured step:
+    // their kernels carry the freed addresses
+    if (gr.arena_generation != ctx->arena.generation) { gr.clear(); gr.arena_generation = ctx->arena.generation; }
     if (gr.entries.size() > 16 && gr.entries.find(key) == gr.entries.end()) gr.clear();
     ent = &gr.entries[key];
     if (ent->exec) {

@@ -69,7 +69,7 @@ def mult_shapes(cfg: core.RauConfig):
                 Wo=(cfg.M, cfg.H), Ws=(cfg.N, cfg.M), wd=(1, cfg.M))
 
 
-class Multimodal(nn.Module):
+class Multimodal(nn.Container):
     def __init__(self, cfg: core.RauConfig, device="cpu"):
         super().__init__()
         self.cfg = cfg

@@ -12,7 +12,7 @@ from .._ffi import check, ffi
 _stream_counter = itertools.count(1)
 
 
-class LSTMStack(nn.Module):
+class LSTMStack(nn.Container):
     def __init__(self, input_size, rnn_size, num_layers, dropout, gate_order, packed_state, dropout_on_first):
         super().__init__()
         self.input_size, self.rnn_size, self.num_layers, self.dropout = input_size, rnn_size, num_layers, float(dropout)

@@ -111,12 +111,12 @@ class Module:
             g.zero_()
 
     def share(self, other, *names):
-        """self[name]:set(other[name]) recursively over self.modules (Module:share)."""
+        """nn.Module:share: self[name]:set(other[name]) for the named fields OF THIS MODULE ONLY.  Stock Torch7 does not
+        recurse here -- nn.Container:share does -- so a module that keeps its weights in child modules must be a
+        Container, or clone('weight', ...) silently shares nothing (the Lua shims follow the same rule)."""
         for n in names:
-            if getattr(other, n, None) is not None:
+            if getattr(other, n, None) is not None and getattr(self, n, None) is not None:
                 setattr(self, n, getattr(other, n))
-        for a, b in zip(self.modules, other.modules):
-            a.share(b, *names)
         return self
 
     def clone(self, *names):
@@ -135,6 +135,19 @@ class Module:
                 setattr(self, k, v.to(device))
         for m in self.modules:
             m.type_(device)
+        return self
+
+
+class Container(Module):
+    """nn.Container: a module whose parameters live in the child modules of self.modules; share() recurses."""
+
+    def add(self, m):
+        self.modules.append(m)
+        return self
+
+    def share(self, other, *names):
+        for a, b in zip(self.modules, other.modules):
+            a.share(b, *names)
         return self
 
 

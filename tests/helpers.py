@@ -51,6 +51,42 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
+# gradients that are ZERO by construction in the reference's step: the do_pred head receives a zeroed gradient
+# (F:582-583 -> wd, bd) and the scalar bias of the 256 -> 1 attention convolution shifts every logit of the softmax alike
+# (F:251, F:289 -> bs = sum_s ds_s = 0).  Their float64 value is rounding noise, so "relative to max|b|" is meaningless;
+# they are held to tol * (largest gradient of the group) instead.
+STRUCTURAL_ZERO = {"mult": ("wd", "bd", "bs")}
+
+
+def per_tensor_rel_err(cfg, group, got_flat, ref_flat):
+    """north_star's "gradients within 1e-3 relative", per NAMED tensor: {name: max|a-b| / max|b|} over the views of one
+    flat group (O.views = what getParameters() hands the script, F:322-324)."""
+    got = O.views(cfg, group, np.asarray(got_flat, dtype=np.float64))
+    ref = O.views(cfg, group, np.asarray(ref_flat, dtype=np.float64))
+    gmax = max(float(np.abs(ref_flat).max()), 1e-30)
+    out = {}
+    for name, r in ref.items():
+        denom = float(np.abs(r).max())
+        if name in STRUCTURAL_ZERO.get(group, ()):
+            denom = gmax
+        out[name] = float(np.abs(got[name] - r).max() / max(denom, 1e-30))
+    return out
+
+
+def assert_grads_per_tensor(cfg, grads, ref_grads, tol, report=None):
+    """every named tensor of the three groups within tol; returns the worst (error, group.name)."""
+    worst = (0.0, "")
+    for g in O.GROUPS:
+        errs = per_tensor_rel_err(cfg, g, grads[g], ref_grads[g])
+        for name, e in errs.items():
+            if report is not None:
+                report[f"{g}.{name}"] = e
+            worst = max(worst, (e, f"{g}.{name}"))
+    bad = {k: v for k, v in (report or {}).items() if v > tol} if report is not None else None
+    assert worst[0] <= tol, (worst, bad)
+    return worst
+
+
 def run_lib_feval(ctx, cfg, params, X, x, x_len, y, masks=None, hop_mask=None, B_global=0, step_t=0):
     """One rau_feval on the GPU from numpy inputs; returns (numpy grads dict, StepBuffers)."""
     import rau_vqa_b200 as R

@@ -5,7 +5,8 @@ import numpy as np
 import pytest
 
 from conftest import small_cfg
-from helpers import dev, lib_cfg, lib_masks, load_golden, oracle_masks_from_golden, rel_err, run_lib_feval
+from helpers import (assert_grads_per_tensor, dev, lib_cfg, lib_masks, load_golden, oracle_masks_from_golden, rel_err,
+                     run_lib_feval)
 from oracle import rau_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -61,6 +62,7 @@ def _check_step(ctx, cfg, params, X, x, x_len, y, masks, hop_mask=None):
         np.testing.assert_array_equal(ans[h][safe], res.answers[h][safe])
     for g in O.GROUPS:
         assert rel_err(grads[g], res.grads[g]) <= tol, g
+    assert_grads_per_tensor(cfg, grads, res.grads, tol, report={})     # ... and every named tensor on its own scale
     return res, grads, out
 
 
