@@ -53,8 +53,14 @@ typedef enum {
 typedef enum {
   RAU_PREC_F32 = 0,     /* fp32 operands, CUDA-core FMA: the exact mode */
   RAU_PREC_BF16 = 1,    /* bf16 operands, tcgen05 MMA, fp32 accumulate in TMEM: the fast mode (~3e-3 relative) */
-  RAU_PREC_BF16X3 = 2   /* bf16 hi/lo split operands (hi*hi + hi*lo + lo*hi, 3 MMA passes into one TMEM accumulator):
-                         * ~1e-5 relative on tcgen05; the DEFAULT, it is the mode that meets the 1e-3 parity bar */
+  RAU_PREC_BF16X3 = 2,  /* bf16 hi/lo split operands (hi*hi + hi*lo + lo*hi, 3 MMA passes into one TMEM accumulator):
+                         * ~2e-5 relative on tcgen05 */
+  RAU_PREC_MIXED = 3    /* the DEFAULT.  The image side of an answering unit -- dropped-out features, I = tanh(Wi X + bi),
+                         * Z = I Wa^T and their backward (dZ, dY, gWa, gWi): 98 % of the step's flops -- runs as ONE fp16 pass
+                         * (11-bit significands: operand rounding 2^-12, eight times finer than bf16; the gradient operands dZ, dY
+                         * are carried times a power of two so that they sit in fp16's normal range, and the products' fp32
+                         * results are scaled back).  Everything on the recurrent chain and the encoder stays bf16x3.
+                         * Measured per-tensor error against the float64 oracle: DESIGN.md section 2. */
 } rau_precision;
 
 typedef enum {

@@ -569,7 +569,7 @@ int tc_gemm_try(rau_ctx* ctx, const SimtGemm& g) {
   if (!prepacked && (long long)g.M * g.N * (long long)(g.K + g.K2) * g.kbatch < tc_min_work()) return 0;
   if (g.batch > 1 && g.kbatch > 1) return 0;
   RAU_TRY(get_encode());
-  const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+  const bool x3 = prec_x3(ctx);
 
   // roles: TMEM lanes (i) take 128 rows per tile, TMEM columns (j) up to 256; pick the cheaper padding
   auto cost = [](int I, int J) { return (long long)((I + 127) / 128 * 128) * ((J + 15) / 16 * 16); };

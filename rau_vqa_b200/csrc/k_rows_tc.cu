@@ -21,6 +21,7 @@
 //   EPI_DY     dY = (D + rowvec[b(r), n] * rowscale[r]) * (1 - I[r, n]^2) -> bf16 hi/lo, colsum[n] += sum_r dY
 #include "rau_model.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace {
@@ -71,6 +72,8 @@ struct RtParams {
   int S;
   float alpha;
   int fast_tanh;
+  int f16;                         // operands (and EPI_TANH / EPI_DY outputs, EPI_DY's saved activation) are fp16, not bf16
+  float gscale;                    // EPI_DY: the accumulator and the output carry this power-of-two gradient scale
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -247,6 +250,14 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
   hi = *reinterpret_cast<uint32_t*>(&h2);
   lo = pack_bf16x2(a - __bfloat162float(ha), b - __bfloat162float(hb));
 }
+// fp16 pair, round-to-nearest, saturating (a scaled gradient that overflows becomes 65504, never inf)
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // upper half <- first source operand
+  return r;
+}
+__device__ __forceinline__ float hf_lo(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u & 0xffffu))); }
+__device__ __forceinline__ float hf_hi(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u >> 16))); }
 __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
@@ -400,7 +411,8 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
     if (!CG2 || leader) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6) | A=bf16 [7,10) | B=bf16 [10,13) |
       // a_major [15] | b_major [16] | N>>3 [17,23) | M>>4 [24,29)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+      const uint32_t fmt = p.f16 ? 0u : 1u;   // A / B element format: 0 = f16, 1 = bf16
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
                              ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((CG2 ? 2 * RT_BM : RT_BM) >> 4) << 24);
       // K-major tile: rows of BK*2 bytes (64 B -> SWIZZLE_64B, 128 B -> SWIZZLE_128B), 8-row groups SBO apart; a 16-k
       //   step is +32 bytes inside the swizzled row.
@@ -526,7 +538,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
       const float* rv = nullptr;
       float rs = 0.0f;
       if (EPI == EPI_ATT || EPI == EPI_DY) rv = p.rowvec + (long long)(rr / p.S) * p.N;
-      if (EPI == EPI_DY) rs = dy_ready ? rs_next : p.rowscale[rr];
+      if (EPI == EPI_DY) rs = (dy_ready ? rs_next : p.rowscale[rr]) * p.gscale;   // (the accumulator holds gscale * dI)
       const int c_lo = half * (p.BN / 64), c_hi = c_lo + p.BN / 64;
       bool released = false;
       uint32_t rv_s = 0;
@@ -578,7 +590,10 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
 #pragma unroll
             for (int k = 0; k < 32; ++k) v[k] = tanh_acc(v[k]);
           }
-          if (p.out_lo) {
+          if (p.f16) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) w0[k] = pack_f16x2(v[2 * k], v[2 * k + 1]);
+          } else if (p.out_lo) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) split_pair(v[2 * k], v[2 * k + 1], w0[k], w0[16 + k]);
           } else {
@@ -770,7 +785,8 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
             const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float y0 = bf_lo(hh[j]) + bf_lo(ll[j]), y1 = bf_hi(hh[j]) + bf_hi(ll[j]);
+              const float y0 = p.f16 ? hf_lo(hh[j]) : bf_lo(hh[j]) + bf_lo(ll[j]);
+              const float y1 = p.f16 ? hf_hi(hh[j]) : bf_hi(hh[j]) + bf_hi(ll[j]);
               const int k = 8 * k8 + 2 * j;
               const float g0 = (v[k] + dd[2 * j] * rs) * (1.0f - y0 * y0);
               const float g1 = (v[k + 1] + dd[2 * j + 1] * rs) * (1.0f - y1 * y1);
@@ -779,7 +795,10 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
             }
           }
           __syncwarp();   // every lane has read its row before the next chunk overwrites the scratch
-          if (p.out_lo) {
+          if (p.f16) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) w0[k] = pack_f16x2(v[2 * k], v[2 * k + 1]);
+          } else if (p.out_lo) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) split_pair(v[2 * k], v[2 * k + 1], w0[k], w0[16 + k]);
           } else {
@@ -788,7 +807,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
           }
           if (p.colsum) {
             const float s0 = warp_transpose_sum32(v, lane);
-            if (nc + lane < p.N) atomicAdd(p.colsum + nc + lane, s0);
+            if (nc + lane < p.N) atomicAdd(p.colsum + nc + lane, s0 * p.alpha);   // (alpha = 1 / gscale)
           }
         }
         // the staging buffer is free once the previous chunk's bulk stores have read it
@@ -952,16 +971,22 @@ int launch_rows(rau_ctx* ctx, const RtParams& p, int grid, int smem_bytes) {
   return launch_rows_v<EPI, 0, 4, 0>(ctx, p, grid, smem_bytes);
 }
 
-__global__ void unpack_hilo_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, int64_t n, float* __restrict__ out) {
+__global__ void unpack_hilo_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, int64_t n, float* __restrict__ out,
+                                   int f16) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = __bfloat162float(hi[i]) + (lo ? __bfloat162float(lo[i]) : 0.0f);
+    out[i] = f16 ? __half2float(reinterpret_cast<const __half*>(hi)[i])
+                 : __bfloat162float(hi[i]) + (lo ? __bfloat162float(lo[i]) : 0.0f);
 }
 
-__global__ void pack_hilo_kernel(const float* __restrict__ in, int64_t n4, bf16* __restrict__ hi, bf16* __restrict__ lo) {
+__global__ void pack_hilo_kernel(const float* __restrict__ in, int64_t n4, bf16* __restrict__ hi, bf16* __restrict__ lo, int f16) {
   RAU_PDL_ENTRY();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 x = reinterpret_cast<const float4*>(in)[i];
     uint32_t h0, l0, h1, l1;
+    if (f16) {
+      reinterpret_cast<uint2*>(hi)[i] = make_uint2(pack_f16x2(x.x, x.y), pack_f16x2(x.z, x.w));
+      continue;
+    }
     split_pair(x.x, x.y, h0, l0);
     split_pair(x.z, x.w, h1, l1);
     reinterpret_cast<uint2*>(hi)[i] = make_uint2(h0, h1);
@@ -975,7 +1000,7 @@ __global__ void pack_hilo_kernel(const float* __restrict__ in, int64_t n4, bf16*
 __global__ void __launch_bounds__(256) xprep_rows_kernel(const float* __restrict__ X, const uint32_t* __restrict__ bits, float scale,
                                                          int C, int S, bf16* __restrict__ hi, bf16* __restrict__ lo, int gen,
                                                          uint32_t thresh, uint2 key, uint32_t stream_lo, uint32_t stream_hi,
-                                                         const StepState* __restrict__ ss) {
+                                                         const StepState* __restrict__ ss, int f16) {
   RAU_PDL_ENTRY();
   extern __shared__ float sT[];   // [S][66]
   const int b = blockIdx.y, c0 = blockIdx.x * 64;
@@ -1015,8 +1040,9 @@ __global__ void __launch_bounds__(256) xprep_rows_kernel(const float* __restrict
   for (int s = warp; s < S; s += 8) {
     const float2 v = *reinterpret_cast<const float2*>(sT + s * 66 + 2 * lane);
     uint32_t h, l;
-    split_pair(v.x, v.y, h, l);
     const int64_t o = (((int64_t)b * S + s) * C + c0) >> 1;
+    if (f16) { reinterpret_cast<uint32_t*>(hi)[o + lane] = pack_f16x2(v.x, v.y); continue; }
+    split_pair(v.x, v.y, h, l);
     reinterpret_cast<uint32_t*>(hi)[o + lane] = h;
     if (lo) reinterpret_cast<uint32_t*>(lo)[o + lane] = l;
   }
@@ -1032,7 +1058,7 @@ __global__ void __launch_bounds__(256) xprep_rows_kernel(const float* __restrict
 __global__ void __launch_bounds__(1024, 1) xprep_rows_hops_kernel(const float* __restrict__ X, float scale, int C, int S, int B, int nHop,
                                                                   bf16* __restrict__ hi, bf16* __restrict__ lo, long long hop_stride,
                                                                   uint32_t thresh, uint2 key, uint32_t stream_lo, uint32_t stream_hi,
-                                                                  const StepState* __restrict__ ss) {
+                                                                  const StepState* __restrict__ ss, int f16) {
   RAU_PDL_ENTRY();
   extern __shared__ float sT_all[];   // 4 x [S][66]
   const int sub = threadIdx.x >> 8, tid = threadIdx.x & 255;
@@ -1085,8 +1111,9 @@ __global__ void __launch_bounds__(1024, 1) xprep_rows_hops_kernel(const float* _
         for (int k = 0; k < 4; ++k) {
           const float a = q0[k] < thresh ? v[k].x * scale : 0.0f, c = q1[k] < thresh ? v[k].y * scale : 0.0f;
           uint32_t hh, ll;
-          split_pair(a, c, hh, ll);
           const int64_t o = (((int64_t)b * S + 4 * s4 + k) * C + c0) >> 1;
+          if (f16) { ph[o + lane] = pack_f16x2(a, c); continue; }
+          split_pair(a, c, hh, ll);
           ph[o + lane] = hh;
           if (pl) pl[o + lane] = ll;
         }
@@ -1177,7 +1204,7 @@ __global__ void __launch_bounds__(256) attn_rows_fwd_kernel(int S, int M, const 
                                                             const bf16* __restrict__ I_lo, float* __restrict__ p_out,
                                                             float* __restrict__ a_out, bf16* __restrict__ p_hi,
                                                             bf16* __restrict__ p_lo, int ldp, int A, const float* __restrict__ Z,
-                                                            const float* __restrict__ qadd, const float* __restrict__ ws) {
+                                                            const float* __restrict__ qadd, const float* __restrict__ ws, int f16) {
   RAU_PDL_ENTRY();
   __shared__ float p[256];
   __shared__ float part[8][256];
@@ -1231,6 +1258,11 @@ __global__ void __launch_bounds__(256) attn_rows_fwd_kernel(int S, int M, const 
     uint4 l = make_uint4(0u, 0u, 0u, 0u);
     if (I_lo) l = __ldg(reinterpret_cast<const uint4*>(I_lo + (r0 + s) * M + c0) + cg);
     const float w = p[s];
+    if (f16) {
+      a[0] = fmaf(w, hf_lo(h.x), a[0]); a[1] = fmaf(w, hf_hi(h.x), a[1]); a[2] = fmaf(w, hf_lo(h.y), a[2]); a[3] = fmaf(w, hf_hi(h.y), a[3]);
+      a[4] = fmaf(w, hf_lo(h.z), a[4]); a[5] = fmaf(w, hf_hi(h.z), a[5]); a[6] = fmaf(w, hf_lo(h.w), a[6]); a[7] = fmaf(w, hf_hi(h.w), a[7]);
+      continue;
+    }
     a[0] = fmaf(w, bf_lo(h.x) + bf_lo(l.x), a[0]); a[1] = fmaf(w, bf_hi(h.x) + bf_hi(l.x), a[1]);
     a[2] = fmaf(w, bf_lo(h.y) + bf_lo(l.y), a[2]); a[3] = fmaf(w, bf_hi(h.y) + bf_hi(l.y), a[3]);
     a[4] = fmaf(w, bf_lo(h.z) + bf_lo(l.z), a[4]); a[5] = fmaf(w, bf_hi(h.z) + bf_hi(l.z), a[5]);
@@ -1249,7 +1281,7 @@ __global__ void __launch_bounds__(256) attn_rows_fwd_kernel(int S, int M, const 
 // backward, part 1 (a warp per row of I, fully parallel over the B*S rows): dp[r] = dp_in[r] + sum_m da[b(r), m] I[r, m]
 __global__ void __launch_bounds__(256) attn_rows_dp_kernel(int R, int S, int M, const bf16* __restrict__ I_hi,
                                                            const bf16* __restrict__ I_lo, const float* __restrict__ da,
-                                                           const float* __restrict__ dp_in, float* __restrict__ dp) {
+                                                           const float* __restrict__ dp_in, float* __restrict__ dp, int f16) {
   RAU_PDL_ENTRY();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -1267,6 +1299,11 @@ __global__ void __launch_bounds__(256) attn_rows_dp_kernel(int R, int S, int M, 
     if (il) l = __ldg(il + w);
     const float4 d0 = __ldg(reinterpret_cast<const float4*>(d + 8 * w));
     const float4 d1 = __ldg(reinterpret_cast<const float4*>(d + 8 * w) + 1);
+    if (f16) {
+      acc = fmaf(d0.x, hf_lo(h.x), acc); acc = fmaf(d0.y, hf_hi(h.x), acc); acc = fmaf(d0.z, hf_lo(h.y), acc); acc = fmaf(d0.w, hf_hi(h.y), acc);
+      acc = fmaf(d1.x, hf_lo(h.z), acc); acc = fmaf(d1.y, hf_hi(h.z), acc); acc = fmaf(d1.z, hf_lo(h.w), acc); acc = fmaf(d1.w, hf_hi(h.w), acc);
+      continue;
+    }
     acc = fmaf(d0.x, bf_lo(h.x) + bf_lo(l.x), acc); acc = fmaf(d0.y, bf_hi(h.x) + bf_hi(l.x), acc);
     acc = fmaf(d0.z, bf_lo(h.y) + bf_lo(l.y), acc); acc = fmaf(d0.w, bf_hi(h.y) + bf_hi(l.y), acc);
     acc = fmaf(d1.x, bf_lo(h.z) + bf_lo(l.z), acc); acc = fmaf(d1.y, bf_hi(h.z) + bf_hi(l.z), acc);
@@ -1286,7 +1323,8 @@ __global__ void __launch_bounds__(256) attn_rows_dz_kernel(int S, int A, const f
                                                            const float* __restrict__ dp, float* __restrict__ ds_out,
                                                            bf16* __restrict__ dZ_hi, bf16* __restrict__ dZ_lo,
                                                            float* __restrict__ dqa, float* __restrict__ gws_part,
-                                                           bf16* __restrict__ ds_hi, bf16* __restrict__ ds_lo, int ldds) {
+                                                           bf16* __restrict__ ds_hi, bf16* __restrict__ ds_lo, int ldds,
+                                                           int f16, float gscale) {
   RAU_PDL_ENTRY();
   __shared__ float ds[256];
   __shared__ float red[32];
@@ -1324,6 +1362,11 @@ __global__ void __launch_bounds__(256) attn_rows_dz_kernel(int S, int A, const f
     sg0 = fmaf(d, e.x, sg0); sg1 = fmaf(d, e.y, sg1); sg2 = fmaf(d, e.z, sg2); sg3 = fmaf(d, e.w, sg3);
     sz0 += z0; sz1 += z1; sz2 += z2; sz3 += z3;
     uint32_t h0, l0, h1, l1;
+    if (f16) {   // one fp16 plane, carried times gscale (the products that read it scale their fp32 results back)
+      reinterpret_cast<uint2*>(dZ_hi + (r0 + s) * A)[ng] =
+          make_uint2(pack_f16x2(z0 * gscale, z1 * gscale), pack_f16x2(z2 * gscale, z3 * gscale));
+      continue;
+    }
     split_pair(z0, z1, h0, l0);
     split_pair(z2, z3, h1, l1);
     reinterpret_cast<uint2*>(dZ_hi + (r0 + s) * A)[ng] = make_uint2(h0, h1);
@@ -1931,7 +1974,11 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   p.bias = g.bias; p.rowvec = g.rowvec; p.colw = g.colw; p.rowout = g.rowout; p.rowscale = g.rowscale;
   p.aux_hi = g.aux_hi; p.aux_lo = g.aux_lo; p.ldaux = g.ldaux; p.colsum = g.colsum; p.S = g.S > 0 ? g.S : 1;
   p.alpha = g.alpha;
-  p.fast_tanh = p.x3 ? 0 : 1;   // single-pass bf16: the result is rounded to bf16 anyway, MUFU.TANH (2^-11) is below that
+  p.f16 = g.f16 ? 1 : 0;
+  p.gscale = g.gscale;
+  RAU_REQUIRE(!(p.f16 && p.x3), "rows_gemm: fp16 operands are single-plane");
+  // single-pass bf16: the result is rounded to bf16 anyway, MUFU.TANH (2^-11) is below that; fp16 keeps the accurate form
+  p.fast_tanh = (p.x3 || p.f16) ? 0 : 1;
   const int items = tiles * p.ksplit;
   int grid = items < sm_avail ? items : sm_avail;
   if (p.cg2) grid = 2 * (items < sm_avail / 2 ? items : sm_avail / 2);   // whole CTA pairs
@@ -1958,12 +2005,14 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   }
 }
 
-int rows_pack(rau_ctx* ctx, const float* W, int64_t n, bool want_lo, bool cache, const char* slot, const bf16** hi, const bf16** lo) {
+int rows_pack(rau_ctx* ctx, const float* W, int64_t n, bool want_lo, bool cache, const char* slot, const bf16** hi, const bf16** lo,
+              bool f16) {
   RAU_REQUIRE(n % 8 == 0 && ((uintptr_t)W & 15) == 0, "rows_pack: %lld elements / alignment", (long long)n);
+  if (f16) want_lo = false;
   char name[128];
   bool cached = false;
   if (cache) {
-    snprintf(name, sizeof(name), "rw.%p.%lld.%d", (const void*)W, (long long)n, want_lo ? 1 : 0);
+    snprintf(name, sizeof(name), "rw.%p.%lld.%d", (const void*)W, (long long)n, f16 ? 2 : (want_lo ? 1 : 0));
     auto it = ctx->tc_epoch.find(name);
     cached = it != ctx->tc_epoch.end() && it->second == ctx->epoch;
   } else {
@@ -1977,7 +2026,7 @@ int rows_pack(rau_ctx* ctx, const float* W, int64_t n, bool want_lo, bool cache,
   if (!cached) {
     int64_t blocks = (n / 4 + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    RAU_LAUNCH_PDL(ctx->stream, (pack_hilo_kernel), (int)blocks, 256, 0, W, n / 4, h, l);
+    RAU_LAUNCH_PDL(ctx->stream, (pack_hilo_kernel), (int)blocks, 256, 0, W, n / 4, h, l, f16 ? 1 : 0);
     RAU_LAUNCH_CHECK(ctx);
     if (cache) ctx->tc_epoch[name] = ctx->epoch;
   }
@@ -1995,14 +2044,14 @@ static int prep_attr() {
   return RAU_OK;
 }
 
-int k_unpack_hilo(rau_ctx* ctx, const bf16* hi, const bf16* lo, int64_t n, float* out) {
-  unpack_hilo_kernel<<<(int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256, 0, ctx->stream>>>(hi, lo, n, out);
+int k_unpack_hilo(rau_ctx* ctx, const bf16* hi, const bf16* lo, int64_t n, float* out, int f16) {
+  unpack_hilo_kernel<<<(int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256, 0, ctx->stream>>>(hi, lo, n, out, f16);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 
 int k_xprep_rows_hops(rau_ctx* ctx, const float* X, int B, int C, int S, int nHop, float scale, bf16* hi, bf16* lo,
-                      int64_t hop_stride, float p_drop, uint64_t stream_id) {
+                      int64_t hop_stride, float p_drop, uint64_t stream_id, int f16) {
   RAU_REQUIRE(C % 64 == 0 && S % 4 == 0 && S <= 200 && ((uintptr_t)X & 15) == 0 && hop_stride % 2 == 0, "k_xprep_rows_hops: C=%d S=%d", C, S);
   const int smem = 4 * S * 66 * 4;
   static bool attr = false;
@@ -2017,20 +2066,20 @@ int k_xprep_rows_hops(rau_ctx* ctx, const float* X, int B, int C, int S, int nHo
   const int grid = (ntiles + 3) / 4 < cap ? (ntiles + 3) / 4 : cap;
   RAU_LAUNCH_PDL(ctx->stream, (xprep_rows_hops_kernel), grid, 1024, smem,
       X, scale, C, S, B, nHop, hi, lo, (long long)hop_stride, thresh, make_uint2((uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32)),
-      (uint32_t)stream_id, (uint32_t)(stream_id >> 32), ctx->ss_active);
+      (uint32_t)stream_id, (uint32_t)(stream_id >> 32), ctx->ss_active, f16);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
 
 int k_xprep_rows(rau_ctx* ctx, const float* X, int B, int C, int S, const uint32_t* bits, float scale, bf16* hi, bf16* lo,
-                 int gen, float p_drop, uint64_t stream_id) {
+                 int gen, float p_drop, uint64_t stream_id, int f16) {
   RAU_REQUIRE(C % 64 == 0 && S % 4 == 0 && S <= 256 && ((uintptr_t)X & 15) == 0, "k_xprep_rows: C=%d S=%d", C, S);
   RAU_TRY(prep_attr());
   const double keep = 1.0 - (double)p_drop;
   const uint32_t thresh = keep >= 1.0 ? 65536u : (uint32_t)(keep * 65536.0 + 0.5);   // 16-bit keep threshold (gen path)
   RAU_LAUNCH_PDL(ctx->stream, (xprep_rows_kernel), dim3(C / 64, B), 256, S * 66 * 4, 
       X, bits, scale, C, S, hi, lo, gen, thresh, make_uint2((uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32)), (uint32_t)stream_id,
-      (uint32_t)(stream_id >> 32), ctx->ss_active);
+      (uint32_t)(stream_id >> 32), ctx->ss_active, f16);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
@@ -2044,10 +2093,10 @@ int k_unprep_rows(rau_ctx* ctx, const float* dXr, int B, int C, int S, const uin
 }
 
 int k_attn_rows_fwd(rau_ctx* ctx, int B, int M, int S, const float* logit, const float* mem, const bf16* I_hi, const bf16* I_lo,
-                    float* p, float* a, bf16* p_hi, bf16* p_lo, int ldp) {
+                    float* p, float* a, bf16* p_hi, bf16* p_lo, int ldp, int f16) {
   RAU_REQUIRE(M % 256 == 0 && S <= 256 && ldp <= 256, "k_attn_rows_fwd: M=%d S=%d", M, S);
   RAU_LAUNCH_PDL(ctx->stream, (attn_rows_fwd_kernel<0>), dim3(B, M / 256), 256, 0, S, M, logit, mem, I_hi, I_lo, p, a, p_hi, p_lo, ldp,
-                 0, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr);
+                 0, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, f16);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
@@ -2055,14 +2104,14 @@ int k_attn_rows_fwd(rau_ctx* ctx, int B, int M, int S, const float* logit, const
 // content logits + attbymemory + attselect in one launch (see attn_rows_fwd_kernel<SCORE>)
 int k_attn_rows_fwd_scored(rau_ctx* ctx, int B, int M, int A, int S, const float* Z, const float* qadd, const float* ws,
                            int fast_tanh, const float* mem, const bf16* I_hi, const bf16* I_lo, float* p, float* a, bf16* p_hi,
-                           bf16* p_lo, int ldp) {
+                           bf16* p_lo, int ldp, int f16) {
   RAU_REQUIRE(M % 256 == 0 && S <= 256 && ldp <= 256 && A % 4 == 0, "k_attn_rows_fwd_scored: M=%d A=%d S=%d", M, A, S);
   if (fast_tanh)
     RAU_LAUNCH_PDL(ctx->stream, (attn_rows_fwd_kernel<2>), dim3(B, M / 256), 256, 0, S, M, (const float*)nullptr, mem, I_hi, I_lo, p, a,
-                   p_hi, p_lo, ldp, A, Z, qadd, ws);
+                   p_hi, p_lo, ldp, A, Z, qadd, ws, f16);
   else
     RAU_LAUNCH_PDL(ctx->stream, (attn_rows_fwd_kernel<1>), dim3(B, M / 256), 256, 0, S, M, (const float*)nullptr, mem, I_hi, I_lo, p, a,
-                   p_hi, p_lo, ldp, A, Z, qadd, ws);
+                   p_hi, p_lo, ldp, A, Z, qadd, ws, f16);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
@@ -2085,12 +2134,13 @@ int k_attn_rows_score(rau_ctx* ctx, int B, int A, int S, const float* Z, const f
 
 int k_attn_rows_bwd(rau_ctx* ctx, int B, int M, int A, int S, const float* E, const bf16* I_hi, const bf16* I_lo, const float* ws,
                     const float* p, const float* dp_in, const float* da, float* ds, bf16* dZ_hi, bf16* dZ_lo, float* dqa,
-                    float* gws_part, bf16* ds_hi, bf16* ds_lo, int ldds, const float* qadd, int fast_tanh, int acc_zeroed) {
+                    float* gws_part, bf16* ds_hi, bf16* ds_lo, int ldds, const float* qadd, int fast_tanh, int acc_zeroed, int f16,
+                    float gscale) {
   RAU_REQUIRE(M % 8 == 0 && S <= 256 && ldds <= 256 && (A == 64 || A == 128 || A == 256), "k_attn_rows_bwd: M=%d A=%d S=%d", M, A, S);
   const int R = B * S;
   float* dp = nullptr;
   RAU_TRY(ctx->arena.get("attn.dp", sizeof(float) * (size_t)R, (void**)&dp));
-  RAU_LAUNCH_PDL(ctx->stream, (attn_rows_dp_kernel), (R + 7) / 8, 256, 0, R, S, M, I_hi, I_lo, da, dp_in, dp);
+  RAU_LAUNCH_PDL(ctx->stream, (attn_rows_dp_kernel), (R + 7) / 8, 256, 0, R, S, M, I_hi, I_lo, da, dp_in, dp, f16);
   RAU_LAUNCH_CHECK(ctx);
   if (!acc_zeroed) {
     RAU_CHECK_CUDA(cudaMemsetAsync(dqa, 0, sizeof(float) * (size_t)B * A, ctx->stream));
@@ -2099,13 +2149,13 @@ int k_attn_rows_bwd(rau_ctx* ctx, int B, int M, int A, int S, const float* E, co
   const int nsl = B >= 128 ? 4 : (B >= 32 ? 8 : 16);   // row slices per image: ~1000 CTAs
   if (!qadd)
     RAU_LAUNCH_PDL(ctx->stream, (attn_rows_dz_kernel<0>), dim3(B, nsl), 256, 0, S, A, E, qadd, ws, p, dp, ds, dZ_hi, dZ_lo, dqa,
-                   gws_part, ds_hi, ds_lo, ldds);
+                   gws_part, ds_hi, ds_lo, ldds, f16, gscale);
   else if (!fast_tanh)
     RAU_LAUNCH_PDL(ctx->stream, (attn_rows_dz_kernel<1>), dim3(B, nsl), 256, 0, S, A, E, qadd, ws, p, dp, ds, dZ_hi, dZ_lo, dqa,
-                   gws_part, ds_hi, ds_lo, ldds);
+                   gws_part, ds_hi, ds_lo, ldds, f16, gscale);
   else
     RAU_LAUNCH_PDL(ctx->stream, (attn_rows_dz_kernel<2>), dim3(B, nsl), 256, 0, S, A, E, qadd, ws, p, dp, ds, dZ_hi, dZ_lo, dqa,
-                   gws_part, ds_hi, ds_lo, ldds);
+                   gws_part, ds_hi, ds_lo, ldds, f16, gscale);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
@@ -2426,7 +2476,7 @@ int rows_contract_try(rau_ctx* ctx, const SimtGemm& g) {
   const int a_mn = (g.sak == 1) ? 0 : (g.sam == 1 ? 1 : -1);
   const int b_mn = (g.sbk == 1) ? 0 : (g.sbn == 1 ? 1 : -1);
   if (a_mn < 0 || b_mn < 0) return 0;
-  const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+  const bool x3 = prec_x3(ctx);
   RowsGemm r;
   r.M = g.M; r.N = g.N; r.K = g.K;
   Packed2D pa, pb, pa2, pb2;

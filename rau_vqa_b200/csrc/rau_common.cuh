@@ -73,7 +73,7 @@ struct rau_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   uint64_t seed = 0x5eed5eedULL;
-  int precision = RAU_PREC_BF16X3;
+  int precision = RAU_PREC_MIXED;
   int sm_count = 148;
   int64_t launches = 0;
   RauArena arena;
@@ -119,6 +119,12 @@ struct rau_ctx {
   std::vector<std::string> stamp_names;
 };
 void rau_phase_mark(rau_ctx* ctx, const char* name);
+
+// precision mode -> operand formats.  prec_x3: products on the recurrent chain / encoder / small nn.Linear layers carry
+// bf16 (hi, lo) operands (three MMA passes).  prec_img_f16: the image-side tensors of an answering unit (Xd, I, dZ, dY and
+// the Wi / Wa shadows) are single fp16 planes, gradient operands scaled by a power of two (RAU_PREC_MIXED).
+static inline bool prec_x3(const rau_ctx* c) { return c->precision == RAU_PREC_BF16X3 || c->precision == RAU_PREC_MIXED; }
+static inline bool prec_img_f16(const rau_ctx* c) { return c->precision == RAU_PREC_MIXED; }
 
 #define RAU_LAUNCH_CHECK(ctx)                                                             \
   do {                                                                                    \

@@ -86,30 +86,31 @@ cudaEvent_t rau_side_event(rau_ctx* ctx) {
 int hop_forward_pre(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const float*>& P, const float* X, int train,
                     const HopSaved& sv) {
   const int M = cfg->M, S = cfg->S, C = cfg->C, R = B * S;
-  const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+  const int f16 = prec_img_f16(ctx) ? 1 : 0;   // image-side tensors are single fp16 planes (RAU_PREC_MIXED)
+  const bool x3 = prec_x3(ctx) && !f16;        // ... or bf16 (hi, lo) pairs
   const uint32_t* xb = (train && cfg->p_x > 0) ? sv.xbits : nullptr;
   const bf16 *Wi_h, *Wi_l;
-  RAU_TRY(rows_pack(ctx, P.Wi, (int64_t)M * C, x3, true, nullptr, &Wi_h, &Wi_l));
+  RAU_TRY(rows_pack(ctx, P.Wi, (int64_t)M * C, x3, true, nullptr, &Wi_h, &Wi_l, f16));
   if (!sv.x_done)
     RAU_TRY(k_xprep_rows(ctx, X, B, C, S, xb, drop_scale(cfg->p_x), sv.Xd_hi, x3 ? sv.Xd_lo : nullptr,
-                         (train && cfg->p_x > 0 && sv.x_philox) ? 1 : 0, cfg->p_x, sv.x_stream));
+                         (train && cfg->p_x > 0 && sv.x_philox) ? 1 : 0, cfg->p_x, sv.x_stream, f16));
   RowsGemm g;
   g.M = R; g.N = M; g.K = C;
   g.A.hi = sv.Xd_hi; g.A.lo = x3 ? sv.Xd_lo : nullptr; g.A.ld = C;
   g.B.hi = Wi_h; g.B.lo = Wi_l; g.B.ld = C;
-  g.epi = ROWS_EPI_TANH; g.bias = P.bi;
+  g.epi = ROWS_EPI_TANH; g.bias = P.bi; g.f16 = f16;
   g.out_hi = sv.I_hi; g.out_lo = x3 ? sv.I_lo : nullptr; g.ldo = M;
   RAU_TRY(rows_gemm(ctx, g));
   // attbycontent (F:244-252), the half the state does not reach: Z = I Wa^T.  hop_forward() adds the query term per image
   // and takes tanh and the ws reduction in a bandwidth-bound pass, so no tensor product is left on the recurrent chain.
   const int A = cfg->A;
   const bf16 *Wa_h, *Wa_l;
-  RAU_TRY(rows_pack(ctx, P.Wa, (int64_t)A * M, x3, true, nullptr, &Wa_h, &Wa_l));
+  RAU_TRY(rows_pack(ctx, P.Wa, (int64_t)A * M, x3, true, nullptr, &Wa_h, &Wa_l, f16));
   RowsGemm z;
   z.M = R; z.N = A; z.K = M;
   z.A.hi = sv.I_hi; z.A.lo = x3 ? sv.I_lo : nullptr; z.A.ld = M;
   z.B.hi = Wa_h; z.B.lo = Wa_l; z.B.ld = M;
-  z.epi = ROWS_EPI_PLAIN;
+  z.epi = ROWS_EPI_PLAIN; z.f16 = f16;
   z.out_f = sv.E; z.ldo = A;
   return rows_gemm(ctx, z);
 }
@@ -123,7 +124,7 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
   const uint32_t* xb = (train && cfg->p_x > 0) ? sv.xbits : nullptr;
   const uint32_t* mb = (train && cfg->p_m > 0) ? sv.mbits : nullptr;
   const bool tc = ctx->precision != RAU_PREC_F32 && S % 4 == 0;   // tcgen05 modes: operands are produced packed
-  const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+  const bool x3 = prec_x3(ctx);
   float* Xd = nullptr;
   if (!tc) RAU_TRY(ctx->arena.get("hop.Xd", sizeof(float) * (size_t)B * C * Sp, (void**)&Xd));
   ARENA(qatt, float, "hop.qatt", B * A);
@@ -174,6 +175,7 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
   if (rows_path(ctx, cfg)) {
     // rows layout (k_rows_tc.cu): r = b*S + s.  sv.Xd_* = drop(X)^T [R,C], sv.I_* = I [R,M], sv.E = Z = I Wa^T [R,A] (fp32)
     const int R = B * S;
+    const int f16i = prec_img_f16(ctx) ? 1 : 0;   // I is one fp16 plane
     ARENA(slog, float, "hop.slog", R);
     // the feature pack, I = tanh(Wi X + bi) and Z = I Wa^T do not depend on the state: in the training step
     // hop_forward_pre() already ran them on the side stream
@@ -200,11 +202,11 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
     const char* e_af = getenv("RAU_ATTN_FUSED");
     if (!(e_af && atoi(e_af) != 0)) {
       RAU_TRY(k_attn_rows_score(ctx, B, A, S, sv.E, sv.qatt, P.ws, x3 ? 0 : 1, slog));
-      RAU_TRY(k_attn_rows_fwd(ctx, B, M, S, slog, mem, sv.I_hi, x3 ? sv.I_lo : nullptr, sv.p, a, sv.p_pk.hi,
-                              x3 ? sv.p_pk.lo : nullptr, (int)sv.p_pk.ld));
+      RAU_TRY(k_attn_rows_fwd(ctx, B, M, S, slog, mem, sv.I_hi, (x3 && !f16i) ? sv.I_lo : nullptr, sv.p, a, sv.p_pk.hi,
+                              x3 ? sv.p_pk.lo : nullptr, (int)sv.p_pk.ld, f16i));
     } else {
-      RAU_TRY(k_attn_rows_fwd_scored(ctx, B, M, A, S, sv.E, sv.qatt, P.ws, x3 ? 0 : 1, mem, sv.I_hi, x3 ? sv.I_lo : nullptr, sv.p, a,
-                                     sv.p_pk.hi, x3 ? sv.p_pk.lo : nullptr, (int)sv.p_pk.ld));
+      RAU_TRY(k_attn_rows_fwd_scored(ctx, B, M, A, S, sv.E, sv.qatt, P.ws, x3 ? 0 : 1, mem, sv.I_hi, (x3 && !f16i) ? sv.I_lo : nullptr,
+                                     sv.p, a, sv.p_pk.hi, x3 ? sv.p_pk.lo : nullptr, (int)sv.p_pk.ld, f16i));
     }
   } else {
   // i_embed (F:238-242): I[b] = tanh(Wi drop(X[b]) + bi), 1x1 convolution = per-image [M,C]x[C,S] product
@@ -339,7 +341,7 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   const uint32_t* xb = (train && cfg->p_x > 0) ? sv.xbits : nullptr;
   const uint32_t* mb = (train && cfg->p_m > 0) ? sv.mbits : nullptr;
   const bool tc = ctx->precision != RAU_PREC_F32 && S % 4 == 0;
-  const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+  const bool x3 = prec_x3(ctx);
   const bool now = deferred == nullptr;   // accumulate the nn.Linear weight / bias gradients inside this call
   float* Xd = nullptr;
   if (!tc || dX) RAU_TRY(ctx->arena.get("hop.Xd", sizeof(float) * (size_t)B * C * Sp, (void**)&Xd));
@@ -454,10 +456,18 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   // attselect + softmax + score conv + tanh of attbycontent, one CTA per image
   const bool rows = rows_path(ctx, cfg);
   const int R = B * S;
+  // RAU_PREC_MIXED: the image-side tensors (I, dZ, dY, Xd, the Wi / Wa shadows) are single fp16 planes.  dZ and dY are carried
+  // times a power of two (~2^12 * B: d loss / d score is O(1 / B), so the scaled values sit in the middle of fp16's range
+  // whatever the batch) and every product that reads one of them scales its fp32 result back.
+  const int f16i = (rows && prec_img_f16(ctx)) ? 1 : 0;
+  const bool x3i = x3 && !f16i;
+  float gs = 1.0f;
+  if (f16i) { gs = 4096.0f; for (int b2 = 1; b2 < B && gs < 1.0e9f; b2 <<= 1) gs *= 2.0f; }
+  if (f16i) { dZ_lo = nullptr; dY_lo = nullptr; }
   if (rows)
-    RAU_TRY(k_attn_rows_bwd(ctx, B, M, A, S, sv.E, sv.I_hi, x3 ? sv.I_lo : nullptr, P.ws, sv.p, dp, dj, ds, dZ_hi, dZ_lo, dqa, gwsp,
+    RAU_TRY(k_attn_rows_bwd(ctx, B, M, A, S, sv.E, sv.I_hi, x3i ? sv.I_lo : nullptr, P.ws, sv.p, dp, dj, ds, dZ_hi, dZ_lo, dqa, gwsp,
                             ds_pk.hi, x3 ? ds_pk.lo : nullptr, (int)ds_pk.ld, sv.qatt, x3 ? 0 : 1,
-                            deferred ? deferred->acc_zeroed : 0));
+                            deferred ? deferred->acc_zeroed : 0, f16i, gs));
   else
     RAU_TRY(k_attn_bwd<float>(ctx, B, M, A, S, Sp, sv.E, sv.I, P.ws, sv.p, dp, dj, ds, nullptr, 0, dZ, dqa, nullptr, gwsp,
                               dZ_hi, dZ_lo));
@@ -475,7 +485,7 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   }
   if (rows) {
     const bf16 *Wa_h, *Wa_l;
-    RAU_TRY(rows_pack(ctx, P.Wa, (int64_t)A * M, x3, true, nullptr, &Wa_h, &Wa_l));
+    RAU_TRY(rows_pack(ctx, P.Wa, (int64_t)A * M, x3i, true, nullptr, &Wa_h, &Wa_l, f16i));
     // nothing below feeds the previous hop's backward: in the training step these three products go to the side stream
     // (capped to ctx->side_ctas SMs) and overlap the chain of small kernels; the caller joins the stream at the end
     cudaStream_t chain = ctx->stream;
@@ -495,7 +505,8 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
       g.A.hi = dZ_hi; g.A.lo = dZ_lo; g.A.ld = A;
       g.B.hi = Wa_h; g.B.lo = Wa_l; g.B.mn = 1; g.B.ld = M;
       g.epi = ROWS_EPI_DY; g.rowvec = dj; g.rowscale = sv.p; g.S = S;
-      g.aux_hi = sv.I_hi; g.aux_lo = x3 ? sv.I_lo : nullptr; g.ldaux = M; g.colsum = G.bi;
+      g.f16 = f16i; g.gscale = gs; g.alpha = 1.0f / gs;
+      g.aux_hi = sv.I_hi; g.aux_lo = x3i ? sv.I_lo : nullptr; g.ldaux = M; g.colsum = G.bi;
       g.out_hi = dY_hi; g.out_lo = dY_lo; g.ldo = M;
       if ((side_rc = rows_gemm(ctx, g)) != RAU_OK) break;
     }
@@ -503,14 +514,16 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
       RowsGemm g;
       g.M = A; g.N = M; g.K = R;
       g.A.hi = dZ_hi; g.A.lo = dZ_lo; g.A.mn = 1; g.A.ld = A;
-      g.B.hi = sv.I_hi; g.B.lo = x3 ? sv.I_lo : nullptr; g.B.mn = 1; g.B.ld = M;
+      g.B.hi = sv.I_hi; g.B.lo = x3i ? sv.I_lo : nullptr; g.B.mn = 1; g.B.ld = M;
+      g.f16 = f16i; g.alpha = 1.0f / gs;
       if ((side_rc = rows_wgrad(ctx, g, G.Wa, M)) != RAU_OK) break;
     }
     if (side) {   // gWi += dY^T drop(X)^T (issued further down in the synchronous mode)
       RowsGemm g;
       g.M = M; g.N = C; g.K = R;
       g.A.hi = dY_hi; g.A.lo = dY_lo; g.A.mn = 1; g.A.ld = M;
-      g.B.hi = sv.Xd_hi; g.B.lo = x3 ? sv.Xd_lo : nullptr; g.B.mn = 1; g.B.ld = C;
+      g.B.hi = sv.Xd_hi; g.B.lo = x3i ? sv.Xd_lo : nullptr; g.B.mn = 1; g.B.ld = C;
+      g.f16 = f16i; g.alpha = 1.0f / gs;
       if ((side_rc = rows_wgrad(ctx, g, G.Wi, C)) != RAU_OK) break;
     }
     } while (0);
@@ -559,18 +572,19 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
       RowsGemm g;
       g.M = M; g.N = C; g.K = R;
       g.A.hi = dY_hi; g.A.lo = dY_lo; g.A.mn = 1; g.A.ld = M;
-      g.B.hi = sv.Xd_hi; g.B.lo = x3 ? sv.Xd_lo : nullptr; g.B.mn = 1; g.B.ld = C;
+      g.B.hi = sv.Xd_hi; g.B.lo = x3i ? sv.Xd_lo : nullptr; g.B.mn = 1; g.B.ld = C;
+      g.f16 = f16i; g.alpha = 1.0f / gs;
       RAU_TRY(rows_wgrad(ctx, g, G.Wi, C));
     }
     if (dX) {   // dX = (dY Wi)^T * mask / (1-p): only on request, the training step discards it (F:598)
       const bf16 *Wi_h, *Wi_l;
-      RAU_TRY(rows_pack(ctx, P.Wi, (int64_t)M * C, x3, true, nullptr, &Wi_h, &Wi_l));
+      RAU_TRY(rows_pack(ctx, P.Wi, (int64_t)M * C, x3i, true, nullptr, &Wi_h, &Wi_l, f16i));
       ARENA(dXr, float, "hopb.dXr", (size_t)R * C);
       RowsGemm g;
       g.M = R; g.N = C; g.K = M;
       g.A.hi = dY_hi; g.A.lo = dY_lo; g.A.ld = M;
       g.B.hi = Wi_h; g.B.lo = Wi_l; g.B.mn = 1; g.B.ld = C;
-      g.epi = ROWS_EPI_PLAIN; g.out_f = dXr; g.ldo = C;
+      g.epi = ROWS_EPI_PLAIN; g.out_f = dXr; g.ldo = C; g.f16 = f16i; g.alpha = 1.0f / gs;
       RAU_TRY(rows_gemm(ctx, g));
       RAU_TRY(k_unprep_rows(ctx, dXr, B, C, S, xb, drop_scale(cfg->p_x), dX));
     }
@@ -865,7 +879,7 @@ int rau_rows_gemm(rau_ctx* ctx, int M, int N, int K, const float* A, int lda, in
   RAU_TRY(rau_check_dev(A, "A")); RAU_TRY(rau_check_dev(B, "B")); RAU_TRY(rau_check_dev(D, "D"));
   RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
   ctx->epoch++;
-  const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+  const bool x3 = prec_x3(ctx);
   RowsGemm g;
   g.M = M; g.N = N; g.K = K;
   RAU_TRY(rows_pack(ctx, A, (int64_t)(a_mn ? K : M) * lda, x3, false, "test.A", &g.A.hi, &g.A.lo));
@@ -881,7 +895,7 @@ int rau_rows_gemm_time(rau_ctx* ctx, int M, int N, int K, int a_mn, int b_mn, in
   RAU_REQUIRE(ctx->precision != RAU_PREC_F32, "rau_rows_gemm_time: tcgen05 modes only");
   RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
   ctx->epoch++;
-  const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+  const bool x3 = prec_x3(ctx);
   const int64_t lda = a_mn ? (M + 7) / 8 * 8 : (K + 7) / 8 * 8, ldb = b_mn ? (N + 7) / 8 * 8 : (K + 7) / 8 * 8;
   const int64_t na = (int64_t)(a_mn ? K : M) * lda, nb = (int64_t)(b_mn ? K : N) * ldb;
   float *A = nullptr, *B = nullptr, *D = nullptr;
@@ -964,19 +978,21 @@ int rau_feature_pack(rau_ctx* ctx, const float* X, int B, int C, int S, int nHop
   RAU_REQUIRE(ctx->precision != RAU_PREC_F32, "rau_feature_pack: tcgen05 modes only");
   RAU_REQUIRE(p > 0.0f && p < 1.0f, "rau_feature_pack: 0 < p < 1");
   RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
-  const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+  const int f16 = prec_img_f16(ctx) ? 1 : 0;
+  const bool x3 = prec_x3(ctx) && !f16;
   const size_t n = (size_t)B * S * C;
   bf16* buf = nullptr;
   RAU_TRY(ctx->arena.get("fp.buf", sizeof(bf16) * 2 * n * nHop, (void**)&buf));
   bf16* hi = buf;
   bf16* lo = buf + n * nHop;
   if (all_hops) {
-    RAU_TRY(k_xprep_rows_hops(ctx, X, B, C, S, nHop, drop_scale(p), hi, x3 ? lo : nullptr, (int64_t)n, p, stream_id));
+    RAU_TRY(k_xprep_rows_hops(ctx, X, B, C, S, nHop, drop_scale(p), hi, x3 ? lo : nullptr, (int64_t)n, p, stream_id, f16));
   } else {
     for (int h = 0; h < nHop; ++h)
-      RAU_TRY(k_xprep_rows(ctx, X, B, C, S, nullptr, drop_scale(p), hi + n * h, x3 ? lo + n * h : nullptr, 1, p, stream_id ^ (uint64_t)h));
+      RAU_TRY(k_xprep_rows(ctx, X, B, C, S, nullptr, drop_scale(p), hi + n * h, x3 ? lo + n * h : nullptr, 1, p, stream_id ^ (uint64_t)h,
+                           f16));
   }
-  return k_unpack_hilo(ctx, hi, x3 ? lo : nullptr, (int64_t)n * nHop, out);
+  return k_unpack_hilo(ctx, hi, x3 ? lo : nullptr, (int64_t)n * nHop, out, f16);
 }
 
 int rau_rows_trace(rau_ctx* ctx, uint64_t* out, int n) {

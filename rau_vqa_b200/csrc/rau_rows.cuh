@@ -34,6 +34,8 @@ struct RowsGemm {
   float* colsum = nullptr;          // [N]
   int S = 0;                        // rows per image
   float alpha = 1.0f;
+  int f16 = 0;                      // operands / EPI_TANH, EPI_DY outputs / EPI_DY's saved activation are fp16 (single plane)
+  float gscale = 1.0f;              // EPI_DY: power-of-two scale carried by A (= dZ) and by the output dY; colsum gets alpha
 };
 
 bool rows_path_enabled();
@@ -52,17 +54,18 @@ int rows_pack_lstm(rau_ctx* ctx, const float* W, int H, int K, int gate_order, b
 int rows_perm_lstm_bias(rau_ctx* ctx, const float* b1, const float* b2, int H, int gate_order, const float** out);
 // same, into a caller-owned packed twin (pitch ldo >= cols, zero padded)
 int rows_pack_into(rau_ctx* ctx, const float* src, int64_t ld, int rows, int cols, bf16* hi, bf16* lo, int64_t ldo);
-int rows_pack(rau_ctx* ctx, const float* W, int64_t n, bool want_lo, bool cache, const char* slot, const bf16** hi, const bf16** lo);
+int rows_pack(rau_ctx* ctx, const float* W, int64_t n, bool want_lo, bool cache, const char* slot, const bf16** hi, const bf16** lo,
+              bool f16 = false);   // f16: one fp16 plane instead of bf16 hi [, lo]
 // gen != 0: draw the keep bits inline from Philox stream `stream_id` with drop rate p_drop (bits is then ignored)
 // the same for nHop hops in one launch (training step, drawn masks): hop h writes hi/lo + h*hop_stride, stream id ^ h
 int k_xprep_rows_hops(rau_ctx* ctx, const float* X, int B, int C, int S, int nHop, float scale, bf16* hi, bf16* lo,
-                      int64_t hop_stride, float p_drop, uint64_t stream_id);
-int k_unpack_hilo(rau_ctx* ctx, const bf16* hi, const bf16* lo, int64_t n, float* out);   // out = hi + lo (tests)
+                      int64_t hop_stride, float p_drop, uint64_t stream_id, int f16 = 0);
+int k_unpack_hilo(rau_ctx* ctx, const bf16* hi, const bf16* lo, int64_t n, float* out, int f16 = 0);   // out = hi + lo (tests)
 int k_xprep_rows(rau_ctx* ctx, const float* X, int B, int C, int S, const uint32_t* bits, float scale, bf16* hi, bf16* lo,
-                 int gen = 0, float p_drop = 0.0f, uint64_t stream_id = 0);
+                 int gen = 0, float p_drop = 0.0f, uint64_t stream_id = 0, int f16 = 0);
 int k_unprep_rows(rau_ctx* ctx, const float* dXr, int B, int C, int S, const uint32_t* bits, float scale, float* dX);
 int k_attn_rows_fwd(rau_ctx* ctx, int B, int M, int S, const float* logit, const float* mem, const bf16* I_hi, const bf16* I_lo,
-                    float* p, float* a, bf16* p_hi = nullptr, bf16* p_lo = nullptr, int ldp = 0);   // p_hi/p_lo: packed twin of p
+                    float* p, float* a, bf16* p_hi = nullptr, bf16* p_lo = nullptr, int ldp = 0, int f16 = 0);   // p_hi/p_lo: packed twin of p
 // one encoder LSTM layer over all T steps in a single persistent launch (k_rows_tc.cu lstm_seq_kernel)
 struct LstmSeq {
   int B = 0, H = 0, T = 0;
@@ -92,8 +95,8 @@ int k_attn_rows_score(rau_ctx* ctx, int B, int A, int S, const float* Z, const f
                       float* logit);
 int k_attn_rows_fwd_scored(rau_ctx* ctx, int B, int M, int A, int S, const float* Z, const float* qadd, const float* ws,
                            int fast_tanh, const float* mem, const bf16* I_hi, const bf16* I_lo, float* p, float* a,
-                           bf16* p_hi = nullptr, bf16* p_lo = nullptr, int ldp = 0);
+                           bf16* p_hi = nullptr, bf16* p_lo = nullptr, int ldp = 0, int f16 = 0);
 int k_attn_rows_bwd(rau_ctx* ctx, int B, int M, int A, int S, const float* E, const bf16* I_hi, const bf16* I_lo, const float* ws,
                     const float* p, const float* dp_in, const float* da, float* ds, bf16* dZ_hi, bf16* dZ_lo, float* dqa,
                     float* gws_part, bf16* ds_hi = nullptr, bf16* ds_lo = nullptr, int ldds = 0,
-                    const float* qadd = nullptr, int fast_tanh = 0, int acc_zeroed = 0);
+                    const float* qadd = nullptr, int fast_tanh = 0, int acc_zeroed = 0, int f16 = 0, float gscale = 1.0f);

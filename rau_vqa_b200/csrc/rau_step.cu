@@ -91,7 +91,7 @@ static int encoder_forward(rau_ctx* ctx, const rau_config* cfg, const rau_batch*
   if (fused) {
     // tcgen05 path: each recurrent step is ONE launch -- gate product h_{t-1} Wh^T (+ hoisted input projection) with the
     // cell update fused behind it in the epilogue (EPI_LSTM), which also emits h_t packed for the next step
-    const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+    const bool x3 = prec_x3(ctx);
     const size_t hb = (size_t)B * Hq;
     ARENA(hpk_all, bf16, "enc.hpk", (size_t)4 * (cfg->T + 1) * hb);   // [layer][hi, lo][T+1][B][Hq], kept for the backward pass
     for (int layer = 0; layer < 2; ++layer) {
@@ -201,7 +201,7 @@ static int encoder_backward(rau_ctx* ctx, const rau_config* cfg, const rau_batch
     // tcgen05 path: the pointwise cell backward writes dG packed (hi, lo) next to the fp32 copy, the recurrent dgrad is a
     // split-K product on the rows engine straight from it, and the four weight gradients reuse the packed operands the
     // forward pass left behind (x, h_{t-1}) -- no pack kernels in the time loop
-    const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+    const bool x3 = prec_x3(ctx);
     const size_t gb = (size_t)B * G4, hb = (size_t)B * Hq;
     const int R = Tm * B;
     ARENA(dGp, bf16, "encb.dGp", (size_t)4 * cfg->T * gb);   // [layer][hi, lo][T][B][4H]
@@ -566,7 +566,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   if (prep_aux && ctx->precision != RAU_PREC_F32 && hop_rows_path(ctx, cfg) && rows_path_enabled() && !(e_pp && atoi(e_pp) == 0)) {
     // the bf16 (hi, lo) shadows of the weights the chain's products read: packed here, next to the encoder, instead of
     // inline at their first use on the chain (the per-epoch cache makes the later calls no-ops)
-    const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+    const bool x3 = prec_x3(ctx);
     const bf16 *ph, *pl;
     int64_t pld;
     const float* pb;
@@ -620,8 +620,8 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     for (int hp = 0; hp < nHop; ++hp) all_philox = all_philox && sv[hp].x_philox;
     if (all_philox) {
       rc = k_xprep_rows_hops(ctx, bt->feats, B, cfg->C, S, nHop, drop_scale(cfg->p_x), sv[0].Xd_hi,
-                             ctx->precision == RAU_PREC_BF16X3 ? sv[0].Xd_lo : nullptr, (int64_t)(sv_bytes / sizeof(bf16)), cfg->p_x,
-                             sv[0].x_stream);
+                             (prec_x3(ctx) && !prec_img_f16(ctx)) ? sv[0].Xd_lo : nullptr, (int64_t)(sv_bytes / sizeof(bf16)),
+                             cfg->p_x, sv[0].x_stream, prec_img_f16(ctx) ? 1 : 0);
       for (int hp = 0; hp < nHop; ++hp) sv[hp].x_done = 1;
     }
     for (int hp = 0; hp < nHop && rc == RAU_OK; ++hp) {
@@ -647,7 +647,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   {
     const bool dq_ = train && cfg->p_q > 0;
     RAU_TRY(k_dropout_hops(ctx, en.rnn_out, (int64_t)B * Q, nHop, dq_ ? sv[0].qbits : nullptr, bits_stride, drop_scale(cfg->p_q),
-                           st_qd, pk_qd.hi, ctx->precision == RAU_PREC_BF16X3 ? pk_qd.lo : nullptr));
+                           st_qd, pk_qd.hi, prec_x3(ctx) ? pk_qd.lo : nullptr));
     SimtGemm g = lin_fwd(nHop * B, M_, Q, st_qd, Q, P.Wq, st_qpre, M_);
     g.bias_n = P.bq;
     g.Ar_hi = pk_qd.hi; g.Ar_lo = pk_qd.lo; g.Ar_ld = pk_qd.ld;
@@ -665,7 +665,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     RAU_TRY(rau_contract(ctx, g));
     const bool dm_ = train && cfg->p_m > 0;
     RAU_TRY(k_dropout_bwd_hops(ctx, st_du + r0 * M_, (int64_t)B * M_, nh, dm_ ? sv[h0].mbits : nullptr, bits_stride,
-                               drop_scale(cfg->p_m), dup.hi, ctx->precision == RAU_PREC_BF16X3 ? dup.lo : nullptr));
+                               drop_scale(cfg->p_m), dup.hi, prec_x3(ctx) ? dup.lo : nullptr));
     SimtGemm g2 = lin_dgrad(nh * B, M_, H, st_du + r0 * M_, M_, P.Wo, st_dh2h + r0 * H, H);
     g2.Ar_hi = dup.hi; g2.Ar_lo = dup.lo; g2.Ar_ld = dup.ld;
     return rau_contract(ctx, g2);
@@ -688,7 +688,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     if (ov_head) { ctx->stream = ctx->side; side_used = true; }   // behind this hop's head on the side stream
     const int rc_ce = k_softmax_ce(ctx, B, N, scores + (size_t)hp * B * N, bt->labels, 1.0f / Bg, hm / Bg, loss + hp,
                                    dscore + (size_t)hp * B * N, dsc.hi, N, ans + (size_t)hp * B,
-                                   ctx->precision == RAU_PREC_BF16X3 ? dsc.lo : nullptr);
+                                   prec_x3(ctx) ? dsc.lo : nullptr);
     if (ctx->phases == 2) rau_phase_mark(ctx, "hop head + criterion done");
     ctx->stream = chain;
     RAU_TRY(rc_ce);
@@ -1121,7 +1121,8 @@ int rau_time_iembed(rau_ctx* ctx, const rau_config* cfg, int B, const float* mul
   const int Sp = rau_sp(cfg->S), M = cfg->M, C = cfg->C, S = cfg->S;
   MultT<const float*> P = mult_views<const float*, const float>(cfg, mult_params);
   const bool tc = ctx->precision != RAU_PREC_F32 && S % 4 == 0;
-  const bool x3 = ctx->precision == RAU_PREC_BF16X3;
+  const int f16 = (prec_img_f16(ctx) && hop_rows_path(ctx, cfg)) ? 1 : 0;
+  const bool x3 = prec_x3(ctx) && !f16;
   if (tc && rows_path_enabled() && C % 64 == 0 && M % 64 == 0) {
     // the training launch of the rows engine: packed dropped-out features in, tanh epilogue, packed (hi, lo) I out
     const int R = B * S;
@@ -1130,13 +1131,13 @@ int rau_time_iembed(rau_ctx* ctx, const rau_config* cfg, int B, const float* mul
     ARENA(Ih, bf16, "time.Ih", (size_t)R * M);
     ARENA(Il, bf16, "time.Il", (size_t)R * M);
     const bf16 *Wi_h, *Wi_l;
-    RAU_TRY(rows_pack(ctx, P.Wi, (int64_t)M * C, x3, true, nullptr, &Wi_h, &Wi_l));
-    RAU_TRY(k_xprep_rows(ctx, X, B, C, S, nullptr, 1.0f, Xh, x3 ? Xl : nullptr));
+    RAU_TRY(rows_pack(ctx, P.Wi, (int64_t)M * C, x3, true, nullptr, &Wi_h, &Wi_l, f16));
+    RAU_TRY(k_xprep_rows(ctx, X, B, C, S, nullptr, 1.0f, Xh, x3 ? Xl : nullptr, 0, 0.0f, 0, f16));
     RowsGemm rg;
     rg.M = R; rg.N = M; rg.K = C;
     rg.A.hi = Xh; rg.A.lo = x3 ? Xl : nullptr; rg.A.ld = C;
     rg.B.hi = Wi_h; rg.B.lo = Wi_l; rg.B.ld = C;
-    rg.epi = ROWS_EPI_TANH; rg.bias = P.bi;
+    rg.epi = ROWS_EPI_TANH; rg.bias = P.bi; rg.f16 = f16;
     rg.out_hi = Ih; rg.out_lo = x3 ? Il : nullptr; rg.ldo = M;
     RAU_TRY(rows_gemm(ctx, rg));   // warm-up
     RAU_CHECK_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -1195,6 +1196,6 @@ int rau_contract(rau_ctx* ctx, const SimtGemm& g) {
   }
   RAU_TRY(simt_gemm(ctx, g));
   if (ctx->precision != RAU_PREC_F32 && g.C_hi && g.scn == 1 && g.batch == 1)   // keep the result's packed twin in step
-    RAU_TRY(rows_pack_into(ctx, g.C, g.scm, g.M, g.N, g.C_hi, ctx->precision == RAU_PREC_BF16X3 ? g.C_lo : nullptr, g.scm));
+    RAU_TRY(rows_pack_into(ctx, g.C, g.scm, g.M, g.N, g.C_hi, prec_x3(ctx) ? g.C_lo : nullptr, g.scm));
   return RAU_OK;
 }

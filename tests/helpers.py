@@ -82,7 +82,7 @@ def assert_grads_per_tensor(cfg, grads, ref_grads, tol, report=None):
             if report is not None:
                 report[f"{g}.{name}"] = e
             worst = max(worst, (e, f"{g}.{name}"))
-    bad = {k: v for k, v in (report or {}).items() if v > tol} if report is not None else None
+    bad = {k: v for k, v in (report or {}).items() if isinstance(v, float) and v > tol} if report is not None else None
     assert worst[0] <= tol, (worst, bad)
     return worst
 

@@ -99,10 +99,13 @@ def _graph_step_vs_oracle(name, cfg, B, seed, precision=None, replays=4, step_t=
     return worst, report
 
 
-def test_ours_full_b256_graph_schedule_matches_oracle():
-    """BASELINE.json configs[2] -- the configuration bench.py reports: Ours_Full, nHop 8, C 512, batch 256."""
+@pytest.mark.parametrize("mode", ["default", "bf16x3"])
+def test_ours_full_b256_graph_schedule_matches_oracle(mode):
+    """BASELINE.json configs[2] -- the configuration bench.py reports: Ours_Full, nHop 8, C 512, batch 256 -- in the default
+    precision mode (RAU_PREC_MIXED) and in bf16x3."""
+    from rau_vqa_b200 import core
     cfg = O.RauConfig(V=16384, C=512, nHop=8, N=2000)
-    _graph_step_vs_oracle("ours_full_b256", cfg, 256, seed=2301)
+    _graph_step_vs_oracle("ours_full_b256", cfg, 256, seed=2301, precision=None if mode == "default" else core.PREC_BF16X3)
 
 
 def test_ours_ms_b64_matches_oracle():

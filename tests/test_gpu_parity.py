@@ -26,19 +26,19 @@ def R():
 TOL_BF16 = 3e-2     # single-pass bf16 operands: the fast mode does NOT meet the parity bar and is not the default
 
 
-@pytest.fixture(scope="module", params=["f32", "bf16x3", "bf16"])
+@pytest.fixture(scope="module", params=["f32", "bf16x3", "bf16", "mixed"])
 def ctx(R, request):
     from rau_vqa_b200 import core
     c = R.Context(0)
-    assert int(c.lib.rau_get_precision(c.h)) == core.PREC_BF16X3      # the default is the parity-grade tcgen05 mode
-    c.set_precision(dict(f32=core.PREC_F32, bf16x3=core.PREC_BF16X3, bf16=core.PREC_BF16)[request.param])
+    assert int(c.lib.rau_get_precision(c.h)) == core.PREC_MIXED      # the default: fp16 image side + bf16x3 chain (parity-grade)
+    c.set_precision(dict(f32=core.PREC_F32, bf16x3=core.PREC_BF16X3, bf16=core.PREC_BF16, mixed=core.PREC_MIXED)[request.param])
     c.mode = request.param
     yield c
     c.close()
 
 
 def tol_for(ctx):
-    return dict(f32=TOL_F32, bf16x3=TOL, bf16=TOL_BF16)[ctx.mode]
+    return dict(f32=TOL_F32, bf16x3=TOL, bf16=TOL_BF16, mixed=TOL)[ctx.mode]
 
 
 def _check_step(ctx, cfg, params, X, x, x_len, y, masks, hop_mask=None):
@@ -62,7 +62,8 @@ def _check_step(ctx, cfg, params, X, x, x_len, y, masks, hop_mask=None):
         np.testing.assert_array_equal(ans[h][safe], res.answers[h][safe])
     for g in O.GROUPS:
         assert rel_err(grads[g], res.grads[g]) <= tol, g
-    assert_grads_per_tensor(cfg, grads, res.grads, tol, report={})     # ... and every named tensor on its own scale
+    # ... and every named tensor on its own scale (fp32 mode: atomics / summation order leave ~5e-5 on the small tensors)
+    assert_grads_per_tensor(cfg, grads, res.grads, max(tol, 1e-4), report={})
     return res, grads, out
 
 

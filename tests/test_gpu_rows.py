@@ -58,7 +58,7 @@ def test_rows_gemm_matches_numpy(R, mode, tol, a_mn, b_mn, shape):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16", "mixed"])
 def test_feature_pack_inline_masks(R, mode):
     """rau_feature_pack: dropout (keep bits drawn inline) + transpose to rows + bf16 split of the image features.
     Kept cells hold x/(1-p), dropped ones 0, the keep rate is 1-p, hops draw different masks, and the one-launch
@@ -66,7 +66,7 @@ def test_feature_pack_inline_masks(R, mode):
     import torch
     from rau_vqa_b200 import core
     from rau_vqa_b200._ffi import check, ffi
-    ctx = R.Context(0, seed=5, precision=dict(bf16x3=core.PREC_BF16X3, bf16=core.PREC_BF16)[mode])
+    ctx = R.Context(0, seed=5, precision=dict(bf16x3=core.PREC_BF16X3, bf16=core.PREC_BF16, mixed=core.PREC_MIXED)[mode])
     B, C, S, nHop, p = 5, 128, 196, 3, 0.3
     rng = np.random.default_rng(11)
     X = (rng.standard_normal((B, C, S)).astype(np.float32) + 3.0)      # no zeros: a zero output means "dropped"
@@ -82,7 +82,7 @@ def test_feature_pack_inline_masks(R, mode):
     got = outs[0]
     ref = np.transpose(X, (0, 2, 1)).reshape(B * S, C) / (1.0 - p)
     keep = got != 0.0
-    tol = 1e-5 if mode == "bf16x3" else 1e-2
+    tol = dict(bf16x3=1e-5, bf16=1e-2, mixed=6e-4)[mode]      # (mixed: one fp16 plane, half an ulp = 2^-12 relative)
     for h in range(nHop):
         np.testing.assert_allclose(got[h][keep[h]], ref[keep[h]], rtol=tol)
         rate = keep[h].mean()
