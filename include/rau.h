@@ -238,6 +238,13 @@ int rau_train_step(rau_ctx* ctx, const rau_config* cfg, const rau_batch* batch,
  * (hops, uni = mean over hops, select = first hop with do_pred>0.5, forced at the last hop). */
 int rau_predict(rau_ctx* ctx, const rau_config* cfg, const rau_batch* batch,
                 float* const params[3], float* pred, float* att);
+/* The test loop's answer extraction on the device (F:903-918): rau_predict, then for each of the nHop+2 prediction tables
+ * the open-ended answer argmax_n pred[n] and -- when mc_choices [B, nmc] (1-based candidate ids as next_batch_feat's ans_mc
+ * delivers them, 0 = empty slot; nmc <= 32) is given -- the multiple-choice answer argmax_n pred[n] * mask[n] with the
+ * reference's multiplicative 0/1 mask.  Answers are 1-based floats [nHop+2, B], ties resolve to the lowest index.
+ * pred / att may be NULL when the dense tables are not wanted. */
+int rau_predict_answers(rau_ctx* ctx, const rau_config* cfg, const rau_batch* batch, float* const params[3],
+                        const float* mc_choices, int nmc, float* oe_answers, float* mc_answers, float* pred, float* att);
 
 /* ------------------------------------------------------------------ module-level hop ----- */
 /* protos.multimodal forward (F:292-307) for one hop: {q,X,c,h} -> {score,do_pred,p,c',h'}.

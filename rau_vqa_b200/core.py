@@ -261,5 +261,23 @@ def predict(ctx: Context, cfg: RauConfig, params, feats, tokens, lengths, max_le
     return pred, att
 
 
-__all__ = ["RauConfig", "Context", "StepBuffers", "feval", "noise_clip", "optim_step", "train_step", "predict", "draw_masks",
+def predict_answers(ctx: Context, cfg: RauConfig, params, feats, tokens, lengths, mc_choices=None, max_len: int = 0,
+                    want_tables: bool = False):
+    """predict_result + the test loop's answer extraction (F:903-918) on the device: returns (oe_answers[nHop+2,B],
+    mc_answers[nHop+2,B] or None[, pred, att]); mc_choices = ans_mc [B, nmc] float, 1-based ids, 0 = empty."""
+    keep = []
+    B = feats.shape[0]
+    b = _batch_struct(keep, B, feats, tokens, lengths, None, max_len, 0)
+    f = dict(dtype=torch.float32, device=feats.device)
+    oe = torch.empty(cfg.nHop + 2, B, **f)
+    mc = torch.empty(cfg.nHop + 2, B, **f) if mc_choices is not None else None
+    pred = torch.empty(cfg.nHop + 2, B, cfg.N, **f) if want_tables else None
+    att = torch.empty(cfg.nHop + 2, B, cfg.S, **f) if want_tables else None
+    check(ctx.lib.rau_predict_answers(ctx.h, cfg.c(), b, _triple(keep, params), fptr(mc_choices),
+                                      0 if mc_choices is None else int(mc_choices.shape[1]), fptr(oe), fptr(mc), fptr(pred),
+                                      fptr(att)))
+    return (oe, mc, pred, att) if want_tables else (oe, mc)
+
+
+__all__ = ["predict_answers", "RauConfig", "Context", "StepBuffers", "feval", "noise_clip", "optim_step", "train_step", "predict", "draw_masks",
            "RauError", "fptr", "bptr", "GROUPS"]

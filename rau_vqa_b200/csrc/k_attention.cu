@@ -247,6 +247,46 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(int N, const float* __r
   }
 }
 
+// Open-ended and multiple-choice answers of predict_result's nHop + 2 prediction tables (F:903-918): a warp per
+// (table, sample) row.  oe = argmax_n pred[n]; mc = argmax_n pred[n] * mask[n], where mask[n] = 1 for the sample's candidate
+// answers (ans_mc, 1-based ids, 0 = empty slot) and 0 elsewhere -- the reference MULTIPLIES by the mask (mc_pred:cmul), so a
+// non-candidate scores 0, not -inf, and wins over all-negative candidates; kept as is.  Ties -> lowest index.  1-based.
+__global__ void __launch_bounds__(256) answers_kernel(int rows, int B, int N, const float* __restrict__ pred,
+                                                      const float* __restrict__ mc, int nmc, float* __restrict__ oe_out,
+                                                      float* __restrict__ mc_out) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int b = row % B;
+  const float* p = pred + (int64_t)row * N;
+  float cand[32];   // (nmc <= 32: the VQA multiple-choice task has 18 candidates)
+  for (int k = 0; k < 32; ++k) cand[k] = (mc != nullptr && k < nmc) ? mc[(int64_t)b * nmc + k] : 0.0f;
+  float mo = -INFINITY, mm = -INFINITY;
+  int ao = 0x7fffffff, am = 0x7fffffff;
+  for (int n = lane; n < N; n += 32) {
+    const float v = p[n];
+    if (v > mo) { mo = v; ao = n; }
+    if (mc_out != nullptr) {
+      bool in = false;
+      for (int k = 0; k < 32; ++k) in = in || (cand[k] == (float)(n + 1));
+      const float w = in ? v : v * 0.0f;   // (cmul by the 0/1 mask: NaN / inf propagate like the reference's product)
+      if (w > mm) { mm = w; am = n; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float v1 = __shfl_xor_sync(0xffffffffu, mo, o);
+    const int a1 = __shfl_xor_sync(0xffffffffu, ao, o);
+    if (v1 > mo || (v1 == mo && a1 < ao)) { mo = v1; ao = a1; }
+    const float v2 = __shfl_xor_sync(0xffffffffu, mm, o);
+    const int a2 = __shfl_xor_sync(0xffffffffu, am, o);
+    if (v2 > mm || (v2 == mm && a2 < am)) { mm = v2; am = a2; }
+  }
+  if (lane == 0) {
+    oe_out[row] = (float)(ao + 1);
+    if (mc_out != nullptr) mc_out[row] = (float)(am + 1);
+  }
+}
+
 // logging-only merged predictions (F:539-574) and predict_result's merge (F:699-721); one CTA per row.
 __global__ void __launch_bounds__(256) merge_preds_kernel(int nHop, int B, int N, int S, const float* __restrict__ scores,
                                                           const float* __restrict__ do_pred, const float* __restrict__ attprob,
@@ -396,6 +436,13 @@ int k_softmax_ce(rau_ctx* ctx, int B, int N, const float* score, const float* la
                  float* loss_sum, float* dscore_f, bf16* dscore_b, int lddb, float* answers, bf16* dscore_lo) {
   RAU_LAUNCH_PDL(ctx->stream, (softmax_ce_kernel), B, 256, 0, N, score, labels, loss_scale, grad_scale, loss_sum, dscore_f, dscore_b, lddb, answers,
                  dscore_lo);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
+
+int k_answers(rau_ctx* ctx, int rows, int B, int N, const float* pred, const float* mc, int nmc, float* oe_out, float* mc_out) {
+  if (nmc > 32) { rau_set_error("k_answers: %d multiple-choice candidates > 32", nmc); return RAU_EINVAL; }
+  answers_kernel<<<(rows + 7) / 8, 256, 0, ctx->stream>>>(rows, B, N, pred, mc, nmc, oe_out, mc != nullptr ? mc_out : nullptr);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }

@@ -99,6 +99,9 @@ int k_merge_preds(rau_ctx* ctx, int nHop, int B, int N, int S, const float* scor
                   float* loss_uni_sel /*[2]*/, float* loss_do_pred /*[nHop]*/, float* answers_uni_sel /*[2,B]*/,
                   float* pred_uni, float* pred_sel, float* att_uni, float* att_sel);
 
+// open-ended / multiple-choice answers of `rows` = (nHop+2)*B prediction rows (F:903-918); mc [B, nmc] 1-based ids, 0 = empty
+int k_answers(rau_ctx* ctx, int rows, int B, int N, const float* pred, const float* mc, int nmc, float* oe_out, float* mc_out);
+
 // ---- noise / clip / optimizers (a13, a14)
 int k_noise_norm(rau_ctx* ctx, float* g, int64_t n, float std, const float* noise_override,
                  uint64_t seed, uint64_t stream_id, double* norm2_out);

@@ -1066,8 +1066,9 @@ int rau_train_step(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, flo
   return r;
 }
 
-int rau_predict(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float* const params[3], float* pred, float* att) {
+static int predict_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float* const params[3], float* pred, float* att) {
   RAU_REQUIRE(ctx, "ctx == NULL");
+  RAU_TRY(rau_check_async_error(ctx));
   RAU_TRY(rau_check_cfg(cfg));
   RAU_REQUIRE(cfg->nlayer == 2, "the fused encoder supports nlayer == 2 (F:209), got %d", cfg->nlayer);
   RAU_TRY(check_batch(cfg, bt));
@@ -1084,7 +1085,7 @@ int rau_predict(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float*
   ARENA(c_all, float, "step.c", (size_t)2 * B * H);
   ARENA(h_all, float, "step.h", (size_t)2 * B * H);
   ARENA(dop, float, "step.dop", (size_t)nHop * B);
-  ARENA(att_own, float, "step.att", (size_t)(nHop + 2) * B * S);
+  ARENA(att_own, float, "pred.att", (size_t)(nHop + 2) * B * S);
   float* attp = att ? att : att_own;
   RAU_TRY(k_fill(ctx, c_all, (int64_t)B * H, 0.0f));
   RAU_TRY(k_fill(ctx, h_all, (int64_t)B * H, 0.0f));
@@ -1108,6 +1109,31 @@ int rau_predict(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float*
                         pred + (size_t)nHop * B * N, pred + (size_t)(nHop + 1) * B * N, attp + (size_t)nHop * B * S,
                         attp + (size_t)(nHop + 1) * B * S));
   return RAU_OK;
+}
+
+int rau_predict(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float* const params[3], float* pred, float* att) {
+  return predict_enqueue(ctx, cfg, bt, params, pred, att);
+}
+
+// predict_result followed by the answer extraction of the test loop (F:903-918) on the device: open-ended answers
+// (argmax over the N answers) and, when the batch carries multiple-choice candidates, the masked argmax
+int rau_predict_answers(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, float* const params[3], const float* mc_choices,
+                        int nmc, float* oe_answers, float* mc_answers, float* pred, float* att) {
+  RAU_REQUIRE(ctx && cfg && bt, "ctx/cfg/batch == NULL");
+  RAU_TRY(rau_check_dev(oe_answers, "oe_answers"));
+  if (mc_choices) {
+    RAU_REQUIRE(nmc > 0 && nmc <= 32, "nmc = %d (1..32)", nmc);
+    RAU_TRY(rau_check_dev(mc_choices, "mc_choices"));
+    RAU_TRY(rau_check_dev(mc_answers, "mc_answers"));
+  }
+  float* pr = pred;
+  if (pr == nullptr) {
+    RAU_TRY(rau_check_cfg(cfg));
+    RAU_REQUIRE(bt->B > 0, "batch size %d", bt->B);
+    RAU_TRY(ctx->arena.get("pred.scores", sizeof(float) * (size_t)(cfg->nHop + 2) * bt->B * cfg->N, (void**)&pr));
+  }
+  RAU_TRY(predict_enqueue(ctx, cfg, bt, params, pr, att));
+  return k_answers(ctx, (cfg->nHop + 2) * bt->B, bt->B, cfg->N, pr, mc_choices, nmc, oe_answers, mc_answers);
 }
 
 int rau_time_iembed(rau_ctx* ctx, const rau_config* cfg, int B, const float* mult_params, const float* X, int iters,

@@ -161,6 +161,52 @@ def test_predict_at_reference_dims_uses_the_hoisted_image_side():
     ctx.close()
 
 
+def test_predict_answers_open_ended_and_multiple_choice_bit_exact():
+    """rau_predict_answers: the test loop's answer extraction (F:903-918) on the device at the reference's dimensions.  The
+    open-ended answer is the argmax of each of the nHop+2 tables; the multiple-choice answer is the argmax of pred * mask
+    with the reference's multiplicative 0/1 mask over the 18 candidates (ans_mc, 0 = empty slot).  Both are compared bit for
+    bit with numpy on the library's own tables, and with the oracle's tables wherever its top-2 margin clears the tolerance."""
+    import rau_vqa_b200 as R
+    cfg = O.RauConfig(V=16384, C=512, nHop=3, N=2000)
+    lc = _lib_cfg(cfg)
+    B, nmc = 24, 18
+    params = O.init_params(cfg, seed=2371)
+    X, x, x_len, _ = O.synth_batch(cfg, B, seed=2372)
+    rng = np.random.default_rng(2373)
+    mc = np.zeros((B, nmc))
+    for b in range(B):
+        k = rng.integers(1, nmc + 1)
+        mc[b, :k] = rng.choice(cfg.N, size=k, replace=False) + 1          # 1-based candidate ids, the rest stays 0 = empty
+    ctx = R.Context(0)
+    P = [dev(params[g]) for g in O.GROUPS]
+    oe, mca, pred, att = R.predict_answers(ctx, lc, P, dev(X), dev(x), dev(x_len), mc_choices=dev(mc), max_len=int(x_len.max()),
+                                           want_tables=True)
+    oe2, none = R.predict_answers(ctx, lc, P, dev(X), dev(x), dev(x_len), max_len=int(x_len.max()))
+    ctx.sync()
+    assert none is None
+    pred = pred.cpu().numpy()
+    mask = np.zeros((B, cfg.N), dtype=np.float32)
+    for b in range(B):
+        for v in mc[b]:
+            if v != 0:
+                mask[b, int(v) - 1] = 1
+    np.testing.assert_array_equal(oe.cpu().numpy(), pred.argmax(2) + 1)
+    np.testing.assert_array_equal(oe2.cpu().numpy(), pred.argmax(2) + 1)
+    np.testing.assert_array_equal(mca.cpu().numpy(), (pred * mask[None]).argmax(2) + 1)
+    p32 = {g: params[g].astype(np.float32).astype(np.float64) for g in O.GROUPS}
+    preds, _ = O.predict(cfg, p32, X.astype(np.float32).astype(np.float64), x, x_len)
+    for k in range(cfg.nHop + 2):
+        top2 = np.sort(preds[k], axis=1)[:, -2:]
+        safe = (top2[:, 1] - top2[:, 0]) > 4 * TOL * np.abs(preds[k]).max()
+        assert safe.sum() >= B // 2
+        np.testing.assert_array_equal(oe.cpu().numpy()[k][safe], preds[k].argmax(1)[safe] + 1)
+        mcs = preds[k] * mask
+        t2 = np.sort(mcs, axis=1)[:, -2:]
+        safe = (t2[:, 1] - t2[:, 0]) > 4 * TOL * np.abs(preds[k]).max()
+        np.testing.assert_array_equal(mca.cpu().numpy()[k][safe], mcs.argmax(1)[safe] + 1)
+    ctx.close()
+
+
 def test_train_graph_survives_a_larger_validation_batch():
     """a captured training step bakes arena addresses in; a validation pass with a larger batch re-allocates
     arena buffers.  train (graph) -> predict (larger B) -> train must equal train -> train."""
