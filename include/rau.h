@@ -55,12 +55,14 @@ typedef enum {
   RAU_PREC_BF16 = 1,    /* bf16 operands, tcgen05 MMA, fp32 accumulate in TMEM: the fast mode (~3e-3 relative) */
   RAU_PREC_BF16X3 = 2,  /* bf16 hi/lo split operands (hi*hi + hi*lo + lo*hi, 3 MMA passes into one TMEM accumulator):
                          * ~2e-5 relative on tcgen05 */
-  RAU_PREC_MIXED = 3    /* the DEFAULT.  The image side of an answering unit -- dropped-out features, I = tanh(Wi X + bi),
-                         * Z = I Wa^T and their backward (dZ, dY, gWa, gWi): 98 % of the step's flops -- runs as ONE fp16 pass
-                         * (11-bit significands: operand rounding 2^-12, eight times finer than bf16; the gradient operands dZ, dY
-                         * are carried times a power of two so that they sit in fp16's normal range, and the products' fp32
-                         * results are scaled back).  Everything on the recurrent chain and the encoder stays bf16x3.
-                         * Measured per-tensor error against the float64 oracle: DESIGN.md section 2. */
+  RAU_PREC_MIXED = 3,   /* the DEFAULT.  The two feature-width products of an answering unit -- I = tanh(Wi drop(X) + bi) and
+                         * gWi += dY^T drop(X): 57 % (C = 512) to 87 % (C = 2048) of the step's flops -- run as ONE fp16 pass
+                         * (11-bit significands: operand rounding 2^-12, eight times finer than bf16; dY is carried times a
+                         * power of two so that it sits in fp16's normal range and gWi's fp32 result is scaled back).
+                         * Everything else -- Z = I Wa^T, dY, gWa, the recurrent chain, the encoder -- stays bf16x3. */
+  RAU_PREC_F16IMG = 4   /* the whole image side of an answering unit as single fp16 planes (I, Z, dZ, dY, gWa as well): a third
+                         * of bf16x3's tensor work and half its activation bytes, at 3e-4 .. 1.1e-3 per-tensor error against
+                         * the float64 oracle -- NOT inside the 1e-3 bar with margin, hence opt-in */
 } rau_precision;
 
 typedef enum {
@@ -262,6 +264,34 @@ int rau_hop_bwd(rau_ctx* ctx, const rau_config* cfg, int B, const float* mult_pa
                 const float* dscore, const float* ddo_pred, const float* dp, const float* dc_out, const float* dh_out,
                 float* dq, float* dX, float* dc, float* dh);
 
+/* ------------------------------------------------------------------ batch feed */
+/* Replaces the synchronous per-step upload of the reference: next_batch_feat hands feval HOST tensors feats[B,C,14,14],
+ * x[T,B], x_len[B], y[B] (utils/vqa_prepro_loader.lua:1009) which it casts and copies on the compute stream, B*C*196*4
+ * bytes per step (F:452-456).  rau_feed keeps `depth` batches in flight: the loader fills a slot's pinned staging, submit
+ * enqueues its upload on a copy stream under the running step, acquire makes the context's stream wait for it and describes
+ * the device copy as a rau_batch, release lets a later submit overwrite it.  RAU_FEED_F16 stages the features as fp16 --
+ * half the PCIe bytes; in the default precision mode they enter the tensor pipe as fp16 anyway, so the step's result does
+ * not change by a bit (tests/test_gpu_feed.py). */
+typedef struct rau_feed rau_feed;
+typedef enum { RAU_FEED_F32 = 0, RAU_FEED_F16 = 1 } rau_feed_format;
+int rau_feed_create(rau_ctx* ctx, const rau_config* cfg, int B, int format, int depth /* 2..8 */, rau_feed** out);
+int rau_feed_destroy(rau_feed* feed);
+size_t rau_feed_host_bytes(const rau_feed* feed);   /* bytes one submit moves host -> device */
+int rau_feed_host_slot(rau_feed* feed, int slot, void** feats, float** tokens, float** lengths, float** labels);
+/* the host-side cast of F:452-456 (feats:float()): n values, float64 (src_is_f64 != 0) or float32 -> the staging format */
+int rau_feed_convert(const rau_feed* feed, const void* src, int src_is_f64, int64_t n, void* dst);
+int rau_feed_submit(rau_feed* feed, int slot);
+int rau_feed_acquire(rau_feed* feed, int slot, rau_batch* batch);
+int rau_feed_release(rau_feed* feed, int slot);
+/* The features of a whole split resident in HBM as fp16 (train2014 at C = 512: 16 GB of the 180 GB): a batch's feature
+ * tensor is a gather by image index, no per-step feature upload.  put: HOST float32 [n,C,S] -> images first .. first+n-1
+ * (0-based), load time, synchronous; gather: image_index = DEVICE array of B floats, 1-based -> feats[B,C,S] float32. */
+typedef struct rau_feat_cache rau_feat_cache;
+int rau_feat_cache_create(rau_ctx* ctx, int64_t n_images, int C, int S, rau_feat_cache** out);
+int rau_feat_cache_destroy(rau_feat_cache* cache);
+int rau_feat_cache_put(rau_feat_cache* cache, int64_t first, int64_t n, const float* host_feats);
+int rau_feat_cache_gather(rau_feat_cache* cache, const float* image_index, int B, float* feats);
+
 /* ------------------------------------------------------------------ multi-GPU - */
 /* One process per GPU.  rank 0 calls rau_comm_unique_id, ships the 128 bytes to the other ranks,
  * every rank calls rau_comm_init.  rau_allreduce_grads sums the three flat grads across ranks. */
@@ -304,6 +334,25 @@ int rau_softmax_ce(rau_ctx* ctx, int B, int N, const float* score, const float* 
  * average milliseconds per launch. */
 int rau_time_iembed(rau_ctx* ctx, const rau_config* cfg, int B, const float* mult_params,
                     const float* X, int iters, float* ms_per_launch);
+
+/* Attention-kernel sweep (BASELINE.json configs[4]): each kernel of one answering unit that touches the 196 x C feature block
+ * or the [B*196, M] activation derived from it, launched alone on synthetic operands at batch B in the context's precision
+ * mode; us_out[RAU_SWEEP_COUNT] receives microseconds per launch (CUDA events around every launch; flush_l2 != 0 evicts L2
+ * with a 256 MB memset before each one).  bench.py turns these into HBM and tensor-pipe fractions. */
+typedef enum {
+  RAU_SWEEP_PACK = 0,        /* dropout + transpose to rows + split of X        (F:239)        HBM    */
+  RAU_SWEEP_IEMBED = 1,      /* I = tanh(Wi Xd + bi)                            (F:240-241)    tensor */
+  RAU_SWEEP_Z = 2,           /* Z = I Wa^T                                      (F:247)        tensor */
+  RAU_SWEEP_SCORE = 3,       /* logit = ws . tanh(Z + qatt)                     (F:246-251)    HBM    */
+  RAU_SWEEP_SOFTMAX_SUM = 4, /* p = softmax(logit + mem), a = sum_s p_s I[:,s]  (F:285-290, F:254-263) HBM */
+  RAU_SWEEP_BWD_DP_DZ = 5,   /* dp = da . I ; softmax / tanh backward -> dZ     (two launches) HBM    */
+  RAU_SWEEP_DY = 6,          /* dY = (dZ Wa + da p^T)(1 - I^2), gbi             tensor                */
+  RAU_SWEEP_GWA = 7,         /* gWa += dZ^T I                                   tensor                */
+  RAU_SWEEP_GWI = 8,         /* gWi += dY^T Xd                                  tensor                */
+  RAU_SWEEP_COUNT = 9
+} rau_sweep_kernel;
+int rau_sweep_attention(rau_ctx* ctx, const rau_config* cfg, int B, const float* mult_params, const float* X, int iters,
+                        int flush_l2, float* us_out);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ import torch
 from ._ffi import RauError, check, ffi, load
 
 GATES_IFOG, GATES_IGFO = 0, 1
-PREC_F32, PREC_BF16, PREC_BF16X3, PREC_MIXED = 0, 1, 2, 3
+PREC_F32, PREC_BF16, PREC_BF16X3, PREC_MIXED, PREC_F16IMG = 0, 1, 2, 3, 4
 OPT_SGD, OPT_SGDM, OPT_SGDMOM, OPT_ADAGRAD, OPT_RMSPROP, OPT_ADAM = range(6)
 GROUPS = ("embed", "rnn", "mult")
 

@@ -72,8 +72,11 @@ struct RtParams {
   int S;
   float alpha;
   int fast_tanh;
-  int f16;                         // operands (and EPI_TANH / EPI_DY outputs, EPI_DY's saved activation) are fp16, not bf16
-  float gscale;                    // EPI_DY: the accumulator and the output carry this power-of-two gradient scale
+  int f16;                         // the operands are fp16, not bf16 (single plane)
+  int of16;                        // EPI_TANH / EPI_DY: the output is ONE fp16 plane (not bf16 hi [, lo])
+  int af16;                        // EPI_DY: the saved activation (aux) is one fp16 plane
+  float gscale;                    // EPI_DY: power-of-two gradient scale carried by the OUTPUT dY
+  float accscale;                  // EPI_DY: gscale / (the scale the accumulator already carries through its A operand dZ)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -538,7 +541,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
       const float* rv = nullptr;
       float rs = 0.0f;
       if (EPI == EPI_ATT || EPI == EPI_DY) rv = p.rowvec + (long long)(rr / p.S) * p.N;
-      if (EPI == EPI_DY) rs = (dy_ready ? rs_next : p.rowscale[rr]) * p.gscale;   // (the accumulator holds gscale * dI)
+      if (EPI == EPI_DY) rs = (dy_ready ? rs_next : p.rowscale[rr]) * p.gscale;   // (dY is written times gscale)
       const int c_lo = half * (p.BN / 64), c_hi = c_lo + p.BN / 64;
       bool released = false;
       uint32_t rv_s = 0;
@@ -590,7 +593,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
 #pragma unroll
             for (int k = 0; k < 32; ++k) v[k] = tanh_acc(v[k]);
           }
-          if (p.f16) {
+          if (p.of16) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) w0[k] = pack_f16x2(v[2 * k], v[2 * k + 1]);
           } else if (p.out_lo) {
@@ -785,17 +788,17 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
             const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float y0 = p.f16 ? hf_lo(hh[j]) : bf_lo(hh[j]) + bf_lo(ll[j]);
-              const float y1 = p.f16 ? hf_hi(hh[j]) : bf_hi(hh[j]) + bf_hi(ll[j]);
+              const float y0 = p.af16 ? hf_lo(hh[j]) : bf_lo(hh[j]) + bf_lo(ll[j]);
+              const float y1 = p.af16 ? hf_hi(hh[j]) : bf_hi(hh[j]) + bf_hi(ll[j]);
               const int k = 8 * k8 + 2 * j;
-              const float g0 = (v[k] + dd[2 * j] * rs) * (1.0f - y0 * y0);
-              const float g1 = (v[k + 1] + dd[2 * j + 1] * rs) * (1.0f - y1 * y1);
+              const float g0 = fmaf(v[k], p.accscale, dd[2 * j] * rs) * (1.0f - y0 * y0);
+              const float g1 = fmaf(v[k + 1], p.accscale, dd[2 * j + 1] * rs) * (1.0f - y1 * y1);
               v[k] = r_ok ? g0 : 0.0f;
               v[k + 1] = r_ok ? g1 : 0.0f;
             }
           }
           __syncwarp();   // every lane has read its row before the next chunk overwrites the scratch
-          if (p.f16) {
+          if (p.of16) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) w0[k] = pack_f16x2(v[2 * k], v[2 * k + 1]);
           } else if (p.out_lo) {
@@ -1975,8 +1978,12 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   p.aux_hi = g.aux_hi; p.aux_lo = g.aux_lo; p.ldaux = g.ldaux; p.colsum = g.colsum; p.S = g.S > 0 ? g.S : 1;
   p.alpha = g.alpha;
   p.f16 = g.f16 ? 1 : 0;
+  p.of16 = g.of16 ? 1 : 0;
+  p.af16 = g.af16 ? 1 : 0;
   p.gscale = g.gscale;
+  p.accscale = g.accscale;
   RAU_REQUIRE(!(p.f16 && p.x3), "rows_gemm: fp16 operands are single-plane");
+  RAU_REQUIRE(!(p.of16 && g.out_lo), "rows_gemm: an fp16 output is single-plane");
   // single-pass bf16: the result is rounded to bf16 anyway, MUFU.TANH (2^-11) is below that; fp16 keeps the accurate form
   p.fast_tanh = (p.x3 || p.f16) ? 0 : 1;
   const int items = tiles * p.ksplit;

@@ -120,11 +120,16 @@ struct rau_ctx {
 };
 void rau_phase_mark(rau_ctx* ctx, const char* name);
 
-// precision mode -> operand formats.  prec_x3: products on the recurrent chain / encoder / small nn.Linear layers carry
-// bf16 (hi, lo) operands (three MMA passes).  prec_img_f16: the image-side tensors of an answering unit (Xd, I, dZ, dY and
-// the Wi / Wa shadows) are single fp16 planes, gradient operands scaled by a power of two (RAU_PREC_MIXED).
-static inline bool prec_x3(const rau_ctx* c) { return c->precision == RAU_PREC_BF16X3 || c->precision == RAU_PREC_MIXED; }
-static inline bool prec_img_f16(const rau_ctx* c) { return c->precision == RAU_PREC_MIXED; }
+// precision mode -> operand formats.
+//   prec_x3       products on the recurrent chain / encoder / small nn.Linear layers carry bf16 (hi, lo) operands (3 passes)
+//   prec_x_f16    the dropped-out features Xd, the Wi shadow and dY are single fp16 planes: I = tanh(Wi Xd + bi) and
+//                 gWi += dY^T Xd are one fp16 pass (RAU_PREC_MIXED and RAU_PREC_F16IMG)
+//   prec_img_f16  I, dZ and the Wa shadow are single fp16 planes too: Z, dY, gWa are one fp16 pass (RAU_PREC_F16IMG only)
+static inline bool prec_x3(const rau_ctx* c) {
+  return c->precision == RAU_PREC_BF16X3 || c->precision == RAU_PREC_MIXED || c->precision == RAU_PREC_F16IMG;
+}
+static inline bool prec_x_f16(const rau_ctx* c) { return c->precision == RAU_PREC_MIXED || c->precision == RAU_PREC_F16IMG; }
+static inline bool prec_img_f16(const rau_ctx* c) { return c->precision == RAU_PREC_F16IMG; }
 
 #define RAU_LAUNCH_CHECK(ctx)                                                             \
   do {                                                                                    \

@@ -202,7 +202,7 @@ int rau_set_seed(rau_ctx* ctx, uint64_t seed) {
 
 int rau_set_precision(rau_ctx* ctx, int precision) {
   RAU_REQUIRE(ctx, "ctx == NULL");
-  RAU_REQUIRE(precision >= RAU_PREC_F32 && precision <= RAU_PREC_MIXED, "unknown precision %d", precision);
+  RAU_REQUIRE(precision >= RAU_PREC_F32 && precision <= RAU_PREC_F16IMG, "unknown precision %d", precision);
   ctx->precision = precision;
   return RAU_OK;
 }

@@ -86,19 +86,21 @@ cudaEvent_t rau_side_event(rau_ctx* ctx) {
 int hop_forward_pre(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const float*>& P, const float* X, int train,
                     const HopSaved& sv) {
   const int M = cfg->M, S = cfg->S, C = cfg->C, R = B * S;
-  const int f16 = prec_img_f16(ctx) ? 1 : 0;   // image-side tensors are single fp16 planes (RAU_PREC_MIXED)
-  const bool x3 = prec_x3(ctx) && !f16;        // ... or bf16 (hi, lo) pairs
+  const int fx = prec_x_f16(ctx) ? 1 : 0;      // Xd and the Wi shadow are single fp16 planes (mixed modes)
+  const int f16 = prec_img_f16(ctx) ? 1 : 0;   // ... and so are I and the Wa shadow (RAU_PREC_F16IMG)
+  const bool x3x = prec_x3(ctx) && !fx;        // Xd / Wi carry a bf16 lo plane
+  const bool x3 = prec_x3(ctx) && !f16;        // I / Wa carry a bf16 lo plane
   const uint32_t* xb = (train && cfg->p_x > 0) ? sv.xbits : nullptr;
   const bf16 *Wi_h, *Wi_l;
-  RAU_TRY(rows_pack(ctx, P.Wi, (int64_t)M * C, x3, true, nullptr, &Wi_h, &Wi_l, f16));
+  RAU_TRY(rows_pack(ctx, P.Wi, (int64_t)M * C, x3x, true, nullptr, &Wi_h, &Wi_l, fx));
   if (!sv.x_done)
-    RAU_TRY(k_xprep_rows(ctx, X, B, C, S, xb, drop_scale(cfg->p_x), sv.Xd_hi, x3 ? sv.Xd_lo : nullptr,
-                         (train && cfg->p_x > 0 && sv.x_philox) ? 1 : 0, cfg->p_x, sv.x_stream, f16));
+    RAU_TRY(k_xprep_rows(ctx, X, B, C, S, xb, drop_scale(cfg->p_x), sv.Xd_hi, x3x ? sv.Xd_lo : nullptr,
+                         (train && cfg->p_x > 0 && sv.x_philox) ? 1 : 0, cfg->p_x, sv.x_stream, fx));
   RowsGemm g;
   g.M = R; g.N = M; g.K = C;
-  g.A.hi = sv.Xd_hi; g.A.lo = x3 ? sv.Xd_lo : nullptr; g.A.ld = C;
+  g.A.hi = sv.Xd_hi; g.A.lo = x3x ? sv.Xd_lo : nullptr; g.A.ld = C;
   g.B.hi = Wi_h; g.B.lo = Wi_l; g.B.ld = C;
-  g.epi = ROWS_EPI_TANH; g.bias = P.bi; g.f16 = f16;
+  g.epi = ROWS_EPI_TANH; g.bias = P.bi; g.f16 = fx; g.of16 = f16;
   g.out_hi = sv.I_hi; g.out_lo = x3 ? sv.I_lo : nullptr; g.ldo = M;
   RAU_TRY(rows_gemm(ctx, g));
   // attbycontent (F:244-252), the half the state does not reach: Z = I Wa^T.  hop_forward() adds the query term per image
@@ -456,18 +458,21 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   // attselect + softmax + score conv + tanh of attbycontent, one CTA per image
   const bool rows = rows_path(ctx, cfg);
   const int R = B * S;
-  // RAU_PREC_MIXED: the image-side tensors (I, dZ, dY, Xd, the Wi / Wa shadows) are single fp16 planes.  dZ and dY are carried
-  // times a power of two (~2^12 * B: d loss / d score is O(1 / B), so the scaled values sit in the middle of fp16's range
-  // whatever the batch) and every product that reads one of them scales its fp32 result back.
-  const int f16i = (rows && prec_img_f16(ctx)) ? 1 : 0;
-  const bool x3i = x3 && !f16i;
+  // Mixed modes: Xd, the Wi shadow and dY are single fp16 planes (RAU_PREC_F16IMG: I, dZ and the Wa shadow too).  The fp16
+  // gradient operands are carried times a power of two (~2^12 * B: d loss / d score is O(1 / B), so the scaled values sit in
+  // the middle of fp16's range whatever the batch) and every product that reads one scales its fp32 result back.
+  const int fxi = (rows && prec_x_f16(ctx)) ? 1 : 0;     // Xd / Wi / dY fp16
+  const int f16i = (rows && prec_img_f16(ctx)) ? 1 : 0;  // I / Wa / dZ fp16
+  const bool x3i = x3 && !f16i;                          // I / Wa / dZ carry a bf16 lo plane
+  const bool x3x = x3 && !fxi;                           // Xd / Wi / dY carry a bf16 lo plane
   float gs = 1.0f;
-  if (f16i) { gs = 4096.0f; for (int b2 = 1; b2 < B && gs < 1.0e9f; b2 <<= 1) gs *= 2.0f; }
-  if (f16i) { dZ_lo = nullptr; dY_lo = nullptr; }
+  if (fxi) { gs = 4096.0f; for (int b2 = 1; b2 < B && gs < 1.0e9f; b2 <<= 1) gs *= 2.0f; }
+  if (f16i) dZ_lo = nullptr;
+  if (fxi) dY_lo = nullptr;
   if (rows)
     RAU_TRY(k_attn_rows_bwd(ctx, B, M, A, S, sv.E, sv.I_hi, x3i ? sv.I_lo : nullptr, P.ws, sv.p, dp, dj, ds, dZ_hi, dZ_lo, dqa, gwsp,
                             ds_pk.hi, x3 ? ds_pk.lo : nullptr, (int)ds_pk.ld, sv.qatt, x3 ? 0 : 1,
-                            deferred ? deferred->acc_zeroed : 0, f16i, gs));
+                            deferred ? deferred->acc_zeroed : 0, f16i, f16i ? gs : 1.0f));
   else
     RAU_TRY(k_attn_bwd<float>(ctx, B, M, A, S, Sp, sv.E, sv.I, P.ws, sv.p, dp, dj, ds, nullptr, 0, dZ, dqa, nullptr, gwsp,
                               dZ_hi, dZ_lo));
@@ -505,7 +510,7 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
       g.A.hi = dZ_hi; g.A.lo = dZ_lo; g.A.ld = A;
       g.B.hi = Wa_h; g.B.lo = Wa_l; g.B.mn = 1; g.B.ld = M;
       g.epi = ROWS_EPI_DY; g.rowvec = dj; g.rowscale = sv.p; g.S = S;
-      g.f16 = f16i; g.gscale = gs; g.alpha = 1.0f / gs;
+      g.f16 = f16i; g.af16 = f16i; g.of16 = fxi; g.gscale = gs; g.accscale = f16i ? 1.0f : gs; g.alpha = 1.0f / gs;
       g.aux_hi = sv.I_hi; g.aux_lo = x3i ? sv.I_lo : nullptr; g.ldaux = M; g.colsum = G.bi;
       g.out_hi = dY_hi; g.out_lo = dY_lo; g.ldo = M;
       if ((side_rc = rows_gemm(ctx, g)) != RAU_OK) break;
@@ -515,15 +520,15 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
       g.M = A; g.N = M; g.K = R;
       g.A.hi = dZ_hi; g.A.lo = dZ_lo; g.A.mn = 1; g.A.ld = A;
       g.B.hi = sv.I_hi; g.B.lo = x3i ? sv.I_lo : nullptr; g.B.mn = 1; g.B.ld = M;
-      g.f16 = f16i; g.alpha = 1.0f / gs;
+      g.f16 = f16i; g.alpha = f16i ? 1.0f / gs : 1.0f;
       if ((side_rc = rows_wgrad(ctx, g, G.Wa, M)) != RAU_OK) break;
     }
     if (side) {   // gWi += dY^T drop(X)^T (issued further down in the synchronous mode)
       RowsGemm g;
       g.M = M; g.N = C; g.K = R;
       g.A.hi = dY_hi; g.A.lo = dY_lo; g.A.mn = 1; g.A.ld = M;
-      g.B.hi = sv.Xd_hi; g.B.lo = x3i ? sv.Xd_lo : nullptr; g.B.mn = 1; g.B.ld = C;
-      g.f16 = f16i; g.alpha = 1.0f / gs;
+      g.B.hi = sv.Xd_hi; g.B.lo = x3x ? sv.Xd_lo : nullptr; g.B.mn = 1; g.B.ld = C;
+      g.f16 = fxi; g.alpha = 1.0f / gs;
       if ((side_rc = rows_wgrad(ctx, g, G.Wi, C)) != RAU_OK) break;
     }
     } while (0);
@@ -572,19 +577,19 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
       RowsGemm g;
       g.M = M; g.N = C; g.K = R;
       g.A.hi = dY_hi; g.A.lo = dY_lo; g.A.mn = 1; g.A.ld = M;
-      g.B.hi = sv.Xd_hi; g.B.lo = x3i ? sv.Xd_lo : nullptr; g.B.mn = 1; g.B.ld = C;
-      g.f16 = f16i; g.alpha = 1.0f / gs;
+      g.B.hi = sv.Xd_hi; g.B.lo = x3x ? sv.Xd_lo : nullptr; g.B.mn = 1; g.B.ld = C;
+      g.f16 = fxi; g.alpha = 1.0f / gs;
       RAU_TRY(rows_wgrad(ctx, g, G.Wi, C));
     }
     if (dX) {   // dX = (dY Wi)^T * mask / (1-p): only on request, the training step discards it (F:598)
       const bf16 *Wi_h, *Wi_l;
-      RAU_TRY(rows_pack(ctx, P.Wi, (int64_t)M * C, x3i, true, nullptr, &Wi_h, &Wi_l, f16i));
+      RAU_TRY(rows_pack(ctx, P.Wi, (int64_t)M * C, x3x, true, nullptr, &Wi_h, &Wi_l, fxi));
       ARENA(dXr, float, "hopb.dXr", (size_t)R * C);
       RowsGemm g;
       g.M = R; g.N = C; g.K = M;
       g.A.hi = dY_hi; g.A.lo = dY_lo; g.A.ld = M;
       g.B.hi = Wi_h; g.B.lo = Wi_l; g.B.mn = 1; g.B.ld = C;
-      g.epi = ROWS_EPI_PLAIN; g.out_f = dXr; g.ldo = C; g.f16 = f16i; g.alpha = 1.0f / gs;
+      g.epi = ROWS_EPI_PLAIN; g.out_f = dXr; g.ldo = C; g.f16 = fxi; g.alpha = 1.0f / gs;
       RAU_TRY(rows_gemm(ctx, g));
       RAU_TRY(k_unprep_rows(ctx, dXr, B, C, S, xb, drop_scale(cfg->p_x), dX));
     }
@@ -978,7 +983,7 @@ int rau_feature_pack(rau_ctx* ctx, const float* X, int B, int C, int S, int nHop
   RAU_REQUIRE(ctx->precision != RAU_PREC_F32, "rau_feature_pack: tcgen05 modes only");
   RAU_REQUIRE(p > 0.0f && p < 1.0f, "rau_feature_pack: 0 < p < 1");
   RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
-  const int f16 = prec_img_f16(ctx) ? 1 : 0;
+  const int f16 = prec_x_f16(ctx) ? 1 : 0;
   const bool x3 = prec_x3(ctx) && !f16;
   const size_t n = (size_t)B * S * C;
   bf16* buf = nullptr;
@@ -993,6 +998,116 @@ int rau_feature_pack(rau_ctx* ctx, const float* X, int B, int C, int S, int nHop
                            f16));
   }
   return k_unpack_hilo(ctx, hi, x3 ? lo : nullptr, (int64_t)n * nHop, out, f16);
+}
+
+// Attention-kernel sweep (BASELINE.json configs[4]): every kernel of one answering unit that touches the
+// 196 x C feature block or the [B*196, 512] activation derived from it, launched ALONE on synthetic operands at batch B in
+// the context's precision mode and timed with CUDA events around each launch (flush_l2 != 0: a 256 MB memset evicts L2
+// before every launch, so small batches do not time an L2-resident working set).  us_out[k], k as rau_sweep_kernel.
+int rau_sweep_attention(rau_ctx* ctx, const rau_config* cfg, int B, const float* mult_params, const float* X, int iters,
+                        int flush_l2, float* us_out) {
+  RAU_REQUIRE(ctx && us_out && iters > 0 && B > 0, "rau_sweep_attention: bad arguments");
+  RAU_TRY(check_cfg(cfg));
+  RAU_REQUIRE(rows_path(ctx, cfg), "rau_sweep_attention: the configuration does not run on the rows engine");
+  RAU_TRY(rau_check_dev(mult_params, "mult_params")); RAU_TRY(rau_check_dev(X, "X"));
+  RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
+  ctx->epoch++;
+  const int M = cfg->M, A = cfg->A, S = cfg->S, C = cfg->C, R = B * S;
+  const int fx = prec_x_f16(ctx) ? 1 : 0, fi = prec_img_f16(ctx) ? 1 : 0;
+  const bool x3 = prec_x3(ctx), x3x = x3 && !fx, x3i = x3 && !fi;
+  MultT<const float*> P = mult_views<const float*, const float>(cfg, mult_params);
+  const size_t svb = hop_saved_layout(cfg, B, nullptr, nullptr);
+  ARENA(svbase, char, "sweep.saved", svb);
+  HopSaved sv;
+  hop_saved_layout(cfg, B, svbase, &sv);
+  ARENA(gW, float, "sweep.gW", (size_t)M * (C > M ? C : M));
+  ARENA(small, float, "sweep.small", (size_t)B * (3 * M + 2 * A + 4 * S) + 1024);
+  ARENA(dZ, bf16, "sweep.dZ", (size_t)2 * R * A);
+  ARENA(dY, bf16, "sweep.dY", (size_t)2 * R * M);
+  ARENA(flush, char, "sweep.flush", (size_t)256 << 20);
+  float* qatt = small; float* mem = qatt + (size_t)B * A; float* slog = mem + (size_t)B * S; float* a = slog + (size_t)B * S;
+  float* dj = a + (size_t)B * M; float* dpin = dj + (size_t)B * M; float* ds = dpin + (size_t)B * S; float* dqa = ds + (size_t)B * S;
+  float* gwsp = dqa + (size_t)B * A; float* gbi = gwsp + (size_t)B * A;
+  RAU_TRY(k_fill(ctx, small, (int64_t)B * (3 * M + 2 * A + 4 * S) + 1024, 1.0e-3f));
+  float gs = 1.0f;
+  if (fx) { gs = 4096.0f; for (int b2 = 1; b2 < B && gs < 1.0e9f; b2 <<= 1) gs *= 2.0f; }
+  const bf16 *Wi_h, *Wi_l, *Wa_h, *Wa_l;
+  RAU_TRY(rows_pack(ctx, P.Wi, (int64_t)M * C, x3x, true, nullptr, &Wi_h, &Wi_l, fx));
+  RAU_TRY(rows_pack(ctx, P.Wa, (int64_t)A * M, x3i, true, nullptr, &Wa_h, &Wa_l, fi));
+  bf16 *dZ_hi = dZ, *dZ_lo = x3i ? dZ + (size_t)R * A : nullptr, *dY_hi = dY, *dY_lo = x3x ? dY + (size_t)R * M : nullptr;
+  auto timed = [&](int slot, const std::function<int()>& launch) -> int {
+    float total = 0.0f;
+    for (int it = 0; it < iters + 1; ++it) {   // (the first launch is a warm-up)
+      if (flush_l2) RAU_CHECK_CUDA(cudaMemsetAsync(flush, it & 1, (size_t)256 << 20, ctx->stream));
+      RAU_CHECK_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+      RAU_TRY(launch());
+      RAU_CHECK_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+      RAU_CHECK_CUDA(cudaEventSynchronize(ctx->ev1));
+      float ms = 0.0f;
+      RAU_CHECK_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+      if (it > 0) total += ms;
+    }
+    us_out[slot] = total * 1000.0f / iters;
+    return RAU_OK;
+  };
+  // forward
+  RAU_TRY(timed(RAU_SWEEP_PACK, [&]() {
+    return k_xprep_rows(ctx, X, B, C, S, nullptr, drop_scale(cfg->p_x), sv.Xd_hi, x3x ? sv.Xd_lo : nullptr, 1, cfg->p_x, 0x77, fx);
+  }));
+  RAU_TRY(timed(RAU_SWEEP_IEMBED, [&]() {
+    RowsGemm g;
+    g.M = R; g.N = M; g.K = C;
+    g.A.hi = sv.Xd_hi; g.A.lo = x3x ? sv.Xd_lo : nullptr; g.A.ld = C;
+    g.B.hi = Wi_h; g.B.lo = Wi_l; g.B.ld = C;
+    g.epi = ROWS_EPI_TANH; g.bias = P.bi; g.f16 = fx; g.of16 = fi;
+    g.out_hi = sv.I_hi; g.out_lo = x3i ? sv.I_lo : nullptr; g.ldo = M;
+    return rows_gemm(ctx, g);
+  }));
+  RAU_TRY(timed(RAU_SWEEP_Z, [&]() {
+    RowsGemm z;
+    z.M = R; z.N = A; z.K = M;
+    z.A.hi = sv.I_hi; z.A.lo = x3i ? sv.I_lo : nullptr; z.A.ld = M;
+    z.B.hi = Wa_h; z.B.lo = Wa_l; z.B.ld = M;
+    z.epi = ROWS_EPI_PLAIN; z.f16 = fi; z.out_f = sv.E; z.ldo = A;
+    return rows_gemm(ctx, z);
+  }));
+  RAU_TRY(timed(RAU_SWEEP_SCORE, [&]() { return k_attn_rows_score(ctx, B, A, S, sv.E, qatt, P.ws, x3 ? 0 : 1, slog); }));
+  RAU_TRY(timed(RAU_SWEEP_SOFTMAX_SUM, [&]() {
+    return k_attn_rows_fwd(ctx, B, M, S, slog, mem, sv.I_hi, x3i ? sv.I_lo : nullptr, sv.p, a, nullptr, nullptr, 0, fi);
+  }));
+  // backward
+  RAU_TRY(timed(RAU_SWEEP_BWD_DP_DZ, [&]() {
+    return k_attn_rows_bwd(ctx, B, M, A, S, sv.E, sv.I_hi, x3i ? sv.I_lo : nullptr, P.ws, sv.p, dpin, dj, ds, dZ_hi, dZ_lo, dqa, gwsp,
+                           nullptr, nullptr, 0, qatt, x3 ? 0 : 1, 0, fi, fi ? gs : 1.0f);
+  }));
+  RAU_TRY(timed(RAU_SWEEP_DY, [&]() {
+    RowsGemm g;
+    g.M = R; g.N = M; g.K = A;
+    g.A.hi = dZ_hi; g.A.lo = dZ_lo; g.A.ld = A;
+    g.B.hi = Wa_h; g.B.lo = Wa_l; g.B.mn = 1; g.B.ld = M;
+    g.epi = ROWS_EPI_DY; g.rowvec = dj; g.rowscale = sv.p; g.S = S;
+    g.f16 = fi; g.af16 = fi; g.of16 = fx; g.gscale = gs; g.accscale = fi ? 1.0f : gs; g.alpha = 1.0f / gs;
+    g.aux_hi = sv.I_hi; g.aux_lo = x3i ? sv.I_lo : nullptr; g.ldaux = M; g.colsum = gbi;
+    g.out_hi = dY_hi; g.out_lo = dY_lo; g.ldo = M;
+    return rows_gemm(ctx, g);
+  }));
+  RAU_TRY(timed(RAU_SWEEP_GWA, [&]() {
+    RowsGemm g;
+    g.M = A; g.N = M; g.K = R;
+    g.A.hi = dZ_hi; g.A.lo = dZ_lo; g.A.mn = 1; g.A.ld = A;
+    g.B.hi = sv.I_hi; g.B.lo = x3i ? sv.I_lo : nullptr; g.B.mn = 1; g.B.ld = M;
+    g.f16 = fi; g.alpha = fi ? 1.0f / gs : 1.0f;
+    return rows_wgrad(ctx, g, gW, M);
+  }));
+  RAU_TRY(timed(RAU_SWEEP_GWI, [&]() {
+    RowsGemm g;
+    g.M = M; g.N = C; g.K = R;
+    g.A.hi = dY_hi; g.A.lo = dY_lo; g.A.mn = 1; g.A.ld = M;
+    g.B.hi = sv.Xd_hi; g.B.lo = x3x ? sv.Xd_lo : nullptr; g.B.mn = 1; g.B.ld = C;
+    g.f16 = fx; g.alpha = 1.0f / gs;
+    return rows_wgrad(ctx, g, gW, C);
+  }));
+  return RAU_OK;
 }
 
 int rau_rows_trace(rau_ctx* ctx, uint64_t* out, int n) {

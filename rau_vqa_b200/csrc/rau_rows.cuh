@@ -34,8 +34,11 @@ struct RowsGemm {
   float* colsum = nullptr;          // [N]
   int S = 0;                        // rows per image
   float alpha = 1.0f;
-  int f16 = 0;                      // operands / EPI_TANH, EPI_DY outputs / EPI_DY's saved activation are fp16 (single plane)
-  float gscale = 1.0f;              // EPI_DY: power-of-two scale carried by A (= dZ) and by the output dY; colsum gets alpha
+  int f16 = 0;                      // the operands are single fp16 planes (lo must be NULL)
+  int of16 = 0;                     // EPI_TANH / EPI_DY: the output is one fp16 plane
+  int af16 = 0;                     // EPI_DY: the saved activation (aux_hi) is one fp16 plane
+  float gscale = 1.0f;              // EPI_DY: power-of-two scale of the output dY; colsum gets alpha (= 1 / gscale)
+  float accscale = 1.0f;            // EPI_DY: gscale / (scale the A operand dZ already carries)
 };
 
 bool rows_path_enabled();

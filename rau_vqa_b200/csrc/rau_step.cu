@@ -620,8 +620,8 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     for (int hp = 0; hp < nHop; ++hp) all_philox = all_philox && sv[hp].x_philox;
     if (all_philox) {
       rc = k_xprep_rows_hops(ctx, bt->feats, B, cfg->C, S, nHop, drop_scale(cfg->p_x), sv[0].Xd_hi,
-                             (prec_x3(ctx) && !prec_img_f16(ctx)) ? sv[0].Xd_lo : nullptr, (int64_t)(sv_bytes / sizeof(bf16)),
-                             cfg->p_x, sv[0].x_stream, prec_img_f16(ctx) ? 1 : 0);
+                             (prec_x3(ctx) && !prec_x_f16(ctx)) ? sv[0].Xd_lo : nullptr, (int64_t)(sv_bytes / sizeof(bf16)),
+                             cfg->p_x, sv[0].x_stream, prec_x_f16(ctx) ? 1 : 0);
       for (int hp = 0; hp < nHop; ++hp) sv[hp].x_done = 1;
     }
     for (int hp = 0; hp < nHop && rc == RAU_OK; ++hp) {
@@ -1147,7 +1147,8 @@ int rau_time_iembed(rau_ctx* ctx, const rau_config* cfg, int B, const float* mul
   const int Sp = rau_sp(cfg->S), M = cfg->M, C = cfg->C, S = cfg->S;
   MultT<const float*> P = mult_views<const float*, const float>(cfg, mult_params);
   const bool tc = ctx->precision != RAU_PREC_F32 && S % 4 == 0;
-  const int f16 = (prec_img_f16(ctx) && hop_rows_path(ctx, cfg)) ? 1 : 0;
+  const int f16 = (prec_x_f16(ctx) && hop_rows_path(ctx, cfg)) ? 1 : 0;   // Xd / Wi fp16
+  const int of16 = (prec_img_f16(ctx) && hop_rows_path(ctx, cfg)) ? 1 : 0;  // I fp16
   const bool x3 = prec_x3(ctx) && !f16;
   if (tc && rows_path_enabled() && C % 64 == 0 && M % 64 == 0) {
     // the training launch of the rows engine: packed dropped-out features in, tanh epilogue, packed (hi, lo) I out
@@ -1163,8 +1164,8 @@ int rau_time_iembed(rau_ctx* ctx, const rau_config* cfg, int B, const float* mul
     rg.M = R; rg.N = M; rg.K = C;
     rg.A.hi = Xh; rg.A.lo = x3 ? Xl : nullptr; rg.A.ld = C;
     rg.B.hi = Wi_h; rg.B.lo = Wi_l; rg.B.ld = C;
-    rg.epi = ROWS_EPI_TANH; rg.bias = P.bi; rg.f16 = f16;
-    rg.out_hi = Ih; rg.out_lo = x3 ? Il : nullptr; rg.ldo = M;
+    rg.epi = ROWS_EPI_TANH; rg.bias = P.bi; rg.f16 = f16; rg.of16 = of16;
+    rg.out_hi = Ih; rg.out_lo = (prec_x3(ctx) && !of16) ? Il : nullptr; rg.ldo = M;
     RAU_TRY(rows_gemm(ctx, rg));   // warm-up
     RAU_CHECK_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     for (int i = 0; i < iters; ++i) RAU_TRY(rows_gemm(ctx, rg));

@@ -1,0 +1,117 @@
+"""The batch feed (rau_feed_*, rau_feat_cache_*) against the direct call with device-resident
+tensors: what arrives through the pinned double-buffered upload -- float32 staging, float16 staging, or a gather from the
+HBM-resident fp16 feature cache -- trains exactly like the same batch handed over as device pointers (F:452-456, LD:1009)."""
+import numpy as np
+import pytest
+
+from helpers import dev
+from oracle import rau_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(B=12, seed=3101):
+    import rau_vqa_b200 as R
+    cfg = O.RauConfig(V=2000, C=128, nHop=2, N=300)
+    lc = R.RauConfig(V=cfg.V, C=cfg.C, nHop=cfg.nHop, N=cfg.N)
+    params = O.init_params(cfg, seed=seed)
+    batches = [O.synth_batch(cfg, B, seed=seed + 1 + i) for i in range(5)]
+    return R, cfg, lc, params, batches
+
+
+def _run(R, lc, params, batches, mode):
+    """five adam steps; mode: 'direct' | FEED_F32 | FEED_F16 | 'direct_f16' (direct call on fp16-rounded features)"""
+    import torch
+    from rau_vqa_b200 import core, feed as F
+    ctx = R.Context(0, seed=9)
+    P = [dev(params[g]) for g in O.GROUPS]
+    G = [torch.zeros_like(p) for p in P]
+    ST = [[torch.zeros_like(p), torch.zeros_like(p)] for p in P]
+    B = batches[0][0].shape[0]
+    out = R.StepBuffers(lc, B, P[0].device, want_scores=False)
+    losses = []
+    if mode in ("direct", "direct_f16"):
+        for it, (X, x, x_len, y) in enumerate(batches, start=1):
+            Xs = X.astype(np.float32)
+            if mode == "direct_f16":
+                Xs = Xs.astype(np.float16).astype(np.float32)
+            core.train_step(ctx, lc, P, G, ST, dev(Xs), dev(x), dev(x_len), dev(y), out, step_t=it, opt_t=it,
+                            max_len=int(x_len.max()))
+            ctx.sync()
+            losses.append(out.loss.cpu().numpy().copy())
+    else:
+        fd = F.Feed(ctx, lc, B, fmt=mode, depth=2)
+        assert fd.bytes_per_batch == B * lc.C * lc.S * (2 if mode == F.FEED_F16 else 4) + 4 * (lc.T * B + 2 * B)
+        fd.fill(0, *batches[0])          # (float64 features, as the loader returns them: LD:1009)
+        fd.submit(0)
+        for it in range(1, len(batches) + 1):
+            slot = (it - 1) % 2
+            if it < len(batches):        # the next batch crosses PCIe under this step
+                fd.fill(1 - slot, *batches[it])
+                fd.submit(1 - slot)
+            b = fd.acquire(slot)
+            assert b.max_len == int(batches[it - 1][2].max()) and b.B == B
+            F.train_step_batch(ctx, lc, P, G, ST, b, out, step_t=it, opt_t=it)
+            fd.release(slot)
+            ctx.sync()
+            losses.append(out.loss.cpu().numpy().copy())
+        fd.close()
+    res = ([p.cpu().numpy() for p in P], np.stack(losses))
+    ctx.close()
+    return res
+
+
+def test_f32_feed_equals_direct_call():
+    R, cfg, lc, params, batches = _setup()
+    from rau_vqa_b200 import feed as F
+    a, b = _run(R, lc, params, batches, "direct"), _run(R, lc, params, batches, F.FEED_F32)
+    np.testing.assert_array_equal(a[1], b[1])
+    for x, y in zip(a[0], b[0]):
+        np.testing.assert_array_equal(x, y)
+
+
+def test_f16_feed_equals_direct_call_on_fp16_rounded_features():
+    """the fp16 staging delivers exactly fp16(x); at toy size (fp32 feature path) that equals the direct call on rounded x"""
+    R, cfg, lc, params, batches = _setup()
+    from rau_vqa_b200 import feed as F
+    a, b = _run(R, lc, params, batches, "direct_f16"), _run(R, lc, params, batches, F.FEED_F16)
+    np.testing.assert_array_equal(a[1], b[1])
+    for x, y in zip(a[0], b[0]):
+        np.testing.assert_array_equal(x, y)
+
+
+def test_f16_feed_changes_no_bit_at_reference_dims_in_the_default_mode():
+    """At the reference's dimensions the features enter the tensor pipe as fp16 (RAU_PREC_MIXED) and the dropout scale
+    1 / (1 - 0.5) = 2 commutes with the rounding: uploading fp16 features gives bit-identical losses and parameters."""
+    import rau_vqa_b200 as R
+    from rau_vqa_b200 import feed as F
+    cfg = O.RauConfig(V=3000, C=512, nHop=2, N=2000)
+    lc = R.RauConfig(V=cfg.V, C=cfg.C, nHop=cfg.nHop, N=cfg.N)
+    params = O.init_params(cfg, seed=3201)
+    batches = [O.synth_batch(cfg, 6, seed=3202 + i) for i in range(3)]
+    a, b = _run(R, lc, params, batches, "direct"), _run(R, lc, params, batches, F.FEED_F16)
+    np.testing.assert_array_equal(a[1], b[1])
+    for x, y in zip(a[0], b[0]):
+        np.testing.assert_array_equal(x, y)
+
+
+def test_feature_cache_gather():
+    import torch
+    import rau_vqa_b200 as R
+    from rau_vqa_b200 import feed as F
+    ctx = R.Context(0)
+    n, C, S = 150, 64, 196
+    rng = np.random.default_rng(1)
+    feats = np.maximum(rng.standard_normal((n, C, S), dtype=np.float32), 0)
+    cache = F.FeatCache(ctx, n, C, S)
+    cache.put(0, feats[:100])
+    cache.put(100, feats[100:])
+    idx = rng.integers(1, n + 1, 37)
+    got = cache.gather(dev(idx))
+    ctx.sync()
+    np.testing.assert_array_equal(got.cpu().numpy(), feats[idx - 1].astype(np.float16).astype(np.float32))
+    from rau_vqa_b200._ffi import RauError
+    with pytest.raises(RauError):
+        cache.put(140, feats[:20])       # past the end
+    cache.close()
+    ctx.close()
