@@ -270,8 +270,8 @@ int rau_hop_bwd(rau_ctx* ctx, const rau_config* cfg, int B, const float* mult_pa
  * bytes per step (F:452-456).  rau_feed keeps `depth` batches in flight: the loader fills a slot's pinned staging, submit
  * enqueues its upload on a copy stream under the running step, acquire makes the context's stream wait for it and describes
  * the device copy as a rau_batch, release lets a later submit overwrite it.  RAU_FEED_F16 stages the features as fp16 --
- * half the PCIe bytes; in the default precision mode they enter the tensor pipe as fp16 anyway, so the step's result does
- * not change by a bit (tests/test_gpu_feed.py). */
+ * half the PCIe bytes; in the default precision mode they enter the tensor pipe as fp16 anyway, so the operand the
+ * tensor pipe sees does not change by a bit (tests/test_gpu_feed.py). */
 typedef struct rau_feed rau_feed;
 typedef enum { RAU_FEED_F32 = 0, RAU_FEED_F16 = 1 } rau_feed_format;
 int rau_feed_create(rau_ctx* ctx, const rau_config* cfg, int B, int format, int depth /* 2..8 */, rau_feed** out);

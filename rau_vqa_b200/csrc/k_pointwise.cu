@@ -82,6 +82,17 @@ __global__ void xmask16_bytes_kernel(uint8_t* __restrict__ out, int B, int C, in
   }
 }
 
+// Evicts L2 by READING a buffer larger than it (a memset would leave L2 full of dirty lines whose write-back the next
+// kernel pays for); the sum is stored only under a condition that never holds, so the loads are not optimised away.
+__global__ void l2_evict_kernel(const float4* __restrict__ buf, int64_t n4, float* __restrict__ sink) {
+  float acc = 0.0f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldcg(buf + i);
+    acc += v.x + v.y + v.z + v.w;
+  }
+  if (acc == 1.2345e38f) *sink = acc;
+}
+
 // ---------------------------------------------------------------- embedding
 __global__ void embed_fwd_kernel(const float* __restrict__ ids, int n, int D, int V, const float* __restrict__ E,
                                  const uint32_t* __restrict__ bits, float scale, float* __restrict__ out_f,
@@ -154,7 +165,8 @@ __global__ void lstm_bwd_kernel(int B, int H, int order, const float* __restrict
                                 const float* __restrict__ dq_h, int lddq,
                                 const float* __restrict__ c_prev, int ldcp, const float* __restrict__ saved,
                                 float* __restrict__ dG, bf16* __restrict__ dG_b, float* __restrict__ dc_prev, int lddcp,
-                                bf16* __restrict__ dG_lo, float* __restrict__ zero_out) {
+                                bf16* __restrict__ dG_lo, float* __restrict__ zero_out, const uint32_t* __restrict__ extra_bits,
+                                int64_t extra_bit0, float extra_scale) {
   RAU_PDL_ENTRY();
   // zero_out ([B, H] contiguous): the buffer the split-K dgrad that follows reduces into (saves a memset node per step)
   if (zero_out)
@@ -171,7 +183,8 @@ __global__ void lstm_bwd_kernel(int B, int H, int order, const float* __restrict
       dc_o = dq_c[(int64_t)b * lddq + j];
       dh_o = dq_h[(int64_t)b * lddq + j];
     }
-    if (dh_extra) dh_o += dh_extra[(int64_t)b * ldhe + j];
+    // (extra_bits: dh_extra is the gradient w.r.t. a dropped-out copy of h -- D:39 -- whose keep mask is applied here)
+    if (dh_extra) dh_o += dh_extra[(int64_t)b * ldhe + j] * keep_scale(extra_bits, extra_bit0 + idx, extra_scale);
     const float i_ = saved[idx], f_ = saved[plane + idx], o_ = saved[2 * plane + idx];
     const float g_ = saved[3 * plane + idx], tc = saved[4 * plane + idx];
     const float cp = c_prev ? c_prev[(int64_t)b * ldcp + j] : 0.0f;
@@ -479,6 +492,11 @@ int k_xmask16_bytes(rau_ctx* ctx, uint8_t* out, int B, int C, int S, int nHop, f
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
+int k_l2_evict(rau_ctx* ctx, const void* buf, size_t bytes, float* sink) {
+  l2_evict_kernel<<<148 * 8, 256, 0, ctx->stream>>>((const float4*)buf, (int64_t)(bytes / 16), sink);
+  RAU_LAUNCH_CHECK(ctx);
+  return RAU_OK;
+}
 int k_mask_pack(rau_ctx* ctx, uint32_t* bits, const uint8_t* bytes, int64_t n) {
   const int64_t nw = (n + 31) / 32;
   RAU_LAUNCH_PDL(ctx->stream, (mask_pack_kernel), grid_for(nw), TPB, 0, bits, bytes, nw, n);
@@ -506,9 +524,10 @@ int k_lstm_fwd(rau_ctx* ctx, int B, int H, int order, const float* G, int ldg, c
 int k_lstm_bwd(rau_ctx* ctx, int B, int H, int order, const float* dc_out, int lddc, const float* dh_out, int lddh,
                const float* dh_extra, int ldhe, const float* lengths, int t, const float* dq_c, const float* dq_h, int lddq,
                const float* c_prev, int ldcp, const float* saved, float* dG, bf16* dG_b, float* dc_prev, int lddcp, bf16* dG_lo,
-               float* zero_out) {
+               float* zero_out, const uint32_t* extra_bits, int64_t extra_bit0, float extra_scale) {
   RAU_LAUNCH_PDL(ctx->stream, (lstm_bwd_kernel), grid_for((int64_t)B * H), TPB, 0, B, H, order, dc_out, lddc, dh_out, lddh, dh_extra, ldhe,
-      lengths, t, dq_c, dq_h, lddq, c_prev, ldcp, saved, dG, dG_b, dc_prev, lddcp, dG_lo, zero_out);
+      lengths, t, dq_c, dq_h, lddq, c_prev, ldcp, saved, dG, dG_b, dc_prev, lddcp, dG_lo, zero_out, extra_bits, extra_bit0,
+      extra_scale);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }

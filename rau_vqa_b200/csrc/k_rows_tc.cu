@@ -72,6 +72,7 @@ struct RtParams {
   int S;
   float alpha;
   int fast_tanh;
+  int ew;                          // epilogue warps of the launch (8, or 16 for the 1-pass i_embed product)
   int f16;                         // the operands are fp16, not bf16 (single plane)
   int of16;                        // EPI_TANH / EPI_DY: the output is ONE fp16 plane (not bf16 hi [, lo])
   int af16;                        // EPI_DY: the saved activation (aux) is one fp16 plane
@@ -302,8 +303,11 @@ __device__ __forceinline__ float warp_transpose_sum32(float* x, int lane) {
   return x[0];
 }
 
-template <int EPI, int X3, int NSTEPS, int CG2>
-__global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_constant__ RtParams p) {
+// EW = epilogue warps (8 or 16; warps 2 .. EW+1, the B producer is warp EW+2).  16 warps put four instead of two warps on
+// every scheduler: the 1-pass fp16 i_embed product is epilogue-latency bound (tmem load -> tanh -> split -> staging -> TMA
+// store per 32-column chunk; ncu: issue slots 35 % busy with 2 warps per scheduler), not tensor bound.
+template <int EPI, int X3, int NSTEPS, int CG2, int EW>
+__global__ void __launch_bounds__(32 * (EW + 3), 1) rows_gemm_kernel(const __grid_constant__ RtParams p) {
   asm volatile("griddepcontrol.launch_dependents;");   // PDL: the next kernel may begin its prologue
   // CG2: launched as clusters of two CTAs (one TPC).  The pair owns 256 rows x BN columns per item: each CTA stages its own
   // 128 rows of A and its half of the B tile, the leader (cluster rank 0) issues cta_group::2 MMAs with M = 256, each CTA
@@ -325,7 +329,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], CG2 ? 16 : 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], CG2 ? 2 * EW : EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
@@ -355,12 +359,12 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
   const uint32_t a_bytes = (uint32_t)RT_BM * p.BK * 2, b_bytes = (uint32_t)(CG2 ? p.BN / 2 : p.BN) * p.BK * 2;
   constexpr int nt = X3 ? 2 : 1;
 
-  if (warp == 0 || warp == 10) {
+  if (warp == 0 || warp == EW + 2) {
     // ===================== TMA producers: warp 0 feeds operand A, warp 10 operand B (one thread issues roughly one
     // cp.async.bulk.tensor per 250 cycles, so the two operands are issued from different warps, and the hi and lo
     // tiles of the bf16x3 split travel as the two planes of ONE 3-D box)
     {
-      const bool isB = warp == 10;
+      const bool isB = warp == EW + 2;
       const int mn = isB ? p.b_mn : p.a_mn;
       const uint32_t my_bytes = nt * (isB ? b_bytes : a_bytes);
       const int nchunk = (isB ? (CG2 ? p.BN / 2 : p.BN) : RT_BM) / 64;
@@ -488,7 +492,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
   } else {
     // ===================== epilogue warps 2..9: TMEM lanes 32*(warp%4) .. +31; the two warps of a lane quarter split
     // the 256 accumulator columns in halves and walk them in 32-column chunks
+    // (a warp reads the TMEM lanes 32 * (warp % 4) ..; the EW / 4 warps of a lane quarter split the accumulator's columns)
     const int q = warp & 3, half = (warp - 2) >> 2;
+    constexpr int NPART = EW / 4;
     uint8_t* stg_p = staging + (size_t)(warp - 2) * p.stg_warp;
     const uint32_t stg0 = smem_u32(stg_p), stg1 = stg0 + 2048u;
     uint32_t li = 0;
@@ -501,7 +507,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
     float rs_next = 0.0f;   // the next item's row scale (p[r]) for this thread's row
     bool dy_ready = false;
     const int arow = lane >> 2, aseg = lane & 3;
-    const int ncols_w = p.BN / 2;   // accumulator columns of this warp
+    const int ncols_w = p.BN / 2;   // accumulator columns of this warp (EPI_DY runs with EW = 8)
     auto aux_fetch = [&](int rowbase_x, int ncx) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -542,7 +548,8 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_gemm_kernel(const __grid_c
       float rs = 0.0f;
       if (EPI == EPI_ATT || EPI == EPI_DY) rv = p.rowvec + (long long)(rr / p.S) * p.N;
       if (EPI == EPI_DY) rs = (dy_ready ? rs_next : p.rowscale[rr]) * p.gscale;   // (dY is written times gscale)
-      const int c_lo = half * (p.BN / 64), c_hi = c_lo + p.BN / 64;
+      const int cper = (p.BN / 32 + NPART - 1) / NPART;   // 32-column chunks per warp
+      const int c_lo = half * cper, c_hi = min(p.BN / 32, c_lo + cper);
       bool released = false;
       uint32_t rv_s = 0;
       if (EPI == EPI_DY && n0 + c_lo * 32 >= p.N) dy_ready = false;   // (no columns for this warp: nothing consumes the prefetch)
@@ -932,11 +939,11 @@ int encode_operand(CUtensorMap* m, const bf16* hi, const bf16* lo, int* swap, in
 
 bool g_attr_done[8] = {false, false, false, false, false, false, false, false};
 
-template <int EPI, int X3, int NSTEPS, int CG2>
+template <int EPI, int X3, int NSTEPS, int CG2, int EW = 8>
 int launch_rows_v(rau_ctx* ctx, const RtParams& p, int grid, int smem_bytes) {
   static bool attr_done = false;
   if (!attr_done) {
-    RAU_CHECK_CUDA(cudaFuncSetAttribute(rows_gemm_kernel<EPI, X3, NSTEPS, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RAU_CHECK_CUDA(cudaFuncSetAttribute(rows_gemm_kernel<EPI, X3, NSTEPS, CG2, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         RT_SMEM_BUDGET + 1024));
     attr_done = true;
   }
@@ -944,7 +951,7 @@ int launch_rows_v(rau_ctx* ctx, const RtParams& p, int grid, int smem_bytes) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(RT_THREADS);
+    cfg.blockDim = dim3(32 * (EW + 3));
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute at[2];
@@ -954,9 +961,9 @@ int launch_rows_v(rau_ctx* ctx, const RtParams& p, int grid, int smem_bytes) {
     at[1].val.programmaticStreamSerializationAllowed = rau_pdl_enabled() ? 1 : 0;
     cfg.attrs = at;
     cfg.numAttrs = 2;
-    (void)cudaLaunchKernelEx(&cfg, rows_gemm_kernel<EPI, X3, NSTEPS, CG2>, p);
+    (void)cudaLaunchKernelEx(&cfg, rows_gemm_kernel<EPI, X3, NSTEPS, CG2, EW>, p);
   } else {
-    RAU_LAUNCH_PDL(ctx->stream, (rows_gemm_kernel<EPI, X3, NSTEPS, CG2>), grid, RT_THREADS, smem_bytes, p);
+    RAU_LAUNCH_PDL(ctx->stream, (rows_gemm_kernel<EPI, X3, NSTEPS, CG2, EW>), grid, 32 * (EW + 3), smem_bytes, p);
   }
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
@@ -966,6 +973,7 @@ int launch_rows_v(rau_ctx* ctx, const RtParams& p, int grid, int smem_bytes) {
 template <int EPI>
 int launch_rows(rau_ctx* ctx, const RtParams& p, int grid, int smem_bytes) {
   constexpr bool pairable = EPI == EPI_PLAIN || EPI == EPI_TANH || EPI == EPI_ATT || EPI == EPI_DY || EPI == EPI_RED;
+  if (EPI == EPI_TANH && p.ew == 16 && p.cg2 && !p.x3) return launch_rows_v<EPI_TANH, 0, 4, 1, 16>(ctx, p, grid, smem_bytes);
   if (pairable && p.cg2) {
     if (p.x3) return launch_rows_v<EPI, 1, 2, pairable ? 1 : 0>(ctx, p, grid, smem_bytes);
     return launch_rows_v<EPI, 0, 4, pairable ? 1 : 0>(ctx, p, grid, smem_bytes);
@@ -1901,7 +1909,13 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   p.stg_warp = (g.epi == EPI_LINEAR && g.out_hi) ? 8192 : RT_STG_WARP;
   p.stage_bytes = (p.x3 ? 2 : 1) * (RT_BM + (p.cg2 ? BN / 2 : BN)) * p.BK * 2;
   if (g.epi == EPI_DY) p.stg_warp = 9216;   // + a 32 x 64 B (hi, lo) scratch per warp (the saved activation is fetched coalesced) + 1 KB row vector
-  p.stages = (RT_SMEM_BUDGET - 8 * p.stg_warp) / p.stage_bytes;
+  {   // the 1-pass (fp16 / bf16) CTA-pair i_embed product is epilogue bound: 16 epilogue warps (RAU_TANH_EW=8: A/B switch)
+    static int ew_tanh = -1;
+    if (ew_tanh < 0) { const char* e = getenv("RAU_TANH_EW"); ew_tanh = (e && atoi(e) == 8) ? 8 : 16; }
+    // (K <= 1024: at K = 2048 the product is tensor bound and the stage the extra staging buffers cost matters more)
+    p.ew = (g.epi == EPI_TANH && p.cg2 && !p.x3 && g.K <= 1024) ? ew_tanh : 8;
+  }
+  p.stages = (RT_SMEM_BUDGET - p.ew * p.stg_warp) / p.stage_bytes;
   if (p.stages > RT_MAXSTAGES) p.stages = RT_MAXSTAGES;
   const int tiles = (p.cg2 ? (p.tiles_m + 1) / 2 : p.tiles_m) * p.tiles_n;   // work items before any K split
   p.ksplit = 1;
@@ -1999,7 +2013,7 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
       p.dbg = (unsigned long long*)buf;
     }
   }
-  const int smem_bytes = p.stages * p.stage_bytes + 8 * p.stg_warp + 1024;
+  const int smem_bytes = p.stages * p.stage_bytes + p.ew * p.stg_warp + 1024;
   switch (g.epi) {
     case EPI_PLAIN: return launch_rows<EPI_PLAIN>(ctx, p, grid, smem_bytes);
     case EPI_RED: return launch_rows<EPI_RED>(ctx, p, grid, smem_bytes);

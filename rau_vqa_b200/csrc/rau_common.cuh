@@ -98,6 +98,7 @@ struct rau_ctx {
   // on at most side_ctas SMs next to the chain of small dependent kernels.  RAU_OVERLAP=0 disables it.
   cudaStream_t side = nullptr;
   cudaStream_t aux = nullptr;                      // short state-independent preparation (fills, masks) next to the encoder
+  cudaStream_t aux2 = nullptr;                     // the encoder backward's second wavefront lane (layer 1 behind layer 2)
   std::vector<cudaEvent_t> side_ev;
   int side_ev_next = 0;
   int side_ctas = 0;

@@ -153,7 +153,8 @@ int rau_ctx_create(rau_ctx** out, int device, void* cuda_stream) {
       cudaMallocHost(&ctx->h_ss, sizeof(StepState) * 64) != cudaSuccess ||
       cudaStreamCreateWithPriority(&ctx->gstream, cudaStreamNonBlocking, -1) != cudaSuccess ||
       cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, 0) != cudaSuccess ||
-      cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, -1) != cudaSuccess) {
+      cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, -1) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&ctx->aux2, cudaStreamNonBlocking, -1) != cudaSuccess) {
     rau_set_error("context allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete ctx;
     return RAU_ECUDA;
@@ -181,6 +182,7 @@ int rau_ctx_destroy(rau_ctx* ctx) {
   if (ctx->gstream) cudaStreamDestroy(ctx->gstream);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->aux) cudaStreamDestroy(ctx->aux);
+  if (ctx->aux2) cudaStreamDestroy(ctx->aux2);
   for (cudaEvent_t e : ctx->side_ev) cudaEventDestroy(e);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);

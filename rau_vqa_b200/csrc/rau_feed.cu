@@ -5,7 +5,7 @@
 //                   format is float32 (as the reference uploads) or float16 (half the PCIe bytes: with eight ranks pulling
 //                   from one host the float32 feed is upload-bound).  In the default precision mode the image features enter
 //                   the tensor pipe as fp16 anyway (x -> fp16(x / (1-p)), and the power-of-two dropout scale commutes with
-//                   the rounding), so the fp16 feed changes no bit of the step's result.
+//                   the rounding), so the fp16 feed changes no bit of what the products read.
 //   rau_feat_cache  the features of a whole split resident in HBM as fp16 (train2014 at C = 512: 82 783 x 196 KB = 16 GB of the
 //                   180 GB), a batch is a gather by image index: no per-step feature upload at all.
 #include "rau_kernels.cuh"

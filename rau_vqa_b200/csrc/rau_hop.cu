@@ -1003,7 +1003,7 @@ int rau_feature_pack(rau_ctx* ctx, const float* X, int B, int C, int S, int nHop
 // Attention-kernel sweep (BASELINE.json configs[4]): every kernel of one answering unit that touches the
 // 196 x C feature block or the [B*196, 512] activation derived from it, launched ALONE on synthetic operands at batch B in
 // the context's precision mode and timed with CUDA events around each launch (flush_l2 != 0: a 256 MB memset evicts L2
-// before every launch, so small batches do not time an L2-resident working set).  us_out[k], k as rau_sweep_kernel.
+// before every launch -- by READING 256 MB, which leaves clean lines -- so small batches do not time an L2-resident working set).  us_out[k], k as rau_sweep_kernel.
 int rau_sweep_attention(rau_ctx* ctx, const rau_config* cfg, int B, const float* mult_params, const float* X, int iters,
                         int flush_l2, float* us_out) {
   RAU_REQUIRE(ctx && us_out && iters > 0 && B > 0, "rau_sweep_attention: bad arguments");
@@ -1025,6 +1025,8 @@ int rau_sweep_attention(rau_ctx* ctx, const rau_config* cfg, int B, const float*
   ARENA(dZ, bf16, "sweep.dZ", (size_t)2 * R * A);
   ARENA(dY, bf16, "sweep.dY", (size_t)2 * R * M);
   ARENA(flush, char, "sweep.flush", (size_t)256 << 20);
+  static bool flush_init = false;
+  if (!flush_init) { RAU_CHECK_CUDA(cudaMemsetAsync(flush, 0, (size_t)256 << 20, ctx->stream)); flush_init = true; }
   float* qatt = small; float* mem = qatt + (size_t)B * A; float* slog = mem + (size_t)B * S; float* a = slog + (size_t)B * S;
   float* dj = a + (size_t)B * M; float* dpin = dj + (size_t)B * M; float* ds = dpin + (size_t)B * S; float* dqa = ds + (size_t)B * S;
   float* gwsp = dqa + (size_t)B * A; float* gbi = gwsp + (size_t)B * A;
@@ -1038,7 +1040,7 @@ int rau_sweep_attention(rau_ctx* ctx, const rau_config* cfg, int B, const float*
   auto timed = [&](int slot, const std::function<int()>& launch) -> int {
     float total = 0.0f;
     for (int it = 0; it < iters + 1; ++it) {   // (the first launch is a warm-up)
-      if (flush_l2) RAU_CHECK_CUDA(cudaMemsetAsync(flush, it & 1, (size_t)256 << 20, ctx->stream));
+      if (flush_l2) RAU_TRY(k_l2_evict(ctx, flush, (size_t)256 << 20, gbi + 512));
       RAU_CHECK_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
       RAU_TRY(launch());
       RAU_CHECK_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));

@@ -32,7 +32,8 @@ int k_lstm_bwd(rau_ctx* ctx, int B, int H, int order,
                const float* lengths, int t, const float* dq_c, const float* dq_h, int lddq,
                const float* c_prev, int ldcp, const float* saved,
                float* dG, bf16* dG_b, float* dc_prev, int lddcp, bf16* dG_lo = nullptr,   // dG_b / dG_lo: packed (hi, lo) copy
-               float* zero_out = nullptr);   // optional [B, H] buffer cleared on the way (target of the next split-K dgrad)
+               float* zero_out = nullptr,    // optional [B, H] buffer cleared on the way (target of the next split-K dgrad)
+               const uint32_t* extra_bits = nullptr, int64_t extra_bit0 = 0, float extra_scale = 1.0f);   // keep mask of dh_extra
 
 // ---- generic elementwise
 // y = x * keep(bits) * scale over a [rows, cols] matrix (mask indexed by row*cols+col); padded output pitch
@@ -55,6 +56,7 @@ int k_tanh_bwd(rau_ctx* ctx, const float* dy, const float* y, int64_t n, float* 
 int k_add(rau_ctx* ctx, const float* a, const float* b, int64_t n, float* y);              // y = a + b
 int k_axpy(rau_ctx* ctx, float alpha, const float* x, int64_t n, float* y);                // y += alpha x
 int k_fill(rau_ctx* ctx, float* x, int64_t n, float v);
+int k_l2_evict(rau_ctx* ctx, const void* buf, size_t bytes, float* sink);   // read `bytes` (> L2) so that L2 holds clean lines only
 int k_to_bf16(rau_ctx* ctx, const float* x, int64_t rows, int cols, int ldx, bf16* y, int ldy, int cols_pad);
 int k_rowdot_sigmoid(rau_ctx* ctx, const float* x, int B, int K, const float* w, const float* b, float* y);
 // wd/bd gradient and dm contribution of the do_pred head (zero in training, kept for the module API)

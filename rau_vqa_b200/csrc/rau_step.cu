@@ -209,6 +209,162 @@ static int encoder_backward(rau_ctx* ctx, const rau_config* cfg, const rau_batch
     float* dHb[2] = {dH2, dH2 + hb};                          // the dgrad of step t reduces into, while reading the other
     bf16* hpk_all = nullptr;
     RAU_TRY(ctx->arena.get("enc.hpk", sizeof(bf16) * (size_t)4 * (cfg->T + 1) * hb, (void**)&hpk_all));
+    // Wavefront (default; RAU_ENC_BWD_WAVE=0 keeps the layer-after-layer form below): step t of layer 1 needs step t of
+    // layer 2 (through the dropped-out h1 that feeds it, D:38-39) and its own step t+1, nothing else -- so the two layers'
+    // backward recurrences run on two streams one step apart: 2 T serial steps become T + 1.  Per step, layer 2 forms
+    // [dH2_{t-1} | du2_t] = dG2_t [Wh2 | Wi2] in ONE split-K product (the input gradient is not hoisted over time any more)
+    // and layer 1 applies the dropout mask of u2 inside its cell backward.
+    const char* e_wv = getenv("RAU_ENC_BWD_WAVE");
+    const char* e_sb = getenv("RAU_LSTM_SEQ_BWD");
+    const bool wave = !(e_wv && atoi(e_wv) == 0) && !(e_sb && atoi(e_sb) != 0) && ctx->aux2 != nullptr && Tm >= 2;
+    if (wave) {
+      bf16* dG1_hi = dGp;
+      bf16* dG1_lo = x3 ? dG1_hi + (size_t)cfg->T * gb : nullptr;
+      bf16* dG2_hi = dGp + (size_t)2 * cfg->T * gb;
+      bf16* dG2_lo = x3 ? dG2_hi + (size_t)cfg->T * gb : nullptr;
+      const bf16 *Wh1_h, *Wh1_l, *Wi1_h, *Wi1_l;
+      int64_t ldwh1, ldwi1;
+      RAU_TRY(rows_pack2d(ctx, Pr + L[0].Wh, Hq, G4, Hq, x3, true, nullptr, &Wh1_h, &Wh1_l, &ldwh1));
+      RAU_TRY(rows_pack2d(ctx, Pr + L[0].Wi, E, G4, E, x3, true, nullptr, &Wi1_h, &Wi1_l, &ldwi1));
+      // [Wh2 | Wi2] side by side: [4H rows, 2 Hq columns] (hi, lo)
+      ARENA(Wcat, bf16, "encb.Wcat", (size_t)2 * G4 * 2 * Hq);
+      bf16* Wcat_hi = Wcat;
+      bf16* Wcat_lo = x3 ? Wcat + (size_t)G4 * 2 * Hq : nullptr;
+      if (ctx->tc_epoch["encb.Wcat"] != ctx->epoch) {   // (packed once per public call, like every weight shadow)
+        RAU_TRY(rows_pack_into(ctx, Pr + L[1].Wh, Hq, G4, Hq, Wcat_hi, Wcat_lo, 2 * Hq));
+        RAU_TRY(rows_pack_into(ctx, Pr + L[1].Wi, Hq, G4, Hq, Wcat_hi + Hq, Wcat_lo ? Wcat_lo + Hq : nullptr, 2 * Hq));
+        ctx->tc_epoch["encb.Wcat"] = ctx->epoch;
+      }
+      // out2[t] = [dH2 into step t | du2 of step t+1 ...]: slab s (1-based step that PRODUCED it) holds dG2_s [Wh2 | Wi2]:
+      // columns 0..Hq-1 = gradient into h2_{s-1} (read by layer 2's step s-1), Hq.. = gradient into u2_s (layer 1's step s)
+      ARENA(out2, float, "encb.out2", (size_t)(cfg->T + 1) * B * 2 * Hq);
+      ARENA(dC1, float, "encb.dC1", (size_t)B * Hq);
+      ARENA(dH1, float, "encb.dH1", (size_t)2 * hb);
+      RAU_CHECK_CUDA(cudaMemsetAsync(out2, 0, sizeof(float) * (size_t)(Tm + 1) * B * 2 * Hq, ctx->stream));
+      cudaStream_t laneA = ctx->stream, laneB = ctx->aux2;
+      cudaEvent_t fork = rau_side_event(ctx);
+      RAU_REQUIRE(fork != nullptr, "cudaEventCreate failed");
+      RAU_CHECK_CUDA(cudaEventRecord(fork, laneA));
+      RAU_CHECK_CUDA(cudaStreamWaitEvent(laneB, fork, 0));
+      struct Back2 { rau_ctx* c; cudaStream_t s; ~Back2() { c->stream = s; } } back2{ctx, laneA};
+      float* dH1b[2] = {dH1, dH1 + hb};
+      // Weight gradients gWi += dG^T x, gWh += dG^T h_{t-1}, gb += sum dG of both layers over the rows of steps s0+1 .. s0+ns
+      // (packed operands of the forward pass), on the side stream when allowed.  They go out in two halves: the late steps'
+      // rows as soon as both lanes are past them, the early steps' rows at the end -- only the second half is exposed.
+      const bool wg_side = side_ok && ctx->side != nullptr;
+      const int th = Tm >= 8 ? Tm / 2 + 1 : 1;   // the loop hands over steps th .. Tm when it has finished step th
+      auto wgrads = [&](int s0, int ns) -> int {
+        if (ns <= 0) return RAU_OK;
+        cudaStream_t cur = ctx->stream;
+        if (wg_side) {   // after everything both lanes have enqueued so far
+          cudaEvent_t ea = rau_side_event(ctx), eb = rau_side_event(ctx);
+          RAU_REQUIRE(ea != nullptr && eb != nullptr, "cudaEventCreate failed");
+          RAU_CHECK_CUDA(cudaEventRecord(ea, laneA));
+          RAU_CHECK_CUDA(cudaEventRecord(eb, laneB));
+          RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->side, ea, 0));
+          RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->side, eb, 0));
+          ctx->stream = ctx->side;
+          ctx->rows_cta_cap = ctx->side_ctas;
+        } else {         // one stream: lane B's rows must be complete before the chain reads them
+          cudaEvent_t eb = rau_side_event(ctx);
+          RAU_REQUIRE(eb != nullptr, "cudaEventCreate failed");
+          RAU_CHECK_CUDA(cudaEventRecord(eb, laneB));
+          RAU_CHECK_CUDA(cudaStreamWaitEvent(laneA, eb, 0));
+          ctx->stream = laneA;
+        }
+        struct Back { rau_ctx* c; cudaStream_t s; ~Back() { c->stream = s; c->rows_cta_cap = 0; } } back{ctx, cur};
+        const int64_t r0 = (int64_t)s0 * B;
+        const int Rn = ns * B;
+        for (int layer = 1; layer >= 0; --layer) {
+          const int in = layer == 0 ? E : Hq;
+          const float* dG = (layer == 1 ? dG2 : dG1) + r0 * G4;
+          const bf16* dGh = (layer == 1 ? dG2_hi : dG1_hi) + r0 * G4;
+          const bf16* dGl = x3 ? (layer == 1 ? dG2_lo : dG1_lo) + r0 * G4 : nullptr;
+          const bf16* x_h = nullptr;
+          const int64_t ldx = (in + 7) / 8 * 8;
+          const size_t xhalf = ((size_t)R * ldx * sizeof(bf16) + 1023) / 1024 * 1024;
+          RAU_TRY(ctx->arena.get(layer == 0 ? "rp.enc.x0" : "rp.enc.x1", xhalf * (x3 ? 2 : 1), (void**)&x_h));
+          const bf16* x_l = x3 ? (const bf16*)((const char*)x_h + xhalf) : nullptr;
+          const bf16* hp_h = hpk_all + (size_t)(2 * layer) * (cfg->T + 1) * hb;
+          const bf16* hp_l = x3 ? hp_h + (size_t)(cfg->T + 1) * hb : nullptr;
+          for (int which = 0; which < 2; ++which) {
+            RowsGemm g;
+            g.M = G4; g.N = which == 0 ? in : Hq; g.K = Rn;
+            g.A.hi = dGh; g.A.lo = dGl; g.A.mn = 1; g.A.ld = G4;
+            g.B.hi = (which == 0 ? x_h + r0 * ldx : hp_h + r0 * Hq);
+            g.B.lo = x3 ? (which == 0 ? x_l + r0 * ldx : hp_l + r0 * Hq) : nullptr;
+            g.B.mn = 1; g.B.ld = which == 0 ? ldx : Hq;
+            g.epi = ROWS_EPI_RED; g.out_f = gR + (which == 0 ? L[layer].Wi : L[layer].Wh); g.ldo = which == 0 ? in : Hq;
+            RAU_TRY(rows_gemm(ctx, g));
+          }
+          RAU_TRY(k_colsum(ctx, dG, Rn, G4, G4, gR + L[layer].bi, 1, gR + L[layer].bh));
+        }
+        if (wg_side && ctx->phases == 2) rau_phase_mark(ctx, "enc weight gradients (half) done");
+        return RAU_OK;
+      };
+      for (int t = Tm; t >= 1; --t) {
+        const bool last = t == Tm;
+        // ---- lane A: layer 2, step t
+        ctx->stream = laneA;
+        {
+          const float* Sp_ = en->S_all + (size_t)(t - 1) * B * Q + 2 * Hq;
+          const float* dh_in = last ? nullptr : out2 + (size_t)(t + 1) * B * 2 * Hq;   // (slab t+1, columns 0..Hq-1)
+          RAU_TRY(k_lstm_bwd(ctx, B, Hq, RAU_GATES_IFOG, last ? nullptr : dC, Hq, dh_in, 2 * Hq, nullptr, 0, bt->lengths, t,
+                             dq + 2 * Hq, dq + 3 * Hq, Q, Sp_, Q, en->sav2 + (size_t)(t - 1) * 5 * hb, dG2 + (size_t)(t - 1) * gb,
+                             dG2_hi + (size_t)(t - 1) * gb, dC, Hq, dG2_lo ? dG2_lo + (size_t)(t - 1) * gb : nullptr, nullptr));
+          RowsGemm g;
+          g.M = B; g.N = 2 * Hq; g.K = G4;
+          g.A.hi = dG2_hi + (size_t)(t - 1) * gb; g.A.lo = dG2_lo ? dG2_lo + (size_t)(t - 1) * gb : nullptr; g.A.ld = G4;
+          g.B.hi = Wcat_hi; g.B.lo = Wcat_lo; g.B.mn = 1; g.B.ld = 2 * Hq;
+          g.epi = ROWS_EPI_RED; g.out_f = out2 + (size_t)t * B * 2 * Hq; g.ldo = 2 * Hq;
+          RAU_TRY(rows_gemm(ctx, g));
+        }
+        cudaEvent_t ev = rau_side_event(ctx);
+        RAU_REQUIRE(ev != nullptr, "cudaEventCreate failed");
+        RAU_CHECK_CUDA(cudaEventRecord(ev, laneA));
+        // ---- lane B: layer 1, step t (one step behind layer 2)
+        RAU_CHECK_CUDA(cudaStreamWaitEvent(laneB, ev, 0));
+        ctx->stream = laneB;
+        {
+          const float* Sp_ = en->S_all + (size_t)(t - 1) * B * Q;
+          float* dH = dH1b[t & 1];
+          float* dH_next = dH1b[(t + 1) & 1];
+          RAU_TRY(k_lstm_bwd(ctx, B, Hq, RAU_GATES_IFOG, last ? nullptr : dC1, Hq, last ? nullptr : dH, Hq,
+                             out2 + (size_t)t * B * 2 * Hq + Hq, 2 * Hq, bt->lengths, t, dq, dq + Hq, Q, Sp_, Q,
+                             en->sav1 + (size_t)(t - 1) * 5 * hb, dG1 + (size_t)(t - 1) * gb, dG1_hi + (size_t)(t - 1) * gb, dC1, Hq,
+                             dG1_lo ? dG1_lo + (size_t)(t - 1) * gb : nullptr, t > 1 ? dH_next : nullptr,
+                             dr ? en->rbits : nullptr, (int64_t)(t - 1) * B * Hq, drop_scale(cfg->p_rnn)));
+          if (t > 1) {
+            RowsGemm g;
+            g.M = B; g.N = Hq; g.K = G4;
+            g.A.hi = dG1_hi + (size_t)(t - 1) * gb; g.A.lo = dG1_lo ? dG1_lo + (size_t)(t - 1) * gb : nullptr; g.A.ld = G4;
+            g.B.hi = Wh1_h; g.B.lo = Wh1_l; g.B.mn = 1; g.B.ld = ldwh1;
+            g.epi = ROWS_EPI_RED; g.out_f = dH_next; g.ldo = Hq;
+            RAU_TRY(rows_gemm(ctx, g));
+          }
+        }
+        if (t == th && th > 1) RAU_TRY(wgrads(th - 1, Tm - th + 1));   // steps th .. Tm are final on both lanes
+      }
+      // the early steps' rows of the weight gradients (the late ones went out in the middle of the loop)
+      RAU_TRY(wgrads(0, th > 1 ? th - 1 : Tm));
+      // lane B rejoins the chain: gradient into the word embedding for every step at once, de = dG1 Wi1
+      cudaEvent_t join = rau_side_event(ctx);
+      RAU_REQUIRE(join != nullptr, "cudaEventCreate failed");
+      RAU_CHECK_CUDA(cudaEventRecord(join, laneB));
+      ctx->stream = laneA;
+      RAU_CHECK_CUDA(cudaStreamWaitEvent(laneA, join, 0));
+      {
+        RowsGemm g;
+        g.M = R; g.N = E; g.K = G4;
+        g.A.hi = dG1_hi; g.A.lo = dG1_lo; g.A.ld = G4;
+        g.B.hi = Wi1_h; g.B.lo = Wi1_l; g.B.mn = 1; g.B.ld = ldwi1;
+        g.epi = ROWS_EPI_LINEAR; g.out_f = de_all; g.ldo = E;
+        RAU_TRY(rows_gemm(ctx, g));
+      }
+      RAU_TRY(k_embed_bwd(ctx, bt->tokens, Tm * B, E, cfg->V, en->e_all, de ? en->ebits : nullptr, drop_scale(cfg->p_embed),
+                          de_all, E, gE));
+      return RAU_OK;
+    }
     for (int layer = 1; layer >= 0; --layer) {
       float* dG = layer == 1 ? dG2 : dG1;
       bf16* dG_hi = dGp + (size_t)(2 * layer) * cfg->T * gb;

@@ -234,6 +234,7 @@ def test_train_graph_survives_a_larger_validation_batch():
         ctx.sync()
         res.append(([p.cpu().numpy() for p in P], out.loss.cpu().numpy().copy()))
         ctx.close()
-    np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-5)
+    # (two contexts, atomics in different orders: 1e-5-level noise; a step that ran on freed buffers differs by O(1))
+    np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-4)
     for a, b in zip(res[0][0], res[1][0]):
-        assert rel_err(a, b) <= 1e-5
+        assert rel_err(a, b) <= 1e-4

@@ -12,7 +12,7 @@ nHop, C, B = dict(ours_full=(8, 512, 256), ours_resnet=(8, 2048, 256), ours_ms=(
 cfg = R.RauConfig(V=16384, C=C, nHop=nHop, N=2000)
 ctx = R.Context(0, seed=123)
 if len(sys.argv) > 2:
-    ctx.set_precision(dict(f32=core.PREC_F32, bf16=core.PREC_BF16, bf16x3=core.PREC_BF16X3)[sys.argv[2]])
+    ctx.set_precision(dict(f32=0, bf16=1, bf16x3=2, mixed=3, f16img=4)[sys.argv[2]])
 dev = torch.device("cuda", 0)
 gen = torch.Generator(device=dev).manual_seed(123)
 P = [(torch.rand(cfg.group_size(g), device=dev, generator=gen) * 0.16 - 0.08) for g in range(3)]
