@@ -545,20 +545,10 @@ bool g_attr_set = false;
 // products below this many multiply-adds stay on the CUDA cores (RAU_TC_MIN_WORK overrides; tests set it to 0 so
 // that toy shapes exercise every TMA / descriptor edge case)
 bool tc_cluster_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("RAU_TC_CLUSTER");
-    v = e ? (atoi(e) != 0) : 0;   // multicast measured slower on the per-image products (profiles/): opt-in
-  }
-  return v != 0;
+  return false;   // (multicast measured slower on the per-image products: the switch is gone, the code path stays for reference)
 }
 long long tc_min_work() {
-  static long long v = -1;
-  if (v < 0) {
-    const char* e = getenv("RAU_TC_MIN_WORK");
-    v = e ? atoll(e) : (1ll << 18);
-  }
-  return v;
+  return rau_process_tuning().tc_min_work;
 }
 }  // namespace
 
@@ -667,7 +657,7 @@ int tc_gemm_try(rau_ctx* ctx, const SimtGemm& g) {
   p.addend = g.addend; p.addend2 = g.addend2; p.bD = g.bD;
   p.sdi = swap ? g.sdn : g.sdm; p.sdj = swap ? g.sdm : g.sdn;
   p.act = g.act; p.accumulate = g.accumulate; p.atomic = ksplit > 1 ? 1 : 0;
-  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("RAU_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
+  p.dbg = 0;
   if (clear_c) {
     if (g.scn == 1)
       RAU_CHECK_CUDA(cudaMemset2DAsync(g.C, (size_t)g.scm * 4, 0, (size_t)g.N * 4, (size_t)g.M, ctx->stream));

@@ -1613,243 +1613,11 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
 }
 
 
-// ================================================================== persistent LSTM recurrence, backward (question encoder)
-// One launch walks the backward recurrence of one encoder LSTM layer, t = T..1 (F:600-615, the transpose of D:33-65):
-//   dG_t = cell backward (dh_t, dc_t, saved gates)         pointwise, the cell-state gradient stays in registers
-//   dh_{t-1} = dG_t Wh                                     [B, 4H] x [4H, H]
-// A CTA owns 128 batch rows x 16 hidden units: it forms the 64 gate-gradient columns of its units (4 gates x 16), writes
-// them out (fp32 + packed, for the weight gradients and the input gradient) AND into shared memory as the A operand of a
-// K = 64 slice of the dgrad, whose B operand -- the 64 rows of Wh that belong to its units, all H columns, hi and lo planes
-// (128 KB at H = 512) -- stays resident.  The [128, H] partial product leaves TMEM through TMA reduce-adds into the
-// step's fp32 accumulator dHacc[t-1] (a fresh zeroed [B, H] slab per step), and the row tile's CTAs meet on a
-// release/acquire counter before they read their 16 columns of it.
-struct LbParams {
-  CUtensorMap mapW, mapR;          // Wh [4H, H] MN-major boxes (64 n x 16 k [x 2 planes]) ; dHacc [(T+1)*B, H] fp32 32 x 32 boxes
-  int B, H, T, tiles_n, b_swap;
-  const float* lengths; const float* dq_c; const float* dq_h; int lddq;   // t == len: the unit's state gradient enters here
-  const float* dh_extra;                        // [T][B][H] gradient from the layer above (or NULL)
-  const float* c_prev; long long s_t; int lds;  // c_{t-1}: state rows of step 0, step stride, row pitch
-  const float* saved; long long ls_t, plane;    // saved gates of step 1: 5 planes (i, f, o, g, tanh c') of [B, H]
-  float* dG; bf16* dG_hi; bf16* dG_lo; long long g_t;   // [T][B][4H] (chunks i, f, o, g), step stride
-  const float* dHacc;                           // [(T+1)][B][H]: slab t = d loss / d h_t through the recurrence (zeroed by the caller)
-  unsigned int* counter; unsigned int* err; unsigned int* err_host;
-};
-
-template <int X3>
-__global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_bwd_kernel(const __grid_constant__ LbParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t w_bar, a_bar, d_bar;
-  __shared__ uint32_t tmem_base_s;
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  constexpr uint32_t NT = X3 ? 2u : 1u;
-  constexpr uint32_t blk = NT * 2048u;            // one TMA box: 64 n x 16 k [x 2 planes]
-  constexpr uint32_t chunk_pitch = 4u * blk;      // the 4 gate blocks (k = 64) of one 64-column chunk
-  const uint32_t nchunks = (uint32_t)p.H / 64u;
-  const uint32_t w_bytes = nchunks * chunk_pitch;
-  constexpr uint32_t a_plane = 128u * 128u;       // A: 128 rows x 64 k bf16, K-major SWIZZLE_128B
-  uint8_t* wsm = smem;
-  uint8_t* asm_ = smem + w_bytes;
-  uint8_t* staging = asm_ + NT * a_plane;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tn = blockIdx.x % p.tiles_n, tm = blockIdx.x / p.tiles_n;
-  const int m0 = tm * 128, u_base = tn * 16;
-
-  if (threadIdx.x == 0) {
-    mbar_init(&w_bar, 1); mbar_init(&a_bar, 8); mbar_init(&d_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.mapW) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.mapR) : "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = tmem_base_s;
-
-  if (warp == 0) {
-    // ===================== the resident B operand: rows chunk*H + u_base .. +16 of Wh for the 4 gate chunks
-    if (elect_one()) {
-      mbar_expect_tx(&w_bar, w_bytes);
-      for (uint32_t c = 0; c < nchunks; ++c)
-        for (int g = 0; g < 4; ++g) {
-          uint8_t* dst = wsm + c * chunk_pitch + (uint32_t)g * blk;
-          if (X3) tma_load_3d(dst, &p.mapW, &w_bar, (int)c * 64, g * p.H + u_base, 0);
-          else tma_load_2d(dst, &p.mapW, &w_bar, (int)c * 64, g * p.H + u_base);
-        }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ===================== MMA issuer: per step 4 k-steps (one per gate chunk) x N halves of 256 columns
-    const uint32_t nhalf = (uint32_t)p.H / 256u;
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint64_t a_hi_off = 0, a_lo_off = (uint64_t)(a_plane >> 4);
-    const uint64_t b_hi_off = p.b_swap ? (2048u >> 4) : 0, b_lo_off = p.b_swap ? 0 : (2048u >> 4);
-    mbar_wait(&w_bar, 0u);
-    for (int t = p.T; t >= 2; --t) {
-      mbar_wait(&a_bar, (uint32_t)(p.T - t) & 1u);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (elect_one()) {
-        const uint64_t da0 = make_desc(smem_u32(asm_), 16u, 1024u, 2u);
-        for (uint32_t h = 0; h < nhalf; ++h) {
-          const uint64_t db0 = make_desc(smem_u32(wsm + h * 4u * chunk_pitch), chunk_pitch, 1024u, 2u);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint64_t oa = (uint64_t)g * (32u >> 4), ob = (uint64_t)g * (blk >> 4);
-            umma_f16(tmem_base + h * 256u, da0 + a_hi_off + oa, db0 + b_hi_off + ob, idesc, g > 0 ? 1u : 0u);
-            if (X3) {
-              umma_f16(tmem_base + h * 256u, da0 + a_hi_off + oa, db0 + b_lo_off + ob, idesc, 1u);
-              umma_f16(tmem_base + h * 256u, da0 + a_lo_off + oa, db0 + b_hi_off + ob, idesc, 1u);
-            }
-          }
-        }
-        umma_commit(&d_bar);
-      }
-      __syncwarp();
-    }
-  } else {
-    // ===================== warps 2..9: thread = batch row (lane quarter q), 8 of the CTA's 16 hidden units (half)
-    const int q = warp & 3, half = (warp - 2) >> 2;
-    const int r = m0 + q * 32 + lane;
-    const bool r_ok = r < p.B;
-    const int rr = r_ok ? r : p.B - 1;
-    const int rowbase = m0 + q * 32;
-    const int u0 = u_base + 8 * half;
-    uint8_t* stg_p = staging + (size_t)(warp - 2) * 4096;
-    const uint32_t stg0 = smem_u32(stg_p);
-    const int len = (int)p.lengths[rr];
-    float dcc[8];   // d loss / d c_t carried down the recurrence
-#pragma unroll
-    for (int u = 0; u < 8; ++u) dcc[u] = 0.0f;
-    auto ld8 = [](const float* src, float* dst) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-      dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w; dst[4] = b.x; dst[5] = b.y; dst[6] = b.z; dst[7] = b.w;
-    };
-    for (int t = p.T; t >= 1; --t) {
-      // everything the forward pass saved for this step: independent of the recurrence, fetched before the wait
-      float gi[8], gf[8], go[8], gg[8], tc[8], cp[8], dhx[8];
-      const float* sb = p.saved + (long long)(t - 1) * p.ls_t + (long long)rr * p.H + u0;
-      ld8(sb, gi); ld8(sb + p.plane, gf); ld8(sb + 2 * p.plane, go); ld8(sb + 3 * p.plane, gg); ld8(sb + 4 * p.plane, tc);
-      ld8(p.c_prev + (long long)(t - 1) * p.s_t + (long long)rr * p.lds + u0, cp);
-      if (p.dh_extra) ld8(p.dh_extra + ((long long)(t - 1) * p.B + rr) * p.H + u0, dhx);
-      else {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) dhx[u] = 0.0f;
-      }
-      float dh[8];
-      if (t < p.T) {   // every CTA of this row tile has reduced its slice of dG_{t+1} Wh into dHacc[t]
-        if (warp == 2 && lane == 0) {
-          const unsigned int need = (unsigned int)p.tiles_n * (unsigned int)(p.T - t);
-          const long long t0 = clock64();
-          while (ld_acquire_u32(p.counter + tm) < need) {
-            if (clock64() - t0 > 4000000000ll) { *p.err = 1u; *p.err_host = 1u; break; }   // never hang the device on a lost peer
-          }
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float4* hs = reinterpret_cast<const float4*>(p.dHacc + ((long long)t * p.B + rr) * p.H + u0);
-        const float4 a = __ldcg(hs), b = __ldcg(hs + 1);
-        dh[0] = a.x; dh[1] = a.y; dh[2] = a.z; dh[3] = a.w; dh[4] = b.x; dh[5] = b.y; dh[6] = b.z; dh[7] = b.w;
-      } else {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) dh[u] = 0.0f;
-      }
-      if (len == t) {   // drnn_out[k] = d_feats[1][k] (F:604-610): the answering units' gradient enters at t = len
-        ld8(p.dq_c + (long long)rr * p.lddq + u0, dcc);
-        ld8(p.dq_h + (long long)rr * p.lddq + u0, dh);
-      }
-      float zi[8], zf[8], zo[8], zg[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float dho = dh[u] + dhx[u];
-        const float d_o = dho * tc[u];
-        const float dc = dcc[u] + dho * go[u] * (1.0f - tc[u] * tc[u]);
-        dcc[u] = dc * gf[u];
-        zi[u] = r_ok ? dc * gg[u] * gi[u] * (1.0f - gi[u]) : 0.0f;
-        zf[u] = r_ok ? dc * cp[u] * gf[u] * (1.0f - gf[u]) : 0.0f;
-        zo[u] = r_ok ? d_o * go[u] * (1.0f - go[u]) : 0.0f;
-        zg[u] = r_ok ? dc * gi[u] * (1.0f - gg[u] * gg[u]) : 0.0f;
-      }
-      // the four gate chunks: global fp32 + packed (weight gradients, input gradient) and the A operand in smem
-      if (t >= 2) {   // the previous step's MMAs have read the A tile: d_bar of that step was waited for below
-      }
-      const float* zs[4] = {zi, zf, zo, zg};
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const float* z = zs[g];
-        uint32_t hh[4], hl[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) split_pair(z[2 * u], z[2 * u + 1], hh[u], hl[u]);
-        if (r_ok) {
-          const long long go_ = (long long)(t - 1) * p.g_t + (long long)r * 4 * p.H + (long long)g * p.H + u0;
-          float4* d = reinterpret_cast<float4*>(p.dG + go_);
-          d[0] = make_float4(z[0], z[1], z[2], z[3]); d[1] = make_float4(z[4], z[5], z[6], z[7]);
-          *reinterpret_cast<uint4*>(p.dG_hi + go_) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-          if (X3) *reinterpret_cast<uint4*>(p.dG_lo + go_) = make_uint4(hl[0], hl[1], hl[2], hl[3]);
-        }
-        if (t >= 2) {   // row (q*32 + lane) of the K-major tile, 16-byte chunk 2g + half, SWIZZLE_128B
-          const uint32_t row = (uint32_t)(q * 32 + lane);
-          const uint32_t a = smem_u32(asm_) + row * 128u + (uint32_t)(((2 * g + half) ^ (int)(row & 7u)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(hh[0]), "r"(hh[1]), "r"(hh[2]), "r"(hh[3]) : "memory");
-          if (X3) asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + a_plane), "r"(hl[0]), "r"(hl[1]), "r"(hl[2]), "r"(hl[3]) : "memory");
-        }
-      }
-      if (t < 2) break;
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&a_bar);
-      // partial dh_{t-1} of this CTA's units: TMEM -> staging -> reduce-add into dHacc[t-1]
-      mbar_wait(&d_bar, (uint32_t)(p.T - t) & 1u);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int nch = p.H / 64;   // 32-column chunks per column half of this warp: H/2 columns
-      for (int ch = 0; ch < nch; ++ch) {
-        const int col = half * (p.H / 2) + ch * 32;
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, v);
-        uint32_t w0[32];
-#pragma unroll
-        for (int k = 0; k < 32; ++k) w0[k] = __float_as_uint(v[k]);
-        if (lane == 0) bulk_wait_read0();   // (a second staging buffer per warp measured slower: the reduce-adds are the bound)
-        __syncwarp();
-        stage_row128(stg0, lane, w0);
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0 && rowbase < p.B) {
-          tma_reduce_add_2d(&p.mapR, stg_p, col, (t - 1) * p.B + rowbase);
-          bulk_commit();
-        }
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      // publish: the reduce-adds are complete, every writer fences, the warps meet, one thread releases the counter
-      if (lane == 0) bulk_wait0();
-      asm volatile("fence.proxy.async;" ::: "memory");
-      __threadfence();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (warp == 2 && lane == 0) red_release_add_u32(p.counter + tm, 1u);
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-  }
-}
-
 bool g_prep_attr = false;
 
 }  // namespace
 
-bool rows_path_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("RAU_ROWS");
-    v = e ? (atoi(e) != 0) : 1;
-  }
-  return v != 0;
-}
+bool rows_path_enabled() { return rau_process_tuning().rows != 0; }
 
 int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   RAU_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "rows_gemm: bad shape %dx%dx%d", g.M, g.N, g.K);
@@ -1888,8 +1656,7 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   p.nkb = (g.K + p.BK - 1) / p.BK;
   const bool seg2 = g.K2 > 0;
   {   // CTA pairs (cta_group::2) for the big K-major products: RAU_CG2=0 keeps everything on single CTAs
-    static int cg2_on = -1;
-    if (cg2_on < 0) { const char* e = getenv("RAU_CG2"); cg2_on = e ? atoi(e) : 1; }
+    const int cg2_on = ctx->tune.cg2;
     const bool pair_epi = g.epi == EPI_PLAIN || g.epi == EPI_TANH || g.epi == EPI_ATT || g.epi == EPI_DY || g.epi == EPI_RED;
     // big row counts (the image-side products), or split-K reductions with at least one pair of row tiles
     const bool pair_shape = g.epi == EPI_RED ? (p.tiles_m >= 2 && p.tiles_m % 2 == 0 && p.nkb >= 64) : p.tiles_m >= 8;
@@ -1910,8 +1677,7 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   p.stage_bytes = (p.x3 ? 2 : 1) * (RT_BM + (p.cg2 ? BN / 2 : BN)) * p.BK * 2;
   if (g.epi == EPI_DY) p.stg_warp = 9216;   // + a 32 x 64 B (hi, lo) scratch per warp (the saved activation is fetched coalesced) + 1 KB row vector
   {   // the 1-pass (fp16 / bf16) CTA-pair i_embed product is epilogue bound: 16 epilogue warps (RAU_TANH_EW=8: A/B switch)
-    static int ew_tanh = -1;
-    if (ew_tanh < 0) { const char* e = getenv("RAU_TANH_EW"); ew_tanh = (e && atoi(e) == 8) ? 8 : 16; }
+    const int ew_tanh = ctx->tune.tanh_ew;
     // (K <= 1024: at K = 2048 the product is tensor bound and the stage the extra staging buffers cost matters more)
     p.ew = (g.epi == EPI_TANH && p.cg2 && !p.x3 && g.K <= 1024) ? ew_tanh : 8;
   }
@@ -2004,9 +1770,7 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   int grid = items < sm_avail ? items : sm_avail;
   if (p.cg2) grid = 2 * (items < sm_avail / 2 ? items : sm_avail / 2);   // whole CTA pairs
   {
-    static int trace = -1;
-    if (trace < 0) { const char* e = getenv("RAU_ROWS_TRACE"); trace = e ? atoi(e) : 0; }
-    if (trace) {   // debugging aid: the stamps of the LAST launch are left in the arena buffer "rows.trace"
+    if (ctx->tune.rows_trace) {   // debugging aid: the stamps of the LAST launch are left in the arena buffer "rows.trace"
       void* buf = nullptr;
       RAU_TRY(ctx->arena.get("rows.trace", sizeof(unsigned long long) * 16 * 148, &buf));
       RAU_CHECK_CUDA(cudaMemsetAsync(buf, 0, sizeof(unsigned long long) * 16 * 148, ctx->stream));
@@ -2122,29 +1886,13 @@ int k_attn_rows_fwd(rau_ctx* ctx, int B, int M, int S, const float* logit, const
   return RAU_OK;
 }
 
-// content logits + attbymemory + attselect in one launch (see attn_rows_fwd_kernel<SCORE>)
-int k_attn_rows_fwd_scored(rau_ctx* ctx, int B, int M, int A, int S, const float* Z, const float* qadd, const float* ws,
-                           int fast_tanh, const float* mem, const bf16* I_hi, const bf16* I_lo, float* p, float* a, bf16* p_hi,
-                           bf16* p_lo, int ldp, int f16) {
-  RAU_REQUIRE(M % 256 == 0 && S <= 256 && ldp <= 256 && A % 4 == 0, "k_attn_rows_fwd_scored: M=%d A=%d S=%d", M, A, S);
-  if (fast_tanh)
-    RAU_LAUNCH_PDL(ctx->stream, (attn_rows_fwd_kernel<2>), dim3(B, M / 256), 256, 0, S, M, (const float*)nullptr, mem, I_hi, I_lo, p, a,
-                   p_hi, p_lo, ldp, A, Z, qadd, ws, f16);
-  else
-    RAU_LAUNCH_PDL(ctx->stream, (attn_rows_fwd_kernel<1>), dim3(B, M / 256), 256, 0, S, M, (const float*)nullptr, mem, I_hi, I_lo, p, a,
-                   p_hi, p_lo, ldp, A, Z, qadd, ws, f16);
-  RAU_LAUNCH_CHECK(ctx);
-  return RAU_OK;
-}
-
 int k_attn_rows_score(rau_ctx* ctx, int B, int A, int S, const float* Z, const float* qadd, const float* ws, int fast_tanh,
                       float* logit) {
   RAU_REQUIRE(A % 4 == 0, "k_attn_rows_score: A=%d", A);
   const int R = B * S;
   int grid = (R + 31) / 32;
-  const char* e_w = getenv("RAU_SCORE_WAVE");   // =0: one batch of 4 rows per warp (1.3 waves at B = 256); default: one wave
-  if (!(e_w && atoi(e_w) == 0)) {
-    const int one_wave = ctx->sm_count * 6;   // 6 CTAs of 256 threads per SM
+  {   // one resident wave (6 CTAs of 256 threads per SM): a warp then walks several batches of 4 rows
+    const int one_wave = ctx->sm_count * 6;
     if (grid > one_wave) grid = (grid + 1) / 2 <= one_wave ? (grid + 1) / 2 : one_wave;
   }
   if (fast_tanh) RAU_LAUNCH_PDL(ctx->stream, (attn_rows_score_kernel<1>), grid, 256, 0, R, S, A, Z, qadd, ws, logit);
@@ -2203,8 +1951,7 @@ static cudaError_t launch_cooperative(cudaStream_t st, void (*kern)(P), int grid
 // when the shape does not fit (the caller then unrolls the per-step EPI_LSTM launches).
 int rows_lstm_seq(rau_ctx* ctx, const LstmSeq& d, int* done) {
   *done = 0;
-  const char* e_on = getenv("RAU_LSTM_SEQ");   // =0: one launch per recurrent step (read per call: the tests switch it)
-  const int on = e_on ? atoi(e_on) : 1;
+  const int on = ctx->tune.lstm_seq;   // RAU_LSTM_SEQ=0: one launch per recurrent step
   const int B = d.B, H = d.H, T = d.T;
   const bool x3 = d.hpk_lo != nullptr;
   if (!on || H % 64 != 0 || T < 1 || !d.hpk_hi || !d.Wh_hi || (x3 != (d.Wh_lo != nullptr))) return RAU_OK;
@@ -2230,7 +1977,7 @@ int rows_lstm_seq(rau_ctx* ctx, const LstmSeq& d, int* done) {
   RAU_REQUIRE(tiles_m <= 64, "rows_lstm_seq: %d row tiles", tiles_m);
   RAU_CHECK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * 64, ctx->stream));
   p.counter = cnt; p.err = ctx->d_err; p.err_host = ctx->h_err_dev;
-  { const char* e_f = getenv("RAU_SEQ_FENCE"); p.fence_all = e_f ? atoi(e_f) : 1; }
+  p.fence_all = 1;
   const int smem_bytes = w_bytes + stages * a_stage + 1024;
   static bool attr_done[2] = {false, false};
   if (!attr_done[x3 ? 1 : 0]) {
@@ -2248,64 +1995,16 @@ int rows_lstm_seq(rau_ctx* ctx, const LstmSeq& d, int* done) {
 }
 
 
-// The backward recurrence of one encoder LSTM layer in one persistent launch (lstm_seq_bwd_kernel).  *done = 0 when the shape
-// does not fit (the caller then unrolls cell backward + split-K dgrad per step).
-int rows_lstm_seq_bwd(rau_ctx* ctx, const LstmSeqBwd& d, int* done) {
-  *done = 0;
-  // Opt-in (RAU_LSTM_SEQ_BWD=1): parity-green, but measured SLOWER than the per-step launches (encoder backward 1.05 ms against
-  // 0.79 ms alone, 1.29 against 1.23 ms next to the side stream).  With 16 hidden units per CTA the dgrad is a 32-way split-K:
-  // 16 MB of fp32 reduce-adds per step against 2-4 MB for the unrolled form, and that traffic, not the launches, is the bound.
-  const char* e_on = getenv("RAU_LSTM_SEQ_BWD");   // (read per call: the tests switch it)
-  const int on = e_on ? atoi(e_on) : 0;
-  const int B = d.B, H = d.H, T = d.T;
-  const bool x3 = d.dG_lo != nullptr;
-  if (!on || (H != 256 && H != 512) || T < 1 || !d.dG_hi || !d.Wh_hi || (x3 != (d.Wh_lo != nullptr))) return RAU_OK;
-  const int tiles_m = (B + 127) / 128, tiles_n = H / 16;
-  const int w_bytes = (H / 64) * 4 * (x3 ? 2 : 1) * 2048, a_bytes = (x3 ? 2 : 1) * 128 * 128;
-  const int smem_bytes = w_bytes + a_bytes + 8 * 4096 + 1024;
-  if (smem_bytes > RT_SMEM_BUDGET + 1024 || tiles_m * tiles_n > ctx->sm_count || tiles_m >= 63) return RAU_OK;
-  RAU_REQUIRE(d.ldwh % 8 == 0 && d.lds % 4 == 0 && d.lddq % 4 == 0, "rows_lstm_seq_bwd: pitches");
-  RAU_TRY(get_encode());
-  LbParams p;
-  memset(&p, 0, sizeof(p));
-  RAU_TRY(encode_operand(&p.mapW, d.Wh_hi, d.Wh_lo, &p.b_swap, 1, H, 4 * H, d.ldwh, 16, 0));
-  float* acc = nullptr;
-  RAU_TRY(ctx->arena.get("lstmseq.dHacc", sizeof(float) * (size_t)(T + 1) * B * H, (void**)&acc));
-  RAU_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(float) * (size_t)(T + 1) * B * H, ctx->stream));
-  RAU_TRY(encode_2d(&p.mapR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, acc, (uint64_t)H, (uint64_t)(T + 1) * B, (uint64_t)H, 32, 32,
-                    CU_TENSOR_MAP_SWIZZLE_128B));
-  p.B = B; p.H = H; p.T = T; p.tiles_n = tiles_n;
-  p.lengths = d.lengths; p.dq_c = d.dq_c; p.dq_h = d.dq_h; p.lddq = d.lddq;
-  p.dh_extra = d.dh_extra;
-  p.c_prev = d.c_prev; p.s_t = d.s_t; p.lds = d.lds;
-  p.saved = d.saved; p.ls_t = (long long)5 * B * H; p.plane = (long long)B * H;
-  p.dG = d.dG; p.dG_hi = d.dG_hi; p.dG_lo = d.dG_lo; p.g_t = (long long)B * 4 * H;
-  p.dHacc = acc;
-  unsigned int* cnt = nullptr;
-  RAU_TRY(ctx->arena.get("lstmseq.cntb", sizeof(unsigned int) * 64, (void**)&cnt));
-  RAU_CHECK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * 64, ctx->stream));
-  p.counter = cnt; p.err = ctx->d_err; p.err_host = ctx->h_err_dev;
-  static bool attr_done[2] = {false, false};
-  if (!attr_done[x3 ? 1 : 0]) {
-    if (x3) RAU_CHECK_CUDA(cudaFuncSetAttribute(lstm_seq_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM_BUDGET + 1024));
-    else RAU_CHECK_CUDA(cudaFuncSetAttribute(lstm_seq_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM_BUDGET + 1024));
-    attr_done[x3 ? 1 : 0] = true;
-  }
-  if (x3) RAU_CHECK_CUDA(launch_cooperative(ctx->stream, lstm_seq_bwd_kernel<1>, tiles_m * tiles_n, LS_THREADS, smem_bytes, p));
-  else RAU_CHECK_CUDA(launch_cooperative(ctx->stream, lstm_seq_bwd_kernel<0>, tiles_m * tiles_n, LS_THREADS, smem_bytes, p));
-  RAU_LAUNCH_CHECK(ctx);
-  *done = 1;
-  return RAU_OK;
-}
-
 // ================================================================== nn.Linear adapter
 namespace {
 // fp32 [rows, cols] (pitch ld) -> packed bf16 (hi [, lo]) [rows, ldo] with ldo = cols rounded up to 8, zero padded
+// wcols (even, <= ldo): columns written per packed row -- ldo for a whole row (zero padded past cols), less when the
+// destination is a column block of a wider packed matrix
 __global__ void pack2d_kernel(const float* __restrict__ in, int64_t ld, int rows, int cols, int ldo, bf16* __restrict__ hi,
-                              bf16* __restrict__ lo) {
+                              bf16* __restrict__ lo, int wcols) {
   RAU_PDL_ENTRY();
-  const int q = ldo >> 1;   // pairs per packed row
-  const int64_t total = (int64_t)rows * q;
+  const int q = wcols >> 1;   // pairs written per packed row
+  const int64_t total = (int64_t)rows * q, pitch = ldo >> 1;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % q) * 2;
     const int64_t r = i / q;
@@ -2313,8 +2012,9 @@ __global__ void pack2d_kernel(const float* __restrict__ in, int64_t ld, int rows
     const float b = c + 1 < cols ? in[r * ld + c + 1] : 0.0f;
     uint32_t h, l;
     split_pair(a, b, h, l);
-    reinterpret_cast<uint32_t*>(hi)[i] = h;
-    if (lo) reinterpret_cast<uint32_t*>(lo)[i] = l;
+    const int64_t o = r * pitch + (c >> 1);
+    reinterpret_cast<uint32_t*>(hi)[o] = h;
+    if (lo) reinterpret_cast<uint32_t*>(lo)[o] = l;
   }
 }
 
@@ -2345,7 +2045,7 @@ int pack2d(rau_ctx* ctx, const float* src, int64_t ld, int rows, int cols, bool 
     int64_t blocks = (work + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
-    RAU_LAUNCH_PDL(ctx->stream, (pack2d_kernel), (int)blocks, 256, 0, src, ld, rows, cols, ldo, (bf16*)out->hi, (bf16*)out->lo);
+    RAU_LAUNCH_PDL(ctx->stream, (pack2d_kernel), (int)blocks, 256, 0, src, ld, rows, cols, ldo, (bf16*)out->hi, (bf16*)out->lo, ldo);
     RAU_LAUNCH_CHECK(ctx);
     if (is_const) ctx->tc_epoch[name] = ctx->epoch;
   }
@@ -2353,13 +2053,15 @@ int pack2d(rau_ctx* ctx, const float* src, int64_t ld, int rows, int cols, bool 
 }
 
 }  // namespace
-int rows_pack_into(rau_ctx* ctx, const float* src, int64_t ld, int rows, int cols, bf16* hi, bf16* lo, int64_t ldo) {
+int rows_pack_into(rau_ctx* ctx, const float* src, int64_t ld, int rows, int cols, bf16* hi, bf16* lo, int64_t ldo, int wcols) {
   RAU_REQUIRE(hi != nullptr && ldo % 2 == 0 && ldo >= cols, "rows_pack_into: bad destination (ldo = %lld)", (long long)ldo);
-  const int64_t work = (int64_t)rows * (ldo / 2);
+  if (wcols <= 0) wcols = (int)ldo;
+  RAU_REQUIRE(wcols % 2 == 0 && wcols <= ldo && wcols >= cols, "rows_pack_into: wcols = %d", wcols);
+  const int64_t work = (int64_t)rows * (wcols / 2);
   int64_t blocks = (work + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  RAU_LAUNCH_PDL(ctx->stream, (pack2d_kernel), (int)blocks, 256, 0, src, ld, rows, cols, (int)ldo, hi, lo);
+  RAU_LAUNCH_PDL(ctx->stream, (pack2d_kernel), (int)blocks, 256, 0, src, ld, rows, cols, (int)ldo, hi, lo, wcols);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
@@ -2469,14 +2171,7 @@ __global__ void linear_init_kernel(float* __restrict__ C, long long ldc, int M, 
   }
 }
 
-long long rows_min_work() {
-  static long long v = -1;
-  if (v < 0) {
-    const char* e = getenv("RAU_TC_MIN_WORK");
-    v = e ? atoll(e) : (1ll << 18);
-  }
-  return v;
-}
+long long rows_min_work() { return rau_process_tuning().tc_min_work; }
 }  // namespace
 
 int rows_contract_try(rau_ctx* ctx, const SimtGemm& g) {

@@ -47,6 +47,30 @@ struct RauArena {
   void release();
 };
 
+// Every environment switch of the library, read in ONE place (rau_tuning_from_env, rau_ctx.cu) when a context is created.
+// The defaults are the measured best; the switches exist for A/B runs, tests of the alternative schedules and debugging.
+struct RauTuning {
+  int graph = 1;          // RAU_GRAPH=0: never capture the step into a CUDA graph
+  int overlap = 7;        // RAU_OVERLAP: bit 0 backward products, bit 1 forward pre-work, bit 2 answer heads on the side stream
+  int side_ctas = 0;      // RAU_SIDE_CTAS: SMs the side stream's launches size themselves for (0 = 4/7 of the device)
+  int side_ctas_fwd = 0;  // RAU_SIDE_CTAS_FWD / _BWD: the same for the forward pre-work / the hops' backward products
+  int side_ctas_bwd = 0;
+  int main_ctas = 0;      // RAU_MAIN_CTAS: SMs the chain's split-K products size for while the side stream runs (0 = the rest)
+  int rows = 1;           // RAU_ROWS=0: route products to the first-cut tcgen05 engine
+  int cg2 = 1;            // RAU_CG2=0: no CTA pairs
+  int tanh_ew = 16;       // RAU_TANH_EW=8: eight epilogue warps for the 1-pass i_embed product
+  int rows_trace = 0;     // RAU_ROWS_TRACE=1: per-CTA clock stamps of rows-engine launches (tools/rows_trace.py)
+  int lstm_seq = 1;       // RAU_LSTM_SEQ=0: one launch per recurrent step of the encoder instead of the persistent kernel
+  int enc_bwd_wave = 1;   // RAU_ENC_BWD_WAVE=0: encoder backward layer after layer instead of the two-stream wavefront
+  int xprep_hops = 1;     // RAU_XPREP_HOPS=0: one feature-pack launch per hop instead of one for all hops
+  int pdl = 0;            // RAU_PDL=1: programmatic dependent launch attribute on every launch (measured slower)
+  int phases = 0;         // RAU_PHASES: 1 = per-phase events of an eager step, 2 = %globaltimer stamps inside the graph
+  long long tc_min_work = 1ll << 18;   // RAU_TC_MIN_WORK: M*N*K below which a product stays on the CUDA-core engine
+  int time_cap = 0;       // RAU_TIME_CAP: SM cap for rau_rows_gemm_time
+};
+RauTuning rau_tuning_from_env();
+const RauTuning& rau_process_tuning();   // read once per process: for the few call sites that have no context at hand
+
 struct RauComm;  // rau_comm.cu
 
 // Per-step scalars kept on the device so that a captured CUDA graph of the training step can be replayed
@@ -74,6 +98,7 @@ struct rau_ctx {
   cudaStream_t stream = nullptr;
   uint64_t seed = 0x5eed5eedULL;
   int precision = RAU_PREC_MIXED;
+  RauTuning tune;
   int sm_count = 148;
   int64_t launches = 0;
   RauArena arena;

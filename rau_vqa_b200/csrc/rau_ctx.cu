@@ -44,14 +44,35 @@ void RauArena::release() {
 
 int rau_comm_destroy_internal(rau_ctx* ctx);  // rau_comm.cu
 
-bool rau_pdl_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("RAU_PDL");
-    v = e ? (atoi(e) != 0) : 0;   // opt-in: measured 4 % SLOWER on the graph-replayed Ours_Full step (8.13 vs 7.79 ms)
-  }
-  return v != 0;
+// the ONLY place the library reads the environment
+RauTuning rau_tuning_from_env() {
+  RauTuning t;
+  auto geti = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+  t.graph = geti("RAU_GRAPH", t.graph);
+  t.overlap = geti("RAU_OVERLAP", t.overlap);
+  t.side_ctas = geti("RAU_SIDE_CTAS", 0);
+  t.side_ctas_fwd = geti("RAU_SIDE_CTAS_FWD", 0);
+  t.side_ctas_bwd = geti("RAU_SIDE_CTAS_BWD", 0);
+  t.main_ctas = geti("RAU_MAIN_CTAS", 0);
+  t.rows = geti("RAU_ROWS", t.rows);
+  t.cg2 = geti("RAU_CG2", t.cg2);
+  t.tanh_ew = geti("RAU_TANH_EW", t.tanh_ew) == 8 ? 8 : 16;
+  t.rows_trace = geti("RAU_ROWS_TRACE", 0);
+  t.lstm_seq = geti("RAU_LSTM_SEQ", t.lstm_seq);
+  t.enc_bwd_wave = geti("RAU_ENC_BWD_WAVE", t.enc_bwd_wave);
+  t.xprep_hops = geti("RAU_XPREP_HOPS", t.xprep_hops);
+  t.pdl = geti("RAU_PDL", 0);   // opt-in: measured SLOWER on the graph-replayed step (6.28 vs 4.82 ms)
+  t.phases = geti("RAU_PHASES", 0);
+  { const char* e = getenv("RAU_TC_MIN_WORK"); if (e) t.tc_min_work = atoll(e); }
+  t.time_cap = geti("RAU_TIME_CAP", 0);
+  return t;
 }
+const RauTuning& rau_process_tuning() {
+  static const RauTuning t = rau_tuning_from_env();
+  return t;
+}
+
+bool rau_pdl_enabled() { return rau_process_tuning().pdl != 0; }
 
 namespace {
 __global__ void stamp_kernel(unsigned long long* out) {
@@ -62,10 +83,7 @@ __global__ void stamp_kernel(unsigned long long* out) {
 }  // namespace
 
 void rau_phase_mark(rau_ctx* ctx, const char* name) {
-  if (ctx->phases < 0) {
-    const char* e = getenv("RAU_PHASES");
-    ctx->phases = e ? atoi(e) : 0;
-  }
+  if (ctx->phases < 0) ctx->phases = ctx->tune.phases;
   if (!ctx->phases) return;
   if (ctx->phases == 2) {
     if (!ctx->stamp_buf && cudaMalloc(&ctx->stamp_buf, sizeof(unsigned long long) * 1024) != cudaSuccess) return;
@@ -159,8 +177,8 @@ int rau_ctx_create(rau_ctx** out, int device, void* cuda_stream) {
     delete ctx;
     return RAU_ECUDA;
   }
-  const char* eg = getenv("RAU_GRAPH");
-  if (eg && atoi(eg) == 0) ctx->graph.disabled = true;
+  ctx->tune = rau_tuning_from_env();
+  if (ctx->tune.graph == 0) ctx->graph.disabled = true;
   *out = ctx;
   return RAU_OK;
 }

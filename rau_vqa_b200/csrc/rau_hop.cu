@@ -138,8 +138,7 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
   // attbymemory's logits Wm h + bm (F:285-290) need the previous state only: in the training step they run on the aux
   // stream next to q_embed / qatt instead of between them on the chain
   cudaEvent_t mem_ev = nullptr;
-  const char* e_ma = getenv("RAU_MEM_AUX");   // =0: keep the memory logits on the chain (A/B switch)
-  if (as && as->head_side && ctx->aux != nullptr && rows_path(ctx, cfg) && sv.hin_pk.hi && !(e_ma && atoi(e_ma) == 0)) {
+  if (as && as->head_side && ctx->aux != nullptr && rows_path(ctx, cfg) && sv.hin_pk.hi) {
     cudaEvent_t ev0 = rau_side_event(ctx);
     mem_ev = rau_side_event(ctx);
     RAU_REQUIRE(ev0 != nullptr && mem_ev != nullptr, "cudaEventCreate failed");
@@ -198,18 +197,11 @@ int hop_forward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const fl
     }
     if (as && as->pre_done) RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, as->pre_done, 0));
     // attbycontent (F:244-252): logit = ws . tanh(Z + ba + qatt[b])  (bs shifts every logit alike: the softmax drops it)
-    // RAU_ATTN_FUSED=1 folds the content-logit pass into the softmax / weighted-sum launch (one launch less per hop): three
-    // A/B pairs on one box measured it SLOWER (5.00 vs 4.90 ms: both channel halves of an image redo the logits and the
-    // two phases no longer overlap across CTAs), so the two launches stay
-    const char* e_af = getenv("RAU_ATTN_FUSED");
-    if (!(e_af && atoi(e_af) != 0)) {
-      RAU_TRY(k_attn_rows_score(ctx, B, A, S, sv.E, sv.qatt, P.ws, x3 ? 0 : 1, slog));
-      RAU_TRY(k_attn_rows_fwd(ctx, B, M, S, slog, mem, sv.I_hi, (x3 && !f16i) ? sv.I_lo : nullptr, sv.p, a, sv.p_pk.hi,
-                              x3 ? sv.p_pk.lo : nullptr, (int)sv.p_pk.ld, f16i));
-    } else {
-      RAU_TRY(k_attn_rows_fwd_scored(ctx, B, M, A, S, sv.E, sv.qatt, P.ws, x3 ? 0 : 1, mem, sv.I_hi, (x3 && !f16i) ? sv.I_lo : nullptr,
-                                     sv.p, a, sv.p_pk.hi, x3 ? sv.p_pk.lo : nullptr, (int)sv.p_pk.ld, f16i));
-    }
+    // (folding the content-logit pass into the softmax / weighted-sum launch measured SLOWER -- 5.00 vs 4.90 ms: both channel
+    // halves of an image redo the logits and the two phases no longer overlap across CTAs -- so the two launches stay)
+    RAU_TRY(k_attn_rows_score(ctx, B, A, S, sv.E, sv.qatt, P.ws, x3 ? 0 : 1, slog));
+    RAU_TRY(k_attn_rows_fwd(ctx, B, M, S, slog, mem, sv.I_hi, (x3 && !f16i) ? sv.I_lo : nullptr, sv.p, a, sv.p_pk.hi,
+                            x3 ? sv.p_pk.lo : nullptr, (int)sv.p_pk.ld, f16i));
   } else {
   // i_embed (F:238-242): I[b] = tanh(Wi drop(X[b]) + bi), 1x1 convolution = per-image [M,C]x[C,S] product
   if (tc) RAU_TRY(k_dropout_pack(ctx, X, (int64_t)B * C, S, xb, drop_scale(cfg->p_x), sv.Xd_hi, x3 ? sv.Xd_lo : nullptr, Sp));
@@ -943,10 +935,7 @@ int rau_rows_gemm_time(rau_ctx* ctx, int M, int N, int K, int a_mn, int b_mn, in
       g.colsum = reduce == 2 ? cs : nullptr;
     }
   }
-  {
-    const char* e = getenv("RAU_TIME_CAP");
-    ctx->rows_cta_cap = e ? atoi(e) : 0;
-  }
+  ctx->rows_cta_cap = ctx->tune.time_cap;
   struct CapReset { rau_ctx* c; ~CapReset() { c->rows_cta_cap = 0; } } cap_reset{ctx};
   RAU_TRY(rows_gemm(ctx, g));   // warm-up (function attributes, arena)
   RAU_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));

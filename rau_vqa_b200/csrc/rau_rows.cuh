@@ -56,7 +56,8 @@ int rows_pack_lstm(rau_ctx* ctx, const float* W, int H, int K, int gate_order, b
                    int64_t* ldo);
 int rows_perm_lstm_bias(rau_ctx* ctx, const float* b1, const float* b2, int H, int gate_order, const float** out);
 // same, into a caller-owned packed twin (pitch ldo >= cols, zero padded)
-int rows_pack_into(rau_ctx* ctx, const float* src, int64_t ld, int rows, int cols, bf16* hi, bf16* lo, int64_t ldo);
+// wcols > 0: write only that many columns per row (the destination is a column block of a wider packed matrix)
+int rows_pack_into(rau_ctx* ctx, const float* src, int64_t ld, int rows, int cols, bf16* hi, bf16* lo, int64_t ldo, int wcols = 0);
 int rows_pack(rau_ctx* ctx, const float* W, int64_t n, bool want_lo, bool cache, const char* slot, const bf16** hi, const bf16** lo,
               bool f16 = false);   // f16: one fp16 plane instead of bf16 hi [, lo]
 // gen != 0: draw the keep bits inline from Philox stream `stream_id` with drop rate p_drop (bits is then ignored)
@@ -80,25 +81,9 @@ struct LstmSeq {
 };
 int rows_lstm_seq(rau_ctx* ctx, const LstmSeq& d, int* done);
 
-// the backward recurrence of one encoder LSTM layer, t = T..1, in a single persistent launch (lstm_seq_bwd_kernel);
-// gate chunks in the order i, f, o, g (RAU_GATES_IFOG)
-struct LstmSeqBwd {
-  int B = 0, H = 0, T = 0;
-  const bf16* Wh_hi = nullptr; const bf16* Wh_lo = nullptr; int64_t ldwh = 0;   // rows_pack2d layout [4H, H]
-  const float* lengths = nullptr; const float* dq_c = nullptr; const float* dq_h = nullptr; int lddq = 0;
-  const float* dh_extra = nullptr;                                              // [T][B][H] or NULL
-  const float* c_prev = nullptr; int64_t s_t = 0; int lds = 0;                  // c of step 0, step stride, pitch
-  const float* saved = nullptr;                                                 // saved gates of step 1, [T][5][B][H]
-  float* dG = nullptr; bf16* dG_hi = nullptr; bf16* dG_lo = nullptr;            // [T][B][4H]
-};
-int rows_lstm_seq_bwd(rau_ctx* ctx, const LstmSeqBwd& d, int* done);
-
 // logit[r] = ws . tanh(Z[r,:] + qadd[b(r),:])  (Z = I Wa^T precomputed; qadd = Wqa qf + bqa + ba)
 int k_attn_rows_score(rau_ctx* ctx, int B, int A, int S, const float* Z, const float* qadd, const float* ws, int fast_tanh,
                       float* logit);
-int k_attn_rows_fwd_scored(rau_ctx* ctx, int B, int M, int A, int S, const float* Z, const float* qadd, const float* ws,
-                           int fast_tanh, const float* mem, const bf16* I_hi, const bf16* I_lo, float* p, float* a,
-                           bf16* p_hi = nullptr, bf16* p_lo = nullptr, int ldp = 0, int f16 = 0);
 int k_attn_rows_bwd(rau_ctx* ctx, int B, int M, int A, int S, const float* E, const bf16* I_hi, const bf16* I_lo, const float* ws,
                     const float* p, const float* dp_in, const float* da, float* ds, bf16* dZ_hi, bf16* dZ_lo, float* dqa,
                     float* gws_part, bf16* ds_hi = nullptr, bf16* ds_lo = nullptr, int ldds = 0,

@@ -214,9 +214,7 @@ static int encoder_backward(rau_ctx* ctx, const rau_config* cfg, const rau_batch
     // backward recurrences run on two streams one step apart: 2 T serial steps become T + 1.  Per step, layer 2 forms
     // [dH2_{t-1} | du2_t] = dG2_t [Wh2 | Wi2] in ONE split-K product (the input gradient is not hoisted over time any more)
     // and layer 1 applies the dropout mask of u2 inside its cell backward.
-    const char* e_wv = getenv("RAU_ENC_BWD_WAVE");
-    const char* e_sb = getenv("RAU_LSTM_SEQ_BWD");
-    const bool wave = !(e_wv && atoi(e_wv) == 0) && !(e_sb && atoi(e_sb) != 0) && ctx->aux2 != nullptr && Tm >= 2;
+    const bool wave = ctx->tune.enc_bwd_wave != 0 && ctx->aux2 != nullptr && Tm >= 2;
     if (wave) {
       bf16* dG1_hi = dGp;
       bf16* dG1_lo = x3 ? dG1_hi + (size_t)cfg->T * gb : nullptr;
@@ -231,8 +229,8 @@ static int encoder_backward(rau_ctx* ctx, const rau_config* cfg, const rau_batch
       bf16* Wcat_hi = Wcat;
       bf16* Wcat_lo = x3 ? Wcat + (size_t)G4 * 2 * Hq : nullptr;
       if (ctx->tc_epoch["encb.Wcat"] != ctx->epoch) {   // (packed once per public call, like every weight shadow)
-        RAU_TRY(rows_pack_into(ctx, Pr + L[1].Wh, Hq, G4, Hq, Wcat_hi, Wcat_lo, 2 * Hq));
-        RAU_TRY(rows_pack_into(ctx, Pr + L[1].Wi, Hq, G4, Hq, Wcat_hi + Hq, Wcat_lo ? Wcat_lo + Hq : nullptr, 2 * Hq));
+        RAU_TRY(rows_pack_into(ctx, Pr + L[1].Wh, Hq, G4, Hq, Wcat_hi, Wcat_lo, 2 * Hq, Hq));
+        RAU_TRY(rows_pack_into(ctx, Pr + L[1].Wi, Hq, G4, Hq, Wcat_hi + Hq, Wcat_lo ? Wcat_lo + Hq : nullptr, 2 * Hq, Hq));
         ctx->tc_epoch["encb.Wcat"] = ctx->epoch;
       }
       // out2[t] = [dH2 into step t | du2 of step t+1 ...]: slab s (1-based step that PRODUCED it) holds dG2_s [Wh2 | Wi2]:
@@ -374,19 +372,7 @@ static int encoder_backward(rau_ctx* ctx, const rau_config* cfg, const rau_batch
       const int in = layer == 0 ? E : Hq;
       RAU_TRY(rows_pack2d(ctx, Pr + L[layer].Wh, Hq, G4, Hq, x3, true, nullptr, &Wh_h, &Wh_l, &ldwh));
       RAU_TRY(rows_pack2d(ctx, Pr + L[layer].Wi, in, G4, in, x3, true, nullptr, &Wi_h, &Wi_l, &ldwi));
-      int seq_done = 0;
-      {   // the whole backward recurrence in one persistent launch when the layer fits
-        LstmSeqBwd d;
-        d.B = B; d.H = Hq; d.T = Tm;
-        d.Wh_hi = Wh_h; d.Wh_lo = Wh_l; d.ldwh = ldwh;
-        d.lengths = bt->lengths; d.dq_c = dq + 2 * layer * Hq; d.dq_h = dq + (2 * layer + 1) * Hq; d.lddq = Q;
-        d.dh_extra = layer == 0 ? du2 : nullptr;
-        d.c_prev = en->S_all + 2 * layer * Hq; d.s_t = (int64_t)B * Q; d.lds = Q;
-        d.saved = layer == 1 ? en->sav2 : en->sav1;
-        d.dG = dG; d.dG_hi = dG_hi; d.dG_lo = dG_lo;
-        RAU_TRY(rows_lstm_seq_bwd(ctx, d, &seq_done));
-      }
-      for (int t = Tm; t >= 1 && !seq_done; --t) {
+      for (int t = Tm; t >= 1; --t) {
         const bool last = t == Tm;
         const float* Sp_ = en->S_all + (size_t)(t - 1) * B * Q + 2 * layer * Hq;
         float* dH = dHb[t & 1];            // written by step t+1's dgrad
@@ -556,28 +542,23 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   rau_phase_mark(ctx, "begin");
   // cross-stream overlap (rows path): RAU_OVERLAP bit 0 = heavy backward products on the side stream, bit 1 = the
   // state-independent i_embed products of all hops on the side stream, next to the encoder and the chain
-  const char* e_ov = getenv("RAU_OVERLAP");   // (read per call: the tests switch it)
-  const int overlap_mode = e_ov ? atoi(e_ov) : 7;
+  const int overlap_mode = ctx->tune.overlap;
   const bool rows_hops = hop_rows_path(ctx, cfg) && ctx->side != nullptr;
   const bool ov_bwd = rows_hops && (overlap_mode & 1);
   const bool ov_fwd = rows_hops && (overlap_mode & 2);
   const bool ov_head = rows_hops && (overlap_mode & 4);   // bit 2: the answer heads + criteria of the forward unroll
   if (ctx->side_ctas == 0) {
-    const char* e = getenv("RAU_SIDE_CTAS");
-    ctx->side_ctas = e ? atoi(e) : (ctx->sm_count * 4) / 7;   // 84 of 148 SMs measured best on Ours_Full (profiles/README.md)
+    ctx->side_ctas = ctx->tune.side_ctas > 0 ? ctx->tune.side_ctas : (ctx->sm_count * 4) / 7;   // 84 of 148 SMs (profiles/README.md)
     if (ctx->side_ctas < 8 || ctx->side_ctas > ctx->sm_count) ctx->side_ctas = ctx->sm_count;
-    const char* eb = getenv("RAU_SIDE_CTAS_BWD");
-    ctx->side_ctas_bwd = eb ? atoi(eb) : 0;
+    ctx->side_ctas_bwd = ctx->tune.side_ctas_bwd;
     if (ctx->side_ctas_bwd < 0 || ctx->side_ctas_bwd > ctx->sm_count) ctx->side_ctas_bwd = 0;
-    const char* ef = getenv("RAU_SIDE_CTAS_FWD");
-    ctx->side_ctas_fwd = ef ? atoi(ef) : ctx->side_ctas;
+    ctx->side_ctas_fwd = ctx->tune.side_ctas_fwd > 0 ? ctx->tune.side_ctas_fwd : ctx->side_ctas;
     if (ctx->side_ctas_fwd < 8 || ctx->side_ctas_fwd > ctx->sm_count) ctx->side_ctas_fwd = ctx->sm_count;
   }
   ctx->side_ev_next = 0;
   {
     // the chain's split-K products size themselves for the SMs the side stream leaves free (one wave, not two)
-    static int mc = -1;
-    if (mc < 0) { const char* e = getenv("RAU_MAIN_CTAS"); mc = e ? atoi(e) : 0; }
+    const int mc = ctx->tune.main_ctas;
     const int auto_cap = ctx->sm_count - ctx->side_ctas >= 32 ? ctx->sm_count - ctx->side_ctas : 0;
     ctx->main_cta_cap = (ov_bwd || ov_fwd) ? (mc > 0 ? mc : auto_cap) : 0;
   }
@@ -718,8 +699,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
                                stream_of(step_t, SK_X, hp, rank)));
     }
   }
-  const char* e_pp = getenv("RAU_PREPACK");   // =0: pack each weight shadow at its first use (A/B switch)
-  if (prep_aux && ctx->precision != RAU_PREC_F32 && hop_rows_path(ctx, cfg) && rows_path_enabled() && !(e_pp && atoi(e_pp) == 0)) {
+  if (prep_aux && ctx->precision != RAU_PREC_F32 && hop_rows_path(ctx, cfg) && rows_path_enabled()) {
     // the bf16 (hi, lo) shadows of the weights the chain's products read: packed here, next to the encoder, instead of
     // inline at their first use on the chain (the per-epoch cache makes the later calls no-ops)
     const bool x3 = prec_x3(ctx);
@@ -771,8 +751,8 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     ctx->rows_cta_cap = ctx->side_ctas_fwd;
     int rc = RAU_OK;
     // drawn feature masks: the feature pack of all hops in one launch (the fp32 features are read once, not nHop times)
-    const char* e_xh = getenv("RAU_XPREP_HOPS");   // =0: one pack launch per hop (same bits; tests compare the two)
-    bool all_philox = train && cfg->p_x > 0 && nHop > 1 && nHop < 65536 && S <= 200 && !(e_xh && atoi(e_xh) == 0);   // (S: its smem slabs)
+    // (RAU_XPREP_HOPS=0: one pack launch per hop -- same bits; a test compares the two)
+    bool all_philox = train && cfg->p_x > 0 && nHop > 1 && nHop < 65536 && S <= 200 && ctx->tune.xprep_hops != 0;   // (S: its smem slabs)
     for (int hp = 0; hp < nHop; ++hp) all_philox = all_philox && sv[hp].x_philox;
     if (all_philox) {
       rc = k_xprep_rows_hops(ctx, bt->feats, B, cfg->C, S, nHop, drop_scale(cfg->p_x), sv[0].Xd_hi,
@@ -826,12 +806,8 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     g2.Ar_hi = dup.hi; g2.Ar_lo = dup.lo; g2.Ar_ld = dup.ld;
     return rau_contract(ctx, g2);
   };
-  cudaEvent_t head_early_done = nullptr;
-  // RAU_HEAD_EARLY=1: head backward of hops 0 .. nHop-2 on the aux stream during the last hop's forward and the logging losses
-  // on the side stream.  Measured 1 % SLOWER in three A/B pairs on one box (4.87 vs 4.81 ms: the extra launches contend
-  // with the last hop's chain), so the whole head backward stays between the two unrolls by default.
-  const char* e_he = getenv("RAU_HEAD_EARLY");
-  const bool head_early_on = e_he && atoi(e_he) != 0;
+  // (running the head backward of hops 0 .. nHop-2 during the last hop's forward measured 1 % SLOWER -- 4.87 vs 4.81 ms: the
+  // extra launches contend with the last hop's chain -- so the whole head backward stays between the two unrolls)
   for (int hp = 0; hp < nHop; ++hp) {
     RAU_TRY(hop_forward(ctx, cfg, B, P, en.rnn_out, bt->feats, c_all + (size_t)hp * B * H, h_all + (size_t)hp * B * H, train,
                         sv[hp], scores + (size_t)hp * B * N, dop + (size_t)hp * B, att + (size_t)hp * B * S,
@@ -848,20 +824,6 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     if (ctx->phases == 2) rau_phase_mark(ctx, "hop head + criterion done");
     ctx->stream = chain;
     RAU_TRY(rc_ce);
-    if (ov_head && hp == nHop - 2 && ctx->aux != nullptr && nHop >= 2 && head_early_on) {
-      // dscore of hops 0 .. nHop-2 is final on the side stream: their head backward runs on the aux stream while the last
-      // hop's forward is still on the chain, so only the last hop's share sits between the two unrolls
-      cudaEvent_t ev = rau_side_event(ctx);
-      head_early_done = rau_side_event(ctx);
-      RAU_REQUIRE(ev != nullptr && head_early_done != nullptr, "cudaEventCreate failed");
-      RAU_CHECK_CUDA(cudaEventRecord(ev, ctx->side));
-      RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->aux, ev, 0));
-      ctx->stream = ctx->aux;
-      const int rc_h = head_backward(0, nHop - 1);
-      ctx->stream = chain;
-      RAU_TRY(rc_h);
-      RAU_CHECK_CUDA(cudaEventRecord(head_early_done, ctx->aux));
-    }
   }
   if (ov_head) {   // scores, do_pred, losses and dscore of every hop are complete before the merge and the backward unroll
     cudaEvent_t ev = rau_side_event(ctx);
@@ -874,7 +836,6 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   // pass reads them, so with the heads on the side stream they stay there (behind the event the chain just waited for)
   {
     cudaStream_t chain = ctx->stream;
-    if (ov_head && head_early_on) ctx->stream = ctx->side;
     const int rc_m = k_merge_preds(ctx, nHop, B, N, S, scores, dop, nullptr, bt->labels, ans, 0, 1.0f / Bg, loss + nHop, loss_dp,
                                    ans + (size_t)nHop * B, nullptr, nullptr, nullptr, nullptr);
     ctx->stream = chain;
@@ -889,12 +850,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   // The answer head's backward needs forward results only: du = drop'(dscore Ws) and Wo^T du of every hop in two products
   // over nHop*B rows before the unroll (dscore already carries the hop mask and 1/B_global)
   ARENA(st_dqt, float, "stack.dqt", (size_t)nHop * B * Q);
-  if (head_early_done) {   // hops 0 .. nHop-2 were done on the aux stream during the last hop's forward: only the last hop is left
-    RAU_TRY(head_backward(nHop - 1, 1));
-    RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, head_early_done, 0));
-  } else {
-    RAU_TRY(head_backward(0, nHop));
-  }
+  RAU_TRY(head_backward(0, nHop));
   const int main_cap_saved = ctx->main_cta_cap;
   if (ov_bwd && ctx->side_ctas_bwd > 0 && ctx->sm_count - ctx->side_ctas_bwd >= 16) ctx->main_cta_cap = ctx->sm_count - ctx->side_ctas_bwd;
   // the attention backward's atomic accumulators of every hop, cleared at once (not two memsets inside every hop's chain)
@@ -1088,11 +1044,8 @@ static int train_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
                         hp->h1, hp->h2, opt_state ? opt_state[g][0] : nullptr, opt_state ? opt_state[g][1] : nullptr, 1,
                         (out && out->norms) ? out->norms + g : nullptr, g);
   };
-  // RAU_EARLY_TAIL=0 keeps the whole tail behind the join (A/B switch)
-  const char* e_et = getenv("RAU_EARLY_TAIL");
   ctx->early_tail_done = nullptr;
-  if (!(e_et && atoi(e_et) == 0))
-    ctx->early_tail = [&]() -> int {   // (called by feval_enqueue with ctx->stream = aux, once group 2's gradients are final)
+  ctx->early_tail = [&]() -> int {   // (called by feval_enqueue with ctx->stream = aux, once group 2's gradients are final)
       if (dp) RAU_TRY(rau_allreduce_internal(ctx, grads[2], rau_group_size(cfg, 2)));
       return finish_group(2);
     };

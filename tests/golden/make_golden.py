@@ -82,7 +82,104 @@ def cells_fixture():
     print("cells_toy.npz")
 
 
+def digest(a, k=24):
+    """a tensor's fingerprint in a fixture that must stay small: sum, l2 norm, max |.|, and k evenly strided entries"""
+    a = np.asarray(a, dtype=np.float64).ravel()
+    idx = np.linspace(0, a.size - 1, min(k, a.size)).astype(np.int64)
+    return np.concatenate([[a.sum(), np.linalg.norm(a), np.abs(a).max()], a[idx]])
+
+
+def hop_fixture(name, C, seed):
+    """SURVEY 8c `rau_hop_{C512,C2048}`: ONE answering unit at the reference's dimensions (M 512, A 256, H 512, S 196; a
+    64-way head and batch 2 keep it small), forward and backward with explicit upstream gradients.  Inputs and weights
+    are regenerated from the seeds (float32-rounded, as the GPU sees them); outputs are stored in full, gradients as digests."""
+    cfg = O.RauConfig(V=10, C=C, N=64, nHop=1)
+    B = 2
+    rng = np.random.default_rng(seed)
+    f32 = lambda a: np.asarray(a, np.float32).astype(np.float64)
+    pm = f32(rng.uniform(-0.08, 0.08, O.group_size(cfg, "mult")))
+    Pm = O.views(cfg, "mult", pm)
+    q, X = f32(rng.standard_normal((B, cfg.Q))), f32(np.maximum(rng.standard_normal((B, C, cfg.S)), 0))
+    c, h = f32(rng.standard_normal((B, cfg.H)) * 0.5), f32(np.tanh(rng.standard_normal((B, cfg.H))))
+    mk = dict(q=(rng.random((B, cfg.Q)) >= 0.5).astype(np.uint8), X=(rng.random((B, C, cfg.S)) >= 0.5).astype(np.uint8),
+              m=(rng.random((B, cfg.M)) >= 0.5).astype(np.uint8))
+    score, dop, p, c2, h2, cache = O.hop_fwd(Pm, cfg, q, X, c, h, mk)
+    ups = [f32(rng.standard_normal(t.shape) * s) for t, s in ((score, 0.01), (dop, 0.01), (p, 0.01), (c2, 0.01), (h2, 0.01))]
+    gflat = np.zeros(pm.size)
+    dq, _, dc, dh = O.hop_bwd(Pm, O.views(cfg, "mult", gflat), cfg, cache, *ups)
+    out = dict(C=C, B=B, seed=seed, N=cfg.N, score=score, do_pred=dop, p=p, c2=c2, h2=h2, dq=digest(dq, 64), dc=dc, dh=dh)
+    for n_, v in O.views(cfg, "mult", gflat).items():
+        out[f"g_{n_}"] = digest(v)
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, float(np.abs(score).max()), float(np.linalg.norm(gflat)))
+
+
+def hop_fixture_inputs(C, seed):
+    """the inputs of hop_fixture again (tests regenerate them; the draw order is the generator's)"""
+    cfg = O.RauConfig(V=10, C=C, N=64, nHop=1)
+    B = 2
+    rng = np.random.default_rng(seed)
+    f32 = lambda a: np.asarray(a, np.float32).astype(np.float64)
+    pm = f32(rng.uniform(-0.08, 0.08, O.group_size(cfg, "mult")))
+    q, X = f32(rng.standard_normal((B, cfg.Q))), f32(np.maximum(rng.standard_normal((B, C, cfg.S)), 0))
+    c, h = f32(rng.standard_normal((B, cfg.H)) * 0.5), f32(np.tanh(rng.standard_normal((B, cfg.H))))
+    mk = dict(q=(rng.random((B, cfg.Q)) >= 0.5).astype(np.uint8), X=(rng.random((B, C, cfg.S)) >= 0.5).astype(np.uint8),
+              m=(rng.random((B, cfg.M)) >= 0.5).astype(np.uint8))
+    shapes = [(B, cfg.N), (B,), (B, cfg.S), (B, cfg.H), (B, cfg.H)]
+    ups = [f32(rng.standard_normal(s) * 0.01) for s in shapes]
+    return cfg, pm, q, X, c, h, mk, ups
+
+
+def encoder_fixture():
+    """SURVEY 8c `encoder_varlen`: the question encoder (F:460-479 / F:600-615) on ragged lengths incl. 1 and T, with an
+    explicit gradient into rnn_out."""
+    cfg = O.RauConfig(**dict(TOY, T=7))
+    B = 6
+    rng = np.random.default_rng(77)
+    params = O.init_params(cfg, seed=78)
+    x_len = np.array([1, 7, 3, 7, 2, 5])
+    x = rng.integers(2, cfg.V + 1, (cfg.T, B))
+    for b in range(B):
+        x[x_len[b]:, b] = 1
+    masks = dict(embed=(rng.random((cfg.T, B, cfg.embed)) >= 0.5).astype(np.float64),
+                 rnn=(rng.random((cfg.T, B, cfg.Hq)) >= 0.5).astype(np.float64))
+    Pe, Pr = O.views(cfg, "embed", params["embed"]), O.views(cfg, "rnn", params["rnn"])
+    rnn_out, caches = O.encoder_fwd(Pe, Pr, cfg, x, x_len, masks)
+    dq = rng.standard_normal(rnn_out.shape)
+    gE, gR = np.zeros_like(params["embed"]), np.zeros_like(params["rnn"])
+    O.encoder_bwd(Pr, O.views(cfg, "embed", gE), O.views(cfg, "rnn", gR), cfg, x_len, caches, dq)
+    np.savez_compressed(os.path.join(HERE, "encoder_varlen.npz"), cfg=np.array([dict(TOY, T=7)[k] for k in sorted(TOY)]),
+                        cfg_keys=np.array(sorted(TOY)), p_embed=params["embed"], p_rnn=params["rnn"], x=x, x_len=x_len,
+                        mask_embed=masks["embed"].astype(np.uint8), mask_rnn=masks["rnn"].astype(np.uint8), rnn_out=rnn_out,
+                        dq=dq, g_embed=gE, g_rnn=gR)
+    print("encoder_varlen.npz", float(np.linalg.norm(gR)))
+
+
+def noise_clip_fixture():
+    """SURVEY 8c `noise_clip`: F:617-648 on three small groups -- one far above the clip threshold, one just above, one below."""
+    cfg = O.RauConfig(**TOY)
+    rng = np.random.default_rng(91)
+    sizes = dict(embed=700, rnn=1300, mult=900)
+    scale = dict(embed=1.0, rnn=0.1 / np.sqrt(1300) * 1.05, mult=1e-4)
+    out = dict(step_t=np.array(4))
+    for g in O.GROUPS:
+        grad = rng.standard_normal(sizes[g]) * scale[g]
+        noise = rng.standard_normal(sizes[g]) * O.noise_std(cfg, 4) * 1e-3
+        clipped = grad.copy()
+        n = O.noise_and_clip(cfg, clipped, noise)
+        out.update({f"grad_{g}": grad, f"noise_{g}": noise, f"out_{g}": clipped, f"norm_{g}": np.array(n)})
+    np.savez_compressed(os.path.join(HERE, "noise_clip.npz"), **out)
+    print("noise_clip.npz", {g: float(out[f"norm_{g}"]) for g in O.GROUPS})
+
+
 if __name__ == "__main__":
     step_fixture("step_toy_adam.npz", TOY, B=3, seed=123, optim="adam")
     step_fixture("step_toy_rmsprop.npz", dict(TOY, nHop=1), B=4, seed=321, optim="rmsprop")
     cells_fixture()
+    # SURVEY.md 8c's list
+    hop_fixture("rau_hop_C512.npz", 512, seed=512)
+    hop_fixture("rau_hop_C2048.npz", 2048, seed=2048)
+    for nh in (1, 3, 8):
+        step_fixture(f"joint_step_nHop{nh}.npz", dict(TOY, nHop=nh), B=4, seed=1000 + nh, optim="adam")
+    encoder_fixture()
+    noise_clip_fixture()

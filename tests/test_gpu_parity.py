@@ -185,6 +185,42 @@ def test_noise_clip_and_every_optimizer(R, ctx):
         assert rel_err(xl.cpu().numpy(), xr) <= 1e-5, name
 
 
+def test_noise_follows_the_callers_iteration_and_adam_keeps_its_own_count(R):
+    """the reference's noise variance uses the `it` handed to feval, eta / ((it + 1) gamma) (F:617-618), while
+    adam's bias correction uses the optimizer state's own counter (OU:79-83).  One rau_train_step at it = 41 with opt_t = 3:
+    the drawn noise has the std of it = 41, the parameter step the size of adam's t = 3."""
+    import torch
+    from rau_vqa_b200 import core
+    cfg = small_cfg()
+    lc = lib_cfg(cfg)
+    c = R.Context(0, seed=3)
+    params = O.init_params(cfg, seed=83)
+    X, x, x_len, y = O.synth_batch(cfg, 4, seed=84, min_len=1)
+    P = [dev(params[g]) for g in O.GROUPS]
+    G = [torch.zeros_like(p) for p in P]
+    ST = [[torch.zeros_like(p), torch.zeros_like(p)] for p in P]
+    out = R.StepBuffers(lc, 4, P[0].device)
+    it, opt_t, eta, gamma, lr = 41, 3, 0.01, 0.55, 1e-3
+    # gradients are ~1e-2 at most here, the noise std at it = 41 is 0.0208: clip off, so g = grad + noise stays in G
+    R.train_step(c, lc, P, G, ST, dev(X), dev(x), dev(x_len), dev(y), out, optim=core.OPT_ADAM, lrs=(lr, lr, lr),
+                 hyper=(0.9, 0.999, 1e-8), eta=eta, gamma=gamma, clip=1e9, step_t=it, opt_t=opt_t, max_len=int(x_len.max()))
+    c.sync()
+    want_std = np.sqrt(eta / ((it + 1) * gamma))
+    ge = G[0].cpu().numpy()                     # the embedding gradient is zero on every row the batch does not touch
+    untouched = np.ones(cfg.V, bool)
+    untouched[np.unique(x.astype(np.int64)) - 1] = False
+    noise = ge.reshape(cfg.V, cfg.embed)[untouched]
+    assert noise.std() == pytest.approx(want_std, rel=0.08), (noise.std(), want_std)
+    # first adam step from zero state: m = (1-b1) g, v = (1-b2) g^2 -> step = lr_t (1-b1) g / (sqrt(1-b2) |g| + eps)
+    lr_t = lr * np.sqrt(1 - 0.999 ** opt_t) / (1 - 0.9 ** opt_t)
+    delta = (P[0].cpu().numpy() - params["embed"].astype(np.float32)).reshape(cfg.V, cfg.embed)[untouched]
+    g = noise
+    want = -lr_t * 0.1 * g / (np.sqrt(0.001) * np.abs(g) + 1e-8)
+    big = np.abs(g) > 1e-4
+    np.testing.assert_allclose(delta[big], want[big], rtol=2e-3)
+    c.close()
+
+
 def test_predict_matches_oracle_and_argmax_is_exact(R, ctx):
     cfg = small_cfg(nHop=3)
     lc = lib_cfg(cfg)
@@ -298,12 +334,12 @@ def test_all_hops_feature_pack_draws_the_same_masks(R):
     assert np.abs(res[0][0]["mult"]).max() > 0
 
 
-@pytest.mark.parametrize("Hq,B,env", [(64, 130, {}), (128, 7, {}), (256, 130, {"RAU_LSTM_SEQ_BWD": "1"}),
+@pytest.mark.parametrize("Hq,B,env", [(64, 130, {}), (128, 7, {}), (256, 130, {"RAU_ENC_BWD_WAVE": "0"}),
                                       (64, 130, {"RAU_LSTM_SEQ": "0"})])
 def test_persistent_encoder_recurrence(R, Hq, B, env):
-    """The persistent recurrence kernels of the question encoder (lstm_seq_kernel; lstm_seq_bwd_kernel when opted in)
-    against the oracle: two row tiles with a ragged second tile, ragged question lengths, several CTAs per row tile that
-    exchange h_t / dh_t through global memory; and the unrolled per-step form for comparison."""
+    """The persistent recurrence kernel of the question encoder (lstm_seq_kernel) and the two-stream wavefront of its backward
+    pass against the oracle: two row tiles with a ragged second tile, ragged question lengths, several CTAs per row tile that
+    exchange h_t through global memory; and the unrolled per-step / layer-after-layer forms for comparison."""
     import os
     from rau_vqa_b200 import core
     cfg = small_cfg(Hq=Hq, embed=16, T=6, nHop=1)
@@ -326,11 +362,12 @@ def test_persistent_encoder_recurrence(R, Hq, B, env):
                 os.environ[k] = v
 
 
-@pytest.mark.parametrize("env", [{"RAU_ATTN_FUSED": "1"}, {"RAU_HEAD_EARLY": "1"}, {"RAU_MEM_AUX": "0", "RAU_PREPACK": "0"},
-                                 {"RAU_OVERLAP": "0"}])
+@pytest.mark.parametrize("env", [{"RAU_OVERLAP": "0"}, {"RAU_OVERLAP": "1"}, {"RAU_ENC_BWD_WAVE": "0"}, {"RAU_XPREP_HOPS": "0"},
+                                 {"RAU_CG2": "0", "RAU_TANH_EW": "8"}])
 def test_opt_in_schedules_match_oracle(R, env):
-    """The alternative schedules kept behind switches (fused content logits, early head backward, no aux-stream work, a
-    single stream) compute the same step: Ours_SS-shaped step against the oracle."""
+    """The alternative schedules kept behind switches (one stream, backward products only on the side stream, encoder
+    backward layer after layer, per-hop feature packs, no CTA pairs / 8 epilogue warps) compute the same step: Ours_SS-shaped
+    step against the oracle."""
     import os
     from rau_vqa_b200 import core
     cfg = O.RauConfig(V=2000, C=512, nHop=2, N=2000)
@@ -375,7 +412,7 @@ def test_full_size_three_stream_schedule_equals_single_stream(R):
     tok, lens_d, y = dev(tok), dev(lens), dev(rng.integers(1, cfg.N + 1, B))
     gen = torch.Generator(device="cpu").manual_seed(9)
     P0 = [(torch.rand(cfg.group_size(g), generator=gen) * 0.16 - 0.08) for g in range(3)]
-    single = {"RAU_OVERLAP": "0", "RAU_GRAPH": "0", "RAU_LSTM_SEQ": "0", "RAU_XPREP_HOPS": "0", "RAU_MEM_AUX": "0", "RAU_PREPACK": "0"}
+    single = {"RAU_OVERLAP": "0", "RAU_GRAPH": "0", "RAU_LSTM_SEQ": "0", "RAU_XPREP_HOPS": "0", "RAU_ENC_BWD_WAVE": "0"}
     res = []
     for env in ({}, single):
         old = {k: os.environ.get(k) for k in env}
@@ -409,3 +446,74 @@ def test_full_size_three_stream_schedule_equals_single_stream(R):
             np.testing.assert_allclose(l, ref_l, rtol=2e-5)
             for k in range(3):
                 assert rel_err(g[k], ref_g[k]) <= 5e-5, k
+
+
+@pytest.mark.parametrize("name", ["joint_step_nHop1.npz", "joint_step_nHop3.npz", "joint_step_nHop8.npz"])
+def test_joint_step_fixtures_on_the_gpu(R, ctx, name):
+    """SURVEY 8c joint_step_{nHop1,3,8}: feval -> explicit noise -> clip -> adam against the committed fixtures."""
+    test_train_step_matches_golden_fixture(R, ctx, name)
+
+
+@pytest.mark.parametrize("C", [512, 2048])
+def test_hop_fixture_at_reference_dims_on_the_gpu(R, C):
+    """SURVEY 8c rau_hop_{C512,C2048} through the module-level ABI (rau_hop_fwd / rau_hop_bwd, the rows engine): outputs in
+    full, gradients through the fixture's digests (sum, norm, max, strided samples), all relative to the tensor's max."""
+    import importlib.util
+    import os
+    import torch
+    from helpers import GOLDEN
+    from rau_vqa_b200.model.RAU import Multimodal
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    z = np.load(os.path.join(GOLDEN, f"rau_hop_C{C}.npz"))
+    cfg, pm, q, X, c, h, mk, ups = mg.hop_fixture_inputs(C, int(z["seed"]))
+    lc = lib_cfg(cfg)
+    mod = Multimodal(lc).cuda()
+    flat, gflat = mod.getParameters()
+    flat.copy_(dev(pm))
+    mod.masks = dict(q=dev(mk["q"]), x=dev(mk["X"]), m=dev(mk["m"]))
+    mod.training()
+    inp = [dev(q), dev(X), dev(c), dev(h)]
+    out = mod.forward(inp)
+    for got, key in zip(out, ("score", "do_pred", "p", "c2", "h2")):
+        assert rel_err(got.cpu().numpy(), z[key]) <= TOL, key
+    gi = mod.backward(inp, [dev(u) for u in ups])
+    assert rel_err(gi[2].cpu().numpy(), z["dc"]) <= TOL and rel_err(gi[3].cpu().numpy(), z["dh"]) <= TOL
+    got_g = O.views(cfg, "mult", gflat.cpu().numpy().astype(np.float64))
+    gmax = max(float(z[f"g_{n}"][2]) for n in got_g)
+    for n, v in got_g.items():
+        d, ref = mg.digest(v), z[f"g_{n}"]
+        scale = max(float(ref[2]), 1e-30)          # the tensor's max |.|
+        # strided samples and the max on the tensor's own scale; the sum over up to a million entries on sqrt(n) * max
+        assert np.abs(d[2:] - ref[2:]).max() <= TOL * scale, n
+        assert abs(d[1] - ref[1]) <= TOL * max(float(ref[1]), 1e-30), n
+        assert abs(d[0] - ref[0]) <= TOL * scale * np.sqrt(v.size), n
+    torch.cuda.synchronize()
+
+
+def test_noise_clip_fixture_on_the_gpu(R):
+    import os
+    from helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "noise_clip.npz"))
+    # rau_noise_clip works on the three flat groups of a configuration: pick one whose group sizes cover the fixture's
+    # vectors and embed them at the front (the rest stays zero and adds nothing to the norms)
+    cfg = small_cfg(V=64)
+    lc = lib_cfg(cfg)
+    c = R.Context(0)
+    G, NZ = [], []
+    for g in O.GROUPS:
+        n = O.group_size(cfg, g)
+        a, b = np.zeros(n), np.zeros(n)
+        k = z[f"grad_{g}"].size
+        assert k <= n
+        a[:k], b[:k] = z[f"grad_{g}"], z[f"noise_{g}"]
+        G.append(dev(a)); NZ.append(dev(b))
+    norms = dev(np.zeros(3))
+    R.noise_clip(c, lc, G, int(z["step_t"]), 0.01, 0.55, 0.1, noise=NZ, norms=norms)
+    c.sync()
+    for i, g in enumerate(O.GROUPS):
+        k = z[f"grad_{g}"].size
+        assert norms[i].item() == pytest.approx(float(z[f"norm_{g}"]), rel=1e-5)
+        assert rel_err(G[i].cpu().numpy()[:k], z[f"out_{g}"]) <= 1e-5
+    c.close()
