@@ -485,9 +485,11 @@ def test_hop_fixture_at_reference_dims_on_the_gpu(R, C):
     for n, v in got_g.items():
         d, ref = mg.digest(v), z[f"g_{n}"]
         scale = max(float(ref[2]), 1e-30)          # the tensor's max |.|
+        if n == "bs":                              # sum_s ds_s = 0 by the softmax's shift invariance: rounding noise only
+            scale = gmax
         # strided samples and the max on the tensor's own scale; the sum over up to a million entries on sqrt(n) * max
         assert np.abs(d[2:] - ref[2:]).max() <= TOL * scale, n
-        assert abs(d[1] - ref[1]) <= TOL * max(float(ref[1]), 1e-30), n
+        assert abs(d[1] - ref[1]) <= TOL * max(float(ref[1]), scale), n
         assert abs(d[0] - ref[0]) <= TOL * scale * np.sqrt(v.size), n
     torch.cuda.synchronize()
 
