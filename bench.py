@@ -289,7 +289,7 @@ class Runner:
         loss_host = torch.empty(self.cfg.nHop + 2, dtype=torch.float32).pin_memory()
         state = {"submitted": -1}
 
-        def step(i):
+        def step(i, last=False):
             if state["submitted"] < i:
                 fd.submit(i % 2)
                 state["submitted"] = i
@@ -297,15 +297,16 @@ class Runner:
             self.it += 1
             F.train_step_batch(self.ctx, self.cfg, self.P, self.G, self.ST, b, self.out, step_t=self.it, opt_t=self.it)
             fd.release(i % 2)
-            fd.submit((i + 1) % 2)      # overlaps with this step's compute (waits for the slot's previous reader on the device)
-            state["submitted"] = i + 1
+            if not last:                # the upload of the NEXT step's batch overlaps with this step's compute (a K-step run
+                fd.submit((i + 1) % 2)  # uploads exactly K batches: none is prefetched behind the last step)
+                state["submitted"] = i + 1
             loss_host.copy_(self.out.loss, non_blocking=True)
 
         for i in range(8):              # both slots seen often enough to be captured
-            step(i)
+            step(i, last=i == 7)
         torch.cuda.synchronize()
         state["submitted"] = -1
-        ms = self.timed(step, steps)
+        ms = self.timed(lambda i: step(i, last=i == steps - 1), steps)
         torch.cuda.synchronize()
         h2d, d2h = fd.bytes_per_batch, loss_host.numel() * 4
         fd.close()

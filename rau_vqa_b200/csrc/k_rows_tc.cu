@@ -1891,9 +1891,18 @@ int k_attn_rows_score(rau_ctx* ctx, int B, int A, int S, const float* Z, const f
   RAU_REQUIRE(A % 4 == 0, "k_attn_rows_score: A=%d", A);
   const int R = B * S;
   int grid = (R + 31) / 32;
-  {   // one resident wave (6 CTAs of 256 threads per SM): a warp then walks several batches of 4 rows
-    const int one_wave = ctx->sm_count * 6;
-    if (grid > one_wave) grid = (grid + 1) / 2 <= one_wave ? (grid + 1) / 2 : one_wave;
+  {   // exactly one resident wave (the occupancy the compiler's register count allows: 56 registers -> 4 CTAs per SM, not
+      // the 6 an earlier cut assumed, which left a 0.32-wave tail): a warp then walks several batches of 4 rows
+    static int per_sm[2] = {0, 0};
+    const int v = fast_tanh ? 1 : 0;
+    if (per_sm[v] == 0) {
+      int n = 0;
+      cudaError_t e = v ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, attn_rows_score_kernel<1>, 256, 0)
+                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, attn_rows_score_kernel<0>, 256, 0);
+      per_sm[v] = (e == cudaSuccess && n > 0) ? n : 4;
+    }
+    const int one_wave = ctx->sm_count * per_sm[v];
+    if (grid > one_wave) grid = one_wave;
   }
   if (fast_tanh) RAU_LAUNCH_PDL(ctx->stream, (attn_rows_score_kernel<1>), grid, 256, 0, R, S, A, Z, qadd, ws, logit);
   else RAU_LAUNCH_PDL(ctx->stream, (attn_rows_score_kernel<0>), grid, 256, 0, R, S, A, Z, qadd, ws, logit);

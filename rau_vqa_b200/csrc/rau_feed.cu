@@ -178,8 +178,9 @@ int rau_feed_submit(rau_feed* f, int slot) {
   if (f->format == RAU_FEED_F16) {
     RAU_CHECK_CUDA(cudaMemcpyAsync(s.d_stage, s.h_feats, nfeat * 2, cudaMemcpyHostToDevice, f->copy));
     RAU_CHECK_CUDA(cudaEventRecord(s.copied, f->copy));
-    half_to_float_kernel<<<blocks_for((int64_t)nfeat / 2), 256, 0, f->copy>>>((const __half2*)s.d_stage, (int64_t)nfeat / 2,
-                                                                              (float2*)s.d_feats);
+    // a SMALL grid: the conversion has a whole training step to finish and must not take SMs from the step's persistent
+    // kernels (32 CTAs move the 154 MB of a 256-sample batch in well under a millisecond)
+    half_to_float_kernel<<<32, 256, 0, f->copy>>>((const __half2*)s.d_stage, (int64_t)nfeat / 2, (float2*)s.d_feats);
     f->ctx->launches++;
     RAU_CHECK_CUDA(cudaGetLastError());
   } else {
