@@ -315,6 +315,8 @@ static int encoder_backward(rau_ctx* ctx, const rau_config* cfg, const rau_batch
           g.A.hi = dG2_hi + (size_t)(t - 1) * gb; g.A.lo = dG2_lo ? dG2_lo + (size_t)(t - 1) * gb : nullptr; g.A.ld = G4;
           g.B.hi = Wcat_hi; g.B.lo = Wcat_lo; g.B.mn = 1; g.B.ld = 2 * Hq;
           g.epi = ROWS_EPI_RED; g.out_f = out2 + (size_t)t * B * 2 * Hq; g.ldo = 2 * Hq;
+          // (both lanes' split-K products size themselves for the chain's whole SM share: halving it per lane measured
+          // slower, 4.49 vs 4.38 ms -- the launch that comes first finishes sooner and the other fills in behind it)
           RAU_TRY(rows_gemm(ctx, g));
         }
         cudaEvent_t ev = rau_side_event(ctx);
@@ -571,6 +573,28 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     RAU_CHECK_CUDA(cudaEventRecord(fork0, ctx->stream));
   }
   bool side_used = false;
+  // Work the chain needs only LATER runs on an auxiliary stream next to it (forked here, joined by the returned event):
+  // sized for `cap` SMs so that it does not crowd the chain's own launches.
+  auto off_chain = [&](cudaStream_t aux, int cap, const std::function<int()>& fn, cudaEvent_t* done) -> int {
+    cudaEvent_t fork = rau_side_event(ctx);
+    *done = rau_side_event(ctx);
+    RAU_REQUIRE(fork != nullptr && *done != nullptr, "cudaEventCreate failed");
+    RAU_CHECK_CUDA(cudaEventRecord(fork, ctx->stream));
+    RAU_CHECK_CUDA(cudaStreamWaitEvent(aux, fork, 0));
+    cudaStream_t chain = ctx->stream;
+    const int cap_saved = ctx->main_cta_cap;
+    ctx->stream = aux;
+    if (cap > 0) ctx->main_cta_cap = cap;
+    const int rc = fn();
+    ctx->stream = chain;
+    ctx->main_cta_cap = cap_saved;
+    RAU_TRY(rc);
+    RAU_CHECK_CUDA(cudaEventRecord(*done, aux));
+    return RAU_OK;
+  };
+  // (only when every operand of the moved products has a producer-written packed twin and a pre-packed weight shadow: a
+  // product that packs an operand on demand does so into a scratch slot shared by all streams)
+  bool split_ok = (ov_fwd || ov_bwd) && ctx->aux != nullptr && ctx->aux2 != nullptr && nHop >= 2;
   Encoder en;
   RAU_TRY(encoder_alloc(ctx, cfg, B, &en));
   // The chain's first launches (masks + word embedding) go out before the side stream is released: the all-hops feature
@@ -699,7 +723,9 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
                                stream_of(step_t, SK_X, hp, rank)));
     }
   }
-  if (prep_aux && ctx->precision != RAU_PREC_F32 && hop_rows_path(ctx, cfg) && rows_path_enabled()) {
+  const bool prepacked = prep_aux && ctx->precision != RAU_PREC_F32 && hop_rows_path(ctx, cfg) && rows_path_enabled();
+  split_ok = split_ok && prepacked && pk_qd.hi && pk_dscore.hi && pk_du.hi && pk_dpre.hi && Q % 8 == 0 && M_ % 8 == 0 && H % 8 == 0;
+  if (prepacked) {
     // the bf16 (hi, lo) shadows of the weights the chain's products read: packed here, next to the encoder, instead of
     // inline at their first use on the chain (the per-epoch cache makes the later calls no-ops)
     const bool x3 = prec_x3(ctx);
@@ -779,15 +805,26 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   // Everything of the unroll that depends on the encoder state only is hoisted out of the per-hop chains: the q dropout
   // of every hop (one launch) and Wq drop_h(q) + bq of every hop (one [nHop*B, Q] x [Q, M] product).
   ARENA(st_qpre, float, "stack.qpre", (size_t)nHop * B * M_);
+  cudaEvent_t qpre_rest_done = nullptr;
   const int64_t bits_stride = (int64_t)(sv_bytes / 4);   // keep bits of consecutive hops are sv_bytes apart
   {
     const bool dq_ = train && cfg->p_q > 0;
     RAU_TRY(k_dropout_hops(ctx, en.rnn_out, (int64_t)B * Q, nHop, dq_ ? sv[0].qbits : nullptr, bits_stride, drop_scale(cfg->p_q),
                            st_qd, pk_qd.hi, prec_x3(ctx) ? pk_qd.lo : nullptr));
-    SimtGemm g = lin_fwd(nHop * B, M_, Q, st_qd, Q, P.Wq, st_qpre, M_);
-    g.bias_n = P.bq;
-    g.Ar_hi = pk_qd.hi; g.Ar_lo = pk_qd.lo; g.Ar_ld = pk_qd.ld;
-    RAU_TRY(rau_contract(ctx, g));
+    auto qpre_rows = [&](int h0, int nh) -> int {   // Wq drop_h(q) + bq for hops h0 .. h0+nh-1
+      const size_t r0 = (size_t)h0 * B;
+      const PK qp = slice(pk_qd, r0);
+      SimtGemm g = lin_fwd(nh * B, M_, Q, st_qd + r0 * Q, Q, P.Wq, st_qpre + r0 * M_, M_);
+      g.bias_n = P.bq;
+      g.Ar_hi = qp.hi; g.Ar_lo = qp.lo; g.Ar_ld = qp.ld;
+      return rau_contract(ctx, g);
+    };
+    if (split_ok) {   // the first hop needs only its own slice: the other hops' product runs next to the first hop's chain
+      RAU_TRY(off_chain(ctx->aux2, 32, [&]() { return qpre_rows(1, nHop - 1); }, &qpre_rest_done));
+      RAU_TRY(qpre_rows(0, 1));
+    } else {
+      RAU_TRY(qpre_rows(0, nHop));
+    }
     for (int hp = 0; hp < nHop; ++hp) sv[hp].qpre = st_qpre + (size_t)hp * B * M_;
   }
   // The answer head's backward needs forward results only: du = drop'(dscore Ws) and Wo^T du for a range of hops in two
@@ -809,6 +846,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   // (running the head backward of hops 0 .. nHop-2 during the last hop's forward measured 1 % SLOWER -- 4.87 vs 4.81 ms: the
   // extra launches contend with the last hop's chain -- so the whole head backward stays between the two unrolls)
   for (int hp = 0; hp < nHop; ++hp) {
+    if (hp == 1 && qpre_rest_done) RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, qpre_rest_done, 0));
     RAU_TRY(hop_forward(ctx, cfg, B, P, en.rnn_out, bt->feats, c_all + (size_t)hp * B * H, h_all + (size_t)hp * B * H, train,
                         sv[hp], scores + (size_t)hp * B * N, dop + (size_t)hp * B, att + (size_t)hp * B * S,
                         c_all + (size_t)(hp + 1) * B * H, h_all + (size_t)(hp + 1) * B * H, &as[hp]));
@@ -850,14 +888,29 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   // The answer head's backward needs forward results only: du = drop'(dscore Ws) and Wo^T du of every hop in two products
   // over nHop*B rows before the unroll (dscore already carries the hop mask and 1/B_global)
   ARENA(st_dqt, float, "stack.dqt", (size_t)nHop * B * Q);
-  RAU_TRY(head_backward(0, nHop));
+  cudaEvent_t head_rest_done = nullptr;
+  if (split_ok) {   // the unroll starts at the last hop: the other hops' head backward runs next to its chain
+    RAU_TRY(off_chain(ctx->aux, 32, [&]() { return head_backward(0, nHop - 1); }, &head_rest_done));
+    RAU_TRY(head_backward(nHop - 1, 1));
+  } else {
+    RAU_TRY(head_backward(0, nHop));
+  }
   const int main_cap_saved = ctx->main_cta_cap;
   if (ov_bwd && ctx->side_ctas_bwd > 0 && ctx->sm_count - ctx->side_ctas_bwd >= 16) ctx->main_cta_cap = ctx->sm_count - ctx->side_ctas_bwd;
   // the attention backward's atomic accumulators of every hop, cleared at once (not two memsets inside every hop's chain)
   RAU_CHECK_CUDA(cudaMemsetAsync(st_dqa, 0, sizeof(float) * (size_t)nHop * B * A_, ctx->stream));
   RAU_CHECK_CUDA(cudaMemsetAsync(st_gwsp, 0, sizeof(float) * (size_t)nHop * B * A_, ctx->stream));
+  cudaEvent_t dqt_done = nullptr;
+  auto dqt_rows = [&](int h0, int nh) -> int {   // (dpre_h Wq) for hops h0 .. h0+nh-1, before the dropout mask of q
+    const size_t r0 = (size_t)h0 * B;
+    const PK dp_ = slice(pk_dpre, r0);
+    SimtGemm g = lin_dgrad(nh * B, M_, Q, st_dpre + r0 * M_, M_, P.Wq, st_dqt + r0 * Q, Q);
+    g.Ar_hi = dp_.hi; g.Ar_lo = dp_.lo; g.Ar_ld = dp_.ld;
+    return rau_contract(ctx, g);
+  };
   for (int hp = nHop - 1; hp >= 0; --hp) {
     const bool last = hp == nHop - 1;
+    if (hp == nHop - 2 && head_rest_done) RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, head_rest_done, 0));
     const float* dc_in = last ? nullptr : dcs + (size_t)((hp + 1) & 1) * B * H;
     const float* dh_in = last ? nullptr : dhs + (size_t)((hp + 1) & 1) * B * H;
     HopGrads hg;
@@ -872,15 +925,20 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
                          dscore + (size_t)hp * B * N, nullptr, nullptr, dc_in, dh_in, dq, last ? 0 : 1, nullptr,
                          dcs + (size_t)(hp & 1) * B * H, dhs + (size_t)(hp & 1) * B * H, &hg, &as[hp]));
     if (ov_bwd) side_used = true;
+    // this hop's share of dq = sum_h drop_h'(dpre_h Wq) is not needed before the unroll ends: next to the chain
+    if (split_ok && hp >= 1) RAU_TRY(off_chain(ctx->aux2, 32, [&]() { return dqt_rows(hp, 1); }, &dqt_done));
     if (ctx->phases == 2) {
       rau_phase_mark(ctx, "hop backward chain done");
       if (ov_bwd) { cudaStream_t c = ctx->stream; ctx->stream = ctx->side; rau_phase_mark(ctx, "hop backward products done"); ctx->stream = c; }
     }
   }
-  {   // dq = sum_h drop_h'(dpre_h Wq): one product over the stacked dpre, one masked sum over the hops
-    SimtGemm g = lin_dgrad(nHop * B, M_, Q, st_dpre, M_, P.Wq, st_dqt, Q);
-    g.Ar_hi = pk_dpre.hi; g.Ar_lo = pk_dpre.lo; g.Ar_ld = pk_dpre.ld;
-    RAU_TRY(rau_contract(ctx, g));
+  {   // dq = sum_h drop_h'(dpre_h Wq): the products over the stacked dpre, then one masked sum over the hops
+    if (split_ok) {
+      RAU_TRY(dqt_rows(0, 1));
+      if (dqt_done) RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, dqt_done, 0));   // (aux2 is in order: the last one covers all)
+    } else {
+      RAU_TRY(dqt_rows(0, nHop));
+    }
     const bool dq_ = train && cfg->p_q > 0;
     RAU_TRY(k_dropout_bwd_sum_hops(ctx, st_dqt, (int64_t)B * Q, nHop, dq_ ? sv[0].qbits : nullptr, bits_stride, drop_scale(cfg->p_q), dq));
   }
