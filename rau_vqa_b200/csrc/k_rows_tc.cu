@@ -76,8 +76,7 @@ struct RtParams {
   int f16;                         // the operands are fp16, not bf16 (single plane)
   int of16;                        // EPI_TANH / EPI_DY: the output is ONE fp16 plane (not bf16 hi [, lo])
   int af16;                        // EPI_DY: the saved activation (aux) is one fp16 plane
-  float gscale;                    // EPI_DY: power-of-two gradient scale carried by the OUTPUT dY
-  float accscale;                  // EPI_DY: gscale / (the scale the accumulator already carries through its A operand dZ)
+  float gscale;                    // EPI_DY: power-of-two gradient scale carried by the A operand dZ and by the output dY
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -225,10 +224,10 @@ __device__ __forceinline__ float rcp_ftz(float x) {
 }
 // tanh to ~1e-7 ABSOLUTE (bf16x3 mode): 1 - 2/(e^2|x| + 1).  Near zero the relative error grows, which is harmless here:
 // the result feeds contractions and (1 - y^2), both of which see the absolute error only.
+// (no |x| / copysign: e^{2x} -> 0 gives -1, -> inf gives rcp(inf) = 0 and +1, and the absolute error is the same either way)
 __device__ __forceinline__ float tanh_acc(float x) {
-  const float e = exp2f_ftz(2.8853900817779268f * fabsf(x));
-  const float t = 1.0f - 2.0f * rcp_ftz(e + 1.0f);
-  return copysignf(t, x);
+  const float e = exp2f_ftz(2.8853900817779268f * x);
+  return fmaf(-2.0f, rcp_ftz(e + 1.0f), 1.0f);
 }
 __device__ __forceinline__ float tanh_hw(float x) {
   float y;
@@ -248,11 +247,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 // hi = bf16(a), lo = bf16(a - hi) for a pair
+// (ONE packed conversion per pair for hi -- F2FP on the ALU pipe -- instead of two scalar F2F, which share the MUFU pipe with
+// the epilogues' ex2 / rcp: ncu showed the one-pass i_embed epilogue queueing on that pipe)
 __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-  __nv_bfloat162 h2 = __halves2bfloat162(ha, hb);
-  hi = *reinterpret_cast<uint32_t*>(&h2);
-  lo = pack_bf16x2(a - __bfloat162float(ha), b - __bfloat162float(hb));
+  hi = pack_bf16x2(a, b);   // low half = bf16(a), high half = bf16(b), round to nearest
+  lo = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
 }
 // fp16 pair, round-to-nearest, saturating (a scaled gradient that overflows becomes 65504, never inf)
 __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
@@ -701,9 +700,13 @@ __global__ void __launch_bounds__(32 * (EW + 3), 1) rows_gemm_kernel(const __gri
                 if (p.bias) t += __ldg(p.bias + n);
                 if (p.bias2) t += __ldg(p.bias2 + n);
                 if (p.addend) t += __ldg(p.addend + (long long)rr * p.ldadd + n);
-                if (p.addend2) t += __ldg(p.addend2 + (long long)rr * p.ldadd + n);
+                if (p.addend2 && p.act != 3) t += __ldg(p.addend2 + (long long)rr * p.ldadd + n);
               }
               v[k] = fmaf(v[k], p.alpha, t);
+              if (p.act == 3 && n < p.N) {   // tanh backward: times (1 - y^2), y = addend2
+                const float y = __ldg(p.addend2 + (long long)rr * p.ldadd + n);
+                v[k] *= fmaf(-y, y, 1.0f);
+              }
             }
           } else {
 #pragma unroll
@@ -712,9 +715,14 @@ __global__ void __launch_bounds__(32 * (EW + 3), 1) rows_gemm_kernel(const __gri
               if (p.bias) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nc) + k4); t.x += b4.x; t.y += b4.y; t.z += b4.z; t.w += b4.w; }
               if (p.bias2) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias2 + nc) + k4); t.x += b4.x; t.y += b4.y; t.z += b4.z; t.w += b4.w; }
               if (p.addend) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.addend + (long long)rr * p.ldadd + nc) + k4); t.x += b4.x; t.y += b4.y; t.z += b4.z; t.w += b4.w; }
-              if (p.addend2) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.addend2 + (long long)rr * p.ldadd + nc) + k4); t.x += b4.x; t.y += b4.y; t.z += b4.z; t.w += b4.w; }
+              if (p.addend2 && p.act != 3) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.addend2 + (long long)rr * p.ldadd + nc) + k4); t.x += b4.x; t.y += b4.y; t.z += b4.z; t.w += b4.w; }
               v[4 * k4] = fmaf(v[4 * k4], p.alpha, t.x); v[4 * k4 + 1] = fmaf(v[4 * k4 + 1], p.alpha, t.y);
               v[4 * k4 + 2] = fmaf(v[4 * k4 + 2], p.alpha, t.z); v[4 * k4 + 3] = fmaf(v[4 * k4 + 3], p.alpha, t.w);
+              if (p.act == 3) {   // tanh backward fused behind the product: times (1 - y^2), y = addend2 (the tanh's output)
+                const float4 y4 = __ldg(reinterpret_cast<const float4*>(p.addend2 + (long long)rr * p.ldadd + nc) + k4);
+                v[4 * k4] *= fmaf(-y4.x, y4.x, 1.0f); v[4 * k4 + 1] *= fmaf(-y4.y, y4.y, 1.0f);
+                v[4 * k4 + 2] *= fmaf(-y4.z, y4.z, 1.0f); v[4 * k4 + 3] *= fmaf(-y4.w, y4.w, 1.0f);
+              }
             }
           }
           if (p.act == 1) {
@@ -798,13 +806,16 @@ __global__ void __launch_bounds__(32 * (EW + 3), 1) rows_gemm_kernel(const __gri
               const float y0 = p.af16 ? hf_lo(hh[j]) : bf_lo(hh[j]) + bf_lo(ll[j]);
               const float y1 = p.af16 ? hf_hi(hh[j]) : bf_hi(hh[j]) + bf_hi(ll[j]);
               const int k = 8 * k8 + 2 * j;
-              const float g0 = fmaf(v[k], p.accscale, dd[2 * j] * rs) * (1.0f - y0 * y0);
-              const float g1 = fmaf(v[k + 1], p.accscale, dd[2 * j + 1] * rs) * (1.0f - y1 * y1);
-              v[k] = r_ok ? g0 : 0.0f;
-              v[k + 1] = r_ok ? g1 : 0.0f;
+              // (the accumulator carries the output's power-of-two scale through its A operand dZ; rs = p[r] * gscale)
+              v[k] = fmaf(dd[2 * j], rs, v[k]) * fmaf(-y0, y0, 1.0f);
+              v[k + 1] = fmaf(dd[2 * j + 1], rs, v[k + 1]) * fmaf(-y1, y1, 1.0f);
             }
           }
           __syncwarp();   // every lane has read its row before the next chunk overwrites the scratch
+          if (!r_ok) {    // rows past M (a ragged last tile only) contribute nothing to the column sums
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = 0.0f;
+          }
           if (p.of16) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) w0[k] = pack_f16x2(v[2 * k], v[2 * k + 1]);
@@ -1373,13 +1384,14 @@ __global__ void __launch_bounds__(256) attn_rows_dz_kernel(int S, int A, const f
     sg0 = fmaf(d, e.x, sg0); sg1 = fmaf(d, e.y, sg1); sg2 = fmaf(d, e.z, sg2); sg3 = fmaf(d, e.w, sg3);
     sz0 += z0; sz1 += z1; sz2 += z2; sz3 += z3;
     uint32_t h0, l0, h1, l1;
-    if (f16) {   // one fp16 plane, carried times gscale (the products that read it scale their fp32 results back)
+    // dZ is carried times gscale, a power of two (the products that read it scale their fp32 results back)
+    if (f16) {   // one fp16 plane
       reinterpret_cast<uint2*>(dZ_hi + (r0 + s) * A)[ng] =
           make_uint2(pack_f16x2(z0 * gscale, z1 * gscale), pack_f16x2(z2 * gscale, z3 * gscale));
       continue;
     }
-    split_pair(z0, z1, h0, l0);
-    split_pair(z2, z3, h1, l1);
+    split_pair(z0 * gscale, z1 * gscale, h0, l0);
+    split_pair(z2 * gscale, z3 * gscale, h1, l1);
     reinterpret_cast<uint2*>(dZ_hi + (r0 + s) * A)[ng] = make_uint2(h0, h1);
     if (dZ_lo) reinterpret_cast<uint2*>(dZ_lo + (r0 + s) * A)[ng] = make_uint2(l0, l1);
   }
@@ -1761,7 +1773,6 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   p.of16 = g.of16 ? 1 : 0;
   p.af16 = g.af16 ? 1 : 0;
   p.gscale = g.gscale;
-  p.accscale = g.accscale;
   RAU_REQUIRE(!(p.f16 && p.x3), "rows_gemm: fp16 operands are single-plane");
   RAU_REQUIRE(!(p.of16 && g.out_lo), "rows_gemm: an fp16 output is single-plane");
   // single-pass bf16: the result is rounded to bf16 anyway, MUFU.TANH (2^-11) is below that; fp16 keeps the accurate form

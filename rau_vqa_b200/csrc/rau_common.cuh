@@ -294,7 +294,7 @@ struct SimtGemm {
   const bf16 *Br_hi = nullptr, *Br_lo = nullptr; int64_t Br_ld = 0;
   int accumulate = 0;
   float alpha = 1.0f;
-  int act = 0;                     // 0 none, 1 tanh, 2 sigmoid
+  int act = 0;                     // 0 none, 1 tanh, 2 sigmoid; 3 (rows engine only) tanh backward: * (1 - addend2^2)
   int n_valid = -1;                // columns >= n_valid are written as 0 (spatial pad)
 };
 int simt_gemm(rau_ctx* ctx, const SimtGemm& g);

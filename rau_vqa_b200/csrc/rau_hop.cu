@@ -426,11 +426,29 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
     if (dG_twin) { g.Ar_hi = dG_pk.hi; g.Ar_lo = dG_pk.lo; g.Ar_ld = 4 * H; }
     RAU_TRY(rau_contract(ctx, g));
   }
-  {
+  // The gradient into the previous state, dh = dG Whh + ds Wm + dpre Wh, feeds nothing before the NEXT hop's cell backward:
+  // in the training step its three products form a lane of their own on the aux stream, each behind the event of its
+  // operand, and the chain keeps only what the next launch on it needs (every operand has a producer-written packed
+  // twin there, so no product packs into the scratch slots the chain's products use).
+  const bool dh_lane = hoisted && as && as->bwd_side && ctx->aux != nullptr && rows_path(ctx, cfg) && dG_twin && ds_pk.hi &&
+                       ds_pk.ld % 8 == 0 && dpre_pk.hi && dpre_pk.ld == M && H % 8 == 0;
+  cudaStream_t chain0 = ctx->stream;
+  auto on_lane = [&](const std::function<int()>& fn) -> int {   // run fn on the aux stream behind everything the chain enqueued so far
+    if (!dh_lane) return fn();
+    cudaEvent_t ev = rau_side_event(ctx);
+    RAU_REQUIRE(ev != nullptr, "cudaEventCreate failed");
+    RAU_CHECK_CUDA(cudaEventRecord(ev, chain0));
+    RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->aux, ev, 0));
+    ctx->stream = ctx->aux;
+    const int rc = fn();
+    ctx->stream = chain0;
+    return rc;
+  };
+  RAU_TRY(on_lane([&]() {
     SimtGemm g = lin_dgrad(B, 4 * H, H, dG, 4 * H, P.Whh, dh, H);
     if (dG_twin) { g.Ar_hi = dG_pk.hi; g.Ar_lo = dG_pk.lo; g.Ar_ld = 4 * H; }
-    RAU_TRY(rau_contract(ctx, g));
-  }
+    return rau_contract(ctx, g);
+  }));
   if (now) {
     RAU_TRY(rau_contract(ctx, lin_wgrad(B, 4 * H, M, dG, 4 * H, sv.j, M, G.Wx, 1.0f)));
     RAU_TRY(rau_contract(ctx, lin_wgrad(B, 4 * H, H, dG, 4 * H, h, H, G.Whh, 1.0f)));
@@ -464,16 +482,16 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   if (rows)
     RAU_TRY(k_attn_rows_bwd(ctx, B, M, A, S, sv.E, sv.I_hi, x3i ? sv.I_lo : nullptr, P.ws, sv.p, dp, dj, ds, dZ_hi, dZ_lo, dqa, gwsp,
                             ds_pk.hi, x3 ? ds_pk.lo : nullptr, (int)ds_pk.ld, sv.qatt, x3 ? 0 : 1,
-                            deferred ? deferred->acc_zeroed : 0, f16i, f16i ? gs : 1.0f));
+                            deferred ? deferred->acc_zeroed : 0, f16i, gs));
   else
     RAU_TRY(k_attn_bwd<float>(ctx, B, M, A, S, Sp, sv.E, sv.I, P.ws, sv.p, dp, dj, ds, nullptr, 0, dZ, dqa, nullptr, gwsp,
                               dZ_hi, dZ_lo));
-  {
+  RAU_TRY(on_lane([&]() {
     SimtGemm g = lin_dgrad(B, S, H, ds, S, P.Wm, dh, H);
     g.accumulate = 1;
     if (rows) { g.Ar_hi = ds_pk.hi; g.Ar_lo = ds_pk.lo; g.Ar_ld = ds_pk.ld; }   // (written by the rows attention backward)
-    RAU_TRY(rau_contract(ctx, g));
-  }
+    return rau_contract(ctx, g);
+  }));
   if (now) {
     RAU_TRY(rau_contract(ctx, lin_wgrad(B, S, H, ds, S, h, H, G.Wm, 1.0f)));
     RAU_TRY(k_colsum(ctx, ds, B, S, S, G.bm, 1));
@@ -502,7 +520,7 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
       g.A.hi = dZ_hi; g.A.lo = dZ_lo; g.A.ld = A;
       g.B.hi = Wa_h; g.B.lo = Wa_l; g.B.mn = 1; g.B.ld = M;
       g.epi = ROWS_EPI_DY; g.rowvec = dj; g.rowscale = sv.p; g.S = S;
-      g.f16 = f16i; g.af16 = f16i; g.of16 = fxi; g.gscale = gs; g.accscale = f16i ? 1.0f : gs; g.alpha = 1.0f / gs;
+      g.f16 = f16i; g.af16 = f16i; g.of16 = fxi; g.gscale = gs; g.alpha = 1.0f / gs;
       g.aux_hi = sv.I_hi; g.aux_lo = x3i ? sv.I_lo : nullptr; g.ldaux = M; g.colsum = G.bi;
       g.out_hi = dY_hi; g.out_lo = dY_lo; g.ldo = M;
       if ((side_rc = rows_gemm(ctx, g)) != RAU_OK) break;
@@ -512,7 +530,7 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
       g.M = A; g.N = M; g.K = R;
       g.A.hi = dZ_hi; g.A.lo = dZ_lo; g.A.mn = 1; g.A.ld = A;
       g.B.hi = sv.I_hi; g.B.lo = x3i ? sv.I_lo : nullptr; g.B.mn = 1; g.B.ld = M;
-      g.f16 = f16i; g.alpha = f16i ? 1.0f / gs : 1.0f;
+      g.f16 = f16i; g.alpha = 1.0f / gs;   // (dZ carries gs)
       if ((side_rc = rows_wgrad(ctx, g, G.Wa, M)) != RAU_OK) break;
     }
     if (side) {   // gWi += dY^T drop(X)^T (issued further down in the synchronous mode)
@@ -555,9 +573,13 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   }
   if (now) RAU_TRY(k_colsum(ctx, dqa, B, A, A, G.ba, 1));   // gba = sum_b sum_s dZ = sum_b dqa
   // dqf = dj + Wqa^T dqa ; gWqa += dqa (x) qf
+  const bool dpre_twin = dpre_pk.hi != nullptr && dpre_pk.ld == M;
+  // training step on the rows engine: the tanh backward of q_embed, dpre = dqf (1 - qf^2), is this product's epilogue
+  const bool fuse_tanh = dh_lane && dpre_twin && M % 32 == 0 && (long long)B * M * A >= rau_process_tuning().tc_min_work;
   {
-    SimtGemm g = lin_dgrad(B, A, M, dqa, A, P.Wqa, dqf, M);
+    SimtGemm g = lin_dgrad(B, A, M, dqa, A, P.Wqa, fuse_tanh ? dpre : dqf, M);
     g.addend = dj; g.sdm = M; g.sdn = 1;
+    if (fuse_tanh) { g.act = 3; g.addend2 = sv.qf; g.C_hi = dpre_pk.hi; g.C_lo = dpre_pk.lo; }
     RAU_TRY(rau_contract(ctx, g));
   }
   if (now) {
@@ -612,19 +634,25 @@ int hop_backward(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<const f
   }
   }
   // q_embed backward
-  const bool dpre_twin = dpre_pk.hi != nullptr && dpre_pk.ld == M;
-  RAU_TRY(k_tanh_bwd(ctx, dqf, sv.qf, (int64_t)B * M, dpre, dpre_twin ? dpre_pk.hi : nullptr, (dpre_twin && x3) ? dpre_pk.lo : nullptr));
+  if (!fuse_tanh)
+    RAU_TRY(k_tanh_bwd(ctx, dqf, sv.qf, (int64_t)B * M, dpre, dpre_twin ? dpre_pk.hi : nullptr, (dpre_twin && x3) ? dpre_pk.lo : nullptr));
   if (!hoisted) {
     SimtGemm g = lin_dgrad(B, M, Q, dpre, M, P.Wq, dqt, Q);
     if (dpre_twin) { g.Ar_hi = dpre_pk.hi; g.Ar_lo = dpre_pk.lo; g.Ar_ld = M; }
     RAU_TRY(rau_contract(ctx, g));
     RAU_TRY(k_dropout_bwd_acc(ctx, dqt, (int64_t)B * Q, qb, drop_scale(cfg->p_q), dq, dq_accumulate));
   }
-  {
+  RAU_TRY(on_lane([&]() {
     SimtGemm g = lin_dgrad(B, M, H, dpre, M, P.Wh, dh, H);
     g.accumulate = 1;
     if (dpre_twin) { g.Ar_hi = dpre_pk.hi; g.Ar_lo = dpre_pk.lo; g.Ar_ld = M; }
-    RAU_TRY(rau_contract(ctx, g));
+    return rau_contract(ctx, g);
+  }));
+  if (dh_lane) {   // the caller's next launch on the chain (the previous hop's cell backward) reads dh
+    cudaEvent_t ev = rau_side_event(ctx);
+    RAU_REQUIRE(ev != nullptr, "cudaEventCreate failed");
+    RAU_CHECK_CUDA(cudaEventRecord(ev, ctx->aux));
+    RAU_CHECK_CUDA(cudaStreamWaitEvent(chain0, ev, 0));
   }
   if (now) {
     RAU_TRY(rau_contract(ctx, lin_wgrad(B, M, Q, dpre, M, sv.qd, Q, G.Wq, 1.0f)));
@@ -1069,7 +1097,7 @@ int rau_sweep_attention(rau_ctx* ctx, const rau_config* cfg, int B, const float*
   // backward
   RAU_TRY(timed(RAU_SWEEP_BWD_DP_DZ, [&]() {
     return k_attn_rows_bwd(ctx, B, M, A, S, sv.E, sv.I_hi, x3i ? sv.I_lo : nullptr, P.ws, sv.p, dpin, dj, ds, dZ_hi, dZ_lo, dqa, gwsp,
-                           nullptr, nullptr, 0, qatt, x3 ? 0 : 1, 0, fi, fi ? gs : 1.0f);
+                           nullptr, nullptr, 0, qatt, x3 ? 0 : 1, 0, fi, gs);
   }));
   RAU_TRY(timed(RAU_SWEEP_DY, [&]() {
     RowsGemm g;
@@ -1077,7 +1105,7 @@ int rau_sweep_attention(rau_ctx* ctx, const rau_config* cfg, int B, const float*
     g.A.hi = dZ_hi; g.A.lo = dZ_lo; g.A.ld = A;
     g.B.hi = Wa_h; g.B.lo = Wa_l; g.B.mn = 1; g.B.ld = M;
     g.epi = ROWS_EPI_DY; g.rowvec = dj; g.rowscale = sv.p; g.S = S;
-    g.f16 = fi; g.af16 = fi; g.of16 = fx; g.gscale = gs; g.accscale = fi ? 1.0f : gs; g.alpha = 1.0f / gs;
+    g.f16 = fi; g.af16 = fi; g.of16 = fx; g.gscale = gs; g.alpha = 1.0f / gs;
     g.aux_hi = sv.I_hi; g.aux_lo = x3i ? sv.I_lo : nullptr; g.ldaux = M; g.colsum = gbi;
     g.out_hi = dY_hi; g.out_lo = dY_lo; g.ldo = M;
     return rows_gemm(ctx, g);
@@ -1087,7 +1115,7 @@ int rau_sweep_attention(rau_ctx* ctx, const rau_config* cfg, int B, const float*
     g.M = A; g.N = M; g.K = R;
     g.A.hi = dZ_hi; g.A.lo = dZ_lo; g.A.mn = 1; g.A.ld = A;
     g.B.hi = sv.I_hi; g.B.lo = x3i ? sv.I_lo : nullptr; g.B.mn = 1; g.B.ld = M;
-    g.f16 = fi; g.alpha = fi ? 1.0f / gs : 1.0f;
+    g.f16 = fi; g.alpha = 1.0f / gs;
     return rows_wgrad(ctx, g, gW, M);
   }));
   RAU_TRY(timed(RAU_SWEEP_GWI, [&]() {

@@ -19,7 +19,7 @@ struct RowsGemm {
   const float* bias = nullptr;      // [N]
   const float* bias2 = nullptr;     // [N]           (EPI_LINEAR)
   const float *addend = nullptr, *addend2 = nullptr; int64_t ldadd = 0;   // [M, ldadd] (EPI_LINEAR)
-  int act = 0;                      // EPI_LINEAR: 0 none, 1 tanh, 2 sigmoid
+  int act = 0;                      // EPI_LINEAR: 0 none, 1 tanh, 2 sigmoid, 3 tanh BACKWARD: result * (1 - addend2^2)
   // EPI_LSTM (N = 4H permuted gate columns, see rows_pack_lstm): bias/addend as above, plus
   const float* c_prev = nullptr; int64_t ldcp = 0;
   float* c_out = nullptr; int64_t ldc = 0;
@@ -37,8 +37,7 @@ struct RowsGemm {
   int f16 = 0;                      // the operands are single fp16 planes (lo must be NULL)
   int of16 = 0;                     // EPI_TANH / EPI_DY: the output is one fp16 plane
   int af16 = 0;                     // EPI_DY: the saved activation (aux_hi) is one fp16 plane
-  float gscale = 1.0f;              // EPI_DY: power-of-two scale of the output dY; colsum gets alpha (= 1 / gscale)
-  float accscale = 1.0f;            // EPI_DY: gscale / (scale the A operand dZ already carries)
+  float gscale = 1.0f;              // EPI_DY: power-of-two scale carried by A (= dZ) and the output dY; colsum gets alpha (= 1 / gscale)
 };
 
 bool rows_path_enabled();

@@ -890,7 +890,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   ARENA(st_dqt, float, "stack.dqt", (size_t)nHop * B * Q);
   cudaEvent_t head_rest_done = nullptr;
   if (split_ok) {   // the unroll starts at the last hop: the other hops' head backward runs next to its chain
-    RAU_TRY(off_chain(ctx->aux, 32, [&]() { return head_backward(0, nHop - 1); }, &head_rest_done));
+    RAU_TRY(off_chain(ctx->aux2, 32, [&]() { return head_backward(0, nHop - 1); }, &head_rest_done));   // (aux carries the hops' dh lane)
     RAU_TRY(head_backward(nHop - 1, 1));
   } else {
     RAU_TRY(head_backward(0, nHop));
