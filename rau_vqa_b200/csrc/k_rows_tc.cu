@@ -1432,6 +1432,20 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// 256-bit global accesses (sm_100): the per-row pieces of the recurrence's inputs and outputs are 32 contiguous bytes per
+// thread -- one request each instead of two.  (Measured per step of lstm_seq_kernel with %globaltimer stamps: the SM's
+// memory port is what bounds it -- 256 KB of h tiles + 32 KB of Gx in, 65 KB out per CTA -- and generic stores still in
+// flight stretch the next handshake's gpu-scope fences by 1-2 us.)
+__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_v8(const float* p, float* v) {
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
 __device__ __forceinline__ void red_release_add_u32(unsigned int* p, unsigned int v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -1553,10 +1567,10 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
 #pragma unroll
     for (int u = 0; u < 8; ++u) cs[u] = 0.0f;
     for (int t = 1; t <= p.T; ++t) {
-      float4 gx[8];   // the input half of this step's gates does not depend on the recurrence: fetch before waiting
-      const float4* gsrc = reinterpret_cast<const float4*>(p.Gx + (long long)(t - 1) * p.gx_t + (long long)rr * p.ldg + nc);
+      float gx[32];   // the input half of this step's gates does not depend on the recurrence: fetch before waiting
+      const float* gsrc = p.Gx + (long long)(t - 1) * p.gx_t + (long long)rr * p.ldg + nc;
 #pragma unroll
-      for (int k4 = 0; k4 < 8; ++k4) gx[k4] = __ldg(gsrc + k4);
+      for (int k8 = 0; k8 < 4; ++k8) ld_global_nc_v8(gsrc + 8 * k8, gx + 8 * k8);
       mbar_wait(&tfull_bar, (uint32_t)(t - 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float v[32];
@@ -1565,9 +1579,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar);
 #pragma unroll
-      for (int k4 = 0; k4 < 8; ++k4) {
-        v[4 * k4] += gx[k4].x; v[4 * k4 + 1] += gx[k4].y; v[4 * k4 + 2] += gx[k4].z; v[4 * k4 + 3] += gx[k4].w;
-      }
+      for (int k = 0; k < 32; ++k) v[k] += gx[k];
       float gi[8], gf[8], go[8], gg[8], tc[8], hn[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -1596,23 +1608,15 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (warp == 2 && lane == 0) red_release_add_u32(p.counter + tm, 1u);
       if (r_ok) {
-        float4* d;
         const long long so = (long long)(t - 1) * p.s_t + (long long)r * p.lds + u0;
-        d = reinterpret_cast<float4*>(p.c_out + so);
-        d[0] = make_float4(cs[0], cs[1], cs[2], cs[3]); d[1] = make_float4(cs[4], cs[5], cs[6], cs[7]);
-        d = reinterpret_cast<float4*>(p.h_out + so);
-        d[0] = make_float4(hn[0], hn[1], hn[2], hn[3]); d[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+        st_global_v8(p.c_out + so, cs);
+        st_global_v8(p.h_out + so, hn);
         float* sbase = p.lsaved + (long long)(t - 1) * p.ls_t + (long long)r * p.H + u0;
-        d = reinterpret_cast<float4*>(sbase);
-        d[0] = make_float4(gi[0], gi[1], gi[2], gi[3]); d[1] = make_float4(gi[4], gi[5], gi[6], gi[7]);
-        d = reinterpret_cast<float4*>(sbase + p.plane);
-        d[0] = make_float4(gf[0], gf[1], gf[2], gf[3]); d[1] = make_float4(gf[4], gf[5], gf[6], gf[7]);
-        d = reinterpret_cast<float4*>(sbase + 2 * p.plane);
-        d[0] = make_float4(go[0], go[1], go[2], go[3]); d[1] = make_float4(go[4], go[5], go[6], go[7]);
-        d = reinterpret_cast<float4*>(sbase + 3 * p.plane);
-        d[0] = make_float4(gg[0], gg[1], gg[2], gg[3]); d[1] = make_float4(gg[4], gg[5], gg[6], gg[7]);
-        d = reinterpret_cast<float4*>(sbase + 4 * p.plane);
-        d[0] = make_float4(tc[0], tc[1], tc[2], tc[3]); d[1] = make_float4(tc[4], tc[5], tc[6], tc[7]);
+        st_global_v8(sbase, gi);
+        st_global_v8(sbase + p.plane, gf);
+        st_global_v8(sbase + 2 * p.plane, go);
+        st_global_v8(sbase + 3 * p.plane, gg);
+        st_global_v8(sbase + 4 * p.plane, tc);
       }
     }
   }
@@ -1981,7 +1985,11 @@ int rows_lstm_seq(rau_ctx* ctx, const LstmSeq& d, int* done) {
   if (stages > RT_MAXSTAGES) stages = RT_MAXSTAGES;
   // every CTA of the grid must be resident at once (they wait for each other): one CTA per SM
   if (stages < 2 || tiles_m * tiles_n > ctx->sm_count) return RAU_OK;
-  RAU_REQUIRE(d.ldwh % 8 == 0 && d.ldg % 4 == 0 && d.lds % 4 == 0, "rows_lstm_seq: pitches");
+  RAU_REQUIRE(d.ldwh % 8 == 0, "rows_lstm_seq: pitches");
+  // (the epilogue moves 32-byte pieces: every pitch and base it touches must be a multiple of 32 bytes)
+  if (d.ldg % 8 != 0 || d.lds % 8 != 0 || d.gx_t % 8 != 0 || d.s_t % 8 != 0 || d.ls_t % 8 != 0 || d.plane % 8 != 0 ||
+      (((uintptr_t)d.Gx | (uintptr_t)d.c_out | (uintptr_t)d.h_out | (uintptr_t)d.lsaved) & 31) != 0)
+    return RAU_OK;
   RAU_TRY(get_encode());
   LsParams p;
   memset(&p, 0, sizeof(p));
