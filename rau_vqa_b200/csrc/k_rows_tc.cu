@@ -61,6 +61,9 @@ struct RtParams {
   bf16* hpk_hi; bf16* hpk_lo; long long ldhp;  // packed h for the next product (optional)
   int ksplit, kb_per;
   int tiles_m, tiles_n, stages, stage_bytes;
+  unsigned int ksplit_magic, tiles_n_magic;   // ceil(2^32 / d): item -> (tile, k slice) -> (tm, tn) without integer divisions
+                                              // (a runtime division is ~150 dependent cycles; three of them sat between the
+                                              // prologue and every CTA's first TMA)
   int out_lo;                      // bf16 outputs: also write the lo array
   const float* bias;
   const float* rowvec;             // [B, N]
@@ -80,6 +83,10 @@ struct RtParams {
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// floor(x / d) for 0 <= x, d < 2^16 with magic = ceil(2^32 / d) (exact in that range); d == 1 has no 32-bit magic
+__device__ __forceinline__ int fast_div(int x, int d, unsigned int magic) {
+  return d == 1 ? x : (int)__umulhi((unsigned int)x, magic);
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -368,18 +375,19 @@ __global__ void __launch_bounds__(32 * (EW + 3), 1) rows_gemm_kernel(const __gri
       const uint32_t my_bytes = nt * (isB ? b_bytes : a_bytes);
       const int nchunk = (isB ? (CG2 ? p.BN / 2 : p.BN) : RT_BM) / 64;
       uint32_t it = 0;
+      int st = 0;          // stage ring position and phase, carried instead of it % stages, it / stages
+      uint32_t ph = 0;
       for (int item = worker; item < items; item += nworkers) {
-        const int ks = item % p.ksplit;
-        const int tile = item / p.ksplit;
-        const int tn = tile % p.tiles_n, tm = tile / p.tiles_n;
+        const int tile = fast_div(item, p.ksplit, p.ksplit_magic);
+        const int ks = item - tile * p.ksplit;
+        const int tm = fast_div(tile, p.tiles_n, p.tiles_n_magic);
+        const int tn = tile - tm * p.tiles_n;
         const int r0 = CG2 ? (isB ? tn * p.BN + (int)cta_rank * (p.BN / 2) : tm * 2 * RT_BM + (int)cta_rank * RT_BM)
                            : (isB ? tn * p.BN : tm * RT_BM);
         const int kb0 = ks * p.kb_per, kb1 = min(p.nkb, kb0 + p.kb_per);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const bool seg2 = kb >= p.nkb1;
           const CUtensorMap* map = isB ? (seg2 ? &p.mapB2[0] : &p.mapB[0]) : (seg2 ? &p.mapA2[0] : &p.mapA[0]);
-          const int st = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1u;
           mbar_wait(&empty_bar[st], ph ^ 1u);
           if (elect_one()) {
             if (it == 0 && !isB) RT_STAMP(2);      // first TMA about to issue
@@ -409,6 +417,7 @@ __global__ void __launch_bounds__(32 * (EW + 3), 1) rows_gemm_kernel(const __gri
             if (it == 7 && !isB) RT_STAMP(13);     // stage 7 fully issued
           }
           __syncwarp();
+          if (++st == p.stages) { st = 0; ph ^= 1u; }
         }
       }
     }
@@ -435,16 +444,16 @@ __global__ void __launch_bounds__(32 * (EW + 3), 1) rows_gemm_kernel(const __gri
       const uint64_t a_hi_off = p.a_swap ? a_p1 : 0, a_lo_off = p.a_swap ? 0 : a_p1;
       const uint64_t b_hi_off = p.b_swap ? b_p1 : 0, b_lo_off = p.b_swap ? 0 : b_p1;
       uint32_t it = 0, li = 0;
+      int st = 0;
+      uint32_t ph = 0;
       for (int item = worker; item < items; item += nworkers, ++li) {
-        const int ks = item % p.ksplit;
+        const int ks = item - fast_div(item, p.ksplit, p.ksplit_magic) * p.ksplit;
         const int kb0 = ks * p.kb_per, kb1 = min(p.nkb, kb0 + p.kb_per);
         const uint32_t ab = li & 1u, aph = (li >> 1) & 1u;
         mbar_wait(&tempty_bar[ab], aph ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t dcol = tmem_base + ab * (uint32_t)RT_BN;
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int st = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1u;
           mbar_wait(&full_bar[st], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (elect_one()) {
@@ -479,6 +488,7 @@ __global__ void __launch_bounds__(32 * (EW + 3), 1) rows_gemm_kernel(const __gri
             if (it == 7) RT_STAMP(14);       // MMAs of k-block 7 issued
           }
           __syncwarp();
+          if (++st == p.stages) { st = 0; ph ^= 1u; }
         }
         if (elect_one()) {
           if (CG2) umma_commit_2sm(&tfull_bar[ab]);   // both CTAs' epilogues
@@ -530,8 +540,9 @@ __global__ void __launch_bounds__(32 * (EW + 3), 1) rows_gemm_kernel(const __gri
       }
     };
     for (int item = worker; item < items; item += nworkers, ++li) {
-      const int tile = item / p.ksplit;
-      const int tn = tile % p.tiles_n, tm = tile / p.tiles_n;
+      const int tile = fast_div(item, p.ksplit, p.ksplit_magic);
+      const int tm = fast_div(tile, p.tiles_n, p.tiles_n_magic);
+      const int tn = tile - tm * p.tiles_n;
       const int m0 = CG2 ? tm * 2 * RT_BM + (int)cta_rank * RT_BM : tm * RT_BM, n0 = tn * p.BN;
       const uint32_t ab = li & 1u, aph = (li >> 1) & 1u;
       const int r = m0 + q * 32 + lane;          // global row of this thread
@@ -781,8 +792,9 @@ __global__ void __launch_bounds__(32 * (EW + 3), 1) rows_gemm_kernel(const __gri
             const int item2 = item + nworkers;
             dy_ready = item2 < items;
             if (dy_ready) {
-              const int tile2 = item2 / p.ksplit;
-              const int tn2 = tile2 % p.tiles_n, tm2 = tile2 / p.tiles_n;
+              const int tile2 = fast_div(item2, p.ksplit, p.ksplit_magic);
+              const int tm2 = fast_div(tile2, p.tiles_n, p.tiles_n_magic);
+              const int tn2 = tile2 - tm2 * p.tiles_n;
               const int rb2 = (CG2 ? tm2 * 2 * RT_BM + (int)cta_rank * RT_BM : tm2 * RT_BM) + q * 32;
               aux_fetch(rb2, min(tn2 * p.BN + c_lo * 32, p.N - 32));
               rv_fetch(rb2, tn2 * p.BN + c_lo * 32);
@@ -1743,6 +1755,9 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   }
   p.kb_per = (p.nkb + p.ksplit - 1) / p.ksplit;
   p.ksplit = (p.nkb + p.kb_per - 1) / p.kb_per;
+  RAU_REQUIRE((long long)tiles * p.ksplit < 65536 && p.ksplit < 65536 && p.tiles_n < 65536, "rows_gemm: %d work items", tiles * p.ksplit);
+  p.ksplit_magic = (unsigned int)((0x100000000ull + (unsigned long long)p.ksplit - 1) / (unsigned long long)p.ksplit);     // (unused when 1)
+  p.tiles_n_magic = (unsigned int)((0x100000000ull + (unsigned long long)p.tiles_n - 1) / (unsigned long long)p.tiles_n);
   RAU_TRY(encode_operand(&p.mapA[0], g.A.hi, g.A.lo, &p.a_swap, g.A.mn, g.M, g.K, g.A.ld, p.BK, RT_BM));
   RAU_TRY(encode_operand(&p.mapB[0], g.B.hi, g.B.lo, &p.b_swap, g.B.mn, g.N, g.K, g.B.ld, p.BK, p.cg2 ? BN / 2 : BN));
   if (seg2) {

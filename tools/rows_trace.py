@@ -9,7 +9,7 @@ from rau_vqa_b200._ffi import check, ffi
 from rau_vqa_b200.core import fptr
 
 names = ["start", "prologue", "tma0", "stage0", "stage1", "mma_done", "acc_ready", "epi_issued", "stores_drained", "end", "issued0", "issued1", "mma0_issued", "issued7", "mma7_issued"]
-for (M, N, K, a_mn, b_mn, red) in [(256, 2048, 512, 0, 0, 0), (256, 512, 2048, 0, 1, 1), (256, 512, 2048, 0, 1, 0), (2048, 512, 2048, 1, 1, 1), (50176, 512, 512, 0, 0, 0)]:
+for (M, N, K, a_mn, b_mn, red) in [(256, 512, 512, 0, 0, 0), (256, 256, 512, 0, 0, 0), (256, 2048, 1024, 0, 0, 0), (256, 512, 2048, 0, 1, 0), (256, 512, 2048, 0, 1, 1)]:
     ctx = R.Context(0, precision=core.PREC_BF16X3)
     a = torch.randn((K, M) if a_mn else (M, K), device="cuda")
     b = torch.randn((K, N) if b_mn else (N, K), device="cuda")
