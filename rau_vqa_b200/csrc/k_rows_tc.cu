@@ -1537,7 +1537,8 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
       }
     }
     __syncwarp();
-    uint32_t it = 0;
+    int st = 0;          // stage ring position and phase (carried: no it % stages, it / stages in the loop)
+    uint32_t ph = 0;
     for (int t = 1; t <= p.T; ++t) {
       if (t > 1) {   // every CTA of this row tile has published its columns of h_{t-1}
         const unsigned int need = (unsigned int)p.tiles_n * (unsigned int)(t - 1);
@@ -1550,9 +1551,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
         __syncwarp();
         asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy writes of the peers -> this thread's TMA reads
       }
-      for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-        const int st = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1u;
+      for (int kb = 0; kb < p.nkb; ++kb) {
         mbar_wait(&empty_bar[st], ph ^ 1u);
         if (elect_one()) {
           mbar_expect_tx(&full_bar[st], a_stage);
@@ -1560,6 +1559,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
           else tma_load_2d(ast + (size_t)st * a_stage, &p.mapA, &full_bar[st], kb * 64, (t - 1) * p.B + m0);
         }
         __syncwarp();
+        if (++st == p.stages) { st = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -1569,13 +1569,12 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
     const uint64_t a_hi_off = p.a_swap ? a_p1 : 0, a_lo_off = p.a_swap ? 0 : a_p1;
     const uint64_t b_hi_off = p.b_swap ? b_p1 : 0, b_lo_off = p.b_swap ? 0 : b_p1;
     mbar_wait(&w_bar, 0u);
-    uint32_t it = 0;
+    int st = 0;
+    uint32_t ph = 0;
     for (int t = 1; t <= p.T; ++t) {
       mbar_wait(&tempty_bar, ((uint32_t)(t - 1) & 1u) ^ 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-        const int st = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1u;
+      for (int kb = 0; kb < p.nkb; ++kb) {
         mbar_wait(&full_bar[st], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
@@ -1594,6 +1593,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
           umma_commit(&empty_bar[st]);
         }
         __syncwarp();
+        if (++st == p.stages) { st = 0; ph ^= 1u; }
       }
       if (elect_one()) umma_commit(&tfull_bar);
       __syncwarp();
