@@ -211,6 +211,84 @@ __global__ void lstm_bwd_kernel(int B, int H, int order, const float* __restrict
   }
 }
 
+// The same cell backward, four hidden units per thread: 16-byte loads and stores, 8-byte packed (hi / lo) stores, 32-bit
+// index arithmetic.  The scalar form issues ~25 memory instructions and two 64-bit divisions per element; this launch sits
+// 2 T times on the encoder backward's serial lanes (and once per hop), so its latency is what matters, not its bytes.
+__device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) {
+  const __nv_bfloat162 p0 = __floats2bfloat162_rn(a, b), p1 = __floats2bfloat162_rn(c, d);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+}
+__global__ void lstm_bwd_vec4_kernel(int B, int H, int order, const float* __restrict__ dc_out, int lddc,
+                                     const float* __restrict__ dh_out, int lddh, const float* __restrict__ dh_extra, int ldhe,
+                                     const float* __restrict__ lengths, int t, const float* __restrict__ dq_c,
+                                     const float* __restrict__ dq_h, int lddq,
+                                     const float* __restrict__ c_prev, int ldcp, const float* __restrict__ saved,
+                                     float* __restrict__ dG, bf16* __restrict__ dG_b, float* __restrict__ dc_prev, int lddcp,
+                                     bf16* __restrict__ dG_lo, float* __restrict__ zero_out, const uint32_t* __restrict__ extra_bits,
+                                     int64_t extra_bit0, float extra_scale) {
+  RAU_PDL_ENTRY();
+  const int total4 = (B * H) >> 2, h4 = H >> 2;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  int ci, cf, co, cg;
+  gate_chunks(order, ci, cf, co, cg);
+  const size_t plane = (size_t)B * H;
+  for (int i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 < total4; i4 += gridDim.x * blockDim.x) {
+    if (zero_out) reinterpret_cast<float4*>(zero_out)[i4] = z4;
+    const int b = i4 / h4, j = (i4 - b * h4) << 2;
+    const int idx = i4 << 2;
+    float4 dc_o = dc_out ? *reinterpret_cast<const float4*>(dc_out + (size_t)b * lddc + j) : z4;
+    float4 dh_o = dh_out ? *reinterpret_cast<const float4*>(dh_out + (size_t)b * lddh + j) : z4;
+    if (lengths != nullptr && (int)lengths[b] == t) {   // drnn_out[k] = d_feats[1][k]  (F:604-610)
+      dc_o = *reinterpret_cast<const float4*>(dq_c + (size_t)b * lddq + j);
+      dh_o = *reinterpret_cast<const float4*>(dq_h + (size_t)b * lddq + j);
+    }
+    if (dh_extra) {   // gradient w.r.t. a dropped-out copy of h (D:39): its keep mask is applied here
+      const float4 e = *reinterpret_cast<const float4*>(dh_extra + (size_t)b * ldhe + j);
+      float k0 = 1.0f, k1 = 1.0f, k2 = 1.0f, k3 = 1.0f;
+      if (extra_bits) {   // (extra_bit0 and idx are multiples of 4: the four keep bits sit in one word)
+        const int64_t bit = extra_bit0 + idx;
+        const uint32_t w = extra_bits[bit >> 5] >> (bit & 31);
+        k0 = (w & 1u) ? extra_scale : 0.0f; k1 = (w & 2u) ? extra_scale : 0.0f;
+        k2 = (w & 4u) ? extra_scale : 0.0f; k3 = (w & 8u) ? extra_scale : 0.0f;
+      }
+      dh_o.x = fmaf(e.x, k0, dh_o.x); dh_o.y = fmaf(e.y, k1, dh_o.y); dh_o.z = fmaf(e.z, k2, dh_o.z); dh_o.w = fmaf(e.w, k3, dh_o.w);
+    }
+    const float4 i_ = reinterpret_cast<const float4*>(saved)[i4], f_ = reinterpret_cast<const float4*>(saved + plane)[i4];
+    const float4 o_ = reinterpret_cast<const float4*>(saved + 2 * plane)[i4], g_ = reinterpret_cast<const float4*>(saved + 3 * plane)[i4];
+    const float4 tc = reinterpret_cast<const float4*>(saved + 4 * plane)[i4];
+    const float4 cp = c_prev ? *reinterpret_cast<const float4*>(c_prev + (size_t)b * ldcp + j) : z4;
+    float gi[4], gf[4], go[4], gg[4], dcp[4];
+#define RAU_CELL_BWD(k, C)                                                        \
+    {                                                                             \
+      const float d_o = dh_o.C * tc.C;                                            \
+      const float dc = dc_o.C + dh_o.C * o_.C * (1.0f - tc.C * tc.C);             \
+      const float d_f = dc * cp.C, d_i = dc * g_.C, d_g = dc * i_.C;              \
+      dcp[k] = dc * f_.C;                                                         \
+      gi[k] = d_i * i_.C * (1.0f - i_.C); gf[k] = d_f * f_.C * (1.0f - f_.C);     \
+      go[k] = d_o * o_.C * (1.0f - o_.C); gg[k] = d_g * (1.0f - g_.C * g_.C);     \
+    }
+    RAU_CELL_BWD(0, x) RAU_CELL_BWD(1, y) RAU_CELL_BWD(2, z) RAU_CELL_BWD(3, w)
+#undef RAU_CELL_BWD
+    if (dc_prev) *reinterpret_cast<float4*>(dc_prev + (size_t)b * lddcp + j) = make_float4(dcp[0], dcp[1], dcp[2], dcp[3]);
+    const size_t row = (size_t)b * 4 * H + j;
+    auto put = [&](int chunk, float a, float b2, float c2, float d) {
+      const size_t o = row + (size_t)chunk * H;
+      if (dG) *reinterpret_cast<float4*>(dG + o) = make_float4(a, b2, c2, d);
+      if (dG_b) {
+        const uint2 hi = pack4_bf16(a, b2, c2, d);
+        *reinterpret_cast<uint2*>(dG_b + o) = hi;
+        if (dG_lo)   // bf16x3 operand: lo = bf16(x - hi)
+          *reinterpret_cast<uint2*>(dG_lo + o) = pack4_bf16(a - __uint_as_float(hi.x << 16), b2 - __uint_as_float(hi.x & 0xffff0000u),
+                                                           c2 - __uint_as_float(hi.y << 16), d - __uint_as_float(hi.y & 0xffff0000u));
+      }
+    };
+    put(ci, gi[0], gi[1], gi[2], gi[3]);
+    put(cf, gf[0], gf[1], gf[2], gf[3]);
+    put(co, go[0], go[1], go[2], go[3]);
+    put(cg, gg[0], gg[1], gg[2], gg[3]);
+  }
+}
+
 // ---------------------------------------------------------------- elementwise
 __global__ void dropout_kernel(const float* __restrict__ x, int64_t rows, int cols, int ldx,
                                const uint32_t* __restrict__ bits, float scale,
@@ -525,6 +603,18 @@ int k_lstm_bwd(rau_ctx* ctx, int B, int H, int order, const float* dc_out, int l
                const float* dh_extra, int ldhe, const float* lengths, int t, const float* dq_c, const float* dq_h, int lddq,
                const float* c_prev, int ldcp, const float* saved, float* dG, bf16* dG_b, float* dc_prev, int lddcp, bf16* dG_lo,
                float* zero_out, const uint32_t* extra_bits, int64_t extra_bit0, float extra_scale) {
+  auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
+  const bool vec4 = H % 4 == 0 && (int64_t)B * H < (1ll << 30) && lddc % 4 == 0 && lddh % 4 == 0 && ldhe % 4 == 0 && lddq % 4 == 0 &&
+                    ldcp % 4 == 0 && lddcp % 4 == 0 && extra_bit0 % 4 == 0 && al16(dc_out) && al16(dh_out) && al16(dh_extra) &&
+                    al16(dq_c) && al16(dq_h) && al16(c_prev) && al16(saved) && al16(dG) && al16(dG_b) && al16(dc_prev) && al16(dG_lo) &&
+                    al16(zero_out);
+  if (vec4) {
+    RAU_LAUNCH_PDL(ctx->stream, (lstm_bwd_vec4_kernel), grid_for((int64_t)B * H / 4), TPB, 0, B, H, order, dc_out, lddc, dh_out, lddh,
+        dh_extra, ldhe, lengths, t, dq_c, dq_h, lddq, c_prev, ldcp, saved, dG, dG_b, dc_prev, lddcp, dG_lo, zero_out, extra_bits,
+        extra_bit0, extra_scale);
+    RAU_LAUNCH_CHECK(ctx);
+    return RAU_OK;
+  }
   RAU_LAUNCH_PDL(ctx->stream, (lstm_bwd_kernel), grid_for((int64_t)B * H), TPB, 0, B, H, order, dc_out, lddc, dh_out, lddh, dh_extra, ldhe,
       lengths, t, dq_c, dq_h, lddq, c_prev, ldcp, saved, dG, dG_b, dc_prev, lddcp, dG_lo, zero_out, extra_bits, extra_bit0,
       extra_scale);
