@@ -553,9 +553,11 @@ def main():
             for w in ("ours_ms", "ours_resnet", "ours_ss"):
                 r2 = Runner(ctx, w, 0, 1, 0, dev, None)
                 r2.prime(3)
+                cs2 = ClockSampler(local)
+                cs2.start()
                 m2, l2 = r2.resident_leg(args.steps)
                 extra[w] = dict(value=r2.B * args.steps / (m2 * 1e-3), unit=UNIT, ms_per_step=m2 / args.steps,
-                                launches_per_step=l2 / args.steps, config=make_config(w, 1))
+                                launches_per_step=l2 / args.steps, clocks=cs2.stop(), config=make_config(w, 1))
                 r2.free()
             extra["sweep"] = sweep(ctx, dev, pk)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
