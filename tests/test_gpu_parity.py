@@ -86,6 +86,15 @@ def test_toy_step_hop_mask_and_ragged_lengths(ctx):
     _check_step(ctx, cfg, params, X, x, x_len, y, masks, hop_mask=[1, 0, 1])
 
 
+def test_sizes_that_are_not_multiples_of_four(ctx):
+    """Hidden sizes, feature channels and answer counts that defeat every vectorised / tcgen05 fast path (odd pitches, unaligned
+    rows): the scalar kernels and the CUDA-core engine carry the step."""
+    cfg = small_cfg(Hq=10, H=6, M=14, A=6, C=22, embed=9, N=27, S=15, nHop=2)
+    params = O.init_params(cfg, seed=33)
+    X, x, x_len, y = O.synth_batch(cfg, 3, seed=34, min_len=1)
+    _check_step(ctx, cfg, params, X, x, x_len, y, O.synth_masks(cfg, 3, seed=35))
+
+
 def test_batch_of_one(ctx):
     cfg = small_cfg(nHop=1)
     params = O.init_params(cfg, seed=23)
