@@ -874,6 +874,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   // pass reads them, so with the heads on the side stream they stay there (behind the event the chain just waited for)
   {
     cudaStream_t chain = ctx->stream;
+    if (ov_head) { ctx->stream = ctx->side; side_used = true; }
     const int rc_m = k_merge_preds(ctx, nHop, B, N, S, scores, dop, nullptr, bt->labels, ans, 0, 1.0f / Bg, loss + nHop, loss_dp,
                                    ans + (size_t)nHop * B, nullptr, nullptr, nullptr, nullptr);
     ctx->stream = chain;
