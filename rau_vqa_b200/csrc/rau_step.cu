@@ -37,6 +37,7 @@ struct Encoder {
   int B, Tm;          // batch, number of unrolled steps
   uint32_t *ebits, *rbits;
   float *e_all, *G1x, *G2x, *u2, *S_all, *sav1, *sav2, *Gt, *rnn_out;
+  int proj0_done = 0;   // a part-1 call already formed layer 1's hoisted input projection
 };
 
 static int encoder_alloc(rau_ctx* ctx, const rau_config* cfg, int B, Encoder* en) {
@@ -58,7 +59,10 @@ static int encoder_alloc(rau_ctx* ctx, const rau_config* cfg, int B, Encoder* en
 }
 
 // F:460-479.  State rows are [c1|h1|c2|h2] (D:23-24, D:68); S_all[t] is the state after step t, S_all[0] = 0.
-// part: 0 = everything, 1 = masks + word embedding only, 2 = the rest (after a part-1 call)
+// part: 0 = everything, 1 = masks + word embedding + (tcgen05 path) layer 1's hoisted input projection, 2 = the rest (after a
+// part-1 call).  The training step releases the side stream between the two parts: its all-hops feature pack keeps 84 SMs
+// and much of HBM busy for ~370 us, and the projection -- the last launch of the chain that is NOT latency-bound -- ran
+// three times slower next to it.
 static int encoder_forward(rau_ctx* ctx, const rau_config* cfg, const rau_batch* bt, const float* Pe, const float* Pr,
                            int train, const rau_masks* masks, int64_t step_t, Encoder* en, int part = 0) {
   const int B = bt->B, Hq = cfg->Hq, E = cfg->embed, Q = 4 * Hq, G4 = 4 * Hq;
@@ -77,10 +81,40 @@ static int encoder_forward(rau_ctx* ctx, const rau_config* cfg, const rau_batch*
     RAU_TRY(k_embed_fwd(ctx, bt->tokens, Tm * B, E, cfg->V, Pe, de ? en->ebits : nullptr, drop_scale(cfg->p_embed),
                         en->e_all, nullptr, 0));
     if (ctx->phases == 2) rau_phase_mark(ctx, "enc embed done");
-    if (part == 1) return RAU_OK;
   }
   const bool fused = ctx->precision != RAU_PREC_F32 && rows_path_enabled() && Hq % 8 == 0 && E % 8 == 0 &&
                      (int64_t)B * G4 * Hq >= (1 << 18);
+  // hoisted input projection of one layer for every step at once, columns in the permuted gate order (tcgen05 path)
+  auto input_projection = [&](int layer) -> int {
+    const bool x3 = prec_x3(ctx);
+    const int in = layer == 0 ? E : Hq;
+    const bf16 *Wi_h, *Wi_l, *x_h, *x_l;
+    int64_t ldwi, ldx;
+    const float* bperm;
+    RAU_TRY(rows_pack_lstm(ctx, Pr + L[layer].Wi, Hq, in, RAU_GATES_IFOG, x3, &Wi_h, &Wi_l, &ldwi));
+    RAU_TRY(rows_perm_lstm_bias(ctx, Pr + L[layer].bi, Pr + L[layer].bh, Hq, RAU_GATES_IFOG, &bperm));
+    RAU_TRY(rows_pack2d(ctx, layer == 0 ? en->e_all : en->u2, in, Tm * B, in, x3, false, layer == 0 ? "enc.x0" : "enc.x1", &x_h,
+                        &x_l, &ldx));
+    RowsGemm g;
+    g.M = Tm * B; g.N = G4; g.K = in;
+    g.A.hi = x_h; g.A.lo = x_l; g.A.ld = ldx;
+    g.B.hi = Wi_h; g.B.lo = Wi_l; g.B.ld = ldwi;
+    g.epi = ROWS_EPI_LINEAR; g.bias = bperm; g.out_f = layer == 0 ? en->G1x : en->G2x; g.ldo = G4;
+    return rows_gemm(ctx, g);
+  };
+  if (part == 1) {
+    en->proj0_done = 0;
+    if (fused) {
+      const int cap = ctx->main_cta_cap;   // (the side stream is not running yet: the whole device)
+      ctx->main_cta_cap = 0;
+      const int rc = input_projection(0);
+      ctx->main_cta_cap = cap;
+      RAU_TRY(rc);
+      en->proj0_done = 1;
+    }
+    return RAU_OK;
+  }
+  if (part == 0) en->proj0_done = 0;
   // layer 1 input projection hoisted over time: G1x = e Wi1^T + bi1 + bh1
   if (!fused) {
     SimtGemm g = lin_fwd(Tm * B, G4, E, en->e_all, E, Pr + L[0].Wi, en->G1x, G4);
@@ -97,27 +131,14 @@ static int encoder_forward(rau_ctx* ctx, const rau_config* cfg, const rau_batch*
     for (int layer = 0; layer < 2; ++layer) {
       bf16* hpk_hi = hpk_all + (size_t)(2 * layer) * (cfg->T + 1) * hb;
       bf16* hpk_lo = hpk_hi + (size_t)(cfg->T + 1) * hb;
-      const int in = layer == 0 ? E : Hq;
-      const bf16 *Wi_h, *Wi_l, *Wh_h, *Wh_l, *x_h, *x_l;
-      int64_t ldwi, ldwh, ldx;
-      const float* bperm;
-      RAU_TRY(rows_pack_lstm(ctx, Pr + L[layer].Wi, Hq, in, RAU_GATES_IFOG, x3, &Wi_h, &Wi_l, &ldwi));
+      const bf16 *Wh_h, *Wh_l;
+      int64_t ldwh;
       RAU_TRY(rows_pack_lstm(ctx, Pr + L[layer].Wh, Hq, Hq, RAU_GATES_IFOG, x3, &Wh_h, &Wh_l, &ldwh));
-      RAU_TRY(rows_perm_lstm_bias(ctx, Pr + L[layer].bi, Pr + L[layer].bh, Hq, RAU_GATES_IFOG, &bperm));
       float* Gx = layer == 0 ? en->G1x : en->G2x;
       if (layer == 1)   // u2 = drop(h1) for every step (D:38-39)
         RAU_TRY(k_dropout(ctx, en->S_all + (size_t)B * Q + Hq, (int64_t)Tm * B, Hq, Q, dr ? en->rbits : nullptr,
                           drop_scale(cfg->p_rnn), en->u2, Hq, nullptr, 0, Hq));
-      RAU_TRY(rows_pack2d(ctx, layer == 0 ? en->e_all : en->u2, in, Tm * B, in, x3, false, layer == 0 ? "enc.x0" : "enc.x1", &x_h,
-                          &x_l, &ldx));
-      {   // input projection of every step at once, columns in the permuted gate order
-        RowsGemm g;
-        g.M = Tm * B; g.N = G4; g.K = in;
-        g.A.hi = x_h; g.A.lo = x_l; g.A.ld = ldx;
-        g.B.hi = Wi_h; g.B.lo = Wi_l; g.B.ld = ldwi;
-        g.epi = ROWS_EPI_LINEAR; g.bias = bperm; g.out_f = Gx; g.ldo = G4;
-        RAU_TRY(rows_gemm(ctx, g));
-      }
+      if (!(layer == 0 && en->proj0_done)) RAU_TRY(input_projection(layer));
       RAU_CHECK_CUDA(cudaMemsetAsync(hpk_hi, 0, hb * sizeof(bf16), ctx->stream));
       if (x3) RAU_CHECK_CUDA(cudaMemsetAsync(hpk_lo, 0, hb * sizeof(bf16), ctx->stream));
       if (ctx->phases == 2) rau_phase_mark(ctx, "enc layer input projection done");
