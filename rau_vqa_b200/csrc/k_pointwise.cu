@@ -76,9 +76,12 @@ __global__ void xmask16_bytes_kernel(uint8_t* __restrict__ out, int B, int C, in
     const int64_t bc = e / S;
     const int c = (int)(bc % C);
     const uint64_t ctr = (uint64_t)(((bc - (c & 1)) * S) + (s & ~3)) >> 2;
-    const uint4 r = philox4x32(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), stream_lo ^ (uint32_t)h, stream_hi), key);
+    const bool shared = rau_xmask_shared(thresh, nHop);
+    const uint4 r = philox4x32(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32),
+                                          shared ? stream_lo ^ RAU_XMASK_SHARED_TAG : stream_lo ^ (uint32_t)h, stream_hi), key);
     const uint32_t w = (s & 3) == 0 ? r.x : (s & 3) == 1 ? r.y : (s & 3) == 2 ? r.z : r.w;
-    out[i] = (uint8_t)((((w >> ((c & 1) * 16)) & 0xffffu) < thresh) ? 1 : 0);
+    if (shared) out[i] = (uint8_t)(((w >> ((c & 1) * 16 + h)) & 1u) ? 0 : 1);
+    else out[i] = (uint8_t)((((w >> ((c & 1) * 16)) & 0xffffu) < thresh) ? 1 : 0);
   }
 }
 

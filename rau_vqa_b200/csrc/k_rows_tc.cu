@@ -1034,11 +1034,14 @@ __global__ void pack_hilo_kernel(const float* __restrict__ in, int64_t n4, bf16*
 __global__ void __launch_bounds__(256) xprep_rows_kernel(const float* __restrict__ X, const uint32_t* __restrict__ bits, float scale,
                                                          int C, int S, bf16* __restrict__ hi, bf16* __restrict__ lo, int gen,
                                                          uint32_t thresh, uint2 key, uint32_t stream_lo, uint32_t stream_hi,
-                                                         const StepState* __restrict__ ss, int f16) {
+                                                         const StepState* __restrict__ ss, int f16, int hop, int nHop) {
   RAU_PDL_ENTRY();
   extern __shared__ float sT[];   // [S][66]
   const int b = blockIdx.y, c0 = blockIdx.x * 64;
   const int S4 = S >> 2;
+  // (hop >= 0: stream_* is the hop's own stream id = base ^ hop; the shared draw of p = 1/2 uses the base)
+  const bool shared = gen && hop >= 0 && rau_xmask_shared(thresh, nHop);
+  if (shared) stream_lo = stream_lo ^ (uint32_t)hop ^ RAU_XMASK_SHARED_TAG;
   if (gen && ss) {   // graph replay: the step part of the stream id lives on the device
     const unsigned long long sid = (((unsigned long long)stream_hi << 32) | stream_lo) ^ (ss->step << 24);
     stream_lo = (uint32_t)sid;
@@ -1055,10 +1058,18 @@ __global__ void __launch_bounds__(256) xprep_rows_kernel(const float* __restrict
       const uint64_t ctr = (uint64_t)(((int64_t)b * C + (cc & ~1)) * S + 4 * s4) >> 2;
       const uint4 r = philox4x32(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), stream_lo, stream_hi), key);
       const int sh = (cc & 1) * 16;
-      t.x = ((r.x >> sh) & 0xffffu) < thresh ? t.x * scale : 0.0f;
-      t.y = ((r.y >> sh) & 0xffffu) < thresh ? t.y * scale : 0.0f;
-      t.z = ((r.z >> sh) & 0xffffu) < thresh ? t.z * scale : 0.0f;
-      t.w = ((r.w >> sh) & 0xffffu) < thresh ? t.w * scale : 0.0f;
+      if (shared) {   // bit `hop` of the element's 16-bit lane, clear = keep
+        const int bit = sh + hop;
+        t.x = ((r.x >> bit) & 1u) ? 0.0f : t.x * scale;
+        t.y = ((r.y >> bit) & 1u) ? 0.0f : t.y * scale;
+        t.z = ((r.z >> bit) & 1u) ? 0.0f : t.z * scale;
+        t.w = ((r.w >> bit) & 1u) ? 0.0f : t.w * scale;
+      } else {
+        t.x = ((r.x >> sh) & 0xffffu) < thresh ? t.x * scale : 0.0f;
+        t.y = ((r.y >> sh) & 0xffffu) < thresh ? t.y * scale : 0.0f;
+        t.z = ((r.z >> sh) & 0xffffu) < thresh ? t.z * scale : 0.0f;
+        t.w = ((r.w >> sh) & 0xffffu) < thresh ? t.w * scale : 0.0f;
+      }
     } else if (bits) {
       const uint32_t w = bits[e >> 5] >> (e & 31);
       t.x = (w & 1u) ? t.x * scale : 0.0f;
@@ -1135,6 +1146,30 @@ __global__ void __launch_bounds__(1024, 1) xprep_rows_hops_kernel(const float* _
 #pragma unroll
       for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const float2*>(sT + (4 * s4 + k) * 66 + 2 * lane);
       const uint64_t ct0 = (e0 + 4 * s4) >> 2;
+      if (rau_xmask_shared(thresh, nHop)) {
+        // p = 1/2: ONE draw for all hops (bit h of a 16-bit lane decides hop h).  The scaled values are packed once; a hop's
+        // stores are the packed words ANDed with a 0 / 0xffff mask per half: 4-5 instructions per channel pair and hop.
+        const uint4 r0 = philox4x32(make_uint4((uint32_t)ct0, (uint32_t)(ct0 >> 32), stream_lo ^ RAU_XMASK_SHARED_TAG, stream_hi), key);
+        const uint32_t keepw[4] = {~r0.x, ~r0.y, ~r0.z, ~r0.w};
+        uint32_t wh[4], wl[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (f16) { wh[k] = pack_f16x2(v[k].x * scale, v[k].y * scale); wl[k] = 0u; }
+          else split_pair(v[k].x * scale, v[k].y * scale, wh[k], wl[k]);
+        }
+        for (int h = 0; h < nHop; ++h) {
+          uint32_t* ph = reinterpret_cast<uint32_t*>(hi + (long long)h * hop_stride);
+          uint32_t* pl = (lo && !f16) ? reinterpret_cast<uint32_t*>(lo + (long long)h * hop_stride) : nullptr;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t m = ((keepw[k] >> h) & 0x00010001u) * 0xffffu;
+            const int64_t o = (((int64_t)b * S + 4 * s4 + k) * C + c0) >> 1;
+            ph[o + lane] = wh[k] & m;
+            if (pl) pl[o + lane] = wl[k] & m;
+          }
+        }
+        continue;
+      }
       for (int h = 0; h < nHop; ++h) {
         const uint4 r0 = philox4x32(make_uint4((uint32_t)ct0, (uint32_t)(ct0 >> 32), stream_lo ^ (uint32_t)h, stream_hi), key);
         const uint32_t q0[4] = {r0.x & 0xffffu, r0.y & 0xffffu, r0.z & 0xffffu, r0.w & 0xffffu};
@@ -1920,14 +1955,14 @@ int k_xprep_rows_hops(rau_ctx* ctx, const float* X, int B, int C, int S, int nHo
 }
 
 int k_xprep_rows(rau_ctx* ctx, const float* X, int B, int C, int S, const uint32_t* bits, float scale, bf16* hi, bf16* lo,
-                 int gen, float p_drop, uint64_t stream_id, int f16) {
+                 int gen, float p_drop, uint64_t stream_id, int f16, int hop, int nHop) {
   RAU_REQUIRE(C % 64 == 0 && S % 4 == 0 && S <= 256 && ((uintptr_t)X & 15) == 0, "k_xprep_rows: C=%d S=%d", C, S);
   RAU_TRY(prep_attr());
   const double keep = 1.0 - (double)p_drop;
   const uint32_t thresh = keep >= 1.0 ? 65536u : (uint32_t)(keep * 65536.0 + 0.5);   // 16-bit keep threshold (gen path)
   RAU_LAUNCH_PDL(ctx->stream, (xprep_rows_kernel), dim3(C / 64, B), 256, S * 66 * 4, 
       X, bits, scale, C, S, hi, lo, gen, thresh, make_uint2((uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32)), (uint32_t)stream_id,
-      (uint32_t)(stream_id >> 32), ctx->ss_active, f16);
+      (uint32_t)(stream_id >> 32), ctx->ss_active, f16, hop, nHop);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }

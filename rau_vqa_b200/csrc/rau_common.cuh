@@ -259,6 +259,13 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 }
 
 // keep-bit lookup in a packed mask (bit i of word i>>5); nullptr = keep everything (evaluate()).
+// Feature-dropout masks drawn inline (F:239, one mask per hop over the same features).  General p: element (b, c, s) of hop h
+// compares 16 bits of the draw (counter = the element's channel-pair x 4-cell group, stream id ^ h) with a threshold.  For
+// p = 1/2 exactly and nHop <= 16 ONE draw serves every hop: hop h keeps the element iff bit h of its 16-bit lane is clear
+// (stream id ^ RAU_XMASK_SHARED_TAG, independent of h) -- 1/nHop of the Philox work, which is what bounds the pack kernel.
+constexpr uint32_t RAU_XMASK_SHARED_TAG = 0xA5A50000u;
+__host__ __device__ __forceinline__ bool rau_xmask_shared(uint32_t thresh16, int nHop) { return thresh16 == 32768u && nHop >= 1 && nHop <= 16; }
+
 __device__ __forceinline__ float keep_scale(const uint32_t* __restrict__ bits, int64_t i, float scale) {
   if (bits == nullptr) return 1.0f;
   return ((bits[i >> 5] >> (i & 31)) & 1u) ? scale : 0.0f;

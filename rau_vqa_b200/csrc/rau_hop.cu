@@ -95,7 +95,7 @@ int hop_forward_pre(rau_ctx* ctx, const rau_config* cfg, int B, const MultT<cons
   RAU_TRY(rows_pack(ctx, P.Wi, (int64_t)M * C, x3x, true, nullptr, &Wi_h, &Wi_l, fx));
   if (!sv.x_done)
     RAU_TRY(k_xprep_rows(ctx, X, B, C, S, xb, drop_scale(cfg->p_x), sv.Xd_hi, x3x ? sv.Xd_lo : nullptr,
-                         (train && cfg->p_x > 0 && sv.x_philox) ? 1 : 0, cfg->p_x, sv.x_stream, fx));
+                         (train && cfg->p_x > 0 && sv.x_philox) ? 1 : 0, cfg->p_x, sv.x_stream, fx, sv.x_hop, sv.x_nhop));
   RowsGemm g;
   g.M = R; g.N = M; g.K = C;
   g.A.hi = sv.Xd_hi; g.A.lo = x3x ? sv.Xd_lo : nullptr; g.A.ld = C;
@@ -1012,7 +1012,7 @@ int rau_feature_pack(rau_ctx* ctx, const float* X, int B, int C, int S, int nHop
   } else {
     for (int h = 0; h < nHop; ++h)
       RAU_TRY(k_xprep_rows(ctx, X, B, C, S, nullptr, drop_scale(p), hi + n * h, x3 ? lo + n * h : nullptr, 1, p, stream_id ^ (uint64_t)h,
-                           f16));
+                           f16, h, nHop));
   }
   return k_unpack_hilo(ctx, hi, x3 ? lo : nullptr, (int64_t)n * nHop, out, f16);
 }

@@ -59,6 +59,7 @@ struct HopSaved {
   int x_philox = 0;
   int x_done = 0;        // the pack already ran (all hops in one launch)
   uint64_t x_stream = 0;
+  int x_hop = -1, x_nhop = 0;   // which hop of how many (the shared draw of p = 1/2 needs both; -1: a lone pack)
   // training step: packed twins of the small activations (all NULL through the module-level API, which packs on demand)
   PK qd_pk, qf_pk, p_pk, j_pk, hin_pk, hout_pk, m_pk;
   // training step: Wq drop_h(q) + bq of this hop, computed for all hops in one product before the unroll (q is the same

@@ -65,7 +65,9 @@ int k_xprep_rows_hops(rau_ctx* ctx, const float* X, int B, int C, int S, int nHo
                       int64_t hop_stride, float p_drop, uint64_t stream_id, int f16 = 0);
 int k_unpack_hilo(rau_ctx* ctx, const bf16* hi, const bf16* lo, int64_t n, float* out, int f16 = 0);   // out = hi + lo (tests)
 int k_xprep_rows(rau_ctx* ctx, const float* X, int B, int C, int S, const uint32_t* bits, float scale, bf16* hi, bf16* lo,
-                 int gen = 0, float p_drop = 0.0f, uint64_t stream_id = 0, int f16 = 0);
+                 int gen = 0, float p_drop = 0.0f, uint64_t stream_id = 0, int f16 = 0, int hop = -1, int nHop = 0);
+// (gen: hop >= 0 and nHop tell the kernel which hop of how many this pack belongs to -- stream_id is then base ^ hop -- so that
+// it draws the same keep bits as the all-hops launch, see rau_xmask_shared)
 int k_unprep_rows(rau_ctx* ctx, const float* dXr, int B, int C, int S, const uint32_t* bits, float scale, float* dX);
 int k_attn_rows_fwd(rau_ctx* ctx, int B, int M, int S, const float* logit, const float* mem, const bf16* I_hi, const bf16* I_lo,
                     float* p, float* a, bf16* p_hi = nullptr, bf16* p_lo = nullptr, int ldp = 0, int f16 = 0);   // p_hi/p_lo: packed twin of p

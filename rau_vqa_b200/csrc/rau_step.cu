@@ -738,6 +738,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     if (hop_rows_path(ctx, cfg) && !(masks && masks->x)) {   // drawn inline by the rows pack kernel
       sv[hp].x_philox = 1;
       sv[hp].x_stream = stream_of(step_t, SK_X, hp, rank);
+      sv[hp].x_hop = hp; sv[hp].x_nhop = nHop;
     } else {
       RAU_TRY(rau_prepare_mask(ctx, sv[hp].xbits, (int64_t)B * cfg->C * S, cfg->p_x, train,
                                masks && masks->x ? masks->x + (size_t)hp * B * cfg->C * S : nullptr,
