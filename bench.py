@@ -494,7 +494,10 @@ def main():
     # The feed's staging format: in the mixed modes the features enter the tensor pipe as fp16 and the power-of-two dropout
     # scale commutes with the rounding, so fp16 staging (half the PCIe bytes) changes no bit of what the products read
     # (tests/test_gpu_feed.py) and is what `e2e` uses; the float32 staging of the reference's upload is in extra.
-    main_fmt = F.FEED_F16 if prec in ("mixed", "f16img") else F.FEED_F32
+    # ... and the all-hops feature pack reads the uploaded fp16 buffer as it is (RAU_FEED_F16_DIRECT: no widening pass on
+    # the copy stream; needs nHop > 1, the one-hop configuration keeps the widened form).  RAU_BENCH_FEED=f16 | f32 overrides.
+    main_fmt = (F.FEED_F16_DIRECT if run.cfg.nHop > 1 else F.FEED_F16) if prec in ("mixed", "f16img") else F.FEED_F32
+    main_fmt = dict(f16=F.FEED_F16, f32=F.FEED_F32, direct=F.FEED_F16_DIRECT).get(os.environ.get("RAU_BENCH_FEED", ""), main_fmt)
     ms_e2e, h2d, d2h = run.e2e_leg(args.steps, main_fmt)
     torch.cuda.synchronize()
     assert torch.isfinite(run.out.loss).all().item(), "loss is not finite"
@@ -502,7 +505,7 @@ def main():
     e2e_v = B * world * args.steps / (ms_e2e * 1e-3)
 
     extra = {}
-    if not args.no_extra and main_fmt == F.FEED_F16:
+    if not args.no_extra and main_fmt != F.FEED_F32:
         # the same step fed through float32 staging, byte for byte what the reference uploads (F:452-456)
         ms32, h2d32, _ = run.e2e_leg(args.steps, F.FEED_F32)
         extra["e2e_f32_feed"] = dict(value=B * world * args.steps / (ms32 * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d32,
@@ -567,7 +570,8 @@ def main():
                     l2=f"{NB} rotating batches ({NB * B * cfg.C * 196 * 4 / 1e6:.0f} MB of features) + >1 GB of saved activations per "
                        "step exceed the 126 MB L2",
                     e2e=dict(value=e2e_v, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e / args.steps,
-                             feed="rau_feed_* (pinned " + ("float16" if main_fmt == F.FEED_F16 else "float32") +
+                             feed="rau_feed_* (pinned " + {F.FEED_F32: "float32", F.FEED_F16: "float16",
+                                                            F.FEED_F16_DIRECT: "float16, read directly by the feature pack:"}[main_fmt] +
                                   " staging, depth 2, copy stream)"),
                     gpu_launches=int(launches), launches_per_step=launches / args.steps, clocks=clocks, roofline=roof,
                     cpu_baseline=cpu, extra=extra)

@@ -332,6 +332,8 @@ __global__ void __launch_bounds__(32 * (EW + 3), 1) rows_gemm_kernel(const __gri
   unsigned long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 16 : nullptr;
 #define RT_STAMP(slot) do { if (dbg) dbg[slot] = clock64(); } while (0)
   if (threadIdx.x == 0) RT_STAMP(0);
+  unsigned long long gt0 = 0;   // (trace only) wall-clock ns of this CTA's lifetime go to slot 15: cycles / ns = the SM clock under load
+  if (dbg && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
@@ -881,6 +883,11 @@ __global__ void __launch_bounds__(32 * (EW + 3), 1) rows_gemm_kernel(const __gri
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (threadIdx.x == 0) RT_STAMP(9);
+  if (dbg && threadIdx.x == 0) {
+    unsigned long long gt1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+    dbg[15] = gt1 - gt0;
+  }
   if (CG2) cluster_sync_all();   // no CTA of the pair leaves while the other may still signal its barriers / read its smem
   if (warp == 1) {
     if (CG2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -1100,7 +1107,9 @@ __global__ void __launch_bounds__(256) xprep_rows_kernel(const float* __restrict
 // Persistent: one 1024-thread CTA per SM it may use (four 256-thread groups, each with its own [S][66] slab and named
 // barrier, walk the (image, 64-channel) tiles).  The big CTAs keep the launch on `gridDim.x` SMs, so the chain's tcgen05
 // launches still find free SMs next to it (a grid of small CTAs spread over every SM and filled their shared memory).
-__global__ void __launch_bounds__(1024, 1) xprep_rows_hops_kernel(const float* __restrict__ X, float scale, int C, int S, int B, int nHop,
+// X16 != NULL: the features arrive as fp16 [B, C, S] (rau_batch.feats_f16, the fp16 feed) and are widened on load.
+__global__ void __launch_bounds__(1024, 1) xprep_rows_hops_kernel(const float* __restrict__ X, const __half* __restrict__ X16,
+                                                                  float scale, int C, int S, int B, int nHop,
                                                                   bf16* __restrict__ hi, bf16* __restrict__ lo, long long hop_stride,
                                                                   uint32_t thresh, uint2 key, uint32_t stream_lo, uint32_t stream_hi,
                                                                   const StepState* __restrict__ ss, int f16) {
@@ -1120,13 +1129,25 @@ __global__ void __launch_bounds__(1024, 1) xprep_rows_hops_kernel(const float* _
     // the tile's 64 x S floats are contiguous in X: batches of 7 independent 16-byte loads per thread, then the
     // transposing stores (a load -> store loop exposes one memory latency per iteration)
     const float4* src = reinterpret_cast<const float4*>(X + ((int64_t)b * C + c0) * S);
+    const uint2* src16 = reinterpret_cast<const uint2*>(X16 + ((int64_t)b * C + c0) * S);
     const int n4 = 64 * S4;
     for (int i0 = tid; i0 < n4; i0 += 256 * 7) {
       float4 t[7];
+      if (X16) {
+        uint2 u[7];
 #pragma unroll
-      for (int k = 0; k < 7; ++k) {
-        const int i = i0 + 256 * k;
-        if (i < n4) t[k] = __ldg(src + i);
+        for (int k = 0; k < 7; ++k) {
+          const int i = i0 + 256 * k;
+          if (i < n4) u[k] = __ldg(src16 + i);
+        }
+#pragma unroll
+        for (int k = 0; k < 7; ++k) t[k] = make_float4(hf_lo(u[k].x), hf_hi(u[k].x), hf_lo(u[k].y), hf_hi(u[k].y));
+      } else {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+          const int i = i0 + 256 * k;
+          if (i < n4) t[k] = __ldg(src + i);
+        }
       }
 #pragma unroll
       for (int k = 0; k < 7; ++k) {
@@ -1933,9 +1954,10 @@ int k_unpack_hilo(rau_ctx* ctx, const bf16* hi, const bf16* lo, int64_t n, float
   return RAU_OK;
 }
 
-int k_xprep_rows_hops(rau_ctx* ctx, const float* X, int B, int C, int S, int nHop, float scale, bf16* hi, bf16* lo,
+int k_xprep_rows_hops(rau_ctx* ctx, const float* X, const void* X16, int B, int C, int S, int nHop, float scale, bf16* hi, bf16* lo,
                       int64_t hop_stride, float p_drop, uint64_t stream_id, int f16) {
-  RAU_REQUIRE(C % 64 == 0 && S % 4 == 0 && S <= 200 && ((uintptr_t)X & 15) == 0 && hop_stride % 2 == 0, "k_xprep_rows_hops: C=%d S=%d", C, S);
+  RAU_REQUIRE(C % 64 == 0 && S % 4 == 0 && S <= 200 && hop_stride % 2 == 0, "k_xprep_rows_hops: C=%d S=%d", C, S);
+  RAU_REQUIRE(X16 ? ((uintptr_t)X16 & 7) == 0 : (X != nullptr && ((uintptr_t)X & 15) == 0), "k_xprep_rows_hops: feature alignment");
   const int smem = 4 * S * 66 * 4;
   static bool attr = false;
   if (!attr) {
@@ -1948,7 +1970,7 @@ int k_xprep_rows_hops(rau_ctx* ctx, const float* X, int B, int C, int S, int nHo
   const int ntiles = (C / 64) * B;
   const int grid = (ntiles + 3) / 4 < cap ? (ntiles + 3) / 4 : cap;
   RAU_LAUNCH_PDL(ctx->stream, (xprep_rows_hops_kernel), grid, 1024, smem,
-      X, scale, C, S, B, nHop, hi, lo, (long long)hop_stride, thresh, make_uint2((uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32)),
+      X, (const __half*)X16, scale, C, S, B, nHop, hi, lo, (long long)hop_stride, thresh, make_uint2((uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32)),
       (uint32_t)stream_id, (uint32_t)(stream_id >> 32), ctx->ss_active, f16);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;

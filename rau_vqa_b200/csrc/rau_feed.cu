@@ -66,7 +66,7 @@ extern "C" {
 
 size_t rau_feed_host_bytes(const rau_feed* f) {
   if (f == nullptr) return 0;
-  const size_t feat = (size_t)f->B * f->C * f->S * (f->format == RAU_FEED_F16 ? 2 : 4);
+  const size_t feat = (size_t)f->B * f->C * f->S * (f->format == RAU_FEED_F32 ? 4 : 2);
   return feat + sizeof(float) * ((size_t)f->T * f->B + 2 * (size_t)f->B);
 }
 
@@ -95,7 +95,7 @@ int rau_feed_create(rau_ctx* ctx, const rau_config* cfg, int B, int format, int 
   *out = nullptr;
   RAU_TRY(rau_check_cfg(cfg));
   RAU_REQUIRE(B > 0 && depth >= 2 && depth <= 8, "rau_feed_create: B = %d, depth = %d (2..8)", B, depth);
-  RAU_REQUIRE(format == RAU_FEED_F32 || format == RAU_FEED_F16, "rau_feed_create: unknown format %d", format);
+  RAU_REQUIRE(format == RAU_FEED_F32 || format == RAU_FEED_F16 || format == RAU_FEED_F16_DIRECT, "rau_feed_create: unknown format %d", format);
   RAU_REQUIRE(((int64_t)cfg->C * cfg->S) % 2 == 0, "rau_feed_create: C*S must be even");
   RAU_CHECK_CUDA(cudaSetDevice(ctx->device));
   rau_feed* f = new rau_feed();
@@ -105,11 +105,11 @@ int rau_feed_create(rau_ctx* ctx, const rau_config* cfg, int B, int format, int 
   bool ok = cudaStreamCreateWithFlags(&f->copy, cudaStreamNonBlocking) == cudaSuccess;
   for (auto& s : f->slots) {
     if (!ok) break;
-    ok = cudaHostAlloc(&s.h_feats, nfeat * (format == RAU_FEED_F16 ? 2 : 4), cudaHostAllocDefault) == cudaSuccess &&
+    ok = cudaHostAlloc(&s.h_feats, nfeat * (format == RAU_FEED_F32 ? 4 : 2), cudaHostAllocDefault) == cudaSuccess &&
          cudaHostAlloc((void**)&s.h_tok, nsmall * sizeof(float), cudaHostAllocDefault) == cudaSuccess &&
-         cudaMalloc((void**)&s.d_feats, nfeat * sizeof(float)) == cudaSuccess &&
+         (format == RAU_FEED_F16_DIRECT || cudaMalloc((void**)&s.d_feats, nfeat * sizeof(float)) == cudaSuccess) &&
          cudaMalloc((void**)&s.d_tok, nsmall * sizeof(float)) == cudaSuccess &&
-         (format != RAU_FEED_F16 || cudaMalloc(&s.d_stage, nfeat * 2) == cudaSuccess) &&
+         (format == RAU_FEED_F32 || cudaMalloc(&s.d_stage, nfeat * 2) == cudaSuccess) &&
          cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&s.freed, cudaEventDisableTiming) == cudaSuccess;
@@ -149,7 +149,7 @@ int rau_feed_convert(const rau_feed* f, const void* src, int src_is_f64, int64_t
   auto work = [=](int64_t a, int64_t b) {
     for (int64_t i = a; i < b; ++i) {
       const float v = src_is_f64 ? (float)((const double*)src)[i] : ((const float*)src)[i];
-      if (fmt == RAU_FEED_F16) ((__half*)dst)[i] = __float2half_rn(v);
+      if (fmt != RAU_FEED_F32) ((__half*)dst)[i] = __float2half_rn(v);
       else ((float*)dst)[i] = v;
     }
   };
@@ -175,7 +175,10 @@ int rau_feed_submit(rau_feed* f, int slot) {
   s.max_len = ml < 1 ? 1 : (ml > f->T ? f->T : ml);
   RAU_CHECK_CUDA(cudaStreamWaitEvent(f->copy, s.freed, 0));
   RAU_CHECK_CUDA(cudaMemcpyAsync(s.d_tok, s.h_tok, nsmall * sizeof(float), cudaMemcpyHostToDevice, f->copy));
-  if (f->format == RAU_FEED_F16) {
+  if (f->format == RAU_FEED_F16_DIRECT) {   // the training step's feature pack reads the fp16 buffer itself
+    RAU_CHECK_CUDA(cudaMemcpyAsync(s.d_stage, s.h_feats, nfeat * 2, cudaMemcpyHostToDevice, f->copy));
+    RAU_CHECK_CUDA(cudaEventRecord(s.copied, f->copy));
+  } else if (f->format == RAU_FEED_F16) {
     RAU_CHECK_CUDA(cudaMemcpyAsync(s.d_stage, s.h_feats, nfeat * 2, cudaMemcpyHostToDevice, f->copy));
     RAU_CHECK_CUDA(cudaEventRecord(s.copied, f->copy));
     // a SMALL grid: the conversion has a whole training step to finish and must not take SMs from the step's persistent
@@ -200,7 +203,7 @@ int rau_feed_acquire(rau_feed* f, int slot, rau_batch* batch) {
   RAU_REQUIRE(s.in_flight, "rau_feed_acquire: slot %d was not submitted", slot);
   RAU_CHECK_CUDA(cudaStreamWaitEvent(f->ctx->stream, s.ready, 0));
   batch->B = f->B; batch->B_global = f->B;
-  batch->feats = s.d_feats; batch->tokens = s.d_tok; batch->lengths = s.d_len; batch->labels = s.d_lab;
+  batch->feats = s.d_feats; batch->feats_f16 = f->format == RAU_FEED_F16_DIRECT ? s.d_stage : nullptr; batch->tokens = s.d_tok; batch->lengths = s.d_len; batch->labels = s.d_lab;
   batch->max_len = s.max_len;
   return RAU_OK;
 }

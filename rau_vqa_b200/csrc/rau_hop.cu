@@ -1008,7 +1008,7 @@ int rau_feature_pack(rau_ctx* ctx, const float* X, int B, int C, int S, int nHop
   bf16* hi = buf;
   bf16* lo = buf + n * nHop;
   if (all_hops) {
-    RAU_TRY(k_xprep_rows_hops(ctx, X, B, C, S, nHop, drop_scale(p), hi, x3 ? lo : nullptr, (int64_t)n, p, stream_id, f16));
+    RAU_TRY(k_xprep_rows_hops(ctx, X, nullptr, B, C, S, nHop, drop_scale(p), hi, x3 ? lo : nullptr, (int64_t)n, p, stream_id, f16));
   } else {
     for (int h = 0; h < nHop; ++h)
       RAU_TRY(k_xprep_rows(ctx, X, B, C, S, nullptr, drop_scale(p), hi + n * h, x3 ? lo + n * h : nullptr, 1, p, stream_id ^ (uint64_t)h,

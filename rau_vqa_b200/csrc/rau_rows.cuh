@@ -61,7 +61,7 @@ int rows_pack(rau_ctx* ctx, const float* W, int64_t n, bool want_lo, bool cache,
               bool f16 = false);   // f16: one fp16 plane instead of bf16 hi [, lo]
 // gen != 0: draw the keep bits inline from Philox stream `stream_id` with drop rate p_drop (bits is then ignored)
 // the same for nHop hops in one launch (training step, drawn masks): hop h writes hi/lo + h*hop_stride, stream id ^ h
-int k_xprep_rows_hops(rau_ctx* ctx, const float* X, int B, int C, int S, int nHop, float scale, bf16* hi, bf16* lo,
+int k_xprep_rows_hops(rau_ctx* ctx, const float* X, const void* X16, int B, int C, int S, int nHop, float scale, bf16* hi, bf16* lo,
                       int64_t hop_stride, float p_drop, uint64_t stream_id, int f16 = 0);
 int k_unpack_hilo(rau_ctx* ctx, const bf16* hi, const bf16* lo, int64_t n, float* out, int f16 = 0);   // out = hi + lo (tests)
 int k_xprep_rows(rau_ctx* ctx, const float* X, int B, int C, int S, const uint32_t* bits, float scale, bf16* hi, bf16* lo,

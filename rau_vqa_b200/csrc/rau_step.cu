@@ -506,11 +506,18 @@ static int encoder_backward(rau_ctx* ctx, const rau_config* cfg, const rau_batch
   return RAU_OK;
 }
 
-static int check_batch(const rau_config* cfg, const rau_batch* bt) {
+// f16_ok: the entry point can run from the fp16 features alone (rau_batch.feats_f16, `feats` == NULL)
+static int check_batch(const rau_config* cfg, const rau_batch* bt, bool f16_ok) {
   RAU_REQUIRE(bt != nullptr, "batch == NULL");
   RAU_REQUIRE(bt->B > 0, "batch size %d", bt->B);
   RAU_REQUIRE(bt->max_len >= 0 && bt->max_len <= cfg->T, "max_len %d outside [0, T=%d]", bt->max_len, cfg->T);
-  RAU_TRY(rau_check_dev(bt->feats, "batch.feats"));
+  if (bt->feats == nullptr && bt->feats_f16 != nullptr) {
+    RAU_REQUIRE(f16_ok, "this entry point needs float32 features: batch.feats is NULL (only batch.feats_f16 is set)");
+    RAU_TRY(rau_check_dev(bt->feats_f16, "batch.feats_f16"));
+    RAU_REQUIRE(((uintptr_t)bt->feats_f16 & 7) == 0, "batch.feats_f16 must be 8-byte aligned");
+  } else {
+    RAU_TRY(rau_check_dev(bt->feats, "batch.feats"));
+  }
   RAU_TRY(rau_check_dev(bt->tokens, "batch.tokens"));
   RAU_TRY(rau_check_dev(bt->lengths, "batch.lengths"));
   return RAU_OK;
@@ -523,7 +530,7 @@ static int feval_validate(rau_ctx* ctx, const rau_config* cfg, const rau_batch* 
   RAU_REQUIRE(ctx, "ctx == NULL");
   RAU_TRY(rau_check_cfg(cfg));
   RAU_REQUIRE(cfg->nlayer == 2, "the fused encoder supports nlayer == 2 (F:209), got %d", cfg->nlayer);
-  RAU_TRY(check_batch(cfg, bt));
+  RAU_TRY(check_batch(cfg, bt, true));
   RAU_TRY(rau_check_dev(bt->labels, "batch.labels"));
   RAU_REQUIRE(params && grads, "params/grads == NULL");
   for (int g = 0; g < 3; ++g) {
@@ -570,6 +577,11 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   const bool ov_bwd = rows_hops && (overlap_mode & 1);
   const bool ov_fwd = rows_hops && (overlap_mode & 2);
   const bool ov_head = rows_hops && (overlap_mode & 4);   // bit 2: the answer heads + criteria of the forward unroll
+  // fp16-only features (rau_batch.feats_f16 without feats): the all-hops feature pack is the one kernel that reads them
+  RAU_REQUIRE(bt->feats != nullptr || (ov_fwd && masks == nullptr && cfg->p_x > 0 && cfg->nHop > 1 && cfg->S <= 200 &&
+                                       ctx->tune.xprep_hops != 0),
+              "batch.feats is NULL: fp16-only features need the all-hops feature pack (tcgen05 rows path with the side stream, "
+              "drawn masks, p_x > 0, nHop > 1, S <= 200)");
   if (ctx->side_ctas == 0) {
     ctx->side_ctas = ctx->tune.side_ctas > 0 ? ctx->tune.side_ctas : (ctx->sm_count * 4) / 7;   // 84 of 148 SMs (profiles/README.md)
     if (ctx->side_ctas < 8 || ctx->side_ctas > ctx->sm_count) ctx->side_ctas = ctx->sm_count;
@@ -802,8 +814,12 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     // (RAU_XPREP_HOPS=0: one pack launch per hop -- same bits; a test compares the two)
     bool all_philox = train && cfg->p_x > 0 && nHop > 1 && nHop < 65536 && S <= 200 && ctx->tune.xprep_hops != 0;   // (S: its smem slabs)
     for (int hp = 0; hp < nHop; ++hp) all_philox = all_philox && sv[hp].x_philox;
-    if (all_philox) {
-      rc = k_xprep_rows_hops(ctx, bt->feats, B, cfg->C, S, nHop, drop_scale(cfg->p_x), sv[0].Xd_hi,
+    if (!all_philox && bt->feats == nullptr) {
+      rau_set_error("batch.feats is NULL: fp16-only features are read by the all-hops feature pack alone (training, drawn masks, "
+                    "p_x > 0, nHop > 1, S <= 200, RAU_XPREP_HOPS != 0)");
+      rc = RAU_EINVAL;
+    } else if (all_philox) {
+      rc = k_xprep_rows_hops(ctx, bt->feats, bt->feats == nullptr ? bt->feats_f16 : nullptr, B, cfg->C, S, nHop, drop_scale(cfg->p_x), sv[0].Xd_hi,
                              (prec_x3(ctx) && !prec_x_f16(ctx)) ? sv[0].Xd_lo : nullptr, (int64_t)(sv_bytes / sizeof(bf16)),
                              cfg->p_x, sv[0].x_stream, prec_x_f16(ctx) ? 1 : 0);
       for (int hp = 0; hp < nHop; ++hp) sv[hp].x_done = 1;
@@ -1261,7 +1277,7 @@ static int predict_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch*
   RAU_TRY(rau_check_async_error(ctx));
   RAU_TRY(rau_check_cfg(cfg));
   RAU_REQUIRE(cfg->nlayer == 2, "the fused encoder supports nlayer == 2 (F:209), got %d", cfg->nlayer);
-  RAU_TRY(check_batch(cfg, bt));
+  RAU_TRY(check_batch(cfg, bt, false));
   RAU_TRY(rau_check_dev(pred, "pred"));
   for (int g = 0; g < 3; ++g) RAU_TRY(rau_check_dev(params[g], "params[g]"));
   RAU_CHECK_CUDA(cudaSetDevice(ctx->device));

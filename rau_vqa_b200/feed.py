@@ -10,7 +10,7 @@ import torch
 from ._ffi import check, ffi
 from .core import Context, RauConfig, fptr
 
-FEED_F32, FEED_F16 = 0, 1
+FEED_F32, FEED_F16, FEED_F16_DIRECT = 0, 1, 2   # (DIRECT: no widening pass; the training step reads the fp16 upload)
 
 
 class Feed:
@@ -31,7 +31,7 @@ class Feed:
         pf, pt, pl, py = ffi.new("void**"), ffi.new("float**"), ffi.new("float**"), ffi.new("float**")
         check(self.ctx.lib.rau_feed_host_slot(self.h, slot, pf, pt, pl, py))
         B, C, S, T = self.B, self.cfg.C, self.cfg.S, self.cfg.T
-        fdt = np.float16 if self.fmt == FEED_F16 else np.float32
+        fdt = np.float32 if self.fmt == FEED_F32 else np.float16
         feats = np.frombuffer(ffi.buffer(pf[0], B * C * S * np.dtype(fdt).itemsize), dtype=fdt).reshape(B, C, S)
         tok = np.frombuffer(ffi.buffer(pt[0], T * B * 4), dtype=np.float32).reshape(T, B)
         ln = np.frombuffer(ffi.buffer(pl[0], B * 4), dtype=np.float32)

@@ -41,7 +41,7 @@ def _run(R, lc, params, batches, mode):
             losses.append(out.loss.cpu().numpy().copy())
     else:
         fd = F.Feed(ctx, lc, B, fmt=mode, depth=2)
-        assert fd.bytes_per_batch == B * lc.C * lc.S * (2 if mode == F.FEED_F16 else 4) + 4 * (lc.T * B + 2 * B)
+        assert fd.bytes_per_batch == B * lc.C * lc.S * (4 if mode == F.FEED_F32 else 2) + 4 * (lc.T * B + 2 * B)
         fd.fill(0, *batches[0])          # (float64 features, as the loader returns them: LD:1009)
         fd.submit(0)
         for it in range(1, len(batches) + 1):
@@ -114,6 +114,50 @@ def test_f16_feed_changes_no_bit_of_what_the_tensor_pipe_sees_in_the_default_mod
     params = O.init_params(cfg, seed=3201)
     batches = [O.synth_batch(cfg, 6, seed=3202 + i) for i in range(3)]
     _same(_run(R, lc, params, batches, "direct"), _run(R, lc, params, batches, F.FEED_F16))
+
+
+def test_f16_direct_feed_trains_like_the_f16_feed():
+    """RAU_FEED_F16_DIRECT: no widening pass on the copy stream -- the all-hops feature pack reads the uploaded fp16 buffer
+    (rau_batch.feats_f16, feats == NULL).  half -> float is exact, so the packed operand is the one the F16 feed produces and
+    the run equals it to summation-order noise; the upload is the same number of bytes."""
+    import rau_vqa_b200 as R
+    from rau_vqa_b200 import feed as F
+    cfg = O.RauConfig(V=3000, C=512, nHop=2, N=2000)
+    lc = R.RauConfig(V=cfg.V, C=cfg.C, nHop=cfg.nHop, N=cfg.N)
+    params = O.init_params(cfg, seed=3301)
+    batches = [O.synth_batch(cfg, 6, seed=3302 + i) for i in range(4)]
+    _same(_run(R, lc, params, batches, F.FEED_F16), _run(R, lc, params, batches, F.FEED_F16_DIRECT))
+
+
+def test_f16_only_batch_is_refused_where_float32_features_are_needed():
+    """a batch that carries only feats_f16 is accepted by the training step on the tcgen05 rows path; the toy shape (CUDA-core
+    feature path) and the inference entry points say so instead of reading a NULL pointer"""
+    import torch
+    import rau_vqa_b200 as R
+    from rau_vqa_b200 import feed as F
+    from rau_vqa_b200._ffi import RauError, ffi
+    from rau_vqa_b200 import core
+    Rm, cfg, lc, params, batches = _setup(B=4)
+    ctx = R.Context(0, seed=9, precision=core.PREC_F32)   # (the CUDA-core engine: no all-hops feature pack)
+    P = [dev(params[g]) for g in O.GROUPS]
+    G = [torch.zeros_like(p) for p in P]
+    ST = [[torch.zeros_like(p), torch.zeros_like(p)] for p in P]
+    out = R.StepBuffers(lc, 4, P[0].device, want_scores=False)
+    fd = F.Feed(ctx, lc, 4, fmt=F.FEED_F16_DIRECT, depth=2)
+    fd.fill(0, *batches[0])
+    fd.submit(0)
+    b = fd.acquire(0)
+    assert b.feats == ffi.NULL and b.feats_f16 != ffi.NULL
+    with pytest.raises(RauError, match="feats is NULL"):
+        F.train_step_batch(ctx, lc, P, G, ST, b, out, step_t=1, opt_t=1)
+    pred = torch.empty(lc.nHop + 2, 4, lc.N, device="cuda")
+    Pp = ffi.new("float*[3]", [ffi.cast("float*", t.data_ptr()) for t in P])
+    with pytest.raises(RauError, match="float32 features"):
+        from rau_vqa_b200._ffi import check
+        check(ctx.lib.rau_predict(ctx.h, lc.c(), b, Pp, ffi.cast("float*", pred.data_ptr()), ffi.NULL))
+    fd.release(0)
+    fd.close()
+    ctx.close()
 
 
 def test_feature_cache_gather():
