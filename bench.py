@@ -359,14 +359,17 @@ class Runner:
             small_h.append(torch.from_numpy(np.concatenate([hb[1].ravel(), hb[2], hb[3], idx])).pin_memory())
         T, B = self.cfg.T, self.B
         small_d = [torch.empty_like(small_h[0], device=self.dev) for _ in range(2)]
-        feats_d = [torch.empty(B, self.cfg.C, self.cfg.S, device=self.dev) for _ in range(2)]
+        # (nHop > 1 in a tcgen05 mode: the gather stays fp16 and the feature pack reads it directly, rau_batch.feats_f16)
+        f16 = self.cfg.nHop > 1 and PREC_NAMES[int(self.ctx.lib.rau_get_precision(self.ctx.h))] != "f32"
+        feats_d = [torch.empty(B, self.cfg.C, self.cfg.S, device=self.dev, dtype=torch.float16 if f16 else torch.float32)
+                   for _ in range(2)]
         loss_host = torch.empty(self.cfg.nHop + 2, dtype=torch.float32).pin_memory()
 
         def step(i):
             s = i % 2
             d = small_d[s]
             d.copy_(small_h[i % self.NB], non_blocking=True)
-            cache.gather(d[T * B + 2 * B:], out=feats_d[s])
+            (cache.gather_f16 if f16 else cache.gather)(d[T * B + 2 * B:], out=feats_d[s])
             self.step((feats_d[s], d[:T * B].view(T, B), d[T * B:T * B + B], d[T * B + B:T * B + 2 * B]))
             loss_host.copy_(self.out.loss, non_blocking=True)
 

@@ -299,6 +299,8 @@ int rau_feat_cache_create(rau_ctx* ctx, int64_t n_images, int C, int S, rau_feat
 int rau_feat_cache_destroy(rau_feat_cache* cache);
 int rau_feat_cache_put(rau_feat_cache* cache, int64_t first, int64_t n, const float* host_feats);
 int rau_feat_cache_gather(rau_feat_cache* cache, const float* image_index, int B, float* feats);
+/* the same without widening: feats_f16[B,C,S] fp16 for rau_batch.feats_f16 (C*S % 8 == 0, 16-byte aligned destination) */
+int rau_feat_cache_gather_f16(rau_feat_cache* cache, const float* image_index, int B, void* feats_f16);
 
 /* ------------------------------------------------------------------ multi-GPU - */
 /* One process per GPU.  rank 0 calls rau_comm_unique_id, ships the 128 bytes to the other ranks,

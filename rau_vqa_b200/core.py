@@ -132,7 +132,11 @@ def _batch_struct(keep, B, feats, tokens, lengths, labels, max_len, B_global):
     b = ffi.new("rau_batch*")
     b.B = B
     b.B_global = B_global or B
-    b.feats = fptr(feats)
+    if feats.dtype == torch.float16:     # fp16 features go in as they are (rau_batch.feats_f16; the training step only)
+        b.feats = ffi.NULL
+        b.feats_f16 = ffi.cast("const void*", feats.data_ptr())
+    else:
+        b.feats = fptr(feats)
     b.tokens = fptr(tokens)
     b.lengths = fptr(lengths)
     b.max_len = int(max_len)

@@ -33,6 +33,17 @@ __global__ void gather_kernel(const __half2* __restrict__ cache, int64_t per2, i
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per2; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] = __half22float2(src[i]);
 }
+// the same gather without widening: out[b] = cache[index[b] - 1] as fp16 (16 bytes per thread and step)
+__global__ void gather_f16_kernel(const uint4* __restrict__ cache, int64_t per8, int64_t n_images, const float* __restrict__ index,
+                                  uint4* __restrict__ out) {
+  const int b = blockIdx.y;
+  int64_t img = (int64_t)index[b] - 1;
+  if (img < 0) img = 0;
+  if (img >= n_images) img = n_images - 1;
+  const uint4* src = cache + img * per8;
+  uint4* dst = out + (int64_t)b * per8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per8; i += (int64_t)gridDim.x * blockDim.x) dst[i] = __ldg(src + i);
+}
 inline int blocks_for(int64_t n) { int64_t b = (n + 255) / 256; return (int)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b)); }
 }  // namespace
 
@@ -274,6 +285,22 @@ int rau_feat_cache_gather(rau_feat_cache* c, const float* image_index, int B, fl
   int gx = (int)((per2 + 255) / 256);
   if (gx > 64) gx = 64;
   gather_kernel<<<dim3(gx, B), 256, 0, c->ctx->stream>>>((const __half2*)c->data, per2, c->n_images, image_index, (float2*)feats);
+  RAU_LAUNCH_CHECK(c->ctx);
+  return RAU_OK;
+}
+
+// The same as fp16 [B, C, S] (rau_batch.feats_f16: the training step's feature pack reads it directly): a third of the
+// gather's HBM traffic.  Needs C*S % 8 == 0 and a 16-byte aligned destination.
+int rau_feat_cache_gather_f16(rau_feat_cache* c, const float* image_index, int B, void* feats_f16) {
+  RAU_REQUIRE(c && B > 0, "rau_feat_cache_gather_f16: bad arguments");
+  RAU_TRY(rau_check_dev(image_index, "image_index"));
+  RAU_TRY(rau_check_dev(feats_f16, "feats_f16"));
+  RAU_REQUIRE(c->per_image % 8 == 0 && ((uintptr_t)feats_f16 & 15) == 0, "rau_feat_cache_gather_f16: C*S %% 8 != 0 or misaligned output");
+  RAU_CHECK_CUDA(cudaSetDevice(c->ctx->device));
+  const int64_t per8 = c->per_image / 8;
+  int gx = (int)((per8 + 255) / 256);
+  if (gx > 64) gx = 64;
+  gather_f16_kernel<<<dim3(gx, B), 256, 0, c->ctx->stream>>>((const uint4*)c->data, per8, c->n_images, image_index, (uint4*)feats_f16);
   RAU_LAUNCH_CHECK(c->ctx);
   return RAU_OK;
 }

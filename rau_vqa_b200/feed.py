@@ -88,6 +88,14 @@ class FeatCache:
         check(self.ctx.lib.rau_feat_cache_gather(self.h, fptr(image_index), B, fptr(out)))
         return out
 
+    def gather_f16(self, image_index: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """the batch's features as fp16 [B, C, S] for rau_batch.feats_f16 (core.train_step(..., feats_f16=...))"""
+        B = image_index.numel()
+        if out is None:
+            out = torch.empty(B, self.C, self.S, dtype=torch.float16, device=image_index.device)
+        check(self.ctx.lib.rau_feat_cache_gather_f16(self.h, fptr(image_index), B, ffi.cast("void*", out.data_ptr())))
+        return out
+
 
 def train_step_batch(ctx: Context, cfg: RauConfig, params, grads, opt_state, batch, out, optim=5, lrs=(3e-3, 3e-3, 3e-4),
                      hyper=(0.9, 0.999, 1e-8), eta=0.01, gamma=0.55, clip=0.1, step_t=0, opt_t=0):

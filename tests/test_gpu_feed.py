@@ -175,6 +175,10 @@ def test_feature_cache_gather():
     got = cache.gather(dev(idx))
     ctx.sync()
     np.testing.assert_array_equal(got.cpu().numpy(), feats[idx - 1].astype(np.float16).astype(np.float32))
+    got16 = cache.gather_f16(dev(idx))      # the same rows without widening (rau_batch.feats_f16)
+    ctx.sync()
+    assert got16.dtype == torch.float16
+    np.testing.assert_array_equal(got16.cpu().numpy(), feats[idx - 1].astype(np.float16))
     from rau_vqa_b200._ffi import RauError
     with pytest.raises(RauError):
         cache.put(140, feats[:20])       # past the end
