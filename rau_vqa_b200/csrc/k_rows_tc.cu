@@ -1002,7 +1002,7 @@ int launch_rows_v(rau_ctx* ctx, const RtParams& p, int grid, int smem_bytes) {
 // the CTA-pair form exists for the big K-major products with fused epilogues
 template <int EPI>
 int launch_rows(rau_ctx* ctx, const RtParams& p, int grid, int smem_bytes) {
-  constexpr bool pairable = EPI == EPI_PLAIN || EPI == EPI_TANH || EPI == EPI_ATT || EPI == EPI_DY || EPI == EPI_RED;
+  constexpr bool pairable = EPI == EPI_PLAIN || EPI == EPI_TANH || EPI == EPI_ATT || EPI == EPI_DY || EPI == EPI_RED || EPI == EPI_LINEAR;
   if (EPI == EPI_TANH && p.ew == 16 && p.cg2 && !p.x3) return launch_rows_v<EPI_TANH, 0, 4, 1, 16>(ctx, p, grid, smem_bytes);
   if (pairable && p.cg2) {
     if (p.x3) return launch_rows_v<EPI, 1, 2, pairable ? 1 : 0>(ctx, p, grid, smem_bytes);
@@ -1774,7 +1774,9 @@ int rows_gemm(rau_ctx* ctx, const RowsGemm& g) {
   const bool seg2 = g.K2 > 0;
   {   // CTA pairs (cta_group::2) for the big K-major products: RAU_CG2=0 keeps everything on single CTAs
     const int cg2_on = ctx->tune.cg2;
-    const bool pair_epi = g.epi == EPI_PLAIN || g.epi == EPI_TANH || g.epi == EPI_ATT || g.epi == EPI_DY || g.epi == EPI_RED;
+    // (EPI_LINEAR: the encoder's hoisted input projections and input gradients, [T*B, in] x [in, 4H]: RAU_LIN_CG2=0 keeps single CTAs)
+    const bool pair_epi = g.epi == EPI_PLAIN || g.epi == EPI_TANH || g.epi == EPI_ATT || g.epi == EPI_DY || g.epi == EPI_RED ||
+                          (g.epi == EPI_LINEAR && ctx->tune.lin_cg2 != 0);
     // big row counts (the image-side products), or split-K reductions with at least one pair of row tiles
     const bool pair_shape = g.epi == EPI_RED ? (p.tiles_m >= 2 && p.tiles_m % 2 == 0 && p.nkb >= 64) : p.tiles_m >= 8;
     p.cg2 = (cg2_on && pair_epi && pair_shape && BN == 256 && !seg2 && sm_avail >= 2) ? 1 : 0;

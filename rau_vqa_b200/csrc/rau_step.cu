@@ -38,7 +38,14 @@ struct Encoder {
   uint32_t *ebits, *rbits;
   float *e_all, *G1x, *G2x, *u2, *S_all, *sav1, *sav2, *Gt, *rnn_out;
   int proj0_done = 0;   // a part-1 call already formed layer 1's hoisted input projection
+  cudaEvent_t w_ready = nullptr;   // the encoder's weight shadows were packed on the aux stream: wait before the first product
 };
+
+// the question encoder runs on the tcgen05 rows engine (hoisted input projections + persistent recurrence)
+static bool encoder_fused(const rau_ctx* ctx, const rau_config* cfg, int B) {
+  return ctx->precision != RAU_PREC_F32 && rows_path_enabled() && cfg->Hq % 8 == 0 && cfg->embed % 8 == 0 &&
+         (int64_t)B * 4 * cfg->Hq * cfg->Hq >= (1 << 18);
+}
 
 static int encoder_alloc(rau_ctx* ctx, const rau_config* cfg, int B, Encoder* en) {
   const int T = cfg->T, Hq = cfg->Hq, E = cfg->embed, Q = 4 * Hq;
@@ -55,6 +62,27 @@ static int encoder_alloc(rau_ctx* ctx, const rau_config* cfg, int B, Encoder* en
   ARENA(rnn_out, float, "enc.out", (size_t)B * Q);
   en->B = B; en->ebits = ebits; en->rbits = rbits; en->e_all = e_all; en->G1x = G1x; en->G2x = G2x; en->u2 = u2;
   en->S_all = S_all; en->sav1 = sav1; en->sav2 = sav2; en->Gt = Gt; en->rnn_out = rnn_out;
+  return RAU_OK;
+}
+
+// The bf16 (hi, lo) shadows of the encoder's weights in the permuted gate order and the permuted bias sums: six small
+// launches that depend on the parameters only.  The training step issues them on the aux stream at its very start (they
+// are cached per public call, so the encoder's own calls below find them done) instead of on the chain in front of each
+// layer's products.
+static int encoder_pack_weights(rau_ctx* ctx, const rau_config* cfg, const float* Pr) {
+  RnnLayerOff L[4];
+  rnn_offsets(cfg, L);
+  const bool x3 = prec_x3(ctx);
+  const int Hq = cfg->Hq;
+  for (int layer = 0; layer < 2; ++layer) {
+    const int in = layer == 0 ? cfg->embed : Hq;
+    const bf16 *h, *l;
+    int64_t ld;
+    const float* bperm;
+    RAU_TRY(rows_pack_lstm(ctx, Pr + L[layer].Wi, Hq, in, RAU_GATES_IFOG, x3, &h, &l, &ld));
+    RAU_TRY(rows_perm_lstm_bias(ctx, Pr + L[layer].bi, Pr + L[layer].bh, Hq, RAU_GATES_IFOG, &bperm));
+    RAU_TRY(rows_pack_lstm(ctx, Pr + L[layer].Wh, Hq, Hq, RAU_GATES_IFOG, x3, &h, &l, &ld));
+  }
   return RAU_OK;
 }
 
@@ -82,8 +110,8 @@ static int encoder_forward(rau_ctx* ctx, const rau_config* cfg, const rau_batch*
                         en->e_all, nullptr, 0));
     if (ctx->phases == 2) rau_phase_mark(ctx, "enc embed done");
   }
-  const bool fused = ctx->precision != RAU_PREC_F32 && rows_path_enabled() && Hq % 8 == 0 && E % 8 == 0 &&
-                     (int64_t)B * G4 * Hq >= (1 << 18);
+  const bool fused = encoder_fused(ctx, cfg, B);
+  if (fused && en->w_ready != nullptr && part != 2) RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, en->w_ready, 0));
   // hoisted input projection of one layer for every step at once, columns in the permuted gate order (tcgen05 path)
   auto input_projection = [&](int layer) -> int {
     const bool x3 = prec_x3(ctx);
@@ -216,8 +244,7 @@ static int encoder_backward(rau_ctx* ctx, const rau_config* cfg, const rau_batch
   ARENA(dH, float, "encb.dH", (size_t)B * Hq);
   ARENA(du2, float, "encb.du2", (size_t)cfg->T * B * Hq);
   ARENA(de_all, float, "encb.de", (size_t)cfg->T * B * E);
-  const bool fused = ctx->precision != RAU_PREC_F32 && rows_path_enabled() && Hq % 8 == 0 && E % 8 == 0 &&
-                     (int64_t)B * G4 * Hq >= (1 << 18);
+  const bool fused = encoder_fused(ctx, cfg, B);
   if (fused) {
     // tcgen05 path: the pointwise cell backward writes dG packed (hi, lo) next to the fp32 copy, the recurrent dgrad is a
     // split-K product on the rows engine straight from it, and the four weight gradients reuse the packed operands the
@@ -566,9 +593,6 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   const int rank = rau_comm_rank(ctx);
   const int train = 1;
 
-  for (int g = 0; g < 3; ++g)   // F:446-448
-    RAU_TRY(k_fill(ctx, grads[g], rau_group_size(cfg, g), 0.0f));
-
   rau_phase_mark(ctx, "begin");
   // cross-stream overlap (rows path): RAU_OVERLAP bit 0 = heavy backward products on the side stream, bit 1 = the
   // state-independent i_embed products of all hops on the side stream, next to the encoder and the chain
@@ -605,6 +629,26 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     RAU_REQUIRE(fork0 != nullptr, "cudaEventCreate failed");
     RAU_CHECK_CUDA(cudaEventRecord(fork0, ctx->stream));
   }
+  // Off the chain's first microseconds, onto the aux stream: the encoder's weight shadows (six small launches the chain
+  // otherwise runs in front of its layers' products) and the zero fill of the three gradient vectors (F:446-448; nothing
+  // accumulates into them before the backward pass, which is ordered behind the aux stream's join after the encoder).
+  cudaEvent_t enc_w_ready = nullptr;
+  if (fork0 != nullptr && ctx->aux != nullptr) {
+    RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->aux, fork0, 0));
+    cudaStream_t chain = ctx->stream;
+    ctx->stream = ctx->aux;
+    int rc = RAU_OK;
+    if (encoder_fused(ctx, cfg, B)) {
+      rc = encoder_pack_weights(ctx, cfg, params[1]);
+      enc_w_ready = rau_side_event(ctx);
+      if (rc == RAU_OK && (enc_w_ready == nullptr || cudaEventRecord(enc_w_ready, ctx->aux) != cudaSuccess)) rc = RAU_ECUDA;
+    }
+    for (int g = 0; g < 3 && rc == RAU_OK; ++g) rc = k_fill(ctx, grads[g], rau_group_size(cfg, g), 0.0f);
+    ctx->stream = chain;
+    RAU_TRY(rc);
+  } else {
+    for (int g = 0; g < 3; ++g) RAU_TRY(k_fill(ctx, grads[g], rau_group_size(cfg, g), 0.0f));
+  }
   bool side_used = false;
   // Work the chain needs only LATER runs on an auxiliary stream next to it (forked here, joined by the returned event):
   // sized for `cap` SMs so that it does not crowd the chain's own launches.
@@ -630,6 +674,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   bool split_ok = (ov_fwd || ov_bwd) && ctx->aux != nullptr && ctx->aux2 != nullptr && nHop >= 2;
   Encoder en;
   RAU_TRY(encoder_alloc(ctx, cfg, B, &en));
+  en.w_ready = enc_w_ready;
   // The chain's first launches (masks + word embedding) go out before the side stream is released: the all-hops feature
   // pack saturates HBM for its first ~250 us and would stretch these latency-bound launches threefold.
   cudaEvent_t fork_side = fork0;

@@ -1,9 +1,6 @@
-python -m pytest tests/test_gpu_feed.py -x -q 2>&1 | tail -3
-python bench.py > gpurun_out/s3_bench_full.json 2> gpurun_out/s3_bench_full.err; echo "bench rc=$?"
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/s3_bench_full.json').read().strip().splitlines()[-1])
-print(d['ms_per_step'], d['value'], d['e2e'], d['clocks'], d['roofline']['frac'])
-for k,v in d['extra'].items():
-    if k!='sweep': print(k, {a:b for a,b in v.items() if a in ('value','ms_per_step','h2d_bytes_per_step','clocks')})
-PY
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+run() { echo "$* -> $(env "$@" python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-extra 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['ms_per_step'],3), round(d['e2e']['ms_per_step'],3))")"; }
+run RAU_X=1
+run RAU_X=2
+run RAU_X=3
+RAU_PHASES=2 python tools/phases.py ours_full > gpurun_out/s3_timeline4.txt 2>&1; tail -58 gpurun_out/s3_timeline4.txt | head -14
