@@ -99,7 +99,7 @@ __global__ void l2_evict_kernel(const float4* __restrict__ buf, int64_t n4, floa
 // ---------------------------------------------------------------- embedding
 __global__ void embed_fwd_kernel(const float* __restrict__ ids, int n, int D, int V, const float* __restrict__ E,
                                  const uint32_t* __restrict__ bits, float scale, float* __restrict__ out_f,
-                                 bf16* __restrict__ out_b, int ldb) {
+                                 bf16* __restrict__ out_b, int ldb, bf16* __restrict__ out_lo) {
   RAU_PDL_ENTRY();
   const int64_t total = (int64_t)n * D;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -108,7 +108,11 @@ __global__ void embed_fwd_kernel(const float* __restrict__ ids, int n, int D, in
     id = min(max(id, 0), V - 1);
     const float v = tanhf(E[(int64_t)id * D + d] * keep_scale(bits, i, scale));
     if (out_f) out_f[i] = v;
-    if (out_b) out_b[(int64_t)r * ldb + d] = __float2bfloat16(v);
+    if (out_b) {   // packed twin for the tcgen05 products: hi [, lo] (the layer-1 input projection reads it as stored)
+      const bf16 h = __float2bfloat16(v);
+      out_b[(int64_t)r * ldb + d] = h;
+      if (out_lo) out_lo[(int64_t)r * ldb + d] = __float2bfloat16(v - __bfloat162float(h));
+    }
   }
 }
 
@@ -316,7 +320,7 @@ __global__ void dropout_kernel(const float* __restrict__ x, int64_t rows, int co
 // nn.Dropout fused with the tcgen05 operand packing: y = x * keep * scale written only as bf16 (hi, lo) rows of
 // pitch cols_pad (zero padded).  Four columns per thread: 128-bit loads, 64-bit stores.
 __global__ void dropout_pack_kernel(const float* __restrict__ x, int64_t rows, int cols, const uint32_t* __restrict__ bits,
-                                    float scale, bf16* __restrict__ hi, bf16* __restrict__ lo, int cols_pad) {
+                                    float scale, bf16* __restrict__ hi, bf16* __restrict__ lo, int cols_pad, int64_t ldx) {
   RAU_PDL_ENTRY();
   const int q = cols_pad >> 2;
   const int64_t total = rows * q;
@@ -325,12 +329,12 @@ __global__ void dropout_pack_kernel(const float* __restrict__ x, int64_t rows, i
     const int c = (int)(i % q) * 4;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (c + 3 < cols) {
-      const float4 t = *reinterpret_cast<const float4*>(x + r * cols + c);
+      const float4 t = *reinterpret_cast<const float4*>(x + r * ldx + c);
       v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     } else {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (c + k < cols) v[k] = x[r * cols + c + k];
+        if (c + k < cols) v[k] = x[r * ldx + c + k];
     }
     __align__(8) bf16 h[4], l[4];
 #pragma unroll
@@ -585,8 +589,8 @@ int k_mask_pack(rau_ctx* ctx, uint32_t* bits, const uint8_t* bytes, int64_t n) {
   return RAU_OK;
 }
 int k_embed_fwd(rau_ctx* ctx, const float* ids, int n, int D, int V, const float* E, const uint32_t* bits, float scale,
-                float* out_f, bf16* out_b, int ldb) {
-  RAU_LAUNCH_PDL(ctx->stream, (embed_fwd_kernel), grid_for((int64_t)n * D), TPB, 0, ids, n, D, V, E, bits, scale, out_f, out_b, ldb);
+                float* out_f, bf16* out_b, int ldb, bf16* out_lo) {
+  RAU_LAUNCH_PDL(ctx->stream, (embed_fwd_kernel), grid_for((int64_t)n * D), TPB, 0, ids, n, D, V, E, bits, scale, out_f, out_b, ldb, out_lo);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }
@@ -631,12 +635,13 @@ int k_dropout(rau_ctx* ctx, const float* x, int64_t rows, int cols, int ldx, con
   return RAU_OK;
 }
 int k_dropout_pack(rau_ctx* ctx, const float* x, int64_t rows, int cols, const uint32_t* bits, float scale, bf16* hi, bf16* lo,
-                   int cols_pad) {
-  if (cols % 4 != 0 || cols_pad % 4 != 0 || ((uintptr_t)x & 15) != 0) {
-    rau_set_error("k_dropout_pack: cols=%d cols_pad=%d must be multiples of 4 and x 16-byte aligned", cols, cols_pad);
+                   int cols_pad, int64_t ldx) {
+  if (ldx <= 0) ldx = cols;
+  if (cols % 4 != 0 || cols_pad % 4 != 0 || ldx % 4 != 0 || ((uintptr_t)x & 15) != 0) {
+    rau_set_error("k_dropout_pack: cols=%d cols_pad=%d ldx=%lld must be multiples of 4 and x 16-byte aligned", cols, cols_pad, (long long)ldx);
     return RAU_EINVAL;
   }
-  RAU_LAUNCH_PDL(ctx->stream, (dropout_pack_kernel), grid_for(rows * (cols_pad / 4), 2), TPB, 0, x, rows, cols, bits, scale, hi, lo, cols_pad);
+  RAU_LAUNCH_PDL(ctx->stream, (dropout_pack_kernel), grid_for(rows * (cols_pad / 4), 2), TPB, 0, x, rows, cols, bits, scale, hi, lo, cols_pad, ldx);
   RAU_LAUNCH_CHECK(ctx);
   return RAU_OK;
 }

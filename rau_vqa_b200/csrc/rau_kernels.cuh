@@ -16,7 +16,7 @@ static inline int64_t mask_words(int64_t n) { return (n + 31) / 32 + 4; }
 
 // ---- word embedding (F:203-206)
 int k_embed_fwd(rau_ctx* ctx, const float* ids, int n, int D, int V, const float* E,
-                const uint32_t* bits, float scale, float* out_f, bf16* out_b, int ldb);
+                const uint32_t* bits, float scale, float* out_f, bf16* out_b, int ldb, bf16* out_lo = nullptr);   // out_b / out_lo: packed (hi, lo)
 int k_embed_bwd(rau_ctx* ctx, const float* ids, int n, int D, int V, const float* out,
                 const uint32_t* bits, float scale, const float* dout, int lddout, float* gE);
 
@@ -41,7 +41,7 @@ int k_dropout(rau_ctx* ctx, const float* x, int64_t rows, int cols, int ldx, con
               float* y_f, int ldyf, bf16* y_b, int ldyb, int cols_pad, bf16* y_lo = nullptr);   // y_b / y_lo: packed (hi, lo)
 // y = x*keep*scale written only as packed bf16 (hi, lo) rows of pitch cols_pad: a tcgen05 operand (cols % 4 == 0)
 int k_dropout_pack(rau_ctx* ctx, const float* x, int64_t rows, int cols, const uint32_t* bits, float scale, bf16* hi, bf16* lo,
-                   int cols_pad);
+                   int cols_pad, int64_t ldx = 0);   // ldx: row pitch of x (0 = cols)
 // y (+)= x*keep*scale  (used for dq accumulation over hops and dX)
 int k_dropout_bwd_acc(rau_ctx* ctx, const float* dx, int64_t n, const uint32_t* bits, float scale, float* y, int accumulate,
                       bf16* y_hi = nullptr, bf16* y_lo = nullptr);

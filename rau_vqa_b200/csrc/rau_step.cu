@@ -39,6 +39,7 @@ struct Encoder {
   float *e_all, *G1x, *G2x, *u2, *S_all, *sav1, *sav2, *Gt, *rnn_out;
   int proj0_done = 0;   // a part-1 call already formed layer 1's hoisted input projection
   cudaEvent_t w_ready = nullptr;   // the encoder's weight shadows were packed on the aux stream: wait before the first product
+  int h0_zeroed = 0;               // ... and the packed h_0 rows of both layers were cleared there
 };
 
 // the question encoder runs on the tcgen05 rows engine (hoisted input projections + persistent recurrence)
@@ -69,7 +70,7 @@ static int encoder_alloc(rau_ctx* ctx, const rau_config* cfg, int B, Encoder* en
 // launches that depend on the parameters only.  The training step issues them on the aux stream at its very start (they
 // are cached per public call, so the encoder's own calls below find them done) instead of on the chain in front of each
 // layer's products.
-static int encoder_pack_weights(rau_ctx* ctx, const rau_config* cfg, const float* Pr) {
+static int encoder_pack_weights(rau_ctx* ctx, const rau_config* cfg, const float* Pr, int B) {
   RnnLayerOff L[4];
   rnn_offsets(cfg, L);
   const bool x3 = prec_x3(ctx);
@@ -83,6 +84,11 @@ static int encoder_pack_weights(rau_ctx* ctx, const rau_config* cfg, const float
     RAU_TRY(rows_perm_lstm_bias(ctx, Pr + L[layer].bi, Pr + L[layer].bh, Hq, RAU_GATES_IFOG, &bperm));
     RAU_TRY(rows_pack_lstm(ctx, Pr + L[layer].Wh, Hq, Hq, RAU_GATES_IFOG, x3, &h, &l, &ld));
   }
+  // ... and the packed h_0 = 0 rows the two recurrences start from (Encoder::h0_zeroed)
+  const size_t hb = (size_t)B * Hq;
+  ARENA(hpk_all, bf16, "enc.hpk", (size_t)4 * (cfg->T + 1) * hb);   // [layer][hi, lo][T+1][B][Hq]
+  for (int k = 0; k < 4; ++k)
+    if (x3 || (k & 1) == 0) RAU_CHECK_CUDA(cudaMemsetAsync(hpk_all + (size_t)k * (cfg->T + 1) * hb, 0, hb * sizeof(bf16), ctx->stream));
   return RAU_OK;
 }
 
@@ -100,29 +106,45 @@ static int encoder_forward(rau_ctx* ctx, const rau_config* cfg, const rau_batch*
   rnn_offsets(cfg, L);
   const int rank = rau_comm_rank(ctx);
   const bool de = train && cfg->p_embed > 0, dr = train && cfg->p_rnn > 0;
+  const bool fused = encoder_fused(ctx, cfg, B);
+  // tcgen05 path: the packed (hi, lo) inputs of the two hoisted projections -- e for layer 1, u2 = drop(h1) for layer 2 -- are
+  // written by their producers (the embedding lookup, the dropout) into the buffers the backward pass's weight gradients
+  // read ("rp.enc.x0" / "rp.enc.x1"), not by a pack launch in front of each projection
+  auto x_buf = [&](int layer, bf16** x_h, bf16** x_l, int64_t* ldx) -> int {
+    const int in = layer == 0 ? E : Hq;
+    *ldx = (in + 7) / 8 * 8;
+    const size_t half = ((size_t)Tm * B * (size_t)*ldx * sizeof(bf16) + 1023) / 1024 * 1024;
+    char* buf = nullptr;
+    RAU_TRY(ctx->arena.get(layer == 0 ? "rp.enc.x0" : "rp.enc.x1", half * (prec_x3(ctx) ? 2 : 1), (void**)&buf));
+    *x_h = (bf16*)buf;
+    *x_l = prec_x3(ctx) ? (bf16*)(buf + half) : nullptr;
+    return RAU_OK;
+  };
   if (part != 2) {
     RAU_TRY(rau_prepare_mask(ctx, en->ebits, (int64_t)Tm * B * E, cfg->p_embed, train, masks ? masks->embed : nullptr,
                              stream_of(step_t, SK_EMBED, 0, rank)));
     RAU_TRY(rau_prepare_mask(ctx, en->rbits, (int64_t)Tm * B * Hq, cfg->p_rnn, train, masks ? masks->rnn : nullptr,
                              stream_of(step_t, SK_RNN, 0, rank)));
     // word_embed for every step at once (F:203-206, F:468)
+    bf16 *e_h = nullptr, *e_l = nullptr;
+    int64_t lde = 0;
+    if (fused) RAU_TRY(x_buf(0, &e_h, &e_l, &lde));
     RAU_TRY(k_embed_fwd(ctx, bt->tokens, Tm * B, E, cfg->V, Pe, de ? en->ebits : nullptr, drop_scale(cfg->p_embed),
-                        en->e_all, nullptr, 0));
+                        en->e_all, e_h, (int)lde, e_l));
     if (ctx->phases == 2) rau_phase_mark(ctx, "enc embed done");
   }
-  const bool fused = encoder_fused(ctx, cfg, B);
   if (fused && en->w_ready != nullptr && part != 2) RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, en->w_ready, 0));
   // hoisted input projection of one layer for every step at once, columns in the permuted gate order (tcgen05 path)
   auto input_projection = [&](int layer) -> int {
     const bool x3 = prec_x3(ctx);
     const int in = layer == 0 ? E : Hq;
-    const bf16 *Wi_h, *Wi_l, *x_h, *x_l;
+    const bf16 *Wi_h, *Wi_l;
+    bf16 *x_h, *x_l;
     int64_t ldwi, ldx;
     const float* bperm;
     RAU_TRY(rows_pack_lstm(ctx, Pr + L[layer].Wi, Hq, in, RAU_GATES_IFOG, x3, &Wi_h, &Wi_l, &ldwi));
     RAU_TRY(rows_perm_lstm_bias(ctx, Pr + L[layer].bi, Pr + L[layer].bh, Hq, RAU_GATES_IFOG, &bperm));
-    RAU_TRY(rows_pack2d(ctx, layer == 0 ? en->e_all : en->u2, in, Tm * B, in, x3, false, layer == 0 ? "enc.x0" : "enc.x1", &x_h,
-                        &x_l, &ldx));
+    RAU_TRY(x_buf(layer, &x_h, &x_l, &ldx));   // (written by k_embed_fwd / k_dropout_pack)
     RowsGemm g;
     g.M = Tm * B; g.N = G4; g.K = in;
     g.A.hi = x_h; g.A.lo = x_l; g.A.ld = ldx;
@@ -163,12 +185,18 @@ static int encoder_forward(rau_ctx* ctx, const rau_config* cfg, const rau_batch*
       int64_t ldwh;
       RAU_TRY(rows_pack_lstm(ctx, Pr + L[layer].Wh, Hq, Hq, RAU_GATES_IFOG, x3, &Wh_h, &Wh_l, &ldwh));
       float* Gx = layer == 0 ? en->G1x : en->G2x;
-      if (layer == 1)   // u2 = drop(h1) for every step (D:38-39)
-        RAU_TRY(k_dropout(ctx, en->S_all + (size_t)B * Q + Hq, (int64_t)Tm * B, Hq, Q, dr ? en->rbits : nullptr,
-                          drop_scale(cfg->p_rnn), en->u2, Hq, nullptr, 0, Hq));
+      if (layer == 1) {   // u2 = drop(h1) for every step (D:38-39), straight into the packed operand of the projection
+        bf16 *u_h, *u_l;
+        int64_t ldu;
+        RAU_TRY(x_buf(1, &u_h, &u_l, &ldu));
+        RAU_TRY(k_dropout_pack(ctx, en->S_all + (size_t)B * Q + Hq, (int64_t)Tm * B, Hq, dr ? en->rbits : nullptr,
+                               drop_scale(cfg->p_rnn), u_h, u_l, (int)ldu, Q));
+      }
       if (!(layer == 0 && en->proj0_done)) RAU_TRY(input_projection(layer));
-      RAU_CHECK_CUDA(cudaMemsetAsync(hpk_hi, 0, hb * sizeof(bf16), ctx->stream));
-      if (x3) RAU_CHECK_CUDA(cudaMemsetAsync(hpk_lo, 0, hb * sizeof(bf16), ctx->stream));
+      if (!en->h0_zeroed) {
+        RAU_CHECK_CUDA(cudaMemsetAsync(hpk_hi, 0, hb * sizeof(bf16), ctx->stream));
+        if (x3) RAU_CHECK_CUDA(cudaMemsetAsync(hpk_lo, 0, hb * sizeof(bf16), ctx->stream));
+      }
       if (ctx->phases == 2) rau_phase_mark(ctx, "enc layer input projection done");
       int seq_done = 0;
       {   // the whole recurrence in one persistent launch when the layer fits (weights resident in shared memory)
@@ -639,7 +667,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     ctx->stream = ctx->aux;
     int rc = RAU_OK;
     if (encoder_fused(ctx, cfg, B)) {
-      rc = encoder_pack_weights(ctx, cfg, params[1]);
+      rc = encoder_pack_weights(ctx, cfg, params[1], B);
       enc_w_ready = rau_side_event(ctx);
       if (rc == RAU_OK && (enc_w_ready == nullptr || cudaEventRecord(enc_w_ready, ctx->aux) != cudaSuccess)) rc = RAU_ECUDA;
     }
@@ -675,6 +703,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   Encoder en;
   RAU_TRY(encoder_alloc(ctx, cfg, B, &en));
   en.w_ready = enc_w_ready;
+  en.h0_zeroed = enc_w_ready != nullptr ? 1 : 0;
   // The chain's first launches (masks + word embedding) go out before the side stream is released: the all-hops feature
   // pack saturates HBM for its first ~250 us and would stretch these latency-bound launches threefold.
   cudaEvent_t fork_side = fork0;

@@ -3,4 +3,4 @@ run() { echo "$* -> $(env "$@" python bench.py --steps 30 --warmup 3 --no-cpu-ba
 run RAU_X=1
 run RAU_X=2
 run RAU_X=3
-RAU_PHASES=2 python tools/phases.py ours_full > gpurun_out/s3_timeline4.txt 2>&1; tail -58 gpurun_out/s3_timeline4.txt | head -14
+RAU_PHASES=2 python tools/phases.py ours_full > gpurun_out/s3_timeline5.txt 2>&1; tail -58 gpurun_out/s3_timeline5.txt | head -14
