@@ -939,7 +939,12 @@ int rau_rows_gemm_time(rau_ctx* ctx, int M, int N, int K, int a_mn, int b_mn, in
   g.out_f = D; g.ldo = (N + 3) / 4 * 4;
   // reduce = 2 / 3: the hop backward's dY epilogue (with / without the bias-gradient column sums), 4: the tanh epilogue;
   // RAU_TIME_CAP limits the CTAs like the side stream's cap does
-  if (reduce >= 2) {
+  if (reduce == 5) {   // the nn.Linear epilogue with a bias (the encoder's hoisted input projections)
+    float* cs = nullptr;
+    RAU_TRY(ctx->arena.get("gt.cs", sizeof(float) * (size_t)N, (void**)&cs));
+    RAU_TRY(k_fill(ctx, cs, N, 0.0f));
+    g.epi = ROWS_EPI_LINEAR; g.bias = cs;
+  } else if (reduce >= 2) {
     RAU_REQUIRE(N % 32 == 0 && M % 196 == 0, "rau_rows_gemm_time: epilogue variants need N %% 32 == 0 and M %% 196 == 0");
     bf16 *aux = nullptr, *outp = nullptr;
     float *rv = nullptr, *rs = nullptr, *cs = nullptr;
