@@ -550,6 +550,14 @@ def main():
                     peak_source=pk["src"] + " bf16 burst (kernel timed alone, 20 back-to-back launches, CUDA events)",
                     ms_per_launch=ms_k, flop_per_launch=flops, algorithmic="2*196*B*M*C flop per launch (SURVEY 8d)",
                     mma_passes=executed, executed_frac=executed * ach / pk["tensor_burst"])
+        # the same launch against the kernel's OTHER roof: packed features in (one fp16 plane in the mixed modes, bf16 hi / hi+lo
+        # otherwise) + I out (fp16 / bf16 hi / hi+lo) per launch over the measured copy bandwidth.  In the default mode the
+        # arithmetic intensity (171 flop/B) is below the ridge of the two measured peaks (253 flop/B): HBM caps `frac` at ~0.67.
+        xb_ = 2 if prec in ("mixed", "f16img", "bf16") else 4
+        ib_ = 2 if prec in ("f16img", "bf16") else 4
+        hbm_bytes = 196.0 * B * (cfg.C * xb_ + cfg.M * ib_)
+        roof["hbm"] = dict(bytes_per_launch=hbm_bytes, achieved_gbs=hbm_bytes / (ms_k * 1e-3) / 1e9, peak_gbs=pk["hbm"],
+                           frac=hbm_bytes / (ms_k * 1e-3) / 1e9 / pk["hbm"])
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu, _ = cpu_baseline_dict(args.workload, 2, 1, args.cpu_sample)
