@@ -135,6 +135,10 @@ struct rau_ctx {
   // clip + optimizer) is issued there on the aux stream (train step only)
   std::function<int()> early_tail;          // set by the train step: [all-reduce,] noise + norm, clip + optimizer of group 2
   cudaEvent_t early_tail_done = nullptr;    // recorded on the aux stream behind it (NULL: it did not run)
+  // the word-embedding group is final when the chain has run the encoder backward, before it waits for the side stream's
+  // weight gradients: its [all-reduce,] noise + norm, clip + optimizer go out on the chain in that gap
+  std::function<int()> early_tail0;
+  bool early_tail0_ran = false;
   int main_cta_cap = 0;                            // > 0 while the side stream is in use: SMs the chain's split-K products size for
   int rows_cta_cap = 0;                            // > 0 while work is being enqueued on the side stream
   // RAU_PHASES=1: eager steps with an event at every phase boundary; rau_phase_report() prints the split

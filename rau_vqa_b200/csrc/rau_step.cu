@@ -1104,6 +1104,11 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   RAU_TRY(encoder_backward(ctx, cfg, bt, params[1], grads[0], grads[1], train, &en, dq, ov_bwd));
   if (ov_bwd) side_used = true;
   if (ctx->phases == 2) rau_phase_mark(ctx, "encoder backward chain done");
+  if (ctx->early_tail0 && side_used) {   // the embedding gradient is final (k_embed_bwd was the chain's last launch)
+    RAU_TRY(ctx->early_tail0());
+    ctx->early_tail0_ran = true;
+    if (ctx->phases == 2) rau_phase_mark(ctx, "embed group done");
+  }
   if (side_used) {   // join: the side stream's gradients (gWi, gWa, gbi) are complete before anything downstream
     cudaEvent_t join = rau_side_event(ctx);
     RAU_REQUIRE(join != nullptr, "cudaEventCreate failed");
@@ -1220,19 +1225,29 @@ static int train_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
       if (dp) RAU_TRY(rau_allreduce_internal(ctx, grads[2], rau_group_size(cfg, 2)));
       return finish_group(2);
     };
+  ctx->early_tail0_ran = false;
+  ctx->early_tail0 = [&]() -> int {   // (called by feval_enqueue on the chain between the encoder backward and the join)
+      if (dp) RAU_TRY(rau_allreduce_internal(ctx, grads[0], rau_group_size(cfg, 0)));
+      return finish_group(0);
+    };
   const int rc_f = feval_enqueue(ctx, cfg, bt, params, grads, hop_mask, masks, out);
   ctx->early_tail = nullptr;
+  ctx->early_tail0 = nullptr;
   RAU_TRY(rc_f);
   cudaEvent_t early = ctx->early_tail_done;
   ctx->early_tail_done = nullptr;
+  const bool todo[3] = {!ctx->early_tail0_ran, true, early == nullptr};   // groups whose tail has not gone out yet
+  ctx->early_tail0_ran = false;
   if (dp) {   // data parallel: one sum over ranks of each flat gradient, the remaining ones as one launch
     RAU_TRY(rau_allreduce_group(ctx, 1));
-    for (int g = 0; g < (early ? 2 : 3); ++g) RAU_TRY(rau_allreduce_internal(ctx, grads[g], rau_group_size(cfg, g)));
+    for (int g = 0; g < 3; ++g)
+      if (todo[g]) RAU_TRY(rau_allreduce_internal(ctx, grads[g], rau_group_size(cfg, g)));
     if (out && out->loss) RAU_TRY(rau_allreduce_internal(ctx, out->loss, cfg->nHop + 2));
     if (out && out->loss_do_pred) RAU_TRY(rau_allreduce_internal(ctx, out->loss_do_pred, cfg->nHop));
     RAU_TRY(rau_allreduce_group(ctx, 0));
   }
-  for (int g = 0; g < (early ? 2 : 3); ++g) RAU_TRY(finish_group(g));
+  for (int g = 0; g < 3; ++g)
+    if (todo[g]) RAU_TRY(finish_group(g));
   if (early) RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, early, 0));
   rau_phase_mark(ctx, "noise + clip + optimizer");
   return RAU_OK;
