@@ -1525,6 +1525,7 @@ struct LsParams {
   unsigned int* err;                            // sticky failure word (device: the optimizer kernel reads it)
   unsigned int* err_host;                       // the same, host-mapped: checked at every public entry point
   int fence_all;                                // every epilogue thread fences before the publish barrier (A/B)
+  const float* lengths; float* sel_c; float* sel_h; int sel_ld;   // optional length selection (LstmSeq)
 };
 constexpr int LS_THREADS = 320;   // TMA producer, MMA issuer, 8 epilogue warps
 
@@ -1667,6 +1668,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
     float cs[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) cs[u] = 0.0f;
+    const int len_r = p.lengths ? (int)p.lengths[rr] : 0;   // (0: never selected)
     for (int t = 1; t <= p.T; ++t) {
       float gx[32];   // the input half of this step's gates does not depend on the recurrence: fetch before waiting
       const float* gsrc = p.Gx + (long long)(t - 1) * p.gx_t + (long long)rr * p.ldg + nc;
@@ -1718,6 +1720,10 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
         st_global_v8(sbase + 2 * p.plane, go);
         st_global_v8(sbase + 3 * p.plane, gg);
         st_global_v8(sbase + 4 * p.plane, tc);
+        if (t == len_r) {   // the question ends here: this row's encoder output (F:472-478)
+          st_global_v8(p.sel_c + (long long)r * p.sel_ld + u0, cs);
+          st_global_v8(p.sel_h + (long long)r * p.sel_ld + u0, hn);
+        }
       }
     }
   }
@@ -2107,11 +2113,18 @@ int rows_lstm_seq(rau_ctx* ctx, const LstmSeq& d, int* done) {
   p.c_out = d.c_out; p.h_out = d.h_out; p.s_t = d.s_t; p.lds = d.lds;
   p.lsaved = d.lsaved; p.ls_t = d.ls_t; p.plane = d.plane;
   p.hpk_hi = d.hpk_hi; p.hpk_lo = d.hpk_lo; p.hp_t = (long long)B * H;
-  unsigned int* cnt = nullptr;
-  RAU_TRY(ctx->arena.get("lstmseq.cnt", sizeof(unsigned int) * 64, (void**)&cnt));
+  unsigned int* cnt = d.counter;
   RAU_REQUIRE(tiles_m <= 64, "rows_lstm_seq: %d row tiles", tiles_m);
-  RAU_CHECK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * 64, ctx->stream));
+  if (cnt == nullptr) {
+    RAU_TRY(ctx->arena.get("lstmseq.cnt", sizeof(unsigned int) * 64, (void**)&cnt));
+    RAU_CHECK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * 64, ctx->stream));
+  }
   p.counter = cnt; p.err = ctx->d_err; p.err_host = ctx->h_err_dev;
+  if (d.lengths && d.sel_c && d.sel_h && d.sel_ld % 8 == 0 && ((((uintptr_t)d.sel_c | (uintptr_t)d.sel_h) & 31) == 0)) {
+    p.lengths = d.lengths; p.sel_c = d.sel_c; p.sel_h = d.sel_h; p.sel_ld = d.sel_ld;
+  } else if (d.lengths) {
+    return RAU_OK;   // (the caller asked for the fused selection and the layout does not allow it: per-step launches + select)
+  }
   p.fence_all = 1;
   const int smem_bytes = w_bytes + stages * a_stage + 1024;
   static bool attr_done[2] = {false, false};

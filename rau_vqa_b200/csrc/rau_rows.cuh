@@ -79,6 +79,10 @@ struct LstmSeq {
   float* c_out = nullptr; float* h_out = nullptr; int64_t s_t = 0; int lds = 0;   // state rows of step 1, step stride, pitch
   float* lsaved = nullptr; int64_t ls_t = 0, plane = 0;                         // saved gates of step 1
   bf16* hpk_hi = nullptr; bf16* hpk_lo = nullptr;                               // packed h stack [(T+1)][B][H], step 0 = zeros
+  // optional: the state of step t == lengths[b] also goes to sel_c / sel_h [B, H] (row pitch sel_ld): the encoder's
+  // length selection (F:472-478) without a launch of its own.  Rows whose length is outside 1..T are left untouched.
+  const float* lengths = nullptr; float* sel_c = nullptr; float* sel_h = nullptr; int sel_ld = 0;
+  unsigned int* counter = nullptr;   // optional: 64 zeroed words for the row tiles' step counters (else cleared here)
 };
 int rows_lstm_seq(rau_ctx* ctx, const LstmSeq& d, int* done);
 

@@ -40,6 +40,9 @@ struct Encoder {
   int proj0_done = 0;   // a part-1 call already formed layer 1's hoisted input projection
   cudaEvent_t w_ready = nullptr;   // the encoder's weight shadows were packed on the aux stream: wait before the first product
   int h0_zeroed = 0;               // ... and the packed h_0 rows of both layers were cleared there
+  int rbits_done = 0;              // ... and the recurrent dropout mask was prepared there
+  unsigned int* seq_cnt = nullptr; // ... and 2 x 64 zeroed step counters for the persistent recurrences, with rnn_out cleared:
+                                   //     the recurrence kernels write the length-selected rows themselves (no select launch)
 };
 
 // the question encoder runs on the tcgen05 rows engine (hoisted input projections + persistent recurrence)
@@ -123,8 +126,9 @@ static int encoder_forward(rau_ctx* ctx, const rau_config* cfg, const rau_batch*
   if (part != 2) {
     RAU_TRY(rau_prepare_mask(ctx, en->ebits, (int64_t)Tm * B * E, cfg->p_embed, train, masks ? masks->embed : nullptr,
                              stream_of(step_t, SK_EMBED, 0, rank)));
-    RAU_TRY(rau_prepare_mask(ctx, en->rbits, (int64_t)Tm * B * Hq, cfg->p_rnn, train, masks ? masks->rnn : nullptr,
-                             stream_of(step_t, SK_RNN, 0, rank)));
+    if (!en->rbits_done)
+      RAU_TRY(rau_prepare_mask(ctx, en->rbits, (int64_t)Tm * B * Hq, cfg->p_rnn, train, masks ? masks->rnn : nullptr,
+                               stream_of(step_t, SK_RNN, 0, rank)));
     // word_embed for every step at once (F:203-206, F:468)
     bf16 *e_h = nullptr, *e_l = nullptr;
     int64_t lde = 0;
@@ -178,6 +182,7 @@ static int encoder_forward(rau_ctx* ctx, const rau_config* cfg, const rau_batch*
     const bool x3 = prec_x3(ctx);
     const size_t hb = (size_t)B * Hq;
     ARENA(hpk_all, bf16, "enc.hpk", (size_t)4 * (cfg->T + 1) * hb);   // [layer][hi, lo][T+1][B][Hq], kept for the backward pass
+    bool sel_fused = true;
     for (int layer = 0; layer < 2; ++layer) {
       bf16* hpk_hi = hpk_all + (size_t)(2 * layer) * (cfg->T + 1) * hb;
       bf16* hpk_lo = hpk_hi + (size_t)(cfg->T + 1) * hb;
@@ -202,6 +207,10 @@ static int encoder_forward(rau_ctx* ctx, const rau_config* cfg, const rau_batch*
       {   // the whole recurrence in one persistent launch when the layer fits (weights resident in shared memory)
         LstmSeq d;
         d.B = B; d.H = Hq; d.T = Tm;
+        if (en->seq_cnt) {   // fused length selection into rnn_out [B, Q] = [c1 | h1 | c2 | h2] (cleared on the aux stream)
+          d.counter = en->seq_cnt + 64 * layer;
+          d.lengths = bt->lengths; d.sel_c = en->rnn_out + 2 * layer * Hq; d.sel_h = d.sel_c + Hq; d.sel_ld = Q;
+        }
         d.Wh_hi = Wh_h; d.Wh_lo = Wh_l; d.ldwh = ldwh;
         d.Gx = Gx; d.gx_t = (int64_t)B * G4; d.ldg = G4;
         d.c_out = en->S_all + (size_t)B * Q + 2 * layer * Hq; d.h_out = d.c_out + Hq; d.s_t = (int64_t)B * Q; d.lds = Q;
@@ -209,6 +218,7 @@ static int encoder_forward(rau_ctx* ctx, const rau_config* cfg, const rau_batch*
         d.hpk_hi = hpk_hi; d.hpk_lo = x3 ? hpk_lo : nullptr;
         RAU_TRY(rows_lstm_seq(ctx, d, &seq_done));
         if (ctx->phases == 2) rau_phase_mark(ctx, "enc layer recurrence done");
+        if (!(seq_done && d.lengths)) sel_fused = false;
       }
       for (int t = 1; t <= Tm && !seq_done; ++t) {
         float* Sp_ = en->S_all + (size_t)(t - 1) * B * Q + 2 * layer * Hq;
@@ -225,7 +235,7 @@ static int encoder_forward(rau_ctx* ctx, const rau_config* cfg, const rau_batch*
         RAU_TRY(rows_gemm(ctx, g));
       }
     }
-    RAU_TRY(k_select_state(ctx, en->S_all, Tm, B, Q, bt->lengths, en->rnn_out));
+    if (!sel_fused) RAU_TRY(k_select_state(ctx, en->S_all, Tm, B, Q, bt->lengths, en->rnn_out));
     return RAU_OK;
   }
   for (int t = 1; t <= Tm; ++t) {   // layer 1 recurrence
@@ -661,6 +671,8 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   // otherwise runs in front of its layers' products) and the zero fill of the three gradient vectors (F:446-448; nothing
   // accumulates into them before the backward pass, which is ordered behind the aux stream's join after the encoder).
   cudaEvent_t enc_w_ready = nullptr;
+  Encoder en;
+  RAU_TRY(encoder_alloc(ctx, cfg, B, &en));
   if (fork0 != nullptr && ctx->aux != nullptr) {
     RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->aux, fork0, 0));
     cudaStream_t chain = ctx->stream;
@@ -668,6 +680,18 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     int rc = RAU_OK;
     if (encoder_fused(ctx, cfg, B)) {
       rc = encoder_pack_weights(ctx, cfg, params[1], B);
+      // the recurrent dropout mask (first read by layer 2's dropout), the cleared encoder output and the persistent
+      // recurrences' step counters: three more small launches the chain does not have to carry
+      const int Tm0 = (bt->max_len > 0 && bt->max_len <= cfg->T) ? bt->max_len : cfg->T;
+      if (rc == RAU_OK)
+        rc = rau_prepare_mask(ctx, en.rbits, (int64_t)Tm0 * B * cfg->Hq, cfg->p_rnn, train, masks ? masks->rnn : nullptr,
+                              stream_of(step_t, SK_RNN, 0, rank));
+      unsigned int* cnt = nullptr;
+      if (rc == RAU_OK) rc = ctx->arena.get("enc.seqcnt", sizeof(unsigned int) * 128, (void**)&cnt);
+      if (rc == RAU_OK && (cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * 128, ctx->aux) != cudaSuccess ||
+                           cudaMemsetAsync(en.rnn_out, 0, sizeof(float) * (size_t)B * 4 * cfg->Hq, ctx->aux) != cudaSuccess))
+        rc = RAU_ECUDA;
+      if (rc == RAU_OK) { en.rbits_done = 1; en.seq_cnt = cnt; }
       enc_w_ready = rau_side_event(ctx);
       if (rc == RAU_OK && (enc_w_ready == nullptr || cudaEventRecord(enc_w_ready, ctx->aux) != cudaSuccess)) rc = RAU_ECUDA;
     }
@@ -700,8 +724,6 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   // (only when every operand of the moved products has a producer-written packed twin and a pre-packed weight shadow: a
   // product that packs an operand on demand does so into a scratch slot shared by all streams)
   bool split_ok = (ov_fwd || ov_bwd) && ctx->aux != nullptr && ctx->aux2 != nullptr && nHop >= 2;
-  Encoder en;
-  RAU_TRY(encoder_alloc(ctx, cfg, B, &en));
   en.w_ready = enc_w_ready;
   en.h0_zeroed = enc_w_ready != nullptr ? 1 : 0;
   // The chain's first launches (masks + word embedding) go out before the side stream is released: the all-hops feature
