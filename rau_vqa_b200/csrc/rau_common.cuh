@@ -59,6 +59,7 @@ struct RauTuning {
   int rows = 1;           // RAU_ROWS=0: route products to the first-cut tcgen05 engine
   int cg2 = 1;            // RAU_CG2=0: no CTA pairs
   int lin_cg2 = 1;        // RAU_LIN_CG2=0: the big-M nn.Linear products (encoder projections) stay on single CTAs
+  int enc_w0 = 1;         // RAU_ENC_W0=0: layer 1's input projection waits for ALL of the aux stream's encoder preparation
   int tanh_ew = 16;       // RAU_TANH_EW=8: eight epilogue warps for the 1-pass i_embed product
   int rows_trace = 0;     // RAU_ROWS_TRACE=1: per-CTA clock stamps of rows-engine launches (tools/rows_trace.py)
   int lstm_seq = 1;       // RAU_LSTM_SEQ=0: one launch per recurrent step of the encoder instead of the persistent kernel

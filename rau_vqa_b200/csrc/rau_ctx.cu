@@ -58,6 +58,7 @@ RauTuning rau_tuning_from_env() {
   t.cg2 = geti("RAU_CG2", t.cg2);
   t.tanh_ew = geti("RAU_TANH_EW", t.tanh_ew) == 8 ? 8 : 16;
   t.lin_cg2 = geti("RAU_LIN_CG2", t.lin_cg2);
+  t.enc_w0 = geti("RAU_ENC_W0", t.enc_w0);
   t.rows_trace = geti("RAU_ROWS_TRACE", 0);
   t.lstm_seq = geti("RAU_LSTM_SEQ", t.lstm_seq);
   t.enc_bwd_wave = geti("RAU_ENC_BWD_WAVE", t.enc_bwd_wave);

@@ -39,6 +39,7 @@ struct Encoder {
   float *e_all, *G1x, *G2x, *u2, *S_all, *sav1, *sav2, *Gt, *rnn_out;
   int proj0_done = 0;   // a part-1 call already formed layer 1's hoisted input projection
   cudaEvent_t w_ready = nullptr;   // the encoder's weight shadows were packed on the aux stream: wait before the first product
+  cudaEvent_t w_ready0 = nullptr;  // ... the part of them layer 1's input projection needs (recorded first)
   int h0_zeroed = 0;               // ... and the packed h_0 rows of both layers were cleared there
   int rbits_done = 0;              // ... and the recurrent dropout mask was prepared there
   unsigned int* seq_cnt = nullptr; // ... and 2 x 64 zeroed step counters for the persistent recurrences, with rnn_out cleared:
@@ -73,7 +74,8 @@ static int encoder_alloc(rau_ctx* ctx, const rau_config* cfg, int B, Encoder* en
 // launches that depend on the parameters only.  The training step issues them on the aux stream at its very start (they
 // are cached per public call, so the encoder's own calls below find them done) instead of on the chain in front of each
 // layer's products.
-static int encoder_pack_weights(rau_ctx* ctx, const rau_config* cfg, const float* Pr, int B) {
+// first != 0: only what layer 1's hoisted input projection needs (its Wi shadow and bias sum); first == 0: everything else
+static int encoder_pack_weights(rau_ctx* ctx, const rau_config* cfg, const float* Pr, int B, int first) {
   RnnLayerOff L[4];
   rnn_offsets(cfg, L);
   const bool x3 = prec_x3(ctx);
@@ -83,8 +85,11 @@ static int encoder_pack_weights(rau_ctx* ctx, const rau_config* cfg, const float
     const bf16 *h, *l;
     int64_t ld;
     const float* bperm;
-    RAU_TRY(rows_pack_lstm(ctx, Pr + L[layer].Wi, Hq, in, RAU_GATES_IFOG, x3, &h, &l, &ld));
-    RAU_TRY(rows_perm_lstm_bias(ctx, Pr + L[layer].bi, Pr + L[layer].bh, Hq, RAU_GATES_IFOG, &bperm));
+    if (first || layer == 1) {   // (cached per public call: the second pass does not repeat layer 1's)
+      RAU_TRY(rows_pack_lstm(ctx, Pr + L[layer].Wi, Hq, in, RAU_GATES_IFOG, x3, &h, &l, &ld));
+      RAU_TRY(rows_perm_lstm_bias(ctx, Pr + L[layer].bi, Pr + L[layer].bh, Hq, RAU_GATES_IFOG, &bperm));
+    }
+    if (first) return RAU_OK;
     RAU_TRY(rows_pack_lstm(ctx, Pr + L[layer].Wh, Hq, Hq, RAU_GATES_IFOG, x3, &h, &l, &ld));
   }
   // ... and the packed h_0 = 0 rows the two recurrences start from (Encoder::h0_zeroed)
@@ -137,7 +142,9 @@ static int encoder_forward(rau_ctx* ctx, const rau_config* cfg, const rau_batch*
                         en->e_all, e_h, (int)lde, e_l));
     if (ctx->phases == 2) rau_phase_mark(ctx, "enc embed done");
   }
-  if (fused && en->w_ready != nullptr && part != 2) RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, en->w_ready, 0));
+  if (fused && en->w_ready0 != nullptr && part != 2)
+    RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->tune.enc_w0 ? en->w_ready0 : en->w_ready, 0));
+  if (fused && en->w_ready != nullptr && part != 1) RAU_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, en->w_ready, 0));
   // hoisted input projection of one layer for every step at once, columns in the permuted gate order (tcgen05 path)
   auto input_projection = [&](int layer) -> int {
     const bool x3 = prec_x3(ctx);
@@ -679,7 +686,10 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
     ctx->stream = ctx->aux;
     int rc = RAU_OK;
     if (encoder_fused(ctx, cfg, B)) {
-      rc = encoder_pack_weights(ctx, cfg, params[1], B);
+      rc = encoder_pack_weights(ctx, cfg, params[1], B, 1);
+      en.w_ready0 = rau_side_event(ctx);
+      if (rc == RAU_OK && (en.w_ready0 == nullptr || cudaEventRecord(en.w_ready0, ctx->aux) != cudaSuccess)) rc = RAU_ECUDA;
+      if (rc == RAU_OK) rc = encoder_pack_weights(ctx, cfg, params[1], B, 0);
       // the recurrent dropout mask (first read by layer 2's dropout), the cleared encoder output and the persistent
       // recurrences' step counters: three more small launches the chain does not have to carry
       const int Tm0 = (bt->max_len > 0 && bt->max_len <= cfg->T) ? bt->max_len : cfg->T;
