@@ -678,6 +678,7 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
   // otherwise runs in front of its layers' products) and the zero fill of the three gradient vectors (F:446-448; nothing
   // accumulates into them before the backward pass, which is ordered behind the aux stream's join after the encoder).
   cudaEvent_t enc_w_ready = nullptr;
+  bool grads_fill_on_aux = false;
   Encoder en;
   RAU_TRY(encoder_alloc(ctx, cfg, B, &en));
   if (fork0 != nullptr && ctx->aux != nullptr) {
@@ -705,9 +706,10 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
       enc_w_ready = rau_side_event(ctx);
       if (rc == RAU_OK && (enc_w_ready == nullptr || cudaEventRecord(enc_w_ready, ctx->aux) != cudaSuccess)) rc = RAU_ECUDA;
     }
-    for (int g = 0; g < 3 && rc == RAU_OK; ++g) rc = k_fill(ctx, grads[g], rau_group_size(cfg, g), 0.0f);
     ctx->stream = chain;
     RAU_TRY(rc);
+    grads_fill_on_aux = true;   // (at the END of the aux stream's preparation below: the fills' thousands of blocks, on the
+                                //  higher-priority stream, kept layer 1's input projection off the SMs for ~20 us)
   } else {
     for (int g = 0; g < 3; ++g) RAU_TRY(k_fill(ctx, grads[g], rau_group_size(cfg, g), 0.0f));
   }
@@ -893,6 +895,9 @@ static int feval_enqueue(rau_ctx* ctx, const rau_config* cfg, const rau_batch* b
       }
   }
   cudaEvent_t prep_done = nullptr;
+  if (grads_fill_on_aux) {   // (prep_aux holds whenever this does: ctx->stream is the aux stream here)
+    for (int g = 0; g < 3; ++g) RAU_TRY(k_fill(ctx, grads[g], rau_group_size(cfg, g), 0.0f));
+  }
   if (prep_aux) {
     prep_done = rau_side_event(ctx);
     RAU_REQUIRE(prep_done != nullptr, "cudaEventCreate failed");
