@@ -80,3 +80,18 @@ def test_header_is_ffi_parseable_without_preprocessor():
     from rau_vqa_b200 import _ffi
     text = _ffi.header_cdef()
     assert "#" not in text and "extern" not in text
+
+
+def test_batch_struct_layout_and_feed_formats(lib):
+    """rau_batch grew a trailing `feats_f16` pointer (fp16 features read directly by the feature pack): the fields every
+    existing caller fills keep their offsets, a zero-filled struct means "float32 features only", and the feed formats
+    keep their numbers (they cross the ABI as plain ints)."""
+    from rau_vqa_b200._ffi import ffi
+    b = ffi.new("rau_batch*")
+    assert b.feats == ffi.NULL and b.feats_f16 == ffi.NULL and b.B == 0 and b.max_len == 0
+    off = {f: ffi.offsetof("rau_batch", f) for f in ("B", "B_global", "feats", "tokens", "lengths", "max_len", "labels", "feats_f16")}
+    assert [off[f] for f in ("B", "B_global", "feats", "tokens", "lengths", "max_len", "labels")] == [0, 4, 8, 16, 24, 32, 40]
+    assert off["feats_f16"] == 48 and ffi.sizeof("rau_batch") == 56
+    assert (lib.RAU_FEED_F32, lib.RAU_FEED_F16, lib.RAU_FEED_F16_DIRECT) == (0, 1, 2)
+    from rau_vqa_b200 import feed as F
+    assert (F.FEED_F32, F.FEED_F16, F.FEED_F16_DIRECT) == (0, 1, 2)
